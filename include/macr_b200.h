@@ -1,0 +1,283 @@
+/*
+ * macr_b200.h -- C ABI of libmacr_b200.so, the B200 (sm_100a) implementation of
+ * MACR's training / scoring hot path.
+ *
+ * Conventions (all entry points):
+ *   - every array pointer is a DEVICE pointer owned by the caller unless the
+ *     parameter name ends in _host; nothing is allocated behind the caller's
+ *     back except inside the opaque trainer handles (created/destroyed explicitly);
+ *   - `stream` is a cudaStream_t passed as void* (NULL = legacy default stream);
+ *   - return value: 0 = ok, <0 = error; macr_last_error() returns a thread-local
+ *     message for the last failing call on this host thread;
+ *   - callable from any host thread; no Python / GIL interaction;
+ *   - all floating point is fp32, all ids are int32 (reference placeholders are
+ *     tf.int32 / tf.float32: macr_mf/model.py:27-29, macr_lightgcn/LightGCN.py:61-63);
+ *   - embedding width d must be 64 (README commands all use --embed_size 64).
+ *
+ * Each declaration cites the reference interface (file:line under /root/reference)
+ * that it replaces.  The reference has no plugin API: the path sits behind a
+ * TF-1.14 session (`sess.run(fetches, feed_dict)`) and one Cython/C++ evaluator
+ * FFI; INTEGRATION.md shows the binding a maintainer would add for each.
+ */
+#ifndef MACR_B200_H
+#define MACR_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define MACR_OK 0
+#define MACR_ERR_INVALID (-1) /* bad argument (shape, null pointer, unsupported d/K) */
+#define MACR_ERR_CUDA (-2)    /* a CUDA runtime call or kernel launch failed        */
+#define MACR_ERR_WORKSPACE (-3) /* caller-provided workspace too small              */
+
+#define MACR_EMBED_DIM 64
+#define MACR_MAX_TOPK 32 /* one rank per lane of a warp */
+
+typedef void *macr_stream_t; /* cudaStream_t */
+
+const char *macr_last_error(void);
+int macr_abi_version(void);
+/* number of SMs of the current device (grid sizing by callers / bench) */
+int macr_device_sm_count(int *out_sms);
+
+/* ------------------------------------------------------------------------- *
+ * K1+K2  gather + five dot products (+ L2 sum of squares)
+ * replaces: tf.nn.embedding_lookup x3 macr_mf/model.py:35-37, the reductions
+ *   :186-187 and the three [B,64]x[64,1] matmuls :194-196; tf.nn.l2_loss x3 :219;
+ *   LightGCN.py:145-150 (propagated rows for scores, raw rows for the L2 term),
+ *   :496-497,:504-506,:525-526.
+ *  Ue/Ie : tables the scores are taken from   (MF: the variables themselves;
+ *          LightGCN: the propagated ua/ia embeddings)
+ *  Ur/Ir : tables the L2 term is taken from   (MF: same pointers as Ue/Ie)
+ *  out   : yp[b]=u.p  yn[b]=u.n  sp[b]=p.w  sn[b]=n.w  su[b]=u.w_user
+ *          regsq[b]=|u|^2+|p|^2+|n|^2 (of the Ur/Ir rows)
+ * ------------------------------------------------------------------------- */
+int macr_gather_dots(const float *Ue, const float *Ie, const float *Ur, const float *Ir,
+                     const float *w, const float *w_user,
+                     const int32_t *users, const int32_t *pos, const int32_t *neg,
+                     int B, int d,
+                     float *yp, float *yn, float *sp, float *sn, float *su, float *regsq,
+                     macr_stream_t stream);
+
+/* ------------------------------------------------------------------------- *
+ * K3  B x B sigmoid-gated BCE grid, forward + backward in one pass
+ * replaces: the [B]*[B,1] broadcast macr_mf/model.py:204-205, the three means
+ *   :211,:213,:215, their sum :217 and TF autodiff of all of it (model.py:74);
+ *   identically LightGCN.py:513-514,:517-523.
+ *   P[i,j]=yp[j]*sig(sp[i])*sig(su[i])   N[i,j]=yn[j]*sig(sn[i])*sig(su[i])
+ *  losses3 = {L_ori, L_item, L_user} (means, before alpha/beta weighting)
+ *  d_yp,d_yn,d_sp,d_sn,d_su = gradient of (L_ori + alpha*L_item + beta*L_user)
+ *  ws: scratch, at least macr_grid_bce_workspace_bytes(B) bytes.
+ * ------------------------------------------------------------------------- */
+size_t macr_grid_bce_workspace_bytes(int B);
+int macr_grid_bce_fwd_bwd(const float *yp, const float *yn, const float *sp, const float *sn,
+                          const float *su, int B, float alpha, float beta,
+                          float *losses3,
+                          float *d_yp, float *d_yn, float *d_sp, float *d_sn, float *d_su,
+                          void *ws, size_t ws_bytes, macr_stream_t stream);
+
+/* ------------------------------------------------------------------------- *
+ * K5a  batch plan: group the batch positions that hit the same table row
+ * replaces: TF-1.14 optimizer.py _deduplicate_indexed_slices (array_ops.unique +
+ *   unsorted_segment_sum) that AdamOptimizer runs on the IndexedSlices gradient of
+ *   embedding_lookup (third-party, not vendored).
+ *  ids   : n_ids row ids (users: B ids; items: pos followed by neg, 2B ids)
+ *  out   : uniq_rows[n_uniq] ascending, seg_off[n_uniq+1], seg_pos[n_ids]
+ *          (positions into `ids`, ascending inside a segment), *n_uniq (device int)
+ *          touched_bitmap: one bit per table row, set for every row in `ids`
+ *          (caller zero-initialises once; macr_adam_touched_rows clears the bits)
+ *  ws    : scratch, at least macr_batch_plan_workspace_bytes(n_ids) bytes.
+ * ------------------------------------------------------------------------- */
+size_t macr_batch_plan_workspace_bytes(int n_ids);
+int macr_batch_plan(const int32_t *ids, int n_ids, int64_t table_rows,
+                    int32_t *uniq_rows, int32_t *seg_off, int32_t *seg_pos, int32_t *n_uniq,
+                    uint32_t *touched_bitmap, void *ws, size_t ws_bytes, macr_stream_t stream);
+
+/* ------------------------------------------------------------------------- *
+ * K5b  TF-1.14 Adam, dense semantics (adam.py _apply_sparse_shared):
+ *   m <- b1*m (all rows); m[idx] += (1-b1)*g;  v <- b2*v (all rows);
+ *   v[idx] += (1-b2)*g*g;  var <- var - lr_t*m/(sqrt(v)+eps) (all rows)
+ * replaces: tf.train.AdamOptimizer(lr).minimize(...)  macr_mf/model.py:74,
+ *   macr_lightgcn/LightGCN.py:201.
+ *  macr_adam_sweep_untouched : rows whose bit in touched_bitmap is 0
+ *     (bitmap may be NULL = all rows): pure decay + move, 24 B / element.
+ *  macr_adam_rows            : rows listed in uniq_rows with their summed
+ *     gradient rows grad_rows[n_uniq][d]; clears their bitmap bits.
+ *  macr_adam_dense           : every row has a gradient (LightGCN tables:
+ *     the dense dE0 is converted to IndexedSlices over range(rows), so the
+ *     same formula applies) ; grad is [rows][d].
+ *  macr_adam_vec             : training_ops ApplyAdam for w / w_user
+ *     (m += (g-m)(1-b1); v += (g*g-v)(1-b2); var -= m*lr_t/(sqrt(v)+eps)).
+ * ------------------------------------------------------------------------- */
+int macr_adam_sweep_untouched(float *var, float *m, float *v, int64_t rows, int d,
+                              const uint32_t *touched_bitmap,
+                              float lr_t, float beta1, float beta2, float eps,
+                              macr_stream_t stream);
+int macr_adam_rows(float *var, float *m, float *v, int64_t rows, int d,
+                   const int32_t *uniq_rows, const float *grad_rows, int n_uniq,
+                   uint32_t *touched_bitmap,
+                   float lr_t, float beta1, float beta2, float eps, macr_stream_t stream);
+int macr_adam_dense(float *var, float *m, float *v, const float *grad, int64_t rows, int d,
+                    float lr_t, float beta1, float beta2, float eps, macr_stream_t stream);
+int macr_adam_vec(float *var, float *m, float *v, const float *grad, int n,
+                  float lr_t, float beta1, float beta2, float eps, macr_stream_t stream);
+
+/* ------------------------------------------------------------------------- *
+ * Whole MF training step behind one handle (what `sess.run([opt_two_bce_both,
+ * loss_two_bce_both, mf_loss_two_bce_both, reg_loss_two_bce_both], feed)` does,
+ * macr_mf/train.py:492-496).  The handle owns scratch + a captured CUDA graph;
+ * tables and Adam slots stay caller-owned device memory and are updated in place.
+ * ------------------------------------------------------------------------- */
+typedef struct macr_mf_trainer macr_mf_trainer;
+
+typedef struct macr_hparams {
+  float lr;        /* --lr            macr_mf/parse.py:47                          */
+  float beta1;     /* 0.9   TF AdamOptimizer default                              */
+  float beta2;     /* 0.999                                                       */
+  float eps;       /* 1e-8                                                        */
+  float alpha;     /* --alpha         parse.py:16                                 */
+  float beta;      /* --beta          parse.py:18                                 */
+  float decay;     /* --regs          parse.py:40 (LightGCN: regs[0])             */
+  int32_t batch_size_flag; /* args.batch_size: divisor of the L2 term, model.py:220 */
+} macr_hparams;
+
+int macr_mf_trainer_create(macr_mf_trainer **out,
+                           float *U, float *mU, float *vU, int64_t n_users,
+                           float *I, float *mI, float *vI, int64_t n_items,
+                           float *w, float *mw, float *vw,
+                           float *w_user, float *mwu, float *vwu,
+                           int d, int max_batch, const macr_hparams *hp, macr_stream_t stream);
+/* ids: device int32 [B] each.  losses_out: device float[4] =
+ *   {loss, mf_loss, reg_loss, L_ori} written on the stream (no host sync).      */
+int macr_mf_trainer_step(macr_mf_trainer *h, const int32_t *users, const int32_t *pos,
+                         const int32_t *neg, int B, float *losses_out);
+/* same, ids in host memory (pinned recommended): H2D copy, step, D2H of 3 floats,
+ * stream-synchronised before return -- the session-style call of train.py:492.   */
+int macr_mf_trainer_step_host(macr_mf_trainer *h, const int32_t *users_host,
+                              const int32_t *pos_host, const int32_t *neg_host, int B,
+                              float *losses_host /*[3] loss, mf, reg*/);
+/* epoch mode (the loop of train.py:470-499 with the batches pre-staged in HBM):
+ * batches: device int32 [n_steps][3][B] (users | pos | neg per step), losses: device
+ * float [n_steps][4].  Replays the captured step graph n_steps times; asynchronous.  */
+int macr_mf_trainer_run(macr_mf_trainer *h, const int32_t *batches, int n_steps, int B,
+                        float *losses);
+/* number of this library's kernels launched by one step (for bench gpu_launches) */
+int macr_mf_trainer_launches_per_step(const macr_mf_trainer *h);
+int64_t macr_mf_trainer_steps_done(const macr_mf_trainer *h);
+/* overwrite the Adam step counter (checkpoint resume) */
+int macr_mf_trainer_set_steps_done(macr_mf_trainer *h, int64_t t);
+int macr_mf_trainer_destroy(macr_mf_trainer *h);
+
+/* ------------------------------------------------------------------------- *
+ * K6  CSR SpMM  Y = A X  (A = D^-1/2 A D^-1/2, float32 CSR, sorted columns)
+ * replaces: 100 row-folds of tf.sparse_tensor_dense_matmul per layer
+ *   macr_lightgcn/LightGCN.py:257-269,:297-305.
+ *  mean_accum (nullable): mean_accum = (accum_init ? 0 : mean_accum) ... see
+ *  macr_lgcn_propagate for the fused layer mean.
+ * ------------------------------------------------------------------------- */
+int macr_spmm_csr(const int32_t *rowptr, const int32_t *col, const float *val, int64_t n_rows,
+                  const float *X, int d, float *Y, macr_stream_t stream);
+/* E_mean = (E0 + A E0 + ... + A^L E0)/(L+1); E0 = concat(U, I) read in place.
+ * replaces LightGCN._create_lightgcn_embed LightGCN.py:288-309.
+ * tmp: 2*N*d floats scratch.  Emean: N*d floats out (rows [0,n_users) users).   */
+int macr_lgcn_propagate(const int32_t *rowptr, const int32_t *col, const float *val,
+                        const float *U, int64_t n_users, const float *I, int64_t n_items,
+                        int d, int n_layers, float *Emean, float *tmp, macr_stream_t stream);
+
+typedef struct macr_lgcn_trainer macr_lgcn_trainer;
+int macr_lgcn_trainer_create(macr_lgcn_trainer **out,
+                             const int32_t *rowptr, const int32_t *col, const float *val,
+                             float *U, float *mU, float *vU, int64_t n_users,
+                             float *I, float *mI, float *vI, int64_t n_items,
+                             float *w, float *mw, float *vw,
+                             float *w_user, float *mwu, float *vwu,
+                             int d, int n_layers, int max_batch, const macr_hparams *hp,
+                             macr_stream_t stream);
+/* losses_out: device float[4] = {loss, mf_loss, emb_loss, L_ori}
+ * (LightGCN.py:598-607 fetch list; reg_loss is the constant 0 of :530).
+ * train=0 computes the losses only (train_thread_test, LightGCN.py:616-647).    */
+int macr_lgcn_trainer_step(macr_lgcn_trainer *h, const int32_t *users, const int32_t *pos,
+                           const int32_t *neg, int B, int train, float *losses_out);
+int macr_lgcn_trainer_step_host(macr_lgcn_trainer *h, const int32_t *users_host,
+                                const int32_t *pos_host, const int32_t *neg_host, int B,
+                                int train, float *losses_host /*[3]*/);
+int macr_lgcn_trainer_run(macr_lgcn_trainer *h, const int32_t *batches, int n_steps, int B,
+                          int train, float *losses);
+/* propagated tables of the current parameters (device, owned by the handle):
+ * users at Emean, items at Emean + n_users*d                                     */
+int macr_lgcn_trainer_embeddings(macr_lgcn_trainer *h, const float **Emean);
+int macr_lgcn_trainer_launches_per_step(const macr_lgcn_trainer *h);
+int64_t macr_lgcn_trainer_steps_done(const macr_lgcn_trainer *h);
+int macr_lgcn_trainer_set_steps_done(macr_lgcn_trainer *h, int64_t t);
+int macr_lgcn_trainer_destroy(macr_lgcn_trainer *h);
+
+/* ------------------------------------------------------------------------- *
+ * K7+K8  full-catalogue counterfactual score + train-item mask + top-K
+ * replaces: sess.run(model.rubi_ratings_both, {users: batch, pos_items: range(I)})
+ *   macr_mf/train.py:249-251 / utility/batch_test.py:85-88, i.e. model.py:45,:199
+ *   S[t,i] = ((u_t . i_i) - c) * sig(i_i . w) * sig(u_t . w_user), then the mask
+ *   (train.py:133 set difference / batch_test.py:124-129 -inf) and the per-row
+ *   top-K (train.py:95 heapq.nlargest, tools.h:13-22 partial_sort_copy).
+ *
+ *  macr_score_gates: sig_i[i] = sigmoid(I_i . w), sig_u[t] = sigmoid(U_q[t] . w_user)
+ *    dot = fp32 FMA chain k=0..63, sigmoid evaluated in fp64 and rounded to fp32
+ *    (so the CPU oracle reproduces the gates bit for bit).
+ *  macr_score_topk:
+ *    Uq [T][d] query-user rows (already gathered), It [n_items][d] this rank's item
+ *    rows whose global ids start at item_id_offset; y = fp32 FMA chain k=0..d-1;
+ *    score = ((y - c) * sig_i) * sig_u.  mask_rowptr/mask_col: CSR over the T query
+ *    users of GLOBAL item ids to exclude, columns ascending inside a row (nullable).
+ *    Order: score descending, ties -> lower item id first.  Rows with fewer than K
+ *    unmasked items are padded with id -1 / score -inf.
+ *    out_ids [T][K] global ids, out_scores [T][K].
+ * ------------------------------------------------------------------------- */
+int macr_score_gates(const float *rows, int64_t n, int d, const float *wvec, float *sig_out,
+                     macr_stream_t stream);
+int macr_gather_rows(const float *table, const int32_t *ids, int n, int d, float *out,
+                     macr_stream_t stream);
+size_t macr_score_topk_workspace_bytes(int T, int64_t n_items, int K);
+int macr_score_topk(const float *Uq, int T, const float *It, int64_t n_items, int d,
+                    const float *sig_i, const float *sig_u, float c,
+                    const int32_t *mask_rowptr, const int32_t *mask_col,
+                    int K, int32_t item_id_offset,
+                    int32_t *out_ids, float *out_scores,
+                    void *ws, size_t ws_bytes, macr_stream_t stream);
+/* dense score matrix, the literal rubi_ratings_both fetch ([T][n_items] fp32, no mask) */
+int macr_score_matrix(const float *Uq, int T, const float *It, int64_t n_items, int d,
+                      const float *sig_i, const float *sig_u, float c,
+                      float *out, macr_stream_t stream);
+/* merge G candidate lists per row (multi-GPU shards after the all-gather, or the
+ * item-chunk partials inside one GPU): in [G][T][K] -> out [T][K], same order rule */
+int macr_topk_merge(const int32_t *ids, const float *scores, int T, int K, int G,
+                    int32_t *out_ids, float *out_scores, macr_stream_t stream);
+
+/* ------------------------------------------------------------------------- *
+ * top-K of a caller-supplied score matrix: drop-in for
+ *   void c_top_k_array_index(float*,int columns,int rows,int top_k,int threads,int* rankings)
+ *   macr_lightgcn/evaluator/cpp/include/tools.h:24-33 (device pointers here).
+ * ------------------------------------------------------------------------- */
+int macr_topk_rows(const float *scores, int columns_num, int rows_num, int top_k,
+                   int32_t *rankings, macr_stream_t stream);
+
+/* ------------------------------------------------------------------------- *
+ * K9  fold-out metrics from top-K ids; output layout identical to
+ *   void evaluate_foldout(int users_num,int* rankings,int rank_len,int** ground_truths,
+ *                         int* ground_truths_num,int thread_num,float* results)
+ *   macr_lightgcn/evaluator/cpp/include/evaluate_foldout.h:115-195:
+ *   out[t][0:K]=precision@1..K, [K:2K]=recall, [2K:3K]=AP, [3K:4K]=NDCG, [4K:5K]=MRR.
+ *   ground truth as CSR (truth_rowptr[T+1], truth_col) instead of int**.
+ *   inv_log2[k] = 1.0/log2(k+2) as double, k<K, computed by the HOST libm so the
+ *   float accumulation matches the reference bit for bit.
+ * ------------------------------------------------------------------------- */
+int macr_foldout_metrics(const int32_t *topk_ids, int T, int K,
+                         const int32_t *truth_rowptr, const int32_t *truth_col,
+                         const double *inv_log2, float *out, macr_stream_t stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* MACR_B200_H */

@@ -1,0 +1,116 @@
+"""ctypes binding of libmacr_b200.so -- the C ABI declared in include/macr_b200.h.
+
+There is NO fallback: if the shared library is missing or a call fails, a ``MacrError`` is
+raised.  Device memory / streams come from torch (plumbing only); every pointer handed to the
+library is a raw ``tensor.data_ptr()``.
+"""
+import ctypes as C
+import os
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libmacr_b200.so")
+_LIB = None
+
+vp = C.c_void_p
+i64 = C.c_int64
+i32 = C.c_int
+f32 = C.c_float
+sz = C.c_size_t
+
+
+class MacrError(RuntimeError):
+    pass
+
+
+class HParams(C.Structure):
+    """macr_hparams of include/macr_b200.h."""
+
+    _fields_ = [("lr", f32), ("beta1", f32), ("beta2", f32), ("eps", f32), ("alpha", f32),
+                ("beta", f32), ("decay", f32), ("batch_size_flag", C.c_int32)]
+
+    @classmethod
+    def make(cls, lr=1e-3, alpha=1e-3, beta=1e-3, decay=1e-5, batch_size=1024, beta1=0.9,
+             beta2=0.999, eps=1e-8):
+        return cls(lr, beta1, beta2, eps, alpha, beta, decay, batch_size)
+
+
+# name -> (restype, argtypes); must list every symbol include/macr_b200.h declares
+PROTOTYPES = {
+    "macr_last_error": (C.c_char_p, []),
+    "macr_abi_version": (i32, []),
+    "macr_device_sm_count": (i32, [C.POINTER(i32)]),
+    "macr_gather_dots": (i32, [vp] * 9 + [i32, i32] + [vp] * 6 + [vp]),
+    "macr_grid_bce_workspace_bytes": (sz, [i32]),
+    "macr_grid_bce_fwd_bwd": (i32, [vp] * 5 + [i32, f32, f32] + [vp] * 6 + [vp, sz, vp]),
+    "macr_batch_plan_workspace_bytes": (sz, [i32]),
+    "macr_batch_plan": (i32, [vp, i32, i64] + [vp] * 5 + [vp, sz, vp]),
+    "macr_adam_sweep_untouched": (i32, [vp, vp, vp, i64, i32, vp, f32, f32, f32, f32, vp]),
+    "macr_adam_rows": (i32, [vp, vp, vp, i64, i32, vp, vp, i32, vp, f32, f32, f32, f32, vp]),
+    "macr_adam_dense": (i32, [vp, vp, vp, vp, i64, i32, f32, f32, f32, f32, vp]),
+    "macr_adam_vec": (i32, [vp, vp, vp, vp, i32, f32, f32, f32, f32, vp]),
+    "macr_mf_trainer_create": (i32, [C.POINTER(vp), vp, vp, vp, i64, vp, vp, vp, i64] + [vp] * 6 +
+                               [i32, i32, C.POINTER(HParams), vp]),
+    "macr_mf_trainer_step": (i32, [vp, vp, vp, vp, i32, vp]),
+    "macr_mf_trainer_step_host": (i32, [vp, vp, vp, vp, i32, vp]),
+    "macr_mf_trainer_run": (i32, [vp, vp, i32, i32, vp]),
+    "macr_mf_trainer_launches_per_step": (i32, [vp]),
+    "macr_mf_trainer_steps_done": (i64, [vp]),
+    "macr_mf_trainer_set_steps_done": (i32, [vp, i64]),
+    "macr_mf_trainer_destroy": (i32, [vp]),
+    "macr_spmm_csr": (i32, [vp, vp, vp, i64, vp, i32, vp, vp]),
+    "macr_lgcn_propagate": (i32, [vp, vp, vp, vp, i64, vp, i64, i32, i32, vp, vp, vp]),
+    "macr_lgcn_trainer_create": (i32, [C.POINTER(vp), vp, vp, vp, vp, vp, vp, i64, vp, vp, vp, i64] +
+                                 [vp] * 6 + [i32, i32, i32, C.POINTER(HParams), vp]),
+    "macr_lgcn_trainer_step": (i32, [vp, vp, vp, vp, i32, i32, vp]),
+    "macr_lgcn_trainer_step_host": (i32, [vp, vp, vp, vp, i32, i32, vp]),
+    "macr_lgcn_trainer_run": (i32, [vp, vp, i32, i32, i32, vp]),
+    "macr_lgcn_trainer_embeddings": (i32, [vp, C.POINTER(vp)]),
+    "macr_lgcn_trainer_launches_per_step": (i32, [vp]),
+    "macr_lgcn_trainer_steps_done": (i64, [vp]),
+    "macr_lgcn_trainer_set_steps_done": (i32, [vp, i64]),
+    "macr_lgcn_trainer_destroy": (i32, [vp]),
+    "macr_score_gates": (i32, [vp, i64, i32, vp, vp, vp]),
+    "macr_gather_rows": (i32, [vp, vp, i32, i32, vp, vp]),
+    "macr_score_topk_workspace_bytes": (sz, [i32, i64, i32]),
+    "macr_score_topk": (i32, [vp, i32, vp, i64, i32, vp, vp, f32, vp, vp, i32, C.c_int32, vp, vp,
+                              vp, sz, vp]),
+    "macr_score_matrix": (i32, [vp, i32, vp, i64, i32, vp, vp, f32, vp, vp]),
+    "macr_topk_merge": (i32, [vp, vp, i32, i32, i32, vp, vp, vp]),
+    "macr_topk_rows": (i32, [vp, i32, i32, i32, vp, vp]),
+    "macr_foldout_metrics": (i32, [vp, i32, i32, vp, vp, vp, vp, vp]),
+}
+
+
+def lib():
+    """Load libmacr_b200.so (built by ``__graft_entry__.build()`` / ``make -C macr_b200/csrc``)."""
+    global _LIB
+    if _LIB is None:
+        if not os.path.exists(LIB_PATH):
+            raise MacrError(
+                f"{LIB_PATH} is missing: build it with `python -c 'import __graft_entry__ as g; "
+                f"g.build()'` (nvcc, sm_100a). There is no CPU fallback.")
+        handle = C.CDLL(LIB_PATH)
+        for name, (res, args) in PROTOTYPES.items():
+            fn = getattr(handle, name)  # AttributeError here = header/library mismatch
+            fn.restype = res
+            fn.argtypes = args
+        _LIB = handle
+    return _LIB
+
+
+def check(rc, what=""):
+    if rc != 0:
+        msg = lib().macr_last_error()
+        raise MacrError(f"{what} failed (rc={rc}): {msg.decode() if msg else ''}")
+
+
+def ptr(t):
+    """Raw device pointer of a torch tensor (None -> NULL)."""
+    return None if t is None else C.c_void_p(t.data_ptr())
+
+
+def stream_ptr(stream=None):
+    import torch
+
+    s = stream if stream is not None else torch.cuda.current_stream()
+    return C.c_void_p(s.cuda_stream)

@@ -1,0 +1,85 @@
+// train_kernels.cuh -- declarations shared by train_kernels.cu (kernels + launchers) and
+// trainer.cu (the step handles).  Internal; the public surface is include/macr_b200.h.
+#pragma once
+#include "common.cuh"
+
+namespace macr {
+
+// Device-resident per-trainer state.  One tiny kernel advances it at the start of every step so
+// a captured CUDA graph can be replayed without touching kernel parameters.
+struct StepState {
+  float b1p, b2p;  // beta1^t, beta2^t as TF keeps them (fp32, repeated multiplication)
+  float lr_t;      // lr * sqrt(1-b2p) / (1-b1p) for the step being executed
+  float pad0;
+  const int32_t *ids_base;  // [n_steps][3][B]  users | pos | neg
+  float *loss_base;         // [n_steps][4]
+  long long step_idx;       // index into ids_base / loss_base for the step being executed
+  long long t;              // Adam steps applied so far
+  const int32_t *cur_ids;   // ids_base + step_idx*3*B
+  float *cur_loss;          // loss_base + step_idx*4
+};
+
+struct GridWs {  // carve-up of the grid kernel's partial-sum workspace
+  int tile;      // 128 or 64
+  int nblk;      // ceil(B / tile)
+  int Bpad;      // nblk * tile
+  float *rowP, *rowN;  // [nblk(j)][Bpad]
+  float *colP, *colN;  // [nblk(i)][Bpad]
+  float *losspart;     // [nblk*nblk]
+  float *litem, *luser;  // [Bpad]
+  size_t bytes;
+};
+GridWs grid_ws_layout(int B, void *base);
+
+struct PlanBufs {  // output of one batch_plan over n_ids ids
+  int32_t *uniq_rows, *seg_off, *seg_pos, *n_uniq;
+};
+
+// launchers (all asynchronous on `s`); *_st variants read ids / lr_t through StepState
+int launch_step_state(StepState *st, int B, float lr, float b1, float b2, int train,
+                      cudaStream_t s);
+int launch_gather_dots(const float *Ue, const float *Ie, const float *Ur, const float *Ir,
+                       const float *w, const float *wu, const int32_t *u, const int32_t *p,
+                       const int32_t *n, const StepState *st, int B, float *yp, float *yn,
+                       float *sp, float *sn, float *su, float *regsq, cudaStream_t s);
+int launch_grid_bce(const float *yp, const float *yn, const float *sp, const float *sn,
+                    const float *su, int B, float alpha, float beta, const GridWs &ws,
+                    float *d_yp, float *d_yn, float *d_sp, float *d_sn, float *d_su,
+                    int want_grad, cudaStream_t s);
+// losses: if st != null writes {loss, mf, reg, L_ori} to st->cur_loss, else {L_ori,L_item,L_user}
+// to losses3.
+int launch_reduce_losses(const GridWs &ws, const float *regsq, int B, float alpha, float beta,
+                         float decay, int batch_size_flag, float *losses3, const StepState *st,
+                         cudaStream_t s);
+size_t plan_ws_bytes(int n_ids);
+int plan_init();
+// two tables in one launch (table 1 optional: n_ids1 == 0)
+int launch_batch_plan2(const int32_t *ids0, const StepState *st0, int ids0_off, int n_ids0,
+                       int64_t rows0, PlanBufs out0, uint32_t *bitmap0, const int32_t *ids1,
+                       int ids1_off, int n_ids1, int64_t rows1, PlanBufs out1, uint32_t *bitmap1,
+                       void *ws, cudaStream_t s);
+int launch_adam_sweep2(float *var0, float *m0, float *v0, int64_t rows0, const uint32_t *bm0,
+                       float *var1, float *m1, float *v1, int64_t rows1, const uint32_t *bm1,
+                       float lr_t, const StepState *st, float b1, float b2, float eps,
+                       cudaStream_t s);
+// summed gradient rows of the unique touched rows (MF: + L2 term) and per-CTA partials of
+// grad(w), grad(w_user)
+int launch_row_grads(const float *Ue, const float *Ie, const float *Ur, const float *Ir,
+                     const float *w, const float *wu, const StepState *st, const int32_t *u,
+                     const int32_t *p, const int32_t *n, int B, const float *d_yp,
+                     const float *d_yn, const float *d_sp, const float *d_sn, const float *d_su,
+                     float lam, PlanBufs planU, PlanBufs planI, float *gU, float *gI,
+                     float *gw_part, float *gwu_part, int *n_part, cudaStream_t s);
+int launch_adam_rows2(float *U, float *mU, float *vU, PlanBufs planU, const float *gU,
+                      uint32_t *bmU, float *I, float *mI, float *vI, PlanBufs planI,
+                      const float *gI, uint32_t *bmI, int max_rows, float lr_t,
+                      const StepState *st, float b1, float b2, float eps, cudaStream_t s);
+int launch_adam_vec2(float *w, float *mw, float *vw, float *wu, float *mwu, float *vwu,
+                     const float *gw_part, const float *gwu_part, int n_part, float lr_t,
+                     const StepState *st, float b1, float b2, float eps, cudaStream_t s);
+int launch_adam_dense(float *var, float *m, float *v, const float *grad, int64_t n_elems,
+                      float lr_t, const StepState *st, float b1, float b2, float eps,
+                      cudaStream_t s);
+int row_grads_max_parts(int B);
+
+}  // namespace macr

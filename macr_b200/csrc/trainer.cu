@@ -1,0 +1,576 @@
+// trainer.cu -- step handles: the whole `sess.run([opt_two_bce_both, loss..., mf..., reg...])`
+// of macr_mf/train.py:492-496 and macr_lightgcn/LightGCN.py:598-607 behind one C call.
+//
+// A handle owns scratch and one captured CUDA graph per batch size.  Nothing in the graph depends
+// on per-step host values: the Adam step state (beta powers), the current batch pointer and the
+// loss destination live in a device-resident StepState that the last kernel of every step
+// advances, so an epoch of pre-staged batches replays the same graph back to back.
+//
+// MF step DAG (two captured streams):
+//     gather_dots -> grid(BxB) -> finalize ----------------+
+//        \-> batch_plan(users|items) -> adam_sweep(untouched rows, HBM-bound)  --+-> row_grads
+//                                                      -> adam_rows -> adam_vec(w,w_user) -> losses
+// The sweep does not depend on the gradients, so it overlaps the MUFU-bound grid.
+#include <map>
+#include <new>
+
+#include "spmm.cuh"
+
+namespace macr {
+
+__global__ void set_io_kernel(StepState *st, const int32_t *ids_base, float *loss_base) {
+  if (threadIdx.x == 0 && blockIdx.x == 0) {
+    st->ids_base = ids_base;
+    st->loss_base = loss_base;
+    st->step_idx = 0;
+  }
+}
+__global__ void set_powers_kernel(StepState *st, float b1p, float b2p, long long t) {
+  if (threadIdx.x == 0 && blockIdx.x == 0) {
+    st->b1p = b1p;
+    st->b2p = b2p;
+    st->t = t;
+  }
+}
+
+struct TrainerBase {
+  float *U, *mU, *vU, *I, *mI, *vI, *w, *mw, *vw, *wu, *mwu, *vwu;
+  int64_t nu, ni;
+  int maxB;
+  macr_hparams hp;
+  cudaStream_t s, side;
+  cudaEvent_t ev_fork, ev_join;
+  StepState *st;
+  int32_t *ids_stage;
+  float *loss_stage;
+  float *scal;  // 11 x maxB: yp yn sp sn su regsq dyp dyn dsp dsn dsu
+  void *gridws;
+  PlanBufs planU, planI;
+  int32_t *plan_mem;
+  float *gU, *gI, *gw_part, *gwu_part;
+  float *pinned_losses;
+  int64_t steps_done;
+  const int32_t *cur_ids_base;
+  float *cur_loss_base;
+  bool single_mode_set;
+  std::map<int, cudaGraphExec_t> graphs;       // train step, keyed by B
+  std::map<int, cudaGraphExec_t> graphs_eval;  // loss-only step (LightGCN test loss)
+
+  float *sc(int k, int) const { return scal + (size_t)k * maxB; }
+
+  int alloc_common(cudaStream_t stream) {
+    s = stream;
+    int rci = plan_init();
+    if (rci) return rci;
+    MACR_CUDA(cudaStreamCreateWithFlags(&side, cudaStreamNonBlocking));
+    MACR_CUDA(cudaEventCreateWithFlags(&ev_fork, cudaEventDisableTiming));
+    MACR_CUDA(cudaEventCreateWithFlags(&ev_join, cudaEventDisableTiming));
+    MACR_CUDA(cudaMalloc(&st, sizeof(StepState)));
+    MACR_CUDA(cudaMemset(st, 0, sizeof(StepState)));
+    MACR_CUDA(cudaMalloc(&ids_stage, sizeof(int32_t) * 3 * (size_t)maxB));
+    MACR_CUDA(cudaMalloc(&loss_stage, sizeof(float) * 4));
+    MACR_CUDA(cudaMalloc(&scal, sizeof(float) * 11 * (size_t)maxB));
+    MACR_CUDA(cudaMalloc(&gridws, grid_ws_layout(maxB, nullptr).bytes + 4096));
+    // plan buffers: users (B) + items (2B): uniq, seg_off(+1), seg_pos, n_uniq
+    const size_t pm = (size_t)maxB * 3 + ((size_t)maxB + 1) + (size_t)maxB * 3 + 2 * (size_t)maxB +
+                      (2 * (size_t)maxB + 1) + 8;
+    MACR_CUDA(cudaMalloc(&plan_mem, sizeof(int32_t) * pm));
+    int32_t *p = plan_mem;
+    planU.uniq_rows = p; p += maxB;
+    planU.seg_off = p; p += maxB + 1;
+    planU.seg_pos = p; p += maxB;
+    planU.n_uniq = p; p += 1;
+    planI.uniq_rows = p; p += 2 * maxB;
+    planI.seg_off = p; p += 2 * maxB + 1;
+    planI.seg_pos = p; p += 2 * maxB;
+    planI.n_uniq = p; p += 1;
+    MACR_CUDA(cudaMalloc(&gU, sizeof(float) * kD * (size_t)maxB));
+    MACR_CUDA(cudaMalloc(&gI, sizeof(float) * kD * 2 * (size_t)maxB));
+    const int parts = row_grads_max_parts(maxB);
+    MACR_CUDA(cudaMalloc(&gw_part, sizeof(float) * kD * (size_t)parts));
+    MACR_CUDA(cudaMalloc(&gwu_part, sizeof(float) * kD * (size_t)parts));
+    MACR_CUDA(cudaMallocHost(&pinned_losses, sizeof(float) * 4));
+    steps_done = 0;
+    cur_ids_base = nullptr;
+    cur_loss_base = nullptr;
+    single_mode_set = false;
+    set_powers_kernel<<<1, 1, 0, s>>>(st, hp.beta1, hp.beta2, 0);
+    MACR_LAUNCH_CHECK();
+    return MACR_OK;
+  }
+
+  void free_common() {
+    for (auto &kv : graphs) cudaGraphExecDestroy(kv.second);
+    for (auto &kv : graphs_eval) cudaGraphExecDestroy(kv.second);
+    cudaFree(st); cudaFree(ids_stage); cudaFree(loss_stage); cudaFree(scal); cudaFree(gridws);
+    cudaFree(plan_mem); cudaFree(gU); cudaFree(gI); cudaFree(gw_part); cudaFree(gwu_part);
+    cudaFreeHost(pinned_losses);
+    cudaEventDestroy(ev_fork); cudaEventDestroy(ev_join);
+    cudaStreamDestroy(side);
+  }
+
+  int set_io(const int32_t *ids_base, float *loss_base) {
+    set_io_kernel<<<1, 1, 0, s>>>(st, ids_base, loss_base);
+    MACR_LAUNCH_CHECK();
+    cur_ids_base = ids_base;
+    cur_loss_base = loss_base;
+    return MACR_OK;
+  }
+
+  int set_steps(int64_t t) {
+    float b1p = hp.beta1, b2p = hp.beta2;  // fp32 repeated multiplication, like adam.py _finish
+    for (int64_t k = 0; k < t; ++k) {
+      b1p = b1p * hp.beta1;
+      b2p = b2p * hp.beta2;
+    }
+    set_powers_kernel<<<1, 1, 0, s>>>(st, b1p, b2p, (long long)t);
+    MACR_LAUNCH_CHECK();
+    steps_done = t;
+    return MACR_OK;
+  }
+};
+
+// -------------------------------------------------------------------------------------------
+// MF
+// -------------------------------------------------------------------------------------------
+}  // namespace macr
+
+struct macr_mf_trainer : macr::TrainerBase {
+  uint32_t *bmU, *bmI;
+  int launches;
+};
+
+namespace macr {
+
+static int mf_enqueue(macr_mf_trainer *h, int B) {
+  const macr_hparams &hp = h->hp;
+  cudaStream_t s = h->s, side = h->side;
+  float *yp = h->sc(0, B), *yn = h->sc(1, B), *sp = h->sc(2, B), *sn = h->sc(3, B),
+        *su = h->sc(4, B), *rq = h->sc(5, B), *dyp = h->sc(6, B), *dyn = h->sc(7, B),
+        *dsp = h->sc(8, B), *dsn = h->sc(9, B), *dsu = h->sc(10, B);
+  const GridWs g = grid_ws_layout(B, h->gridws);
+  int rc;
+  int launches = 0;
+  // fork: plan + dense sweep need only the ids and the step state
+  MACR_CUDA(cudaEventRecord(h->ev_fork, s));
+  MACR_CUDA(cudaStreamWaitEvent(side, h->ev_fork, 0));
+  rc = launch_batch_plan2(nullptr, h->st, 0, B, h->nu, h->planU, h->bmU, nullptr, B, 2 * B, h->ni,
+                          h->planI, h->bmI, nullptr, side);
+  if (rc) return rc;
+  rc = launch_adam_sweep2(h->U, h->mU, h->vU, h->nu, h->bmU, h->I, h->mI, h->vI, h->ni, h->bmI,
+                          hp.lr, h->st, hp.beta1, hp.beta2, hp.eps, side);
+  if (rc) return rc;
+  MACR_CUDA(cudaEventRecord(h->ev_join, side));
+  launches += 2;
+  // main: gather -> grid -> finalize
+  rc = launch_gather_dots(h->U, h->I, h->U, h->I, h->w, h->wu, nullptr, nullptr, nullptr, h->st, B,
+                          yp, yn, sp, sn, su, rq, s);
+  if (rc) return rc;
+  rc = launch_grid_bce(yp, yn, sp, sn, su, B, hp.alpha, hp.beta, g, dyp, dyn, dsp, dsn, dsu, 1, s);
+  if (rc) return rc;
+  launches += 3;
+  MACR_CUDA(cudaStreamWaitEvent(s, h->ev_join, 0));
+  const float lam = hp.decay / (float)hp.batch_size_flag;
+  int n_part = 0;
+  rc = launch_row_grads(h->U, h->I, h->U, h->I, h->w, h->wu, h->st, nullptr, nullptr, nullptr, B,
+                        dyp, dyn, dsp, dsn, dsu, lam, h->planU, h->planI, h->gU, h->gI, h->gw_part,
+                        h->gwu_part, &n_part, s);
+  if (rc) return rc;
+  rc = launch_adam_rows2(h->U, h->mU, h->vU, h->planU, h->gU, h->bmU, h->I, h->mI, h->vI, h->planI,
+                         h->gI, h->bmI, B, hp.lr, h->st, hp.beta1, hp.beta2, hp.eps, s);
+  if (rc) return rc;
+  rc = launch_adam_vec2(h->w, h->mw, h->vw, h->wu, h->mwu, h->vwu, h->gw_part, h->gwu_part, n_part,
+                        hp.lr, h->st, hp.beta1, hp.beta2, hp.eps, s);
+  if (rc) return rc;
+  rc = launch_reduce_losses(g, rq, B, hp.alpha, hp.beta, hp.decay, hp.batch_size_flag, nullptr,
+                            h->st, s);
+  if (rc) return rc;
+  rc = launch_step_state(h->st, B, hp.lr, hp.beta1, hp.beta2, 1, s);
+  if (rc) return rc;
+  launches += 5;
+  h->launches = launches;
+  return MACR_OK;
+}
+
+template <class H, class F>
+static int get_graph(H *h, std::map<int, cudaGraphExec_t> &cache, int B, F enqueue,
+                     cudaGraphExec_t *out) {
+  auto it = cache.find(B);
+  if (it != cache.end()) {
+    *out = it->second;
+    return MACR_OK;
+  }
+  cudaGraph_t graph = nullptr;
+  MACR_CUDA(cudaStreamBeginCapture(h->s, cudaStreamCaptureModeThreadLocal));
+  int rc = enqueue(h, B);
+  cudaError_t e = cudaStreamEndCapture(h->s, &graph);
+  if (rc) {
+    if (graph) cudaGraphDestroy(graph);
+    return rc;
+  }
+  if (e != cudaSuccess) return fail(MACR_ERR_CUDA, "graph capture: %s", cudaGetErrorString(e));
+  cudaGraphExec_t exec = nullptr;
+  e = cudaGraphInstantiate(&exec, graph, 0);
+  cudaGraphDestroy(graph);
+  if (e != cudaSuccess) return fail(MACR_ERR_CUDA, "graph instantiate: %s", cudaGetErrorString(e));
+  cache[B] = exec;
+  *out = exec;
+  return MACR_OK;
+}
+
+}  // namespace macr
+
+using namespace macr;
+
+static int check_tables(const void *U, const void *mU, const void *vU, const void *I,
+                        const void *mI, const void *vI, const void *w, const void *mw,
+                        const void *vw, const void *wu, const void *mwu, const void *vwu) {
+  return (U && mU && vU && I && mI && vI && w && mw && vw && wu && mwu && vwu) ? 1 : 0;
+}
+
+extern "C" int macr_mf_trainer_create(macr_mf_trainer **out, float *U, float *mU, float *vU,
+                                      int64_t n_users, float *I, float *mI, float *vI,
+                                      int64_t n_items, float *w, float *mw, float *vw,
+                                      float *w_user, float *mwu, float *vwu, int d, int max_batch,
+                                      const macr_hparams *hp, macr_stream_t stream) {
+  MACR_CHECK_ARG(out && hp, "macr_mf_trainer_create: null out/hparams");
+  MACR_CHECK_ARG(d == kD, "macr_mf_trainer_create: d must be %d (got %d)", kD, d);
+  MACR_CHECK_ARG(max_batch > 0 && max_batch <= 8192,
+                 "macr_mf_trainer_create: max_batch must be in [1,8192] (got %d)", max_batch);
+  MACR_CHECK_ARG(n_users > 0 && n_items > 0, "macr_mf_trainer_create: empty table");
+  MACR_CHECK_ARG(check_tables(U, mU, vU, I, mI, vI, w, mw, vw, w_user, mwu, vwu),
+                 "macr_mf_trainer_create: null table pointer");
+  MACR_CHECK_ARG(hp->batch_size_flag > 0, "macr_mf_trainer_create: batch_size_flag must be > 0");
+  macr_mf_trainer *h = new (std::nothrow) macr_mf_trainer();
+  MACR_CHECK_ARG(h, "macr_mf_trainer_create: out of host memory");
+  h->U = U; h->mU = mU; h->vU = vU; h->I = I; h->mI = mI; h->vI = vI;
+  h->w = w; h->mw = mw; h->vw = vw; h->wu = w_user; h->mwu = mwu; h->vwu = vwu;
+  h->nu = n_users; h->ni = n_items; h->maxB = max_batch; h->hp = *hp; h->launches = 0;
+  int rc = h->alloc_common(as_stream(stream));
+  if (rc) return rc;
+  const size_t wu_words = (size_t)((n_users + 31) / 32), wi_words = (size_t)((n_items + 31) / 32);
+  MACR_CUDA(cudaMalloc(&h->bmU, sizeof(uint32_t) * wu_words));
+  MACR_CUDA(cudaMalloc(&h->bmI, sizeof(uint32_t) * wi_words));
+  MACR_CUDA(cudaMemsetAsync(h->bmU, 0, sizeof(uint32_t) * wu_words, h->s));
+  MACR_CUDA(cudaMemsetAsync(h->bmI, 0, sizeof(uint32_t) * wi_words, h->s));
+  MACR_CUDA(cudaStreamSynchronize(h->s));
+  *out = h;
+  return MACR_OK;
+}
+
+template <class H, class F>
+static int run_steps(H *h, std::map<int, cudaGraphExec_t> &cache, F enq, const int32_t *batches,
+                     int n_steps, int B, float *losses) {
+  MACR_CHECK_ARG(h, "trainer: null handle");
+  MACR_CHECK_ARG(B > 0 && B <= h->maxB, "trainer: batch %d outside (0,%d]", B, h->maxB);
+  MACR_CHECK_ARG(n_steps >= 0, "trainer: negative step count");
+  if (n_steps == 0) return MACR_OK;
+  cudaGraphExec_t exec;
+  int rc = get_graph(h, cache, B, enq, &exec);
+  if (rc) return rc;
+  rc = h->set_io(batches, losses);
+  if (rc) return rc;
+  for (int k = 0; k < n_steps; ++k) MACR_CUDA(cudaGraphLaunch(exec, h->s));
+  return MACR_OK;
+}
+
+static int stage_ids_device(TrainerBase *h, const int32_t *u, const int32_t *p, const int32_t *n,
+                            int B, cudaMemcpyKind kind) {
+  const size_t nb = sizeof(int32_t) * (size_t)B;
+  if (p == u + B && n == u + 2 * B) {
+    MACR_CUDA(cudaMemcpyAsync(h->ids_stage, u, 3 * nb, kind, h->s));
+  } else {
+    MACR_CUDA(cudaMemcpyAsync(h->ids_stage, u, nb, kind, h->s));
+    MACR_CUDA(cudaMemcpyAsync(h->ids_stage + B, p, nb, kind, h->s));
+    MACR_CUDA(cudaMemcpyAsync(h->ids_stage + 2 * B, n, nb, kind, h->s));
+  }
+  return MACR_OK;
+}
+
+extern "C" int macr_mf_trainer_step(macr_mf_trainer *h, const int32_t *users, const int32_t *pos,
+                                    const int32_t *neg, int B, float *losses_out) {
+  MACR_CHECK_ARG(h && users && pos && neg, "macr_mf_trainer_step: null argument");
+  MACR_CHECK_ARG(B > 0 && B <= h->maxB, "macr_mf_trainer_step: batch %d outside (0,%d]", B, h->maxB);
+  int rc = stage_ids_device(h, users, pos, neg, B, cudaMemcpyDeviceToDevice);
+  if (rc) return rc;
+  rc = run_steps(h, h->graphs, mf_enqueue, h->ids_stage, 1, B, h->loss_stage);
+  if (rc) return rc;
+  h->steps_done += 1;
+  if (losses_out)
+    MACR_CUDA(cudaMemcpyAsync(losses_out, h->loss_stage, sizeof(float) * 4,
+                              cudaMemcpyDeviceToDevice, h->s));
+  return MACR_OK;
+}
+
+extern "C" int macr_mf_trainer_step_host(macr_mf_trainer *h, const int32_t *users_host,
+                                         const int32_t *pos_host, const int32_t *neg_host, int B,
+                                         float *losses_host) {
+  MACR_CHECK_ARG(h && users_host && pos_host && neg_host, "macr_mf_trainer_step_host: null argument");
+  MACR_CHECK_ARG(B > 0 && B <= h->maxB, "macr_mf_trainer_step_host: batch %d outside (0,%d]", B,
+                 h->maxB);
+  int rc = stage_ids_device(h, users_host, pos_host, neg_host, B, cudaMemcpyHostToDevice);
+  if (rc) return rc;
+  rc = run_steps(h, h->graphs, mf_enqueue, h->ids_stage, 1, B, h->loss_stage);
+  if (rc) return rc;
+  h->steps_done += 1;
+  MACR_CUDA(cudaMemcpyAsync(h->pinned_losses, h->loss_stage, sizeof(float) * 4,
+                            cudaMemcpyDeviceToHost, h->s));
+  MACR_CUDA(cudaStreamSynchronize(h->s));
+  if (losses_host) memcpy(losses_host, h->pinned_losses, sizeof(float) * 3);
+  return MACR_OK;
+}
+
+extern "C" int macr_mf_trainer_run(macr_mf_trainer *h, const int32_t *batches, int n_steps, int B,
+                                   float *losses) {
+  MACR_CHECK_ARG(h && batches && losses, "macr_mf_trainer_run: null argument");
+  int rc = run_steps(h, h->graphs, mf_enqueue, batches, n_steps, B, losses);
+  if (rc) return rc;
+  h->steps_done += n_steps;
+  return MACR_OK;
+}
+
+extern "C" int macr_mf_trainer_launches_per_step(const macr_mf_trainer *h) {
+  return h ? h->launches : 0;
+}
+extern "C" int64_t macr_mf_trainer_steps_done(const macr_mf_trainer *h) {
+  return h ? h->steps_done : -1;
+}
+extern "C" int macr_mf_trainer_set_steps_done(macr_mf_trainer *h, int64_t t) {
+  MACR_CHECK_ARG(h && t >= 0, "macr_mf_trainer_set_steps_done: bad argument");
+  return h->set_steps(t);
+}
+extern "C" int macr_mf_trainer_destroy(macr_mf_trainer *h) {
+  if (!h) return MACR_OK;
+  cudaStreamSynchronize(h->s);
+  cudaStreamSynchronize(h->side);
+  h->free_common();
+  cudaFree(h->bmU);
+  cudaFree(h->bmI);
+  delete h;
+  return MACR_OK;
+}
+
+// -------------------------------------------------------------------------------------------
+// LightGCN
+// -------------------------------------------------------------------------------------------
+struct macr_lgcn_trainer : macr::TrainerBase {
+  const int32_t *rowptr, *col;
+  const float *val;
+  int L;
+  float *Emean, *tmp, *g3;  // [N][64], 2x[N][64], [N][64]
+  bool emb_dirty;
+  int launches;
+};
+
+namespace macr {
+
+static int lgcn_enqueue_impl(macr_lgcn_trainer *h, int B, int train) {
+  const macr_hparams &hp = h->hp;
+  cudaStream_t s = h->s, side = h->side;
+  const int64_t N = h->nu + h->ni;
+  float *yp = h->sc(0, B), *yn = h->sc(1, B), *sp = h->sc(2, B), *sn = h->sc(3, B),
+        *su = h->sc(4, B), *rq = h->sc(5, B), *dyp = h->sc(6, B), *dyn = h->sc(7, B),
+        *dsp = h->sc(8, B), *dsn = h->sc(9, B), *dsu = h->sc(10, B);
+  const GridWs g = grid_ws_layout(B, h->gridws);
+  const float *Ue = h->Emean, *Ie = h->Emean + h->nu * kD;
+  int rc, launches = 0;
+  if (train) {
+    MACR_CUDA(cudaEventRecord(h->ev_fork, s));
+    MACR_CUDA(cudaStreamWaitEvent(side, h->ev_fork, 0));
+    rc = launch_batch_plan2(nullptr, h->st, 0, B, h->nu, h->planU, nullptr, nullptr, B, 2 * B,
+                            h->ni, h->planI, nullptr, nullptr, side);
+    if (rc) return rc;
+    MACR_CUDA(cudaMemsetAsync(h->g3, 0, sizeof(float) * N * kD, side));
+    MACR_CUDA(cudaEventRecord(h->ev_join, side));
+    launches += 1;
+  }
+  rc = launch_lgcn_propagate(h->rowptr, h->col, h->val, h->U, h->nu, h->I, h->ni, h->L, h->Emean,
+                             h->tmp, s);
+  if (rc) return rc;
+  launches += h->L;
+  rc = launch_gather_dots(Ue, Ie, h->U, h->I, h->w, h->wu, nullptr, nullptr, nullptr, h->st, B, yp,
+                          yn, sp, sn, su, rq, s);
+  if (rc) return rc;
+  rc = launch_grid_bce(yp, yn, sp, sn, su, B, hp.alpha, hp.beta, g, dyp, dyn, dsp, dsn, dsu, train,
+                       s);
+  if (rc) return rc;
+  launches += 3;
+  if (train) {
+    MACR_CUDA(cudaStreamWaitEvent(s, h->ev_join, 0));
+    int n_part = 0;
+    rc = launch_row_grads(Ue, Ie, h->U, h->I, h->w, h->wu, h->st, nullptr, nullptr, nullptr, B, dyp,
+                          dyn, dsp, dsn, dsu, 0.f, h->planU, h->planI, h->gU, h->gI, h->gw_part,
+                          h->gwu_part, &n_part, s);
+    if (rc) return rc;
+    rc = launch_scatter_rows(h->planU, h->gU, h->planI, h->gI, B, h->nu, (float)(h->L + 1), h->g3,
+                             s);
+    if (rc) return rc;
+    launches += 2;
+    // backward through the layer stack: acc_L = g3; acc_{k-1} = g3 + A^T acc_k  (A symmetric)
+    float *buf[2] = {h->tmp, h->tmp + N * kD};
+    const float *acc = h->g3;
+    for (int k = 0; k < h->L; ++k) {
+      RowSrc x{acc, acc, N};
+      rc = launch_spmm(h->rowptr, h->col, h->val, N, x, h->g3, buf[k & 1], x, nullptr, 0.f, s);
+      if (rc) return rc;
+      acc = buf[k & 1];
+      launches += 1;
+    }
+    float *grad = const_cast<float *>(acc);
+    const float lam = hp.decay / (float)hp.batch_size_flag;
+    rc = launch_l2_rows(h->planU, h->planI, B, h->U, h->I, h->nu, lam, grad, s);
+    if (rc) return rc;
+    rc = launch_adam_dense(h->U, h->mU, h->vU, grad, h->nu * kD, hp.lr, h->st, hp.beta1, hp.beta2,
+                           hp.eps, s);
+    if (rc) return rc;
+    rc = launch_adam_dense(h->I, h->mI, h->vI, grad + h->nu * kD, h->ni * kD, hp.lr, h->st,
+                           hp.beta1, hp.beta2, hp.eps, s);
+    if (rc) return rc;
+    rc = launch_adam_vec2(h->w, h->mw, h->vw, h->wu, h->mwu, h->vwu, h->gw_part, h->gwu_part,
+                          n_part, hp.lr, h->st, hp.beta1, hp.beta2, hp.eps, s);
+    if (rc) return rc;
+    launches += 4;
+  }
+  rc = launch_reduce_losses(g, rq, B, hp.alpha, hp.beta, hp.decay, hp.batch_size_flag, nullptr,
+                            h->st, s);
+  if (rc) return rc;
+  rc = launch_step_state(h->st, B, hp.lr, hp.beta1, hp.beta2, train, s);
+  if (rc) return rc;
+  launches += 2;
+  if (train) h->launches = launches;
+  return MACR_OK;
+}
+static int lgcn_enqueue_train(macr_lgcn_trainer *h, int B) { return lgcn_enqueue_impl(h, B, 1); }
+static int lgcn_enqueue_eval(macr_lgcn_trainer *h, int B) { return lgcn_enqueue_impl(h, B, 0); }
+
+}  // namespace macr
+
+extern "C" int macr_lgcn_trainer_create(macr_lgcn_trainer **out, const int32_t *rowptr,
+                                        const int32_t *col, const float *val, float *U, float *mU,
+                                        float *vU, int64_t n_users, float *I, float *mI, float *vI,
+                                        int64_t n_items, float *w, float *mw, float *vw,
+                                        float *w_user, float *mwu, float *vwu, int d, int n_layers,
+                                        int max_batch, const macr_hparams *hp,
+                                        macr_stream_t stream) {
+  MACR_CHECK_ARG(out && hp, "macr_lgcn_trainer_create: null out/hparams");
+  MACR_CHECK_ARG(d == kD, "macr_lgcn_trainer_create: d must be %d (got %d)", kD, d);
+  MACR_CHECK_ARG(max_batch > 0 && max_batch <= 8192,
+                 "macr_lgcn_trainer_create: max_batch must be in [1,8192] (got %d)", max_batch);
+  MACR_CHECK_ARG(n_layers >= 0 && n_layers <= 16, "macr_lgcn_trainer_create: bad n_layers %d",
+                 n_layers);
+  MACR_CHECK_ARG(rowptr && col && val, "macr_lgcn_trainer_create: null adjacency");
+  MACR_CHECK_ARG(n_users > 0 && n_items > 0, "macr_lgcn_trainer_create: empty table");
+  MACR_CHECK_ARG(check_tables(U, mU, vU, I, mI, vI, w, mw, vw, w_user, mwu, vwu),
+                 "macr_lgcn_trainer_create: null table pointer");
+  MACR_CHECK_ARG(hp->batch_size_flag > 0, "macr_lgcn_trainer_create: batch_size_flag must be > 0");
+  macr_lgcn_trainer *h = new (std::nothrow) macr_lgcn_trainer();
+  MACR_CHECK_ARG(h, "macr_lgcn_trainer_create: out of host memory");
+  h->U = U; h->mU = mU; h->vU = vU; h->I = I; h->mI = mI; h->vI = vI;
+  h->w = w; h->mw = mw; h->vw = vw; h->wu = w_user; h->mwu = mwu; h->vwu = vwu;
+  h->nu = n_users; h->ni = n_items; h->maxB = max_batch; h->hp = *hp;
+  h->rowptr = rowptr; h->col = col; h->val = val; h->L = n_layers; h->launches = 0;
+  int rc = h->alloc_common(as_stream(stream));
+  if (rc) return rc;
+  const size_t ne = (size_t)(n_users + n_items) * kD;
+  MACR_CUDA(cudaMalloc(&h->Emean, sizeof(float) * ne));
+  MACR_CUDA(cudaMalloc(&h->tmp, sizeof(float) * ne * 2));
+  MACR_CUDA(cudaMalloc(&h->g3, sizeof(float) * ne));
+  h->emb_dirty = true;
+  MACR_CUDA(cudaStreamSynchronize(h->s));
+  *out = h;
+  return MACR_OK;
+}
+
+extern "C" int macr_lgcn_trainer_step(macr_lgcn_trainer *h, const int32_t *users,
+                                      const int32_t *pos, const int32_t *neg, int B, int train,
+                                      float *losses_out) {
+  MACR_CHECK_ARG(h && users && pos && neg, "macr_lgcn_trainer_step: null argument");
+  MACR_CHECK_ARG(B > 0 && B <= h->maxB, "macr_lgcn_trainer_step: batch %d outside (0,%d]", B,
+                 h->maxB);
+  int rc = stage_ids_device(h, users, pos, neg, B, cudaMemcpyDeviceToDevice);
+  if (rc) return rc;
+  rc = train ? run_steps(h, h->graphs, lgcn_enqueue_train, h->ids_stage, 1, B, h->loss_stage)
+             : run_steps(h, h->graphs_eval, lgcn_enqueue_eval, h->ids_stage, 1, B, h->loss_stage);
+  if (rc) return rc;
+  if (train) {
+    h->steps_done += 1;
+    h->emb_dirty = true;
+  } else {
+    h->emb_dirty = false;  // Emean now holds the propagation of the current parameters
+  }
+  if (losses_out)
+    MACR_CUDA(cudaMemcpyAsync(losses_out, h->loss_stage, sizeof(float) * 4,
+                              cudaMemcpyDeviceToDevice, h->s));
+  return MACR_OK;
+}
+
+extern "C" int macr_lgcn_trainer_step_host(macr_lgcn_trainer *h, const int32_t *users_host,
+                                           const int32_t *pos_host, const int32_t *neg_host, int B,
+                                           int train, float *losses_host) {
+  MACR_CHECK_ARG(h && users_host && pos_host && neg_host, "macr_lgcn_trainer_step_host: null argument");
+  MACR_CHECK_ARG(B > 0 && B <= h->maxB, "macr_lgcn_trainer_step_host: batch %d outside (0,%d]", B,
+                 h->maxB);
+  int rc = stage_ids_device(h, users_host, pos_host, neg_host, B, cudaMemcpyHostToDevice);
+  if (rc) return rc;
+  rc = train ? run_steps(h, h->graphs, lgcn_enqueue_train, h->ids_stage, 1, B, h->loss_stage)
+             : run_steps(h, h->graphs_eval, lgcn_enqueue_eval, h->ids_stage, 1, B, h->loss_stage);
+  if (rc) return rc;
+  if (train) {
+    h->steps_done += 1;
+    h->emb_dirty = true;
+  } else {
+    h->emb_dirty = false;
+  }
+  MACR_CUDA(cudaMemcpyAsync(h->pinned_losses, h->loss_stage, sizeof(float) * 4,
+                            cudaMemcpyDeviceToHost, h->s));
+  MACR_CUDA(cudaStreamSynchronize(h->s));
+  if (losses_host) memcpy(losses_host, h->pinned_losses, sizeof(float) * 3);
+  return MACR_OK;
+}
+
+extern "C" int macr_lgcn_trainer_run(macr_lgcn_trainer *h, const int32_t *batches, int n_steps,
+                                     int B, int train, float *losses) {
+  MACR_CHECK_ARG(h && batches && losses, "macr_lgcn_trainer_run: null argument");
+  int rc = train ? run_steps(h, h->graphs, lgcn_enqueue_train, batches, n_steps, B, losses)
+                 : run_steps(h, h->graphs_eval, lgcn_enqueue_eval, batches, n_steps, B, losses);
+  if (rc) return rc;
+  if (train && n_steps > 0) {
+    h->steps_done += n_steps;
+    h->emb_dirty = true;
+  }
+  return MACR_OK;
+}
+
+extern "C" int macr_lgcn_trainer_embeddings(macr_lgcn_trainer *h, const float **Emean) {
+  MACR_CHECK_ARG(h && Emean, "macr_lgcn_trainer_embeddings: null argument");
+  if (h->emb_dirty) {
+    int rc = launch_lgcn_propagate(h->rowptr, h->col, h->val, h->U, h->nu, h->I, h->ni, h->L,
+                                   h->Emean, h->tmp, h->s);
+    if (rc) return rc;
+    h->emb_dirty = false;
+  }
+  *Emean = h->Emean;
+  return MACR_OK;
+}
+
+extern "C" int macr_lgcn_trainer_launches_per_step(const macr_lgcn_trainer *h) {
+  return h ? h->launches : 0;
+}
+extern "C" int64_t macr_lgcn_trainer_steps_done(const macr_lgcn_trainer *h) {
+  return h ? h->steps_done : -1;
+}
+extern "C" int macr_lgcn_trainer_set_steps_done(macr_lgcn_trainer *h, int64_t t) {
+  MACR_CHECK_ARG(h && t >= 0, "macr_lgcn_trainer_set_steps_done: bad argument");
+  return h->set_steps(t);
+}
+extern "C" int macr_lgcn_trainer_destroy(macr_lgcn_trainer *h) {
+  if (!h) return MACR_OK;
+  cudaStreamSynchronize(h->s);
+  cudaStreamSynchronize(h->side);
+  h->free_common();
+  cudaFree(h->Emean);
+  cudaFree(h->tmp);
+  cudaFree(h->g3);
+  delete h;
+  return MACR_OK;
+}
