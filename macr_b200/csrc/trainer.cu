@@ -38,7 +38,9 @@ struct TrainerBase {
   int64_t nu, ni;
   int maxB;
   macr_hparams hp;
-  cudaStream_t s, side;
+  cudaStream_t s;         // caller's stream: graphs are launched here
+  cudaStream_t cs, side;  // private streams the step DAG is captured on (the legacy default
+                          // stream cannot be captured)
   cudaEvent_t ev_fork, ev_join;
   StepState *st;
   int32_t *ids_stage;
@@ -62,6 +64,7 @@ struct TrainerBase {
     s = stream;
     int rci = plan_init();
     if (rci) return rci;
+    MACR_CUDA(cudaStreamCreateWithFlags(&cs, cudaStreamNonBlocking));
     MACR_CUDA(cudaStreamCreateWithFlags(&side, cudaStreamNonBlocking));
     MACR_CUDA(cudaEventCreateWithFlags(&ev_fork, cudaEventDisableTiming));
     MACR_CUDA(cudaEventCreateWithFlags(&ev_join, cudaEventDisableTiming));
@@ -107,6 +110,7 @@ struct TrainerBase {
     cudaFreeHost(pinned_losses);
     cudaEventDestroy(ev_fork); cudaEventDestroy(ev_join);
     cudaStreamDestroy(side);
+    cudaStreamDestroy(cs);
   }
 
   int set_io(const int32_t *ids_base, float *loss_base) {
@@ -144,7 +148,7 @@ namespace macr {
 
 static int mf_enqueue(macr_mf_trainer *h, int B) {
   const macr_hparams &hp = h->hp;
-  cudaStream_t s = h->s, side = h->side;
+  cudaStream_t s = h->cs, side = h->side;
   float *yp = h->sc(0, B), *yn = h->sc(1, B), *sp = h->sc(2, B), *sn = h->sc(3, B),
         *su = h->sc(4, B), *rq = h->sc(5, B), *dyp = h->sc(6, B), *dyn = h->sc(7, B),
         *dsp = h->sc(8, B), *dsn = h->sc(9, B), *dsu = h->sc(10, B);
@@ -201,9 +205,9 @@ static int get_graph(H *h, std::map<int, cudaGraphExec_t> &cache, int B, F enque
     return MACR_OK;
   }
   cudaGraph_t graph = nullptr;
-  MACR_CUDA(cudaStreamBeginCapture(h->s, cudaStreamCaptureModeThreadLocal));
+  MACR_CUDA(cudaStreamBeginCapture(h->cs, cudaStreamCaptureModeThreadLocal));
   int rc = enqueue(h, B);
-  cudaError_t e = cudaStreamEndCapture(h->s, &graph);
+  cudaError_t e = cudaStreamEndCapture(h->cs, &graph);
   if (rc) {
     if (graph) cudaGraphDestroy(graph);
     return rc;
@@ -366,7 +370,7 @@ namespace macr {
 
 static int lgcn_enqueue_impl(macr_lgcn_trainer *h, int B, int train) {
   const macr_hparams &hp = h->hp;
-  cudaStream_t s = h->s, side = h->side;
+  cudaStream_t s = h->cs, side = h->side;
   const int64_t N = h->nu + h->ni;
   float *yp = h->sc(0, B), *yn = h->sc(1, B), *sp = h->sc(2, B), *sn = h->sc(3, B),
         *su = h->sc(4, B), *rq = h->sc(5, B), *dyp = h->sc(6, B), *dyn = h->sc(7, B),
