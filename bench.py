@@ -1,0 +1,380 @@
+#!/usr/bin/env python
+"""bench.py -- MACR hot path on B200: train interactions/sec (d=64) + full-catalogue scores/sec.
+
+Contract: `python bench.py --gpus N --steps K --warmup W [--impl reference]` prints ONE JSON line.
+
+Workload at N=1 (BASELINE.json configs[1]): MACR-MF, Gowalla shapes (U=29 858, I=40 981, d=64),
+B=4096, `--train rubibceboth`, synthetic triples per SURVEY.md section 8(d):
+users = first B of rng.permutation(U), pos ~ Zipf(1.0) truncated to [0,I), neg ~ U[0,I), seed 12345.
+
+  value        device-resident throughput: batches pre-staged in HBM, one captured step graph per
+               step, every step timed with CUDA events on the launching stream, L2 flushed
+               (256 MiB memset) between timed steps.
+  e2e          same step through the session-style call (`MFTrainer.step_host`): ids in pinned host
+               memory, H2D copy + step + D2H of the losses + stream sync inside the timed region.
+  roofline     the Adam dense sweep (the HBM-bound kernel of the step), timed alone with CUDA
+               events, L2 flushed between launches; algorithmic bytes = 24*d*(U+I) per launch.
+  cpu_baseline the oracle port of the step (C + OpenMP) on this box's host cores, bounded sample.
+  scoring      full-catalogue counterfactual score + mask + top-20, scores/sec (T test users x I).
+
+N>1: the training step of this configuration does not shard profitably (a 40 us step), so the
+ranks run independent replicas ("replicas only", e.g. the c / alpha / beta sweep of tune.py) and
+`value` is their aggregate; `scoring` is item-sharded across the ranks with one NCCL all-gather of
+the per-shard top-K candidates and an on-device merge.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+N_USERS, N_ITEMS, D, BATCH = 29858, 40981, 64, 4096  # gowalla, README.md:40
+N_TEST_USERS = 15424
+TOPK = 20
+HP = dict(lr=1e-3, alpha=1e-2, beta=1e-3, decay=1e-5, batch_size=BATCH)  # README.md:40
+N_BATCHES = 200
+
+
+def synth_model(seed):
+    rng = np.random.RandomState(seed)
+    lim_u, lim_i, lim_w = np.sqrt(6.0 / (N_USERS + D)), np.sqrt(6.0 / (N_ITEMS + D)), np.sqrt(6.0 / (D + 1))
+    U = rng.uniform(-lim_u, lim_u, (N_USERS, D)).astype(np.float32)
+    I = rng.uniform(-lim_i, lim_i, (N_ITEMS, D)).astype(np.float32)
+    w = rng.uniform(-lim_w, lim_w, D).astype(np.float32)
+    wu = rng.uniform(-lim_w, lim_w, D).astype(np.float32)
+    return U, I, w, wu
+
+
+def synth_batches(seed, n):
+    rng = np.random.RandomState(seed)
+    ranks = np.arange(1, N_ITEMS + 1, dtype=np.float64)
+    cdf = np.cumsum(1.0 / ranks)
+    cdf /= cdf[-1]
+    out = np.empty((n, 3, BATCH), np.int32)
+    for s in range(n):
+        out[s, 0] = rng.permutation(N_USERS)[:BATCH]
+        out[s, 1] = np.minimum(np.searchsorted(cdf, rng.rand(BATCH)), N_ITEMS - 1)
+        out[s, 2] = rng.randint(0, N_ITEMS, BATCH)
+    return out
+
+
+def synth_mask(seed, n_rows, avg):
+    rng = np.random.RandomState(seed)
+    cnt = np.maximum(1, rng.poisson(avg, n_rows)).astype(np.int64)
+    rowptr = np.zeros(n_rows + 1, np.int32)
+    rowptr[1:] = np.cumsum(cnt)
+    col = np.empty(rowptr[-1], np.int32)
+    for r in range(n_rows):
+        col[rowptr[r]:rowptr[r + 1]] = np.sort(rng.choice(N_ITEMS, size=cnt[r], replace=False))
+    return rowptr, col
+
+
+class ClockSampler(threading.Thread):
+    """nvidia-smi clocks + throttle reasons during the timed region (B200_PROFILING.md)."""
+
+    Q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        super().__init__(daemon=True)
+        self.index, self.rows, self._stop_evt = index, [], threading.Event()
+
+    def run(self):
+        while not self._stop_evt.is_set():
+            try:
+                out = subprocess.run(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                                      "-i", str(self.index)], capture_output=True, text=True, timeout=5).stdout
+                self.rows.append([x.strip() for x in out.strip().split(",")])
+            except Exception:
+                pass
+            self._stop_evt.wait(0.2)
+
+    def stop(self):
+        self._stop_evt.set()
+        self.join(timeout=3)
+        sm, mx, reasons = [], 0, set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for r in self.rows:
+            try:
+                sm.append(float(r[0]))
+                mx = max(mx, float(r[1]))
+                for nme, v in zip(names, r[2:6]):
+                    if v.lower().startswith("active"):
+                        reasons.add(nme)
+            except Exception:
+                continue
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": mx or None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def measured_peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        with open(p) as f:
+            return json.load(f), "measured"
+    return {"hbm_gbs": 6650.0, "bf16_tflops": 1590.0}, "fallback"
+
+
+def cpu_step_baseline(steps, threads=None):
+    """oracle port of the step on the host cores; bounded sample of the same workload."""
+    import oracle
+
+    oracle.build()
+    threads = threads or os.cpu_count() or 1
+    oracle.set_threads(threads)
+    U, I, w, wu = synth_model(12345)
+    st = oracle.MFState(U, I, w, wu)
+    hp = oracle.HParams.make(**HP)
+    batches = synth_batches(12345, steps + 1)
+    oracle.mf_step(st, *batches[0], hp)  # warm-up
+    times = []
+    for s in range(steps):
+        t0 = time.perf_counter()
+        oracle.mf_step(st, *batches[1 + s], hp)
+        times.append(time.perf_counter() - t0)
+    ms = 1e3 * float(np.mean(times))
+    return BATCH / (ms * 1e-3), ms, threads
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    steps = max(1, min(args.steps, 20))
+    t_all = time.perf_counter()
+    for _ in range(max(0, min(args.warmup, 2))):
+        pass  # warm-up is the untimed first step inside cpu_step_baseline
+    val, ms, threads = cpu_step_baseline(steps)
+    line = {
+        "impl": "reference", "metric": "train_interactions_per_sec", "value": val,
+        "unit": "interactions/s", "n_gpus": args.gpus, "steps": steps, "warmup": 1,
+        "ms_per_step": ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "f32", "data": "synthetic",
+        "config": {"workload": "MACR-MF gowalla-shape U=29858 I=40981 d=64 B=4096 rubibceboth "
+                               "(one training step; oracle port of the TF-1.14 CPU path)"},
+        "cpu_baseline": {"value": val, "unit": "interactions/s", "cores": threads, "kind": "port",
+                         "sample": f"{steps} steps of B=4096 after 1 warm-up step"},
+        "e2e": {"value": val, "unit": "interactions/s", "h2d_bytes_per_step": 0,
+                "d2h_bytes_per_step": 0},
+        "wall_s": time.perf_counter() - t_all,
+    }
+    print(json.dumps(line))
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=100)
+    ap.add_argument("--warmup", type=int, default=20)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-scoring", action="store_true")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        return run_reference(args)
+
+    import torch
+    import torch.distributed as dist
+
+    from macr_b200 import ops
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device (no CPU fallback)")
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    K, W = args.steps, max(3, args.warmup)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def max_over_ranks(x):
+        if world == 1:
+            return x
+        t = torch.tensor([x], dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    # ---------------- model + batches resident in HBM ----------------
+    U, I, w, wu = synth_model(12345 + rank)
+    hp = ops.HParams.make(**HP)
+    tr = ops.MFTrainer(U, I, w, wu, hp, max_batch=BATCH, device=dev)
+    nb = min(N_BATCHES, max(K, W))
+    batches_h = synth_batches(12345 + rank, nb)
+    batches = torch.from_numpy(batches_h).to(dev)
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)  # > 126 MB L2
+    losses = torch.zeros((nb, 4), dtype=torch.float32, device=dev)
+
+    def one_step(s):
+        tr.run(batches[s % nb:s % nb + 1], losses[s % nb:s % nb + 1])
+
+    for s in range(W):
+        one_step(s)
+    barrier()
+    sampler = ClockSampler(local_rank)
+    sampler.start()
+    # (1) device-resident, L2 flushed between timed steps
+    evs = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(K)]
+    barrier()
+    for s in range(K):
+        flush.zero_()
+        evs[s][0].record()
+        one_step(W + s)
+        evs[s][1].record()
+    barrier()
+    step_ms = [a.elapsed_time(b) for a, b in evs]
+    t_flushed = max_over_ranks(sum(step_ms) * 1e-3)
+    # (2) back-to-back replay (tables stay L2-resident between steps, as in a real epoch)
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    e0.record()
+    done = 0
+    while done < K:
+        n = min(nb, K - done)
+        tr.run(batches[:n], losses[:n])
+        done += n
+    e1.record()
+    barrier()
+    t_b2b = max_over_ranks(e0.elapsed_time(e1) * 1e-3)
+    # (3) end to end through the session-style host call
+    pin = torch.from_numpy(batches_h[:min(nb, 32)].copy()).pin_memory()  # [n,3,B] int32, pinned
+    for s in range(3):
+        tr.step_pinned(pin[s % pin.shape[0]])
+    barrier()
+    t0 = time.perf_counter()
+    for s in range(K):
+        tr.step_pinned(pin[s % pin.shape[0]])
+    torch.cuda.synchronize()
+    t_e2e_local = time.perf_counter() - t0
+    barrier()
+    t_e2e = max_over_ranks(t_e2e_local)
+    clocks = sampler.stop()
+    final_loss = float(losses[(W + K - 1) % nb, 0].item())
+
+    # ---------------- roofline of the HBM-bound kernel: the Adam dense sweep ----------------
+    peaks, peak_kind = measured_peaks()
+    rows = N_USERS + N_ITEMS
+    sweep_bytes = 24.0 * D * rows
+    # steady-state tables: every row has non-zero Adam moments (no all-zero-row shortcut)
+    bigv = torch.randn((rows, D), dtype=torch.float32, device=dev) * 0.05
+    bigm = torch.randn((rows, D), dtype=torch.float32, device=dev) * 1e-4
+    bigvv = torch.rand((rows, D), dtype=torch.float32, device=dev) * 1e-7 + 1e-9
+    n_sw = 30
+    sw_ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(n_sw)]
+    for _ in range(3):
+        ops.adam_sweep_untouched(bigv, bigm, bigvv, None, 1e-4)
+    for k in range(n_sw):
+        flush.zero_()
+        sw_ev[k][0].record()
+        ops.adam_sweep_untouched(bigv, bigm, bigvv, None, 1e-4)
+        sw_ev[k][1].record()
+    torch.cuda.synchronize()
+    sw_ms = float(np.mean([a.elapsed_time(b) for a, b in sw_ev]))
+    achieved = sweep_bytes / (sw_ms * 1e-3) / 1e9
+    step_bytes = 24.0 * D * rows + 12.0 * D * BATCH + 12.0 * BATCH + 48.0 * D
+    ms_per_step = 1e3 * t_flushed / K
+    roofline = {"bound": "hbm", "kernel": "adam_sweep_kernel", "achieved": achieved,
+                "peak": peaks["hbm_gbs"], "peak_kind": peak_kind, "unit": "GB/s",
+                "frac": achieved / peaks["hbm_gbs"], "traffic": None,
+                "bytes_per_launch": sweep_bytes, "ms_per_launch": sw_ms,
+                "step": {"bytes_per_step": step_bytes,
+                         "achieved": step_bytes / (ms_per_step * 1e-3) / 1e9,
+                         "frac": step_bytes / (ms_per_step * 1e-3) / 1e9 / peaks["hbm_gbs"],
+                         "note": "whole step; the BxB grid kernel is MUFU-bound, not HBM-bound"}}
+    del bigv, bigm, bigvv
+
+    # ---------------- scoring: full catalogue, item-sharded across ranks ----------------
+    scoring = None
+    if not args.no_scoring:
+        T_q = N_TEST_USERS
+        bounds = np.linspace(0, N_ITEMS, world + 1).astype(np.int64)
+        lo, hi = int(bounds[rank]), int(bounds[rank + 1])
+        Us, Is, ws_, wus = synth_model(777)  # same model on every rank
+        Us *= 10
+        Is *= 10
+        dU = torch.from_numpy(Us).to(dev)
+        dIt = torch.from_numpy(np.ascontiguousarray(Is[lo:hi])).to(dev)
+        q = torch.from_numpy(np.random.RandomState(5).permutation(N_USERS)[:T_q].astype(np.int32)).to(dev)
+        mrp, mcol = synth_mask(9, T_q, 27)
+        dmrp, dmcol = torch.from_numpy(mrp).to(dev), torch.from_numpy(mcol).to(dev)
+        dw, dwu = torch.from_numpy(ws_).to(dev), torch.from_numpy(wus).to(dev)
+
+        def score_once():
+            Uq = ops.gather_rows(dU, q)
+            si, su = ops.score_gates(dIt, dw), ops.score_gates(Uq, dwu)
+            ids, sc = ops.score_topk(Uq, dIt, si, su, 40.0, dmrp, dmcol, TOPK, item_id_offset=lo)
+            if world > 1:
+                gi = torch.empty((world,) + ids.shape, dtype=ids.dtype, device=dev)
+                gs = torch.empty((world,) + sc.shape, dtype=sc.dtype, device=dev)
+                dist.all_gather_into_tensor(gi, ids)
+                dist.all_gather_into_tensor(gs, sc)
+                ids, sc = ops.topk_merge(gi, gs)
+            return ids, sc
+
+        for _ in range(3):
+            score_once()
+        reps = 10
+        barrier()
+        s0, s1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        s0.record()
+        for _ in range(reps):
+            ids, sc = score_once()
+        s1.record()
+        barrier()
+        t_sc = max_over_ranks(s0.elapsed_time(s1) * 1e-3) / reps
+        scoring = {"metric": "full_catalog_scores_per_sec", "value": T_q * N_ITEMS / t_sc,
+                   "unit": "scores/s", "ms_per_eval": 1e3 * t_sc, "test_users": T_q,
+                   "items": N_ITEMS, "topk": TOPK, "sharding": f"items/{world}",
+                   "gflops": 2.0 * D * T_q * N_ITEMS / t_sc / 1e9,
+                   "checksum": int(ids.to(torch.int64).sum().item())}
+
+    # ---------------- CPU baseline (rank 0, N=1 only) ----------------
+    cpu = None
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        cv, cms, cth = cpu_step_baseline(8)
+        cpu = {"value": cv, "unit": "interactions/s", "cores": cth, "kind": "port",
+               "ms_per_step": cms, "sample": "8 steps of the same B=4096 workload after 1 warm-up step"}
+
+    if rank == 0:
+        line = {
+            "metric": "train_interactions_per_sec", "value": world * BATCH * K / t_flushed,
+            "unit": "interactions/s", "n_gpus": world, "steps": K, "warmup": W,
+            "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": "MACR-MF gowalla-shape U=29858 I=40981 d=64 B=4096 rubibceboth "
+                                   "alpha=1e-2 beta=1e-3 regs=1e-5 lr=1e-3 (BASELINE configs[1])",
+                       "l2": "256 MiB memset between timed steps (tables fit the 126 MB L2)",
+                       "parallelism": "replicas only" if world > 1 else "single GPU",
+                       "batches_resident": nb},
+            "value_back_to_back": world * BATCH * K / t_b2b,
+            "ms_per_step_back_to_back": 1e3 * t_b2b / K,
+            "e2e": {"value": world * BATCH * K / t_e2e, "unit": "interactions/s",
+                    "ms_per_step": 1e3 * t_e2e / K, "h2d_bytes_per_step": 3 * 4 * BATCH,
+                    "d2h_bytes_per_step": 16, "api": "MFTrainer.step_pinned -> macr_mf_trainer_step_host (ids in pinned host memory)"},
+            "gpu_launches": tr.launches_per_step * K,
+            "launches_per_step": tr.launches_per_step,
+            "roofline": roofline, "cpu_baseline": cpu, "scoring": scoring, "clocks": clocks,
+            "final_loss": final_loss,
+        }
+        print(json.dumps(line))
+    tr.close()
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -89,15 +89,22 @@ extern "C" size_t macr_batch_plan_workspace_bytes(int n_ids) { return plan_ws_by
 
 extern "C" int macr_batch_plan(const int32_t *ids, int n_ids, int64_t table_rows,
                                int32_t *uniq_rows, int32_t *seg_off, int32_t *seg_pos,
-                               int32_t *n_uniq, uint32_t *touched_bitmap, void *ws, size_t,
-                               macr_stream_t stream) {
+                               int32_t *n_uniq, uint32_t *touched_bitmap, void *ws,
+                               size_t ws_bytes, macr_stream_t stream) {
   MACR_CHECK_ARG(n_ids > 0 && n_ids <= 16384, "macr_batch_plan: n_ids must be in [1,16384] (got %d)",
                  n_ids);
-  MACR_CHECK_ARG(ids && uniq_rows && seg_off && seg_pos && n_uniq, "macr_batch_plan: null pointer");
-  PlanBufs out{uniq_rows, seg_off, seg_pos, n_uniq};
-  PlanBufs none{nullptr, nullptr, nullptr, nullptr};
-  return launch_batch_plan2(ids, nullptr, 0, n_ids, table_rows, out, touched_bitmap, nullptr, 0, 0,
-                            0, none, nullptr, ws, as_stream(stream));
+  MACR_CHECK_ARG(ids && uniq_rows && seg_off && seg_pos && n_uniq && ws,
+                 "macr_batch_plan: null pointer");
+  if (ws_bytes < plan_ws_bytes(n_ids))
+    return fail(MACR_ERR_WORKSPACE, "macr_batch_plan: workspace %zu < %zu bytes", ws_bytes,
+                plan_ws_bytes(n_ids));
+  cudaStream_t s = as_stream(stream);
+  MACR_CUDA(cudaMemsetAsync(ws, 0, plan_ws_bytes(n_ids), s));  // arrival tickets start at zero
+  PlanBufs out = plan_carve(uniq_rows, seg_off, seg_pos, n_uniq, ws, n_ids);
+  PlanBufs none{};
+  (void)table_rows;
+  return launch_batch_plan2(ids, nullptr, 0, n_ids, out, touched_bitmap, nullptr, 0, 0, none, nullptr,
+                            s);
 }
 
 extern "C" int macr_adam_sweep_untouched(float *var, float *m, float *v, int64_t rows, int d,
@@ -122,8 +129,11 @@ extern "C" int macr_adam_rows(float *var, float *m, float *v, int64_t rows, int 
   MACR_CUDA(cudaMallocAsync(&cnt, sizeof(int32_t) * 2, s));
   MACR_CUDA(cudaMemcpyAsync(cnt, &n_uniq, sizeof(int32_t), cudaMemcpyHostToDevice, s));
   MACR_CUDA(cudaMemsetAsync(cnt + 1, 0, sizeof(int32_t), s));
-  PlanBufs pu{const_cast<int32_t *>(uniq_rows), nullptr, nullptr, cnt};
-  PlanBufs pi{nullptr, nullptr, nullptr, cnt + 1};
+  PlanBufs pu{};
+  pu.uniq_rows = const_cast<int32_t *>(uniq_rows);
+  pu.n_uniq = cnt;
+  PlanBufs pi{};
+  pi.n_uniq = cnt + 1;
   // n_uniq user-slot warps, no item-slot work
   int rc = launch_adam_rows2(var, m, v, pu, grad_rows, touched_bitmap, nullptr, nullptr, nullptr,
                              pi, nullptr, nullptr, n_uniq, lr_t, nullptr, beta1, beta2, eps, s);

@@ -261,7 +261,9 @@ grid_bce_kernel(const float *__restrict__ yp, const float *__restrict__ yn,
 }
 
 // per-b epilogue of the grid: fold the tile partials, finish the chain rule through the three
-// sigmoids, add the alpha / beta branch gradients (model.py:213-217)
+// sigmoids, add the alpha / beta branch gradients (model.py:213-217).
+// 256 threads = 64 batch positions x 4 partial arrays, so the nblk-long folds run 4-wide and
+// coalesced; thread (b, 0) then finishes the scalar math.
 __global__ void __launch_bounds__(256)
 grid_finalize_kernel(const float *__restrict__ sp, const float *__restrict__ sn,
                      const float *__restrict__ su, int B, int Bpad, int nblk, float alpha,
@@ -271,8 +273,28 @@ grid_finalize_kernel(const float *__restrict__ sp, const float *__restrict__ sn,
                      float *__restrict__ d_yn, float *__restrict__ d_sp, float *__restrict__ d_sn,
                      float *__restrict__ d_su, float *__restrict__ litem,
                      float *__restrict__ luser, int want_grad) {
-  const int b = blockIdx.x * blockDim.x + threadIdx.x;
-  if (b >= B) return;
+  __shared__ float sh[4][64];
+  const int bl = threadIdx.x & 63, which = threadIdx.x >> 6;
+  const int b = blockIdx.x * 64 + bl;
+  if (want_grad) {
+    const float *src = which == 0 ? rowP_part : which == 1 ? rowN_part : which == 2 ? colP_part
+                                                                                     : colN_part;
+    float acc = 0.f;
+    if (b < B) {
+      int k = 0;
+      for (; k + 8 <= nblk; k += 8) {
+        float v[8];
+#pragma unroll
+        for (int q = 0; q < 8; ++q) v[q] = src[(size_t)(k + q) * Bpad + b];
+#pragma unroll
+        for (int q = 0; q < 8; ++q) acc += v[q];
+      }
+      for (; k < nblk; ++k) acc += src[(size_t)k * Bpad + b];
+    }
+    sh[which][bl] = acc;
+    __syncthreads();
+  }
+  if (which != 0 || b >= B) return;
   const float a = sigmoid_precise(sp[b]), an = sigmoid_precise(sn[b]),
               g = sigmoid_precise(su[b]);
   const float ea = a + kBceEps, ean = (1.0f - an) + kBceEps;
@@ -280,13 +302,7 @@ grid_finalize_kernel(const float *__restrict__ sp, const float *__restrict__ sn,
   litem[b] = -logf(ea) - logf(ean);
   luser[b] = -logf(eg) - logf(eg1);
   if (!want_grad) return;
-  float rp = 0.f, rn = 0.f, cp = 0.f, cn = 0.f;
-  for (int k = 0; k < nblk; ++k) {
-    rp += rowP_part[(size_t)k * Bpad + b];
-    rn += rowN_part[(size_t)k * Bpad + b];
-    cp += colP_part[(size_t)k * Bpad + b];
-    cn += colN_part[(size_t)k * Bpad + b];
-  }
+  const float rp = sh[0][bl], rn = sh[1][bl], cp = sh[2][bl], cn = sh[3][bl];
   const float invB = 1.0f / (float)B;
   const float invBB = invB * invB;
   d_yp[b] = cp * invBB;
@@ -342,7 +358,7 @@ int launch_grid_bce(const float *yp, const float *yn, const float *sp, const flo
     else launch_grid_t<4, false>(yp, yn, sp, sn, su, B, ws, s);
   }
   MACR_LAUNCH_CHECK();
-  grid_finalize_kernel<<<(B + 255) / 256, 256, 0, s>>>(sp, sn, su, B, ws.Bpad, ws.nblk, alpha,
+  grid_finalize_kernel<<<(B + 63) / 64, 256, 0, s>>>(sp, sn, su, B, ws.Bpad, ws.nblk, alpha,
                                                        beta, ws.rowP, ws.rowN, ws.colP, ws.colN,
                                                        d_yp, d_yn, d_sp, d_sn, d_su, ws.litem,
                                                        ws.luser, want_grad);
@@ -413,128 +429,234 @@ int launch_reduce_losses(const GridWs &ws, const float *regsq, int B, float alph
 }
 
 // ---------------------------------------------------------------------------------------------
-// K5a: batch plan.  One CTA per table sorts (row<<32 | position) keys in shared memory
-// (bitonic network), then marks segment heads and compacts them with a block scan.  The order
-// inside a segment is ascending position, i.e. the order TF's unsorted_segment_sum adds in.
+// K5a: batch plan -- group the batch positions that hit the same table row, deterministically.
+// All-pairs counting instead of a sort (n <= 16384 ids, so n^2 equality tests spread over the
+// whole GPU cost a few microseconds and need no table-sized scratch):
+//   phase 1 (every CTA): 32 positions x 8 sub-lanes; the full id array is staged in shared
+//     memory and each position learns  rank  = #earlier positions with the same row,
+//     total = #positions with the same row,  lead = first position with the same row.
+//   phase 2 (last CTA to finish, per table): positions with rank 0 are segment leaders; one block
+//     scan over the positions gives their slot (first-occurrence order, the order
+//     array_ops.unique produces) and the segment offsets; every position then drops itself at
+//     seg_off[slot] + rank, i.e. ascending position inside a segment -- the order TF's
+//     unsorted_segment_sum adds in.
 // ---------------------------------------------------------------------------------------------
 struct PlanTable {
   const int32_t *ids;
-  int ids_off, n_ids;
-  long long rows;
+  int ids_off, n_ids, blocks;
   PlanBufs out;
   uint32_t *bitmap;
+  int32_t *total, *lead;
+  unsigned *counter;
 };
 
-static int next_pow2(int n) {
-  int p = 1024;
-  while (p < n) p <<= 1;
-  return p;
-}
-size_t plan_ws_bytes(int) { return 16; }
+constexpr int kPlanPos = 128;  // positions per CTA in phase 1 (x 8 sub-lanes = 1024 threads)
 
 __global__ void __launch_bounds__(1024)
-batch_plan_kernel(PlanTable t0, PlanTable t1, const StepState *st, int B, int npow2) {
-  extern __shared__ __align__(16) unsigned long long keys[];
-  __shared__ int warp_tot[32];
-  __shared__ int s_total;
-  const PlanTable t = blockIdx.x == 0 ? t0 : t1;
-  if (t.n_ids == 0) return;
-  const int tid = threadIdx.x;
+batch_plan_kernel(PlanTable t0, PlanTable t1, const StepState *st, int B) {
+  extern __shared__ __align__(16) int32_t sids[];
+  const bool second = (int)blockIdx.x >= t0.blocks;
+  const PlanTable &t = second ? t1 : t0;
+  const int blk = second ? blockIdx.x - t0.blocks : blockIdx.x;
+  const int tid = threadIdx.x, n = t.n_ids;
   const int32_t *ids = (st ? st->ids_base + st->step_idx * 3LL * B : t.ids) + t.ids_off;
-  for (int e = tid; e < npow2; e += 1024)
-    keys[e] = e < t.n_ids
-                  ? (((unsigned long long)(uint32_t)ids[e]) << 32) | (unsigned long long)(uint32_t)e
-                  : ~0ull;
+  const int n4 = (n + 3) >> 2;
+  if ((n & 3) == 0 && (reinterpret_cast<uintptr_t>(ids) & 15) == 0) {
+    const int4 *g4 = reinterpret_cast<const int4 *>(ids);
+    int4 *d4 = reinterpret_cast<int4 *>(sids);
+    for (int e = tid; e < n4; e += 1024) d4[e] = g4[e];
+  } else {
+    for (int e = tid; e < n4 * 4; e += 1024) sids[e] = e < n ? ids[e] : -1;
+  }
   __syncthreads();
-  for (int k = 2; k <= npow2; k <<= 1) {
-    for (int j = k >> 1; j > 0; j >>= 1) {
-      for (int x = tid; x < (npow2 >> 1); x += 1024) {
-        const int i = ((x & ~(j - 1)) << 1) | (x & (j - 1));
-        const int l = i | j;
-        const unsigned long long ka = keys[i], kb = keys[l];
-        const bool up = (i & k) == 0;
-        if ((ka > kb) == up) {
-          keys[i] = kb;
-          keys[l] = ka;
-        }
-      }
-      __syncthreads();
+
+  const int q = blk * kPlanPos + (tid >> 3), sub = tid & 7;
+  const int my = q < n ? sids[q] : -2;
+  int rank = 0, total = 0, lead = 0x7fffffff;
+  const int4 *s4 = reinterpret_cast<const int4 *>(sids);
+#pragma unroll 4
+  for (int i = sub; i < n4; i += 8) {
+    const int4 x = s4[i];
+    if (x.x == my || x.y == my || x.z == my || x.w == my) {  // rare: matches are sparse
+      const int j = 4 * i;
+      const int e0 = x.x == my, e1 = x.y == my, e2 = x.z == my, e3 = x.w == my;
+      total += e0 + e1 + e2 + e3;
+      rank += (e0 & (j < q)) + (e1 & (j + 1 < q)) + (e2 & (j + 2 < q)) + (e3 & (j + 3 < q));
+      const int f = e0 ? j : e1 ? j + 1 : e2 ? j + 2 : j + 3;
+      lead = min(lead, f);
     }
   }
-  // segment heads + compaction
-  const int per = npow2 >> 10;
-  const int e0 = tid * per;
-  int cnt = 0;
-  for (int e = e0; e < e0 + per; ++e) {
-    if (e < t.n_ids) {
-      const uint32_t r = (uint32_t)(keys[e] >> 32);
-      cnt += (e == 0 || r != (uint32_t)(keys[e - 1] >> 32)) ? 1 : 0;
+#pragma unroll
+  for (int o = 1; o < 8; o <<= 1) {
+    rank += __shfl_xor_sync(0xffffffffu, rank, o);
+    total += __shfl_xor_sync(0xffffffffu, total, o);
+    lead = min(lead, __shfl_xor_sync(0xffffffffu, lead, o));
+  }
+  if (sub == 0 && q < n) {
+    t.out.rank[q] = rank;
+    t.total[q] = total;
+    t.lead[q] = lead;
+    if (t.bitmap) atomicOr(&t.bitmap[(uint32_t)my >> 5], 1u << (my & 31));
+  }
+}
+
+// phase 2: one CTA per table.  rank / total / slot / seg_off are staged in shared memory (16-bit:
+// n <= 16384) so the sequential passes every thread makes over its consecutive positions never
+// wait on global memory; everything that touches global memory is coalesced and independent.
+__global__ void __launch_bounds__(1024)
+batch_plan_tail_kernel(PlanTable t0, PlanTable t1, const StepState *st, int B) {
+  extern __shared__ __align__(16) unsigned short sh16[];
+  __shared__ int s_scan[2][32];
+  const PlanTable &t = blockIdx.x == 0 ? t0 : t1;
+  const int tid = threadIdx.x, n = t.n_ids;
+  if (n == 0) return;
+  const int32_t *ids = (st ? st->ids_base + st->step_idx * 3LL * B : t.ids) + t.ids_off;
+  const int npad = ((n + 1023) / 1024) * 1024;
+  unsigned short *rankS = sh16, *totalS = sh16 + npad, *slotS = sh16 + 2 * npad,
+                 *offS = sh16 + 3 * npad;
+  constexpr int kMaxPer = 16;
+  int leadv[kMaxPer], idv[kMaxPer];
+#pragma unroll
+  for (int k = 0; k < kMaxPer; ++k) {
+    const int x = tid + k * 1024;
+    if (x < npad) {
+      rankS[x] = x < n ? (unsigned short)t.out.rank[x] : (unsigned short)1;
+      totalS[x] = x < n ? (unsigned short)t.total[x] : (unsigned short)0;
+      leadv[k] = x < n ? t.lead[x] : 0;
+      idv[k] = x < n ? ids[x] : 0;
     }
   }
-  int incl = cnt;
+  __syncthreads();
+  const int per = npad >> 10;
+  const int q0 = tid * per, q1 = q0 + per;
+  int cntL = 0, sumT = 0;
+  for (int x = q0; x < q1; ++x)
+    if (rankS[x] == 0) {
+      cntL += 1;
+      sumT += totalS[x];
+    }
+  int iL = cntL, iT = sumT;
 #pragma unroll
   for (int o = 1; o < 32; o <<= 1) {
-    const int v = __shfl_up_sync(0xffffffffu, incl, o);
-    if ((tid & 31) >= o) incl += v;
-  }
-  if ((tid & 31) == 31) warp_tot[tid >> 5] = incl;
-  __syncthreads();
-  if (tid < 32) {
-    int v = warp_tot[tid];
-    int inc2 = v;
-#pragma unroll
-    for (int o = 1; o < 32; o <<= 1) {
-      const int y = __shfl_up_sync(0xffffffffu, inc2, o);
-      if (tid >= o) inc2 += y;
+    const int a = __shfl_up_sync(0xffffffffu, iL, o), b = __shfl_up_sync(0xffffffffu, iT, o);
+    if ((tid & 31) >= o) {
+      iL += a;
+      iT += b;
     }
-    warp_tot[tid] = inc2 - v;  // exclusive
-    if (tid == 31) s_total = inc2;
+  }
+  if ((tid & 31) == 31) {
+    s_scan[0][tid >> 5] = iL;
+    s_scan[1][tid >> 5] = iT;
   }
   __syncthreads();
-  int slot = warp_tot[tid >> 5] + incl - cnt;
-  for (int e = e0; e < e0 + per; ++e) {
-    if (e < t.n_ids) {
-      const unsigned long long k = keys[e];
-      const uint32_t r = (uint32_t)(k >> 32);
-      t.out.seg_pos[e] = (int32_t)(uint32_t)k;
-      if (e == 0 || r != (uint32_t)(keys[e - 1] >> 32)) {
-        t.out.uniq_rows[slot] = (int32_t)r;
-        t.out.seg_off[slot] = e;
-        if (t.bitmap) atomicOr(&t.bitmap[r >> 5], 1u << (r & 31));
-        ++slot;
-      }
+  int baseL = 0, baseT = 0, allL = 0;
+#pragma unroll
+  for (int w = 0; w < 32; ++w) {
+    const int a = s_scan[0][w], b = s_scan[1][w];
+    if (w < (tid >> 5)) {
+      baseL += a;
+      baseT += b;
+    }
+    allL += a;
+  }
+  int slot = baseL + iL - cntL, off = baseT + iT - sumT;
+  for (int x = q0; x < q1; ++x)
+    if (rankS[x] == 0) {
+      slotS[x] = (unsigned short)slot;
+      offS[slot] = (unsigned short)off;
+      off += totalS[x];
+      ++slot;
+    }
+  __syncthreads();
+#pragma unroll
+  for (int k = 0; k < kMaxPer; ++k) {
+    const int x = tid + k * 1024;
+    if (x < n) {
+      const int sl = slotS[leadv[k]];
+      const int rk = rankS[x];
+      t.out.pslot[x] = sl;
+      t.out.seg_pos[(int)offS[sl] + rk] = x;
+      if (rk == 0) t.out.uniq_rows[sl] = idv[k];
+    }
+    if (x < allL) {
+      t.out.seg_off[x] = offS[x];
+      t.out.done[x] = 0;
     }
   }
   if (tid == 0) {
-    t.out.seg_off[s_total] = t.n_ids;
-    *t.out.n_uniq = s_total;
+    t.out.seg_off[allL] = n;
+    *t.out.n_uniq = allL;
   }
 }
 
-int plan_init() {  // opt in to 128 KB dynamic shared memory once (outside any stream capture)
+// touched-row bitmaps of both tables straight from the ids (lets the dense sweep start without
+// waiting for the plan)
+__global__ void __launch_bounds__(256)
+mark_touched_kernel(const StepState *st, const int32_t *ids_direct, int B, uint32_t *bmU,
+                    uint32_t *bmI) {
+  const int e = blockIdx.x * blockDim.x + threadIdx.x;
+  if (e >= 3 * B) return;
+  const int32_t *ids = st ? st->ids_base + st->step_idx * 3LL * B : ids_direct;
+  const uint32_t r = (uint32_t)ids[e];
+  atomicOr(&(e < B ? bmU : bmI)[r >> 5], 1u << (r & 31));
+}
+
+int launch_mark_touched(const StepState *st, const int32_t *ids, int B, uint32_t *bmU,
+                        uint32_t *bmI, cudaStream_t s) {
+  mark_touched_kernel<<<(3 * B + 255) / 256, 256, 0, s>>>(st, ids, B, bmU, bmI);
+  MACR_LAUNCH_CHECK();
+  return MACR_OK;
+}
+
+// scratch layout behind PlanBufs (rank, pslot, done) and PlanTable (total, lead, counter)
+size_t plan_ws_bytes(int n_ids) { return sizeof(int32_t) * (5 * (size_t)n_ids + 16); }
+
+int plan_init() {  // opt in to 64 KB dynamic shared memory once (outside any stream capture)
   static bool attr_set = false;
   if (!attr_set) {
     MACR_CUDA(cudaFuncSetAttribute(batch_plan_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                   16384 * 8));
+                                   16384 * 4));
+    MACR_CUDA(cudaFuncSetAttribute(batch_plan_tail_kernel,
+                                   cudaFuncAttributeMaxDynamicSharedMemorySize, 16384 * 8));
     attr_set = true;
   }
   return MACR_OK;
 }
 
+PlanBufs plan_carve(int32_t *uniq_rows, int32_t *seg_off, int32_t *seg_pos, int32_t *n_uniq,
+                    void *ws, int n_ids) {
+  int32_t *p = reinterpret_cast<int32_t *>(ws);
+  PlanBufs b;
+  b.uniq_rows = uniq_rows;
+  b.seg_off = seg_off;
+  b.seg_pos = seg_pos;
+  b.n_uniq = n_uniq;
+  b.rank = p;
+  b.pslot = p + n_ids;
+  b.done = p + 2 * (size_t)n_ids;
+  b.total = p + 3 * (size_t)n_ids;
+  b.lead = p + 4 * (size_t)n_ids;
+  b.counter = reinterpret_cast<unsigned *>(p + 5 * (size_t)n_ids);
+  return b;
+}
+
 int launch_batch_plan2(const int32_t *ids0, const StepState *st, int ids0_off, int n_ids0,
-                       int64_t rows0, PlanBufs out0, uint32_t *bitmap0, const int32_t *ids1,
-                       int ids1_off, int n_ids1, int64_t rows1, PlanBufs out1, uint32_t *bitmap1,
-                       void *, cudaStream_t s) {
+                       PlanBufs out0, uint32_t *bitmap0, const int32_t *ids1, int ids1_off,
+                       int n_ids1, PlanBufs out1, uint32_t *bitmap1, cudaStream_t s) {
   const int nmax = n_ids0 > n_ids1 ? n_ids0 : n_ids1;
   MACR_CHECK_ARG(nmax <= 16384, "batch plan supports at most 16384 ids per table (batch <= 8192)");
-  const int npow2 = next_pow2(nmax);
-  const size_t smem = (size_t)npow2 * sizeof(unsigned long long);
   int rci = plan_init();
   if (rci) return rci;
-  PlanTable t0{ids0, ids0_off, n_ids0, rows0, out0, bitmap0};
-  PlanTable t1{ids1, ids1_off, n_ids1, rows1, out1, bitmap1};
+  PlanTable t0{ids0, ids0_off, n_ids0, (n_ids0 + kPlanPos - 1) / kPlanPos, out0, bitmap0, out0.total, out0.lead,
+               out0.counter};
+  PlanTable t1{ids1, ids1_off, n_ids1, (n_ids1 + kPlanPos - 1) / kPlanPos, out1, bitmap1, out1.total, out1.lead,
+               out1.counter};
+  const size_t smem = (size_t)((nmax + 3) / 4) * 16;
   const int B = st ? n_ids0 : 0;  // trainer convention: table 0 = users (B ids)
-  batch_plan_kernel<<<n_ids1 > 0 ? 2 : 1, 1024, smem, s>>>(t0, t1, st, B, npow2);
+  batch_plan_kernel<<<t0.blocks + t1.blocks, 1024, smem, s>>>(t0, t1, st, B);
+  MACR_LAUNCH_CHECK();
+  const size_t smem2 = (size_t)(((nmax + 1023) / 1024) * 1024) * 8;
+  batch_plan_tail_kernel<<<n_ids1 > 0 ? 2 : 1, 1024, smem2, s>>>(t0, t1, st, B);
   MACR_LAUNCH_CHECK();
   return MACR_OK;
 }
@@ -588,6 +710,11 @@ adam_sweep_kernel(SweepTable t0, SweepTable t1, float lr_or_lrt, const StepState
 #pragma unroll
     for (int k = 0; k < UNROLL; ++k)
       if (live[k]) {
+        // rows never touched so far have m = v = 0: the update is the identity, bit for bit
+        // (m*b1 = 0, v*b2 = 0, var - (lr_t*0)/(0+eps) = var) -> nothing to compute or write
+        const bool zero = mm[k].x == 0.f && mm[k].y == 0.f && mm[k].z == 0.f && mm[k].w == 0.f &&
+                          vv[k].x == 0.f && vv[k].y == 0.f && vv[k].z == 0.f && vv[k].w == 0.f;
+        if (zero) continue;
         adam_decay_only(x[k].x, mm[k].x, vv[k].x, lr_t, b1, b2, eps);
         adam_decay_only(x[k].y, mm[k].y, vv[k].y, lr_t, b1, b2, eps);
         adam_decay_only(x[k].z, mm[k].z, vv[k].z, lr_t, b1, b2, eps);
@@ -617,13 +744,21 @@ int launch_adam_sweep2(float *var0, float *m0, float *v0, int64_t rows0, const u
 }
 
 // ---------------------------------------------------------------------------------------------
-// row gradients of the unique touched rows.  One warp per unique row walks its segment in
-// ascending batch position and sums  d(loss)/d(row)  in registers (lane l owns dims 2l, 2l+1):
+// row gradients of the unique touched rows, summed per table row (the IndexedSlices dedup).
 //   user row r :  sum_b  dyp_b*Ie[p_b] + dyn_b*Ie[n_b] + dsu_b*w_user (+ lam*Ur[r])
 //   item row r :  sum_q  dy_q*Ue[u_b] + ds_q*w (+ lam*Ir[r]),  q<B: pos role, q>=B: neg role
-// and the warp's share of grad(w_user) = (sum dsu)*Ue[r] / grad(w) = (sum ds)*Ie[r].
+// Popular items own segments hundreds of positions long, so the unit of work is <= 32
+// consecutive entries of one segment: the warp launched for position q works only if
+// rank[q] % 32 == 0.  Its lanes fetch the 32 entries' metadata with one coalesced access each,
+// then the row gathers (lane l owns dims 2l, 2l+1) are issued 4 entries at a time.  Segments
+// longer than one unit leave per-unit partials in `unit_part`; the last unit to arrive
+// (per-segment ticket) adds them in unit order, so the sum is order-deterministic.
+// Extra CTAs at the end of the grid reduce grad(w) = sum_b dsp_b*pe_b + dsn_b*ne_b and
+// grad(w_user) = sum_b dsu_b*ue_b into per-CTA partials (fixed composition, fixed order).
 // ---------------------------------------------------------------------------------------------
 constexpr int kRowWarps = 8;
+constexpr int kUnit = 32;
+constexpr int kWgradPerCta = 64;  // batch positions per w-gradient CTA
 
 __global__ void __launch_bounds__(kRowWarps * 32)
 row_grads_kernel(const float *__restrict__ Ue, const float *__restrict__ Ie,
@@ -633,103 +768,158 @@ row_grads_kernel(const float *__restrict__ Ue, const float *__restrict__ Ie,
                  const float *__restrict__ d_yp, const float *__restrict__ d_yn,
                  const float *__restrict__ d_sp, const float *__restrict__ d_sn,
                  const float *__restrict__ d_su, float lam, PlanBufs planU, PlanBufs planI,
-                 float *__restrict__ gU, float *__restrict__ gI, float *__restrict__ gw_part,
-                 float *__restrict__ gwu_part) {
+                 float *__restrict__ gU, float *__restrict__ gI, float *unit_part, int pos_ctas,
+                 float *__restrict__ gw_part, float *__restrict__ gwu_part) {
   __shared__ float2 sW[kRowWarps][32], sWU[kRowWarps][32];
   const int lane = threadIdx.x & 31, wl = threadIdx.x >> 5;
-  const int wid = blockIdx.x * kRowWarps + wl;
   const int32_t *u = step_ids(st, u_, B, 0), *p = step_ids(st, p_, B, 1),
                 *n = step_ids(st, n_, B, 2);
-  float2 cw = make_float2(0.f, 0.f), cwu = make_float2(0.f, 0.f);
-  if (wid < B) {
-    if (wid < *planU.n_uniq) {
-      const long long r = planU.uniq_rows[wid];
-      const int s0 = planU.seg_off[wid], s1 = planU.seg_off[wid + 1];
-      const float2 wuv = reinterpret_cast<const float2 *>(wu)[lane];
-      const float2 raw = reinterpret_cast<const float2 *>(Ur + r * kD)[lane];
-      float2 g = make_float2(0.f, 0.f);
-      float csum = 0.f;
-      for (int e = s0; e < s1; ++e) {
-        const int b = planU.seg_pos[e];
-        const float dyp = d_yp[b], dyn = d_yn[b], dsu = d_su[b];
+
+  if ((int)blockIdx.x >= pos_ctas) {  // ---- grad(w), grad(w_user) partials ----
+    const int cta = blockIdx.x - pos_ctas;
+    float2 aw = make_float2(0.f, 0.f), awu = make_float2(0.f, 0.f);
+    const int b0 = cta * kWgradPerCta + wl * (kWgradPerCta / kRowWarps);
+#pragma unroll 4
+    for (int k = 0; k < kWgradPerCta / kRowWarps; ++k) {
+      const int b = b0 + k;
+      if (b < B) {
+        const float dsp = d_sp[b], dsn = d_sn[b], dsu = d_su[b];
         const float2 pe = reinterpret_cast<const float2 *>(Ie + (long long)p[b] * kD)[lane];
         const float2 ne = reinterpret_cast<const float2 *>(Ie + (long long)n[b] * kD)[lane];
-        float x = dyp * pe.x + dyn * ne.x + dsu * wuv.x;
-        float y = dyp * pe.y + dyn * ne.y + dsu * wuv.y;
-        if (lam != 0.f) {
-          x += lam * raw.x;
-          y += lam * raw.y;
-        }
-        g.x += x;
-        g.y += y;
-        csum += dsu;
-      }
-      reinterpret_cast<float2 *>(gU + (long long)wid * kD)[lane] = g;
-      const float2 ue = reinterpret_cast<const float2 *>(Ue + r * kD)[lane];
-      cwu = make_float2(csum * ue.x, csum * ue.y);
-    }
-  } else {
-    const int wi = wid - B;
-    if (wi < 2 * B && wi < *planI.n_uniq) {
-      const long long r = planI.uniq_rows[wi];
-      const int s0 = planI.seg_off[wi], s1 = planI.seg_off[wi + 1];
-      const float2 wv = reinterpret_cast<const float2 *>(w)[lane];
-      const float2 raw = reinterpret_cast<const float2 *>(Ir + r * kD)[lane];
-      float2 g = make_float2(0.f, 0.f);
-      float csum = 0.f;
-      for (int e = s0; e < s1; ++e) {
-        const int q = planI.seg_pos[e];
-        const bool is_pos = q < B;
-        const int b = is_pos ? q : q - B;
-        const float dy = is_pos ? d_yp[b] : d_yn[b];
-        const float ds = is_pos ? d_sp[b] : d_sn[b];
         const float2 ue = reinterpret_cast<const float2 *>(Ue + (long long)u[b] * kD)[lane];
-        float x = dy * ue.x + ds * wv.x;
-        float y = dy * ue.y + ds * wv.y;
+        aw.x += dsp * pe.x + dsn * ne.x;
+        aw.y += dsp * pe.y + dsn * ne.y;
+        awu.x += dsu * ue.x;
+        awu.y += dsu * ue.y;
+      }
+    }
+    sW[wl][lane] = aw;
+    sWU[wl][lane] = awu;
+    __syncthreads();
+    if (wl == 0) {
+      float2 a = make_float2(0.f, 0.f), c = make_float2(0.f, 0.f);
+#pragma unroll
+      for (int k = 0; k < kRowWarps; ++k) {
+        a.x += sW[k][lane].x;
+        a.y += sW[k][lane].y;
+        c.x += sWU[k][lane].x;
+        c.y += sWU[k][lane].y;
+      }
+      reinterpret_cast<float2 *>(gw_part + (long long)cta * kD)[lane] = a;
+      reinterpret_cast<float2 *>(gwu_part + (long long)cta * kD)[lane] = c;
+    }
+    return;
+  }
+
+  const int wid = blockIdx.x * kRowWarps + wl;  // one warp per batch position: users, then items
+  if (wid >= 3 * B) return;
+  const bool item = wid >= B;
+  const int q = item ? wid - B : wid;
+  const PlanBufs &pl = item ? planI : planU;
+  const int rk = pl.rank[q];
+  if (rk % kUnit != 0) return;
+  const int slot = pl.pslot[q];
+  const int s0 = pl.seg_off[slot], s1 = pl.seg_off[slot + 1];
+  const int total = s1 - s0;
+  const int base = s0 + rk;
+  const int cnt = min(kUnit, s1 - base);
+  const long long r = pl.uniq_rows[slot];
+  const float2 bias = reinterpret_cast<const float2 *>(item ? w : wu)[lane];
+  const float2 raw = reinterpret_cast<const float2 *>((item ? Ir : Ur) + r * kD)[lane];
+  const float lx = lam * raw.x, ly = lam * raw.y;
+
+  // metadata of this unit's entries, one entry per lane
+  int ra = 0, rb = 0;
+  float ca = 0.f, cb = 0.f, cs = 0.f;
+  if (lane < cnt) {
+    const int qq = pl.seg_pos[base + lane];
+    if (!item) {
+      ra = p[qq];
+      rb = n[qq];
+      ca = d_yp[qq];
+      cb = d_yn[qq];
+      cs = d_su[qq];
+    } else {
+      const bool is_pos = qq < B;
+      const int b = is_pos ? qq : qq - B;
+      ra = u[b];
+      ca = is_pos ? d_yp[b] : d_yn[b];
+      cs = is_pos ? d_sp[b] : d_sn[b];
+    }
+  }
+  const float *tabA = item ? Ue : Ie;
+  float2 g = make_float2(0.f, 0.f);
+  for (int e0 = 0; e0 < cnt; e0 += 4) {
+    float2 va[4], vb[4];
+    float fa[4], fb[4], fs[4];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      const int e = min(e0 + k, cnt - 1);
+      const int ia = __shfl_sync(0xffffffffu, ra, e);
+      const int ib = __shfl_sync(0xffffffffu, rb, e);
+      fa[k] = __shfl_sync(0xffffffffu, ca, e);
+      fb[k] = __shfl_sync(0xffffffffu, cb, e);
+      fs[k] = __shfl_sync(0xffffffffu, cs, e);
+      va[k] = reinterpret_cast<const float2 *>(tabA + (long long)ia * kD)[lane];
+      vb[k] = item ? make_float2(0.f, 0.f)
+                   : reinterpret_cast<const float2 *>(Ie + (long long)ib * kD)[lane];
+    }
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      if (e0 + k < cnt) {
+        float x = fa[k] * va[k].x + fb[k] * vb[k].x + fs[k] * bias.x;
+        float y = fa[k] * va[k].y + fb[k] * vb[k].y + fs[k] * bias.y;
         if (lam != 0.f) {
-          x += lam * raw.x;
-          y += lam * raw.y;
+          x += lx;
+          y += ly;
         }
         g.x += x;
         g.y += y;
-        csum += ds;
       }
-      reinterpret_cast<float2 *>(gI + (long long)wi * kD)[lane] = g;
-      const float2 ie = reinterpret_cast<const float2 *>(Ie + r * kD)[lane];
-      cw = make_float2(csum * ie.x, csum * ie.y);
     }
   }
-  sW[wl][lane] = cw;
-  sWU[wl][lane] = cwu;
-  __syncthreads();
-  if (wl == 0) {
-    float2 a = make_float2(0.f, 0.f), c = make_float2(0.f, 0.f);
-#pragma unroll
-    for (int k = 0; k < kRowWarps; ++k) {
-      a.x += sW[k][lane].x;
-      a.y += sW[k][lane].y;
-      c.x += sWU[k][lane].x;
-      c.y += sWU[k][lane].y;
-    }
-    reinterpret_cast<float2 *>(gw_part + (long long)blockIdx.x * kD)[lane] = a;
-    reinterpret_cast<float2 *>(gwu_part + (long long)blockIdx.x * kD)[lane] = c;
+  float *gout = (item ? gI : gU) + (long long)slot * kD;
+  if (total <= kUnit) {
+    reinterpret_cast<float2 *>(gout)[lane] = g;
+    return;
   }
+  // multi-unit segment: publish the partial, the last unit to arrive folds them in unit order
+  float *mypart = unit_part + ((long long)(item ? B : 0) + q) * kD;
+  reinterpret_cast<float2 *>(mypart)[lane] = g;
+  __threadfence();
+  int ticket = 0;
+  if (lane == 0) ticket = atomicAdd(&pl.done[slot], 1);
+  ticket = __shfl_sync(0xffffffffu, ticket, 0);
+  const int n_units = (total + kUnit - 1) / kUnit;
+  if (ticket != n_units - 1) return;
+  __threadfence();
+  float2 acc = make_float2(0.f, 0.f);
+  for (int k = 0; k < n_units; ++k) {
+    const int qk = pl.seg_pos[s0 + k * kUnit];
+    const float2 v = __ldcg(reinterpret_cast<const float2 *>(
+                                unit_part + ((long long)(item ? B : 0) + qk) * kD) + lane);
+    acc.x += v.x;
+    acc.y += v.y;
+  }
+  reinterpret_cast<float2 *>(gout)[lane] = acc;
 }
 
-int row_grads_max_parts(int B) { return (3 * B + kRowWarps - 1) / kRowWarps; }
+int row_grads_max_parts(int B) { return (B + kWgradPerCta - 1) / kWgradPerCta; }
 
 int launch_row_grads(const float *Ue, const float *Ie, const float *Ur, const float *Ir,
                      const float *w, const float *wu, const StepState *st, const int32_t *u,
                      const int32_t *p, const int32_t *n, int B, const float *d_yp,
                      const float *d_yn, const float *d_sp, const float *d_sn, const float *d_su,
                      float lam, PlanBufs planU, PlanBufs planI, float *gU, float *gI,
-                     float *gw_part, float *gwu_part, int *n_part, cudaStream_t s) {
-  const int blocks = row_grads_max_parts(B);
-  row_grads_kernel<<<blocks, kRowWarps * 32, 0, s>>>(Ue, Ie, Ur, Ir, w, wu, st, u, p, n, B, d_yp,
-                                                     d_yn, d_sp, d_sn, d_su, lam, planU, planI, gU,
-                                                     gI, gw_part, gwu_part);
+                     float *unit_part, float *gw_part, float *gwu_part, int *n_part,
+                     cudaStream_t s) {
+  const int pos_ctas = (3 * B + kRowWarps - 1) / kRowWarps;
+  const int w_ctas = row_grads_max_parts(B);
+  row_grads_kernel<<<pos_ctas + w_ctas, kRowWarps * 32, 0, s>>>(
+      Ue, Ie, Ur, Ir, w, wu, st, u, p, n, B, d_yp, d_yn, d_sp, d_sn, d_su, lam, planU, planI, gU,
+      gI, unit_part, pos_ctas, gw_part, gwu_part);
   MACR_LAUNCH_CHECK();
-  if (n_part) *n_part = blocks;
+  if (n_part) *n_part = w_ctas;
   return MACR_OK;
 }
 
@@ -866,6 +1056,103 @@ __global__ void step_advance_kernel(StepState *st, float b1, float b2, int train
 
 int launch_step_state(StepState *st, int, float, float b1, float b2, int train, cudaStream_t s) {
   step_advance_kernel<<<1, 32, 0, s>>>(st, b1, b2, train);
+  MACR_LAUNCH_CHECK();
+  return MACR_OK;
+}
+
+// ---------------------------------------------------------------------------------------------
+// last kernel of a step (one CTA): ApplyAdam on w / w_user from the per-CTA gradient partials,
+// the loss reduction, and the step-state advance (adam.py _finish: beta powers *= beta).
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(1024)
+step_tail_kernel(float *w, float *mw, float *vw, float *wu, float *mwu, float *vwu,
+                 const float *__restrict__ gw_part, const float *__restrict__ gwu_part, int n_part,
+                 const float *__restrict__ losspart, int nparts, const float *__restrict__ litem,
+                 const float *__restrict__ luser, const float *__restrict__ regsq, int B,
+                 macr_hparams hp, StepState *st, int train) {
+  __shared__ double sh[1024];
+  __shared__ float shg[2][8][kD];
+  const int tid = threadIdx.x;
+  const float lr_t = step_lr_t(st, hp.lr);
+  if (train) {
+    const int k = tid & 63, which = (tid >> 6) & 1, grp = tid >> 7;  // 8 groups x 2 vectors x 64
+    const float *src = which ? gwu_part : gw_part;
+    float a = 0.f;
+    for (int q = grp; q < n_part; q += 8) a += src[(long long)q * kD + k];
+    shg[which][grp][k] = a;
+  }
+  double a0 = 0, a1 = 0, a2 = 0, a3 = 0;
+  for (int k = tid; k < nparts; k += 1024) a0 += losspart[k];
+  for (int k = tid; k < B; k += 1024) {
+    a1 += litem[k];
+    a2 += luser[k];
+    a3 += regsq[k];
+  }
+  // one fixed-shape reduction tree for the four sums: warp shuffles, then the 32 warp leaders
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    a0 += __shfl_xor_sync(0xffffffffu, a0, o);
+    a1 += __shfl_xor_sync(0xffffffffu, a1, o);
+    a2 += __shfl_xor_sync(0xffffffffu, a2, o);
+    a3 += __shfl_xor_sync(0xffffffffu, a3, o);
+  }
+  if ((tid & 31) == 0) {
+    sh[(tid >> 5) * 4 + 0] = a0;
+    sh[(tid >> 5) * 4 + 1] = a1;
+    sh[(tid >> 5) * 4 + 2] = a2;
+    sh[(tid >> 5) * 4 + 3] = a3;
+  }
+  __syncthreads();  // also publishes shg
+  if (tid == 0) {
+    a0 = a1 = a2 = a3 = 0;
+    for (int k = 0; k < 32; ++k) {
+      a0 += sh[k * 4 + 0];
+      a1 += sh[k * 4 + 1];
+      a2 += sh[k * 4 + 2];
+      a3 += sh[k * 4 + 3];
+    }
+  }
+  if (train && tid < 2 * kD) {
+    const int k = tid & 63, which = tid >> 6;
+    float g = 0.f;
+#pragma unroll
+    for (int q = 0; q < 8; ++q) g += shg[which][q][k];
+    const float omb1 = __fsub_rn(1.0f, hp.beta1), omb2 = __fsub_rn(1.0f, hp.beta2);
+    float *var = which ? wu : w, *m = which ? mwu : mw, *v = which ? vwu : vw;
+    const float mn = __fadd_rn(m[k], __fmul_rn(__fsub_rn(g, m[k]), omb1));
+    const float vn = __fadd_rn(v[k], __fmul_rn(__fsub_rn(__fmul_rn(g, g), v[k]), omb2));
+    m[k] = mn;
+    v[k] = vn;
+    var[k] = __fsub_rn(var[k], __fdiv_rn(__fmul_rn(mn, lr_t), __fadd_rn(__fsqrt_rn(vn), hp.eps)));
+  }
+  __syncthreads();  // every lr_t read of this step is done
+  if (tid == 0) {
+    const double invB = 1.0 / (double)B;
+    const float l_ori = (float)(-0.6931471805599453 * a0 * invB * invB);
+    const float l_item = (float)(a1 * invB), l_user = (float)(a2 * invB);
+    const float reg = hp.decay * ((float)(a3 * 0.5) / (float)hp.batch_size_flag);
+    const float mf = l_ori + hp.alpha * l_item + hp.beta * l_user;
+    float *out = st->loss_base + st->step_idx * 4;
+    out[0] = mf + reg;
+    out[1] = mf;
+    out[2] = reg;
+    out[3] = l_ori;
+    if (train) {
+      st->b1p = __fmul_rn(st->b1p, hp.beta1);
+      st->b2p = __fmul_rn(st->b2p, hp.beta2);
+      st->t += 1;
+    }
+    st->step_idx += 1;
+  }
+}
+
+int launch_step_tail(float *w, float *mw, float *vw, float *wu, float *mwu, float *vwu,
+                     const float *gw_part, const float *gwu_part, int n_part, const GridWs &ws,
+                     const float *regsq, int B, const macr_hparams &hp, StepState *st, int train,
+                     cudaStream_t s) {
+  step_tail_kernel<<<1, 1024, 0, s>>>(w, mw, vw, wu, mwu, vwu, gw_part, gwu_part, n_part,
+                                      ws.losspart, ws.nblk * ws.nblk, ws.litem, ws.luser, regsq, B,
+                                      hp, st, train);
   MACR_LAUNCH_CHECK();
   return MACR_OK;
 }

@@ -31,9 +31,19 @@ struct GridWs {  // carve-up of the grid kernel's partial-sum workspace
 };
 GridWs grid_ws_layout(int B, void *base);
 
-struct PlanBufs {  // output of one batch_plan over n_ids ids
-  int32_t *uniq_rows, *seg_off, *seg_pos, *n_uniq;
+struct PlanBufs {  // output of one batch_plan over n_ids ids (+ its scratch)
+  int32_t *uniq_rows;  // [n_uniq] table row of every segment, first-occurrence order
+  int32_t *seg_off;    // [n_uniq+1]
+  int32_t *seg_pos;    // [n_ids] batch positions, ascending inside a segment
+  int32_t *n_uniq;     // device scalar
+  int32_t *rank;       // [n_ids] rank of a position inside its segment
+  int32_t *pslot;      // [n_ids] segment index of a position
+  int32_t *done;       // [n_ids] per-segment arrival counters (multi-unit segments)
+  int32_t *total, *lead;  // [n_ids] scratch of the planning kernel
+  unsigned *counter;      // last-CTA-done ticket
 };
+PlanBufs plan_carve(int32_t *uniq_rows, int32_t *seg_off, int32_t *seg_pos, int32_t *n_uniq,
+                    void *ws, int n_ids);
 
 // launchers (all asynchronous on `s`); *_st variants read ids / lr_t through StepState
 int launch_step_state(StepState *st, int B, float lr, float b1, float b2, int train,
@@ -55,9 +65,10 @@ size_t plan_ws_bytes(int n_ids);
 int plan_init();
 // two tables in one launch (table 1 optional: n_ids1 == 0)
 int launch_batch_plan2(const int32_t *ids0, const StepState *st0, int ids0_off, int n_ids0,
-                       int64_t rows0, PlanBufs out0, uint32_t *bitmap0, const int32_t *ids1,
-                       int ids1_off, int n_ids1, int64_t rows1, PlanBufs out1, uint32_t *bitmap1,
-                       void *ws, cudaStream_t s);
+                       PlanBufs out0, uint32_t *bitmap0, const int32_t *ids1, int ids1_off,
+                       int n_ids1, PlanBufs out1, uint32_t *bitmap1, cudaStream_t s);
+int launch_mark_touched(const StepState *st, const int32_t *ids, int B, uint32_t *bmU,
+                        uint32_t *bmI, cudaStream_t s);
 int launch_adam_sweep2(float *var0, float *m0, float *v0, int64_t rows0, const uint32_t *bm0,
                        float *var1, float *m1, float *v1, int64_t rows1, const uint32_t *bm1,
                        float lr_t, const StepState *st, float b1, float b2, float eps,
@@ -69,7 +80,8 @@ int launch_row_grads(const float *Ue, const float *Ie, const float *Ur, const fl
                      const int32_t *p, const int32_t *n, int B, const float *d_yp,
                      const float *d_yn, const float *d_sp, const float *d_sn, const float *d_su,
                      float lam, PlanBufs planU, PlanBufs planI, float *gU, float *gI,
-                     float *gw_part, float *gwu_part, int *n_part, cudaStream_t s);
+                     float *unit_part, float *gw_part, float *gwu_part, int *n_part,
+                     cudaStream_t s);
 int launch_adam_rows2(float *U, float *mU, float *vU, PlanBufs planU, const float *gU,
                       uint32_t *bmU, float *I, float *mI, float *vI, PlanBufs planI,
                       const float *gI, uint32_t *bmI, int max_rows, float lr_t,
@@ -77,6 +89,11 @@ int launch_adam_rows2(float *U, float *mU, float *vU, PlanBufs planU, const floa
 int launch_adam_vec2(float *w, float *mw, float *vw, float *wu, float *mwu, float *vwu,
                      const float *gw_part, const float *gwu_part, int n_part, float lr_t,
                      const StepState *st, float b1, float b2, float eps, cudaStream_t s);
+// last kernel of a step: ApplyAdam on w / w_user (train), loss reduction, state advance
+int launch_step_tail(float *w, float *mw, float *vw, float *wu, float *mwu, float *vwu,
+                     const float *gw_part, const float *gwu_part, int n_part, const GridWs &ws,
+                     const float *regsq, int B, const macr_hparams &hp, StepState *st, int train,
+                     cudaStream_t s);
 int launch_adam_dense(float *var, float *m, float *v, const float *grad, int64_t n_elems,
                       float lr_t, const StepState *st, float b1, float b2, float eps,
                       cudaStream_t s);

@@ -39,9 +39,9 @@ struct TrainerBase {
   int maxB;
   macr_hparams hp;
   cudaStream_t s;         // caller's stream: graphs are launched here
-  cudaStream_t cs, side;  // private streams the step DAG is captured on (the legacy default
+  cudaStream_t cs, side, side2;  // private streams the step DAG is captured on (the legacy default
                           // stream cannot be captured)
-  cudaEvent_t ev_fork, ev_join;
+  cudaEvent_t ev_fork, ev_join, ev_join2;
   StepState *st;
   int32_t *ids_stage;
   float *loss_stage;
@@ -49,7 +49,7 @@ struct TrainerBase {
   void *gridws;
   PlanBufs planU, planI;
   int32_t *plan_mem;
-  float *gU, *gI, *gw_part, *gwu_part;
+  float *gU, *gI, *gw_part, *gwu_part, *unit_part;
   float *pinned_losses;
   int64_t steps_done;
   const int32_t *cur_ids_base;
@@ -66,6 +66,8 @@ struct TrainerBase {
     if (rci) return rci;
     MACR_CUDA(cudaStreamCreateWithFlags(&cs, cudaStreamNonBlocking));
     MACR_CUDA(cudaStreamCreateWithFlags(&side, cudaStreamNonBlocking));
+    MACR_CUDA(cudaStreamCreateWithFlags(&side2, cudaStreamNonBlocking));
+    MACR_CUDA(cudaEventCreateWithFlags(&ev_join2, cudaEventDisableTiming));
     MACR_CUDA(cudaEventCreateWithFlags(&ev_fork, cudaEventDisableTiming));
     MACR_CUDA(cudaEventCreateWithFlags(&ev_join, cudaEventDisableTiming));
     MACR_CUDA(cudaMalloc(&st, sizeof(StepState)));
@@ -74,19 +76,28 @@ struct TrainerBase {
     MACR_CUDA(cudaMalloc(&loss_stage, sizeof(float) * 4));
     MACR_CUDA(cudaMalloc(&scal, sizeof(float) * 11 * (size_t)maxB));
     MACR_CUDA(cudaMalloc(&gridws, grid_ws_layout(maxB, nullptr).bytes + 4096));
-    // plan buffers: users (B) + items (2B): uniq, seg_off(+1), seg_pos, n_uniq
-    const size_t pm = (size_t)maxB * 3 + ((size_t)maxB + 1) + (size_t)maxB * 3 + 2 * (size_t)maxB +
-                      (2 * (size_t)maxB + 1) + 8;
-    MACR_CUDA(cudaMalloc(&plan_mem, sizeof(int32_t) * pm));
-    int32_t *p = plan_mem;
-    planU.uniq_rows = p; p += maxB;
-    planU.seg_off = p; p += maxB + 1;
-    planU.seg_pos = p; p += maxB;
-    planU.n_uniq = p; p += 1;
-    planI.uniq_rows = p; p += 2 * maxB;
-    planI.seg_off = p; p += 2 * maxB + 1;
-    planI.seg_pos = p; p += 2 * maxB;
-    planI.n_uniq = p; p += 1;
+    // plan buffers: users (B ids) + items (2B ids): uniq, seg_off(+1), seg_pos, n_uniq + scratch
+    const size_t pm = (size_t)maxB * 3 + 8 + (size_t)maxB * 6 + 8;
+    MACR_CUDA(cudaMalloc(&plan_mem, sizeof(int32_t) * pm + plan_ws_bytes(maxB) +
+                                        plan_ws_bytes(2 * maxB)));
+    MACR_CUDA(cudaMemset(plan_mem, 0, sizeof(int32_t) * pm + plan_ws_bytes(maxB) +
+                                          plan_ws_bytes(2 * maxB)));
+    {
+      int32_t *p = plan_mem;
+      int32_t *uU = p; p += maxB;
+      int32_t *oU = p; p += maxB + 1;
+      int32_t *sU = p; p += maxB;
+      int32_t *nU = p; p += 1;
+      int32_t *uI = p; p += 2 * maxB;
+      int32_t *oI = p; p += 2 * maxB + 1;
+      int32_t *sI = p; p += 2 * maxB;
+      int32_t *nI = p; p += 1;
+      p = plan_mem + pm;
+      planU = plan_carve(uU, oU, sU, nU, p, maxB);
+      planI = plan_carve(uI, oI, sI, nI, reinterpret_cast<char *>(p) + plan_ws_bytes(maxB),
+                         2 * maxB);
+    }
+    MACR_CUDA(cudaMalloc(&unit_part, sizeof(float) * kD * 3 * (size_t)maxB));
     MACR_CUDA(cudaMalloc(&gU, sizeof(float) * kD * (size_t)maxB));
     MACR_CUDA(cudaMalloc(&gI, sizeof(float) * kD * 2 * (size_t)maxB));
     const int parts = row_grads_max_parts(maxB);
@@ -106,10 +117,12 @@ struct TrainerBase {
     for (auto &kv : graphs) cudaGraphExecDestroy(kv.second);
     for (auto &kv : graphs_eval) cudaGraphExecDestroy(kv.second);
     cudaFree(st); cudaFree(ids_stage); cudaFree(loss_stage); cudaFree(scal); cudaFree(gridws);
-    cudaFree(plan_mem); cudaFree(gU); cudaFree(gI); cudaFree(gw_part); cudaFree(gwu_part);
+    cudaFree(plan_mem); cudaFree(unit_part); cudaFree(gU); cudaFree(gI); cudaFree(gw_part); cudaFree(gwu_part);
     cudaFreeHost(pinned_losses);
     cudaEventDestroy(ev_fork); cudaEventDestroy(ev_join);
+    cudaEventDestroy(ev_join2);
     cudaStreamDestroy(side);
+    cudaStreamDestroy(side2);
     cudaStreamDestroy(cs);
   }
 
@@ -155,17 +168,22 @@ static int mf_enqueue(macr_mf_trainer *h, int B) {
   const GridWs g = grid_ws_layout(B, h->gridws);
   int rc;
   int launches = 0;
-  // fork: plan + dense sweep need only the ids and the step state
+  // fork: the plan and the dense sweep need only the ids and the step state
+  cudaStream_t side2 = h->side2;
   MACR_CUDA(cudaEventRecord(h->ev_fork, s));
   MACR_CUDA(cudaStreamWaitEvent(side, h->ev_fork, 0));
-  rc = launch_batch_plan2(nullptr, h->st, 0, B, h->nu, h->planU, h->bmU, nullptr, B, 2 * B, h->ni,
-                          h->planI, h->bmI, nullptr, side);
-  if (rc) return rc;
-  rc = launch_adam_sweep2(h->U, h->mU, h->vU, h->nu, h->bmU, h->I, h->mI, h->vI, h->ni, h->bmI,
-                          hp.lr, h->st, hp.beta1, hp.beta2, hp.eps, side);
+  MACR_CUDA(cudaStreamWaitEvent(side2, h->ev_fork, 0));
+  rc = launch_batch_plan2(nullptr, h->st, 0, B, h->planU, nullptr, nullptr, B, 2 * B, h->planI,
+                          nullptr, side);
   if (rc) return rc;
   MACR_CUDA(cudaEventRecord(h->ev_join, side));
-  launches += 2;
+  rc = launch_mark_touched(h->st, nullptr, B, h->bmU, h->bmI, side2);
+  if (rc) return rc;
+  rc = launch_adam_sweep2(h->U, h->mU, h->vU, h->nu, h->bmU, h->I, h->mI, h->vI, h->ni, h->bmI,
+                          hp.lr, h->st, hp.beta1, hp.beta2, hp.eps, side2);
+  if (rc) return rc;
+  MACR_CUDA(cudaEventRecord(h->ev_join2, side2));
+  launches += 4;
   // main: gather -> grid -> finalize
   rc = launch_gather_dots(h->U, h->I, h->U, h->I, h->w, h->wu, nullptr, nullptr, nullptr, h->st, B,
                           yp, yn, sp, sn, su, rq, s);
@@ -174,24 +192,20 @@ static int mf_enqueue(macr_mf_trainer *h, int B) {
   if (rc) return rc;
   launches += 3;
   MACR_CUDA(cudaStreamWaitEvent(s, h->ev_join, 0));
+  MACR_CUDA(cudaStreamWaitEvent(s, h->ev_join2, 0));
   const float lam = hp.decay / (float)hp.batch_size_flag;
   int n_part = 0;
   rc = launch_row_grads(h->U, h->I, h->U, h->I, h->w, h->wu, h->st, nullptr, nullptr, nullptr, B,
-                        dyp, dyn, dsp, dsn, dsu, lam, h->planU, h->planI, h->gU, h->gI, h->gw_part,
-                        h->gwu_part, &n_part, s);
+                        dyp, dyn, dsp, dsn, dsu, lam, h->planU, h->planI, h->gU, h->gI, h->unit_part,
+                        h->gw_part, h->gwu_part, &n_part, s);
   if (rc) return rc;
   rc = launch_adam_rows2(h->U, h->mU, h->vU, h->planU, h->gU, h->bmU, h->I, h->mI, h->vI, h->planI,
                          h->gI, h->bmI, B, hp.lr, h->st, hp.beta1, hp.beta2, hp.eps, s);
   if (rc) return rc;
-  rc = launch_adam_vec2(h->w, h->mw, h->vw, h->wu, h->mwu, h->vwu, h->gw_part, h->gwu_part, n_part,
-                        hp.lr, h->st, hp.beta1, hp.beta2, hp.eps, s);
+  rc = launch_step_tail(h->w, h->mw, h->vw, h->wu, h->mwu, h->vwu, h->gw_part, h->gwu_part, n_part,
+                        g, rq, B, hp, h->st, 1, s);
   if (rc) return rc;
-  rc = launch_reduce_losses(g, rq, B, hp.alpha, hp.beta, hp.decay, hp.batch_size_flag, nullptr,
-                            h->st, s);
-  if (rc) return rc;
-  rc = launch_step_state(h->st, B, hp.lr, hp.beta1, hp.beta2, 1, s);
-  if (rc) return rc;
-  launches += 5;
+  launches += 3;
   h->launches = launches;
   return MACR_OK;
 }
@@ -381,12 +395,12 @@ static int lgcn_enqueue_impl(macr_lgcn_trainer *h, int B, int train) {
   if (train) {
     MACR_CUDA(cudaEventRecord(h->ev_fork, s));
     MACR_CUDA(cudaStreamWaitEvent(side, h->ev_fork, 0));
-    rc = launch_batch_plan2(nullptr, h->st, 0, B, h->nu, h->planU, nullptr, nullptr, B, 2 * B,
-                            h->ni, h->planI, nullptr, nullptr, side);
+    rc = launch_batch_plan2(nullptr, h->st, 0, B, h->planU, nullptr, nullptr, B, 2 * B, h->planI,
+                            nullptr, side);
     if (rc) return rc;
     MACR_CUDA(cudaMemsetAsync(h->g3, 0, sizeof(float) * N * kD, side));
     MACR_CUDA(cudaEventRecord(h->ev_join, side));
-    launches += 1;
+    launches += 2;
   }
   rc = launch_lgcn_propagate(h->rowptr, h->col, h->val, h->U, h->nu, h->I, h->ni, h->L, h->Emean,
                              h->tmp, s);
@@ -403,8 +417,8 @@ static int lgcn_enqueue_impl(macr_lgcn_trainer *h, int B, int train) {
     MACR_CUDA(cudaStreamWaitEvent(s, h->ev_join, 0));
     int n_part = 0;
     rc = launch_row_grads(Ue, Ie, h->U, h->I, h->w, h->wu, h->st, nullptr, nullptr, nullptr, B, dyp,
-                          dyn, dsp, dsn, dsu, 0.f, h->planU, h->planI, h->gU, h->gI, h->gw_part,
-                          h->gwu_part, &n_part, s);
+                          dyn, dsp, dsn, dsu, 0.f, h->planU, h->planI, h->gU, h->gI, h->unit_part,
+                          h->gw_part, h->gwu_part, &n_part, s);
     if (rc) return rc;
     rc = launch_scatter_rows(h->planU, h->gU, h->planI, h->gI, B, h->nu, (float)(h->L + 1), h->g3,
                              s);
@@ -430,17 +444,16 @@ static int lgcn_enqueue_impl(macr_lgcn_trainer *h, int B, int train) {
     rc = launch_adam_dense(h->I, h->mI, h->vI, grad + h->nu * kD, h->ni * kD, hp.lr, h->st,
                            hp.beta1, hp.beta2, hp.eps, s);
     if (rc) return rc;
-    rc = launch_adam_vec2(h->w, h->mw, h->vw, h->wu, h->mwu, h->vwu, h->gw_part, h->gwu_part,
-                          n_part, hp.lr, h->st, hp.beta1, hp.beta2, hp.eps, s);
+    launches += 3;
+    rc = launch_step_tail(h->w, h->mw, h->vw, h->wu, h->mwu, h->vwu, h->gw_part, h->gwu_part,
+                          n_part, g, rq, B, hp, h->st, 1, s);
     if (rc) return rc;
-    launches += 4;
+  } else {
+    rc = launch_step_tail(h->w, h->mw, h->vw, h->wu, h->mwu, h->vwu, h->gw_part, h->gwu_part, 0,
+                          g, rq, B, hp, h->st, 0, s);
+    if (rc) return rc;
   }
-  rc = launch_reduce_losses(g, rq, B, hp.alpha, hp.beta, hp.decay, hp.batch_size_flag, nullptr,
-                            h->st, s);
-  if (rc) return rc;
-  rc = launch_step_state(h->st, B, hp.lr, hp.beta1, hp.beta2, train, s);
-  if (rc) return rc;
-  launches += 2;
+  launches += 1;
   if (train) h->launches = launches;
   return MACR_OK;
 }

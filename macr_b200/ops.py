@@ -71,8 +71,11 @@ def batch_plan(ids, table_rows, bitmap=None):
     seg_off = torch.empty(n + 1, dtype=torch.int32, device=dev)
     seg_pos = torch.empty(n, dtype=torch.int32, device=dev)
     n_uniq = torch.zeros(1, dtype=torch.int32, device=dev)
+    nbytes = lib().macr_batch_plan_workspace_bytes(n)
+    ws = torch.empty(nbytes, dtype=torch.uint8, device=dev)
     check(lib().macr_batch_plan(_i(ids), n, table_rows, ptr(uniq), ptr(seg_off), ptr(seg_pos),
-                                ptr(n_uniq), ptr(bitmap), None, 0, stream_ptr()), "macr_batch_plan")
+                                ptr(n_uniq), ptr(bitmap), ptr(ws), nbytes, stream_ptr()),
+          "macr_batch_plan")
     k = int(n_uniq.item())
     return uniq[:k], seg_off[: k + 1], seg_pos
 
@@ -239,6 +242,15 @@ class MFTrainer:
         buf[B:2 * B] = pos
         buf[2 * B:3 * B] = neg
         base = self._pin_ids.data_ptr()
+        check(lib().macr_mf_trainer_step_host(self._h, C.c_void_p(base), C.c_void_p(base + 4 * B),
+                                              C.c_void_p(base + 8 * B), B, self._host_loss),
+              "macr_mf_trainer_step_host")
+        return float(self._host_loss[0]), float(self._host_loss[1]), float(self._host_loss[2])
+
+    def step_pinned(self, ids3):
+        """ids3: pinned host int32 tensor [3,B] (users | pos | neg). Returns (loss, mf, reg)."""
+        B = ids3.shape[1]
+        base = ids3.data_ptr()
         check(lib().macr_mf_trainer_step_host(self._h, C.c_void_p(base), C.c_void_p(base + 4 * B),
                                               C.c_void_p(base + 8 * B), B, self._host_loss),
               "macr_mf_trainer_step_host")

@@ -72,7 +72,8 @@ def test_batch_plan(T, ops, n_ids, rows):
     bitmap = T.zeros((rows + 31) // 32, dtype=T.int32, device="cuda")
     uniq, seg_off, seg_pos = ops.batch_plan(dev(T, ids), rows, bitmap.view(T.int32))
     uniq, seg_off, seg_pos = uniq.cpu().numpy(), seg_off.cpu().numpy(), seg_pos.cpu().numpy()
-    want_uniq = np.unique(ids)
+    _, first = np.unique(ids, return_index=True)
+    want_uniq = ids[np.sort(first)]  # first-occurrence order, like array_ops.unique
     np.testing.assert_array_equal(uniq, want_uniq)
     assert seg_off[0] == 0 and seg_off[-1] == n_ids
     for k, r in enumerate(want_uniq):
@@ -80,7 +81,7 @@ def test_batch_plan(T, ops, n_ids, rows):
         np.testing.assert_array_equal(pos, np.nonzero(ids == r)[0])  # ascending positions
     bits = np.unpackbits(bitmap.cpu().numpy().view(np.uint8), bitorder="little")[:rows]
     want_bits = np.zeros(rows, np.uint8)
-    want_bits[want_uniq] = 1
+    want_bits[np.unique(ids)] = 1
     np.testing.assert_array_equal(bits, want_bits)
 
 
@@ -93,7 +94,7 @@ def test_adam_kernels_bit_exact(T, ops, oracle):
     v = (rng.rand(rows, d).astype(np.float32)) * 1e-5
     m[::7] = 0
     v[::7] = 0
-    idx = np.unique(rng.randint(0, rows, 500)).astype(np.int32)
+    idx = rng.permutation(np.unique(rng.randint(0, rows, 500))).astype(np.int32)
     g = rng.randn(len(idx), d).astype(np.float32) * 1e-3
     lr_t = oracle.adam_lr_t(1e-3, 0.9 ** 5, 0.999 ** 5)
     ov, om, ovv = var.copy(), m.copy(), v.copy()
