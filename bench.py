@@ -123,6 +123,15 @@ def measured_peaks():
     return {"hbm_gbs": 6650.0, "bf16_tflops": 1590.0}, "fallback"
 
 
+def ncu_traffic(kernel):
+    """dram bytes per launch of `kernel` from the committed `ncu --set full` summary."""
+    p = os.path.join(ROOT, "profiles", "ncu_traffic.json")
+    if os.path.exists(p):
+        with open(p) as f:
+            return json.load(f).get(kernel, {}).get("dram_bytes_per_launch")
+    return None
+
+
 def cpu_step_baseline(steps, threads=None):
     """oracle port of the step on the host cores; bounded sample of the same workload."""
     import oracle
@@ -269,33 +278,60 @@ def main():
     peaks, peak_kind = measured_peaks()
     rows = N_USERS + N_ITEMS
     sweep_bytes = 24.0 * D * rows
-    # steady-state tables: every row has non-zero Adam moments (no all-zero-row shortcut)
-    bigv = torch.randn((rows, D), dtype=torch.float32, device=dev) * 0.05
-    bigm = torch.randn((rows, D), dtype=torch.float32, device=dev) * 1e-4
-    bigvv = torch.rand((rows, D), dtype=torch.float32, device=dev) * 1e-7 + 1e-9
-    n_sw = 30
-    sw_ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(n_sw)]
-    for _ in range(3):
-        ops.adam_sweep_untouched(bigv, bigm, bigvv, None, 1e-4)
-    for k in range(n_sw):
-        flush.zero_()
-        sw_ev[k][0].record()
-        ops.adam_sweep_untouched(bigv, bigm, bigvv, None, 1e-4)
-        sw_ev[k][1].record()
+    # steady-state tables: every row has non-zero Adam moments (no all-zero-row shortcut).
+    # NSETS independent (var, m, v) sets, 6 x 54 MB = 326 MB > the 126 MB L2, swept round-robin
+    # between ONE pair of events: every launch finds its operands evicted (inputs larger than
+    # L2), and no per-launch event / launch-gap overhead is folded into an 18 us kernel.
+    NSETS, ROUNDS = 6, 10
+    sets = []
+    for _ in range(NSETS):
+        sets.append((torch.randn((rows, D), dtype=torch.float32, device=dev) * 0.05,
+                     torch.randn((rows, D), dtype=torch.float32, device=dev) * 1e-4,
+                     torch.rand((rows, D), dtype=torch.float32, device=dev) * 1e-7 + 1e-9))
+    side = torch.cuda.Stream(device=dev)
+    with torch.cuda.stream(side):  # warm-up, then capture one round-robin pass as a CUDA graph
+        for a, b, c in sets:
+            ops.adam_sweep_untouched(a, b, c, None, 1e-4)
     torch.cuda.synchronize()
-    sw_ms = float(np.mean([a.elapsed_time(b) for a, b in sw_ev]))
+    g_sweep = torch.cuda.CUDAGraph()
+    with torch.cuda.graph(g_sweep, stream=side):
+        for a, b, c in sets:
+            ops.adam_sweep_untouched(a, b, c, None, 1e-4)
+    g_sweep.replay()
+    torch.cuda.synchronize()
+    se0, se1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    se0.record()
+    for _ in range(ROUNDS):
+        g_sweep.replay()
+    se1.record()
+    torch.cuda.synchronize()
+    sw_ms = se0.elapsed_time(se1) / (NSETS * ROUNDS)
     achieved = sweep_bytes / (sw_ms * 1e-3) / 1e9
+    # one launch alone between two events, L2 flushed before it (includes launch latency)
+    one_ev = []
+    for k in range(10):
+        flush.zero_()
+        a0, a1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a0.record()
+        ops.adam_sweep_untouched(*sets[k % NSETS], None, 1e-4)
+        a1.record()
+        one_ev.append((a0, a1))
+    torch.cuda.synchronize()
+    sw_single_ms = float(np.mean([a.elapsed_time(b) for a, b in one_ev]))
+    del sets
     step_bytes = 24.0 * D * rows + 12.0 * D * BATCH + 12.0 * BATCH + 48.0 * D
     ms_per_step = 1e3 * t_flushed / K
     roofline = {"bound": "hbm", "kernel": "adam_sweep_kernel", "achieved": achieved,
                 "peak": peaks["hbm_gbs"], "peak_kind": peak_kind, "unit": "GB/s",
-                "frac": achieved / peaks["hbm_gbs"], "traffic": None,
+                "frac": achieved / peaks["hbm_gbs"], "traffic": ncu_traffic("adam_sweep_kernel"),
                 "bytes_per_launch": sweep_bytes, "ms_per_launch": sw_ms,
+                "ms_per_launch_single_flushed": sw_single_ms,
+                "method": "60 launches (10 replays of a 6-launch CUDA graph) round-robin over 6 table "
+                          "sets (326 MB > L2) between one event pair on the launching stream",
                 "step": {"bytes_per_step": step_bytes,
                          "achieved": step_bytes / (ms_per_step * 1e-3) / 1e9,
                          "frac": step_bytes / (ms_per_step * 1e-3) / 1e9 / peaks["hbm_gbs"],
                          "note": "whole step; the BxB grid kernel is MUFU-bound, not HBM-bound"}}
-    del bigv, bigm, bigvv
 
     # ---------------- scoring: full catalogue, item-sharded across ranks ----------------
     scoring = None

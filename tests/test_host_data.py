@@ -1,0 +1,132 @@
+"""Host data path vs golden vectors produced by the REFERENCE's own loaders / samplers
+(tests/golden/make_golden.py ran macr_mf/load_data.py and macr_lightgcn/utility/load_data.py
+from /root/reference).  Bit-exact: sampled triples, adjacency CSR structure and values."""
+import hashlib
+import json
+import os
+import random
+import types
+
+import numpy as np
+import pytest
+
+GOLD = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+REF_DATA = "/root/reference/data"
+
+
+def _mf_args(data_path, dataset, batch_size):
+    return types.SimpleNamespace(data_path=data_path, dataset=dataset, batch_size=batch_size,
+                                 data_type="ori", model="mf", source="normal", valid_set="test")
+
+
+def _sha1(u, p, n):
+    return hashlib.sha1(np.array([u, p, n], np.int64).tobytes()).hexdigest()
+
+
+def test_mf_loader_and_sampler_tiny(capsys):
+    from macr_b200.host.data_mf import Data
+
+    g = np.load(os.path.join(GOLD, "mf_sampler.npz"))
+    data = Data(_mf_args(GOLD + "/", "tiny", 16))
+    assert (data.n_users, data.n_items, data.n_train, data.n_test) == tuple(
+        int(g[k]) for k in ("n_users", "n_items", "n_train", "n_test"))
+    random.seed(12345)
+    np.testing.assert_array_equal(np.array(data.sample(), np.int64), g["b1"])
+    np.testing.assert_array_equal(np.array(data.sample(), np.int64), g["b2"])
+    data.batch_size = 200  # > n_users: users drawn with replacement (load_data.py:546-547)
+    b3 = np.array(data.sample(), np.int64)
+    np.testing.assert_array_equal(b3, g["b3"])
+    # user 7 has no train line -> positive item 0 (load_data.py:552-553)
+    assert np.all(b3[1][b3[0] == 7] == 0)
+    # negatives never come from the user's train list
+    for u, n in zip(b3[0], b3[2]):
+        assert n not in data.train_user_list[u]
+
+
+def test_lgcn_loader_sampler_adjacency_tiny():
+    from macr_b200.host.data_lgcn import Data
+
+    g = np.load(os.path.join(GOLD, "lgcn_sampler.npz"))
+    data = Data(os.path.join(GOLD, "tiny"), 16, types.SimpleNamespace(valid_set="test"))
+    assert (data.n_users, data.n_items, data.n_train, data.n_test) == tuple(
+        int(g[k]) for k in ("n_users", "n_items", "n_train", "n_test"))
+    np.testing.assert_array_equal(np.array(data.exist_users), g["exist_users"])  # file order
+    random.seed(12345)
+    np.random.seed(12345)
+    np.testing.assert_array_equal(np.array(data.sample(), np.int64), g["b1"])
+    np.testing.assert_array_equal(np.array(data.sample(), np.int64), g["b2"])
+    a = np.load(os.path.join(GOLD, "lgcn_adj_tiny.npz"))
+    rowptr, col, val = data.adj_csr("pre")
+    np.testing.assert_array_equal(rowptr, a["indptr"])
+    np.testing.assert_array_equal(col, a["indices"])
+    np.testing.assert_array_equal(val, a["data"])  # float32 values bit for bit
+    # symmetric, zero row for the user without interactions (inf -> 0)
+    import scipy.sparse as sp
+
+    M = sp.csr_matrix((val, col, rowptr), shape=tuple(a["shape"]))
+    assert abs(M - M.T).max() == 0
+    assert M[7].nnz == 0
+
+
+def test_lgcn_sample_test_runs_and_excludes_known_items():
+    from macr_b200.host.data_lgcn import Data
+
+    data = Data(os.path.join(GOLD, "tiny"), 8, types.SimpleNamespace(valid_set="test"))
+    random.seed(1)
+    np.random.seed(1)
+    users, pos, neg = data.sample_test()
+    assert len(users) == len(pos) == len(neg) == 8
+    for u, p, n in zip(users, pos, neg):
+        assert p in data.test_set[u]
+        assert n not in data.test_set[u] and n not in data.train_items.get(u, [])
+
+
+@pytest.mark.skipif(not os.path.isdir(os.path.join(REF_DATA, "addressa")),
+                    reason="reference data set not mounted")
+def test_addressa_digests(monkeypatch):
+    """Real data: first sampled batch and the `pre` adjacency hash equal the reference's."""
+    from macr_b200.host import data_lgcn, data_mf
+
+    with open(os.path.join(GOLD, "digests.json")) as f:
+        dg = json.load(f)
+    monkeypatch.chdir("/root/reference")  # the MF loader reads ./data/<dataset>/
+    d = data_mf.Data(_mf_args("./data/", "addressa", 1024))
+    want = dg["mf_addressa"]
+    assert (d.n_users, d.n_items, d.n_train, d.n_test, len(d.test_users)) == (
+        want["n_users"], want["n_items"], want["n_train"], want["n_test"], want["n_test_users"])
+    random.seed(12345)
+    u, p, n = d.sample()
+    assert _sha1(u, p, n) == want["first_batch_sha1"]
+
+    g = data_lgcn.Data(os.path.join(REF_DATA, "addressa"), 1024, types.SimpleNamespace(valid_set="test"))
+    want = dg["lgcn_addressa"]
+    random.seed(12345)
+    np.random.seed(12345)
+    u, p, n = g.sample()
+    assert _sha1(u, [int(x) for x in p], [int(x) for x in n]) == want["first_batch_sha1"]
+    rowptr, col, val = g.adj_csr("pre")
+    h = hashlib.sha1()
+    for a in (rowptr, col, val):
+        h.update(a.tobytes())
+    assert int(val.size) == want["adj_nnz"]
+    assert h.hexdigest() == want["adj_sha1"]
+
+
+def test_flag_defaults_match_reference_parsers():
+    from macr_b200.host import flags
+
+    with open(os.path.join(GOLD, "parser_defaults.json")) as f:
+        want = json.load(f)
+    got_mf = vars(flags.parse_mf_args([]))
+    got_lg = vars(flags.parse_lgcn_args([]))
+    for k, v in want["mf"].items():
+        assert got_mf[k] == v, k
+    for k, v in want["lgcn"].items():
+        assert got_lg[k] == v, k
+    # README commands parse (README.md:52,82)
+    a = flags.parse_mf_args("--dataset addressa --batch_size 1024 --cuda 0 --saveID 1 --log_interval 10 "
+                            "--lr 0.001 --train rubibceboth --test rubi --c 40 --alpha 1e-3 --beta 1e-3".split())
+    assert (a.train, a.test, a.c, a.batch_size) == ("rubibceboth", "rubi", 40.0, 1024)
+    b = flags.parse_lgcn_args("--dataset addressa --batch_size 1024 --layer_size [64,64] --loss bceboth "
+                              "--test rubiboth --c 40 --alpha 1e-2 --beta 1e-3 --epoch 2000".split())
+    assert flags.as_list(b.layer_size) == [64, 64] and b.loss == "bceboth"
