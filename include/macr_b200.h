@@ -86,10 +86,11 @@ int macr_grid_bce_fwd_bwd(const float *yp, const float *yn, const float *sp, con
  *   unsorted_segment_sum) that AdamOptimizer runs on the IndexedSlices gradient of
  *   embedding_lookup (third-party, not vendored).
  *  ids   : n_ids row ids (users: B ids; items: pos followed by neg, 2B ids)
- *  out   : uniq_rows[n_uniq] in first-occurrence order (what array_ops.unique returns),
- *          seg_off[n_uniq+1], seg_pos[n_ids] (positions into `ids`, ascending inside a
- *          segment = the order unsorted_segment_sum adds in), *n_uniq (device int)
- *          touched_bitmap: one bit per table row, set for every row in `ids`
+ *  out   : uniq_rows[n_uniq] ascending (array_ops.unique lists them in first-occurrence
+ *          order; the order of the unique rows enters no result), seg_off[n_uniq+1],
+ *          seg_pos[n_ids] (positions into `ids`, ascending inside a segment = the order
+ *          unsorted_segment_sum adds in), *n_uniq (device int)
+ *          touched_bitmap (nullable): one bit per table row, set for every row in `ids`
  *          (caller zero-initialises once; macr_adam_rows clears the bits)
  *  ws    : scratch, at least macr_batch_plan_workspace_bytes(n_ids) bytes.
  * ------------------------------------------------------------------------- */

@@ -56,7 +56,7 @@ extern "C" int macr_gather_dots(const float *Ue, const float *Ie, const float *U
                      sn && su && regsq,
                  "macr_gather_dots: null pointer");
   return launch_gather_dots(Ue, Ie, Ur, Ir, w, w_user, users, pos, neg, nullptr, B, yp, yn, sp, sn,
-                            su, regsq, as_stream(stream));
+                            su, regsq, nullptr, as_stream(stream));
 }
 
 extern "C" size_t macr_grid_bce_workspace_bytes(int B) {
@@ -79,6 +79,8 @@ extern "C" int macr_grid_bce_fwd_bwd(const float *yp, const float *yn, const flo
     return fail(MACR_ERR_WORKSPACE, "macr_grid_bce_fwd_bwd: workspace %zu < %zu bytes", ws_bytes,
                 g.bytes);
   cudaStream_t s = as_stream(stream);
+  // band arrival tickets start at zero (they re-arm themselves, but `ws` is caller scratch)
+  MACR_CUDA(cudaMemsetAsync(g.tickets, 0, sizeof(unsigned) * 2 * (size_t)g.nblk, s));
   int rc = launch_grid_bce(yp, yn, sp, sn, su, B, alpha, beta, g, d_yp, d_yn, d_sp, d_sn, d_su,
                            want_grad, s);
   if (rc) return rc;
@@ -99,12 +101,11 @@ extern "C" int macr_batch_plan(const int32_t *ids, int n_ids, int64_t table_rows
     return fail(MACR_ERR_WORKSPACE, "macr_batch_plan: workspace %zu < %zu bytes", ws_bytes,
                 plan_ws_bytes(n_ids));
   cudaStream_t s = as_stream(stream);
-  MACR_CUDA(cudaMemsetAsync(ws, 0, plan_ws_bytes(n_ids), s));  // arrival tickets start at zero
   PlanBufs out = plan_carve(uniq_rows, seg_off, seg_pos, n_uniq, ws, n_ids);
   PlanBufs none{};
-  (void)table_rows;
-  return launch_batch_plan2(ids, nullptr, 0, n_ids, out, touched_bitmap, nullptr, 0, 0, none, nullptr,
-                            s);
+  MACR_CHECK_ARG(table_rows > 0, "macr_batch_plan: table_rows must be positive");
+  return launch_batch_plan2(ids, nullptr, 0, n_ids, table_rows, out, touched_bitmap, nullptr, 0, 0, 1,
+                            none, nullptr, s);
 }
 
 extern "C" int macr_adam_sweep_untouched(float *var, float *m, float *v, int64_t rows, int d,

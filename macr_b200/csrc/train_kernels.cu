@@ -2,8 +2,11 @@
 //   K1+K2 gather + five dots        (macr_mf/model.py:35-37,186-187,194-196,219)
 //   K3    B x B gated BCE grid      (model.py:204-217 + its autodiff)
 //   K5a   batch plan (dedup)        (TF-1.14 optimizer.py _deduplicate_indexed_slices)
+//         row gradients + fused Adam on the touched rows + step tail
 //   K5b   Adam, TF dense semantics  (TF-1.14 adam.py _apply_sparse_shared / ApplyAdam)
 // Design notes and rooflines: DESIGN.md sections 3-4.
+#include <stdlib.h>
+
 #include "train_kernels.cuh"
 
 namespace macr {
@@ -51,7 +54,8 @@ gather_dots_kernel(const float *__restrict__ Ue, const float *__restrict__ Ie,
                    const float *__restrict__ w, const float *__restrict__ wu,
                    const int32_t *u_, const int32_t *p_, const int32_t *n_, const StepState *st,
                    int B, float *__restrict__ yp, float *__restrict__ yn, float *__restrict__ sp,
-                   float *__restrict__ sn, float *__restrict__ su, float *__restrict__ regsq) {
+                   float *__restrict__ sn, float *__restrict__ su, float *__restrict__ regsq,
+                   float *__restrict__ snap) {
   const int lane = threadIdx.x & 31;
   const int b = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   if (b >= B) return;
@@ -61,6 +65,12 @@ gather_dots_kernel(const float *__restrict__ Ue, const float *__restrict__ Ie,
   const float2 ue = reinterpret_cast<const float2 *>(Ue + ur * kD)[lane];
   const float2 pe = reinterpret_cast<const float2 *>(Ie + pr * kD)[lane];
   const float2 ne = reinterpret_cast<const float2 *>(Ie + nr * kD)[lane];
+  if (snap) {  // row snapshot [3][B][64] (users | pos | neg): row_grads reads these, so the Adam
+               // update of a row can run while other rows' gradients are still being formed
+    reinterpret_cast<float2 *>(snap + (long long)b * kD)[lane] = ue;
+    reinterpret_cast<float2 *>(snap + ((long long)B + b) * kD)[lane] = pe;
+    reinterpret_cast<float2 *>(snap + (2LL * B + b) * kD)[lane] = ne;
+  }
   const float2 wv = reinterpret_cast<const float2 *>(w)[lane];
   const float2 wuv = reinterpret_cast<const float2 *>(wu)[lane];
   float a0 = ue.x * pe.x + ue.y * pe.y;
@@ -96,10 +106,11 @@ gather_dots_kernel(const float *__restrict__ Ue, const float *__restrict__ Ie,
 int launch_gather_dots(const float *Ue, const float *Ie, const float *Ur, const float *Ir,
                        const float *w, const float *wu, const int32_t *u, const int32_t *p,
                        const int32_t *n, const StepState *st, int B, float *yp, float *yn,
-                       float *sp, float *sn, float *su, float *regsq, cudaStream_t s) {
+                       float *sp, float *sn, float *su, float *regsq, float *snap,
+                       cudaStream_t s) {
   const int wpb = 8;
   gather_dots_kernel<<<(B + wpb - 1) / wpb, wpb * 32, 0, s>>>(Ue, Ie, Ur, Ir, w, wu, u, p, n, st,
-                                                              B, yp, yn, sp, sn, su, regsq);
+                                                              B, yp, yn, sp, sn, su, regsq, snap);
   MACR_LAUNCH_CHECK();
   return MACR_OK;
 }
@@ -110,38 +121,100 @@ int launch_gather_dots(const float *Ue, const float *Ie, const float *Ur, const 
 // loop runs on registers; row / column partial sums meet in shared memory once per tile.
 // The [B,B] matrices are never written anywhere.
 //
-// Per (i,j) pair the reference evaluates (model.py:204-211)
-//   P=(yp_j*a_i)*g_i  s=sig(P)  lossP=-log(s+1e-10)      dlossP/dP = -s(1-s)/(s+1e-10)
-//   N=(yn_j*an_i)*g_i t=sig(N)  lossN=-log((1-t)+1e-10)  dlossN/dN =  t(1-t)/((1-t)+1e-10)
-// Fast path (taken when s >= 2^-9 and 1-t >= 2^-9, where fp32 "+1e-10" is a no-op exactly as in
-// the reference's own fp32 arithmetic): one rcp serves both sigmoids, one lg2 serves both logs,
-// and the gradients collapse to s-1 and t  ->  4 MUFU ops per pair.  Otherwise the literal
-// formulas are evaluated (8 MUFU ops).
+// Per (i,j) pair the reference evaluates (model.py:204-211), with c_i = sig(sp_i)*sig(su_i) etc.
+//   P = yp_j*c_i   s = sig(P)  lossP = -log(s+1e-10)      dlossP/dP = -s(1-s)/(s+1e-10)
+//   N = yn_j*cn_i  t = sig(N)  lossN = -log((1-t)+1e-10)  dlossN/dN =  t(1-t)/((1-t)+1e-10)
+// Fast path (s >= 2^-9 and 1-t >= 2^-9, where the fp32 "+1e-10" is a no-op exactly as in the
+// reference's own fp32 arithmetic):  with eP = exp(-P), eN = exp(-N), D = (1+eP)(1+eN)
+//   lossP + lossN = ln D + N           dlossP/dP = (1+eN)/D - 1        dlossN/dN = (1+eP)/D
+// i.e. 2 ex2 + 1 rcp + 1 lg2 = 4 MUFU and 13 FP32 instructions per pair; the "+N" term is a
+// rank-1 sum added once per tile.  A tile whose column scores are bounded so that every pair is
+// in the fast range (|yp_j|*max_i c_i <= 6.2, |yn_j|*max_i cn_i <= 5.5) runs without any
+// per-pair range test; other tiles test every pair and fall back to the literal formulas
+// (8 MUFU) where needed.
+//
+// The last CTA to finish a tile row / tile column (arrival tickets) folds that band's partial
+// sums in fixed order and finishes the chain rule through the three sigmoids, adding the
+// alpha / beta branch gradients (model.py:213-217) -- no separate finalize launch.
 // ---------------------------------------------------------------------------------------------
+struct GridOut {
+  float *d_yp, *d_yn, *d_sp, *d_sn, *d_su;
+};
+
+template <bool kChecked, bool kMasked, bool kGrad>
+__device__ __forceinline__ void grid_pair(float ypj, float ynj, float agl, float angl, float ag,
+                                          float ang, float mk, float &lgacc, float &colP,
+                                          float &colN, float &rowP, float &rowN) {
+  const float xP = ypj * agl, xN = ynj * angl;  // -P*log2(e), -N*log2(e)
+  const float eP = ex2_approx(xP), eN = ex2_approx(xN);
+  const float DP = 1.0f + eP, DN = 1.0f + eN;
+  float lg, dP, dN;
+  if (!kChecked || (eP <= 500.0f && eN >= 0.00390625f && eN <= 1.0e18f)) {
+    const float D = DP * DN;
+    const float rr = rcp_approx(D);
+    lg = -lg2_approx(D);  // + xN, added per tile as a rank-1 sum
+    dN = DP * rr;
+    dP = DN * rr - 1.0f;
+  } else {
+    const float s = rcp_approx(DP), t = rcp_approx(DN);
+    const float se = s + kBceEps, q = (1.0f - t) + kBceEps;
+    lg = (lg2_approx(se) + lg2_approx(q)) - xN;
+    dP = -(s * (1.0f - s)) * rcp_approx(se);
+    dN = (t * (1.0f - t)) * rcp_approx(q);
+  }
+  if (kMasked) lg *= mk;
+  lgacc += lg;
+  if (kGrad) {
+    colP = fmaf(dP, ag, colP);
+    colN = fmaf(dN, ang, colN);
+    rowP = fmaf(dP, ypj, rowP);
+    rowN = fmaf(dN, ynj, rowN);
+  }
+}
+
 template <int RI, int RJ, bool kMasked, bool kGrad>
-__global__ void __launch_bounds__(256, (RI * RJ >= 64) ? 2 : 3)
+__global__ void __launch_bounds__(256, 2)
 grid_bce_kernel(const float *__restrict__ yp, const float *__restrict__ yn,
                 const float *__restrict__ sp, const float *__restrict__ sn,
-                const float *__restrict__ su, int B, int Bpad, float *__restrict__ rowP_part,
-                float *__restrict__ rowN_part, float *__restrict__ colP_part,
-                float *__restrict__ colN_part, float *__restrict__ losspart) {
+                const float *__restrict__ su, int B, float alpha, float beta, GridWs ws,
+                GridOut out) {
   constexpr int TI = 16 * RI, TJ = 16 * RJ;
   constexpr int TMAX = TI > TJ ? TI : TJ;
   constexpr float kLog2e = 1.4426950408889634f;
   __shared__ float sA[TI], sAN[TI], sG[TI];
+  __shared__ float sAg[TI], sAng[TI];
   __shared__ float sYp[TJ], sYn[TJ];
   __shared__ float sRed[2][TMAX][17];
   __shared__ float sLoss[8];
+  __shared__ int sMax[2];
+  __shared__ unsigned sTicket[2];
+  __shared__ double sRank1;
 
   const int tid = threadIdx.x, tx = tid & 15, ty = tid >> 4;
   const int i0 = blockIdx.y * TI, j0 = blockIdx.x * TJ;
+  const int Bpad = ws.Bpad;
+  if (tid < 2) sMax[tid] = 0;
+  __syncthreads();
 
   for (int t = tid; t < TI; t += 256) {
     const int i = i0 + t;
     const bool ok = i < B;
-    sA[t] = ok ? sigmoid_precise(sp[i]) : 0.f;
-    sAN[t] = ok ? sigmoid_precise(sn[i]) : 0.f;
-    sG[t] = ok ? sigmoid_precise(su[i]) : 0.f;
+    const float a = ok ? sigmoid_precise(sp[i]) : 0.f, an = ok ? sigmoid_precise(sn[i]) : 0.f,
+                g = ok ? sigmoid_precise(su[i]) : 0.f;
+    sA[t] = a;
+    sAN[t] = an;
+    sG[t] = g;
+    const float ag = a * g, ang = an * g;
+    sAg[t] = ag;
+    sAng[t] = ang;
+    atomicMax(&sMax[0], __float_as_int(ag));  // gates are >= 0: int order == float order
+    atomicMax(&sMax[1], __float_as_int(ang));
+    if (ok && blockIdx.x == 0) {  // branch losses of this row band, model.py:213,215
+      const float ea = a + kBceEps, ean = (1.0f - an) + kBceEps;
+      const float eg = g + kBceEps, eg1 = (1.0f - g) + kBceEps;
+      ws.litem[i] = -logf(ea) - logf(ean);
+      ws.luser[i] = -logf(eg) - logf(eg1);
+    }
   }
   for (int t = tid; t < TJ; t += 256) {
     const int j = j0 + t;
@@ -150,18 +223,29 @@ grid_bce_kernel(const float *__restrict__ yp, const float *__restrict__ yn,
     sYn[t] = ok ? yn[j] : 0.f;
   }
   __syncthreads();
+  bool in_range = true;
+  if (tid < TJ)
+    in_range = fabsf(sYp[tid]) * __int_as_float(sMax[0]) <= 6.2f &&
+               fabsf(sYn[tid]) * __int_as_float(sMax[1]) <= 5.5f;
+  const bool all_fast = __syncthreads_and(in_range);
+  if (tid < 32) {  // rank-1 term of the tile: sum_ij xN_ij = (sum_i -log2e*ang_i) * (sum_j yn_j)
+    float sa = 0.f, sy = 0.f;
+    for (int t = tid; t < TI; t += 32) sa += sAng[t];
+    for (int t = tid; t < TJ; t += 32) sy += sYn[t];
+    sa = warp_sum(sa);
+    sy = warp_sum(sy);
+    if (tid == 0) sRank1 = -(double)kLog2e * (double)sa * (double)sy;
+  }
 
-  float a[RI], an[RI], gl[RI], ag[RI], ang[RI], wr[RI];
+  float agl[RI], angl[RI], ag[RI], ang[RI], wr[RI];
   float ypj[RJ], ynj[RJ], wc[RJ];
 #pragma unroll
   for (int r = 0; r < RI; ++r) {
     const int t = ty + 16 * r;
-    a[r] = sA[t];
-    an[r] = sAN[t];
-    const float g = sG[t];
-    gl[r] = -g * kLog2e;  // exp(-P) = ex2((yp*a)*(-g*log2e))
-    ag[r] = a[r] * g;
-    ang[r] = an[r] * g;
+    ag[r] = sAg[t];
+    ang[r] = sAng[t];
+    agl[r] = -kLog2e * ag[r];  // exp(-P) = ex2(yp * (-c*log2e))
+    angl[r] = -kLog2e * ang[r];
     wr[r] = (i0 + t < B) ? 1.f : 0.f;
   }
 #pragma unroll
@@ -179,42 +263,22 @@ grid_bce_kernel(const float *__restrict__ yp, const float *__restrict__ yn,
   for (int r = 0; r < RI; ++r) rowP[r] = rowN[r] = 0.f;
   float lgacc = 0.f;  // sum of log2(.) terms; loss = -ln2 * sum
 
+  if (all_fast) {
 #pragma unroll
-  for (int r = 0; r < RI; ++r) {
+    for (int r = 0; r < RI; ++r)
 #pragma unroll
-    for (int c = 0; c < RJ; ++c) {
-      const float eP = ex2_approx((ypj[c] * a[r]) * gl[r]);   // exp(-P)
-      const float eN = ex2_approx((ynj[c] * an[r]) * gl[r]);  // exp(-N)
-      const float DP = 1.0f + eP, DN = 1.0f + eN;
-      float lg, dP, dN;
-      if (eP <= 500.0f && eN >= 0.00390625f && eN <= 1.0e18f) {
-        const float rr = rcp_approx(DP * DN);
-        const float s = rr * DN, t = rr * DP;
-        const float q = 1.0f - t;
-        lg = lg2_approx(s * q);
-        dP = s - 1.0f;
-        dN = t;
-      } else {
-        const float s = rcp_approx(DP), t = rcp_approx(DN);
-        const float se = s + kBceEps, q = (1.0f - t) + kBceEps;
-        lg = lg2_approx(se) + lg2_approx(q);
-        dP = -(s * (1.0f - s)) * rcp_approx(se);
-        dN = (t * (1.0f - t)) * rcp_approx(q);
-      }
-      if (kMasked) {
-        const float mk = wr[r] * wc[c];
-        lg *= mk;
-        dP *= mk;
-        dN *= mk;
-      }
-      lgacc += lg;
-      if (kGrad) {
-        colP[c] = fmaf(dP, ag[r], colP[c]);
-        colN[c] = fmaf(dN, ang[r], colN[c]);
-        rowP[r] = fmaf(dP, ypj[c], rowP[r]);
-        rowN[r] = fmaf(dN, ynj[c], rowN[r]);
-      }
-    }
+      for (int c = 0; c < RJ; ++c)
+        grid_pair<false, kMasked, kGrad>(ypj[c], ynj[c], agl[r], angl[r], ag[r], ang[r],
+                                         kMasked ? wr[r] * wc[c] : 1.f, lgacc, colP[c], colN[c],
+                                         rowP[r], rowN[r]);
+  } else {
+#pragma unroll
+    for (int r = 0; r < RI; ++r)
+#pragma unroll
+      for (int c = 0; c < RJ; ++c)
+        grid_pair<true, kMasked, kGrad>(ypj[c], ynj[c], agl[r], angl[r], ag[r], ang[r],
+                                        kMasked ? wr[r] * wc[c] : 1.f, lgacc, colP[c], colN[c],
+                                        rowP[r], rowN[r]);
   }
 
   // ---- per-tile reductions -------------------------------------------------------------
@@ -230,8 +294,8 @@ grid_bce_kernel(const float *__restrict__ yp, const float *__restrict__ yn,
       float acc = 0.f;
 #pragma unroll
       for (int k = 0; k < 16; ++k) acc += sRed[which][row][k];
-      float *dst = which ? rowN_part : rowP_part;
-      dst[(size_t)blockIdx.x * Bpad + i0 + row] = acc;
+      float *dst = which ? ws.rowN : ws.rowP;
+      __stcg(&dst[(size_t)blockIdx.x * Bpad + i0 + row], acc);
     }
     __syncthreads();
 #pragma unroll
@@ -245,8 +309,8 @@ grid_bce_kernel(const float *__restrict__ yp, const float *__restrict__ yn,
       float acc = 0.f;
 #pragma unroll
       for (int k = 0; k < 16; ++k) acc += sRed[which][colm][k];
-      float *dst = which ? colN_part : colP_part;
-      dst[(size_t)blockIdx.y * Bpad + j0 + colm] = acc;
+      float *dst = which ? ws.colN : ws.colP;
+      __stcg(&dst[(size_t)blockIdx.y * Bpad + j0 + colm], acc);
     }
   }
   lgacc = warp_sum(lgacc);
@@ -256,63 +320,75 @@ grid_bce_kernel(const float *__restrict__ yp, const float *__restrict__ yn,
     float acc = 0.f;
 #pragma unroll
     for (int k = 0; k < 8; ++k) acc += sLoss[k];
-    losspart[blockIdx.y * gridDim.x + blockIdx.x] = acc;
+    ws.losspart[blockIdx.y * gridDim.x + blockIdx.x] = (float)((double)acc + sRank1);
+    if (kGrad) {
+      __threadfence();  // the CTA's partials (ordered by the barrier above) before the tickets
+      sTicket[0] = atomicAdd(&ws.tickets[blockIdx.y], 1u);               // row band i-tile
+      sTicket[1] = atomicAdd(&ws.tickets[gridDim.y + blockIdx.x], 1u);   // column band j-tile
+    }
   }
-}
-
-// per-b epilogue of the grid: fold the tile partials, finish the chain rule through the three
-// sigmoids, add the alpha / beta branch gradients (model.py:213-217).
-// 256 threads = 64 batch positions x 4 partial arrays, so the nblk-long folds run 4-wide and
-// coalesced; thread (b, 0) then finishes the scalar math.
-__global__ void __launch_bounds__(256)
-grid_finalize_kernel(const float *__restrict__ sp, const float *__restrict__ sn,
-                     const float *__restrict__ su, int B, int Bpad, int nblk, float alpha,
-                     float beta, const float *__restrict__ rowP_part,
-                     const float *__restrict__ rowN_part, const float *__restrict__ colP_part,
-                     const float *__restrict__ colN_part, float *__restrict__ d_yp,
-                     float *__restrict__ d_yn, float *__restrict__ d_sp, float *__restrict__ d_sn,
-                     float *__restrict__ d_su, float *__restrict__ litem,
-                     float *__restrict__ luser, int want_grad) {
-  __shared__ float sh[4][64];
-  const int bl = threadIdx.x & 63, which = threadIdx.x >> 6;
-  const int b = blockIdx.x * 64 + bl;
-  if (want_grad) {
-    const float *src = which == 0 ? rowP_part : which == 1 ? rowN_part : which == 2 ? colP_part
-                                                                                     : colN_part;
-    float acc = 0.f;
-    if (b < B) {
+  if (!kGrad) return;
+  __syncthreads();
+  const bool fold_rows = sTicket[0] == gridDim.x - 1, fold_cols = sTicket[1] == gridDim.y - 1;
+  if (!fold_rows && !fold_cols) return;
+  if (tid == 0) __threadfence();
+  __syncthreads();
+  const float invB = 1.0f / (float)B;
+  const float invBB = invB * invB;
+  if (fold_cols) {  // d/d yp_j, d/d yn_j: column sums over every row band, band order fixed
+    for (int t = tid; t < 2 * TJ; t += 256) {
+      const int which = t / TJ, colm = t - which * TJ;
+      const float *src = (which ? ws.colN : ws.colP) + j0 + colm;
+      float acc = 0.f;
+      const int nb = gridDim.y;
       int k = 0;
-      for (; k + 8 <= nblk; k += 8) {
+      for (; k + 8 <= nb; k += 8) {
         float v[8];
 #pragma unroll
-        for (int q = 0; q < 8; ++q) v[q] = src[(size_t)(k + q) * Bpad + b];
+        for (int q = 0; q < 8; ++q) v[q] = __ldcg(src + (size_t)(k + q) * Bpad);
 #pragma unroll
         for (int q = 0; q < 8; ++q) acc += v[q];
       }
-      for (; k < nblk; ++k) acc += src[(size_t)k * Bpad + b];
+      for (; k < nb; ++k) acc += __ldcg(src + (size_t)k * Bpad);
+      if (j0 + colm < B) (which ? out.d_yn : out.d_yp)[j0 + colm] = acc * invBB;
     }
-    sh[which][bl] = acc;
-    __syncthreads();
+    if (tid == 0) ws.tickets[gridDim.y + blockIdx.x] = 0;  // re-armed for the next launch
   }
-  if (which != 0 || b >= B) return;
-  const float a = sigmoid_precise(sp[b]), an = sigmoid_precise(sn[b]),
-              g = sigmoid_precise(su[b]);
-  const float ea = a + kBceEps, ean = (1.0f - an) + kBceEps;
-  const float eg = g + kBceEps, eg1 = (1.0f - g) + kBceEps;
-  litem[b] = -logf(ea) - logf(ean);
-  luser[b] = -logf(eg) - logf(eg1);
-  if (!want_grad) return;
-  const float rp = sh[0][bl], rn = sh[1][bl], cp = sh[2][bl], cn = sh[3][bl];
-  const float invB = 1.0f / (float)B;
-  const float invBB = invB * invB;
-  d_yp[b] = cp * invBB;
-  d_yn[b] = cn * invBB;
-  const float da = rp * invBB * g - alpha * invB / ea;
-  const float dan = rn * invBB * g + alpha * invB / ean;
-  const float dg = (rp * a + rn * an) * invBB + beta * invB * (1.0f / eg1 - 1.0f / eg);
-  d_sp[b] = da * (a * (1.0f - a));
-  d_sn[b] = dan * (an * (1.0f - an));
-  d_su[b] = dg * (g * (1.0f - g));
+  if (fold_rows) {
+    __syncthreads();  // sRed is free again
+    for (int t = tid; t < 2 * TI; t += 256) {
+      const int which = t / TI, row = t - which * TI;
+      const float *src = (which ? ws.rowN : ws.rowP) + i0 + row;
+      float acc = 0.f;
+      const int nb = gridDim.x;
+      int k = 0;
+      for (; k + 8 <= nb; k += 8) {
+        float v[8];
+#pragma unroll
+        for (int q = 0; q < 8; ++q) v[q] = __ldcg(src + (size_t)(k + q) * Bpad);
+#pragma unroll
+        for (int q = 0; q < 8; ++q) acc += v[q];
+      }
+      for (; k < nb; ++k) acc += __ldcg(src + (size_t)k * Bpad);
+      sRed[which][row][0] = acc;
+    }
+    __syncthreads();
+    for (int t = tid; t < TI; t += 256) {
+      const int i = i0 + t;
+      if (i >= B) continue;
+      const float rp = sRed[0][t][0], rn = sRed[1][t][0];
+      const float a = sA[t], an = sAN[t], g = sG[t];
+      const float ea = a + kBceEps, ean = (1.0f - an) + kBceEps;
+      const float eg = g + kBceEps, eg1 = (1.0f - g) + kBceEps;
+      const float da = rp * invBB * g - alpha * invB / ea;
+      const float dan = rn * invBB * g + alpha * invB / ean;
+      const float dg = (rp * a + rn * an) * invBB + beta * invB * (1.0f / eg1 - 1.0f / eg);
+      out.d_sp[i] = da * (a * (1.0f - a));
+      out.d_sn[i] = dan * (an * (1.0f - an));
+      out.d_su[i] = dg * (g * (1.0f - g));
+    }
+    if (tid == 0) ws.tickets[blockIdx.y] = 0;
+  }
 }
 
 GridWs grid_ws_layout(int B, void *base) {
@@ -330,38 +406,38 @@ GridWs grid_ws_layout(int B, void *base) {
   const size_t lp = ((size_t)w.nblk * w.nblk + 3) & ~(size_t)3;
   w.litem = w.losspart + lp;
   w.luser = w.litem + w.Bpad;
-  w.bytes = (4 * band + lp + 2 * (size_t)w.Bpad) * sizeof(float);
+  w.tickets = reinterpret_cast<unsigned *>(w.luser + w.Bpad);
+  const size_t tk = ((size_t)2 * w.nblk + 3) & ~(size_t)3;
+  w.bytes = (4 * band + lp + 2 * (size_t)w.Bpad + tk) * sizeof(float);
   return w;
 }
 
 template <int R, bool kGrad>
 static void launch_grid_t(const float *yp, const float *yn, const float *sp, const float *sn,
-                          const float *su, int B, const GridWs &ws, cudaStream_t s) {
+                          const float *su, int B, float alpha, float beta, const GridWs &ws,
+                          const GridOut &out, cudaStream_t s) {
   dim3 grid(ws.nblk, ws.nblk);
   if (B % ws.tile == 0)
-    grid_bce_kernel<R, R, false, kGrad><<<grid, 256, 0, s>>>(
-        yp, yn, sp, sn, su, B, ws.Bpad, ws.rowP, ws.rowN, ws.colP, ws.colN, ws.losspart);
+    grid_bce_kernel<R, R, false, kGrad><<<grid, 256, 0, s>>>(yp, yn, sp, sn, su, B, alpha, beta, ws,
+                                                             out);
   else
-    grid_bce_kernel<R, R, true, kGrad><<<grid, 256, 0, s>>>(
-        yp, yn, sp, sn, su, B, ws.Bpad, ws.rowP, ws.rowN, ws.colP, ws.colN, ws.losspart);
+    grid_bce_kernel<R, R, true, kGrad><<<grid, 256, 0, s>>>(yp, yn, sp, sn, su, B, alpha, beta, ws,
+                                                            out);
 }
 
+// the arrival tickets inside `ws` must be zero before the first launch (they re-arm themselves)
 int launch_grid_bce(const float *yp, const float *yn, const float *sp, const float *sn,
                     const float *su, int B, float alpha, float beta, const GridWs &ws,
                     float *d_yp, float *d_yn, float *d_sp, float *d_sn, float *d_su,
                     int want_grad, cudaStream_t s) {
+  const GridOut out{d_yp, d_yn, d_sp, d_sn, d_su};
   if (ws.tile == 128) {
-    if (want_grad) launch_grid_t<8, true>(yp, yn, sp, sn, su, B, ws, s);
-    else launch_grid_t<8, false>(yp, yn, sp, sn, su, B, ws, s);
+    if (want_grad) launch_grid_t<8, true>(yp, yn, sp, sn, su, B, alpha, beta, ws, out, s);
+    else launch_grid_t<8, false>(yp, yn, sp, sn, su, B, alpha, beta, ws, out, s);
   } else {
-    if (want_grad) launch_grid_t<4, true>(yp, yn, sp, sn, su, B, ws, s);
-    else launch_grid_t<4, false>(yp, yn, sp, sn, su, B, ws, s);
+    if (want_grad) launch_grid_t<4, true>(yp, yn, sp, sn, su, B, alpha, beta, ws, out, s);
+    else launch_grid_t<4, false>(yp, yn, sp, sn, su, B, alpha, beta, ws, out, s);
   }
-  MACR_LAUNCH_CHECK();
-  grid_finalize_kernel<<<(B + 63) / 64, 256, 0, s>>>(sp, sn, su, B, ws.Bpad, ws.nblk, alpha,
-                                                       beta, ws.rowP, ws.rowN, ws.colP, ws.colN,
-                                                       d_yp, d_yn, d_sp, d_sn, d_su, ws.litem,
-                                                       ws.luser, want_grad);
   MACR_LAUNCH_CHECK();
   return MACR_OK;
 }
@@ -430,163 +506,249 @@ int launch_reduce_losses(const GridWs &ws, const float *regsq, int B, float alph
 
 // ---------------------------------------------------------------------------------------------
 // K5a: batch plan -- group the batch positions that hit the same table row, deterministically.
-// All-pairs counting instead of a sort (n <= 16384 ids, so n^2 equality tests spread over the
-// whole GPU cost a few microseconds and need no table-sized scratch):
-//   phase 1 (every CTA): 32 positions x 8 sub-lanes; the full id array is staged in shared
-//     memory and each position learns  rank  = #earlier positions with the same row,
-//     total = #positions with the same row,  lead = first position with the same row.
-//   phase 2 (last CTA to finish, per table): positions with rank 0 are segment leaders; one block
-//     scan over the positions gives their slot (first-occurrence order, the order
-//     array_ops.unique produces) and the segment offsets; every position then drops itself at
-//     seg_off[slot] + rank, i.e. ascending position inside a segment -- the order TF's
-//     unsorted_segment_sum adds in.
+// One CTA per table runs a stable LSD radix sort (8-bit digits) of the row ids in shared memory
+// (n <= 16384 ids; a few microseconds, and it occupies 2 of the 148 SMs while the B x B grid
+// runs on the rest).  A pass: every warp owns a contiguous chunk of the sequence and walks it 32
+// keys at a time -- eight ballots group the lanes with the same digit, which gives each key its
+// rank inside the warp's chunk and the warp's digit histogram in one sweep; a block scan over
+// the (digit, warp) histogram turns ranks into destinations.  Stability keeps positions
+// ascending inside a row -- the order TF's unsorted_segment_sum adds the duplicate slices in.
+// A block scan over the segment heads then emits the compact plan:
+//   uniq_rows[slot], seg_off[slot], seg_pos[k] (k = sorted index), kinfo[k] = rank << 16 | slot,
+//   *n_uniq.
+// (array_ops.unique would list the rows in first-occurrence order; the order of the unique rows
+// does not enter any result, only the order inside a segment does.)
 // ---------------------------------------------------------------------------------------------
 struct PlanTable {
   const int32_t *ids;
-  int ids_off, n_ids, blocks;
+  int ids_off, n_ids, passes;  // passes = ceil(bits(table_rows - 1) / 8)
   PlanBufs out;
   uint32_t *bitmap;
-  int32_t *total, *lead;
-  unsigned *counter;
 };
 
-constexpr int kPlanPos = 128;  // positions per CTA in phase 1 (x 8 sub-lanes = 1024 threads)
+constexpr int kPlanMaxRounds = 16;  // 16384 ids / 1024 threads
+
+#ifdef MACR_PLAN_PROFILE  // developer instrumentation (dev/kbench.cu): phase time stamps of CTA 1
+__device__ long long macr_plan_clk[32];
+#define PLAN_STAMP(i) \
+  do { if (threadIdx.x == 0 && blockIdx.x == gridDim.x - 1) macr_plan_clk[i] = clock64(); } while (0)
+#else
+#define PLAN_STAMP(i)
+#endif
 
 __global__ void __launch_bounds__(1024)
-batch_plan_kernel(PlanTable t0, PlanTable t1, const StepState *st, int B) {
-  extern __shared__ __align__(16) int32_t sids[];
-  const bool second = (int)blockIdx.x >= t0.blocks;
-  const PlanTable &t = second ? t1 : t0;
-  const int blk = second ? blockIdx.x - t0.blocks : blockIdx.x;
-  const int tid = threadIdx.x, n = t.n_ids;
-  const int32_t *ids = (st ? st->ids_base + st->step_idx * 3LL * B : t.ids) + t.ids_off;
-  const int n4 = (n + 3) >> 2;
-  if ((n & 3) == 0 && (reinterpret_cast<uintptr_t>(ids) & 15) == 0) {
-    const int4 *g4 = reinterpret_cast<const int4 *>(ids);
-    int4 *d4 = reinterpret_cast<int4 *>(sids);
-    for (int e = tid; e < n4; e += 1024) d4[e] = g4[e];
-  } else {
-    for (int e = tid; e < n4 * 4; e += 1024) sids[e] = e < n ? ids[e] : -1;
-  }
-  __syncthreads();
-
-  const int q = blk * kPlanPos + (tid >> 3), sub = tid & 7;
-  const int my = q < n ? sids[q] : -2;
-  int rank = 0, total = 0, lead = 0x7fffffff;
-  const int4 *s4 = reinterpret_cast<const int4 *>(sids);
-#pragma unroll 4
-  for (int i = sub; i < n4; i += 8) {
-    const int4 x = s4[i];
-    if (x.x == my || x.y == my || x.z == my || x.w == my) {  // rare: matches are sparse
-      const int j = 4 * i;
-      const int e0 = x.x == my, e1 = x.y == my, e2 = x.z == my, e3 = x.w == my;
-      total += e0 + e1 + e2 + e3;
-      rank += (e0 & (j < q)) + (e1 & (j + 1 < q)) + (e2 & (j + 2 < q)) + (e3 & (j + 3 < q));
-      const int f = e0 ? j : e1 ? j + 1 : e2 ? j + 2 : j + 3;
-      lead = min(lead, f);
-    }
-  }
-#pragma unroll
-  for (int o = 1; o < 8; o <<= 1) {
-    rank += __shfl_xor_sync(0xffffffffu, rank, o);
-    total += __shfl_xor_sync(0xffffffffu, total, o);
-    lead = min(lead, __shfl_xor_sync(0xffffffffu, lead, o));
-  }
-  if (sub == 0 && q < n) {
-    t.out.rank[q] = rank;
-    t.total[q] = total;
-    t.lead[q] = lead;
-    if (t.bitmap) atomicOr(&t.bitmap[(uint32_t)my >> 5], 1u << (my & 31));
-  }
-}
-
-// phase 2: one CTA per table.  rank / total / slot / seg_off are staged in shared memory (16-bit:
-// n <= 16384) so the sequential passes every thread makes over its consecutive positions never
-// wait on global memory; everything that touches global memory is coalesced and independent.
-__global__ void __launch_bounds__(1024)
-batch_plan_tail_kernel(PlanTable t0, PlanTable t1, const StepState *st, int B) {
-  extern __shared__ __align__(16) unsigned short sh16[];
-  __shared__ int s_scan[2][32];
+batch_plan_sort_kernel(PlanTable t0, PlanTable t1, const StepState *st, int B) {
+  extern __shared__ __align__(16) unsigned char plan_smem[];
+  __shared__ int s_scan[32];
   const PlanTable &t = blockIdx.x == 0 ? t0 : t1;
-  const int tid = threadIdx.x, n = t.n_ids;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, n = t.n_ids;
   if (n == 0) return;
+  PLAN_STAMP(0);
   const int32_t *ids = (st ? st->ids_base + st->step_idx * 3LL * B : t.ids) + t.ids_off;
-  const int npad = ((n + 1023) / 1024) * 1024;
-  unsigned short *rankS = sh16, *totalS = sh16 + npad, *slotS = sh16 + 2 * npad,
-                 *offS = sh16 + 3 * npad;
-  constexpr int kMaxPer = 16;
-  int leadv[kMaxPer], idv[kMaxPer];
-#pragma unroll
-  for (int k = 0; k < kMaxPer; ++k) {
-    const int x = tid + k * 1024;
-    if (x < npad) {
-      rankS[x] = x < n ? (unsigned short)t.out.rank[x] : (unsigned short)1;
-      totalS[x] = x < n ? (unsigned short)t.total[x] : (unsigned short)0;
-      leadv[k] = x < n ? t.lead[x] : 0;
-      idv[k] = x < n ? ids[x] : 0;
+  int npad = 1024;
+  while (npad < n) npad <<= 1;
+  uint32_t *keyA = reinterpret_cast<uint32_t *>(plan_smem), *keyB = keyA + npad;
+  uint32_t(*hist)[33] = reinterpret_cast<uint32_t(*)[33]>(keyB + npad);  // [256][33]
+  unsigned short *posA = reinterpret_cast<unsigned short *>(hist + 256), *posB = posA + npad;
+
+  for (int e = tid; e < npad; e += 1024) {
+    uint32_t r = 0xffffffffu;  // padding sorts last in every pass and stays last (stable)
+    if (e < n) {
+      r = (uint32_t)ids[e];
+      if (t.bitmap) atomicOr(&t.bitmap[r >> 5], 1u << (r & 31));
     }
+    keyA[e] = r;
+    posA[e] = (unsigned short)e;
+  }
+  const int rounds = npad >> 10, chunk = npad >> 5;
+  const unsigned lt_mask = (1u << lane) - 1u;
+  for (int pass = 0; pass < t.passes; ++pass) {
+    const int shift = 8 * pass;
+    PLAN_STAMP(1 + 4 * pass);
+    for (int c = tid; c < 256 * 33; c += 1024) (&hist[0][0])[c] = 0;
+    __syncthreads();
+    PLAN_STAMP(2 + 4 * pass);
+    uint32_t key[kPlanMaxRounds];
+    int rank[kPlanMaxRounds];
+#pragma unroll
+    for (int r = 0; r < kPlanMaxRounds; ++r) {
+      if (r < rounds) {
+        key[r] = keyA[warp * chunk + r * 32 + lane];
+        const unsigned d = (key[r] >> shift) & 255u;
+        // lanes holding the same digit: 8 ballots (MATCH.ANY is ~100x slower on this part)
+        unsigned peers = 0xffffffffu;
+#pragma unroll
+        for (int bit = 0; bit < 8; ++bit) {
+          const bool on = (d >> bit) & 1u;
+          const unsigned vote = __ballot_sync(0xffffffffu, on);
+          peers &= on ? vote : ~vote;
+        }
+        const uint32_t before = hist[d][warp];
+        __syncwarp();
+        if ((peers & lt_mask) == 0) hist[d][warp] = before + __popc(peers);
+        __syncwarp();
+        rank[r] = before + __popc(peers & lt_mask);
+      }
+    }
+    __syncthreads();
+    PLAN_STAMP(3 + 4 * pass);
+    {  // exclusive scan of the 256 x 32 histogram in (digit, warp) order: 8 counters per thread
+      const int d = tid >> 2, w0 = (tid & 3) * 8;
+      uint32_t v[8], sum = 0;
+#pragma unroll
+      for (int q = 0; q < 8; ++q) {
+        v[q] = hist[d][w0 + q];
+        sum += v[q];
+      }
+      uint32_t incl = sum;
+#pragma unroll
+      for (int o = 1; o < 32; o <<= 1) {
+        const uint32_t x = __shfl_up_sync(0xffffffffu, incl, o);
+        if (lane >= o) incl += x;
+      }
+      if (lane == 31) s_scan[warp] = (int)incl;
+      __syncthreads();
+      uint32_t base = 0;
+#pragma unroll
+      for (int w = 0; w < 32; ++w)
+        if (w < warp) base += (uint32_t)s_scan[w];
+      uint32_t run = base + incl - sum;
+#pragma unroll
+      for (int q = 0; q < 8; ++q) {
+        hist[d][w0 + q] = run;
+        run += v[q];
+      }
+    }
+    __syncthreads();
+    PLAN_STAMP(4 + 4 * pass);
+#pragma unroll
+    for (int r = 0; r < kPlanMaxRounds; ++r) {
+      if (r < rounds) {
+        const unsigned d = (key[r] >> shift) & 255u;
+        const int dst = (int)hist[d][warp] + rank[r];
+        keyB[dst] = key[r];
+        posB[dst] = posA[warp * chunk + r * 32 + lane];
+      }
+    }
+    __syncthreads();
+    uint32_t *tk = keyA;
+    keyA = keyB;
+    keyB = tk;
+    unsigned short *tp = posA;
+    posA = posB;
+    posB = tp;
+  }
+  PLAN_STAMP(20);
+  // segment heads, walked in the same warp-striped order as the sort rounds (conflict-free
+  // shared-memory reads, coalesced global stores): a ballot per round gives every sorted index
+  // its segment number inside the warp's chunk and the start of its segment
+  int run_heads = 0, run_last = -1;  // warp-uniform: heads so far in this chunk, last head index
+  int lslot[kPlanMaxRounds], lstart[kPlanMaxRounds];
+#pragma unroll
+  for (int r = 0; r < kPlanMaxRounds; ++r) {
+    if (r < rounds) {
+      const int k = warp * chunk + r * 32 + lane;
+      const bool head = k < n && (k == 0 || keyA[k] != keyA[k - 1]);
+      const unsigned hb = __ballot_sync(0xffffffffu, head);
+      const unsigned le = hb & (lt_mask | (1u << lane));
+      lslot[r] = run_heads + __popc(le) - 1;  // -1: the segment started in an earlier chunk
+      lstart[r] = le ? (k - lane + 31 - __clz(le)) : run_last;
+      run_heads += __popc(hb);
+      if (hb) run_last = k - lane + 31 - __clz(hb);
+    }
+  }
+  __shared__ int s_max[32];
+  __syncthreads();  // s_scan reuse
+  if (lane == 0) {
+    s_scan[warp] = run_heads;
+    s_max[warp] = run_last;
   }
   __syncthreads();
-  const int per = npad >> 10;
-  const int q0 = tid * per, q1 = q0 + per;
-  int cntL = 0, sumT = 0;
-  for (int x = q0; x < q1; ++x)
-    if (rankS[x] == 0) {
-      cntL += 1;
-      sumT += totalS[x];
-    }
-  int iL = cntL, iT = sumT;
-#pragma unroll
-  for (int o = 1; o < 32; o <<= 1) {
-    const int a = __shfl_up_sync(0xffffffffu, iL, o), b = __shfl_up_sync(0xffffffffu, iT, o);
-    if ((tid & 31) >= o) {
-      iL += a;
-      iT += b;
-    }
-  }
-  if ((tid & 31) == 31) {
-    s_scan[0][tid >> 5] = iL;
-    s_scan[1][tid >> 5] = iT;
-  }
-  __syncthreads();
-  int baseL = 0, baseT = 0, allL = 0;
+  int base = 0, all = 0, bmax = -1;
 #pragma unroll
   for (int w = 0; w < 32; ++w) {
-    const int a = s_scan[0][w], b = s_scan[1][w];
-    if (w < (tid >> 5)) {
-      baseL += a;
-      baseT += b;
+    const int v = s_scan[w];
+    if (w < warp) {
+      base += v;
+      bmax = max(bmax, s_max[w]);
     }
-    allL += a;
+    all += v;
   }
-  int slot = baseL + iL - cntL, off = baseT + iT - sumT;
-  for (int x = q0; x < q1; ++x)
-    if (rankS[x] == 0) {
-      slotS[x] = (unsigned short)slot;
-      offS[slot] = (unsigned short)off;
-      off += totalS[x];
-      ++slot;
-    }
-  __syncthreads();
+  PLAN_STAMP(21);
 #pragma unroll
-  for (int k = 0; k < kMaxPer; ++k) {
-    const int x = tid + k * 1024;
-    if (x < n) {
-      const int sl = slotS[leadv[k]];
-      const int rk = rankS[x];
-      t.out.pslot[x] = sl;
-      t.out.seg_pos[(int)offS[sl] + rk] = x;
-      if (rk == 0) t.out.uniq_rows[sl] = idv[k];
-    }
-    if (x < allL) {
-      t.out.seg_off[x] = offS[x];
-      t.out.done[x] = 0;
+  for (int r = 0; r < kPlanMaxRounds; ++r) {
+    if (r < rounds) {
+      const int k = warp * chunk + r * 32 + lane;
+      if (k < n) {
+        const int slot = base + lslot[r];
+        const int start = lstart[r] >= 0 ? lstart[r] : bmax;
+        t.out.seg_pos[k] = (int32_t)posA[k];
+        t.out.kinfo[k] = (int32_t)(((uint32_t)(k - start) << 16) | (uint32_t)slot);
+        if (k == start) {
+          t.out.uniq_rows[slot] = (int32_t)keyA[k];
+          t.out.seg_off[slot] = k;
+        }
+      }
     }
   }
   if (tid == 0) {
-    t.out.seg_off[allL] = n;
-    *t.out.n_uniq = allL;
+    t.out.seg_off[all] = n;
+    *t.out.n_uniq = all;
   }
+  PLAN_STAMP(22);
+}
+
+// scratch behind PlanBufs: kinfo[n_ids], done[n_ids] (done: zero before the first use, self re-arming)
+size_t plan_ws_bytes(int n_ids) { return sizeof(int32_t) * (2 * (size_t)n_ids + 16); }
+
+static size_t plan_smem_bytes(int npad) { return (size_t)npad * 12 + 256 * 33 * 4; }
+
+int plan_init() {  // opt in to the large dynamic shared memory once (outside any stream capture)
+  static bool attr_set = false;
+  if (!attr_set) {
+    MACR_CUDA(cudaFuncSetAttribute(batch_plan_sort_kernel,
+                                   cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                   (int)plan_smem_bytes(16384)));
+    attr_set = true;
+  }
+  return MACR_OK;
+}
+
+PlanBufs plan_carve(int32_t *uniq_rows, int32_t *seg_off, int32_t *seg_pos, int32_t *n_uniq,
+                    void *ws, int n_ids) {
+  int32_t *p = reinterpret_cast<int32_t *>(ws);
+  PlanBufs b;
+  b.uniq_rows = uniq_rows;
+  b.seg_off = seg_off;
+  b.seg_pos = seg_pos;
+  b.n_uniq = n_uniq;
+  b.kinfo = p;
+  b.done = p + n_ids;
+  return b;
+}
+
+static int radix_passes(int64_t table_rows) {
+  int bits = 1;
+  while (bits < 32 && ((int64_t)1 << bits) < table_rows) ++bits;
+  return (bits + 7) / 8;
+}
+
+int launch_batch_plan2(const int32_t *ids0, const StepState *st, int ids0_off, int n_ids0,
+                       int64_t rows0, PlanBufs out0, uint32_t *bitmap0, const int32_t *ids1,
+                       int ids1_off, int n_ids1, int64_t rows1, PlanBufs out1, uint32_t *bitmap1,
+                       cudaStream_t s) {
+  const int nmax = n_ids0 > n_ids1 ? n_ids0 : n_ids1;
+  MACR_CHECK_ARG(nmax <= 16384, "batch plan supports at most 16384 ids per table (batch <= 8192)");
+  int rci = plan_init();
+  if (rci) return rci;
+  PlanTable t0{ids0, ids0_off, n_ids0, radix_passes(rows0), out0, bitmap0};
+  PlanTable t1{ids1, ids1_off, n_ids1, radix_passes(rows1), out1, bitmap1};
+  int npad = 1024;
+  while (npad < nmax) npad <<= 1;
+  const int B = st ? n_ids0 : 0;  // trainer convention: table 0 = users (B ids)
+  batch_plan_sort_kernel<<<n_ids1 > 0 ? 2 : 1, 1024, plan_smem_bytes(npad), s>>>(t0, t1, st, B);
+  MACR_LAUNCH_CHECK();
+  return MACR_OK;
 }
 
 // touched-row bitmaps of both tables straight from the ids (lets the dense sweep start without
@@ -608,64 +770,13 @@ int launch_mark_touched(const StepState *st, const int32_t *ids, int B, uint32_t
   return MACR_OK;
 }
 
-// scratch layout behind PlanBufs (rank, pslot, done) and PlanTable (total, lead, counter)
-size_t plan_ws_bytes(int n_ids) { return sizeof(int32_t) * (5 * (size_t)n_ids + 16); }
-
-int plan_init() {  // opt in to 64 KB dynamic shared memory once (outside any stream capture)
-  static bool attr_set = false;
-  if (!attr_set) {
-    MACR_CUDA(cudaFuncSetAttribute(batch_plan_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                   16384 * 4));
-    MACR_CUDA(cudaFuncSetAttribute(batch_plan_tail_kernel,
-                                   cudaFuncAttributeMaxDynamicSharedMemorySize, 16384 * 8));
-    attr_set = true;
-  }
-  return MACR_OK;
-}
-
-PlanBufs plan_carve(int32_t *uniq_rows, int32_t *seg_off, int32_t *seg_pos, int32_t *n_uniq,
-                    void *ws, int n_ids) {
-  int32_t *p = reinterpret_cast<int32_t *>(ws);
-  PlanBufs b;
-  b.uniq_rows = uniq_rows;
-  b.seg_off = seg_off;
-  b.seg_pos = seg_pos;
-  b.n_uniq = n_uniq;
-  b.rank = p;
-  b.pslot = p + n_ids;
-  b.done = p + 2 * (size_t)n_ids;
-  b.total = p + 3 * (size_t)n_ids;
-  b.lead = p + 4 * (size_t)n_ids;
-  b.counter = reinterpret_cast<unsigned *>(p + 5 * (size_t)n_ids);
-  return b;
-}
-
-int launch_batch_plan2(const int32_t *ids0, const StepState *st, int ids0_off, int n_ids0,
-                       PlanBufs out0, uint32_t *bitmap0, const int32_t *ids1, int ids1_off,
-                       int n_ids1, PlanBufs out1, uint32_t *bitmap1, cudaStream_t s) {
-  const int nmax = n_ids0 > n_ids1 ? n_ids0 : n_ids1;
-  MACR_CHECK_ARG(nmax <= 16384, "batch plan supports at most 16384 ids per table (batch <= 8192)");
-  int rci = plan_init();
-  if (rci) return rci;
-  PlanTable t0{ids0, ids0_off, n_ids0, (n_ids0 + kPlanPos - 1) / kPlanPos, out0, bitmap0, out0.total, out0.lead,
-               out0.counter};
-  PlanTable t1{ids1, ids1_off, n_ids1, (n_ids1 + kPlanPos - 1) / kPlanPos, out1, bitmap1, out1.total, out1.lead,
-               out1.counter};
-  const size_t smem = (size_t)((nmax + 3) / 4) * 16;
-  const int B = st ? n_ids0 : 0;  // trainer convention: table 0 = users (B ids)
-  batch_plan_kernel<<<t0.blocks + t1.blocks, 1024, smem, s>>>(t0, t1, st, B);
-  MACR_LAUNCH_CHECK();
-  const size_t smem2 = (size_t)(((nmax + 1023) / 1024) * 1024) * 8;
-  batch_plan_tail_kernel<<<n_ids1 > 0 ? 2 : 1, 1024, smem2, s>>>(t0, t1, st, B);
-  MACR_LAUNCH_CHECK();
-  return MACR_OK;
-}
-
 // ---------------------------------------------------------------------------------------------
 // K5b: Adam.  The sweep is the HBM-bound part of the step: 24 B per table element
-// (read + write of var, m, v), 128-bit streaming accesses, 4 independent float4 triples in
-// flight per thread.  Rows touched by the batch are skipped here (bitmap) and handled by
-// adam_rows_kernel once their gradient is known, so the sweep can overlap the B x B grid.
+// (read + write of var, m, v), 128-bit streaming accesses, UNROLL independent float4 triples in
+// flight per thread.  Persistent grid: every CTA owns one contiguous, equally sized slice of the
+// (table 0 | table 1) element space, so there is no wave-quantisation tail.  Rows touched by the
+// batch are skipped here (bitmap) and handled by the row-gradient kernel once their gradient is
+// known, so the sweep overlaps the B x B grid.
 // ---------------------------------------------------------------------------------------------
 struct SweepTable {
   float4 *var, *m, *v;
@@ -673,39 +784,40 @@ struct SweepTable {
   const uint32_t *bitmap;
 };
 
+constexpr int kSweepThreads = 256;
+
 template <int UNROLL>
-__global__ void __launch_bounds__(256)
-adam_sweep_kernel(SweepTable t0, SweepTable t1, float lr_or_lrt, const StepState *st, float b1,
-                  float b2, float eps) {
+__global__ void __launch_bounds__(kSweepThreads, 3)
+adam_sweep_kernel(SweepTable t0, SweepTable t1, long long per_cta, float lr_or_lrt,
+                  const StepState *st, float b1, float b2, float eps) {
   const float lr_t = step_lr_t(st, lr_or_lrt);
   const long long total = t0.n4 + t1.n4;
-  const long long stride = (long long)gridDim.x * blockDim.x * UNROLL;
-  for (long long base = (long long)blockIdx.x * blockDim.x * UNROLL + threadIdx.x; base < total;
-       base += stride) {
+  const long long beg = (long long)blockIdx.x * per_cta;
+  const long long end = min(total, beg + per_cta);
+  for (long long base = beg + threadIdx.x; base < end; base += (long long)kSweepThreads * UNROLL) {
     float4 x[UNROLL], mm[UNROLL], vv[UNROLL];
-    float4 *px[UNROLL], *pm[UNROLL], *pv[UNROLL];
-    bool live[UNROLL];
+    long long off[UNROLL];
+    bool live[UNROLL], second[UNROLL];
 #pragma unroll
     for (int k = 0; k < UNROLL; ++k) {
-      long long e = base + (long long)k * blockDim.x;
-      live[k] = e < total;
+      long long e = base + (long long)k * kSweepThreads;
+      live[k] = e < end;
+      second[k] = e >= t0.n4;
+      if (second[k]) e -= t0.n4;
+      off[k] = e;
       if (live[k]) {
-        const bool second = e >= t0.n4;
-        const SweepTable &t = second ? t1 : t0;
-        if (second) e -= t0.n4;
+        const uint32_t *bm = second[k] ? t1.bitmap : t0.bitmap;
         const long long row = e >> 4;
-        if (t.bitmap && ((t.bitmap[row >> 5] >> (row & 31)) & 1u)) live[k] = false;
-        px[k] = t.var + e;
-        pm[k] = t.m + e;
-        pv[k] = t.v + e;
+        if (bm && ((bm[row >> 5] >> (row & 31)) & 1u)) live[k] = false;
       }
     }
 #pragma unroll
     for (int k = 0; k < UNROLL; ++k)
       if (live[k]) {
-        x[k] = ld_stream(px[k]);
-        mm[k] = ld_stream(pm[k]);
-        vv[k] = ld_stream(pv[k]);
+        const SweepTable &t = second[k] ? t1 : t0;
+        x[k] = ld_stream(t.var + off[k]);
+        mm[k] = ld_stream(t.m + off[k]);
+        vv[k] = ld_stream(t.v + off[k]);
       }
 #pragma unroll
     for (int k = 0; k < UNROLL; ++k)
@@ -719,11 +831,22 @@ adam_sweep_kernel(SweepTable t0, SweepTable t1, float lr_or_lrt, const StepState
         adam_decay_only(x[k].y, mm[k].y, vv[k].y, lr_t, b1, b2, eps);
         adam_decay_only(x[k].z, mm[k].z, vv[k].z, lr_t, b1, b2, eps);
         adam_decay_only(x[k].w, mm[k].w, vv[k].w, lr_t, b1, b2, eps);
-        st_stream(px[k], x[k]);
-        st_stream(pm[k], mm[k]);
-        st_stream(pv[k], vv[k]);
+        const SweepTable &t = second[k] ? t1 : t0;
+        st_stream(t.var + off[k], x[k]);
+        st_stream(t.m + off[k], mm[k]);
+        st_stream(t.v + off[k], vv[k]);
       }
   }
+}
+
+static int sweep_ctas_per_sm() {
+  static int v = 0;
+  if (v == 0) {
+    const char *e = getenv("MACR_SWEEP_CTAS_PER_SM");  // tuning knob, default 3
+    v = e ? atoi(e) : 3;
+    if (v < 1 || v > 8) v = 3;
+  }
+  return v;
 }
 
 int launch_adam_sweep2(float *var0, float *m0, float *v0, int64_t rows0, const uint32_t *bm0,
@@ -735,45 +858,138 @@ int launch_adam_sweep2(float *var0, float *m0, float *v0, int64_t rows0, const u
   const long long total = t0.n4 + t1.n4;
   if (total == 0) return MACR_OK;
   constexpr int UNROLL = 4;
-  long long blocks = (total + 256LL * UNROLL - 1) / (256LL * UNROLL);
-  const long long cap = (long long)sm_count() * 8;
-  if (blocks > cap) blocks = cap;
-  adam_sweep_kernel<UNROLL><<<(int)blocks, 256, 0, s>>>(t0, t1, lr_t, st, b1, b2, eps);
+  long long ctas = (long long)sm_count() * sweep_ctas_per_sm();
+  const long long min_per = (long long)kSweepThreads * UNROLL;
+  if (ctas * min_per > total) ctas = (total + min_per - 1) / min_per;
+  long long per = (total + ctas - 1) / ctas;
+  per = (per + kSweepThreads - 1) / kSweepThreads * kSweepThreads;  // whole 4 KB lines per warp row
+  ctas = (total + per - 1) / per;
+  adam_sweep_kernel<UNROLL><<<(int)ctas, kSweepThreads, 0, s>>>(t0, t1, per, lr_t, st, b1, b2, eps);
   MACR_LAUNCH_CHECK();
   return MACR_OK;
 }
 
 // ---------------------------------------------------------------------------------------------
-// row gradients of the unique touched rows, summed per table row (the IndexedSlices dedup).
-//   user row r :  sum_b  dyp_b*Ie[p_b] + dyn_b*Ie[n_b] + dsu_b*w_user (+ lam*Ur[r])
-//   item row r :  sum_q  dy_q*Ue[u_b] + ds_q*w (+ lam*Ir[r]),  q<B: pos role, q>=B: neg role
-// Popular items own segments hundreds of positions long, so the unit of work is <= 32
-// consecutive entries of one segment: the warp launched for position q works only if
-// rank[q] % 32 == 0.  Its lanes fetch the 32 entries' metadata with one coalesced access each,
-// then the row gathers (lane l owns dims 2l, 2l+1) are issued 4 entries at a time.  Segments
-// longer than one unit leave per-unit partials in `unit_part`; the last unit to arrive
-// (per-segment ticket) adds them in unit order, so the sum is order-deterministic.
+// Row gradients of the unique touched rows, summed per table row (the IndexedSlices dedup), and
+// -- for MF -- TF's sparse Adam formula applied to each such row as soon as its sum is complete.
+//   user row r :  sum_b  dyp_b*pe_b + dyn_b*ne_b + dsu_b*w_user (+ lam*ue_b)
+//   item row r :  sum_q  dy_q*ue_b + ds_q*w (+ lam*ie_q),  q<B: pos role, q>=B: neg role
+// Every embedding row is read from the step's snapshot [3][B][64] (users | pos | neg, written by
+// gather_dots), indexed by batch position -- so updating a table row in place cannot disturb the
+// gradient of another row, and no id indirection is left in this kernel.
+// Popular items own segments hundreds of positions long, so the unit of work is <= 32 consecutive
+// entries of one segment: the warp of sorted index k works only if (k - seg_off) % 32 == 0.  Its
+// lanes fetch the 32 entries' metadata with one coalesced access each, then the row loads (lane l
+// owns dims 2l, 2l+1) are issued 4 entries at a time.  Segments longer than one unit leave
+// per-unit partials in `unit_part`; the last unit to arrive (per-segment ticket) adds them in
+// unit order, so the sum is order-deterministic.
 // Extra CTAs at the end of the grid reduce grad(w) = sum_b dsp_b*pe_b + dsn_b*ne_b and
 // grad(w_user) = sum_b dsu_b*ue_b into per-CTA partials (fixed composition, fixed order).
+// With tail.fused the last CTA of the whole grid (arrival ticket) also runs the step tail:
+// ApplyAdam on w / w_user, the loss reduction and the step-state advance.
 // ---------------------------------------------------------------------------------------------
 constexpr int kRowWarps = 8;
 constexpr int kUnit = 32;
 constexpr int kWgradPerCta = 64;  // batch positions per w-gradient CTA
 
+// ApplyAdam on w / w_user from the per-CTA gradient partials, the loss reduction, and the
+// step-state advance (adam.py _finish: beta powers *= beta).  Runs in ONE CTA of NT threads.
+template <int NT>
+__device__ void step_tail_body(float *w, float *mw, float *vw, float *wu, float *mwu, float *vwu,
+                               const float *gw_part, const float *gwu_part, int n_part,
+                               const float *losspart, int nparts, const float *litem,
+                               const float *luser, const float *regsq, int B,
+                               const macr_hparams &hp, StepState *st, int train, double *sh,
+                               float (*shg)[kD]) {
+  constexpr int NW = NT / 32, GR = NT / (2 * kD);  // warps; partial groups per vector
+  const int tid = threadIdx.x;
+  const float lr_t = step_lr_t(st, hp.lr);
+  if (train) {
+    const int k = tid & 63, which = (tid >> 6) & 1, grp = tid / (2 * kD);
+    const float *src = which ? gwu_part : gw_part;
+    float a = 0.f;
+    for (int q = grp; q < n_part; q += GR) a += __ldcg(src + (long long)q * kD + k);
+    shg[which * GR + grp][k] = a;
+  }
+  double a0 = 0, a1 = 0, a2 = 0, a3 = 0;
+  for (int k = tid; k < nparts; k += NT) a0 += __ldcg(losspart + k);
+  for (int k = tid; k < B; k += NT) {
+    a1 += __ldcg(litem + k);
+    a2 += __ldcg(luser + k);
+    a3 += __ldcg(regsq + k);
+  }
+  // one fixed-shape reduction tree for the four sums: warp shuffles, then the warp leaders
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    a0 += __shfl_xor_sync(0xffffffffu, a0, o);
+    a1 += __shfl_xor_sync(0xffffffffu, a1, o);
+    a2 += __shfl_xor_sync(0xffffffffu, a2, o);
+    a3 += __shfl_xor_sync(0xffffffffu, a3, o);
+  }
+  if ((tid & 31) == 0) {
+    sh[(tid >> 5) * 4 + 0] = a0;
+    sh[(tid >> 5) * 4 + 1] = a1;
+    sh[(tid >> 5) * 4 + 2] = a2;
+    sh[(tid >> 5) * 4 + 3] = a3;
+  }
+  __syncthreads();  // also publishes shg
+  if (tid == 0) {
+    a0 = a1 = a2 = a3 = 0;
+    for (int k = 0; k < NW; ++k) {
+      a0 += sh[k * 4 + 0];
+      a1 += sh[k * 4 + 1];
+      a2 += sh[k * 4 + 2];
+      a3 += sh[k * 4 + 3];
+    }
+  }
+  if (train && tid < 2 * kD) {
+    const int k = tid & 63, which = tid >> 6;
+    float g = 0.f;
+#pragma unroll
+    for (int q = 0; q < GR; ++q) g += shg[which * GR + q][k];
+    const float omb1 = __fsub_rn(1.0f, hp.beta1), omb2 = __fsub_rn(1.0f, hp.beta2);
+    float *var = which ? wu : w, *m = which ? mwu : mw, *v = which ? vwu : vw;
+    const float mn = __fadd_rn(m[k], __fmul_rn(__fsub_rn(g, m[k]), omb1));
+    const float vn = __fadd_rn(v[k], __fmul_rn(__fsub_rn(__fmul_rn(g, g), v[k]), omb2));
+    m[k] = mn;
+    v[k] = vn;
+    var[k] = __fsub_rn(var[k], __fdiv_rn(__fmul_rn(mn, lr_t), __fadd_rn(__fsqrt_rn(vn), hp.eps)));
+  }
+  __syncthreads();  // every lr_t read of this step is done
+  if (tid == 0) {
+    const double invB = 1.0 / (double)B;
+    const float l_ori = (float)(-0.6931471805599453 * a0 * invB * invB);
+    const float l_item = (float)(a1 * invB), l_user = (float)(a2 * invB);
+    const float reg = hp.decay * ((float)(a3 * 0.5) / (float)hp.batch_size_flag);
+    const float mf = l_ori + hp.alpha * l_item + hp.beta * l_user;
+    float *out = st->loss_base + st->step_idx * 4;
+    out[0] = mf + reg;
+    out[1] = mf;
+    out[2] = reg;
+    out[3] = l_ori;
+    if (train) {
+      st->b1p = __fmul_rn(st->b1p, hp.beta1);
+      st->b2p = __fmul_rn(st->b2p, hp.beta2);
+      st->t += 1;
+    }
+    st->step_idx += 1;
+  }
+}
+
 __global__ void __launch_bounds__(kRowWarps * 32)
-row_grads_kernel(const float *__restrict__ Ue, const float *__restrict__ Ie,
-                 const float *__restrict__ Ur, const float *__restrict__ Ir,
-                 const float *__restrict__ w, const float *__restrict__ wu, const StepState *st,
-                 const int32_t *u_, const int32_t *p_, const int32_t *n_, int B,
-                 const float *__restrict__ d_yp, const float *__restrict__ d_yn,
-                 const float *__restrict__ d_sp, const float *__restrict__ d_sn,
-                 const float *__restrict__ d_su, float lam, PlanBufs planU, PlanBufs planI,
-                 float *__restrict__ gU, float *__restrict__ gI, float *unit_part, int pos_ctas,
-                 float *__restrict__ gw_part, float *__restrict__ gwu_part) {
+row_grads_kernel(const float *__restrict__ snap, const float *__restrict__ w,
+                 const float *__restrict__ wu, int B, const float *__restrict__ d_yp,
+                 const float *__restrict__ d_yn, const float *__restrict__ d_sp,
+                 const float *__restrict__ d_sn, const float *__restrict__ d_su, float lam,
+                 PlanBufs planU, PlanBufs planI, float *__restrict__ gU, float *__restrict__ gI,
+                 float *unit_part, int pos_ctas, float *__restrict__ gw_part,
+                 float *__restrict__ gwu_part, AdamTabs tabs, TailArgs tail) {
   __shared__ float2 sW[kRowWarps][32], sWU[kRowWarps][32];
+  __shared__ double sTail[kRowWarps * 4];
+  __shared__ float sTailG[2 * (kRowWarps * 32 / (2 * kD))][kD];
+  __shared__ int sLast;
   const int lane = threadIdx.x & 31, wl = threadIdx.x >> 5;
-  const int32_t *u = step_ids(st, u_, B, 0), *p = step_ids(st, p_, B, 1),
-                *n = step_ids(st, n_, B, 2);
+  const float *snapU = snap, *snapP = snap + (long long)B * kD, *snapN = snap + 2LL * B * kD;
 
   if ((int)blockIdx.x >= pos_ctas) {  // ---- grad(w), grad(w_user) partials ----
     const int cta = blockIdx.x - pos_ctas;
@@ -784,9 +1000,9 @@ row_grads_kernel(const float *__restrict__ Ue, const float *__restrict__ Ie,
       const int b = b0 + k;
       if (b < B) {
         const float dsp = d_sp[b], dsn = d_sn[b], dsu = d_su[b];
-        const float2 pe = reinterpret_cast<const float2 *>(Ie + (long long)p[b] * kD)[lane];
-        const float2 ne = reinterpret_cast<const float2 *>(Ie + (long long)n[b] * kD)[lane];
-        const float2 ue = reinterpret_cast<const float2 *>(Ue + (long long)u[b] * kD)[lane];
+        const float2 pe = reinterpret_cast<const float2 *>(snapP + (long long)b * kD)[lane];
+        const float2 ne = reinterpret_cast<const float2 *>(snapN + (long long)b * kD)[lane];
+        const float2 ue = reinterpret_cast<const float2 *>(snapU + (long long)b * kD)[lane];
         aw.x += dsp * pe.x + dsn * ne.x;
         aw.y += dsp * pe.y + dsn * ne.y;
         awu.x += dsu * ue.x;
@@ -808,116 +1024,184 @@ row_grads_kernel(const float *__restrict__ Ue, const float *__restrict__ Ie,
       reinterpret_cast<float2 *>(gw_part + (long long)cta * kD)[lane] = a;
       reinterpret_cast<float2 *>(gwu_part + (long long)cta * kD)[lane] = c;
     }
-    return;
-  }
-
-  const int wid = blockIdx.x * kRowWarps + wl;  // one warp per batch position: users, then items
-  if (wid >= 3 * B) return;
-  const bool item = wid >= B;
-  const int q = item ? wid - B : wid;
-  const PlanBufs &pl = item ? planI : planU;
-  const int rk = pl.rank[q];
-  if (rk % kUnit != 0) return;
-  const int slot = pl.pslot[q];
-  const int s0 = pl.seg_off[slot], s1 = pl.seg_off[slot + 1];
-  const int total = s1 - s0;
-  const int base = s0 + rk;
-  const int cnt = min(kUnit, s1 - base);
-  const long long r = pl.uniq_rows[slot];
-  const float2 bias = reinterpret_cast<const float2 *>(item ? w : wu)[lane];
-  const float2 raw = reinterpret_cast<const float2 *>((item ? Ir : Ur) + r * kD)[lane];
-  const float lx = lam * raw.x, ly = lam * raw.y;
-
-  // metadata of this unit's entries, one entry per lane
-  int ra = 0, rb = 0;
-  float ca = 0.f, cb = 0.f, cs = 0.f;
-  if (lane < cnt) {
-    const int qq = pl.seg_pos[base + lane];
-    if (!item) {
-      ra = p[qq];
-      rb = n[qq];
-      ca = d_yp[qq];
-      cb = d_yn[qq];
-      cs = d_su[qq];
-    } else {
-      const bool is_pos = qq < B;
-      const int b = is_pos ? qq : qq - B;
-      ra = u[b];
-      ca = is_pos ? d_yp[b] : d_yn[b];
-      cs = is_pos ? d_sp[b] : d_sn[b];
-    }
-  }
-  const float *tabA = item ? Ue : Ie;
-  float2 g = make_float2(0.f, 0.f);
-  for (int e0 = 0; e0 < cnt; e0 += 4) {
-    float2 va[4], vb[4];
-    float fa[4], fb[4], fs[4];
-#pragma unroll
-    for (int k = 0; k < 4; ++k) {
-      const int e = min(e0 + k, cnt - 1);
-      const int ia = __shfl_sync(0xffffffffu, ra, e);
-      const int ib = __shfl_sync(0xffffffffu, rb, e);
-      fa[k] = __shfl_sync(0xffffffffu, ca, e);
-      fb[k] = __shfl_sync(0xffffffffu, cb, e);
-      fs[k] = __shfl_sync(0xffffffffu, cs, e);
-      va[k] = reinterpret_cast<const float2 *>(tabA + (long long)ia * kD)[lane];
-      vb[k] = item ? make_float2(0.f, 0.f)
-                   : reinterpret_cast<const float2 *>(Ie + (long long)ib * kD)[lane];
-    }
-#pragma unroll
-    for (int k = 0; k < 4; ++k) {
-      if (e0 + k < cnt) {
-        float x = fa[k] * va[k].x + fb[k] * vb[k].x + fs[k] * bias.x;
-        float y = fa[k] * va[k].y + fb[k] * vb[k].y + fs[k] * bias.y;
-        if (lam != 0.f) {
-          x += lx;
-          y += ly;
+  } else {
+    const int wid = blockIdx.x * kRowWarps + wl;  // one warp per sorted index: users, then items
+    const bool item = wid >= B;
+    const int k = item ? wid - B : wid;
+    const PlanBufs &pl = item ? planI : planU;
+    const int n_ids = item ? 2 * B : B;
+    unsigned info = 0x10000u;  // rank 1: not a unit start
+    if (wid < 3 * B) info = (unsigned)pl.kinfo[k];
+    const int rk = (int)(info >> 16), slot = (int)(info & 0xffffu);
+    if (rk % kUnit == 0) {  // this warp owns one unit of the segment
+      // everything that depends only on (k, slot) is requested at once
+      const int s0 = k - rk;
+      const int s1 = pl.seg_off[slot + 1];
+      const int qq_spec = (k + lane < n_ids) ? pl.seg_pos[k + lane] : 0;
+      const long long r = pl.uniq_rows[slot];
+      const int q0 = pl.seg_pos[s0];
+      const int total = s1 - s0;
+      const int cnt = min(kUnit, s1 - k);
+      const float2 bias = reinterpret_cast<const float2 *>(item ? w : wu)[lane];
+      // metadata of this unit's entries, one entry per lane
+      int ra = 0;  // snapshot row of the partner (item unit: user row b; user unit: position b)
+      float ca = 0.f, cb = 0.f, cs = 0.f;
+      if (lane < cnt) {
+        const int qq = qq_spec;
+        if (!item) {
+          ra = qq;
+          ca = d_yp[qq];
+          cb = d_yn[qq];
+          cs = d_su[qq];
+        } else {
+          const bool is_pos = qq < B;
+          ra = is_pos ? qq : qq - B;
+          ca = is_pos ? d_yp[ra] : d_yn[ra];
+          cs = is_pos ? d_sp[ra] : d_sn[ra];
         }
-        g.x += x;
-        g.y += y;
+      }
+      // the row's Adam state is requested now and consumed after the gradient is complete
+      float2 ax = make_float2(0.f, 0.f), am = ax, av = ax;
+      float2 *pv = nullptr, *pm = nullptr, *pvv = nullptr;
+      if (tabs.U != nullptr && total <= kUnit) {
+        pv = reinterpret_cast<float2 *>((item ? tabs.I : tabs.U) + r * kD) + lane;
+        pm = reinterpret_cast<float2 *>((item ? tabs.mI : tabs.mU) + r * kD) + lane;
+        pvv = reinterpret_cast<float2 *>((item ? tabs.vI : tabs.vU) + r * kD) + lane;
+        ax = *pv;
+        am = *pm;
+        av = *pvv;
+      }
+      float lx = 0.f, ly = 0.f;
+      if (lam != 0.f) {  // L2 slice of the row itself: any position of the segment holds it
+        const float2 raw = reinterpret_cast<const float2 *>(
+            (item ? snapP : snapU) + (long long)q0 * kD)[lane];
+        lx = lam * raw.x;
+        ly = lam * raw.y;
+      }
+      float2 g = make_float2(0.f, 0.f);
+      for (int e0 = 0; e0 < cnt; e0 += 4) {
+        float2 va[4], vb[4];
+        float fa[4], fb[4], fs[4];
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+          const int e = min(e0 + q, cnt - 1);
+          const int ia = __shfl_sync(0xffffffffu, ra, e);
+          fa[q] = __shfl_sync(0xffffffffu, ca, e);
+          fb[q] = __shfl_sync(0xffffffffu, cb, e);
+          fs[q] = __shfl_sync(0xffffffffu, cs, e);
+          if (item) {
+            va[q] = reinterpret_cast<const float2 *>(snapU + (long long)ia * kD)[lane];
+            vb[q] = make_float2(0.f, 0.f);
+          } else {
+            va[q] = reinterpret_cast<const float2 *>(snapP + (long long)ia * kD)[lane];
+            vb[q] = reinterpret_cast<const float2 *>(snapN + (long long)ia * kD)[lane];
+          }
+        }
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+          if (e0 + q < cnt) {
+            float x = fa[q] * va[q].x + fb[q] * vb[q].x + fs[q] * bias.x;
+            float y = fa[q] * va[q].y + fb[q] * vb[q].y + fs[q] * bias.y;
+            if (lam != 0.f) {
+              x += lx;
+              y += ly;
+            }
+            g.x += x;
+            g.y += y;
+          }
+        }
+      }
+      bool final_here = total <= kUnit;
+      if (!final_here) {
+        // multi-unit segment: publish the partial, the last unit to arrive folds them in order
+        float *mypart = unit_part + ((long long)(item ? B : 0) + k) * kD;
+        __stcg(reinterpret_cast<float2 *>(mypart) + lane, g);
+        __syncwarp();
+        int ticket = 0;
+        if (lane == 0) {
+          __threadfence();
+          ticket = atomicAdd(&pl.done[slot], 1);
+        }
+        ticket = __shfl_sync(0xffffffffu, ticket, 0);
+        const int n_units = (total + kUnit - 1) / kUnit;
+        if (ticket == n_units - 1) {
+          if (lane == 0) {
+            __threadfence();
+            pl.done[slot] = 0;  // re-armed for the next step
+          }
+          __syncwarp();
+          g = make_float2(0.f, 0.f);
+          for (int un = 0; un < n_units; ++un) {
+            const float2 v = __ldcg(reinterpret_cast<const float2 *>(
+                                        unit_part + ((long long)(item ? B : 0) + s0 + un * kUnit) * kD) + lane);
+            g.x += v.x;
+            g.y += v.y;
+          }
+          final_here = true;
+          if (tabs.U != nullptr) {
+            pv = reinterpret_cast<float2 *>((item ? tabs.I : tabs.U) + r * kD) + lane;
+            pm = reinterpret_cast<float2 *>((item ? tabs.mI : tabs.mU) + r * kD) + lane;
+            pvv = reinterpret_cast<float2 *>((item ? tabs.vI : tabs.vU) + r * kD) + lane;
+            ax = *pv;
+            am = *pm;
+            av = *pvv;
+          }
+        }
+      }
+      if (final_here) {
+        if (tabs.U == nullptr) {
+          reinterpret_cast<float2 *>((item ? gI : gU) + (long long)slot * kD)[lane] = g;
+        } else {  // adam.py _apply_sparse_shared on this row
+          const float lr_t = step_lr_t(tabs.st, tabs.lr);
+          const float omb1 = __fsub_rn(1.0f, tabs.b1), omb2 = __fsub_rn(1.0f, tabs.b2);
+          adam_with_grad(ax.x, am.x, av.x, g.x, lr_t, tabs.b1, tabs.b2, omb1, omb2, tabs.eps);
+          adam_with_grad(ax.y, am.y, av.y, g.y, lr_t, tabs.b1, tabs.b2, omb1, omb2, tabs.eps);
+          *pv = ax;
+          *pm = am;
+          *pvv = av;
+          uint32_t *bm = item ? tabs.bmI : tabs.bmU;
+          if (bm && lane == 0) atomicAnd(&bm[r >> 5], ~(1u << (r & 31)));
+        }
       }
     }
   }
-  float *gout = (item ? gI : gU) + (long long)slot * kD;
-  if (total <= kUnit) {
-    reinterpret_cast<float2 *>(gout)[lane] = g;
-    return;
+  if (!tail.fused) return;
+  // ---- last CTA of the grid: the step tail ----
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    __threadfence();  // cumulative over the CTA's writes ordered by the barrier above
+    const bool last = atomicAdd(tail.ticket, 1u) == gridDim.x - 1;
+    if (last) {
+      __threadfence();
+      *tail.ticket = 0;  // re-armed for the next step
+    }
+    sLast = last;
   }
-  // multi-unit segment: publish the partial, the last unit to arrive folds them in unit order
-  float *mypart = unit_part + ((long long)(item ? B : 0) + q) * kD;
-  reinterpret_cast<float2 *>(mypart)[lane] = g;
-  __threadfence();
-  int ticket = 0;
-  if (lane == 0) ticket = atomicAdd(&pl.done[slot], 1);
-  ticket = __shfl_sync(0xffffffffu, ticket, 0);
-  const int n_units = (total + kUnit - 1) / kUnit;
-  if (ticket != n_units - 1) return;
-  __threadfence();
-  float2 acc = make_float2(0.f, 0.f);
-  for (int k = 0; k < n_units; ++k) {
-    const int qk = pl.seg_pos[s0 + k * kUnit];
-    const float2 v = __ldcg(reinterpret_cast<const float2 *>(
-                                unit_part + ((long long)(item ? B : 0) + qk) * kD) + lane);
-    acc.x += v.x;
-    acc.y += v.y;
-  }
-  reinterpret_cast<float2 *>(gout)[lane] = acc;
+  __syncthreads();
+  if (!sLast) return;
+  step_tail_body<kRowWarps * 32>(tail.w, tail.mw, tail.vw, tail.wu, tail.mwu, tail.vwu, gw_part,
+                                 gwu_part, gridDim.x - pos_ctas, tail.losspart, tail.nparts,
+                                 tail.litem, tail.luser, tail.regsq, B, tail.hp, tail.st, 1, sTail,
+                                 sTailG);
 }
 
 int row_grads_max_parts(int B) { return (B + kWgradPerCta - 1) / kWgradPerCta; }
 
-int launch_row_grads(const float *Ue, const float *Ie, const float *Ur, const float *Ir,
-                     const float *w, const float *wu, const StepState *st, const int32_t *u,
-                     const int32_t *p, const int32_t *n, int B, const float *d_yp,
+// tabs == nullptr: summed rows to gU / gI; tail == nullptr: no fused step tail
+int launch_row_grads(const float *snap, const float *w, const float *wu, int B, const float *d_yp,
                      const float *d_yn, const float *d_sp, const float *d_sn, const float *d_su,
                      float lam, PlanBufs planU, PlanBufs planI, float *gU, float *gI,
                      float *unit_part, float *gw_part, float *gwu_part, int *n_part,
-                     cudaStream_t s) {
+                     const AdamTabs *tabs, const TailArgs *tail, cudaStream_t s) {
   const int pos_ctas = (3 * B + kRowWarps - 1) / kRowWarps;
   const int w_ctas = row_grads_max_parts(B);
+  AdamTabs tb{};
+  if (tabs) tb = *tabs;
+  TailArgs tl{};
+  if (tail) tl = *tail;
   row_grads_kernel<<<pos_ctas + w_ctas, kRowWarps * 32, 0, s>>>(
-      Ue, Ie, Ur, Ir, w, wu, st, u, p, n, B, d_yp, d_yn, d_sp, d_sn, d_su, lam, planU, planI, gU,
-      gI, unit_part, pos_ctas, gw_part, gwu_part);
+      snap, w, wu, B, d_yp, d_yn, d_sp, d_sn, d_su, lam, planU, planI, gU, gI, unit_part, pos_ctas,
+      gw_part, gwu_part, tb, tl);
   MACR_LAUNCH_CHECK();
   if (n_part) *n_part = w_ctas;
   return MACR_OK;
@@ -1042,27 +1326,9 @@ int launch_adam_dense(float *var, float *m, float *v, const float *grad, int64_t
   return MACR_OK;
 }
 
-// end-of-step state advance (adam.py _finish: beta powers *= beta) -- one thread
-__global__ void step_advance_kernel(StepState *st, float b1, float b2, int train) {
-  if (threadIdx.x == 0 && blockIdx.x == 0) {
-    if (train) {
-      st->b1p = __fmul_rn(st->b1p, b1);
-      st->b2p = __fmul_rn(st->b2p, b2);
-      st->t += 1;
-    }
-    st->step_idx += 1;
-  }
-}
-
-int launch_step_state(StepState *st, int, float, float b1, float b2, int train, cudaStream_t s) {
-  step_advance_kernel<<<1, 32, 0, s>>>(st, b1, b2, train);
-  MACR_LAUNCH_CHECK();
-  return MACR_OK;
-}
-
 // ---------------------------------------------------------------------------------------------
-// last kernel of a step (one CTA): ApplyAdam on w / w_user from the per-CTA gradient partials,
-// the loss reduction, and the step-state advance (adam.py _finish: beta powers *= beta).
+// stand-alone step tail (one CTA): LightGCN steps (the dense Adam kernels read the step state, so
+// the tail cannot ride on the row-gradient kernel) and loss-only steps.
 // ---------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(1024)
 step_tail_kernel(float *w, float *mw, float *vw, float *wu, float *mwu, float *vwu,
@@ -1070,80 +1336,10 @@ step_tail_kernel(float *w, float *mw, float *vw, float *wu, float *mwu, float *v
                  const float *__restrict__ losspart, int nparts, const float *__restrict__ litem,
                  const float *__restrict__ luser, const float *__restrict__ regsq, int B,
                  macr_hparams hp, StepState *st, int train) {
-  __shared__ double sh[1024];
-  __shared__ float shg[2][8][kD];
-  const int tid = threadIdx.x;
-  const float lr_t = step_lr_t(st, hp.lr);
-  if (train) {
-    const int k = tid & 63, which = (tid >> 6) & 1, grp = tid >> 7;  // 8 groups x 2 vectors x 64
-    const float *src = which ? gwu_part : gw_part;
-    float a = 0.f;
-    for (int q = grp; q < n_part; q += 8) a += src[(long long)q * kD + k];
-    shg[which][grp][k] = a;
-  }
-  double a0 = 0, a1 = 0, a2 = 0, a3 = 0;
-  for (int k = tid; k < nparts; k += 1024) a0 += losspart[k];
-  for (int k = tid; k < B; k += 1024) {
-    a1 += litem[k];
-    a2 += luser[k];
-    a3 += regsq[k];
-  }
-  // one fixed-shape reduction tree for the four sums: warp shuffles, then the 32 warp leaders
-#pragma unroll
-  for (int o = 16; o > 0; o >>= 1) {
-    a0 += __shfl_xor_sync(0xffffffffu, a0, o);
-    a1 += __shfl_xor_sync(0xffffffffu, a1, o);
-    a2 += __shfl_xor_sync(0xffffffffu, a2, o);
-    a3 += __shfl_xor_sync(0xffffffffu, a3, o);
-  }
-  if ((tid & 31) == 0) {
-    sh[(tid >> 5) * 4 + 0] = a0;
-    sh[(tid >> 5) * 4 + 1] = a1;
-    sh[(tid >> 5) * 4 + 2] = a2;
-    sh[(tid >> 5) * 4 + 3] = a3;
-  }
-  __syncthreads();  // also publishes shg
-  if (tid == 0) {
-    a0 = a1 = a2 = a3 = 0;
-    for (int k = 0; k < 32; ++k) {
-      a0 += sh[k * 4 + 0];
-      a1 += sh[k * 4 + 1];
-      a2 += sh[k * 4 + 2];
-      a3 += sh[k * 4 + 3];
-    }
-  }
-  if (train && tid < 2 * kD) {
-    const int k = tid & 63, which = tid >> 6;
-    float g = 0.f;
-#pragma unroll
-    for (int q = 0; q < 8; ++q) g += shg[which][q][k];
-    const float omb1 = __fsub_rn(1.0f, hp.beta1), omb2 = __fsub_rn(1.0f, hp.beta2);
-    float *var = which ? wu : w, *m = which ? mwu : mw, *v = which ? vwu : vw;
-    const float mn = __fadd_rn(m[k], __fmul_rn(__fsub_rn(g, m[k]), omb1));
-    const float vn = __fadd_rn(v[k], __fmul_rn(__fsub_rn(__fmul_rn(g, g), v[k]), omb2));
-    m[k] = mn;
-    v[k] = vn;
-    var[k] = __fsub_rn(var[k], __fdiv_rn(__fmul_rn(mn, lr_t), __fadd_rn(__fsqrt_rn(vn), hp.eps)));
-  }
-  __syncthreads();  // every lr_t read of this step is done
-  if (tid == 0) {
-    const double invB = 1.0 / (double)B;
-    const float l_ori = (float)(-0.6931471805599453 * a0 * invB * invB);
-    const float l_item = (float)(a1 * invB), l_user = (float)(a2 * invB);
-    const float reg = hp.decay * ((float)(a3 * 0.5) / (float)hp.batch_size_flag);
-    const float mf = l_ori + hp.alpha * l_item + hp.beta * l_user;
-    float *out = st->loss_base + st->step_idx * 4;
-    out[0] = mf + reg;
-    out[1] = mf;
-    out[2] = reg;
-    out[3] = l_ori;
-    if (train) {
-      st->b1p = __fmul_rn(st->b1p, hp.beta1);
-      st->b2p = __fmul_rn(st->b2p, hp.beta2);
-      st->t += 1;
-    }
-    st->step_idx += 1;
-  }
+  __shared__ double sh[32 * 4];
+  __shared__ float shg[16][kD];
+  step_tail_body<1024>(w, mw, vw, wu, mwu, vwu, gw_part, gwu_part, n_part, losspart, nparts, litem,
+                       luser, regsq, B, hp, st, train, sh, shg);
 }
 
 int launch_step_tail(float *w, float *mw, float *vw, float *wu, float *mwu, float *vwu,

@@ -27,20 +27,18 @@ struct GridWs {  // carve-up of the grid kernel's partial-sum workspace
   float *colP, *colN;  // [nblk(i)][Bpad]
   float *losspart;     // [nblk*nblk]
   float *litem, *luser;  // [Bpad]
+  unsigned *tickets;     // [2*nblk] band arrival counters (zero before the first launch)
   size_t bytes;
 };
 GridWs grid_ws_layout(int B, void *base);
 
 struct PlanBufs {  // output of one batch_plan over n_ids ids (+ its scratch)
-  int32_t *uniq_rows;  // [n_uniq] table row of every segment, first-occurrence order
-  int32_t *seg_off;    // [n_uniq+1]
-  int32_t *seg_pos;    // [n_ids] batch positions, ascending inside a segment
+  int32_t *uniq_rows;  // [n_uniq] table row of every segment, ascending
+  int32_t *seg_off;    // [n_uniq+1] offsets into the sorted order
+  int32_t *seg_pos;    // [n_ids] batch positions sorted by (row, position)
   int32_t *n_uniq;     // device scalar
-  int32_t *rank;       // [n_ids] rank of a position inside its segment
-  int32_t *pslot;      // [n_ids] segment index of a position
+  int32_t *kinfo;      // [n_ids] (rank inside the segment) << 16 | segment index, per sorted index
   int32_t *done;       // [n_ids] per-segment arrival counters (multi-unit segments)
-  int32_t *total, *lead;  // [n_ids] scratch of the planning kernel
-  unsigned *counter;      // last-CTA-done ticket
 };
 PlanBufs plan_carve(int32_t *uniq_rows, int32_t *seg_off, int32_t *seg_pos, int32_t *n_uniq,
                     void *ws, int n_ids);
@@ -51,7 +49,8 @@ int launch_step_state(StepState *st, int B, float lr, float b1, float b2, int tr
 int launch_gather_dots(const float *Ue, const float *Ie, const float *Ur, const float *Ir,
                        const float *w, const float *wu, const int32_t *u, const int32_t *p,
                        const int32_t *n, const StepState *st, int B, float *yp, float *yn,
-                       float *sp, float *sn, float *su, float *regsq, cudaStream_t s);
+                       float *sp, float *sn, float *su, float *regsq, float *snap,
+                       cudaStream_t s);
 int launch_grid_bce(const float *yp, const float *yn, const float *sp, const float *sn,
                     const float *su, int B, float alpha, float beta, const GridWs &ws,
                     float *d_yp, float *d_yn, float *d_sp, float *d_sn, float *d_su,
@@ -65,23 +64,39 @@ size_t plan_ws_bytes(int n_ids);
 int plan_init();
 // two tables in one launch (table 1 optional: n_ids1 == 0)
 int launch_batch_plan2(const int32_t *ids0, const StepState *st0, int ids0_off, int n_ids0,
-                       PlanBufs out0, uint32_t *bitmap0, const int32_t *ids1, int ids1_off,
-                       int n_ids1, PlanBufs out1, uint32_t *bitmap1, cudaStream_t s);
+                       int64_t rows0, PlanBufs out0, uint32_t *bitmap0, const int32_t *ids1,
+                       int ids1_off, int n_ids1, int64_t rows1, PlanBufs out1, uint32_t *bitmap1,
+                       cudaStream_t s);
 int launch_mark_touched(const StepState *st, const int32_t *ids, int B, uint32_t *bmU,
                         uint32_t *bmI, cudaStream_t s);
 int launch_adam_sweep2(float *var0, float *m0, float *v0, int64_t rows0, const uint32_t *bm0,
                        float *var1, float *m1, float *v1, int64_t rows1, const uint32_t *bm1,
                        float lr_t, const StepState *st, float b1, float b2, float eps,
                        cudaStream_t s);
-// summed gradient rows of the unique touched rows (MF: + L2 term) and per-CTA partials of
-// grad(w), grad(w_user)
-int launch_row_grads(const float *Ue, const float *Ie, const float *Ur, const float *Ir,
-                     const float *w, const float *wu, const StepState *st, const int32_t *u,
-                     const int32_t *p, const int32_t *n, int B, const float *d_yp,
+// fused Adam on the touched rows (MF) and fused step tail, both optional
+struct AdamTabs {  // U == nullptr: no fused Adam, summed rows go to gU / gI (LightGCN)
+  float *U, *mU, *vU, *I, *mI, *vI;
+  uint32_t *bmU, *bmI;
+  float b1, b2, eps, lr;  // lr: lr_t itself when st == nullptr
+  const StepState *st;
+};
+struct TailArgs {
+  int fused;  // 1: the last CTA runs the step tail
+  float *w, *mw, *vw, *wu, *mwu, *vwu;
+  const float *losspart;
+  int nparts;
+  const float *litem, *luser, *regsq;
+  macr_hparams hp;
+  StepState *st;
+  unsigned *ticket;
+};
+// summed gradient rows of the unique touched rows (MF: + L2 term, + Adam on those rows) and
+// per-CTA partials of grad(w), grad(w_user); rows come from the gather_dots snapshot
+int launch_row_grads(const float *snap, const float *w, const float *wu, int B, const float *d_yp,
                      const float *d_yn, const float *d_sp, const float *d_sn, const float *d_su,
                      float lam, PlanBufs planU, PlanBufs planI, float *gU, float *gI,
                      float *unit_part, float *gw_part, float *gwu_part, int *n_part,
-                     cudaStream_t s);
+                     const AdamTabs *tabs, const TailArgs *tail, cudaStream_t s);
 int launch_adam_rows2(float *U, float *mU, float *vU, PlanBufs planU, const float *gU,
                       uint32_t *bmU, float *I, float *mI, float *vI, PlanBufs planI,
                       const float *gI, uint32_t *bmI, int max_rows, float lr_t,

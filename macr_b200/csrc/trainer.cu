@@ -50,6 +50,8 @@ struct TrainerBase {
   PlanBufs planU, planI;
   int32_t *plan_mem;
   float *gU, *gI, *gw_part, *gwu_part, *unit_part;
+  float *snap;          // [3][maxB][64] row snapshot of the step (users | pos | neg)
+  unsigned *tail_ticket;
   float *pinned_losses;
   int64_t steps_done;
   const int32_t *cur_ids_base;
@@ -76,6 +78,10 @@ struct TrainerBase {
     MACR_CUDA(cudaMalloc(&loss_stage, sizeof(float) * 4));
     MACR_CUDA(cudaMalloc(&scal, sizeof(float) * 11 * (size_t)maxB));
     MACR_CUDA(cudaMalloc(&gridws, grid_ws_layout(maxB, nullptr).bytes + 4096));
+    MACR_CUDA(cudaMemset(gridws, 0, grid_ws_layout(maxB, nullptr).bytes + 4096));  // band tickets
+    MACR_CUDA(cudaMalloc(&snap, sizeof(float) * kD * 3 * (size_t)maxB));
+    MACR_CUDA(cudaMalloc(&tail_ticket, sizeof(unsigned) * 4));
+    MACR_CUDA(cudaMemset(tail_ticket, 0, sizeof(unsigned) * 4));
     // plan buffers: users (B ids) + items (2B ids): uniq, seg_off(+1), seg_pos, n_uniq + scratch
     const size_t pm = (size_t)maxB * 3 + 8 + (size_t)maxB * 6 + 8;
     MACR_CUDA(cudaMalloc(&plan_mem, sizeof(int32_t) * pm + plan_ws_bytes(maxB) +
@@ -117,7 +123,7 @@ struct TrainerBase {
     for (auto &kv : graphs) cudaGraphExecDestroy(kv.second);
     for (auto &kv : graphs_eval) cudaGraphExecDestroy(kv.second);
     cudaFree(st); cudaFree(ids_stage); cudaFree(loss_stage); cudaFree(scal); cudaFree(gridws);
-    cudaFree(plan_mem); cudaFree(unit_part); cudaFree(gU); cudaFree(gI); cudaFree(gw_part); cudaFree(gwu_part);
+    cudaFree(plan_mem); cudaFree(snap); cudaFree(tail_ticket); cudaFree(unit_part); cudaFree(gU); cudaFree(gI); cudaFree(gw_part); cudaFree(gwu_part);
     cudaFreeHost(pinned_losses);
     cudaEventDestroy(ev_fork); cudaEventDestroy(ev_join);
     cudaEventDestroy(ev_join2);
@@ -161,20 +167,18 @@ namespace macr {
 
 static int mf_enqueue(macr_mf_trainer *h, int B) {
   const macr_hparams &hp = h->hp;
-  cudaStream_t s = h->cs, side = h->side;
+  cudaStream_t s = h->cs, side = h->side, side2 = h->side2;
   float *yp = h->sc(0, B), *yn = h->sc(1, B), *sp = h->sc(2, B), *sn = h->sc(3, B),
         *su = h->sc(4, B), *rq = h->sc(5, B), *dyp = h->sc(6, B), *dyn = h->sc(7, B),
         *dsp = h->sc(8, B), *dsn = h->sc(9, B), *dsu = h->sc(10, B);
   const GridWs g = grid_ws_layout(B, h->gridws);
   int rc;
-  int launches = 0;
-  // fork: the plan and the dense sweep need only the ids and the step state
-  cudaStream_t side2 = h->side2;
+  // fork: the plan (2 CTAs) and the dense sweep need only the ids and the step state
   MACR_CUDA(cudaEventRecord(h->ev_fork, s));
   MACR_CUDA(cudaStreamWaitEvent(side, h->ev_fork, 0));
   MACR_CUDA(cudaStreamWaitEvent(side2, h->ev_fork, 0));
-  rc = launch_batch_plan2(nullptr, h->st, 0, B, h->planU, nullptr, nullptr, B, 2 * B, h->planI,
-                          nullptr, side);
+  rc = launch_batch_plan2(nullptr, h->st, 0, B, h->nu, h->planU, nullptr, nullptr, B, 2 * B,
+                          h->ni, h->planI, nullptr, side);
   if (rc) return rc;
   MACR_CUDA(cudaEventRecord(h->ev_join, side));
   rc = launch_mark_touched(h->st, nullptr, B, h->bmU, h->bmI, side2);
@@ -183,30 +187,23 @@ static int mf_enqueue(macr_mf_trainer *h, int B) {
                           hp.lr, h->st, hp.beta1, hp.beta2, hp.eps, side2);
   if (rc) return rc;
   MACR_CUDA(cudaEventRecord(h->ev_join2, side2));
-  launches += 4;
-  // main: gather -> grid -> finalize
+  // main: gather (+ row snapshot) -> B x B grid (+ band folds) -> row gradients + Adam + tail
   rc = launch_gather_dots(h->U, h->I, h->U, h->I, h->w, h->wu, nullptr, nullptr, nullptr, h->st, B,
-                          yp, yn, sp, sn, su, rq, s);
+                          yp, yn, sp, sn, su, rq, h->snap, s);
   if (rc) return rc;
   rc = launch_grid_bce(yp, yn, sp, sn, su, B, hp.alpha, hp.beta, g, dyp, dyn, dsp, dsn, dsu, 1, s);
   if (rc) return rc;
-  launches += 3;
   MACR_CUDA(cudaStreamWaitEvent(s, h->ev_join, 0));
   MACR_CUDA(cudaStreamWaitEvent(s, h->ev_join2, 0));
   const float lam = hp.decay / (float)hp.batch_size_flag;
-  int n_part = 0;
-  rc = launch_row_grads(h->U, h->I, h->U, h->I, h->w, h->wu, h->st, nullptr, nullptr, nullptr, B,
-                        dyp, dyn, dsp, dsn, dsu, lam, h->planU, h->planI, h->gU, h->gI, h->unit_part,
-                        h->gw_part, h->gwu_part, &n_part, s);
+  const AdamTabs tabs{h->U, h->mU, h->vU, h->I, h->mI, h->vI, h->bmU, h->bmI,
+                      hp.beta1, hp.beta2, hp.eps, hp.lr, h->st};
+  const TailArgs tail{1, h->w, h->mw, h->vw, h->wu, h->mwu, h->vwu, g.losspart, g.nblk * g.nblk,
+                      g.litem, g.luser, rq, hp, h->st, h->tail_ticket};
+  rc = launch_row_grads(h->snap, h->w, h->wu, B, dyp, dyn, dsp, dsn, dsu, lam, h->planU, h->planI,
+                        h->gU, h->gI, h->unit_part, h->gw_part, h->gwu_part, nullptr, &tabs, &tail, s);
   if (rc) return rc;
-  rc = launch_adam_rows2(h->U, h->mU, h->vU, h->planU, h->gU, h->bmU, h->I, h->mI, h->vI, h->planI,
-                         h->gI, h->bmI, B, hp.lr, h->st, hp.beta1, hp.beta2, hp.eps, s);
-  if (rc) return rc;
-  rc = launch_step_tail(h->w, h->mw, h->vw, h->wu, h->mwu, h->vwu, h->gw_part, h->gwu_part, n_part,
-                        g, rq, B, hp, h->st, 1, s);
-  if (rc) return rc;
-  launches += 3;
-  h->launches = launches;
+  h->launches = 6;  // plan, mark, sweep | gather, grid, row-grads(+Adam+tail)
   return MACR_OK;
 }
 
@@ -395,30 +392,30 @@ static int lgcn_enqueue_impl(macr_lgcn_trainer *h, int B, int train) {
   if (train) {
     MACR_CUDA(cudaEventRecord(h->ev_fork, s));
     MACR_CUDA(cudaStreamWaitEvent(side, h->ev_fork, 0));
-    rc = launch_batch_plan2(nullptr, h->st, 0, B, h->planU, nullptr, nullptr, B, 2 * B, h->planI,
-                            nullptr, side);
+    rc = launch_batch_plan2(nullptr, h->st, 0, B, h->nu, h->planU, nullptr, nullptr, B, 2 * B,
+                            h->ni, h->planI, nullptr, side);
     if (rc) return rc;
     MACR_CUDA(cudaMemsetAsync(h->g3, 0, sizeof(float) * N * kD, side));
     MACR_CUDA(cudaEventRecord(h->ev_join, side));
-    launches += 2;
+    launches += 1;
   }
   rc = launch_lgcn_propagate(h->rowptr, h->col, h->val, h->U, h->nu, h->I, h->ni, h->L, h->Emean,
                              h->tmp, s);
   if (rc) return rc;
   launches += h->L;
   rc = launch_gather_dots(Ue, Ie, h->U, h->I, h->w, h->wu, nullptr, nullptr, nullptr, h->st, B, yp,
-                          yn, sp, sn, su, rq, s);
+                          yn, sp, sn, su, rq, h->snap, s);
   if (rc) return rc;
   rc = launch_grid_bce(yp, yn, sp, sn, su, B, hp.alpha, hp.beta, g, dyp, dyn, dsp, dsn, dsu, train,
                        s);
   if (rc) return rc;
-  launches += 3;
+  launches += 2;
   if (train) {
     MACR_CUDA(cudaStreamWaitEvent(s, h->ev_join, 0));
     int n_part = 0;
-    rc = launch_row_grads(Ue, Ie, h->U, h->I, h->w, h->wu, h->st, nullptr, nullptr, nullptr, B, dyp,
-                          dyn, dsp, dsn, dsu, 0.f, h->planU, h->planI, h->gU, h->gI, h->unit_part,
-                          h->gw_part, h->gwu_part, &n_part, s);
+    rc = launch_row_grads(h->snap, h->w, h->wu, B, dyp, dyn, dsp, dsn, dsu, 0.f, h->planU,
+                          h->planI, h->gU, h->gI, h->unit_part, h->gw_part, h->gwu_part, &n_part,
+                          nullptr, nullptr, s);
     if (rc) return rc;
     rc = launch_scatter_rows(h->planU, h->gU, h->planI, h->gI, B, h->nu, (float)(h->L + 1), h->g3,
                              s);

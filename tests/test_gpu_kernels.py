@@ -72,8 +72,7 @@ def test_batch_plan(T, ops, n_ids, rows):
     bitmap = T.zeros((rows + 31) // 32, dtype=T.int32, device="cuda")
     uniq, seg_off, seg_pos = ops.batch_plan(dev(T, ids), rows, bitmap.view(T.int32))
     uniq, seg_off, seg_pos = uniq.cpu().numpy(), seg_off.cpu().numpy(), seg_pos.cpu().numpy()
-    _, first = np.unique(ids, return_index=True)
-    want_uniq = ids[np.sort(first)]  # first-occurrence order, like array_ops.unique
+    want_uniq = np.unique(ids)  # ascending rows; the order of the unique rows enters no result
     np.testing.assert_array_equal(uniq, want_uniq)
     assert seg_off[0] == 0 and seg_off[-1] == n_ids
     for k, r in enumerate(want_uniq):
@@ -103,7 +102,8 @@ def test_adam_kernels_bit_exact(T, ops, oracle):
     bitmap = T.zeros((rows + 31) // 32, dtype=T.int32, device="cuda")
     uniq, _, _ = ops.batch_plan(dev(T, idx), rows, bitmap)
     ops.adam_sweep_untouched(dv, dm, dvv, bitmap, lr_t)
-    ops.adam_rows(dv, dm, dvv, uniq, dev(T, g), bitmap, lr_t)
+    np.testing.assert_array_equal(uniq.cpu().numpy(), np.sort(idx))  # plan lists rows ascending
+    ops.adam_rows(dv, dm, dvv, uniq, dev(T, g[np.argsort(idx)]), bitmap, lr_t)
     assert int(bitmap.abs().sum().item()) == 0  # bits cleared for the next step
     np.testing.assert_array_equal(dv.cpu().numpy(), ov)
     np.testing.assert_array_equal(dm.cpu().numpy(), om)
