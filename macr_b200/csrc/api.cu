@@ -56,7 +56,7 @@ extern "C" int macr_gather_dots(const float *Ue, const float *Ie, const float *U
                      sn && su && regsq,
                  "macr_gather_dots: null pointer");
   return launch_gather_dots(Ue, Ie, Ur, Ir, w, w_user, users, pos, neg, nullptr, B, yp, yn, sp, sn,
-                            su, regsq, nullptr, as_stream(stream));
+                            su, regsq, nullptr, nullptr, as_stream(stream));
 }
 
 extern "C" size_t macr_grid_bce_workspace_bytes(int B) {
@@ -79,10 +79,11 @@ extern "C" int macr_grid_bce_fwd_bwd(const float *yp, const float *yn, const flo
     return fail(MACR_ERR_WORKSPACE, "macr_grid_bce_fwd_bwd: workspace %zu < %zu bytes", ws_bytes,
                 g.bytes);
   cudaStream_t s = as_stream(stream);
-  // band arrival tickets start at zero (they re-arm themselves, but `ws` is caller scratch)
-  MACR_CUDA(cudaMemsetAsync(g.tickets, 0, sizeof(unsigned) * 2 * (size_t)g.nblk, s));
-  int rc = launch_grid_bce(yp, yn, sp, sn, su, B, alpha, beta, g, d_yp, d_yn, d_sp, d_sn, d_su,
-                           want_grad, s);
+  // partial-sum slots start empty (the folders re-arm them, but `ws` is caller scratch)
+  if (want_grad) MACR_CUDA(cudaMemsetAsync(ws, 0xff, g.part_bytes, s));
+  int rc = launch_gates(sp, sn, su, B, g, s);
+  if (rc) return rc;
+  rc = launch_grid_bce(yp, yn, B, alpha, beta, g, d_yp, d_yn, d_sp, d_sn, d_su, want_grad, s);
   if (rc) return rc;
   return launch_reduce_losses(g, nullptr, B, alpha, beta, 0.f, 1, losses3, nullptr, s);
 }

@@ -127,22 +127,22 @@ int main(int argc, char **argv) {
   CK(cudaMalloc(&snap, 4 * 3 * (size_t)B * kD));
   float *yp = sc, *yn = sc + B, *sp = sc + 2 * B, *sn = sc + 3 * B, *su = sc + 4 * B, *rq = sc + 5 * B,
         *dyp = sc + 6 * B, *dyn = sc + 7 * B, *dsp = sc + 8 * B, *dsn = sc + 9 * B, *dsu = sc + 10 * B;
+  void *gws;
+  GridWs g0 = grid_ws_layout(B, nullptr);
+  CK(cudaMalloc(&gws, g0.bytes));
+  CK(cudaMemset(gws, 0xff, g0.bytes));
+  GridWs g = grid_ws_layout(B, gws);
   auto gather = [&]() {
     launch_gather_dots(U, I, U, I, w, wu, d_ids, d_ids + B, d_ids + 2 * B, nullptr, B, yp, yn, sp, sn,
-                       su, rq, snap, 0);
+                       su, rq, snap, &g, 0);
   };
   printf("gather_dots         warm %7.2f us   cold %7.2f us\n", time_us(gather, 20, nullptr, 0),
          time_us(gather, 20, flush, fb));
   // ---- grid ----
-  void *gws;
-  GridWs g0 = grid_ws_layout(B, nullptr);
-  CK(cudaMalloc(&gws, g0.bytes));
-  CK(cudaMemset(gws, 0, g0.bytes));
-  GridWs g = grid_ws_layout(B, gws);
-  auto grid = [&]() { launch_grid_bce(yp, yn, sp, sn, su, B, 1e-2f, 1e-3f, g, dyp, dyn, dsp, dsn, dsu, 1, 0); };
+  auto grid = [&]() { launch_grid_bce(yp, yn, B, 1e-2f, 1e-3f, g, dyp, dyn, dsp, dsn, dsu, 1, 0); };
   printf("grid_bce (grad)     warm %7.2f us   cold %7.2f us\n", time_us(grid, 20, nullptr, 0),
          time_us(grid, 20, flush, fb));
-  auto grid0 = [&]() { launch_grid_bce(yp, yn, sp, sn, su, B, 1e-2f, 1e-3f, g, dyp, dyn, dsp, dsn, dsu, 0, 0); };
+  auto grid0 = [&]() { launch_grid_bce(yp, yn, B, 1e-2f, 1e-3f, g, dyp, dyn, dsp, dsn, dsu, 0, 0); };
   printf("grid_bce (loss)     warm %7.2f us\n", time_us(grid0, 20, nullptr, 0));
   // ---- sweep ----
   auto sweep = [&]() {

@@ -45,6 +45,12 @@ __device__ __forceinline__ const int32_t *step_ids(const StepState *st, const in
   return st->ids_base + st->step_idx * 3LL * B + (long long)which * B;
 }
 
+struct GateOut {
+  float *gA, *gAN, *gG, *litem, *luser;
+};
+__device__ __forceinline__ void gate_values(float sp, float sn, float su, float &a, float &an,
+                                            float &g, float &litem, float &luser);
+
 // ---------------------------------------------------------------------------------------------
 // K1+K2: one warp per triple; lane l owns elements [2l, 2l+1] of every 64-wide row
 // ---------------------------------------------------------------------------------------------
@@ -55,7 +61,7 @@ gather_dots_kernel(const float *__restrict__ Ue, const float *__restrict__ Ie,
                    const int32_t *u_, const int32_t *p_, const int32_t *n_, const StepState *st,
                    int B, float *__restrict__ yp, float *__restrict__ yn, float *__restrict__ sp,
                    float *__restrict__ sn, float *__restrict__ su, float *__restrict__ regsq,
-                   float *__restrict__ snap) {
+                   float *__restrict__ snap, GateOut gates) {
   const int lane = threadIdx.x & 31;
   const int b = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   if (b >= B) return;
@@ -100,6 +106,15 @@ gather_dots_kernel(const float *__restrict__ Ue, const float *__restrict__ Ie,
     sn[b] = a3;
     su[b] = a4;
     regsq[b] = a5;
+    if (gates.gA) {  // gates + branch losses for the B x B grid (computed once per position)
+      float a, an, g, li, lu;
+      gate_values(a2, a3, a4, a, an, g, li, lu);
+      gates.gA[b] = a;
+      gates.gAN[b] = an;
+      gates.gG[b] = g;
+      gates.litem[b] = li;
+      gates.luser[b] = lu;
+    }
   }
 }
 
@@ -107,10 +122,12 @@ int launch_gather_dots(const float *Ue, const float *Ie, const float *Ur, const 
                        const float *w, const float *wu, const int32_t *u, const int32_t *p,
                        const int32_t *n, const StepState *st, int B, float *yp, float *yn,
                        float *sp, float *sn, float *su, float *regsq, float *snap,
-                       cudaStream_t s) {
+                       const GridWs *gates, cudaStream_t s) {
   const int wpb = 8;
-  gather_dots_kernel<<<(B + wpb - 1) / wpb, wpb * 32, 0, s>>>(Ue, Ie, Ur, Ir, w, wu, u, p, n, st,
-                                                              B, yp, yn, sp, sn, su, regsq, snap);
+  GateOut go{};
+  if (gates) go = GateOut{gates->gA, gates->gAN, gates->gG, gates->litem, gates->luser};
+  gather_dots_kernel<<<(B + wpb - 1) / wpb, wpb * 32, 0, s>>>(
+      Ue, Ie, Ur, Ir, w, wu, u, p, n, st, B, yp, yn, sp, sn, su, regsq, snap, go);
   MACR_LAUNCH_CHECK();
   return MACR_OK;
 }
@@ -133,18 +150,17 @@ int launch_gather_dots(const float *Ue, const float *Ie, const float *Ur, const 
 // per-pair range test; other tiles test every pair and fall back to the literal formulas
 // (8 MUFU) where needed.
 //
-// The last CTA to finish a tile row / tile column (arrival tickets) folds that band's partial
-// sums in fixed order and finishes the chain rule through the three sigmoids, adding the
-// alpha / beta branch gradients (model.py:213-217) -- no separate finalize launch.
+// Extra CTAs at the end of the grid fold each band's partial sums in fixed order and finish the
+// chain rule through the three sigmoids (see grid_fold_band) -- no separate finalize launch.
 // ---------------------------------------------------------------------------------------------
 struct GridOut {
   float *d_yp, *d_yn, *d_sp, *d_sn, *d_su;
 };
 
 template <bool kChecked, bool kMasked, bool kGrad>
-__device__ __forceinline__ void grid_pair(float ypj, float ynj, float agl, float angl, float ag,
-                                          float ang, float mk, float &lgacc, float &colP,
-                                          float &colN, float &rowP, float &rowN) {
+__device__ __forceinline__ void grid_pair(float ypj, float ynj, float agl, float angl, float mk,
+                                          float &lgacc, float &colP, float &colN, float &rowP,
+                                          float &rowN) {
   const float xP = ypj * agl, xN = ynj * angl;  // -P*log2(e), -N*log2(e)
   const float eP = ex2_approx(xP), eN = ex2_approx(xN);
   const float DP = 1.0f + eP, DN = 1.0f + eN;
@@ -164,57 +180,132 @@ __device__ __forceinline__ void grid_pair(float ypj, float ynj, float agl, float
   }
   if (kMasked) lg *= mk;
   lgacc += lg;
-  if (kGrad) {
-    colP = fmaf(dP, ag, colP);
-    colN = fmaf(dN, ang, colN);
+  if (kGrad) {  // column sums carry the -log2(e) factor of agl / angl; it is divided out once
+    colP = fmaf(dP, agl, colP);
+    colN = fmaf(dN, angl, colN);
     rowP = fmaf(dP, ypj, rowP);
     rowN = fmaf(dN, ynj, rowN);
   }
 }
 
-template <int RI, int RJ, bool kMasked, bool kGrad>
-__global__ void __launch_bounds__(256, 2)
-grid_bce_kernel(const float *__restrict__ yp, const float *__restrict__ yn,
-                const float *__restrict__ sp, const float *__restrict__ sn,
-                const float *__restrict__ su, int B, float alpha, float beta, GridWs ws,
-                GridOut out) {
+// Band folds without any synchronisation cost in the tile CTAs: every partial-sum slot holds a
+// sentinel bit pattern (kPartEmpty, a NaN no arithmetic produces) until its tile CTA stores the
+// value -- a single 4-byte store, so a reader sees either the sentinel or the value.  One extra
+// CTA per row band and per column band, placed at the END of the grid, polls its band's slots
+// in fixed order (deterministic sum), re-arms them, and finishes the chain rule through the
+// three sigmoids with the alpha / beta branch gradients (model.py:213-217).  The folders are
+// dispatched with the last wave of tiles and never hold more than nblk_i + nblk_j CTA slots.
+constexpr unsigned kPartEmpty = 0xffffffffu;
+
+__device__ __forceinline__ float not_sentinel(float v) {
+  return __float_as_uint(v) == kPartEmpty ? __uint_as_float(0x7fc00000u) : v;
+}
+
+// sum of n slots `stride` floats apart, in index order; waits for slots that are still empty
+// and re-arms every slot it consumed.  Loads are issued kFoldBatch at a time (one L2 round trip
+// per batch).
+constexpr int kFoldBatch = 16;
+
+__device__ __forceinline__ float take_partials(float *slot, int n, size_t stride) {
+  float acc = 0.f;
+  for (int k0 = 0; k0 < n; k0 += kFoldBatch) {
+    unsigned bits[kFoldBatch];
+    for (;;) {
+      bool ready = true;
+#pragma unroll
+      for (int q = 0; q < kFoldBatch; ++q) {
+        bits[q] = 0;
+        if (k0 + q < n)
+          asm volatile("ld.volatile.global.u32 %0, [%1];"
+                       : "=r"(bits[q])
+                       : "l"(slot + (size_t)(k0 + q) * stride));
+      }
+#pragma unroll
+      for (int q = 0; q < kFoldBatch; ++q) ready = ready && bits[q] != kPartEmpty;
+      if (ready) break;
+      __nanosleep(100);
+    }
+#pragma unroll
+    for (int q = 0; q < kFoldBatch; ++q)
+      if (k0 + q < n) {
+        acc += __uint_as_float(bits[q]);
+        asm volatile("st.volatile.global.u32 [%0], %1;" ::"l"(slot + (size_t)(k0 + q) * stride),
+                     "r"(kPartEmpty)
+                     : "memory");
+      }
+  }
+  return acc;
+}
+
+template <int TI, int TJ>
+__device__ void grid_fold_band(int f, int B, float alpha, float beta, const GridWs &ws,
+                               const GridOut &out, float *scratch /* >= 2*TI floats */) {
+  const int tid = threadIdx.x, Bpad = ws.Bpad;
+  const float invB = 1.0f / (float)B;
+  const float invBB = invB * invB;
+  if (f < ws.nblk_i) {  // row band f: d/d sp_i, sn_i, su_i
+    const int i0 = f * TI;
+    for (int t = tid; t < 2 * TI; t += 256) {
+      const int which = t / TI, row = t - which * TI;
+      float *src = (which ? ws.rowN : ws.rowP) + i0 + row;
+      scratch[t] = take_partials(src, ws.nblk_j, Bpad);
+    }
+    __syncthreads();
+    for (int t = tid; t < TI; t += 256) {
+      const int i = i0 + t;
+      if (i >= B) continue;
+      const float rp = scratch[t], rn = scratch[TI + t];
+      const float a = ws.gA[i], an = ws.gAN[i], g = ws.gG[i];
+      const float ea = a + kBceEps, ean = (1.0f - an) + kBceEps;
+      const float eg = g + kBceEps, eg1 = (1.0f - g) + kBceEps;
+      const float da = rp * invBB * g - alpha * invB / ea;
+      const float dan = rn * invBB * g + alpha * invB / ean;
+      const float dg = (rp * a + rn * an) * invBB + beta * invB * (1.0f / eg1 - 1.0f / eg);
+      out.d_sp[i] = da * (a * (1.0f - a));
+      out.d_sn[i] = dan * (an * (1.0f - an));
+      out.d_su[i] = dg * (g * (1.0f - g));
+    }
+  } else if (f < ws.nblk_i + ws.nblk_j) {  // column band: d/d yp_j, d/d yn_j
+    const int j0 = (f - ws.nblk_i) * TJ;
+    for (int t = tid; t < 2 * TJ; t += 256) {
+      const int which = t / TJ, colm = t - which * TJ;
+      float *src = (which ? ws.colN : ws.colP) + j0 + colm;
+      const float acc = take_partials(src, ws.nblk_i, Bpad);
+      if (j0 + colm < B) (which ? out.d_yn : out.d_yp)[j0 + colm] = acc * invBB;
+    }
+  }
+}
+
+template <int RI, int RJ, int MINB, bool kMasked, bool kGrad>
+__global__ void __launch_bounds__(256, MINB)
+grid_bce_kernel(const float *__restrict__ yp, const float *__restrict__ yn, int B, float alpha,
+                float beta, GridWs ws, GridOut out) {
   constexpr int TI = 16 * RI, TJ = 16 * RJ;
   constexpr int TMAX = TI > TJ ? TI : TJ;
   constexpr float kLog2e = 1.4426950408889634f;
-  __shared__ float sA[TI], sAN[TI], sG[TI];
   __shared__ float sAg[TI], sAng[TI];
   __shared__ float sYp[TJ], sYn[TJ];
   __shared__ float sRed[2][TMAX][17];
   __shared__ float sLoss[8];
-  __shared__ int sMax[2];
-  __shared__ unsigned sTicket[2];
+  __shared__ float sMax[2][8];
   __shared__ double sRank1;
 
   const int tid = threadIdx.x, tx = tid & 15, ty = tid >> 4;
-  const int i0 = blockIdx.y * TI, j0 = blockIdx.x * TJ;
   const int Bpad = ws.Bpad;
-  if (tid < 2) sMax[tid] = 0;
-  __syncthreads();
-
+  if (kGrad && (int)blockIdx.y >= ws.nblk_i) {  // band folders ride at the end of the grid
+    grid_fold_band<TI, TJ>((blockIdx.y - ws.nblk_i) * gridDim.x + blockIdx.x, B, alpha, beta, ws, out,
+                           &sRed[0][0][0]);
+    return;
+  }
+  const int i0 = blockIdx.y * TI, j0 = blockIdx.x * TJ;
+  // gates sig(sp)*sig(su), sig(sn)*sig(su) of this row band, precomputed once per step by
+  // gate_kernel / gather_dots
   for (int t = tid; t < TI; t += 256) {
     const int i = i0 + t;
     const bool ok = i < B;
-    const float a = ok ? sigmoid_precise(sp[i]) : 0.f, an = ok ? sigmoid_precise(sn[i]) : 0.f,
-                g = ok ? sigmoid_precise(su[i]) : 0.f;
-    sA[t] = a;
-    sAN[t] = an;
-    sG[t] = g;
-    const float ag = a * g, ang = an * g;
-    sAg[t] = ag;
-    sAng[t] = ang;
-    atomicMax(&sMax[0], __float_as_int(ag));  // gates are >= 0: int order == float order
-    atomicMax(&sMax[1], __float_as_int(ang));
-    if (ok && blockIdx.x == 0) {  // branch losses of this row band, model.py:213,215
-      const float ea = a + kBceEps, ean = (1.0f - an) + kBceEps;
-      const float eg = g + kBceEps, eg1 = (1.0f - g) + kBceEps;
-      ws.litem[i] = -logf(ea) - logf(ean);
-      ws.luser[i] = -logf(eg) - logf(eg1);
-    }
+    const float g = ok ? ws.gG[i] : 0.f;
+    sAg[t] = ok ? ws.gA[i] * g : 0.f;
+    sAng[t] = ok ? ws.gAN[i] * g : 0.f;
   }
   for (int t = tid; t < TJ; t += 256) {
     const int j = j0 + t;
@@ -223,29 +314,17 @@ grid_bce_kernel(const float *__restrict__ yp, const float *__restrict__ yn,
     sYn[t] = ok ? yn[j] : 0.f;
   }
   __syncthreads();
-  bool in_range = true;
-  if (tid < TJ)
-    in_range = fabsf(sYp[tid]) * __int_as_float(sMax[0]) <= 6.2f &&
-               fabsf(sYn[tid]) * __int_as_float(sMax[1]) <= 5.5f;
-  const bool all_fast = __syncthreads_and(in_range);
-  if (tid < 32) {  // rank-1 term of the tile: sum_ij xN_ij = (sum_i -log2e*ang_i) * (sum_j yn_j)
-    float sa = 0.f, sy = 0.f;
-    for (int t = tid; t < TI; t += 32) sa += sAng[t];
-    for (int t = tid; t < TJ; t += 32) sy += sYn[t];
-    sa = warp_sum(sa);
-    sy = warp_sum(sy);
-    if (tid == 0) sRank1 = -(double)kLog2e * (double)sa * (double)sy;
-  }
-
-  float agl[RI], angl[RI], ag[RI], ang[RI], wr[RI];
+  float agl[RI], angl[RI], wr[RI];
   float ypj[RJ], ynj[RJ], wc[RJ];
+  float mg = 0.f, mgn = 0.f;
 #pragma unroll
   for (int r = 0; r < RI; ++r) {
     const int t = ty + 16 * r;
-    ag[r] = sAg[t];
-    ang[r] = sAng[t];
-    agl[r] = -kLog2e * ag[r];  // exp(-P) = ex2(yp * (-c*log2e))
-    angl[r] = -kLog2e * ang[r];
+    const float ag = sAg[t], ang = sAng[t];
+    mg = fmaxf(mg, ag);
+    mgn = fmaxf(mgn, ang);
+    agl[r] = -kLog2e * ag;  // exp(-P) = ex2(yp * (-c*log2e))
+    angl[r] = -kLog2e * ang;
     wr[r] = (i0 + t < B) ? 1.f : 0.f;
   }
 #pragma unroll
@@ -254,6 +333,39 @@ grid_bce_kernel(const float *__restrict__ yp, const float *__restrict__ yn,
     ypj[c] = sYp[t];
     ynj[c] = sYn[t];
     wc[c] = (j0 + t < B) ? 1.f : 0.f;
+  }
+
+  // largest gate of the band -> can the whole tile skip the per-pair range test?
+  {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      mg = fmaxf(mg, __shfl_xor_sync(0xffffffffu, mg, o));
+      mgn = fmaxf(mgn, __shfl_xor_sync(0xffffffffu, mgn, o));
+    }
+    if ((tid & 31) == 0) {
+      sMax[0][tid >> 5] = mg;
+      sMax[1][tid >> 5] = mgn;
+    }
+  }
+  __syncthreads();
+  bool in_range = true;
+  {
+    float mg = 0.f, mgn = 0.f;
+#pragma unroll
+    for (int q = 0; q < 8; ++q) {
+      mg = fmaxf(mg, sMax[0][q]);
+      mgn = fmaxf(mgn, sMax[1][q]);
+    }
+    if (tid < TJ) in_range = fabsf(sYp[tid]) * mg <= 6.2f && fabsf(sYn[tid]) * mgn <= 5.5f;
+  }
+  const bool all_fast = __syncthreads_and(in_range);
+  if (tid < 32) {  // rank-1 term of the tile: sum_ij xN_ij = (sum_i -log2e*ang_i) * (sum_j yn_j)
+    float sa = 0.f, sy = 0.f;
+    for (int t = tid; t < TI; t += 32) sa += sAng[t];
+    for (int t = tid; t < TJ; t += 32) sy += sYn[t];
+    sa = warp_sum(sa);
+    sy = warp_sum(sy);
+    if (tid == 0) sRank1 = -(double)kLog2e * (double)sa * (double)sy;
   }
 
   float colP[RJ], colN[RJ], rowP[RI], rowN[RI];
@@ -268,7 +380,7 @@ grid_bce_kernel(const float *__restrict__ yp, const float *__restrict__ yn,
     for (int r = 0; r < RI; ++r)
 #pragma unroll
       for (int c = 0; c < RJ; ++c)
-        grid_pair<false, kMasked, kGrad>(ypj[c], ynj[c], agl[r], angl[r], ag[r], ang[r],
+        grid_pair<false, kMasked, kGrad>(ypj[c], ynj[c], agl[r], angl[r],
                                          kMasked ? wr[r] * wc[c] : 1.f, lgacc, colP[c], colN[c],
                                          rowP[r], rowN[r]);
   } else {
@@ -276,7 +388,7 @@ grid_bce_kernel(const float *__restrict__ yp, const float *__restrict__ yn,
     for (int r = 0; r < RI; ++r)
 #pragma unroll
       for (int c = 0; c < RJ; ++c)
-        grid_pair<true, kMasked, kGrad>(ypj[c], ynj[c], agl[r], angl[r], ag[r], ang[r],
+        grid_pair<true, kMasked, kGrad>(ypj[c], ynj[c], agl[r], angl[r],
                                         kMasked ? wr[r] * wc[c] : 1.f, lgacc, colP[c], colN[c],
                                         rowP[r], rowN[r]);
   }
@@ -295,7 +407,7 @@ grid_bce_kernel(const float *__restrict__ yp, const float *__restrict__ yn,
 #pragma unroll
       for (int k = 0; k < 16; ++k) acc += sRed[which][row][k];
       float *dst = which ? ws.rowN : ws.rowP;
-      __stcg(&dst[(size_t)blockIdx.x * Bpad + i0 + row], acc);
+      __stcg(&dst[(size_t)blockIdx.x * Bpad + i0 + row], not_sentinel(acc));
     }
     __syncthreads();
 #pragma unroll
@@ -310,7 +422,7 @@ grid_bce_kernel(const float *__restrict__ yp, const float *__restrict__ yn,
 #pragma unroll
       for (int k = 0; k < 16; ++k) acc += sRed[which][colm][k];
       float *dst = which ? ws.colN : ws.colP;
-      __stcg(&dst[(size_t)blockIdx.y * Bpad + j0 + colm], acc);
+      __stcg(&dst[(size_t)blockIdx.y * Bpad + j0 + colm], not_sentinel(acc * (-1.0f / kLog2e)));
     }
   }
   lgacc = warp_sum(lgacc);
@@ -319,125 +431,124 @@ grid_bce_kernel(const float *__restrict__ yp, const float *__restrict__ yn,
   if (tid == 0) {
     float acc = 0.f;
 #pragma unroll
-    for (int k = 0; k < 8; ++k) acc += sLoss[k];
+    for (int q = 0; q < 8; ++q) acc += sLoss[q];
     ws.losspart[blockIdx.y * gridDim.x + blockIdx.x] = (float)((double)acc + sRank1);
-    if (kGrad) {
-      __threadfence();  // the CTA's partials (ordered by the barrier above) before the tickets
-      sTicket[0] = atomicAdd(&ws.tickets[blockIdx.y], 1u);               // row band i-tile
-      sTicket[1] = atomicAdd(&ws.tickets[gridDim.y + blockIdx.x], 1u);   // column band j-tile
+  }
+}
+
+// tile shapes: rows x cols = 16*RI x 16*RJ.  Row bands and column bands may have different widths.
+static void grid_cfg(int B, int *ri, int *rj) {
+  static int env_ri = -1, env_rj = -1;
+  if (env_ri < 0) {
+    const char *e = getenv("MACR_GRID_TILE");  // developer knob: "88", "48", "84", "44"
+    env_ri = env_rj = 0;
+    if (e && e[0] && e[1]) {
+      env_ri = e[0] - '0';
+      env_rj = e[1] - '0';
     }
   }
-  if (!kGrad) return;
-  __syncthreads();
-  const bool fold_rows = sTicket[0] == gridDim.x - 1, fold_cols = sTicket[1] == gridDim.y - 1;
-  if (!fold_rows && !fold_cols) return;
-  if (tid == 0) __threadfence();
-  __syncthreads();
-  const float invB = 1.0f / (float)B;
-  const float invBB = invB * invB;
-  if (fold_cols) {  // d/d yp_j, d/d yn_j: column sums over every row band, band order fixed
-    for (int t = tid; t < 2 * TJ; t += 256) {
-      const int which = t / TJ, colm = t - which * TJ;
-      const float *src = (which ? ws.colN : ws.colP) + j0 + colm;
-      float acc = 0.f;
-      const int nb = gridDim.y;
-      int k = 0;
-      for (; k + 8 <= nb; k += 8) {
-        float v[8];
-#pragma unroll
-        for (int q = 0; q < 8; ++q) v[q] = __ldcg(src + (size_t)(k + q) * Bpad);
-#pragma unroll
-        for (int q = 0; q < 8; ++q) acc += v[q];
-      }
-      for (; k < nb; ++k) acc += __ldcg(src + (size_t)k * Bpad);
-      if (j0 + colm < B) (which ? out.d_yn : out.d_yp)[j0 + colm] = acc * invBB;
-    }
-    if (tid == 0) ws.tickets[gridDim.y + blockIdx.x] = 0;  // re-armed for the next launch
+  if (env_ri > 0 && B >= 2048) {
+    *ri = env_ri;
+    *rj = env_rj;
+    return;
   }
-  if (fold_rows) {
-    __syncthreads();  // sRed is free again
-    for (int t = tid; t < 2 * TI; t += 256) {
-      const int which = t / TI, row = t - which * TI;
-      const float *src = (which ? ws.rowN : ws.rowP) + i0 + row;
-      float acc = 0.f;
-      const int nb = gridDim.x;
-      int k = 0;
-      for (; k + 8 <= nb; k += 8) {
-        float v[8];
-#pragma unroll
-        for (int q = 0; q < 8; ++q) v[q] = __ldcg(src + (size_t)(k + q) * Bpad);
-#pragma unroll
-        for (int q = 0; q < 8; ++q) acc += v[q];
-      }
-      for (; k < nb; ++k) acc += __ldcg(src + (size_t)k * Bpad);
-      sRed[which][row][0] = acc;
-    }
-    __syncthreads();
-    for (int t = tid; t < TI; t += 256) {
-      const int i = i0 + t;
-      if (i >= B) continue;
-      const float rp = sRed[0][t][0], rn = sRed[1][t][0];
-      const float a = sA[t], an = sAN[t], g = sG[t];
-      const float ea = a + kBceEps, ean = (1.0f - an) + kBceEps;
-      const float eg = g + kBceEps, eg1 = (1.0f - g) + kBceEps;
-      const float da = rp * invBB * g - alpha * invB / ea;
-      const float dan = rn * invBB * g + alpha * invB / ean;
-      const float dg = (rp * a + rn * an) * invBB + beta * invB * (1.0f / eg1 - 1.0f / eg);
-      out.d_sp[i] = da * (a * (1.0f - a));
-      out.d_sn[i] = dan * (an * (1.0f - an));
-      out.d_su[i] = dg * (g * (1.0f - g));
-    }
-    if (tid == 0) ws.tickets[blockIdx.y] = 0;
-  }
+  *ri = *rj = (B >= 2048) ? 8 : 4;
 }
 
 GridWs grid_ws_layout(int B, void *base) {
   GridWs w;
-  w.tile = (B >= 2048) ? 128 : 64;
-  w.nblk = (B + w.tile - 1) / w.tile;
-  w.Bpad = w.nblk * w.tile;
+  int ri, rj;
+  grid_cfg(B, &ri, &rj);
+  w.tile_i = 16 * ri;
+  w.tile_j = 16 * rj;
+  w.nblk_i = (B + w.tile_i - 1) / w.tile_i;
+  w.nblk_j = (B + w.tile_j - 1) / w.tile_j;
+  const int tmax = w.tile_i > w.tile_j ? w.tile_i : w.tile_j;
+  w.Bpad = (B + tmax - 1) / tmax * tmax;
   float *p = reinterpret_cast<float *>(base);
-  const size_t band = (size_t)w.nblk * w.Bpad;
+  const size_t band_r = (size_t)w.nblk_j * w.Bpad, band_c = (size_t)w.nblk_i * w.Bpad;
   w.rowP = p;
-  w.rowN = p + band;
-  w.colP = p + 2 * band;
-  w.colN = p + 3 * band;
-  w.losspart = p + 4 * band;
-  const size_t lp = ((size_t)w.nblk * w.nblk + 3) & ~(size_t)3;
+  w.rowN = p + band_r;
+  w.colP = p + 2 * band_r;
+  w.colN = p + 2 * band_r + band_c;
+  w.losspart = p + 2 * band_r + 2 * band_c;
+  const size_t lp = ((size_t)w.nblk_i * w.nblk_j + 3) & ~(size_t)3;
   w.litem = w.losspart + lp;
   w.luser = w.litem + w.Bpad;
-  w.tickets = reinterpret_cast<unsigned *>(w.luser + w.Bpad);
-  const size_t tk = ((size_t)2 * w.nblk + 3) & ~(size_t)3;
-  w.bytes = (4 * band + lp + 2 * (size_t)w.Bpad + tk) * sizeof(float);
+  w.gA = w.luser + w.Bpad;
+  w.gAN = w.gA + w.Bpad;
+  w.gG = w.gAN + w.Bpad;
+  w.part_bytes = (2 * band_r + 2 * band_c) * sizeof(float);  // rowP..colN: sentinel-armed slots
+  w.bytes = (2 * band_r + 2 * band_c + lp + 5 * (size_t)w.Bpad) * sizeof(float);
   return w;
 }
 
-template <int R, bool kGrad>
-static void launch_grid_t(const float *yp, const float *yn, const float *sp, const float *sn,
-                          const float *su, int B, float alpha, float beta, const GridWs &ws,
-                          const GridOut &out, cudaStream_t s) {
-  dim3 grid(ws.nblk, ws.nblk);
-  if (B % ws.tile == 0)
-    grid_bce_kernel<R, R, false, kGrad><<<grid, 256, 0, s>>>(yp, yn, sp, sn, su, B, alpha, beta, ws,
-                                                             out);
-  else
-    grid_bce_kernel<R, R, true, kGrad><<<grid, 256, 0, s>>>(yp, yn, sp, sn, su, B, alpha, beta, ws,
-                                                            out);
+// gates and branch losses of the batch from the three branch logits (model.py:204-205,213,215):
+// a = sig(sp), an = sig(sn), g = sig(su); litem = -log(a+eps) - log(1-an+eps); luser likewise.
+// (The trainers get the same values straight from gather_dots.)
+__device__ __forceinline__ void gate_values(float sp, float sn, float su, float &a, float &an,
+                                            float &g, float &litem, float &luser) {
+  a = sigmoid_precise(sp);
+  an = sigmoid_precise(sn);
+  g = sigmoid_precise(su);
+  const float ea = a + kBceEps, ean = (1.0f - an) + kBceEps;
+  const float eg = g + kBceEps, eg1 = (1.0f - g) + kBceEps;
+  litem = -logf(ea) - logf(ean);
+  luser = -logf(eg) - logf(eg1);
 }
 
-// the arrival tickets inside `ws` must be zero before the first launch (they re-arm themselves)
-int launch_grid_bce(const float *yp, const float *yn, const float *sp, const float *sn,
-                    const float *su, int B, float alpha, float beta, const GridWs &ws,
-                    float *d_yp, float *d_yn, float *d_sp, float *d_sn, float *d_su,
-                    int want_grad, cudaStream_t s) {
+__global__ void __launch_bounds__(256)
+gate_kernel(const float *__restrict__ sp, const float *__restrict__ sn,
+            const float *__restrict__ su, int B, GridWs ws) {
+  const int b = blockIdx.x * blockDim.x + threadIdx.x;
+  if (b >= B) return;
+  float a, an, g, li, lu;
+  gate_values(sp[b], sn[b], su[b], a, an, g, li, lu);
+  ws.gA[b] = a;
+  ws.gAN[b] = an;
+  ws.gG[b] = g;
+  ws.litem[b] = li;
+  ws.luser[b] = lu;
+}
+
+int launch_gates(const float *sp, const float *sn, const float *su, int B, const GridWs &ws,
+                 cudaStream_t s) {
+  gate_kernel<<<(B + 255) / 256, 256, 0, s>>>(sp, sn, su, B, ws);
+  MACR_LAUNCH_CHECK();
+  return MACR_OK;
+}
+
+template <int RI, int RJ, int MINB, bool kGrad>
+static void launch_grid_t(const float *yp, const float *yn, int B, float alpha, float beta,
+                          const GridWs &ws, const GridOut &out, cudaStream_t s) {
+  // tiles, then (grad only) one folder CTA per row band and per column band
+  const int fold_rows = kGrad ? (ws.nblk_i + ws.nblk_j + ws.nblk_j - 1) / ws.nblk_j : 0;
+  dim3 grid(ws.nblk_j, ws.nblk_i + fold_rows);
+  if (B % ws.tile_i == 0 && B % ws.tile_j == 0)
+    grid_bce_kernel<RI, RJ, MINB, false, kGrad><<<grid, 256, 0, s>>>(yp, yn, B, alpha, beta, ws, out);
+  else
+    grid_bce_kernel<RI, RJ, MINB, true, kGrad><<<grid, 256, 0, s>>>(yp, yn, B, alpha, beta, ws, out);
+}
+
+// the partial-sum slots of `ws` (first ws.part_bytes bytes) must hold 0xff bytes before the first
+// launch (the folders re-arm them);
+// ws.gA / gAN / gG / litem / luser must hold the gates of the batch (launch_gates / gather_dots)
+int launch_grid_bce(const float *yp, const float *yn, int B, float alpha, float beta,
+                    const GridWs &ws, float *d_yp, float *d_yn, float *d_sp, float *d_sn,
+                    float *d_su, int want_grad, cudaStream_t s) {
   const GridOut out{d_yp, d_yn, d_sp, d_sn, d_su};
-  if (ws.tile == 128) {
-    if (want_grad) launch_grid_t<8, true>(yp, yn, sp, sn, su, B, alpha, beta, ws, out, s);
-    else launch_grid_t<8, false>(yp, yn, sp, sn, su, B, alpha, beta, ws, out, s);
-  } else {
-    if (want_grad) launch_grid_t<4, true>(yp, yn, sp, sn, su, B, alpha, beta, ws, out, s);
-    else launch_grid_t<4, false>(yp, yn, sp, sn, su, B, alpha, beta, ws, out, s);
-  }
+  const int ri = ws.tile_i / 16, rj = ws.tile_j / 16;
+#define MACR_GRID_CASE(RI_, RJ_, MINB_)                                                          \
+  if (ri == RI_ && rj == RJ_) {                                                                   \
+    if (want_grad) launch_grid_t<RI_, RJ_, MINB_, true>(yp, yn, B, alpha, beta, ws, out, s);      \
+    else launch_grid_t<RI_, RJ_, MINB_, false>(yp, yn, B, alpha, beta, ws, out, s);               \
+  } else
+  MACR_GRID_CASE(8, 8, 2)
+  MACR_GRID_CASE(4, 8, 3)
+  MACR_GRID_CASE(8, 4, 3)
+  MACR_GRID_CASE(4, 4, 4)
+  return fail(MACR_ERR_INVALID, "grid tile %dx%d not instantiated", ri, rj);
+#undef MACR_GRID_CASE
   MACR_LAUNCH_CHECK();
   return MACR_OK;
 }
@@ -497,7 +608,7 @@ reduce_losses_kernel(const float *__restrict__ losspart, int nparts, const float
 int launch_reduce_losses(const GridWs &ws, const float *regsq, int B, float alpha, float beta,
                          float decay, int batch_size_flag, float *losses3, const StepState *st,
                          cudaStream_t s) {
-  reduce_losses_kernel<<<1, 1024, 0, s>>>(ws.losspart, ws.nblk * ws.nblk, ws.litem, ws.luser,
+  reduce_losses_kernel<<<1, 1024, 0, s>>>(ws.losspart, ws.nblk_i * ws.nblk_j, ws.litem, ws.luser,
                                           regsq, B, alpha, beta, decay, batch_size_flag, losses3,
                                           st);
   MACR_LAUNCH_CHECK();
@@ -1347,7 +1458,7 @@ int launch_step_tail(float *w, float *mw, float *vw, float *wu, float *mwu, floa
                      const float *regsq, int B, const macr_hparams &hp, StepState *st, int train,
                      cudaStream_t s) {
   step_tail_kernel<<<1, 1024, 0, s>>>(w, mw, vw, wu, mwu, vwu, gw_part, gwu_part, n_part,
-                                      ws.losspart, ws.nblk * ws.nblk, ws.litem, ws.luser, regsq, B,
+                                      ws.losspart, ws.nblk_i * ws.nblk_j, ws.litem, ws.luser, regsq, B,
                                       hp, st, train);
   MACR_LAUNCH_CHECK();
   return MACR_OK;

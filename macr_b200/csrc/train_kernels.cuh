@@ -20,14 +20,15 @@ struct StepState {
 };
 
 struct GridWs {  // carve-up of the grid kernel's partial-sum workspace
-  int tile;      // 128 or 64
-  int nblk;      // ceil(B / tile)
-  int Bpad;      // nblk * tile
-  float *rowP, *rowN;  // [nblk(j)][Bpad]
-  float *colP, *colN;  // [nblk(i)][Bpad]
-  float *losspart;     // [nblk*nblk]
-  float *litem, *luser;  // [Bpad]
-  unsigned *tickets;     // [2*nblk] band arrival counters (zero before the first launch)
+  int tile_i, tile_j;  // rows x columns of one CTA tile
+  int nblk_i, nblk_j;  // ceil(B / tile_i), ceil(B / tile_j)
+  int Bpad;            // B rounded up to the larger tile
+  float *rowP, *rowN;  // [nblk_j][Bpad]
+  float *colP, *colN;  // [nblk_i][Bpad]
+  float *losspart;     // [nblk_i*nblk_j]
+  float *litem, *luser;  // [Bpad] branch losses per position (model.py:213,215)
+  float *gA, *gAN, *gG;  // [Bpad] sig(sp), sig(sn), sig(su)
+  size_t part_bytes;     // leading bytes of the workspace that must be 0xff before the first launch
   size_t bytes;
 };
 GridWs grid_ws_layout(int B, void *base);
@@ -50,11 +51,13 @@ int launch_gather_dots(const float *Ue, const float *Ie, const float *Ur, const 
                        const float *w, const float *wu, const int32_t *u, const int32_t *p,
                        const int32_t *n, const StepState *st, int B, float *yp, float *yn,
                        float *sp, float *sn, float *su, float *regsq, float *snap,
-                       cudaStream_t s);
-int launch_grid_bce(const float *yp, const float *yn, const float *sp, const float *sn,
-                    const float *su, int B, float alpha, float beta, const GridWs &ws,
-                    float *d_yp, float *d_yn, float *d_sp, float *d_sn, float *d_su,
-                    int want_grad, cudaStream_t s);
+                       const GridWs *gates, cudaStream_t s);
+// gates of the batch into ws (the stand-alone grid entry point; trainers use gather_dots)
+int launch_gates(const float *sp, const float *sn, const float *su, int B, const GridWs &ws,
+                 cudaStream_t s);
+int launch_grid_bce(const float *yp, const float *yn, int B, float alpha, float beta,
+                    const GridWs &ws, float *d_yp, float *d_yn, float *d_sp, float *d_sn,
+                    float *d_su, int want_grad, cudaStream_t s);
 // losses: if st != null writes {loss, mf, reg, L_ori} to st->cur_loss, else {L_ori,L_item,L_user}
 // to losses3.
 int launch_reduce_losses(const GridWs &ws, const float *regsq, int B, float alpha, float beta,

@@ -78,7 +78,7 @@ struct TrainerBase {
     MACR_CUDA(cudaMalloc(&loss_stage, sizeof(float) * 4));
     MACR_CUDA(cudaMalloc(&scal, sizeof(float) * 11 * (size_t)maxB));
     MACR_CUDA(cudaMalloc(&gridws, grid_ws_layout(maxB, nullptr).bytes + 4096));
-    MACR_CUDA(cudaMemset(gridws, 0, grid_ws_layout(maxB, nullptr).bytes + 4096));  // band tickets
+    MACR_CUDA(cudaMemset(gridws, 0xff, grid_ws_layout(maxB, nullptr).bytes + 4096));  // empty slots
     MACR_CUDA(cudaMalloc(&snap, sizeof(float) * kD * 3 * (size_t)maxB));
     MACR_CUDA(cudaMalloc(&tail_ticket, sizeof(unsigned) * 4));
     MACR_CUDA(cudaMemset(tail_ticket, 0, sizeof(unsigned) * 4));
@@ -189,16 +189,16 @@ static int mf_enqueue(macr_mf_trainer *h, int B) {
   MACR_CUDA(cudaEventRecord(h->ev_join2, side2));
   // main: gather (+ row snapshot) -> B x B grid (+ band folds) -> row gradients + Adam + tail
   rc = launch_gather_dots(h->U, h->I, h->U, h->I, h->w, h->wu, nullptr, nullptr, nullptr, h->st, B,
-                          yp, yn, sp, sn, su, rq, h->snap, s);
+                          yp, yn, sp, sn, su, rq, h->snap, &g, s);
   if (rc) return rc;
-  rc = launch_grid_bce(yp, yn, sp, sn, su, B, hp.alpha, hp.beta, g, dyp, dyn, dsp, dsn, dsu, 1, s);
+  rc = launch_grid_bce(yp, yn, B, hp.alpha, hp.beta, g, dyp, dyn, dsp, dsn, dsu, 1, s);
   if (rc) return rc;
   MACR_CUDA(cudaStreamWaitEvent(s, h->ev_join, 0));
   MACR_CUDA(cudaStreamWaitEvent(s, h->ev_join2, 0));
   const float lam = hp.decay / (float)hp.batch_size_flag;
   const AdamTabs tabs{h->U, h->mU, h->vU, h->I, h->mI, h->vI, h->bmU, h->bmI,
                       hp.beta1, hp.beta2, hp.eps, hp.lr, h->st};
-  const TailArgs tail{1, h->w, h->mw, h->vw, h->wu, h->mwu, h->vwu, g.losspart, g.nblk * g.nblk,
+  const TailArgs tail{1, h->w, h->mw, h->vw, h->wu, h->mwu, h->vwu, g.losspart, g.nblk_i * g.nblk_j,
                       g.litem, g.luser, rq, hp, h->st, h->tail_ticket};
   rc = launch_row_grads(h->snap, h->w, h->wu, B, dyp, dyn, dsp, dsn, dsu, lam, h->planU, h->planI,
                         h->gU, h->gI, h->unit_part, h->gw_part, h->gwu_part, nullptr, &tabs, &tail, s);
@@ -404,10 +404,9 @@ static int lgcn_enqueue_impl(macr_lgcn_trainer *h, int B, int train) {
   if (rc) return rc;
   launches += h->L;
   rc = launch_gather_dots(Ue, Ie, h->U, h->I, h->w, h->wu, nullptr, nullptr, nullptr, h->st, B, yp,
-                          yn, sp, sn, su, rq, h->snap, s);
+                          yn, sp, sn, su, rq, h->snap, &g, s);
   if (rc) return rc;
-  rc = launch_grid_bce(yp, yn, sp, sn, su, B, hp.alpha, hp.beta, g, dyp, dyn, dsp, dsn, dsu, train,
-                       s);
+  rc = launch_grid_bce(yp, yn, B, hp.alpha, hp.beta, g, dyp, dyn, dsp, dsn, dsu, train, s);
   if (rc) return rc;
   launches += 2;
   if (train) {
