@@ -80,12 +80,15 @@ extern "C" int macr_grid_bce_fwd_bwd(const float *yp, const float *yn, const flo
                 g.bytes);
   cudaStream_t s = as_stream(stream);
   // partial-sum slots start empty (the folders re-arm them, but `ws` is caller scratch)
-  if (want_grad) MACR_CUDA(cudaMemsetAsync(ws, 0xff, g.part_bytes, s));
+  MACR_CUDA(cudaMemsetAsync(ws, 0xff, g.part_bytes, s));
   int rc = launch_gates(sp, sn, su, B, g, s);
   if (rc) return rc;
-  rc = launch_grid_bce(yp, yn, B, alpha, beta, g, d_yp, d_yn, d_sp, d_sn, d_su, want_grad, s);
-  if (rc) return rc;
-  return launch_reduce_losses(g, nullptr, B, alpha, beta, 0.f, 1, losses3, nullptr, s);
+  macr_hparams hp{};
+  hp.alpha = alpha;
+  hp.beta = beta;
+  hp.batch_size_flag = 1;
+  return launch_grid_bce(yp, yn, B, hp, g, d_yp, d_yn, d_sp, d_sn, d_su, want_grad, nullptr, nullptr,
+                         losses3, s);
 }
 
 extern "C" size_t macr_batch_plan_workspace_bytes(int n_ids) { return plan_ws_bytes(n_ids); }

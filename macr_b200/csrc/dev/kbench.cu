@@ -139,10 +139,14 @@ int main(int argc, char **argv) {
   printf("gather_dots         warm %7.2f us   cold %7.2f us\n", time_us(gather, 20, nullptr, 0),
          time_us(gather, 20, flush, fb));
   // ---- grid ----
-  auto grid = [&]() { launch_grid_bce(yp, yn, B, 1e-2f, 1e-3f, g, dyp, dyn, dsp, dsn, dsu, 1, 0); };
+  macr_hparams hpk{};
+  hpk.alpha = 1e-2f; hpk.beta = 1e-3f; hpk.batch_size_flag = 1;
+  float *l3;
+  CK(cudaMalloc(&l3, 64));
+  auto grid = [&]() { launch_grid_bce(yp, yn, B, hpk, g, dyp, dyn, dsp, dsn, dsu, 1, nullptr, nullptr, l3, 0); };
   printf("grid_bce (grad)     warm %7.2f us   cold %7.2f us\n", time_us(grid, 20, nullptr, 0),
          time_us(grid, 20, flush, fb));
-  auto grid0 = [&]() { launch_grid_bce(yp, yn, B, 1e-2f, 1e-3f, g, dyp, dyn, dsp, dsn, dsu, 0, 0); };
+  auto grid0 = [&]() { launch_grid_bce(yp, yn, B, hpk, g, dyp, dyn, dsp, dsn, dsu, 0, nullptr, nullptr, l3, 0); };
   printf("grid_bce (loss)     warm %7.2f us\n", time_us(grid0, 20, nullptr, 0));
   // ---- sweep ----
   auto sweep = [&]() {

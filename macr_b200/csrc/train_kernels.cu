@@ -155,6 +155,12 @@ int launch_gather_dots(const float *Ue, const float *Ie, const float *Ur, const 
 // ---------------------------------------------------------------------------------------------
 struct GridOut {
   float *d_yp, *d_yn, *d_sp, *d_sn, *d_su;
+  // loss outputs (written by the loss folder CTA): st != nullptr -> {loss, mf, reg, L_ori} at
+  // st->loss_base + 4*st->step_idx, else {L_ori, L_item, L_user} at losses3
+  const float *regsq;
+  macr_hparams hp;
+  const StepState *st;
+  float *losses3;
 };
 
 template <bool kChecked, bool kMasked, bool kGrad>
@@ -237,6 +243,70 @@ __device__ __forceinline__ float take_partials(float *slot, int n, size_t stride
   return acc;
 }
 
+// the loss folder: sum of the tile loss partials (sentinel-armed slots like the band partials)
+// and of the per-position branch losses / L2 squares -> the step's loss scalars (model.py:217-221)
+__device__ void grid_fold_losses(int B, const GridWs &ws, const GridOut &out, double *sh) {
+  const int tid = threadIdx.x;
+  const int nparts = ws.nblk_i * ws.nblk_j;
+  // everything that does not depend on the tiles first: destination, per-position sums
+  float *dst = out.losses3;
+  if (out.st != nullptr) dst = out.st->loss_base + out.st->step_idx * 4;
+  double a1 = 0, a2 = 0, a3 = 0;
+#pragma unroll 4
+  for (int k = tid; k < B; k += 256) {
+    a1 += ws.litem[k];
+    a2 += ws.luser[k];
+    if (out.regsq) a3 += out.regsq[k];
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    a1 += __shfl_xor_sync(0xffffffffu, a1, o);
+    a2 += __shfl_xor_sync(0xffffffffu, a2, o);
+    a3 += __shfl_xor_sync(0xffffffffu, a3, o);
+  }
+  if ((tid & 31) == 0) {
+    sh[(tid >> 5) * 4 + 1] = a1;
+    sh[(tid >> 5) * 4 + 2] = a2;
+    sh[(tid >> 5) * 4 + 3] = a3;
+  }
+  __syncthreads();
+  const double invB = 1.0 / (double)B;
+  float l_item = 0.f, l_user = 0.f, reg = 0.f;
+  if (tid == 0) {
+    a1 = a2 = a3 = 0;
+    for (int k = 0; k < 8; ++k) {
+      a1 += sh[k * 4 + 1];
+      a2 += sh[k * 4 + 2];
+      a3 += sh[k * 4 + 3];
+    }
+    l_item = (float)(a1 * invB);
+    l_user = (float)(a2 * invB);
+    reg = out.hp.decay * ((float)(a3 * 0.5) / (float)out.hp.batch_size_flag);
+  }
+  // the tile partials as they arrive
+  double a0 = 0;
+  if (tid < nparts) a0 = (double)take_partials(ws.losspart + tid, (nparts - tid + 255) / 256, 256);
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) a0 += __shfl_xor_sync(0xffffffffu, a0, o);
+  if ((tid & 31) == 0) sh[(tid >> 5) * 4] = a0;
+  __syncthreads();
+  if (tid != 0) return;
+  a0 = 0;
+  for (int k = 0; k < 8; ++k) a0 += sh[k * 4];
+  const float l_ori = (float)(-0.6931471805599453 * a0 * invB * invB);
+  if (out.st == nullptr) {
+    dst[0] = l_ori;
+    dst[1] = l_item;
+    dst[2] = l_user;
+  } else {
+    const float mf = l_ori + out.hp.alpha * l_item + out.hp.beta * l_user;
+    dst[0] = mf + reg;
+    dst[1] = mf;
+    dst[2] = reg;
+    dst[3] = l_ori;
+  }
+}
+
 template <int TI, int TJ>
 __device__ void grid_fold_band(int f, int B, float alpha, float beta, const GridWs &ws,
                                const GridOut &out, float *scratch /* >= 2*TI floats */) {
@@ -292,9 +362,12 @@ grid_bce_kernel(const float *__restrict__ yp, const float *__restrict__ yn, int 
 
   const int tid = threadIdx.x, tx = tid & 15, ty = tid >> 4;
   const int Bpad = ws.Bpad;
-  if (kGrad && (int)blockIdx.y >= ws.nblk_i) {  // band folders ride at the end of the grid
-    grid_fold_band<TI, TJ>((blockIdx.y - ws.nblk_i) * gridDim.x + blockIdx.x, B, alpha, beta, ws, out,
-                           &sRed[0][0][0]);
+  if ((int)blockIdx.y >= ws.nblk_i) {  // folders ride at the end of the grid
+    const int f = (blockIdx.y - ws.nblk_i) * gridDim.x + blockIdx.x;
+    if (f == 0)
+      grid_fold_losses(B, ws, out, reinterpret_cast<double *>(&sRed[0][0][0]));
+    else if (kGrad)
+      grid_fold_band<TI, TJ>(f - 1, B, alpha, beta, ws, out, &sRed[0][0][0]);
     return;
   }
   const int i0 = blockIdx.y * TI, j0 = blockIdx.x * TJ;
@@ -432,7 +505,7 @@ grid_bce_kernel(const float *__restrict__ yp, const float *__restrict__ yn, int 
     float acc = 0.f;
 #pragma unroll
     for (int q = 0; q < 8; ++q) acc += sLoss[q];
-    ws.losspart[blockIdx.y * gridDim.x + blockIdx.x] = (float)((double)acc + sRank1);
+    __stcg(&ws.losspart[blockIdx.y * gridDim.x + blockIdx.x], not_sentinel((float)((double)acc + sRank1)));
   }
 }
 
@@ -478,7 +551,7 @@ GridWs grid_ws_layout(int B, void *base) {
   w.gA = w.luser + w.Bpad;
   w.gAN = w.gA + w.Bpad;
   w.gG = w.gAN + w.Bpad;
-  w.part_bytes = (2 * band_r + 2 * band_c) * sizeof(float);  // rowP..colN: sentinel-armed slots
+  w.part_bytes = (2 * band_r + 2 * band_c + lp) * sizeof(float);  // rowP..losspart: armed slots
   w.bytes = (2 * band_r + 2 * band_c + lp + 5 * (size_t)w.Bpad) * sizeof(float);
   return w;
 }
@@ -521,8 +594,9 @@ int launch_gates(const float *sp, const float *sn, const float *su, int B, const
 template <int RI, int RJ, int MINB, bool kGrad>
 static void launch_grid_t(const float *yp, const float *yn, int B, float alpha, float beta,
                           const GridWs &ws, const GridOut &out, cudaStream_t s) {
-  // tiles, then (grad only) one folder CTA per row band and per column band
-  const int fold_rows = kGrad ? (ws.nblk_i + ws.nblk_j + ws.nblk_j - 1) / ws.nblk_j : 0;
+  // tiles, then the loss folder and (grad only) one folder CTA per row band and per column band
+  const int folders = 1 + (kGrad ? ws.nblk_i + ws.nblk_j : 0);
+  const int fold_rows = (folders + ws.nblk_j - 1) / ws.nblk_j;
   dim3 grid(ws.nblk_j, ws.nblk_i + fold_rows);
   if (B % ws.tile_i == 0 && B % ws.tile_j == 0)
     grid_bce_kernel<RI, RJ, MINB, false, kGrad><<<grid, 256, 0, s>>>(yp, yn, B, alpha, beta, ws, out);
@@ -533,10 +607,12 @@ static void launch_grid_t(const float *yp, const float *yn, int B, float alpha, 
 // the partial-sum slots of `ws` (first ws.part_bytes bytes) must hold 0xff bytes before the first
 // launch (the folders re-arm them);
 // ws.gA / gAN / gG / litem / luser must hold the gates of the batch (launch_gates / gather_dots)
-int launch_grid_bce(const float *yp, const float *yn, int B, float alpha, float beta,
+int launch_grid_bce(const float *yp, const float *yn, int B, const macr_hparams &hp,
                     const GridWs &ws, float *d_yp, float *d_yn, float *d_sp, float *d_sn,
-                    float *d_su, int want_grad, cudaStream_t s) {
-  const GridOut out{d_yp, d_yn, d_sp, d_sn, d_su};
+                    float *d_su, int want_grad, const float *regsq, const StepState *st,
+                    float *losses3, cudaStream_t s) {
+  const float alpha = hp.alpha, beta = hp.beta;
+  const GridOut out{d_yp, d_yn, d_sp, d_sn, d_su, regsq, hp, st, losses3};
   const int ri = ws.tile_i / 16, rj = ws.tile_j / 16;
 #define MACR_GRID_CASE(RI_, RJ_, MINB_)                                                          \
   if (ri == RI_ && rj == RJ_) {                                                                   \
@@ -553,68 +629,6 @@ int launch_grid_bce(const float *yp, const float *yn, int B, float alpha, float 
   return MACR_OK;
 }
 
-// deterministic block sum in double (fixed tree); result valid in thread 0
-__device__ double block_sum_1024(double v, double *sh) {
-  const int tid = threadIdx.x;
-  sh[tid] = v;
-  __syncthreads();
-  for (int o = 512; o > 0; o >>= 1) {
-    if (tid < o) sh[tid] += sh[tid + o];
-    __syncthreads();
-  }
-  const double r = sh[0];
-  __syncthreads();
-  return r;
-}
-
-__global__ void __launch_bounds__(1024)
-reduce_losses_kernel(const float *__restrict__ losspart, int nparts, const float *__restrict__ litem,
-                     const float *__restrict__ luser, const float *__restrict__ regsq, int B,
-                     float alpha, float beta, float decay, int batch_size_flag,
-                     float *__restrict__ losses3, const StepState *st) {
-  __shared__ double sh[1024];
-  const int tid = threadIdx.x;
-  double a0 = 0, a1 = 0, a2 = 0, a3 = 0;
-  for (int k = tid; k < nparts; k += 1024) a0 += losspart[k];
-  for (int k = tid; k < B; k += 1024) {
-    a1 += litem[k];
-    a2 += luser[k];
-    if (regsq) a3 += regsq[k];
-  }
-  a0 = block_sum_1024(a0, sh);
-  a1 = block_sum_1024(a1, sh);
-  a2 = block_sum_1024(a2, sh);
-  a3 = block_sum_1024(a3, sh);
-  if (tid == 0) {
-    const double invB = 1.0 / (double)B;
-    const float l_ori = (float)(-0.6931471805599453 * a0 * invB * invB);
-    const float l_item = (float)(a1 * invB), l_user = (float)(a2 * invB);
-    if (st == nullptr) {
-      losses3[0] = l_ori;
-      losses3[1] = l_item;
-      losses3[2] = l_user;
-    } else {
-      const float reg = decay * ((float)(a3 * 0.5) / (float)batch_size_flag);
-      const float mf = l_ori + alpha * l_item + beta * l_user;
-      float *out = st->loss_base + st->step_idx * 4;
-      out[0] = mf + reg;
-      out[1] = mf;
-      out[2] = reg;
-      out[3] = l_ori;
-    }
-  }
-}
-
-int launch_reduce_losses(const GridWs &ws, const float *regsq, int B, float alpha, float beta,
-                         float decay, int batch_size_flag, float *losses3, const StepState *st,
-                         cudaStream_t s) {
-  reduce_losses_kernel<<<1, 1024, 0, s>>>(ws.losspart, ws.nblk_i * ws.nblk_j, ws.litem, ws.luser,
-                                          regsq, B, alpha, beta, decay, batch_size_flag, losses3,
-                                          st);
-  MACR_LAUNCH_CHECK();
-  return MACR_OK;
-}
-
 // ---------------------------------------------------------------------------------------------
 // K5a: batch plan -- group the batch positions that hit the same table row, deterministically.
 // One CTA per table runs a stable LSD radix sort (8-bit digits) of the row ids in shared memory
@@ -625,8 +639,9 @@ int launch_reduce_losses(const GridWs &ws, const float *regsq, int B, float alph
 // the (digit, warp) histogram turns ranks into destinations.  Stability keeps positions
 // ascending inside a row -- the order TF's unsorted_segment_sum adds the duplicate slices in.
 // A block scan over the segment heads then emits the compact plan:
-//   uniq_rows[slot], seg_off[slot], seg_pos[k] (k = sorted index), kinfo[k] = rank << 16 | slot,
-//   *n_uniq.
+//   uniq_rows[slot], seg_off[slot], seg_pos[k] (k = sorted index), *n_uniq, and one 16-byte
+//   record per sorted index {rank << 16 | slot, row, position, first position of the segment}
+//   -- everything the row-gradient kernel needs about an entry in one load.
 // (array_ops.unique would list the rows in first-occurrence order; the order of the unique rows
 // does not enter any result, only the order inside a segment does.)
 // ---------------------------------------------------------------------------------------------
@@ -794,7 +809,8 @@ batch_plan_sort_kernel(PlanTable t0, PlanTable t1, const StepState *st, int B) {
         const int slot = base + lslot[r];
         const int start = lstart[r] >= 0 ? lstart[r] : bmax;
         t.out.seg_pos[k] = (int32_t)posA[k];
-        t.out.kinfo[k] = (int32_t)(((uint32_t)(k - start) << 16) | (uint32_t)slot);
+        t.out.rec[k] = make_int4((int)(((uint32_t)(k - start) << 16) | (uint32_t)slot), (int)keyA[k],
+                                 (int)posA[k], (int)posA[start]);
         if (k == start) {
           t.out.uniq_rows[slot] = (int32_t)keyA[k];
           t.out.seg_off[slot] = k;
@@ -809,8 +825,8 @@ batch_plan_sort_kernel(PlanTable t0, PlanTable t1, const StepState *st, int B) {
   PLAN_STAMP(22);
 }
 
-// scratch behind PlanBufs: kinfo[n_ids], done[n_ids] (done: zero before the first use, self re-arming)
-size_t plan_ws_bytes(int n_ids) { return sizeof(int32_t) * (2 * (size_t)n_ids + 16); }
+// scratch behind PlanBufs: rec[n_ids] (int4), done[n_ids] (zero before the first use, self re-arming)
+size_t plan_ws_bytes(int n_ids) { return sizeof(int32_t) * (5 * (size_t)n_ids + 16); }
 
 static size_t plan_smem_bytes(int npad) { return (size_t)npad * 12 + 256 * 33 * 4; }
 
@@ -833,8 +849,8 @@ PlanBufs plan_carve(int32_t *uniq_rows, int32_t *seg_off, int32_t *seg_pos, int3
   b.seg_off = seg_off;
   b.seg_pos = seg_pos;
   b.n_uniq = n_uniq;
-  b.kinfo = p;
-  b.done = p + n_ids;
+  b.rec = reinterpret_cast<int4 *>(p);  // ws is 16-byte aligned (cudaMalloc / torch allocations)
+  b.done = p + 4 * (size_t)n_ids;
   return b;
 }
 
@@ -1003,16 +1019,15 @@ constexpr int kRowWarps = 8;
 constexpr int kUnit = 32;
 constexpr int kWgradPerCta = 64;  // batch positions per w-gradient CTA
 
-// ApplyAdam on w / w_user from the per-CTA gradient partials, the loss reduction, and the
-// step-state advance (adam.py _finish: beta powers *= beta).  Runs in ONE CTA of NT threads.
+// ApplyAdam on w / w_user from the per-CTA gradient partials and the step-state advance
+// (adam.py _finish: beta powers *= beta).  Runs in ONE CTA of NT threads.  (The loss scalars of
+// the step are produced by the grid kernel's loss folder.)
 template <int NT>
 __device__ void step_tail_body(float *w, float *mw, float *vw, float *wu, float *mwu, float *vwu,
                                const float *gw_part, const float *gwu_part, int n_part,
-                               const float *losspart, int nparts, const float *litem,
-                               const float *luser, const float *regsq, int B,
-                               const macr_hparams &hp, StepState *st, int train, double *sh,
+                               const macr_hparams &hp, StepState *st, int train,
                                float (*shg)[kD]) {
-  constexpr int NW = NT / 32, GR = NT / (2 * kD);  // warps; partial groups per vector
+  constexpr int GR = NT / (2 * kD);  // partial groups per vector
   const int tid = threadIdx.x;
   const float lr_t = step_lr_t(st, hp.lr);
   if (train) {
@@ -1022,37 +1037,7 @@ __device__ void step_tail_body(float *w, float *mw, float *vw, float *wu, float 
     for (int q = grp; q < n_part; q += GR) a += __ldcg(src + (long long)q * kD + k);
     shg[which * GR + grp][k] = a;
   }
-  double a0 = 0, a1 = 0, a2 = 0, a3 = 0;
-  for (int k = tid; k < nparts; k += NT) a0 += __ldcg(losspart + k);
-  for (int k = tid; k < B; k += NT) {
-    a1 += __ldcg(litem + k);
-    a2 += __ldcg(luser + k);
-    a3 += __ldcg(regsq + k);
-  }
-  // one fixed-shape reduction tree for the four sums: warp shuffles, then the warp leaders
-#pragma unroll
-  for (int o = 16; o > 0; o >>= 1) {
-    a0 += __shfl_xor_sync(0xffffffffu, a0, o);
-    a1 += __shfl_xor_sync(0xffffffffu, a1, o);
-    a2 += __shfl_xor_sync(0xffffffffu, a2, o);
-    a3 += __shfl_xor_sync(0xffffffffu, a3, o);
-  }
-  if ((tid & 31) == 0) {
-    sh[(tid >> 5) * 4 + 0] = a0;
-    sh[(tid >> 5) * 4 + 1] = a1;
-    sh[(tid >> 5) * 4 + 2] = a2;
-    sh[(tid >> 5) * 4 + 3] = a3;
-  }
-  __syncthreads();  // also publishes shg
-  if (tid == 0) {
-    a0 = a1 = a2 = a3 = 0;
-    for (int k = 0; k < NW; ++k) {
-      a0 += sh[k * 4 + 0];
-      a1 += sh[k * 4 + 1];
-      a2 += sh[k * 4 + 2];
-      a3 += sh[k * 4 + 3];
-    }
-  }
+  __syncthreads();
   if (train && tid < 2 * kD) {
     const int k = tid & 63, which = tid >> 6;
     float g = 0.f;
@@ -1068,16 +1053,6 @@ __device__ void step_tail_body(float *w, float *mw, float *vw, float *wu, float 
   }
   __syncthreads();  // every lr_t read of this step is done
   if (tid == 0) {
-    const double invB = 1.0 / (double)B;
-    const float l_ori = (float)(-0.6931471805599453 * a0 * invB * invB);
-    const float l_item = (float)(a1 * invB), l_user = (float)(a2 * invB);
-    const float reg = hp.decay * ((float)(a3 * 0.5) / (float)hp.batch_size_flag);
-    const float mf = l_ori + hp.alpha * l_item + hp.beta * l_user;
-    float *out = st->loss_base + st->step_idx * 4;
-    out[0] = mf + reg;
-    out[1] = mf;
-    out[2] = reg;
-    out[3] = l_ori;
     if (train) {
       st->b1p = __fmul_rn(st->b1p, hp.beta1);
       st->b2p = __fmul_rn(st->b2p, hp.beta2);
@@ -1096,7 +1071,6 @@ row_grads_kernel(const float *__restrict__ snap, const float *__restrict__ w,
                  float *unit_part, int pos_ctas, float *__restrict__ gw_part,
                  float *__restrict__ gwu_part, AdamTabs tabs, TailArgs tail) {
   __shared__ float2 sW[kRowWarps][32], sWU[kRowWarps][32];
-  __shared__ double sTail[kRowWarps * 4];
   __shared__ float sTailG[2 * (kRowWarps * 32 / (2 * kD))][kD];
   __shared__ int sLast;
   const int lane = threadIdx.x & 31, wl = threadIdx.x >> 5;
@@ -1141,18 +1115,23 @@ row_grads_kernel(const float *__restrict__ snap, const float *__restrict__ w,
     const int k = item ? wid - B : wid;
     const PlanBufs &pl = item ? planI : planU;
     const int n_ids = item ? 2 * B : B;
-    unsigned info = 0x10000u;  // rank 1: not a unit start
-    if (wid < 3 * B) info = (unsigned)pl.kinfo[k];
+    // level 1: one 16-byte record per lane (entry k + lane), plus the record after the unit
+    int4 rec = make_int4(0x10000, 0, 0, 0);  // rank 1: not a unit start
+    if (wid < 3 * B && k + lane < n_ids) rec = pl.rec[k + lane];
+    int next_info = -1;
+    if (lane == 0 && wid < 3 * B && k + kUnit < n_ids) next_info = pl.rec[k + kUnit].x;
+    const unsigned info = (unsigned)__shfl_sync(0xffffffffu, rec.x, 0);
     const int rk = (int)(info >> 16), slot = (int)(info & 0xffffu);
     if (rk % kUnit == 0) {  // this warp owns one unit of the segment
-      // everything that depends only on (k, slot) is requested at once
       const int s0 = k - rk;
-      const int s1 = pl.seg_off[slot + 1];
-      const int qq_spec = (k + lane < n_ids) ? pl.seg_pos[k + lane] : 0;
-      const long long r = pl.uniq_rows[slot];
-      const int q0 = pl.seg_pos[s0];
-      const int total = s1 - s0;
-      const int cnt = min(kUnit, s1 - k);
+      const bool mine = (rec.x & 0xffff) == slot && k + lane < n_ids;
+      const int cnt = __popc(__ballot_sync(0xffffffffu, mine));  // sorted: a prefix of the lanes
+      const long long r = __shfl_sync(0xffffffffu, rec.y, 0);
+      const int q0 = __shfl_sync(0xffffffffu, rec.w, 0);
+      next_info = __shfl_sync(0xffffffffu, next_info, 0);
+      const bool multi = rk > 0 || (cnt == kUnit && next_info >= 0 && (next_info & 0xffff) == slot);
+      const int total = multi ? pl.seg_off[slot + 1] - s0 : cnt;
+      const int qq_spec = rec.z;
       const float2 bias = reinterpret_cast<const float2 *>(item ? w : wu)[lane];
       // metadata of this unit's entries, one entry per lane
       int ra = 0;  // snapshot row of the partner (item unit: user row b; user unit: position b)
@@ -1291,9 +1270,7 @@ row_grads_kernel(const float *__restrict__ snap, const float *__restrict__ w,
   __syncthreads();
   if (!sLast) return;
   step_tail_body<kRowWarps * 32>(tail.w, tail.mw, tail.vw, tail.wu, tail.mwu, tail.vwu, gw_part,
-                                 gwu_part, gridDim.x - pos_ctas, tail.losspart, tail.nparts,
-                                 tail.litem, tail.luser, tail.regsq, B, tail.hp, tail.st, 1, sTail,
-                                 sTailG);
+                                 gwu_part, gridDim.x - pos_ctas, tail.hp, tail.st, 1, sTailG);
 }
 
 int row_grads_max_parts(int B) { return (B + kWgradPerCta - 1) / kWgradPerCta; }
@@ -1444,22 +1421,16 @@ int launch_adam_dense(float *var, float *m, float *v, const float *grad, int64_t
 __global__ void __launch_bounds__(1024)
 step_tail_kernel(float *w, float *mw, float *vw, float *wu, float *mwu, float *vwu,
                  const float *__restrict__ gw_part, const float *__restrict__ gwu_part, int n_part,
-                 const float *__restrict__ losspart, int nparts, const float *__restrict__ litem,
-                 const float *__restrict__ luser, const float *__restrict__ regsq, int B,
                  macr_hparams hp, StepState *st, int train) {
-  __shared__ double sh[32 * 4];
   __shared__ float shg[16][kD];
-  step_tail_body<1024>(w, mw, vw, wu, mwu, vwu, gw_part, gwu_part, n_part, losspart, nparts, litem,
-                       luser, regsq, B, hp, st, train, sh, shg);
+  step_tail_body<1024>(w, mw, vw, wu, mwu, vwu, gw_part, gwu_part, n_part, hp, st, train, shg);
 }
 
 int launch_step_tail(float *w, float *mw, float *vw, float *wu, float *mwu, float *vwu,
-                     const float *gw_part, const float *gwu_part, int n_part, const GridWs &ws,
-                     const float *regsq, int B, const macr_hparams &hp, StepState *st, int train,
-                     cudaStream_t s) {
-  step_tail_kernel<<<1, 1024, 0, s>>>(w, mw, vw, wu, mwu, vwu, gw_part, gwu_part, n_part,
-                                      ws.losspart, ws.nblk_i * ws.nblk_j, ws.litem, ws.luser, regsq, B,
-                                      hp, st, train);
+                     const float *gw_part, const float *gwu_part, int n_part,
+                     const macr_hparams &hp, StepState *st, int train, cudaStream_t s) {
+  step_tail_kernel<<<1, 1024, 0, s>>>(w, mw, vw, wu, mwu, vwu, gw_part, gwu_part, n_part, hp, st,
+                                      train);
   MACR_LAUNCH_CHECK();
   return MACR_OK;
 }

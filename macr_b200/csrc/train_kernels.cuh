@@ -38,7 +38,8 @@ struct PlanBufs {  // output of one batch_plan over n_ids ids (+ its scratch)
   int32_t *seg_off;    // [n_uniq+1] offsets into the sorted order
   int32_t *seg_pos;    // [n_ids] batch positions sorted by (row, position)
   int32_t *n_uniq;     // device scalar
-  int32_t *kinfo;      // [n_ids] (rank inside the segment) << 16 | segment index, per sorted index
+  int4 *rec;           // [n_ids] per sorted index: {rank << 16 | slot, row, position, first position
+                       //          of the segment}
   int32_t *done;       // [n_ids] per-segment arrival counters (multi-unit segments)
 };
 PlanBufs plan_carve(int32_t *uniq_rows, int32_t *seg_off, int32_t *seg_pos, int32_t *n_uniq,
@@ -55,14 +56,12 @@ int launch_gather_dots(const float *Ue, const float *Ie, const float *Ur, const 
 // gates of the batch into ws (the stand-alone grid entry point; trainers use gather_dots)
 int launch_gates(const float *sp, const float *sn, const float *su, int B, const GridWs &ws,
                  cudaStream_t s);
-int launch_grid_bce(const float *yp, const float *yn, int B, float alpha, float beta,
+// B x B grid + band folds + the step's loss scalars.  st != nullptr: {loss, mf, reg, L_ori} go
+// to st->loss_base + 4*st->step_idx (regsq required); else {L_ori, L_item, L_user} to losses3.
+int launch_grid_bce(const float *yp, const float *yn, int B, const macr_hparams &hp,
                     const GridWs &ws, float *d_yp, float *d_yn, float *d_sp, float *d_sn,
-                    float *d_su, int want_grad, cudaStream_t s);
-// losses: if st != null writes {loss, mf, reg, L_ori} to st->cur_loss, else {L_ori,L_item,L_user}
-// to losses3.
-int launch_reduce_losses(const GridWs &ws, const float *regsq, int B, float alpha, float beta,
-                         float decay, int batch_size_flag, float *losses3, const StepState *st,
-                         cudaStream_t s);
+                    float *d_su, int want_grad, const float *regsq, const StepState *st,
+                    float *losses3, cudaStream_t s);
 size_t plan_ws_bytes(int n_ids);
 int plan_init();
 // two tables in one launch (table 1 optional: n_ids1 == 0)
@@ -86,9 +85,6 @@ struct AdamTabs {  // U == nullptr: no fused Adam, summed rows go to gU / gI (Li
 struct TailArgs {
   int fused;  // 1: the last CTA runs the step tail
   float *w, *mw, *vw, *wu, *mwu, *vwu;
-  const float *losspart;
-  int nparts;
-  const float *litem, *luser, *regsq;
   macr_hparams hp;
   StepState *st;
   unsigned *ticket;
@@ -107,11 +103,10 @@ int launch_adam_rows2(float *U, float *mU, float *vU, PlanBufs planU, const floa
 int launch_adam_vec2(float *w, float *mw, float *vw, float *wu, float *mwu, float *vwu,
                      const float *gw_part, const float *gwu_part, int n_part, float lr_t,
                      const StepState *st, float b1, float b2, float eps, cudaStream_t s);
-// last kernel of a step: ApplyAdam on w / w_user (train), loss reduction, state advance
+// last kernel of a LightGCN / loss-only step: ApplyAdam on w / w_user (train), state advance
 int launch_step_tail(float *w, float *mw, float *vw, float *wu, float *mwu, float *vwu,
-                     const float *gw_part, const float *gwu_part, int n_part, const GridWs &ws,
-                     const float *regsq, int B, const macr_hparams &hp, StepState *st, int train,
-                     cudaStream_t s);
+                     const float *gw_part, const float *gwu_part, int n_part,
+                     const macr_hparams &hp, StepState *st, int train, cudaStream_t s);
 int launch_adam_dense(float *var, float *m, float *v, const float *grad, int64_t n_elems,
                       float lr_t, const StepState *st, float b1, float b2, float eps,
                       cudaStream_t s);

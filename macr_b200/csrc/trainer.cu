@@ -191,15 +191,14 @@ static int mf_enqueue(macr_mf_trainer *h, int B) {
   rc = launch_gather_dots(h->U, h->I, h->U, h->I, h->w, h->wu, nullptr, nullptr, nullptr, h->st, B,
                           yp, yn, sp, sn, su, rq, h->snap, &g, s);
   if (rc) return rc;
-  rc = launch_grid_bce(yp, yn, B, hp.alpha, hp.beta, g, dyp, dyn, dsp, dsn, dsu, 1, s);
+  rc = launch_grid_bce(yp, yn, B, hp, g, dyp, dyn, dsp, dsn, dsu, 1, rq, h->st, nullptr, s);
   if (rc) return rc;
   MACR_CUDA(cudaStreamWaitEvent(s, h->ev_join, 0));
   MACR_CUDA(cudaStreamWaitEvent(s, h->ev_join2, 0));
   const float lam = hp.decay / (float)hp.batch_size_flag;
   const AdamTabs tabs{h->U, h->mU, h->vU, h->I, h->mI, h->vI, h->bmU, h->bmI,
                       hp.beta1, hp.beta2, hp.eps, hp.lr, h->st};
-  const TailArgs tail{1, h->w, h->mw, h->vw, h->wu, h->mwu, h->vwu, g.losspart, g.nblk_i * g.nblk_j,
-                      g.litem, g.luser, rq, hp, h->st, h->tail_ticket};
+  const TailArgs tail{1, h->w, h->mw, h->vw, h->wu, h->mwu, h->vwu, hp, h->st, h->tail_ticket};
   rc = launch_row_grads(h->snap, h->w, h->wu, B, dyp, dyn, dsp, dsn, dsu, lam, h->planU, h->planI,
                         h->gU, h->gI, h->unit_part, h->gw_part, h->gwu_part, nullptr, &tabs, &tail, s);
   if (rc) return rc;
@@ -406,7 +405,7 @@ static int lgcn_enqueue_impl(macr_lgcn_trainer *h, int B, int train) {
   rc = launch_gather_dots(Ue, Ie, h->U, h->I, h->w, h->wu, nullptr, nullptr, nullptr, h->st, B, yp,
                           yn, sp, sn, su, rq, h->snap, &g, s);
   if (rc) return rc;
-  rc = launch_grid_bce(yp, yn, B, hp.alpha, hp.beta, g, dyp, dyn, dsp, dsn, dsu, train, s);
+  rc = launch_grid_bce(yp, yn, B, hp, g, dyp, dyn, dsp, dsn, dsu, train, rq, h->st, nullptr, s);
   if (rc) return rc;
   launches += 2;
   if (train) {
@@ -442,11 +441,11 @@ static int lgcn_enqueue_impl(macr_lgcn_trainer *h, int B, int train) {
     if (rc) return rc;
     launches += 3;
     rc = launch_step_tail(h->w, h->mw, h->vw, h->wu, h->mwu, h->vwu, h->gw_part, h->gwu_part,
-                          n_part, g, rq, B, hp, h->st, 1, s);
+                          n_part, hp, h->st, 1, s);
     if (rc) return rc;
   } else {
     rc = launch_step_tail(h->w, h->mw, h->vw, h->wu, h->mwu, h->vwu, h->gw_part, h->gwu_part, 0,
-                          g, rq, B, hp, h->st, 0, s);
+                          hp, h->st, 0, s);
     if (rc) return rc;
   }
   launches += 1;
