@@ -1,0 +1,210 @@
+"""`python macr_lightgcn/LightGCN.py ...` -- the LightGCN driver of the reference
+(macr_lightgcn/LightGCN.py:649-905) on the B200 path: same flags, the same double-buffered
+sampler / train threads, the same test-loss pass and early stopping, same log lines.
+Only `--alg_type lightgcn --loss bceboth` (with `--test rubiboth` or `--test normal`) is
+implemented."""
+import logging
+import os
+import random
+import sys
+import threading
+from time import time
+
+import numpy as np
+import scipy.sparse as sp
+
+from ..host import checkpoint, flags
+from ..host.data_lgcn import Data
+from ..host.evaluate import LGCNEvaluator
+from ..host.model_lgcn import LightGCN
+from ..host.session import Session
+
+
+def early_stopping(log_value, best_value, stopping_step, expected_order="acc", flag_step=100):
+    """utility/helper.py:35-50."""
+    assert expected_order in ("acc", "dec")
+    better = log_value >= best_value if expected_order == "acc" else log_value <= best_value
+    if better:
+        stopping_step, best_value = 0, log_value
+    else:
+        stopping_step += 1
+    should_stop = stopping_step >= flag_step
+    if should_stop:
+        print("Early stopping is trigger at step: {} log:{}".format(flag_step, log_value))
+    return best_value, stopping_step, should_stop
+
+
+class _Worker(threading.Thread):
+    """sample_thread / train_thread of LightGCN.py:566-647: run `fn`, keep its result in .data."""
+
+    def __init__(self, fn):
+        super().__init__()
+        self.fn, self.data, self.error = fn, None, None
+
+    def run(self):
+        try:
+            self.data = self.fn()
+        except BaseException as e:  # surfaced by the joining thread
+            self.error = e
+
+    def result(self):
+        self.join()
+        if self.error is not None:
+            raise self.error
+        return self.data
+
+
+def main(argv=None):
+    args = flags.parse_lgcn_args(argv)
+    logging.getLogger().setLevel(logging.INFO)
+    if args.alg_type != "lightgcn" or args.loss != "bceboth":
+        raise SystemExit(f"--alg_type {args.alg_type} --loss {args.loss}: only lightgcn / bceboth is "
+                         "implemented on the B200 path (DESIGN.md section 8)")
+    data_generator = Data(path=args.data_path + args.dataset, batch_size=args.batch_size, args=args)
+    seed = 12345  # LightGCN.py:651-655
+    random.seed(seed)
+    os.environ["PYTHONHASHSEED"] = str(seed)
+    np.random.seed(seed)
+    logging.basicConfig(filename="LightGCN_{}_{}_{}_{}".format(args.dataset, args.loss, args.test, args.alpha))
+    config = {"n_users": data_generator.n_users, "n_items": data_generator.n_items}
+    plain_adj, norm_adj, mean_adj, pre_adj = data_generator.get_adj_mat()
+    if args.adj_type == "plain":
+        config["norm_adj"] = plain_adj
+        print("use the plain adjacency matrix")
+    elif args.adj_type == "norm":
+        config["norm_adj"] = norm_adj
+        print("use the normalized adjacency matrix")
+    elif args.adj_type == "gcmc":
+        config["norm_adj"] = mean_adj
+        print("use the gcmc adjacency matrix")
+    elif args.adj_type == "pre":
+        config["norm_adj"] = pre_adj
+        print("use the pre adjcency matrix")
+    else:
+        config["norm_adj"] = mean_adj + sp.eye(mean_adj.shape[0])
+        print("use the mean adjacency matrix")
+    pretrain_data = None
+    if args.pretrain == -1:  # load_pretrained_data, LightGCN.py:557-564
+        path = "%spretrain/%s/%s.npz" % (args.proj_path, args.dataset, "embedding")
+        pretrain_data = np.load(path)
+        print("load the pretrained embeddings.")
+    model = LightGCN(data_config=config, pretrain_data=pretrain_data, args=args)
+    sess = Session()
+    evaluator = LGCNEvaluator(data_generator, args.batch_size, eval_mode=args.eval_mode)
+    layer = "-".join(str(l) for l in flags.as_list(args.layer_size))
+    weights_save_path = "%sweights/%s/%s/%s/l%s_r%s" % (
+        args.weights_path, args.dataset, model.model_type, layer, str(args.lr),
+        "-".join(str(r) for r in flags.as_list(args.regs)))
+    if args.save_flag == 1:
+        os.makedirs(weights_save_path, exist_ok=True)
+
+    train_fetch = [model.opt_two_bce_both, model.loss_two_bce_both, model.mf_loss_two_bce_both,
+                   model.emb_loss_two_bce_both, model.reg_loss_two_bce_both]
+    test_fetch = [model.loss_two_bce_both, model.mf_loss_two_bce_both, model.emb_loss_two_bce_both]
+    drops = {model.node_dropout: flags.as_list(args.node_dropout),
+             model.mess_dropout: flags.as_list(args.mess_dropout)}
+
+    def run_on(fetch, triple):
+        users, pos_items, neg_items = triple
+        feed = {model.users: users, model.pos_items: pos_items, model.neg_items: neg_items}
+        feed.update(drops)
+        return sess.run(fetch, feed_dict=feed)
+
+    cur_best_pre_0, stopping_step, should_stop = 0.0, 0, False
+    best_epoch, ret = 0, None
+    config["best_c_hr"], config["best_c_epoch"] = 0, 0
+    for epoch in range(1, args.epoch + 1):
+        t1 = time()
+        loss, mf_loss, emb_loss, reg_loss = 0.0, 0.0, 0.0, 0.0
+        n_batch = data_generator.n_train // args.batch_size + 1
+        sample_last = _Worker(data_generator.sample)
+        sample_last.start()
+        sample_last.join()
+        for _ in range(n_batch):  # sampler for step t+1 overlaps the device step t (:762-777)
+            triple = sample_last.result()
+            train_cur = _Worker(lambda tr=triple: run_on(train_fetch, tr))
+            sample_next = _Worker(data_generator.sample)
+            train_cur.start()
+            sample_next.start()
+            sample_next.join()
+            _, batch_loss, batch_mf_loss, batch_emb_loss, _ = train_cur.result()
+            sample_last = sample_next
+            loss += batch_loss / n_batch
+            mf_loss += batch_mf_loss / n_batch
+            emb_loss += batch_emb_loss / n_batch
+        if np.isnan(loss):
+            print("ERROR: loss is nan.")
+            sys.exit()
+        if (epoch % args.log_interval) != 0:
+            if args.verbose > 0 and epoch % args.verbose == 0:
+                perf_str = "Epoch %d [%.1fs]: train==[%.5f=%.5f + %.5f]" % (epoch, time() - t1, loss, mf_loss, emb_loss)
+                print(perf_str)
+                logging.info(perf_str)
+            continue
+
+        # test loss: n_batch loss-only steps on sample_test() triples (:799-819; consumes RNG)
+        loss_test, mf_loss_test, emb_loss_test, reg_loss_test = 0.0, 0.0, 0.0, 0.0
+        sample_last = _Worker(data_generator.sample_test)
+        sample_last.start()
+        sample_last.join()
+        for _ in range(n_batch):
+            triple = sample_last.result()
+            train_cur = _Worker(lambda tr=triple: run_on(test_fetch, tr))
+            sample_next = _Worker(data_generator.sample_test)
+            train_cur.start()
+            sample_next.start()
+            sample_next.join()
+            bl, bm, be = train_cur.result()
+            sample_last = sample_next
+            loss_test += bl / n_batch
+            mf_loss_test += bm / n_batch
+            emb_loss_test += be / n_batch
+
+        t2 = time()
+        users_to_test = list(data_generator.test_set.keys())
+        perf_str = ""
+        if args.test == "normal":
+            ret = evaluator.test(sess, model, users_to_test, drop_flag=True)
+            t3 = time()
+            if args.verbose > 0:
+                perf_str = ("Epoch %d [%.1fs + %.1fs]: test==[%.5f=%.5f + %.5f + %.5f], recall=[%s], "
+                            "hr=[%s], ndcg=[%s]\n") % (
+                    epoch, t2 - t1, t3 - t2, loss_test, mf_loss_test, emb_loss_test, reg_loss_test,
+                    ", ".join("%.5f" % r for r in ret["recall"]),
+                    ", ".join("%.5f" % r for r in ret["hr"]),
+                    ", ".join("%.5f" % r for r in ret["ndcg"]))
+                print(perf_str, end="")
+                logging.info(perf_str)
+        elif args.test == "rubiboth":
+            print("Epoch %d" % epoch)
+            c = args.c
+            model.update_c(sess, c)
+            ret = evaluator.test(sess, model, users_to_test, method=args.test)
+            if args.verbose > 0:
+                perf_str += "c:%.2f recall=[%.5f, %.5f], hit=[%.5f, %.5f], ndcg=[%.5f, %.5f]\n" % (
+                    c, ret["recall"][0], ret["recall"][-1], ret["hr"][0], ret["hr"][-1],
+                    ret["ndcg"][0], ret["ndcg"][-1])
+            print(perf_str, end="")
+            logging.info(perf_str)
+        else:
+            raise SystemExit(f"--test {args.test}: only rubiboth / normal are implemented")
+
+        cur_best_pre_0, stopping_step, should_stop = early_stopping(
+            ret["hr"][0], cur_best_pre_0, stopping_step, expected_order="acc", flag_step=10)
+        if ret["hr"][0] == cur_best_pre_0:
+            best_epoch = epoch
+        if args.save_flag == 1:
+            checkpoint.save(weights_save_path + "/weights_{}-{}.npz".format(args.saveID, epoch), model,
+                            {"epoch": epoch})
+            print("save the weights in path: ", weights_save_path)
+        if should_stop and args.early_stop == 1:
+            if args.save_flag == 1:
+                with open(weights_save_path + "/best_epoch_{}.txt".format(args.saveID), "w") as f:
+                    f.write(str(config["best_c_epoch"] if args.test != "normal" else best_epoch))
+            break
+    model.close()
+    return {"best_epoch": best_epoch, "best_hr": cur_best_pre_0, "last": ret}
+
+
+if __name__ == "__main__":
+    main()

@@ -573,6 +573,7 @@ extern "C" int64_t macr_lgcn_trainer_steps_done(const macr_lgcn_trainer *h) {
 }
 extern "C" int macr_lgcn_trainer_set_steps_done(macr_lgcn_trainer *h, int64_t t) {
   MACR_CHECK_ARG(h && t >= 0, "macr_lgcn_trainer_set_steps_done: bad argument");
+  h->emb_dirty = true;  // checkpoint resume: the caller has just overwritten the tables
   return h->set_steps(t);
 }
 extern "C" int macr_lgcn_trainer_destroy(macr_lgcn_trainer *h) {

@@ -1,0 +1,180 @@
+"""Evaluation drivers: full-catalogue counterfactual score -> train-item mask -> top-K -> metrics.
+
+  MFEvaluator.test        macr_mf/train.py:162-311 (`test`) with `test_one_user` (:119-138),
+                          `ranklist_by_sorted` (:89-104) and `get_performance` (:106-117)
+  LGCNEvaluator.test      macr_lightgcn/utility/batch_test.py:26-162
+  eval_score_matrix_foldout
+                          macr_lightgcn/evaluator/cpp/evaluate_foldout.py:12-18 (drop-in)
+
+Default (`eval_mode="fused"`): the [B_u, I] score matrix never exists -- one fused kernel
+scores, masks and keeps K ids per user, and only those ids (MF) or the [T, 5K] metric curves
+(LightGCN) come back to the host.  `eval_mode="matrix"` runs the literal sequence of the
+reference (fetch `rubi_ratings_both`, mask, rank) through the same C ABI and exists to show the
+two agree.  The O(B*I) Python side loops of the reference that compute values nobody reads
+(train.py:261-277, batch_test.py:94-115 incl. the `Lightgcn_macr.txt` dump) are not reproduced.
+"""
+import numpy as np
+import torch
+
+from .. import ops
+from .data_mf import lists_to_csr
+
+_FETCH_OF = {"rubi_both": "rubi_ratings_both", "rubiboth": "rubi_ratings_both", "o": "batch_ratings",
+             "normal": "batch_ratings"}
+
+
+def _batches(seq, size):
+    # the reference walks n // size + 1 batches (the last one may be empty); empty ones are skipped
+    for s in range(0, len(seq), size):
+        yield seq[s:s + size]
+
+
+# ------------------------------------------------------------------------------------------------
+# MF: precision / recall / ndcg / hit_ratio @Ks in float64 (train.py:32-117)
+# ------------------------------------------------------------------------------------------------
+def mf_metrics_from_hits(hits, n_pos, Ks):
+    """hits [T, Kmax] 0/1 in rank order, n_pos [T] = len(user_pos_test) -> dict of sums over users
+    of the per-user metrics (train.py:106-117; dcg at :44-57, ndcg_at_k method 1 at :60-75)."""
+    hits = np.asarray(hits, dtype=np.float64)
+    n_pos = np.asarray(n_pos, dtype=np.float64)
+    out = {k: np.zeros(len(Ks)) for k in ("precision", "recall", "ndcg", "hit_ratio")}
+    Kmax = hits.shape[1]
+    discount = 1.0 / np.log2(np.arange(2, Kmax + 2))
+    for j, K in enumerate(Ks):
+        h = hits[:, :K]
+        got = h.sum(1)
+        out["precision"][j] = np.sum(got / K)
+        out["recall"][j] = np.sum(got / n_pos)
+        dcg = (h * discount[:K]).sum(1)
+        ideal = np.minimum(n_pos, K).astype(np.int64)
+        idcg = np.concatenate([[0.0], np.cumsum(discount[:K])])[ideal]
+        out["ndcg"][j] = np.sum(np.where(idcg > 0, dcg / np.where(idcg > 0, idcg, 1.0), 0.0))
+        out["hit_ratio"][j] = np.sum(got > 0)
+    return out
+
+
+def _hits(topk_ids, truth_lists):
+    ids = np.asarray(topk_ids)
+    out = np.zeros(ids.shape, np.float64)
+    for t, pos in enumerate(truth_lists):
+        out[t] = np.isin(ids[t], pos)
+    return out
+
+
+class MFEvaluator:
+    def __init__(self, data, Ks, batch_size, eval_mode="fused"):
+        self.data, self.Ks, self.batch_size, self.eval_mode = data, list(Ks), batch_size, eval_mode
+
+    def test(self, sess, model, test_users, batch_test_flag=False, model_type="o", valid_set="test"):
+        if model_type not in _FETCH_OF:
+            raise NotImplementedError(f"model_type {model_type!r} is outside the MACR hot path")
+        Kmax = max(self.Ks)
+        truth_of = self.data.test_user_list if valid_set == "test" else self.data.valid_user_list
+        sums = {k: np.zeros(len(self.Ks)) for k in ("precision", "recall", "ndcg", "hit_ratio")}
+        n_test_users, count = len(test_users), 0
+        gated = _FETCH_OF[model_type] == "rubi_ratings_both"
+        for user_batch in _batches(test_users, self.batch_size):
+            mrp, mcol = self.data.train_csr(user_batch)  # all_items - train_items, train.py:132-133
+            if self.eval_mode == "fused":
+                if gated:
+                    ids, _ = model.topk(user_batch, Kmax, mrp, mcol)
+                else:
+                    ids, _ = _plain_topk(model, user_batch, Kmax, mrp, mcol)
+                ids = ids.cpu().numpy()
+            else:  # literal: fetch the matrix, mask, rank on the host (heapq.nlargest order)
+                rate = sess.run(getattr(model, _FETCH_OF[model_type]),
+                                {model.users: user_batch, model.pos_items: range(self.data.n_items)})
+                ids = host_topk(rate, mrp, mcol, Kmax)
+            truth = [truth_of[u] for u in user_batch]
+            part = mf_metrics_from_hits(_hits(ids, truth), [len(t) for t in truth], self.Ks)
+            for k in sums:
+                sums[k] += part[k]
+            count += len(user_batch)
+        assert count == n_test_users  # train.py:309
+        return {k: v / n_test_users for k, v in sums.items()}
+
+
+def _plain_topk(model, users, K, mrp, mcol):
+    """top-K of batch_ratings (no gates): same fused kernel with sig = 1, c = 0."""
+    Ut, It, _w, _wu = model._score_tables()
+    with torch.cuda.device(model.dev):
+        Uq = ops.gather_rows(Ut, model._ids(users))
+        si = torch.ones(It.shape[0], dtype=torch.float32, device=model.dev)
+        su = torch.ones(Uq.shape[0], dtype=torch.float32, device=model.dev)
+        mc = model._ids(mcol) if len(mcol) else torch.zeros(1, dtype=torch.int32, device=model.dev)
+        return ops.score_topk(Uq, It, si, su, 0.0, model._ids(mrp), mc, K)
+
+
+def host_topk(rate, mask_rowptr, mask_col, K):
+    """Rank a host score matrix: masked items removed, score descending, lower id first."""
+    rate = np.array(rate, dtype=np.float32, copy=True)
+    T, n = rate.shape
+    out = np.full((T, K), -1, np.int32)
+    for t in range(T):
+        row = rate[t]
+        row[mask_col[mask_rowptr[t]:mask_rowptr[t + 1]]] = -np.inf
+        order = np.lexsort((np.arange(n), -row))[:K]
+        order = order[~np.isneginf(row[order])]  # fewer than K unmasked items: pad with -1
+        out[t, :len(order)] = order
+    return out
+
+
+# ------------------------------------------------------------------------------------------------
+# LightGCN: fold-out metric curves (evaluate_foldout.h:16-195) + the hr rewrite of batch_test.py
+# ------------------------------------------------------------------------------------------------
+class LGCNEvaluator:
+    def __init__(self, data, batch_size, eval_mode="fused"):
+        self.data, self.batch_size, self.eval_mode = data, batch_size, eval_mode
+
+    def test(self, sess, model, users_to_test, drop_flag=False, train_set_flag=0, method="normal"):
+        if method not in _FETCH_OF:
+            raise NotImplementedError(f"method {method!r} is outside the MACR hot path")
+        top_show = np.sort(model.Ks)
+        max_top = int(max(top_show))
+        gated = _FETCH_OF[method] == "rubi_ratings_both"
+        all_result, count = [], 0
+        for user_batch in _batches(users_to_test, self.batch_size):
+            mrp, mcol = self.data.train_csr(user_batch) if train_set_flag == 0 else \
+                (np.zeros(len(user_batch) + 1, np.int32), np.zeros(0, np.int32))
+            trp, tcol = self.data.truth_csr(user_batch)
+            if self.eval_mode == "fused":
+                if gated:
+                    ids, _ = model.topk(user_batch, max_top, mrp, mcol)
+                else:
+                    ids, _ = _plain_topk(model, user_batch, max_top, mrp, mcol)
+                with torch.cuda.device(model.dev):
+                    res = ops.foldout_metrics(ids, model._ids(trp), model._ids(tcol)).cpu().numpy()
+            else:
+                rate = sess.run(getattr(model, _FETCH_OF[method]),
+                                {model.users: user_batch, model.pos_items: range(self.data.n_items)})
+                rate = np.array(rate, dtype=np.float32, copy=True)
+                for idx in range(len(user_batch)):  # batch_test.py:124-129
+                    rate[idx][mcol[mrp[idx]:mrp[idx + 1]]] = -np.inf
+                res = eval_score_matrix_foldout(rate, [self.data.test_set[u] for u in user_batch],
+                                                max_top, device=model.dev)
+            all_result.append(res)
+            count += len(res)
+        assert count == len(users_to_test)  # batch_test.py:139
+        all_result = np.concatenate(all_result, axis=0)
+        K = max_top
+        all_result[:, 2 * K:3 * K] = (all_result[:, K:2 * K] != 0).astype(np.float32)  # :143-149
+        final = np.mean(all_result, axis=0).reshape(5, K)[:, top_show - 1]            # :151-157
+        return {"hr": final[2].copy(), "recall": final[1].copy(), "ndcg": final[3].copy()}
+
+
+def eval_score_matrix_foldout(score_matrix, test_items, top_k=20, thread_num=None, device="cuda:0"):
+    """Drop-in for evaluator/cpp/evaluate_foldout.py:12-18: float32 [rows, 5*top_k] laid out
+    [precision | recall | ap | ndcg | mrr] x top_k.  `thread_num` is accepted and ignored (the
+    reference builds a 5 x cpu_count thread pool per call; here one kernel ranks every row).
+    Ties: lower item id first (std::partial_sort_copy leaves tie order unspecified)."""
+    if len(score_matrix) != len(test_items):
+        raise ValueError("The lengths of score_matrix and test_items are not equal.")
+    dev = torch.device(device)
+    with torch.cuda.device(dev):
+        scores = torch.as_tensor(np.ascontiguousarray(score_matrix, dtype=np.float32)).to(dev)
+        if scores.shape[0] == 0:
+            return np.zeros((0, 5 * top_k), np.float32)
+        rk = ops.topk_rows(scores, top_k)
+        trp, tcol = lists_to_csr(list(test_items), len(test_items), sort_unique=False)
+        tcol_d = torch.as_tensor(tcol if len(tcol) else np.zeros(1, np.int32)).to(dev)
+        return ops.foldout_metrics(rk, torch.as_tensor(trp).to(dev), tcol_d).cpu().numpy()

@@ -1,0 +1,112 @@
+"""`LightGCN` facade -- the attribute surface of macr_lightgcn/LightGCN.py:32-555 for
+`--alg_type lightgcn --loss bceboth --test rubiboth`.
+
+Fetching
+  [opt_two_bce_both, loss_two_bce_both, mf_loss_two_bce_both, emb_loss_two_bce_both,
+   reg_loss_two_bce_both]  -> one training step: L-layer CSR SpMM propagation, the B x B gated
+   BCE on the propagated rows with the L2 term on the raw rows, backward through the layer
+   stack, TF-faithful Adam (LightGCN.py:197-201,288-309,495-532); returns
+   (None, loss, mf_loss, emb_loss, [0.])                       (reg_loss is a constant, :530)
+  [loss_two_bce_both, mf_loss_two_bce_both, emb_loss_two_bce_both] -> the same losses without an
+   update (train_thread_test, LightGCN.py:616-647)
+  rubi_ratings_both / batch_ratings -> score matrix on the propagated tables (:166,509)
+"""
+import ast
+
+import numpy as np
+import torch
+
+from .. import ops
+from .model_mf import _ScoringMixin, init_weights
+from .session import Fetch, Placeholder, Unsupported
+
+_TRAIN = ("opt_two_bce_both", "loss_two_bce_both", "mf_loss_two_bce_both", "emb_loss_two_bce_both",
+          "reg_loss_two_bce_both")
+_UNSUPPORTED = (
+    "opt", "loss", "mf_loss", "emb_loss", "reg_loss", "opt_bce", "loss_bce", "mf_loss_bce",
+    "emb_loss_bce", "reg_loss_bce", "opt_two_bce1", "loss_two_bce1", "mf_loss_two_bce1",
+    "emb_loss_two_bce1", "reg_loss_two_bce1", "opt_two_bce2", "loss_two_bce2", "mf_loss_two_bce2",
+    "emb_loss_two_bce2", "reg_loss_two_bce2", "rubi_ratings1", "rubi_ratings2",
+    "batch_ratings_causal_c", "direct_minus_ratings_both",
+)
+
+
+class LightGCN(_ScoringMixin):
+    def __init__(self, data_config, pretrain_data=None, args=None, device=None):
+        if args is None:
+            raise ValueError("LightGCN(data_config, pretrain_data, args=...): pass the parsed flags "
+                             "(the reference reads a module-global `args`)")
+        if args.alg_type != "lightgcn":
+            raise NotImplementedError("only --alg_type lightgcn is on the MACR hot path")
+        self.model_type, self.adj_type, self.alg_type = "lightgcn", args.adj_type, args.alg_type
+        self.n_users, self.n_items = data_config["n_users"], data_config["n_items"]
+        self.lr, self.emb_dim, self.batch_size = args.lr, args.embed_size, args.batch_size
+        self.weight_size = list(ast.literal_eval(args.layer_size))
+        self.n_layers = len(self.weight_size)                      # LightGCN.py:49-50
+        self.regs = list(ast.literal_eval(args.regs))
+        self.decay = self.regs[0]                                  # :52
+        self.alpha, self.beta, self.c = args.alpha, args.beta, args.c
+        self.Ks = list(ast.literal_eval(args.Ks))                  # :57
+        self.verbose = args.verbose
+        self.rubi_c = 0.0
+        if self.emb_dim != ops.D:
+            raise ops.MacrError(f"--embed_size must be {ops.D} (got {self.emb_dim})")
+        dev_index = getattr(args, "device", 0) if device is None else device
+        self.dev = torch.device("cuda", dev_index) if isinstance(dev_index, int) else torch.device(dev_index)
+        A = data_config["norm_adj"].tocsr().astype(np.float32)     # scipy, :666-681
+        A.sort_indices()
+        if pretrain_data is not None:                              # --pretrain -1, :222-231
+            U = np.asarray(pretrain_data["user_embed"], np.float32)
+            I = np.asarray(pretrain_data["item_embed"], np.float32)
+            _, _, w, wu = init_weights(self.n_users, self.n_items, self.emb_dim,
+                                       getattr(args, "init_seed", 12345))
+        else:
+            U, I, w, wu = init_weights(self.n_users, self.n_items, self.emb_dim,
+                                       getattr(args, "init_seed", 12345), getattr(args, "init_npz", ""))
+        self.hp = ops.HParams.make(lr=self.lr, alpha=self.alpha, beta=self.beta, decay=self.decay,
+                                   batch_size=self.batch_size)
+        self.trainer = ops.LGCNTrainer(A.indptr.astype(np.int32), A.indices.astype(np.int32),
+                                       A.data.astype(np.float32), U, I, w, wu, self.n_layers, self.hp,
+                                       max_batch=min(max(self.batch_size, 1), 8192), device=self.dev)
+        for name in ("users", "pos_items", "neg_items", "node_dropout", "mess_dropout"):
+            setattr(self, name, Placeholder(self, name))
+        for name in _TRAIN + ("rubi_ratings_both", "batch_ratings"):
+            setattr(self, name, Fetch(self, name))
+        for name in _UNSUPPORTED:
+            setattr(self, name, Unsupported(self, name))
+
+    def _run(self, names, feeds):
+        if any(n in _TRAIN for n in names):
+            train = any(n.startswith("opt") for n in names)
+            loss, mf, emb = self.step(feeds["users"], feeds["pos_items"], feeds["neg_items"], train)
+            val = {"opt_two_bce_both": None, "loss_two_bce_both": loss, "mf_loss_two_bce_both": mf,
+                   "emb_loss_two_bce_both": emb, "reg_loss_two_bce_both": np.zeros(1, np.float32)}
+            return [val[n] for n in names]
+        return [self._run_scores(n, feeds) for n in names]
+
+    def step(self, users, pos_items, neg_items, train=True):
+        with torch.cuda.device(self.dev):
+            return self.trainer.step_host(users, pos_items, neg_items, train=train)
+
+    def _score_tables(self):
+        with torch.cuda.device(self.dev):
+            ue, ie = self.trainer.embeddings()  # propagated once per parameter version
+        t = self.trainer.tab
+        return ue, ie, t.w, t.wu
+
+    def state_dict(self):
+        sd = self.trainer.tab.state_dict()
+        sd["steps_done"] = np.int64(self.trainer.steps_done)
+        sd["rubi_c"] = np.float32(self.rubi_c)
+        return sd
+
+    def load_state_dict(self, sd):
+        t = self.trainer.tab
+        with torch.no_grad():
+            for k in ("U", "mU", "vU", "I", "mI", "vI", "w", "mw", "vw", "wu", "mwu", "vwu"):
+                getattr(t, k).copy_(torch.as_tensor(np.asarray(sd[k], np.float32)).reshape(getattr(t, k).shape))
+        self.trainer.set_steps_done(int(sd["steps_done"]))
+        self.rubi_c = float(sd.get("rubi_c", 0.0))
+
+    def close(self):
+        self.trainer.close()

@@ -1,0 +1,203 @@
+"""-m gpu: the host-side mirror of the reference interface (session facades, evaluators, CLI
+drivers, checkpoints) on the tiny data set of tests/golden, checked against the CPU oracle."""
+import os
+import random
+import types
+
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+GOLD = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+
+
+def mf_args(**kw):
+    from macr_b200.host import flags
+
+    argv = ["--data_path", GOLD + "/", "--dataset", "tiny", "--batch_size", "32", "--train", "rubibceboth",
+            "--test", "rubi", "--c", "2.0", "--alpha", "1e-2", "--beta", "1e-3", "--lr", "0.01",
+            "--save_flag", "0", "--verbose", "0"]
+    a = flags.parse_mf_args(argv)
+    for k, v in kw.items():
+        setattr(a, k, v)
+    return a
+
+
+def lgcn_args(**kw):
+    from macr_b200.host import flags
+
+    argv = ["--data_path", GOLD + "/", "--dataset", "tiny", "--batch_size", "32", "--layer_size", "[64,64]",
+            "--loss", "bceboth", "--test", "rubiboth", "--c", "2.0", "--alpha", "1e-2", "--beta", "1e-3",
+            "--lr", "0.01", "--Ks", "[5,20]", "--save_flag", "0", "--verbose", "0"]
+    a = flags.parse_lgcn_args(argv)
+    for k, v in kw.items():
+        setattr(a, k, v)
+    return a
+
+
+def test_mf_facade_steps_scores_and_eval_match_oracle(oracle):
+    from macr_b200.host.data_mf import Data
+    from macr_b200.host.evaluate import MFEvaluator
+    from macr_b200.host.model_mf import BPRMF, init_weights
+    from macr_b200.host.session import Session
+    from oracle import mf_metrics
+
+    args = mf_args()
+    data = Data(args)
+    model = BPRMF(args, {"n_users": data.n_users, "n_items": data.n_items})
+    sess = Session()
+    U, I, w, wu = init_weights(data.n_users, data.n_items, 64, args.init_seed)
+    U, I = U * 8, I * 8  # non-degenerate scores
+    model.load_state_dict({**{k: np.zeros_like(v) for k, v in model.state_dict().items() if k[0] in "mv"},
+                           "U": U, "I": I, "w": w, "wu": wu, "steps_done": 0})
+    st = oracle.MFState(U, I, w, wu)
+    hp = oracle.HParams.make(lr=args.lr, alpha=args.alpha, beta=args.beta, decay=args.regs,
+                             batch_size=args.batch_size)
+    random.seed(12345)
+    for _ in range(5):
+        users, pos, neg = data.sample()
+        got = sess.run([model.opt_two_bce_both, model.loss_two_bce_both, model.mf_loss_two_bce_both,
+                        model.reg_loss_two_bce_both],
+                       feed_dict={model.users: users, model.pos_items: pos, model.neg_items: neg})
+        want = oracle.mf_step(st, users, pos, neg, hp)
+        assert got[0] is None
+        np.testing.assert_allclose(got[1:], want[:3], rtol=1e-4, atol=1e-4)
+    # the literal rubi_ratings_both fetch
+    model.update_c(sess, args.c)
+    test_users = list(data.test_user_list.keys())
+    M = sess.run(model.rubi_ratings_both, {model.users: test_users[:10], model.pos_items: list(range(data.n_items))})
+    assert M.shape == (10, data.n_items) and M.dtype == np.float32
+    Uq = np.ascontiguousarray(st.U[test_users[:10]])
+    want_M = oracle.score_matrix(Uq, st.I, oracle.score_gates(st.I, st.w), oracle.score_gates(Uq, st.wu), args.c)
+    np.testing.assert_allclose(M, want_M, rtol=1e-4, atol=1e-5)
+    B0 = sess.run(model.batch_ratings, {model.users: test_users[:10], model.pos_items: range(data.n_items)})
+    np.testing.assert_allclose(B0, Uq @ st.I.T, rtol=1e-4, atol=1e-5)
+    # evaluation: fused == literal matrix path == oracle ranking + reference metric arithmetic
+    Ks = [5, 20]
+    fused = MFEvaluator(data, Ks, 32, "fused").test(sess, model, test_users, model_type="rubi_both")
+    literal = MFEvaluator(data, Ks, 32, "matrix").test(sess, model, test_users, model_type="rubi_both")
+    t = model.trainer.tab
+    Ud, Id, wd, wud = (x.cpu().numpy() for x in (t.U, t.I, t.w, t.wu))
+    Uq = np.ascontiguousarray(Ud[test_users])
+    mrp, mcol = data.train_csr(test_users)
+    ids, _ = oracle.score_topk(Uq, Id, oracle.score_gates(Id, wd), oracle.score_gates(Uq, wud), args.c,
+                               mrp, mcol, 20)
+    want = mf_metrics.evaluate(ids, [data.test_user_list[u] for u in test_users], Ks)
+    for k in want:
+        np.testing.assert_allclose(fused[k], want[k], rtol=1e-9, atol=1e-12, err_msg=k)
+        np.testing.assert_allclose(literal[k], want[k], rtol=1e-9, atol=1e-12, err_msg=k)
+    model.close()
+
+
+def test_mf_checkpoint_resume_is_bit_exact(tmp_path):
+    from macr_b200.host import checkpoint
+    from macr_b200.host.data_mf import Data
+    from macr_b200.host.model_mf import BPRMF
+
+    args = mf_args()
+    data = Data(args)
+    cfg = {"n_users": data.n_users, "n_items": data.n_items}
+
+    def steps(model, n):
+        out = []
+        for _ in range(n):
+            out.append(model.train_step(*data.sample()))
+        return out
+
+    random.seed(7)
+    a = BPRMF(args, cfg)
+    steps(a, 3)
+    path = str(tmp_path / "ck.npz")
+    checkpoint.save(path, a)
+    tail_a = steps(a, 3)
+    b = BPRMF(args, cfg)
+    random.seed(123)  # wrong stream on purpose: load() restores it
+    checkpoint.load(path, b)
+    tail_b = steps(b, 3)
+    assert tail_a == tail_b
+    np.testing.assert_array_equal(a.trainer.tab.U.cpu().numpy(), b.trainer.tab.U.cpu().numpy())
+    np.testing.assert_array_equal(a.trainer.tab.vI.cpu().numpy(), b.trainer.tab.vI.cpu().numpy())
+    a.close()
+    b.close()
+
+
+def test_lgcn_facade_and_evaluator_match_oracle(oracle):
+    from macr_b200.host.data_lgcn import Data
+    from macr_b200.host.evaluate import LGCNEvaluator
+    from macr_b200.host.model_lgcn import LightGCN
+    from macr_b200.host.session import Session
+    from helpers import lists_to_csr
+
+    args = lgcn_args()
+    data = Data(GOLD + "/tiny", args.batch_size, args)
+    _, _, _, pre = data.get_adj_mat()
+    model = LightGCN({"n_users": data.n_users, "n_items": data.n_items, "norm_adj": pre}, None, args=args)
+    sess = Session()
+    sd = model.state_dict()
+    st = oracle.MFState(sd["U"], sd["I"], sd["w"], sd["wu"])
+    rowptr, col, val = data.adj_csr("pre")
+    hp = oracle.HParams.make(lr=args.lr, alpha=args.alpha, beta=args.beta, decay=1e-5, batch_size=args.batch_size)
+    random.seed(12345)
+    np.random.seed(12345)
+    feed = lambda t: {model.users: t[0], model.pos_items: t[1], model.neg_items: t[2],
+                      model.node_dropout: [0.1], model.mess_dropout: [0.1]}
+    for _ in range(4):
+        tr = data.sample()
+        lo_eval = oracle.lgcn_step(st, rowptr, col, val, 2, *tr, hp, train=False)
+        got_eval = sess.run([model.loss_two_bce_both, model.mf_loss_two_bce_both, model.emb_loss_two_bce_both], feed(tr))
+        np.testing.assert_allclose(got_eval, lo_eval[:3], rtol=1e-4, atol=1e-4)
+        lo = oracle.lgcn_step(st, rowptr, col, val, 2, *tr, hp, train=True)
+        got = sess.run([model.opt_two_bce_both, model.loss_two_bce_both, model.mf_loss_two_bce_both,
+                        model.emb_loss_two_bce_both, model.reg_loss_two_bce_both], feed(tr))
+        np.testing.assert_allclose(got[1:4], lo[:3], rtol=1e-4, atol=1e-4)
+        assert got[0] is None and np.array_equal(got[4], [0.0])
+    model.update_c(sess, args.c)
+    users = list(data.test_set.keys())
+    fused = LGCNEvaluator(data, 32, "fused").test(sess, model, users, method="rubiboth")
+    literal = LGCNEvaluator(data, 32, "matrix").test(sess, model, users, method="rubiboth")
+    # oracle route: propagate -> score -> -inf mask -> top-K -> foldout curves -> hr rewrite
+    E = oracle.lgcn_propagate(rowptr, col, val, st.U, st.I, 2)
+    Ue, Ie = E[:data.n_users], np.ascontiguousarray(E[data.n_users:])
+    Uq = np.ascontiguousarray(Ue[users])
+    mrp, mcol = data.train_csr(users)
+    ids, _ = oracle.score_topk(Uq, Ie, oracle.score_gates(Ie, st.w), oracle.score_gates(Uq, st.wu), args.c,
+                               mrp, mcol, 20)
+    trp, tcol = lists_to_csr([data.test_set[u] for u in users])
+    res = oracle.foldout_metrics(ids, trp, tcol)
+    res[:, 40:60] = (res[:, 20:40] != 0)
+    final = res.mean(0).reshape(5, 20)[:, np.array([5, 20]) - 1]
+    for key, row in (("hr", 2), ("recall", 1), ("ndcg", 3)):
+        np.testing.assert_allclose(fused[key], final[row], rtol=1e-5, atol=1e-6, err_msg=key)
+        np.testing.assert_allclose(literal[key], final[row], rtol=1e-5, atol=1e-6, err_msg=key)
+    model.close()
+
+
+def test_eval_score_matrix_foldout_drop_in_matches_reference_golden():
+    from macr_b200.host.evaluate import eval_score_matrix_foldout
+
+    g = np.load(os.path.join(GOLD, "ref_evaluator.npz"))
+    off = np.concatenate([[0], np.cumsum(g["truth_len"])])
+    truth = [g["truth"][off[i]:off[i + 1]].tolist() for i in range(len(g["truth_len"]))]
+    got = eval_score_matrix_foldout(g["scores"], truth, top_k=20, thread_num=8)
+    np.testing.assert_array_equal(got, g["results"])  # the reference's own C++ output, bit for bit
+    with pytest.raises(ValueError):
+        eval_score_matrix_foldout(g["scores"], truth[:-1])
+
+
+def test_cli_drivers_run_end_to_end(tmp_path, monkeypatch, capsys):
+    from macr_b200.cli import lightgcn, train_mf
+
+    monkeypatch.chdir(tmp_path)
+    cfg = train_mf.main(["--data_path", GOLD + "/", "--dataset", "tiny", "--batch_size", "32", "--epoch", "4",
+                         "--log_interval", "2", "--train", "rubibceboth", "--test", "rubi", "--c", "2",
+                         "--lr", "0.01", "--saveID", "t"])
+    out = capsys.readouterr().out
+    assert "c:2.00 [" in out and "hit=[" in out and "Epoch 0 [" in out
+    assert os.path.exists("mf_tiny_checkpoint/wd_1e-05_lr_0.01_t/3_ckpt.npz")
+    assert 0 <= cfg["best_hr"] <= 1
+    res = lightgcn.main(["--data_path", GOLD + "/", "--dataset", "tiny", "--batch_size", "32", "--epoch", "2",
+                         "--log_interval", "1", "--layer_size", "[64,64]", "--Ks", "[20]", "--loss", "bceboth",
+                         "--test", "rubiboth", "--c", "2", "--lr", "0.001", "--weights_path", str(tmp_path) + "/"])
+    out = capsys.readouterr().out
+    assert "c:2.00 recall=[" in out and "use the pre adjcency matrix" in out
+    assert res["last"] is not None and 0 <= res["best_hr"] <= 1
