@@ -337,29 +337,23 @@ def main():
     scoring = None
     if not args.no_scoring:
         T_q = N_TEST_USERS
-        bounds = np.linspace(0, N_ITEMS, world + 1).astype(np.int64)
-        lo, hi = int(bounds[rank]), int(bounds[rank + 1])
         Us, Is, ws_, wus = synth_model(777)  # same model on every rank
         Us *= 10
         Is *= 10
+        from macr_b200.host.dist import ShardedScorer
+
         dU = torch.from_numpy(Us).to(dev)
-        dIt = torch.from_numpy(np.ascontiguousarray(Is[lo:hi])).to(dev)
         q = torch.from_numpy(np.random.RandomState(5).permutation(N_USERS)[:T_q].astype(np.int32)).to(dev)
         mrp, mcol = synth_mask(9, T_q, 27)
         dmrp, dmcol = torch.from_numpy(mrp).to(dev), torch.from_numpy(mcol).to(dev)
         dw, dwu = torch.from_numpy(ws_).to(dev), torch.from_numpy(wus).to(dev)
+        # item table row-partitioned across the ranks (each rank keeps only its shard + its gates)
+        scorer = ShardedScorer(torch.from_numpy(Is).to(dev), dw, rank=rank, world=world)
 
         def score_once():
             Uq = ops.gather_rows(dU, q)
-            si, su = ops.score_gates(dIt, dw), ops.score_gates(Uq, dwu)
-            ids, sc = ops.score_topk(Uq, dIt, si, su, 40.0, dmrp, dmcol, TOPK, item_id_offset=lo)
-            if world > 1:
-                gi = torch.empty((world,) + ids.shape, dtype=ids.dtype, device=dev)
-                gs = torch.empty((world,) + sc.shape, dtype=sc.dtype, device=dev)
-                dist.all_gather_into_tensor(gi, ids)
-                dist.all_gather_into_tensor(gs, sc)
-                ids, sc = ops.topk_merge(gi, gs)
-            return ids, sc
+            su = ops.score_gates(Uq, dwu)
+            return scorer.topk(Uq, su, 40.0, dmrp, dmcol, TOPK)
 
         for _ in range(3):
             score_once()

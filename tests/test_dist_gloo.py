@@ -1,0 +1,73 @@
+"""world_size-2 gloo test (CPU) of the multi-GPU scoring plumbing: shard bounds, id offsets, the
+all-gather layout [G][T][K], and that shard-then-merge equals the unsharded ranking.  The
+per-shard scoring and the merge are done by the CPU oracle here (the checker); on the GPU the
+same plumbing feeds macr_score_topk / macr_topk_merge (tests/test_gpu_kernels.py,
+bench.py --gpus N)."""
+import os
+import socket
+
+import numpy as np
+import pytest
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+from helpers import lists_to_csr, make_interactions, make_model
+
+
+def _free_port():
+    with socket.socket() as s:
+        s.bind(("127.0.0.1", 0))
+        return s.getsockname()[1]
+
+
+def _worker(rank, world, port, out_dir):
+    import oracle
+    from macr_b200.host import dist as mdist
+
+    os.environ["MASTER_ADDR"], os.environ["MASTER_PORT"] = "127.0.0.1", str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        n_users, n_items, T, K = 120, 1001, 64, 20
+        U, I, w, wu = make_model(3, n_users, n_items, scale=8.0)
+        q = np.random.RandomState(4).permutation(n_users)[:T]
+        Uq = np.ascontiguousarray(U[q])
+        lists = make_interactions(5, T, n_items, 25)
+        mrp, mcol = lists_to_csr(lists)
+        sig_u = oracle.score_gates(Uq, wu)
+        b = mdist.item_shard_bounds(n_items, world)
+        assert b[0] == 0 and b[-1] == n_items and np.all(np.diff(b) > 0)
+        lo, hi = int(b[rank]), int(b[rank + 1])
+        It = np.ascontiguousarray(I[lo:hi])
+        ids, sc = oracle.score_topk(Uq, It, oracle.score_gates(It, w), sig_u, 40.0, mrp, mcol, K,
+                                    item_id_offset=lo)
+        assert ids.min() >= lo and ids.max() < hi
+        gi, gs = mdist.all_gather_candidates(torch.from_numpy(ids), torch.from_numpy(sc))
+        assert gi.shape == (world, T, K)
+        np.testing.assert_array_equal(gi[rank].numpy(), ids)  # shard order = rank order
+        mi, ms = oracle.topk_merge(gi.numpy().copy(), gs.numpy().copy())
+        want_i, want_s = oracle.score_topk(Uq, I, oracle.score_gates(I, w), sig_u, 40.0, mrp, mcol, K)
+        np.testing.assert_array_equal(mi, want_i)
+        np.testing.assert_array_equal(ms, want_s)
+        # every rank ends with the same global list
+        chk = torch.tensor([int(mi.astype(np.int64).sum())])
+        both = [torch.zeros_like(chk) for _ in range(world)]
+        dist.all_gather(both, chk)
+        assert len({int(x) for x in both}) == 1
+        open(os.path.join(out_dir, f"ok{rank}"), "w").write("ok")
+    finally:
+        dist.destroy_process_group()
+
+
+def test_sharded_scoring_plumbing_world2(tmp_path, oracle):
+    world = 2
+    mp.spawn(_worker, args=(world, _free_port(), str(tmp_path)), nprocs=world, join=True)
+    assert all(os.path.exists(tmp_path / f"ok{r}") for r in range(world))
+
+
+def test_shard_bounds_cover_everything():
+    from macr_b200.host.dist import item_shard_bounds
+
+    for n, g in ((8790, 8), (40981, 8), (7, 8), (1_000_000, 4)):
+        b = item_shard_bounds(n, g)
+        assert b[0] == 0 and b[-1] == n and len(b) == g + 1 and np.all(np.diff(b) >= 0)
