@@ -1,0 +1,63 @@
+"""Developer check of the tcgen05 scoring path against the exact fp32 kernel (GPU box only)."""
+import sys, os, time
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import numpy as np
+import torch
+from macr_b200 import ops
+from macr_b200._lib import lib
+sys.path.insert(0, os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "tests"))
+from helpers import make_model, make_interactions, lists_to_csr
+
+
+def run(T_users, n_items, K, c, mask_deg, splits, scale=10.0, seed=0, time_it=False):
+    U, I, w, wu = make_model(seed, T_users, n_items, scale=scale)
+    lists = make_interactions(seed + 1, T_users, n_items, mask_deg) if mask_deg else None
+    dev = torch.device("cuda")
+    dU, dI = torch.from_numpy(U).to(dev), torch.from_numpy(I).to(dev)
+    si, su = ops.score_gates(dI, torch.from_numpy(w).to(dev)), ops.score_gates(dU, torch.from_numpy(wu).to(dev))
+    mrp = mcol = None
+    if lists is not None:
+        a, b = lists_to_csr(lists)
+        mrp, mcol = torch.from_numpy(a).to(dev), torch.from_numpy(b).to(dev)
+    ei, es = ops.score_topk_exact(dU, dI, si, su, c, mrp, mcol, K)
+    lib().macr_score_tc_set_splits(*splits)
+    stats = torch.zeros(2, dtype=torch.int64, device=dev)
+    ti, ts = ops.score_topk_tc(dU, dI, si, su, c, mrp, mcol, K, stats=stats)
+    torch.cuda.synchronize()
+    bad_rows = int((ti != ei).any(dim=1).sum().item())
+    bad_sc = int((ts != es).any(dim=1).sum().item())
+    st = stats.cpu().tolist()
+    print(f"T={T_users} I={n_items} K={K} c={c} mask={mask_deg} splits={splits}: id-mismatch rows {bad_rows}, "
+          f"score-mismatch rows {bad_sc}, fallback rows {st[0]}, candidates/row {st[1] / max(1, T_users - st[0]):.1f}",
+          flush=True)
+    if bad_rows:
+        r = int((ti != ei).any(dim=1).nonzero()[0].item())
+        print(" first bad row", r, "\n  tc   ", ti[r].tolist(), "\n  exact", ei[r].tolist())
+        print("  tc sc", ts[r].tolist()[:6], "\n  ex sc", es[r].tolist()[:6])
+    if time_it:
+        for fn, name in ((lambda: ops.score_topk_tc(dU, dI, si, su, c, mrp, mcol, K), "tc"),
+                         (lambda: ops.score_topk_exact(dU, dI, si, su, c, mrp, mcol, K), "exact")):
+            for _ in range(2):
+                fn()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            for _ in range(5):
+                fn()
+            e1.record()
+            torch.cuda.synchronize()
+            ms = e0.elapsed_time(e1) / 5
+            print(f"   {name}: {ms:.3f} ms  {T_users * n_items / ms / 1e6:.1f} G scores/s", flush=True)
+    return bad_rows == 0 and bad_sc == 0
+
+
+if __name__ == "__main__":
+    ok = True
+    ok &= run(128, 5120, 20, 40.0, 0, (1, 1))
+    ok &= run(128, 5120, 20, 40.0, 0, (3, 3))
+    ok &= run(300, 6000, 20, 40.0, 30, (1, 3))
+    ok &= run(300, 6000, 20, 0.0, 30, (3, 3))
+    ok &= run(1000, 40981, 20, 40.0, 27, (1, 3))
+    ok &= run(15424, 40981, 20, 40.0, 27, (1, 3), time_it=True)
+    ok &= run(15424, 40981, 20, 40.0, 27, (1, 1), time_it=True)
+    ok &= run(15424, 40981, 20, 40.0, 27, (3, 3), time_it=True)
+    print("ALL OK" if ok else "FAILURES")

@@ -13,33 +13,12 @@
 #include <math.h>
 
 #include "common.cuh"
+#include "score.cuh"
 
 namespace macr {
 
 constexpr int kTU = 128, kTN = 128;
 constexpr int kMaxKFast = 32;
-
-__device__ __forceinline__ bool better(float sa, int ia, float sb, int ib) {
-  return sa > sb || (sa == sb && ia < ib);
-}
-
-// sorted-list insert, list held one rank per lane; (cs,cid) warp-uniform
-__device__ __forceinline__ void list_insert(float &ls, int &li, float cs, int cid, int lane,
-                                            unsigned kmask, int K) {
-  const unsigned bal = __ballot_sync(0xffffffffu, better(ls, li, cs, cid)) & kmask;
-  const int pos = __popc(bal);
-  const float us = __shfl_up_sync(0xffffffffu, ls, 1);
-  const int ui = __shfl_up_sync(0xffffffffu, li, 1);
-  if (pos < K) {
-    if (lane == pos) {
-      ls = cs;
-      li = cid;
-    } else if (lane > pos) {
-      ls = us;
-      li = ui;
-    }
-  }
-}
 
 __device__ __forceinline__ bool is_masked(const int32_t *__restrict__ mask_col, int lo, int hi,
                                           int gid) {
@@ -67,7 +46,13 @@ score_kernel(const float *__restrict__ Uq, int T, const float *__restrict__ It, 
              const float *__restrict__ sig_i, const float *__restrict__ sig_u, float c,
              const int32_t *__restrict__ mask_rowptr, const int32_t *__restrict__ mask_col, int K,
              int id_off, long long chunk_items, int32_t *__restrict__ part_ids,
-             float *__restrict__ part_scores, float *__restrict__ out_matrix) {
+             float *__restrict__ part_scores, float *__restrict__ out_matrix,
+             const int32_t *__restrict__ row_map, const int *__restrict__ n_rows_dev) {
+  // row_map != nullptr: slot t of this launch is query row row_map[t], and only the first
+  // *n_rows_dev slots exist (overflow queue of the tcgen05 path); outputs stay in slot order
+  const int Tpitch = T;  // partial lists keep the pitch of the full launch
+  if (row_map) T = min(T, *n_rows_dev);
+  if ((int)blockIdx.x * kTU >= T) return;
   extern __shared__ __align__(16) unsigned char smem_raw[];
   ScoreSmem &sm = *reinterpret_cast<ScoreSmem *>(smem_raw);
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -82,13 +67,14 @@ score_kernel(const float *__restrict__ Uq, int T, const float *__restrict__ It, 
     const int t = u0 + r;
     for (int kq = kq0; kq < kD / 4; kq += 2) {
       float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-      if (t < T) v = reinterpret_cast<const float4 *>(Uq + (long long)t * kD)[kq];
+      if (t < T) v = reinterpret_cast<const float4 *>(Uq + (long long)(row_map ? row_map[t] : t) * kD)[kq];
       sm.sU[4 * kq + 0][r] = v.x;
       sm.sU[4 * kq + 1][r] = v.y;
       sm.sU[4 * kq + 2][r] = v.z;
       sm.sU[4 * kq + 3][r] = v.w;
     }
-    if (tid < kTU) sm.sigU[tid] = (u0 + tid < T) ? sig_u[u0 + tid] : 0.f;
+    if (tid < kTU)
+      sm.sigU[tid] = (u0 + tid < T) ? sig_u[row_map ? row_map[u0 + tid] : u0 + tid] : 0.f;
   }
 
   // per-warp top-K lists for users warp*16 .. warp*16+15 (rank = lane)
@@ -102,8 +88,9 @@ score_kernel(const float *__restrict__ Uq, int T, const float *__restrict__ It, 
       ls[j] = -INFINITY;
       li[j] = 0x7fffffff;
       const int t = u0 + warp * 16 + j;
-      mlo[j] = (mask_rowptr && t < T) ? mask_rowptr[t] : 0;
-      mhi[j] = (mask_rowptr && t < T) ? mask_rowptr[t + 1] : 0;
+      const int tr = (row_map && t < T) ? row_map[t] : t;
+      mlo[j] = (mask_rowptr && t < T) ? mask_rowptr[tr] : 0;
+      mhi[j] = (mask_rowptr && t < T) ? mask_rowptr[tr + 1] : 0;
     }
   }
 
@@ -191,16 +178,16 @@ score_kernel(const float *__restrict__ Uq, int T, const float *__restrict__ It, 
         const int colm = lane + 32 * e;
         const float s = sm.sS[ur][colm];
         const int gid = id_off + (int)(it0 + colm);
-        const bool pass = (it0 + colm < i_end) && better(s, gid, ws, wi);
+        const bool pass = (it0 + colm < i_end) && score_better(s, gid, ws, wi);
         unsigned m = __ballot_sync(0xffffffffu, pass);
         while (m) {
           const int src = __ffs(m) - 1;
           m &= m - 1;
           const float cs = __shfl_sync(0xffffffffu, s, src);
           const int cid = id_off + (int)(it0 + src + 32 * e);
-          if (!better(cs, cid, ws, wi)) continue;
+          if (!score_better(cs, cid, ws, wi)) continue;
           if (is_masked(mask_col, mlo[j], mhi[j], cid)) continue;
-          list_insert(ls[j], li[j], cs, cid, lane, kmask, K);
+          score_list_insert(ls[j], li[j], cs, cid, lane, kmask, K);
           ws = __shfl_sync(0xffffffffu, ls[j], K - 1);
           wi = __shfl_sync(0xffffffffu, li[j], K - 1);
         }
@@ -213,7 +200,7 @@ score_kernel(const float *__restrict__ Uq, int T, const float *__restrict__ It, 
     for (int j = 0; j < 16; ++j) {
       const int t = u0 + warp * 16 + j;
       if (t < T && lane < K) {
-        const long long o = ((long long)blockIdx.y * T + t) * K + lane;
+        const long long o = ((long long)blockIdx.y * Tpitch + t) * K + lane;
         const bool empty = li[j] == 0x7fffffff;
         part_ids[o] = empty ? -1 : li[j];
         part_scores[o] = empty ? -INFINITY : ls[j];
@@ -225,10 +212,12 @@ score_kernel(const float *__restrict__ Uq, int T, const float *__restrict__ It, 
 // merge G sorted candidate lists per row -> top-K (score desc, lower id first); one warp per row
 __global__ void __launch_bounds__(256)
 topk_merge_kernel(const int32_t *__restrict__ ids, const float *__restrict__ scores, int T, int K,
-                  int G, int32_t *__restrict__ out_ids, float *__restrict__ out_scores) {
+                  int G, int32_t *__restrict__ out_ids, float *__restrict__ out_scores,
+                  const int32_t *__restrict__ row_map, const int *__restrict__ n_rows_dev) {
   const int lane = threadIdx.x & 31;
   const int t = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
-  if (t >= T) return;
+  if (t >= T || (row_map && t >= *n_rows_dev)) return;
+  const int to = row_map ? row_map[t] : t;  // output row
   const unsigned kmask = (K >= 32) ? 0xffffffffu : ((1u << K) - 1u);
   float ls = -INFINITY;
   int li = 0x7fffffff;
@@ -242,14 +231,14 @@ topk_merge_kernel(const int32_t *__restrict__ ids, const float *__restrict__ sco
       if (cid < 0) break;  // lists are padded at the tail
       const float ws = __shfl_sync(0xffffffffu, ls, K - 1);
       const int wi = __shfl_sync(0xffffffffu, li, K - 1);
-      if (!better(cs, cid, ws, wi)) break;  // sorted input: the rest of this list loses too
-      list_insert(ls, li, cs, cid, lane, kmask, K);
+      if (!score_better(cs, cid, ws, wi)) break;  // sorted input: the rest of this list loses too
+      score_list_insert(ls, li, cs, cid, lane, kmask, K);
     }
   }
   if (lane < K) {
     const bool empty = li == 0x7fffffff;
-    out_ids[(long long)t * K + lane] = empty ? -1 : li;
-    out_scores[(long long)t * K + lane] = empty ? -INFINITY : ls;
+    out_ids[(long long)to * K + lane] = empty ? -1 : li;
+    out_scores[(long long)to * K + lane] = empty ? -INFINITY : ls;
   }
 }
 
@@ -269,14 +258,14 @@ topk_rows_kernel(const float *__restrict__ scores, int cols, int rows, int K,
   for (int c0 = 0; c0 < cols; c0 += 32) {
     const int cidx = c0 + lane;
     const float s = cidx < cols ? row[cidx] : -INFINITY;
-    unsigned m = __ballot_sync(0xffffffffu, cidx < cols && better(s, cidx, ws, wi));
+    unsigned m = __ballot_sync(0xffffffffu, cidx < cols && score_better(s, cidx, ws, wi));
     while (m) {
       const int src = __ffs(m) - 1;
       m &= m - 1;
       const float cs = __shfl_sync(0xffffffffu, s, src);
       const int cid = c0 + src;
-      if (!better(cs, cid, ws, wi)) continue;
-      list_insert(ls, li, cs, cid, lane, kmask, K);
+      if (!score_better(cs, cid, ws, wi)) continue;
+      score_list_insert(ls, li, cs, cid, lane, kmask, K);
       ws = __shfl_sync(0xffffffffu, ls, K - 1);
       wi = __shfl_sync(0xffffffffu, li, K - 1);
     }
@@ -399,12 +388,48 @@ extern "C" int macr_score_topk(const float *Uq, int T, const float *It, int64_t 
   dim3 grid((T + kTU - 1) / kTU, chunks);
   score_kernel<true><<<grid, 256, sizeof(ScoreSmem), s>>>(Uq, T, It, n_items, sig_i, sig_u, c,
                                                           mask_rowptr, mask_col, K, item_id_offset,
-                                                          chunk_items, pids, psc, nullptr);
+                                                          chunk_items, pids, psc, nullptr,
+                                                          nullptr, nullptr);
   MACR_LAUNCH_CHECK();
-  topk_merge_kernel<<<(T + 7) / 8, 256, 0, s>>>(pids, psc, T, K, chunks, out_ids, out_scores);
+  topk_merge_kernel<<<(T + 7) / 8, 256, 0, s>>>(pids, psc, T, K, chunks, out_ids, out_scores,
+                                                nullptr, nullptr);
   MACR_LAUNCH_CHECK();
   return MACR_OK;
 }
+
+namespace macr {
+size_t score_exact_workspace_bytes(int T, long long n_items, int K) {
+  return macr_score_topk_workspace_bytes(T, n_items, K);
+}
+
+int score_exact_rows(const float *Uq, int T, const float *It, long long n_items,
+                     const float *sig_i, const float *sig_u, float c, const int32_t *mask_rowptr,
+                     const int32_t *mask_col, int K, int id_off, const int32_t *row_map,
+                     const int *n_rows_dev, int32_t *out_ids, float *out_scores, void *ws,
+                     size_t ws_bytes, cudaStream_t s) {
+  const size_t need = score_exact_workspace_bytes(T, n_items, K);
+  if (ws_bytes < need)
+    return fail(MACR_ERR_WORKSPACE, "score_exact_rows: workspace %zu < %zu bytes", ws_bytes, need);
+  int rc = score_smem_opt_in();
+  if (rc) return rc;
+  const int chunks = pick_chunks(T, n_items);
+  const long long itiles = (n_items + kTN - 1) / kTN;
+  const long long chunk_items = ((itiles + chunks - 1) / chunks) * kTN;
+  int32_t *pids = reinterpret_cast<int32_t *>(ws);
+  float *psc = reinterpret_cast<float *>(pids + (size_t)chunks * T * K);
+  dim3 grid((T + kTU - 1) / kTU, chunks);
+  // partial lists are indexed [chunk][slot][K] with the full-T pitch
+  score_kernel<true><<<grid, 256, sizeof(ScoreSmem), s>>>(Uq, T, It, n_items, sig_i, sig_u, c,
+                                                          mask_rowptr, mask_col, K, id_off,
+                                                          chunk_items, pids, psc, nullptr, row_map,
+                                                          n_rows_dev);
+  MACR_LAUNCH_CHECK();
+  topk_merge_kernel<<<(T + 7) / 8, 256, 0, s>>>(pids, psc, T, K, chunks, out_ids, out_scores,
+                                                row_map, n_rows_dev);
+  MACR_LAUNCH_CHECK();
+  return MACR_OK;
+}
+}  // namespace macr
 
 extern "C" int macr_score_matrix(const float *Uq, int T, const float *It, int64_t n_items, int d,
                                  const float *sig_i, const float *sig_u, float c, float *out,
@@ -421,7 +446,7 @@ extern "C" int macr_score_matrix(const float *Uq, int T, const float *It, int64_
   dim3 grid((T + kTU - 1) / kTU, chunks);
   score_kernel<false><<<grid, 256, sizeof(ScoreSmem), as_stream(stream)>>>(
       Uq, T, It, n_items, sig_i, sig_u, c, nullptr, nullptr, 1, 0, chunk_items, nullptr, nullptr,
-      out);
+      out, nullptr, nullptr);
   MACR_LAUNCH_CHECK();
   return MACR_OK;
 }
@@ -434,7 +459,7 @@ extern "C" int macr_topk_merge(const int32_t *ids, const float *scores, int T, i
   if (T == 0) return MACR_OK;
   MACR_CHECK_ARG(ids && scores && out_ids && out_scores, "macr_topk_merge: null pointer");
   topk_merge_kernel<<<(T + 7) / 8, 256, 0, as_stream(stream)>>>(ids, scores, T, K, G, out_ids,
-                                                                out_scores);
+                                                                out_scores, nullptr, nullptr);
   MACR_LAUNCH_CHECK();
   return MACR_OK;
 }

@@ -1,0 +1,880 @@
+// score_tc.cu -- K7+K8 on the 5th-generation tensor cores: TMA-fed tcgen05 (kind::tf32) tiles with
+// the accumulator in TMEM and the counterfactual correction ((y - c) * sig_i) fused into the
+// TMEM->register epilogue, followed by an EXACT fp32 re-rank, so the emitted ids and scores are
+// bit-identical to the fp32 path of score.cu (and to the CPU oracle).
+//   replaces sess.run(model.rubi_ratings_both, ...) + host top-K
+//   (macr_mf/train.py:249-251,89-104; macr_lightgcn/utility/batch_test.py:85-134; model.py:45,199).
+//
+// Why two tensor-core passes.  A running per-row top-K in the epilogue costs ~K(1+ln(n/K)) list
+// insertions per row, serialised across the 32 rows a warp owns: far more than the 4 instructions
+// per score of the pass itself.  Instead:
+//   pass MAX     per (row, 128-item tile): max over the unmasked items of the approximate score.
+//   threshold    thr[row] = K-th largest tile maximum - (eps_max + eps_filter + slack).  K tiles
+//                hold an unmasked item scoring >= the K-th largest tile maximum, so the exact K-th
+//                best score is >= thr + eps_filter: every item of the true top-K passes the filter.
+//   pass FILTER  same tiles again; append (score, id) of unmasked items with score >= thr to the
+//                (row, item-chunk) candidate list (a register counter per thread: no atomics).
+//                Expected K*(1+small) candidates per row.
+//   re-rank      one warp per row: exact fp32 FMA-chain score of every candidate (the arithmetic
+//                of score.cu), sorted insert (score desc, lower id first) -> out.
+//   fallback     a row whose candidate list overflowed (degenerate score distributions) is
+//                re-done by the exact fp32 kernel (score.cu) -- never silently wrong.
+// eps_* are rigorous bounds of |approximate - exact| (see row_threshold_kernel).  Operands are
+// split x = hi + lo (hi = tf32(x), lo = tf32(x - hi)); NSPLIT=3 accumulates hi*hi + hi*lo + lo*hi
+// (~fp32 accuracy), NSPLIT=1 only hi*hi.
+//
+// Kernel anatomy (one CTA per SM, persistent over (user tile, item chunk) work items):
+//   warp 0      TMA producer   cp.async.bulk.tensor.2d, 128B-swizzled K-major boxes of 128 rows x 32 fp32
+//   warp 1      MMA issuer     tcgen05.mma.cta_group::1.kind::tf32, M=128 N=128 K=8, D in TMEM
+//                              (2 accumulator buffers x 128 columns); also owns TMEM alloc/dealloc
+//   warps 2..5  epilogue       tcgen05.ld.32x32b.x32 (thread = user row), fused correction,
+//                              tile maximum / threshold filter, train-item mask from a per-row
+//                              cursor into the sorted CSR mask
+// mbarrier pipelines: user tile full/empty, item stages full/empty, TMEM full/empty.
+#include <cuda.h>
+#include <math.h>
+
+#include "common.cuh"
+#include "score.cuh"
+
+namespace macr {
+namespace tc {
+
+constexpr int BM = 128;              // user rows per tile (UMMA M, TMEM lanes)
+constexpr int BN = 128;              // items per tile (UMMA N, TMEM columns per buffer)
+constexpr int KB = 32;               // fp32 per 128-byte swizzle row
+constexpr int NKB = kD / KB;         // K blocks per operand tile (2)
+constexpr int KBLK_BYTES = BM * 128; // one K block of one operand tile: 128 rows x 128 B
+constexpr int OPER_BYTES = NKB * KBLK_BYTES;  // 32 KiB: a 128 x 64 fp32 operand tile
+constexpr int kCap = 64;             // candidate slots per (row, item chunk)
+constexpr int kThreads = 192;
+constexpr int kTmemCols = 256;
+constexpr int MODE_MAX = 0, MODE_FILTER = 1;
+
+template <int NSPLIT>
+struct Cfg {
+  static constexpr int PARTS = NSPLIT == 1 ? 1 : 2;             // hi (, lo)
+  static constexpr int STAGES = NSPLIT == 1 ? 4 : 2;            // item-tile ring
+  static constexpr int A_BYTES = PARTS * OPER_BYTES;
+  static constexpr int STAGE_BYTES = PARTS * OPER_BYTES;
+  static constexpr int SMEM_BYTES = 1024 /*align*/ + A_BYTES + STAGES * STAGE_BYTES + 2048;
+};
+
+// ---- PTX wrappers ----------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void *p) {
+  return (uint32_t)__cvta_generic_to_shared(p);
+}
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes)
+               : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+// spin on a phase parity; a 4 s watchdog turns a protocol bug into a trap instead of a hang
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+  uint32_t done = 0;
+  long long t0 = 0;
+  for (uint32_t it = 0;; ++it) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(done)
+        : "r"(bar), "r"(parity)
+        : "memory");
+    if (done) return;
+    if ((it & 0xfff) == 0xfff) {
+      const long long now = clock64();
+      if (t0 == 0) t0 = now;
+      else if (now - t0 > 8000000000LL) __trap();
+    }
+  }
+}
+__device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap *map, uint32_t bar,
+                                            int c0, int c1) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+      ::"r"(dst), "l"(reinterpret_cast<uint64_t>(map)), "r"(bar), "r"(c0), "r"(c1)
+      : "memory");
+}
+__device__ __forceinline__ void tc_fence_before() {
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+}
+__device__ __forceinline__ void tc_fence_after() {
+  asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+}
+__device__ __forceinline__ void tc_commit(uint32_t bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar)
+               : "memory");
+}
+// D[tmem] (+)= A[smem] * B[smem]^T, tf32 inputs, fp32 accumulate
+__device__ __forceinline__ void tc_mma_tf32(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc,
+                                            uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}"
+      ::"r"(d_tmem), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+// K-major, 128-byte swizzle: 8-row groups 1024 B apart (SBO), version 1 (sm_100), layout type 2
+__device__ __forceinline__ uint64_t umma_desc(uint32_t smem_addr) {
+  uint64_t d = 0;
+  d |= (uint64_t)((smem_addr >> 4) & 0x3FFF);
+  d |= (uint64_t)1 << 16;            // leading byte offset (ignored for swizzled K-major)
+  d |= (uint64_t)(1024 >> 4) << 32;  // stride byte offset
+  d |= (uint64_t)1 << 46;            // descriptor version
+  d |= (uint64_t)2 << 61;            // SWIZZLE_128B
+  return d;
+}
+// kind::tf32, fp32 accumulate, A and B K-major, M=128, N=128
+constexpr uint32_t kIdesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(BN >> 3) << 17) |
+                            ((uint32_t)(BM >> 4) << 24);
+
+#define MACR_R32(v)                                                                              \
+  "+r"(v[0]), "+r"(v[1]), "+r"(v[2]), "+r"(v[3]), "+r"(v[4]), "+r"(v[5]), "+r"(v[6]), "+r"(v[7]), \
+      "+r"(v[8]), "+r"(v[9]), "+r"(v[10]), "+r"(v[11]), "+r"(v[12]), "+r"(v[13]), "+r"(v[14]),    \
+      "+r"(v[15]), "+r"(v[16]), "+r"(v[17]), "+r"(v[18]), "+r"(v[19]), "+r"(v[20]), "+r"(v[21]),  \
+      "+r"(v[22]), "+r"(v[23]), "+r"(v[24]), "+r"(v[25]), "+r"(v[26]), "+r"(v[27]), "+r"(v[28]),  \
+      "+r"(v[29]), "+r"(v[30]), "+r"(v[31])
+#define MACR_W32(v)                                                                              \
+  "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), \
+      "=r"(v[8]), "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]),    \
+      "=r"(v[15]), "=r"(v[16]), "=r"(v[17]), "=r"(v[18]), "=r"(v[19]), "=r"(v[20]), "=r"(v[21]),  \
+      "=r"(v[22]), "=r"(v[23]), "=r"(v[24]), "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]),  \
+      "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
+
+// 32 consecutive accumulator columns of this thread's TMEM lane (= user row)
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&v)[32]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+      "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+      : MACR_W32(v)
+      : "r"(taddr)
+      : "memory");
+}
+// the registers are operands so no use of them can be scheduled above the wait
+__device__ __forceinline__ void tmem_ld_wait(uint32_t (&v)[32]) {
+  asm volatile("tcgen05.wait::ld.sync.aligned;" : MACR_R32(v)::"memory");
+}
+
+struct TileParams {
+  int T;            // query rows in this row block
+  int n_items;      // items in this shard
+  int n_utiles, n_itiles, n_chunks, tiles_per_chunk;
+  float c;
+  int id_off;       // global id of local item 0 (mask_col holds global ids)
+  int ld_tm;        // row pitch of tilemax
+};
+
+// ---------------------------------------------------------------------------------------------
+template <int MODE, int NSPLIT>
+__global__ void __launch_bounds__(kThreads, 1)
+score_tc_kernel(const __grid_constant__ CUtensorMap tmUhi, const __grid_constant__ CUtensorMap tmUlo,
+                const __grid_constant__ CUtensorMap tmIhi, const __grid_constant__ CUtensorMap tmIlo,
+                const TileParams P, const float *__restrict__ sig_i,
+                const int32_t *__restrict__ mask_rowptr, const int32_t *__restrict__ mask_col,
+                float *__restrict__ tilemax, const float *__restrict__ thr,
+                uint2 *__restrict__ cand, int *__restrict__ cand_cnt) {
+  using C = Cfg<NSPLIT>;
+  extern __shared__ unsigned char smem_raw[];
+  // 1024-byte alignment: the 128B swizzle pattern repeats every 8 rows x 128 B
+  unsigned char *smem = reinterpret_cast<unsigned char *>(
+      (reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  unsigned char *sA = smem;                 // [PARTS][NKB][128 x 128 B]
+  unsigned char *sB = smem + C::A_BYTES;    // [STAGES][PARTS][NKB][128 x 128 B]
+  unsigned char *tail = sB + C::STAGES * C::STAGE_BYTES;
+  uint64_t *bars = reinterpret_cast<uint64_t *>(tail);  // see indices below
+  float *sSig = reinterpret_cast<float *>(tail + 256);  // [2][BN]
+  uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(tail + 256 + 2 * BN * 4);
+
+  enum { A_FULL = 0, A_EMPTY = 1, TM_FULL = 2, TM_EMPTY = 4, B_FULL = 6, B_EMPTY = 6 + C::STAGES };
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const uint32_t bar0 = smem_u32(bars);
+  auto BAR = [&](int i) { return bar0 + 8u * (uint32_t)i; };
+
+  if (threadIdx.x == 0) {
+    mbar_init(BAR(A_FULL), 1);
+    mbar_init(BAR(A_EMPTY), 1);
+    for (int b = 0; b < 2; ++b) {
+      mbar_init(BAR(TM_FULL + b), 1);
+      mbar_init(BAR(TM_EMPTY + b), 4);  // one arrive per epilogue warp
+    }
+    for (int s = 0; s < C::STAGES; ++s) {
+      mbar_init(BAR(B_FULL + s), 1);
+      mbar_init(BAR(B_EMPTY + s), 1);
+    }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 1) {  // TMEM: 2 accumulator buffers of 128 columns
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(
+                     smem_u32(tmem_slot)),
+                 "r"(kTmemCols)
+                 : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+  const int n_work = P.n_utiles * P.n_chunks;
+
+  if (warp == 0) {
+    // =============================== TMA producer ===============================
+    if (lane == 0) {
+      const CUtensorMap *mapsU[2] = {&tmUhi, &tmUlo};
+      const CUtensorMap *mapsI[2] = {&tmIhi, &tmIlo};
+      int stage = 0;
+      uint32_t phase = 0, a_phase = 0;
+      for (int w = blockIdx.x; w < n_work; w += gridDim.x) {
+        const int ut = w / P.n_chunks, ch = w - ut * P.n_chunks;
+        const int t_begin = ch * P.tiles_per_chunk;
+        const int t_end = min(P.n_itiles, t_begin + P.tiles_per_chunk);
+        mbar_wait(BAR(A_EMPTY), a_phase ^ 1);
+        mbar_expect_tx(BAR(A_FULL), C::A_BYTES);
+        for (int p = 0; p < C::PARTS; ++p)
+          for (int kb = 0; kb < NKB; ++kb)
+            tma_load_2d(smem_u32(sA + (p * NKB + kb) * KBLK_BYTES), mapsU[p], BAR(A_FULL), kb * KB,
+                        ut * BM);
+        a_phase ^= 1;
+        for (int t = t_begin; t < t_end; ++t) {
+          mbar_wait(BAR(B_EMPTY + stage), phase ^ 1);
+          mbar_expect_tx(BAR(B_FULL + stage), C::STAGE_BYTES);
+          unsigned char *dst = sB + stage * C::STAGE_BYTES;
+          for (int p = 0; p < C::PARTS; ++p)
+            for (int kb = 0; kb < NKB; ++kb)
+              tma_load_2d(smem_u32(dst + (p * NKB + kb) * KBLK_BYTES), mapsI[p],
+                          BAR(B_FULL + stage), kb * KB, t * BN);
+          if (++stage == C::STAGES) {
+            stage = 0;
+            phase ^= 1;
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // =============================== MMA issuer ===============================
+    if (lane == 0) {
+      int stage = 0;
+      uint32_t phase = 0, a_phase = 0;
+      uint32_t n = 0;  // running tile counter -> TMEM buffer ring
+      const uint32_t a_addr = smem_u32(sA);
+      for (int w = blockIdx.x; w < n_work; w += gridDim.x) {
+        const int ut = w / P.n_chunks, ch = w - ut * P.n_chunks;
+        const int t_begin = ch * P.tiles_per_chunk;
+        const int t_end = min(P.n_itiles, t_begin + P.tiles_per_chunk);
+        mbar_wait(BAR(A_FULL), a_phase);
+        a_phase ^= 1;
+        for (int t = t_begin; t < t_end; ++t, ++n) {
+          const uint32_t buf = n & 1;
+          mbar_wait(BAR(TM_EMPTY + buf), ((n >> 1) & 1) ^ 1);
+          mbar_wait(BAR(B_FULL + stage), phase);
+          tc_fence_after();
+          const uint32_t b_addr = smem_u32(sB + stage * C::STAGE_BYTES);
+          const uint32_t d_tmem = tmem_base + buf * BN;
+          uint32_t acc = 0;
+          // (A part, B part): lo*hi, hi*lo, then hi*hi
+          constexpr int NP = NSPLIT == 1 ? 1 : 3;
+          const int pa[3] = {NSPLIT == 1 ? 0 : 1, 0, 0};
+          const int pb[3] = {0, 1, 0};
+#pragma unroll
+          for (int sp = 0; sp < NP; ++sp) {
+#pragma unroll
+            for (int kb = 0; kb < NKB; ++kb) {
+#pragma unroll
+              for (int ks = 0; ks < KB / 8; ++ks) {
+                const uint64_t ad =
+                    umma_desc(a_addr + (pa[sp] * NKB + kb) * KBLK_BYTES + ks * 32);
+                const uint64_t bd =
+                    umma_desc(b_addr + (pb[sp] * NKB + kb) * KBLK_BYTES + ks * 32);
+                tc_mma_tf32(d_tmem, ad, bd, kIdesc, acc);
+                acc = 1;
+              }
+            }
+          }
+          tc_commit(BAR(B_EMPTY + stage));   // item stage may be refilled
+          tc_commit(BAR(TM_FULL + buf));     // accumulator ready for the epilogue
+          if (t == t_end - 1) tc_commit(BAR(A_EMPTY));
+          if (++stage == C::STAGES) {
+            stage = 0;
+            phase ^= 1;
+          }
+        }
+      }
+    }
+  } else {
+    // =============================== epilogue (128 threads) ===============================
+    const int q = warp & 3;                 // TMEM lane quarter this warp may read
+    const int r_in = q * 32 + lane;         // row inside the user tile
+    const int te = threadIdx.x - 64;        // 0..127
+    uint32_t n = 0;
+    for (int w = blockIdx.x; w < n_work; w += gridDim.x) {
+      const int ut = w / P.n_chunks, ch = w - ut * P.n_chunks;
+      const int t_begin = ch * P.tiles_per_chunk;
+      const int t_end = min(P.n_itiles, t_begin + P.tiles_per_chunk);
+      const int row = ut * BM + r_in;
+      const bool valid = row < P.T;
+      // cursor into this row's sorted train-item list, positioned at the chunk's first item
+      int mptr = 0, mend = 0;
+      if (valid && mask_rowptr) {
+        mptr = mask_rowptr[row];
+        mend = mask_rowptr[row + 1];
+        const int first = P.id_off + t_begin * BN;
+        int lo = mptr, hi = mend;
+        while (lo < hi) {
+          const int mid = (lo + hi) >> 1;
+          if (mask_col[mid] < first) lo = mid + 1;
+          else hi = mid;
+        }
+        mptr = lo;
+      }
+      int nxt = mptr < mend ? mask_col[mptr] : 0x7fffffff;
+      int nxt2 = mptr + 1 < mend ? mask_col[mptr + 1] : 0x7fffffff;
+      float thr_r = INFINITY;
+      int cnt = 0;
+      uint2 *my_cand = nullptr;
+      if (MODE == MODE_FILTER && valid) {
+        thr_r = thr[row];
+        my_cand = cand + ((size_t)row * P.n_chunks + ch) * kCap;
+      }
+      // item gate of column te of the next tile (prefetched one tile ahead)
+      float sig_next = (t_begin * BN + te < P.n_items) ? sig_i[t_begin * BN + te] : 0.f;
+
+      for (int t = t_begin; t < t_end; ++t, ++n) {
+        const uint32_t buf = n & 1;
+        sSig[buf * BN + te] = sig_next;
+        if (t + 1 < t_end) {
+          const int cn = (t + 1) * BN + te;
+          sig_next = cn < P.n_items ? sig_i[cn] : 0.f;
+        }
+        asm volatile("bar.sync 1, 128;" ::: "memory");
+        // mask words of this tile: train items of the row + columns beyond the catalogue
+        uint32_t mw0 = 0, mw1 = 0, mw2 = 0, mw3 = 0;
+        {
+          const int g0 = P.id_off + t * BN, g1 = g0 + BN;
+          while (nxt < g1) {
+            const int b = nxt - g0;
+            if (b >= 0) {
+              const uint32_t bit = 1u << (b & 31);
+              const int ws = b >> 5;
+              mw0 |= ws == 0 ? bit : 0u;
+              mw1 |= ws == 1 ? bit : 0u;
+              mw2 |= ws == 2 ? bit : 0u;
+              mw3 |= ws == 3 ? bit : 0u;
+            }
+            nxt = nxt2;
+            ++mptr;
+            nxt2 = mptr + 1 < mend ? mask_col[mptr + 1] : 0x7fffffff;
+          }
+          const int nv = P.n_items - t * BN;  // valid columns of this tile
+          if (nv < BN) {
+            mw0 |= nv <= 0 ? 0xffffffffu : (nv < 32 ? ~((1u << nv) - 1u) : 0u);
+            mw1 |= nv <= 32 ? 0xffffffffu : (nv < 64 ? ~((1u << (nv - 32)) - 1u) : 0u);
+            mw2 |= nv <= 64 ? 0xffffffffu : (nv < 96 ? ~((1u << (nv - 64)) - 1u) : 0u);
+            mw3 |= nv <= 96 ? 0xffffffffu : ~((1u << (nv - 96)) - 1u);
+          }
+        }
+        mbar_wait(BAR(TM_FULL + buf), (n >> 1) & 1);
+        tc_fence_after();
+        const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + buf * BN;
+        const float *sg = sSig + buf * BN;
+        float m = -INFINITY;
+        uint32_t va[32], vb[32];
+
+        auto process = [&](uint32_t (&v)[32], int cb, uint32_t mw) {
+          const float4 *sg4 = reinterpret_cast<const float4 *>(sg + cb * 32);
+          if (MODE == MODE_MAX) {
+            if (__any_sync(0xffffffffu, mw != 0u)) {
+#pragma unroll
+              for (int j4 = 0; j4 < 8; ++j4) {
+                const float4 g = sg4[j4];
+                const float gg[4] = {g.x, g.y, g.z, g.w};
+#pragma unroll
+                for (int e = 0; e < 4; ++e) {
+                  const int j = j4 * 4 + e;
+                  float s = __fmul_rn(__fsub_rn(__uint_as_float(v[j]), P.c), gg[e]);
+                  s = ((mw >> j) & 1u) ? -INFINITY : s;
+                  m = fmaxf(m, s);
+                }
+              }
+            } else {
+#pragma unroll
+              for (int j4 = 0; j4 < 8; ++j4) {
+                const float4 g = sg4[j4];
+                const float gg[4] = {g.x, g.y, g.z, g.w};
+#pragma unroll
+                for (int e = 0; e < 4; ++e)
+                  m = fmaxf(m, __fmul_rn(__fsub_rn(__uint_as_float(v[j4 * 4 + e]), P.c), gg[e]));
+              }
+            }
+          } else {
+            const int gbase = P.id_off + t * BN + cb * 32;
+#pragma unroll
+            for (int j4 = 0; j4 < 8; ++j4) {
+              const float4 g = sg4[j4];
+              const float gg[4] = {g.x, g.y, g.z, g.w};
+#pragma unroll
+              for (int e = 0; e < 4; ++e) {
+                const int j = j4 * 4 + e;
+                const float s = __fmul_rn(__fsub_rn(__uint_as_float(v[j]), P.c), gg[e]);
+                if (s >= thr_r) {
+                  if (!((mw >> j) & 1u)) {
+                    if (cnt < kCap) my_cand[cnt] = make_uint2(__float_as_uint(s), (uint32_t)(gbase + j));
+                    ++cnt;
+                  }
+                }
+              }
+            }
+          }
+        };
+
+        __syncwarp();
+        tmem_ld32(taddr + 0, va);
+        tmem_ld_wait(va);
+        tmem_ld32(taddr + 32, vb);
+        process(va, 0, mw0);
+        tmem_ld_wait(vb);
+        tmem_ld32(taddr + 64, va);
+        process(vb, 1, mw1);
+        tmem_ld_wait(va);
+        tmem_ld32(taddr + 96, vb);
+        process(va, 2, mw2);
+        tmem_ld_wait(vb);
+        // all TMEM reads of this buffer are complete: hand it back to the MMA warp
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(BAR(TM_EMPTY + buf));
+        process(vb, 3, mw3);
+        if (MODE == MODE_MAX && valid) tilemax[(size_t)row * P.ld_tm + t] = m;
+      }
+      if (MODE == MODE_FILTER && valid) cand_cnt[(size_t)row * P.n_chunks + ch] = cnt;
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base),
+                 "r"(kTmemCols)
+                 : "memory");
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// operand preparation: hi = tf32(x) (round to nearest), lo = tf32(x - hi); row norm
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ float to_tf32(float x) {
+  uint32_t r;
+  asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(x));
+  return __uint_as_float(r);
+}
+
+// one half-warp per row (float4 per lane); norm_out[row] = ||row||_2 rounded up a little;
+// norm_max (nullable): max over rows via atomicMax on the bit pattern (non-negative floats)
+__global__ void __launch_bounds__(256)
+split_rows_kernel(const float *__restrict__ X, long long n, float *__restrict__ hi,
+                  float *__restrict__ lo, float *__restrict__ norm_out,
+                  unsigned int *__restrict__ norm_max) {
+  const long long r = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 4;
+  const int hl = threadIdx.x & 15;
+  float ss = 0.f;
+  if (r < n) {
+    const float4 v = reinterpret_cast<const float4 *>(X + r * kD)[hl];
+    float4 h, l;
+    h.x = to_tf32(v.x), h.y = to_tf32(v.y), h.z = to_tf32(v.z), h.w = to_tf32(v.w);
+    l.x = to_tf32(v.x - h.x), l.y = to_tf32(v.y - h.y), l.z = to_tf32(v.z - h.z),
+    l.w = to_tf32(v.w - h.w);
+    reinterpret_cast<float4 *>(hi + r * kD)[hl] = h;
+    reinterpret_cast<float4 *>(lo + r * kD)[hl] = l;
+    ss = v.x * v.x + v.y * v.y + v.z * v.z + v.w * v.w;
+  }
+#pragma unroll
+  for (int o = 8; o > 0; o >>= 1) ss += __shfl_xor_sync(0xffffffffu, ss, o);
+  if (r < n && hl == 0) {
+    const float nrm = sqrtf(ss) * 1.0001f;  // the sum of squares itself is rounded
+    if (norm_out) norm_out[r] = nrm;
+    if (norm_max) atomicMax(norm_max, __float_as_uint(nrm));
+  }
+}
+
+// thr[row] = (K-th largest tile maximum) - (eps_max + eps_filter + slack), one warp per row.
+// With y~ the tensor-core dot product and y the fp32 FMA chain:  |y~ - y| <= kappa * |u| * |i|
+//   kappa(NSPLIT=1) = 2^-9   (two tf32 roundings 2^-11 each, products exact, fp32 accumulation)
+//   kappa(NSPLIT=3) = 2^-15  (dropped lo*lo 2^-22, tf32 rounding of lo 2 x 2^-22, fp32 accumulation
+//                             of 192 products and of the 64-term reference chain ~2^-17)
+// and the two roundings of ((y - c) * sig_i) add at most 2^-22 * (|c| + |u||i|).
+__global__ void __launch_bounds__(256)
+row_threshold_kernel(const float *__restrict__ tilemax, int T, int n_itiles, int ld_tm, int K,
+                     const float *__restrict__ unorm, const unsigned int *__restrict__ inorm_max,
+                     float c, float kappa_sum, float *__restrict__ thr) {
+  const int lane = threadIdx.x & 31;
+  const int t = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (t >= T) return;
+  const unsigned kmask = (K >= 32) ? 0xffffffffu : ((1u << K) - 1u);
+  const float *row = tilemax + (size_t)t * ld_tm;
+  float ls = -INFINITY;
+  int li = 0x7fffffff;
+  float ws = -INFINITY;
+  int wi = 0x7fffffff;
+  for (int c0 = 0; c0 < n_itiles; c0 += 32) {
+    const int cidx = c0 + lane;
+    const float s = cidx < n_itiles ? row[cidx] : -INFINITY;
+    unsigned m = __ballot_sync(0xffffffffu, cidx < n_itiles && score_better(s, cidx, ws, wi));
+    while (m) {
+      const int src = __ffs(m) - 1;
+      m &= m - 1;
+      const float cs = __shfl_sync(0xffffffffu, s, src);
+      const int cid = c0 + src;
+      if (!score_better(cs, cid, ws, wi)) continue;
+      score_list_insert(ls, li, cs, cid, lane, kmask, K);
+      ws = __shfl_sync(0xffffffffu, ls, K - 1);
+      wi = __shfl_sync(0xffffffffu, li, K - 1);
+    }
+  }
+  if (lane == 0) {
+    float out = -INFINITY;
+    if (wi != 0x7fffffff && ws > -INFINITY) {
+      const float yb = unorm[t] * __uint_as_float(*inorm_max);
+      const float eps = kappa_sum * yb + 2.f * 4.76837158e-7f /*2^-21*/ * (fabsf(c) + yb);
+      out = ws - eps - 9.5367e-7f /*2^-20*/ * fabsf(ws);
+    }
+    thr[t] = out;
+  }
+}
+
+// exact re-rank of the candidates of one row (one warp per row); rows whose lists overflowed are
+// queued for the exact fp32 kernel instead
+__global__ void __launch_bounds__(256)
+rerank_kernel(const float *__restrict__ Uq, int T, const float *__restrict__ It,
+              const float *__restrict__ sig_i, const float *__restrict__ sig_u, float c, int id_off,
+              const uint2 *__restrict__ cand, const int *__restrict__ cand_cnt, int n_chunks, int K,
+              int32_t *__restrict__ out_ids, float *__restrict__ out_scores,
+              int32_t *__restrict__ fb_rows, int *__restrict__ fb_count,
+              unsigned long long *__restrict__ cand_total) {
+  __shared__ float su[8][kD];
+  const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
+  const int t = blockIdx.x * 8 + wib;
+  if (t >= T) return;
+  const unsigned kmask = (K >= 32) ? 0xffffffffu : ((1u << K) - 1u);
+  bool overflow = false;
+  int total = 0;
+  for (int ch = lane; ch < n_chunks; ch += 32) {
+    const int cn = cand_cnt[(size_t)t * n_chunks + ch];
+    overflow |= cn > kCap;
+    total += min(cn, kCap);
+  }
+  overflow = __any_sync(0xffffffffu, overflow);
+  if (overflow) {
+    if (lane == 0) fb_rows[atomicAdd(fb_count, 1)] = t;
+    return;
+  }
+  if (cand_total) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) total += __shfl_xor_sync(0xffffffffu, total, o);
+    if (lane == 0) atomicAdd(cand_total, (unsigned long long)total);
+  }
+  su[wib][lane] = Uq[(size_t)t * kD + lane];
+  su[wib][lane + 32] = Uq[(size_t)t * kD + lane + 32];
+  __syncwarp();
+  const float sgu = sig_u[t];
+  float ls = -INFINITY;
+  int li = 0x7fffffff;
+  for (int ch = 0; ch < n_chunks; ++ch) {
+    const int cn = cand_cnt[(size_t)t * n_chunks + ch];
+    const uint2 *cl = cand + ((size_t)t * n_chunks + ch) * kCap;
+    for (int b0 = 0; b0 < cn; b0 += 32) {
+      const int e = b0 + lane;
+      float s = -INFINITY;
+      int gid = -1;
+      if (e < cn) {
+        gid = (int)cl[e].y;
+        const float4 *ip = reinterpret_cast<const float4 *>(It + (size_t)(gid - id_off) * kD);
+        float acc = 0.f;
+#pragma unroll
+        for (int q4 = 0; q4 < kD / 4; ++q4) {
+          const float4 v = ip[q4];
+          acc = fmaf(su[wib][4 * q4 + 0], v.x, acc);
+          acc = fmaf(su[wib][4 * q4 + 1], v.y, acc);
+          acc = fmaf(su[wib][4 * q4 + 2], v.z, acc);
+          acc = fmaf(su[wib][4 * q4 + 3], v.w, acc);
+        }
+        s = __fmul_rn(__fmul_rn(__fsub_rn(acc, c), sig_i[gid - id_off]), sgu);
+      }
+      const int nb = min(32, cn - b0);
+      for (int k = 0; k < nb; ++k) {
+        const float cs = __shfl_sync(0xffffffffu, s, k);
+        const int cid = __shfl_sync(0xffffffffu, gid, k);
+        const float ws = __shfl_sync(0xffffffffu, ls, K - 1);
+        const int wi = __shfl_sync(0xffffffffu, li, K - 1);
+        if (score_better(cs, cid, ws, wi)) score_list_insert(ls, li, cs, cid, lane, kmask, K);
+      }
+    }
+  }
+  if (lane < K) {
+    const bool empty = li == 0x7fffffff;
+    out_ids[(size_t)t * K + lane] = empty ? -1 : li;
+    out_scores[(size_t)t * K + lane] = empty ? -INFINITY : ls;
+  }
+}
+
+__global__ void accumulate_stats_kernel(int64_t *stats, const int *fb_count,
+                                        const unsigned long long *cand_total) {
+  stats[0] += *fb_count;
+  stats[1] += (int64_t)*cand_total;
+}
+static void accumulate_stats(int64_t *stats, const int *fb_count,
+                             const unsigned long long *cand_total, cudaStream_t s) {
+  accumulate_stats_kernel<<<1, 1, 0, s>>>(stats, fb_count, cand_total);
+}
+
+// ---------------------------------------------------------------------------------------------
+// host side
+// ---------------------------------------------------------------------------------------------
+typedef CUresult (*EncodeTiledFn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *,
+                                  const cuuint64_t *, const cuuint64_t *, const cuuint32_t *,
+                                  const cuuint32_t *, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static EncodeTiledFn encode_fn() {
+  static EncodeTiledFn fn = nullptr;
+  if (!fn) {
+    void *p = nullptr;
+    cudaDriverEntryPointQueryResult qr;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &qr) ==
+            cudaSuccess &&
+        qr == cudaDriverEntryPointSuccess)
+      fn = reinterpret_cast<EncodeTiledFn>(p);
+  }
+  return fn;
+}
+
+// [rows][64] fp32 row-major -> boxes of 128 rows x 32 fp32 (128 B), 128-byte swizzle;
+// rows beyond `rows` read as zeros
+static int make_map(CUtensorMap *m, const float *base, long long rows) {
+  EncodeTiledFn fn = encode_fn();
+  if (!fn) return fail(MACR_ERR_CUDA, "cuTensorMapEncodeTiled is not available from the driver");
+  cuuint64_t dims[2] = {(cuuint64_t)kD, (cuuint64_t)rows};
+  cuuint64_t strides[1] = {(cuuint64_t)kD * sizeof(float)};
+  cuuint32_t box[2] = {(cuuint32_t)KB, (cuuint32_t)BM};
+  cuuint32_t estr[2] = {1, 1};
+  CUresult r = fn(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float *>(base), dims, strides,
+                  box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                  CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) return fail(MACR_ERR_CUDA, "cuTensorMapEncodeTiled failed (%d)", (int)r);
+  return MACR_OK;
+}
+
+struct Plan {
+  int TB;        // query rows per row block
+  int n_itiles, n_chunks, tiles_per_chunk, ld_tm;
+  size_t off_uhi, off_ulo, off_ihi, off_ilo, off_unorm, off_misc, off_tilemax, off_thr, off_cand,
+      off_cnt, off_fbrows, off_exact, total;
+  size_t exact_bytes;
+};
+
+static size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
+
+static Plan make_plan(int T, long long n_items, int K) {
+  Plan p;
+  p.n_itiles = (int)((n_items + BN - 1) / BN);
+  p.ld_tm = (p.n_itiles + 31) / 32 * 32;
+  // row block: tile maxima at most ~256 MiB
+  long long tb = (256LL << 20) / (4LL * p.ld_tm);
+  tb = tb / BM * BM;
+  if (tb < 1024) tb = 1024;
+  if (tb > T) tb = T;
+  p.TB = (int)tb;
+  const int utiles = (p.TB + BM - 1) / BM;
+  // item chunks: enough work items to balance the SMs, every chunk non-empty
+  const int sms = sm_count();
+  int best = 1;
+  double best_cost = 1e30;
+  for (int nc = 1; nc <= 8 && nc * 4 <= p.n_itiles; ++nc) {
+    const int tpc = (p.n_itiles + nc - 1) / nc;
+    const int ncr = (p.n_itiles + tpc - 1) / tpc;
+    const long long work = (long long)utiles * ncr;
+    const long long rounds = (work + sms - 1) / sms;
+    const double cost = (double)rounds * tpc;  // tiles on the busiest SM
+    if (cost < best_cost * 0.97) {
+      best_cost = cost;
+      best = ncr;
+    }
+  }
+  p.tiles_per_chunk = (p.n_itiles + best - 1) / best;
+  p.n_chunks = (p.n_itiles + p.tiles_per_chunk - 1) / p.tiles_per_chunk;
+  size_t o = 0;
+  auto take = [&](size_t bytes) {
+    const size_t at = o;
+    o = align_up(o + bytes, 1024);
+    return at;
+  };
+  p.off_uhi = take((size_t)p.TB * kD * 4);
+  p.off_ulo = take((size_t)p.TB * kD * 4);
+  p.off_ihi = take((size_t)n_items * kD * 4);
+  p.off_ilo = take((size_t)n_items * kD * 4);
+  p.off_unorm = take((size_t)p.TB * 4);
+  p.off_misc = take(64);  // [0] item norm max (uint bits) [1] fb_count [2..3] cand_total (u64)
+  p.off_tilemax = take((size_t)p.TB * p.ld_tm * 4);
+  p.off_thr = take((size_t)p.TB * 4);
+  p.off_cand = take((size_t)p.TB * p.n_chunks * kCap * 8);
+  p.off_cnt = take((size_t)p.TB * p.n_chunks * 4);
+  p.off_fbrows = take((size_t)p.TB * 4);
+  p.exact_bytes = score_exact_workspace_bytes(p.TB, n_items, K);
+  p.off_exact = take(p.exact_bytes);
+  p.total = o + 1024;
+  return p;
+}
+
+static int g_nsplit_max = 1, g_nsplit_filter = 3;
+
+template <int MODE, int NSPLIT>
+static int launch_pass(const CUtensorMap &uh, const CUtensorMap &ul, const CUtensorMap &ih,
+                       const CUtensorMap &il, const TileParams &P, const float *sig_i,
+                       const int32_t *mrp, const int32_t *mcol, float *tilemax, const float *thr,
+                       uint2 *cand, int *cnt, cudaStream_t s) {
+  static bool opted = false;
+  if (!opted) {
+    MACR_CUDA(cudaFuncSetAttribute(score_tc_kernel<MODE, NSPLIT>,
+                                   cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                   Cfg<NSPLIT>::SMEM_BYTES));
+    opted = true;
+  }
+  const int n_work = P.n_utiles * P.n_chunks;
+  const int grid = n_work < sm_count() ? n_work : sm_count();
+  score_tc_kernel<MODE, NSPLIT><<<grid, kThreads, Cfg<NSPLIT>::SMEM_BYTES, s>>>(
+      uh, ul, ih, il, P, sig_i, mrp, mcol, tilemax, thr, cand, cnt);
+  MACR_LAUNCH_CHECK();
+  return MACR_OK;
+}
+
+}  // namespace tc
+}  // namespace macr
+
+using namespace macr;
+
+extern "C" int macr_score_tc_set_splits(int nsplit_max, int nsplit_filter) {
+  MACR_CHECK_ARG((nsplit_max == 1 || nsplit_max == 3) && (nsplit_filter == 1 || nsplit_filter == 3),
+                 "macr_score_tc_set_splits: splits must be 1 or 3");
+  tc::g_nsplit_max = nsplit_max;
+  tc::g_nsplit_filter = nsplit_filter;
+  return MACR_OK;
+}
+
+extern "C" size_t macr_score_topk_tc_workspace_bytes(int T, int64_t n_items, int K) {
+  if (T <= 0 || n_items <= 0 || K <= 0) return 1024;
+  return tc::make_plan(T, n_items, K).total;
+}
+
+extern "C" int macr_score_topk_tc(const float *Uq, int T, const float *It, int64_t n_items, int d,
+                                  const float *sig_i, const float *sig_u, float c,
+                                  const int32_t *mask_rowptr, const int32_t *mask_col, int K,
+                                  int32_t item_id_offset, int32_t *out_ids, float *out_scores,
+                                  void *ws, size_t ws_bytes, int64_t *stats,
+                                  macr_stream_t stream) {
+  using namespace tc;
+  MACR_CHECK_ARG(d == kD, "macr_score_topk_tc: d must be %d (got %d)", kD, d);
+  MACR_CHECK_ARG(K >= 1 && K <= 32, "macr_score_topk_tc: K must be in [1,32] (got %d)", K);
+  MACR_CHECK_ARG(T >= 0 && n_items >= 0, "macr_score_topk_tc: negative size");
+  if (T == 0) return MACR_OK;
+  MACR_CHECK_ARG(n_items >= (int64_t)2 * K * BN && n_items < (1LL << 31) - BN,
+                 "macr_score_topk_tc: needs at least 2*K*%d items (got %lld): use macr_score_topk",
+                 BN, (long long)n_items);
+  MACR_CHECK_ARG(Uq && It && sig_i && sig_u && out_ids && out_scores && ws,
+                 "macr_score_topk_tc: null pointer");
+  MACR_CHECK_ARG((reinterpret_cast<uintptr_t>(ws) & 1023) == 0,
+                 "macr_score_topk_tc: workspace must be 1024-byte aligned");
+  const Plan p = make_plan(T, n_items, K);
+  if (ws_bytes < p.total)
+    return fail(MACR_ERR_WORKSPACE, "macr_score_topk_tc: workspace %zu < %zu bytes", ws_bytes,
+                p.total);
+  cudaStream_t s = as_stream(stream);
+  unsigned char *w = reinterpret_cast<unsigned char *>(ws);
+  float *uhi = reinterpret_cast<float *>(w + p.off_uhi), *ulo = reinterpret_cast<float *>(w + p.off_ulo);
+  float *ihi = reinterpret_cast<float *>(w + p.off_ihi), *ilo = reinterpret_cast<float *>(w + p.off_ilo);
+  float *unorm = reinterpret_cast<float *>(w + p.off_unorm);
+  unsigned int *misc = reinterpret_cast<unsigned int *>(w + p.off_misc);
+  float *tilemax = reinterpret_cast<float *>(w + p.off_tilemax);
+  float *thr = reinterpret_cast<float *>(w + p.off_thr);
+  uint2 *cand = reinterpret_cast<uint2 *>(w + p.off_cand);
+  int *cnt = reinterpret_cast<int *>(w + p.off_cnt);
+  int32_t *fb_rows = reinterpret_cast<int32_t *>(w + p.off_fbrows);
+  int *fb_count = reinterpret_cast<int *>(misc + 1);
+  unsigned long long *cand_total = reinterpret_cast<unsigned long long *>(misc + 2);
+
+  MACR_CUDA(cudaMemsetAsync(misc, 0, 64, s));
+  split_rows_kernel<<<(unsigned)((n_items * 16 + 255) / 256), 256, 0, s>>>(It, n_items, ihi, ilo,
+                                                                           nullptr, misc);
+  MACR_LAUNCH_CHECK();
+  CUtensorMap mih, mil;
+  int rc = make_map(&mih, ihi, n_items);
+  if (rc) return rc;
+  rc = make_map(&mil, ilo, n_items);
+  if (rc) return rc;
+  const float kappa1 = 1.953125e-3f /*2^-9*/, kappa3 = 3.0517578125e-5f /*2^-15*/;
+  const float kappa_sum = (g_nsplit_max == 1 ? kappa1 : kappa3) + (g_nsplit_filter == 1 ? kappa1 : kappa3);
+
+  for (int t0 = 0; t0 < T; t0 += p.TB) {
+    const int nb = T - t0 < p.TB ? T - t0 : p.TB;
+    const float *Ub = Uq + (size_t)t0 * kD;
+    const int32_t *mrp = mask_rowptr ? mask_rowptr + t0 : nullptr;
+    split_rows_kernel<<<(unsigned)(((long long)nb * 16 + 255) / 256), 256, 0, s>>>(Ub, nb, uhi, ulo,
+                                                                                  unorm, nullptr);
+    MACR_LAUNCH_CHECK();
+    CUtensorMap muh, mul;
+    rc = make_map(&muh, uhi, nb);
+    if (rc) return rc;
+    rc = make_map(&mul, ulo, nb);
+    if (rc) return rc;
+    TileParams P;
+    P.T = nb;
+    P.n_items = (int)n_items;
+    P.n_utiles = (nb + BM - 1) / BM;
+    P.n_itiles = p.n_itiles;
+    P.n_chunks = p.n_chunks;
+    P.tiles_per_chunk = p.tiles_per_chunk;
+    P.c = c;
+    P.id_off = item_id_offset;
+    P.ld_tm = p.ld_tm;
+    if (g_nsplit_max == 1)
+      rc = launch_pass<MODE_MAX, 1>(muh, mul, mih, mil, P, sig_i, mrp, mask_col, tilemax, nullptr,
+                                    nullptr, nullptr, s);
+    else
+      rc = launch_pass<MODE_MAX, 3>(muh, mul, mih, mil, P, sig_i, mrp, mask_col, tilemax, nullptr,
+                                    nullptr, nullptr, s);
+    if (rc) return rc;
+    row_threshold_kernel<<<(nb + 7) / 8, 256, 0, s>>>(tilemax, nb, p.n_itiles, p.ld_tm, K, unorm,
+                                                      misc, c, kappa_sum, thr);
+    MACR_LAUNCH_CHECK();
+    if (g_nsplit_filter == 1)
+      rc = launch_pass<MODE_FILTER, 1>(muh, mul, mih, mil, P, sig_i, mrp, mask_col, nullptr, thr,
+                                       cand, cnt, s);
+    else
+      rc = launch_pass<MODE_FILTER, 3>(muh, mul, mih, mil, P, sig_i, mrp, mask_col, nullptr, thr,
+                                       cand, cnt, s);
+    if (rc) return rc;
+    MACR_CUDA(cudaMemsetAsync(fb_count, 0, sizeof(int), s));
+    rerank_kernel<<<(nb + 7) / 8, 256, 0, s>>>(Ub, nb, It, sig_i, sig_u + t0, c, item_id_offset,
+                                               cand, cnt, p.n_chunks, K,
+                                               out_ids + (size_t)t0 * K, out_scores + (size_t)t0 * K,
+                                               fb_rows, fb_count, cand_total);
+    MACR_LAUNCH_CHECK();
+    // rows whose candidate lists overflowed: exact fp32 kernel on the queued rows (device-side
+    // count, so nothing is read back; the launch is a no-op when the queue is empty)
+    rc = score_exact_rows(Ub, nb, It, n_items, sig_i, sig_u + t0, c, mrp, mask_col, K,
+                          item_id_offset, fb_rows, fb_count, out_ids + (size_t)t0 * K,
+                          out_scores + (size_t)t0 * K, w + p.off_exact, p.exact_bytes, s);
+    if (rc) return rc;
+    if (stats) {
+      // stats[0] += rows sent to the exact kernel, stats[1] += candidates re-ranked
+      accumulate_stats(stats, fb_count, cand_total, s);
+      MACR_CUDA(cudaMemsetAsync(cand_total, 0, sizeof(unsigned long long), s));
+    }
+  }
+  return MACR_OK;
+}

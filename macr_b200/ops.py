@@ -133,8 +133,37 @@ def gather_rows(table, ids):
     return out
 
 
+TC_MIN_TILES_PER_K = 2  # the tcgen05 path needs n_items >= 2*K*128 (include/macr_b200.h)
+
+
+def score_topk_tc(Uq, It, sig_i, sig_u, c, mask_rowptr, mask_col, K, item_id_offset=0, stats=None):
+    """Tensor-core (tcgen05 + TMA) score + mask + top-K; bit-identical to `score_topk_exact`.
+    stats: optional int64[2] device tensor, += {rows re-done by the exact kernel, candidates}."""
+    T, n_items = Uq.shape[0], It.shape[0]
+    dev = Uq.device
+    ids = torch.empty((T, K), dtype=torch.int32, device=dev)
+    sc = torch.empty((T, K), dtype=torch.float32, device=dev)
+    nbytes = lib().macr_score_topk_tc_workspace_bytes(T, n_items, K)
+    ws = torch.empty(nbytes + 1024, dtype=torch.uint8, device=dev)
+    off = (-ws.data_ptr()) % 1024
+    check(lib().macr_score_topk_tc(_f(Uq), T, _f(It), n_items, Uq.shape[1], _f(sig_i), _f(sig_u), c,
+                                   ptr(mask_rowptr), ptr(mask_col), K, item_id_offset, ptr(ids),
+                                   ptr(sc), C.c_void_p(ws.data_ptr() + off), nbytes, ptr(stats),
+                                   stream_ptr()), "macr_score_topk_tc")
+    return ids, sc
+
+
 def score_topk(Uq, It, sig_i, sig_u, c, mask_rowptr, mask_col, K, item_id_offset=0):
-    """Fused score + mask + top-K. -> (ids [T,K] int32 global ids, scores [T,K] fp32)."""
+    """Fused score + mask + top-K. -> (ids [T,K] int32 global ids, scores [T,K] fp32).
+    Catalogues of at least 2*K tiles of 128 items go to the tcgen05 path, smaller ones to the
+    exact fp32 kernel; both give the same bits."""
+    if It.shape[0] >= TC_MIN_TILES_PER_K * K * 128 and K <= 32 and Uq.shape[0] > 0:
+        return score_topk_tc(Uq, It, sig_i, sig_u, c, mask_rowptr, mask_col, K, item_id_offset)
+    return score_topk_exact(Uq, It, sig_i, sig_u, c, mask_rowptr, mask_col, K, item_id_offset)
+
+
+def score_topk_exact(Uq, It, sig_i, sig_u, c, mask_rowptr, mask_col, K, item_id_offset=0):
+    """Exact fp32 CUDA-core kernel (score.cu)."""
     T, n_items = Uq.shape[0], It.shape[0]
     dev = Uq.device
     ids = torch.empty((T, K), dtype=torch.int32, device=dev)
