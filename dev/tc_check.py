@@ -50,6 +50,62 @@ def run(T_users, n_items, K, c, mask_deg, splits, scale=10.0, seed=0, time_it=Fa
     return bad_rows == 0 and bad_sc == 0
 
 
+def run_special():
+    """heavy train lists, all-equal scores (overflow -> exact fallback), sharded ids, negative c"""
+    dev = torch.device("cuda")
+    ok = True
+    # heavy users: 3000 of 9000 items masked for some rows
+    T_users, n_items, K = 200, 9000, 20
+    U, I, w, wu = make_model(5, T_users, n_items, scale=10.0)
+    rng = np.random.RandomState(5)
+    lists = [np.sort(rng.choice(n_items, size=(3000 if u % 7 == 0 else 40), replace=False)).astype(np.int32)
+             for u in range(T_users)]
+    a, b = lists_to_csr(lists)
+    dU, dI = torch.from_numpy(U).to(dev), torch.from_numpy(I).to(dev)
+    si, su = ops.score_gates(dI, torch.from_numpy(w).to(dev)), ops.score_gates(dU, torch.from_numpy(wu).to(dev))
+    mrp, mcol = torch.from_numpy(a).to(dev), torch.from_numpy(b).to(dev)
+    for c in (40.0, -3.0, 0.0):
+        ei, es = ops.score_topk_exact(dU, dI, si, su, c, mrp, mcol, K)
+        st = torch.zeros(2, dtype=torch.int64, device=dev)
+        ti, ts = ops.score_topk_tc(dU, dI, si, su, c, mrp, mcol, K, stats=st)
+        good = bool((ti == ei).all().item() and (ts == es).all().item())
+        print(f"heavy masks c={c}: {'ok' if good else 'MISMATCH'} fallback {st[0].item()} cand/row {st[1].item() / T_users:.1f}", flush=True)
+        ok &= good
+    # sharded: item_id_offset
+    lo = 4000
+    ei, es = ops.score_topk_exact(dU, dI[lo:].contiguous(), si[lo:].contiguous(), su, 40.0, mrp, mcol, K, item_id_offset=lo)
+    ti, ts = ops.score_topk_tc(dU, dI[lo:].contiguous(), si[lo:].contiguous(), su, 40.0, mrp, mcol, K, item_id_offset=lo)
+    good = bool((ti == ei).all().item() and (ts == es).all().item())
+    print("shard offset:", "ok" if good else "MISMATCH", flush=True)
+    ok &= good
+    # degenerate: all scores equal -> every item is a candidate -> overflow -> exact fallback
+    Z = torch.zeros((150, 64), device=dev)
+    ZI = torch.zeros((5000, 64), device=dev)
+    h = torch.full((5000,), 0.5, device=dev)
+    hu = torch.full((150,), 0.5, device=dev)
+    ei, es = ops.score_topk_exact(Z, ZI, h, hu, 40.0, None, None, K)
+    st = torch.zeros(2, dtype=torch.int64, device=dev)
+    ti, ts = ops.score_topk_tc(Z, ZI, h, hu, 40.0, None, None, K, stats=st)
+    good = bool((ti == ei).all().item() and (ts == es).all().item())
+    print("all-equal scores:", "ok" if good else "MISMATCH", "fallback rows", st[0].item(), ti[0, :5].tolist(), flush=True)
+    ok &= good
+    # tiny init (epoch-0 evaluation): scores differ in the last bits
+    U, I, w, wu = make_model(9, 300, 6000, scale=1.0)
+    dU, dI = torch.from_numpy(U).to(dev), torch.from_numpy(I).to(dev)
+    si, su = ops.score_gates(dI, torch.from_numpy(w).to(dev)), ops.score_gates(dU, torch.from_numpy(wu).to(dev))
+    for sp in ((1, 1), (1, 3), (3, 3)):
+        lib().macr_score_tc_set_splits(*sp)
+        ei, es = ops.score_topk_exact(dU, dI, si, su, 40.0, None, None, K)
+        st = torch.zeros(2, dtype=torch.int64, device=dev)
+        ti, ts = ops.score_topk_tc(dU, dI, si, su, 40.0, None, None, K, stats=st)
+        good = bool((ti == ei).all().item() and (ts == es).all().item())
+        print(f"xavier-init scale=1 splits={sp}:", "ok" if good else "MISMATCH", "fallback", st[0].item(),
+              f"cand/row {st[1].item() / max(1, 300 - st[0].item()):.1f}", flush=True)
+        ok &= good
+    lib().macr_score_tc_set_splits(1, 1)
+    return ok
+
+
 if __name__ == "__main__":
     ok = True
     ok &= run(128, 5120, 20, 40.0, 0, (1, 1))
@@ -60,4 +116,5 @@ if __name__ == "__main__":
     ok &= run(15424, 40981, 20, 40.0, 27, (1, 3), time_it=True)
     ok &= run(15424, 40981, 20, 40.0, 27, (1, 1), time_it=True)
     ok &= run(15424, 40981, 20, 40.0, 27, (3, 3), time_it=True)
+    ok &= run_special()
     print("ALL OK" if ok else "FAILURES")

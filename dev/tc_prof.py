@@ -1,0 +1,22 @@
+import sys, os
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+sys.path.insert(0, os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "tests"))
+import numpy as np, torch
+from macr_b200 import ops
+from macr_b200._lib import lib
+from helpers import make_model, make_interactions, lists_to_csr
+T_users, n_items, K, c = 15424, 40981, 20, 40.0
+splits = tuple(int(x) for x in (sys.argv[1:3] if len(sys.argv) > 2 else (1, 3)))
+U, I, w, wu = make_model(0, T_users, n_items, scale=10.0)
+rng = np.random.RandomState(1)
+cnt = np.maximum(1, rng.poisson(27, T_users))
+rowptr = np.zeros(T_users + 1, np.int32); rowptr[1:] = np.cumsum(cnt)
+col = np.concatenate([np.sort(rng.choice(n_items, size=k, replace=False)) for k in cnt]).astype(np.int32)
+dev = torch.device("cuda")
+dU, dI = torch.from_numpy(U).to(dev), torch.from_numpy(I).to(dev)
+si, su = ops.score_gates(dI, torch.from_numpy(w).to(dev)), ops.score_gates(dU, torch.from_numpy(wu).to(dev))
+mrp, mcol = torch.from_numpy(rowptr).to(dev), torch.from_numpy(col).to(dev)
+lib().macr_score_tc_set_splits(*splits)
+for _ in range(3):
+    ops.score_topk_tc(dU, dI, si, su, c, mrp, mcol, K)
+torch.cuda.synchronize()

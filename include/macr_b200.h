@@ -250,10 +250,10 @@ int macr_score_topk(const float *Uq, int T, const float *It, int64_t n_items, in
                     void *ws, size_t ws_bytes, macr_stream_t stream);
 /* Same contract and bit-identical results as macr_score_topk, computed on the tensor cores:
  * two TMA-fed tcgen05 (kind::tf32, accumulator in TMEM) passes over the T x n_items tile grid
- * -- per-tile maxima -> a proven per-row threshold -> candidate filter -- then an exact fp32
- * re-rank of the ~K candidates per row; rows whose candidate list overflows are re-done by the
- * exact kernel (macr_b200/csrc/score_tc.cu).  Needs n_items >= 2*K*128 (smaller catalogues:
- * macr_score_topk).  ws must be 1024-byte aligned.  stats (nullable, device int64[2]) is
+ * -- per-batch maxima -> a proven per-row threshold -> candidate filter -- then an exact fp32
+ * re-rank of the ~1.5 K candidates per row; rows whose candidate list overflows are re-done by
+ * the exact kernel (macr_b200/csrc/score_tc.cu).  Needs 2048 <= n_items <~ 1.5 M per call
+ * (smaller catalogues: macr_score_topk; larger: shard).  ws must be 1024-byte aligned.  stats (nullable, device int64[2]) is
  * incremented by {rows re-done by the exact kernel, candidates re-ranked}.
  * macr_score_tc_set_splits: tf32 operand splits (1 = hi*hi, 3 = hi*hi+hi*lo+lo*hi ~ fp32) of
  * the maxima pass and of the filter pass; results are exact for every setting. */

@@ -8,13 +8,16 @@
 // Why two tensor-core passes.  A running per-row top-K in the epilogue costs ~K(1+ln(n/K)) list
 // insertions per row, serialised across the 32 rows a warp owns: far more than the 4 instructions
 // per score of the pass itself.  Instead:
-//   pass MAX     per (row, 128-item tile): max over the unmasked items of the approximate score.
-//   threshold    thr[row] = K-th largest tile maximum - (eps_max + eps_filter + slack).  K tiles
-//                hold an unmasked item scoring >= the K-th largest tile maximum, so the exact K-th
-//                best score is >= thr + eps_filter: every item of the true top-K passes the filter.
-//   pass FILTER  same tiles again; append (score, id) of unmasked items with score >= thr to the
+//   pass MAX     per (row, batch of 32 items): max of the approximate score (2 instructions per
+//                score: the gate is folded into the item operand, see score_tc_kernel).
+//   threshold    m_K = K-th largest of 32 maxima over disjoint groups of batches that hold no
+//                train item of the row; thr[row] = m_K - (eps_max + eps_filter + slack).  K
+//                distinct unmasked items score >= m_K, so the exact K-th best score is
+//                >= thr + eps_filter: every item of the true top-K passes the filter.
+//   pass FILTER  same tiles again, but only batches whose maximum reaches the threshold are
+//                read back from TMEM; unmasked items with score >= thr are appended to the
 //                (row, item-chunk) candidate list (a register counter per thread: no atomics).
-//                Expected K*(1+small) candidates per row.
+//                Expected ~1.5 K candidates per row.
 //   re-rank      one warp per row: exact fp32 FMA-chain score of every candidate (the arithmetic
 //                of score.cu), sorted insert (score desc, lower id first) -> out.
 //   fallback     a row whose candidate list overflowed (degenerate score distributions) is
@@ -27,8 +30,9 @@
 //   warp 0      TMA producer   cp.async.bulk.tensor.2d, 128B-swizzled K-major boxes of 128 rows x 32 fp32
 //   warp 1      MMA issuer     tcgen05.mma.cta_group::1.kind::tf32, M=128 N=128 K=8, D in TMEM
 //                              (2 accumulator buffers x 128 columns); also owns TMEM alloc/dealloc
-//   warps 2..5  epilogue       tcgen05.ld.32x32b.x32 (thread = user row), fused correction,
-//                              tile maximum / threshold filter, train-item mask from a per-row
+//   warps 2..9  epilogue       two warpgroups, warpgroup g owns TMEM buffer g (tiles alternate):
+//                              tcgen05.ld.32x32b.x32 (thread = user row), fused correction,
+//                              batch maxima / threshold filter, train-item mask from a per-row
 //                              cursor into the sorted CSR mask
 // mbarrier pipelines: user tile full/empty, item stages full/empty, TMEM full/empty.
 #include <cuda.h>
@@ -46,8 +50,8 @@ constexpr int KB = 32;               // fp32 per 128-byte swizzle row
 constexpr int NKB = kD / KB;         // K blocks per operand tile (2)
 constexpr int KBLK_BYTES = BM * 128; // one K block of one operand tile: 128 rows x 128 B
 constexpr int OPER_BYTES = NKB * KBLK_BYTES;  // 32 KiB: a 128 x 64 fp32 operand tile
-constexpr int kCap = 64;             // candidate slots per (row, item chunk)
-constexpr int kThreads = 192;
+constexpr int kCap = 32;             // candidate slots per (row, item chunk, epilogue warpgroup)
+constexpr int kThreads = 320;           // producer, MMA issuer, 2 epilogue warpgroups
 constexpr int kTmemCols = 256;
 constexpr int MODE_MAX = 0, MODE_FILTER = 1;
 
@@ -167,19 +171,39 @@ struct TileParams {
   int T;            // query rows in this row block
   int n_items;      // items in this shard
   int n_utiles, n_itiles, n_chunks, tiles_per_chunk;
-  float c;
   int id_off;       // global id of local item 0 (mask_col holds global ids)
-  int ld_tm;        // row pitch of tilemax
+  int ld_tm;        // row pitch of the batch maxima (floats), 4 per item tile
 };
 
+// max over 32 accumulator columns of (acc - c*sig): 4 independent chains
+__device__ __forceinline__ float batch_max(const uint32_t (&v)[32], const float *cs) {
+  const float4 *c4 = reinterpret_cast<const float4 *>(cs);
+  float m0 = -INFINITY, m1 = -INFINITY, m2 = -INFINITY, m3 = -INFINITY;
+#pragma unroll
+  for (int j4 = 0; j4 < 8; ++j4) {
+    const float4 g = c4[j4];
+    m0 = fmaxf(m0, __uint_as_float(v[4 * j4 + 0]) - g.x);
+    m1 = fmaxf(m1, __uint_as_float(v[4 * j4 + 1]) - g.y);
+    m2 = fmaxf(m2, __uint_as_float(v[4 * j4 + 2]) - g.z);
+    m3 = fmaxf(m3, __uint_as_float(v[4 * j4 + 3]) - g.w);
+  }
+  return fmaxf(fmaxf(m0, m1), fmaxf(m2, m3));
+}
+
+// ---------------------------------------------------------------------------------------------
+// The item operand is pre-scaled by its gate (rows sig_i * I_i), so the accumulator holds
+// sig_i * y and the approximate score is  acc - c*sig_i  (one FADD per score in the epilogue).
+//   MODE_MAX     bmax[row][4*tile + b] = max over the 32 columns of batch b (masked items included;
+//                the threshold kernel leaves batches holding a train item of the row out)
+//   MODE_FILTER  batches with bmax >= thr.y are re-read; unmasked scores >= thr.x are appended
 // ---------------------------------------------------------------------------------------------
 template <int MODE, int NSPLIT>
 __global__ void __launch_bounds__(kThreads, 1)
 score_tc_kernel(const __grid_constant__ CUtensorMap tmUhi, const __grid_constant__ CUtensorMap tmUlo,
                 const __grid_constant__ CUtensorMap tmIhi, const __grid_constant__ CUtensorMap tmIlo,
-                const TileParams P, const float *__restrict__ sig_i,
+                const TileParams P, const float *__restrict__ csig,
                 const int32_t *__restrict__ mask_rowptr, const int32_t *__restrict__ mask_col,
-                float *__restrict__ tilemax, const float *__restrict__ thr,
+                float *__restrict__ bmax, const float2 *__restrict__ thr,
                 uint2 *__restrict__ cand, int *__restrict__ cand_cnt) {
   using C = Cfg<NSPLIT>;
   extern __shared__ unsigned char smem_raw[];
@@ -190,8 +214,8 @@ score_tc_kernel(const __grid_constant__ CUtensorMap tmUhi, const __grid_constant
   unsigned char *sB = smem + C::A_BYTES;    // [STAGES][PARTS][NKB][128 x 128 B]
   unsigned char *tail = sB + C::STAGES * C::STAGE_BYTES;
   uint64_t *bars = reinterpret_cast<uint64_t *>(tail);  // see indices below
-  float *sSig = reinterpret_cast<float *>(tail + 256);  // [2][BN]
-  uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(tail + 256 + 2 * BN * 4);
+  float *sCs = reinterpret_cast<float *>(tail + 256);   // [2 warpgroups][2][BN]  c*sig of the tile
+  uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(tail + 256 + 4 * BN * 4);
 
   enum { A_FULL = 0, A_EMPTY = 1, TM_FULL = 2, TM_EMPTY = 4, B_FULL = 6, B_EMPTY = 6 + C::STAGES };
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -203,7 +227,7 @@ score_tc_kernel(const __grid_constant__ CUtensorMap tmUhi, const __grid_constant
     mbar_init(BAR(A_EMPTY), 1);
     for (int b = 0; b < 2; ++b) {
       mbar_init(BAR(TM_FULL + b), 1);
-      mbar_init(BAR(TM_EMPTY + b), 4);  // one arrive per epilogue warp
+      mbar_init(BAR(TM_EMPTY + b), 4);  // one arrive per warp of the owning epilogue warpgroup
     }
     for (int s = 0; s < C::STAGES; ++s) {
       mbar_init(BAR(B_FULL + s), 1);
@@ -308,10 +332,12 @@ score_tc_kernel(const __grid_constant__ CUtensorMap tmUhi, const __grid_constant
       }
     }
   } else {
-    // =============================== epilogue (128 threads) ===============================
+    // ============ epilogue: 2 warpgroups of 128 threads, warpgroup g owns TMEM buffer g ============
+    const int g = (warp - 2) >> 2;          // warpgroup: tiles with (n & 1) == g
     const int q = warp & 3;                 // TMEM lane quarter this warp may read
     const int r_in = q * 32 + lane;         // row inside the user tile
-    const int te = threadIdx.x - 64;        // 0..127
+    const int te = (threadIdx.x - 64) & 127;
+    const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + g * BN;
     uint32_t n = 0;
     for (int w = blockIdx.x; w < n_work; w += gridDim.x) {
       const int ut = w / P.n_chunks, ch = w - ut * P.n_chunks;
@@ -319,140 +345,141 @@ score_tc_kernel(const __grid_constant__ CUtensorMap tmUhi, const __grid_constant
       const int t_end = min(P.n_itiles, t_begin + P.tiles_per_chunk);
       const int row = ut * BM + r_in;
       const bool valid = row < P.T;
-      // cursor into this row's sorted train-item list, positioned at the chunk's first item
-      int mptr = 0, mend = 0;
-      if (valid && mask_rowptr) {
-        mptr = mask_rowptr[row];
-        mend = mask_rowptr[row + 1];
-        const int first = P.id_off + t_begin * BN;
-        int lo = mptr, hi = mend;
-        while (lo < hi) {
-          const int mid = (lo + hi) >> 1;
-          if (mask_col[mid] < first) lo = mid + 1;
-          else hi = mid;
-        }
-        mptr = lo;
-      }
-      int nxt = mptr < mend ? mask_col[mptr] : 0x7fffffff;
-      int nxt2 = mptr + 1 < mend ? mask_col[mptr + 1] : 0x7fffffff;
-      float thr_r = INFINITY;
+      int mptr = 0, mend = 0, nxt = 0x7fffffff, nxt2 = 0x7fffffff;
+      float2 th = make_float2(INFINITY, INFINITY);
       int cnt = 0;
       uint2 *my_cand = nullptr;
       if (MODE == MODE_FILTER && valid) {
-        thr_r = thr[row];
-        my_cand = cand + ((size_t)row * P.n_chunks + ch) * kCap;
+        // cursor into this row's sorted train-item list, positioned at the chunk's first item
+        if (mask_rowptr) {
+          mptr = mask_rowptr[row];
+          mend = mask_rowptr[row + 1];
+          const int first = P.id_off + t_begin * BN;
+          int lo = mptr, hi = mend;
+          while (lo < hi) {
+            const int mid = (lo + hi) >> 1;
+            if (mask_col[mid] < first) lo = mid + 1;
+            else hi = mid;
+          }
+          mptr = lo;
+          nxt = mptr < mend ? mask_col[mptr] : 0x7fffffff;
+          nxt2 = mptr + 1 < mend ? mask_col[mptr + 1] : 0x7fffffff;
+        }
+        th = thr[row];
+        my_cand = cand + (((size_t)row * P.n_chunks + ch) * 2 + g) * kCap;  // one list per warpgroup
       }
-      // item gate of column te of the next tile (prefetched one tile ahead)
-      float sig_next = (t_begin * BN + te < P.n_items) ? sig_i[t_begin * BN + te] : 0.f;
+      // c*sig of column te of this warpgroup's next tile (prefetched one tile ahead);
+      // +inf beyond the catalogue, so those columns score -inf
+      int t_mine = t_begin + ((g ^ (int)n) & 1);
+      float cs_next = INFINITY;
+      if (t_mine < t_end && t_mine * BN + te < P.n_items) cs_next = csig[t_mine * BN + te];
 
       for (int t = t_begin; t < t_end; ++t, ++n) {
-        const uint32_t buf = n & 1;
-        sSig[buf * BN + te] = sig_next;
-        if (t + 1 < t_end) {
-          const int cn = (t + 1) * BN + te;
-          sig_next = cn < P.n_items ? sig_i[cn] : 0.f;
-        }
-        asm volatile("bar.sync 1, 128;" ::: "memory");
-        // mask words of this tile: train items of the row + columns beyond the catalogue
-        uint32_t mw0 = 0, mw1 = 0, mw2 = 0, mw3 = 0;
-        {
-          const int g0 = P.id_off + t * BN, g1 = g0 + BN;
-          while (nxt < g1) {
-            const int b = nxt - g0;
-            if (b >= 0) {
-              const uint32_t bit = 1u << (b & 31);
-              const int ws = b >> 5;
-              mw0 |= ws == 0 ? bit : 0u;
-              mw1 |= ws == 1 ? bit : 0u;
-              mw2 |= ws == 2 ? bit : 0u;
-              mw3 |= ws == 3 ? bit : 0u;
-            }
-            nxt = nxt2;
-            ++mptr;
-            nxt2 = mptr + 1 < mend ? mask_col[mptr + 1] : 0x7fffffff;
-          }
-          const int nv = P.n_items - t * BN;  // valid columns of this tile
-          if (nv < BN) {
-            mw0 |= nv <= 0 ? 0xffffffffu : (nv < 32 ? ~((1u << nv) - 1u) : 0u);
-            mw1 |= nv <= 32 ? 0xffffffffu : (nv < 64 ? ~((1u << (nv - 32)) - 1u) : 0u);
-            mw2 |= nv <= 64 ? 0xffffffffu : (nv < 96 ? ~((1u << (nv - 64)) - 1u) : 0u);
-            mw3 |= nv <= 96 ? 0xffffffffu : ~((1u << (nv - 96)) - 1u);
-          }
-        }
-        mbar_wait(BAR(TM_FULL + buf), (n >> 1) & 1);
-        tc_fence_after();
-        const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + buf * BN;
-        const float *sg = sSig + buf * BN;
-        float m = -INFINITY;
+        if ((int)(n & 1) != g) continue;
+        // double-buffered by tile parity: one barrier per tile then orders the writes of tile
+        // k+2 after every read of tile k
+        float *cs = sCs + (g * 2 + ((n >> 1) & 1)) * BN;
+        cs[te] = cs_next;
+        cs_next = INFINITY;
+        if (t + 2 < t_end && (t + 2) * BN + te < P.n_items) cs_next = csig[(t + 2) * BN + te];
+        asm volatile("bar.sync %0, 128;" ::"r"(1 + g) : "memory");
+        const uint32_t full_parity = (n >> 1) & 1;
         uint32_t va[32], vb[32];
-
-        auto process = [&](uint32_t (&v)[32], int cb, uint32_t mw) {
-          const float4 *sg4 = reinterpret_cast<const float4 *>(sg + cb * 32);
-          if (MODE == MODE_MAX) {
-            if (__any_sync(0xffffffffu, mw != 0u)) {
-#pragma unroll
-              for (int j4 = 0; j4 < 8; ++j4) {
-                const float4 g = sg4[j4];
-                const float gg[4] = {g.x, g.y, g.z, g.w};
-#pragma unroll
-                for (int e = 0; e < 4; ++e) {
-                  const int j = j4 * 4 + e;
-                  float s = __fmul_rn(__fsub_rn(__uint_as_float(v[j]), P.c), gg[e]);
-                  s = ((mw >> j) & 1u) ? -INFINITY : s;
-                  m = fmaxf(m, s);
-                }
+        if (MODE == MODE_MAX) {
+          mbar_wait(BAR(TM_FULL + g), full_parity);
+          tc_fence_after();
+          __syncwarp();
+          tmem_ld32(taddr + 0, va);
+          tmem_ld_wait(va);
+          tmem_ld32(taddr + 32, vb);
+          const float b0 = batch_max(va, cs + 0);
+          tmem_ld_wait(vb);
+          tmem_ld32(taddr + 64, va);
+          const float b1 = batch_max(vb, cs + 32);
+          tmem_ld_wait(va);
+          tmem_ld32(taddr + 96, vb);
+          const float b2 = batch_max(va, cs + 64);
+          tmem_ld_wait(vb);
+          // all TMEM reads of this buffer are complete: hand it back to the MMA warp
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(BAR(TM_EMPTY + g));
+          const float b3 = batch_max(vb, cs + 96);
+          if (valid)
+            *reinterpret_cast<float4 *>(bmax + (size_t)row * P.ld_tm + 4 * t) =
+                make_float4(b0, b1, b2, b3);
+        } else {
+          // mask words of this tile: train items of the row + columns beyond the catalogue
+          uint32_t mw[4] = {0u, 0u, 0u, 0u};
+          {
+            const int g0 = P.id_off + t * BN, g1 = g0 + BN;
+            while (nxt < g1) {
+              const int b = nxt - g0;
+              if (b >= 0) {
+                const uint32_t bit = 1u << (b & 31);
+                const int ws = b >> 5;
+                mw[0] |= ws == 0 ? bit : 0u;
+                mw[1] |= ws == 1 ? bit : 0u;
+                mw[2] |= ws == 2 ? bit : 0u;
+                mw[3] |= ws == 3 ? bit : 0u;
               }
-            } else {
-#pragma unroll
-              for (int j4 = 0; j4 < 8; ++j4) {
-                const float4 g = sg4[j4];
-                const float gg[4] = {g.x, g.y, g.z, g.w};
-#pragma unroll
-                for (int e = 0; e < 4; ++e)
-                  m = fmaxf(m, __fmul_rn(__fsub_rn(__uint_as_float(v[j4 * 4 + e]), P.c), gg[e]));
-              }
+              nxt = nxt2;
+              ++mptr;
+              nxt2 = mptr + 1 < mend ? mask_col[mptr + 1] : 0x7fffffff;
             }
-          } else {
-            const int gbase = P.id_off + t * BN + cb * 32;
+            const int nv = P.n_items - t * BN;  // valid columns of this tile
+            if (nv < BN) {
+              mw[0] |= nv <= 0 ? 0xffffffffu : (nv < 32 ? ~((1u << nv) - 1u) : 0u);
+              mw[1] |= nv <= 32 ? 0xffffffffu : (nv < 64 ? ~((1u << (nv - 32)) - 1u) : 0u);
+              mw[2] |= nv <= 64 ? 0xffffffffu : (nv < 96 ? ~((1u << (nv - 64)) - 1u) : 0u);
+              mw[3] |= nv <= 96 ? 0xffffffffu : ~((1u << (nv - 96)) - 1u);
+            }
+          }
+          float4 bm = make_float4(-INFINITY, -INFINITY, -INFINITY, -INFINITY);
+          if (valid) bm = *reinterpret_cast<const float4 *>(bmax + (size_t)row * P.ld_tm + 4 * t);
+          const float bmv[4] = {bm.x, bm.y, bm.z, bm.w};
+          mbar_wait(BAR(TM_FULL + g), full_parity);
+          tc_fence_after();
 #pragma unroll
-            for (int j4 = 0; j4 < 8; ++j4) {
-              const float4 g = sg4[j4];
-              const float gg[4] = {g.x, g.y, g.z, g.w};
+          for (int cb = 0; cb < 4; ++cb) {
+            const bool need = bmv[cb] >= th.y;
+            __syncwarp();
+            if (__any_sync(0xffffffffu, need)) {
+              tmem_ld32(taddr + cb * 32, va);
+              tmem_ld_wait(va);
+              if (need) {
+                const float4 *c4 = reinterpret_cast<const float4 *>(cs + cb * 32);
+                const int gbase = P.id_off + t * BN + cb * 32;
+                const uint32_t mwb = mw[cb];
 #pragma unroll
-              for (int e = 0; e < 4; ++e) {
-                const int j = j4 * 4 + e;
-                const float s = __fmul_rn(__fsub_rn(__uint_as_float(v[j]), P.c), gg[e]);
-                if (s >= thr_r) {
-                  if (!((mw >> j) & 1u)) {
-                    if (cnt < kCap) my_cand[cnt] = make_uint2(__float_as_uint(s), (uint32_t)(gbase + j));
-                    ++cnt;
+                for (int j4 = 0; j4 < 8; ++j4) {
+                  const float4 gg = c4[j4];
+                  const float s0 = __uint_as_float(va[4 * j4 + 0]) - gg.x;
+                  const float s1 = __uint_as_float(va[4 * j4 + 1]) - gg.y;
+                  const float s2 = __uint_as_float(va[4 * j4 + 2]) - gg.z;
+                  const float s3 = __uint_as_float(va[4 * j4 + 3]) - gg.w;
+                  if (fmaxf(fmaxf(s0, s1), fmaxf(s2, s3)) >= th.x) {
+                    const float ss[4] = {s0, s1, s2, s3};
+#pragma unroll
+                    for (int e = 0; e < 4; ++e) {
+                      const int j = 4 * j4 + e;
+                      if (ss[e] >= th.x && !((mwb >> j) & 1u)) {
+                        if (cnt < kCap)
+                          my_cand[cnt] = make_uint2(__float_as_uint(ss[e]), (uint32_t)(gbase + j));
+                        ++cnt;
+                      }
+                    }
                   }
                 }
               }
             }
           }
-        };
-
-        __syncwarp();
-        tmem_ld32(taddr + 0, va);
-        tmem_ld_wait(va);
-        tmem_ld32(taddr + 32, vb);
-        process(va, 0, mw0);
-        tmem_ld_wait(vb);
-        tmem_ld32(taddr + 64, va);
-        process(vb, 1, mw1);
-        tmem_ld_wait(va);
-        tmem_ld32(taddr + 96, vb);
-        process(va, 2, mw2);
-        tmem_ld_wait(vb);
-        // all TMEM reads of this buffer are complete: hand it back to the MMA warp
-        tc_fence_before();
-        __syncwarp();
-        if (lane == 0) mbar_arrive(BAR(TM_EMPTY + buf));
-        process(vb, 3, mw3);
-        if (MODE == MODE_MAX && valid) tilemax[(size_t)row * P.ld_tm + t] = m;
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(BAR(TM_EMPTY + g));
+        }
       }
-      if (MODE == MODE_FILTER && valid) cand_cnt[(size_t)row * P.n_chunks + ch] = cnt;
+      if (MODE == MODE_FILTER && valid) cand_cnt[((size_t)row * P.n_chunks + ch) * 2 + g] = cnt;
     }
   }
 
@@ -467,7 +494,8 @@ score_tc_kernel(const __grid_constant__ CUtensorMap tmUhi, const __grid_constant
 }
 
 // ---------------------------------------------------------------------------------------------
-// operand preparation: hi = tf32(x) (round to nearest), lo = tf32(x - hi); row norm
+// operand preparation: x' = x * scale[row] (items: the gate sig_i; users: 1), hi = tf32(x')
+// (round to nearest), lo = tf32(x' - hi); row norm of x'; csig[row] = c * scale[row]
 // ---------------------------------------------------------------------------------------------
 __device__ __forceinline__ float to_tf32(float x) {
   uint32_t r;
@@ -478,14 +506,21 @@ __device__ __forceinline__ float to_tf32(float x) {
 // one half-warp per row (float4 per lane); norm_out[row] = ||row||_2 rounded up a little;
 // norm_max (nullable): max over rows via atomicMax on the bit pattern (non-negative floats)
 __global__ void __launch_bounds__(256)
-split_rows_kernel(const float *__restrict__ X, long long n, float *__restrict__ hi,
-                  float *__restrict__ lo, float *__restrict__ norm_out,
+split_rows_kernel(const float *__restrict__ X, long long n, const float *__restrict__ scale,
+                  float c, float *__restrict__ hi, float *__restrict__ lo,
+                  float *__restrict__ csig, float *__restrict__ norm_out,
                   unsigned int *__restrict__ norm_max) {
   const long long r = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 4;
   const int hl = threadIdx.x & 15;
   float ss = 0.f;
   if (r < n) {
-    const float4 v = reinterpret_cast<const float4 *>(X + r * kD)[hl];
+    float4 v = reinterpret_cast<const float4 *>(X + r * kD)[hl];
+    if (scale) {
+      const float sc = scale[r];
+      v.x = __fmul_rn(v.x, sc), v.y = __fmul_rn(v.y, sc), v.z = __fmul_rn(v.z, sc),
+      v.w = __fmul_rn(v.w, sc);
+      if (hl == 0) csig[r] = __fmul_rn(c, sc);
+    }
     float4 h, l;
     h.x = to_tf32(v.x), h.y = to_tf32(v.y), h.z = to_tf32(v.z), h.w = to_tf32(v.w);
     l.x = to_tf32(v.x - h.x), l.y = to_tf32(v.y - h.y), l.z = to_tf32(v.z - h.z),
@@ -503,46 +538,62 @@ split_rows_kernel(const float *__restrict__ X, long long n, float *__restrict__ 
   }
 }
 
-// thr[row] = (K-th largest tile maximum) - (eps_max + eps_filter + slack), one warp per row.
-// With y~ the tensor-core dot product and y the fp32 FMA chain:  |y~ - y| <= kappa * |u| * |i|
+// thr[row] = {filter threshold, batch-skip threshold}, one warp per row.
+// Lane l takes the maximum over the batches b = l (mod 32) that hold no train item of the row
+// (bitmap in shared memory built from the row's mask list).  The 32 lane maxima come from
+// disjoint batches, so K of them exceed the K-th largest lane maximum m_K: the exact K-th best
+// score of the row is >= m_K - eps.  With y~ the tensor-core dot product of the gate-scaled item
+// row and y the fp32 FMA chain:  |y~ - sig*y| <= kappa * |u| * |sig*i|
 //   kappa(NSPLIT=1) = 2^-9   (two tf32 roundings 2^-11 each, products exact, fp32 accumulation)
 //   kappa(NSPLIT=3) = 2^-15  (dropped lo*lo 2^-22, tf32 rounding of lo 2 x 2^-22, fp32 accumulation
-//                             of 192 products and of the 64-term reference chain ~2^-17)
-// and the two roundings of ((y - c) * sig_i) add at most 2^-22 * (|c| + |u||i|).
+//                             of 192 products, the 64-term reference chain and the gate pre-scale)
+// and the roundings of (acc - c*sig) versus ((y - c) * sig) add at most 2^-22 * (|c| + |u||i|)
+// per pass.  eps = eps(maxima pass) + eps(filter pass).
 __global__ void __launch_bounds__(256)
-row_threshold_kernel(const float *__restrict__ tilemax, int T, int n_itiles, int ld_tm, int K,
-                     const float *__restrict__ unorm, const unsigned int *__restrict__ inorm_max,
-                     float c, float kappa_sum, float *__restrict__ thr) {
-  const int lane = threadIdx.x & 31;
-  const int t = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+row_threshold_kernel(const float *__restrict__ bmax, int T, int n_batches, int ld_tm, int K,
+                     const int32_t *__restrict__ mask_rowptr, const int32_t *__restrict__ mask_col,
+                     int id_off, int n_items, const float *__restrict__ unorm,
+                     const unsigned int *__restrict__ inorm_max, float c, float kappa_sum,
+                     int bm_words, float2 *__restrict__ thr) {
+  extern __shared__ uint32_t s_bits[];  // [8 warps][bm_words]
+  const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
+  const int t = blockIdx.x * 8 + wib;
   if (t >= T) return;
-  const unsigned kmask = (K >= 32) ? 0xffffffffu : ((1u << K) - 1u);
-  const float *row = tilemax + (size_t)t * ld_tm;
-  float ls = -INFINITY;
-  int li = 0x7fffffff;
-  float ws = -INFINITY;
-  int wi = 0x7fffffff;
-  for (int c0 = 0; c0 < n_itiles; c0 += 32) {
-    const int cidx = c0 + lane;
-    const float s = cidx < n_itiles ? row[cidx] : -INFINITY;
-    unsigned m = __ballot_sync(0xffffffffu, cidx < n_itiles && score_better(s, cidx, ws, wi));
-    while (m) {
-      const int src = __ffs(m) - 1;
-      m &= m - 1;
-      const float cs = __shfl_sync(0xffffffffu, s, src);
-      const int cid = c0 + src;
-      if (!score_better(cs, cid, ws, wi)) continue;
-      score_list_insert(ls, li, cs, cid, lane, kmask, K);
-      ws = __shfl_sync(0xffffffffu, ls, K - 1);
-      wi = __shfl_sync(0xffffffffu, li, K - 1);
+  uint32_t *bits = s_bits + (size_t)wib * bm_words;
+  for (int i = lane; i < bm_words; i += 32) bits[i] = 0u;
+  __syncwarp();
+  if (mask_rowptr) {
+    const int lo = mask_rowptr[t], hi = mask_rowptr[t + 1];
+    for (int e = lo + lane; e < hi; e += 32) {
+      const int loc = mask_col[e] - id_off;
+      if (loc >= 0 && loc < n_items) atomicOr(&bits[loc >> 10], 1u << ((loc >> 5) & 31));
     }
+    __syncwarp();
   }
+  const float *row = bmax + (size_t)t * ld_tm;
+  float m = -INFINITY;
+  for (int b0 = 0; b0 < n_batches; b0 += 32) {
+    const int b = b0 + lane;
+    const uint32_t word = bits[b0 >> 5];
+    if (b < n_batches && !((word >> lane) & 1u)) m = fmaxf(m, row[b]);
+  }
+  // rank of this lane's maximum among the 32 (ties broken by lane) -> K-th largest
+  int rank = 0;
+#pragma unroll
+  for (int o = 0; o < 32; ++o) {
+    const float mo = __shfl_sync(0xffffffffu, m, o);
+    rank += (mo > m || (mo == m && o < lane)) ? 1 : 0;
+  }
+  const unsigned who = __ballot_sync(0xffffffffu, rank == K - 1);
+  const float mk = __shfl_sync(0xffffffffu, m, __ffs(who) - 1);
   if (lane == 0) {
-    float out = -INFINITY;
-    if (wi != 0x7fffffff && ws > -INFINITY) {
+    float2 out = make_float2(-INFINITY, -INFINITY);
+    if (mk > -INFINITY) {
       const float yb = unorm[t] * __uint_as_float(*inorm_max);
-      const float eps = kappa_sum * yb + 2.f * 4.76837158e-7f /*2^-21*/ * (fabsf(c) + yb);
-      out = ws - eps - 9.5367e-7f /*2^-20*/ * fabsf(ws);
+      const float eps = kappa_sum * yb + 9.5367431640625e-7f /*2^-20*/ * (fabsf(c) + yb);
+      out.x = mk - eps - 9.5367431640625e-7f * fabsf(mk);
+      out.y = out.x - eps;  // a batch can hold a filter-pass score >= thr.x only if its
+                            // maxima-pass maximum is >= thr.x - eps
     }
     thr[t] = out;
   }
@@ -673,7 +724,7 @@ static int make_map(CUtensorMap *m, const float *base, long long rows) {
 struct Plan {
   int TB;        // query rows per row block
   int n_itiles, n_chunks, tiles_per_chunk, ld_tm;
-  size_t off_uhi, off_ulo, off_ihi, off_ilo, off_unorm, off_misc, off_tilemax, off_thr, off_cand,
+  size_t off_uhi, off_ulo, off_ihi, off_ilo, off_csig, off_unorm, off_misc, off_tilemax, off_thr, off_cand,
       off_cnt, off_fbrows, off_exact, total;
   size_t exact_bytes;
 };
@@ -683,7 +734,7 @@ static size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
 static Plan make_plan(int T, long long n_items, int K) {
   Plan p;
   p.n_itiles = (int)((n_items + BN - 1) / BN);
-  p.ld_tm = (p.n_itiles + 31) / 32 * 32;
+  p.ld_tm = (4 * p.n_itiles + 31) / 32 * 32;  // 4 batch maxima per item tile
   // row block: tile maxima at most ~256 MiB
   long long tb = (256LL << 20) / (4LL * p.ld_tm);
   tb = tb / BM * BM;
@@ -718,12 +769,13 @@ static Plan make_plan(int T, long long n_items, int K) {
   p.off_ulo = take((size_t)p.TB * kD * 4);
   p.off_ihi = take((size_t)n_items * kD * 4);
   p.off_ilo = take((size_t)n_items * kD * 4);
+  p.off_csig = take((size_t)n_items * 4);
   p.off_unorm = take((size_t)p.TB * 4);
   p.off_misc = take(64);  // [0] item norm max (uint bits) [1] fb_count [2..3] cand_total (u64)
   p.off_tilemax = take((size_t)p.TB * p.ld_tm * 4);
-  p.off_thr = take((size_t)p.TB * 4);
-  p.off_cand = take((size_t)p.TB * p.n_chunks * kCap * 8);
-  p.off_cnt = take((size_t)p.TB * p.n_chunks * 4);
+  p.off_thr = take((size_t)p.TB * 8);
+  p.off_cand = take((size_t)p.TB * p.n_chunks * 2 * kCap * 8);
+  p.off_cnt = take((size_t)p.TB * p.n_chunks * 2 * 4);
   p.off_fbrows = take((size_t)p.TB * 4);
   p.exact_bytes = score_exact_workspace_bytes(p.TB, n_items, K);
   p.off_exact = take(p.exact_bytes);
@@ -731,12 +783,12 @@ static Plan make_plan(int T, long long n_items, int K) {
   return p;
 }
 
-static int g_nsplit_max = 1, g_nsplit_filter = 3;
+static int g_nsplit_max = 1, g_nsplit_filter = 1;
 
 template <int MODE, int NSPLIT>
 static int launch_pass(const CUtensorMap &uh, const CUtensorMap &ul, const CUtensorMap &ih,
                        const CUtensorMap &il, const TileParams &P, const float *sig_i,
-                       const int32_t *mrp, const int32_t *mcol, float *tilemax, const float *thr,
+                       const int32_t *mrp, const int32_t *mcol, float *tilemax, const float2 *thr,
                        uint2 *cand, int *cnt, cudaStream_t s) {
   static bool opted = false;
   if (!opted) {
@@ -782,9 +834,11 @@ extern "C" int macr_score_topk_tc(const float *Uq, int T, const float *It, int64
   MACR_CHECK_ARG(K >= 1 && K <= 32, "macr_score_topk_tc: K must be in [1,32] (got %d)", K);
   MACR_CHECK_ARG(T >= 0 && n_items >= 0, "macr_score_topk_tc: negative size");
   if (T == 0) return MACR_OK;
-  MACR_CHECK_ARG(n_items >= (int64_t)2 * K * BN && n_items < (1LL << 31) - BN,
-                 "macr_score_topk_tc: needs at least 2*K*%d items (got %lld): use macr_score_topk",
-                 BN, (long long)n_items);
+  MACR_CHECK_ARG(n_items >= 2048 && n_items < (1LL << 31) - BN,
+                 "macr_score_topk_tc: needs at least 2048 items (got %lld): use macr_score_topk",
+                 (long long)n_items);
+  MACR_CHECK_ARG((8LL * ((4 * ((n_items + BN - 1) / BN) + 31) / 32) * 4) <= 48 * 1024,
+                 "macr_score_topk_tc: more than ~1.5M items per shard: shard the catalogue");
   MACR_CHECK_ARG(Uq && It && sig_i && sig_u && out_ids && out_scores && ws,
                  "macr_score_topk_tc: null pointer");
   MACR_CHECK_ARG((reinterpret_cast<uintptr_t>(ws) & 1023) == 0,
@@ -800,7 +854,8 @@ extern "C" int macr_score_topk_tc(const float *Uq, int T, const float *It, int64
   float *unorm = reinterpret_cast<float *>(w + p.off_unorm);
   unsigned int *misc = reinterpret_cast<unsigned int *>(w + p.off_misc);
   float *tilemax = reinterpret_cast<float *>(w + p.off_tilemax);
-  float *thr = reinterpret_cast<float *>(w + p.off_thr);
+  float2 *thr = reinterpret_cast<float2 *>(w + p.off_thr);
+  float *csig = reinterpret_cast<float *>(w + p.off_csig);
   uint2 *cand = reinterpret_cast<uint2 *>(w + p.off_cand);
   int *cnt = reinterpret_cast<int *>(w + p.off_cnt);
   int32_t *fb_rows = reinterpret_cast<int32_t *>(w + p.off_fbrows);
@@ -808,8 +863,8 @@ extern "C" int macr_score_topk_tc(const float *Uq, int T, const float *It, int64
   unsigned long long *cand_total = reinterpret_cast<unsigned long long *>(misc + 2);
 
   MACR_CUDA(cudaMemsetAsync(misc, 0, 64, s));
-  split_rows_kernel<<<(unsigned)((n_items * 16 + 255) / 256), 256, 0, s>>>(It, n_items, ihi, ilo,
-                                                                           nullptr, misc);
+  split_rows_kernel<<<(unsigned)((n_items * 16 + 255) / 256), 256, 0, s>>>(
+      It, n_items, sig_i, c, ihi, ilo, csig, nullptr, misc);
   MACR_LAUNCH_CHECK();
   CUtensorMap mih, mil;
   int rc = make_map(&mih, ihi, n_items);
@@ -823,8 +878,8 @@ extern "C" int macr_score_topk_tc(const float *Uq, int T, const float *It, int64
     const int nb = T - t0 < p.TB ? T - t0 : p.TB;
     const float *Ub = Uq + (size_t)t0 * kD;
     const int32_t *mrp = mask_rowptr ? mask_rowptr + t0 : nullptr;
-    split_rows_kernel<<<(unsigned)(((long long)nb * 16 + 255) / 256), 256, 0, s>>>(Ub, nb, uhi, ulo,
-                                                                                  unorm, nullptr);
+    split_rows_kernel<<<(unsigned)(((long long)nb * 16 + 255) / 256), 256, 0, s>>>(
+        Ub, nb, nullptr, 0.f, uhi, ulo, nullptr, unorm, nullptr);
     MACR_LAUNCH_CHECK();
     CUtensorMap muh, mul;
     rc = make_map(&muh, uhi, nb);
@@ -838,29 +893,30 @@ extern "C" int macr_score_topk_tc(const float *Uq, int T, const float *It, int64
     P.n_itiles = p.n_itiles;
     P.n_chunks = p.n_chunks;
     P.tiles_per_chunk = p.tiles_per_chunk;
-    P.c = c;
     P.id_off = item_id_offset;
     P.ld_tm = p.ld_tm;
     if (g_nsplit_max == 1)
-      rc = launch_pass<MODE_MAX, 1>(muh, mul, mih, mil, P, sig_i, mrp, mask_col, tilemax, nullptr,
+      rc = launch_pass<MODE_MAX, 1>(muh, mul, mih, mil, P, csig, mrp, mask_col, tilemax, nullptr,
                                     nullptr, nullptr, s);
     else
-      rc = launch_pass<MODE_MAX, 3>(muh, mul, mih, mil, P, sig_i, mrp, mask_col, tilemax, nullptr,
+      rc = launch_pass<MODE_MAX, 3>(muh, mul, mih, mil, P, csig, mrp, mask_col, tilemax, nullptr,
                                     nullptr, nullptr, s);
     if (rc) return rc;
-    row_threshold_kernel<<<(nb + 7) / 8, 256, 0, s>>>(tilemax, nb, p.n_itiles, p.ld_tm, K, unorm,
-                                                      misc, c, kappa_sum, thr);
+    const int n_batches = 4 * p.n_itiles, bm_words = (n_batches + 31) / 32;
+    row_threshold_kernel<<<(nb + 7) / 8, 256, (size_t)8 * bm_words * 4, s>>>(
+        tilemax, nb, n_batches, p.ld_tm, K, mrp, mask_col, item_id_offset, (int)n_items, unorm,
+        misc, c, kappa_sum, bm_words, thr);
     MACR_LAUNCH_CHECK();
     if (g_nsplit_filter == 1)
-      rc = launch_pass<MODE_FILTER, 1>(muh, mul, mih, mil, P, sig_i, mrp, mask_col, nullptr, thr,
+      rc = launch_pass<MODE_FILTER, 1>(muh, mul, mih, mil, P, csig, mrp, mask_col, tilemax, thr,
                                        cand, cnt, s);
     else
-      rc = launch_pass<MODE_FILTER, 3>(muh, mul, mih, mil, P, sig_i, mrp, mask_col, nullptr, thr,
+      rc = launch_pass<MODE_FILTER, 3>(muh, mul, mih, mil, P, csig, mrp, mask_col, tilemax, thr,
                                        cand, cnt, s);
     if (rc) return rc;
     MACR_CUDA(cudaMemsetAsync(fb_count, 0, sizeof(int), s));
     rerank_kernel<<<(nb + 7) / 8, 256, 0, s>>>(Ub, nb, It, sig_i, sig_u + t0, c, item_id_offset,
-                                               cand, cnt, p.n_chunks, K,
+                                               cand, cnt, 2 * p.n_chunks, K,
                                                out_ids + (size_t)t0 * K, out_scores + (size_t)t0 * K,
                                                fb_rows, fb_count, cand_total);
     MACR_LAUNCH_CHECK();

@@ -133,7 +133,7 @@ def gather_rows(table, ids):
     return out
 
 
-TC_MIN_TILES_PER_K = 2  # the tcgen05 path needs n_items >= 2*K*128 (include/macr_b200.h)
+TC_MIN_ITEMS = 4096  # smaller catalogues go to the exact fp32 kernel (the tcgen05 path needs >= 2048)
 
 
 def score_topk_tc(Uq, It, sig_i, sig_u, c, mask_rowptr, mask_col, K, item_id_offset=0, stats=None):
@@ -155,9 +155,9 @@ def score_topk_tc(Uq, It, sig_i, sig_u, c, mask_rowptr, mask_col, K, item_id_off
 
 def score_topk(Uq, It, sig_i, sig_u, c, mask_rowptr, mask_col, K, item_id_offset=0):
     """Fused score + mask + top-K. -> (ids [T,K] int32 global ids, scores [T,K] fp32).
-    Catalogues of at least 2*K tiles of 128 items go to the tcgen05 path, smaller ones to the
-    exact fp32 kernel; both give the same bits."""
-    if It.shape[0] >= TC_MIN_TILES_PER_K * K * 128 and K <= 32 and Uq.shape[0] > 0:
+    Catalogues of at least TC_MIN_ITEMS items go to the tcgen05 path, smaller ones to the exact
+    fp32 kernel; both give the same bits."""
+    if It.shape[0] >= TC_MIN_ITEMS and K <= 32 and Uq.shape[0] > 0:
         return score_topk_tc(Uq, It, sig_i, sig_u, c, mask_rowptr, mask_col, K, item_id_offset)
     return score_topk_exact(Uq, It, sig_i, sig_u, c, mask_rowptr, mask_col, K, item_id_offset)
 
