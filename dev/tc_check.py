@@ -20,7 +20,6 @@ def run(T_users, n_items, K, c, mask_deg, splits, scale=10.0, seed=0, time_it=Fa
         a, b = lists_to_csr(lists)
         mrp, mcol = torch.from_numpy(a).to(dev), torch.from_numpy(b).to(dev)
     ei, es = ops.score_topk_exact(dU, dI, si, su, c, mrp, mcol, K)
-    lib().macr_score_tc_set_splits(*splits)
     stats = torch.zeros(2, dtype=torch.int64, device=dev)
     ti, ts = ops.score_topk_tc(dU, dI, si, su, c, mrp, mcol, K, stats=stats)
     torch.cuda.synchronize()
@@ -94,7 +93,6 @@ def run_special():
     dU, dI = torch.from_numpy(U).to(dev), torch.from_numpy(I).to(dev)
     si, su = ops.score_gates(dI, torch.from_numpy(w).to(dev)), ops.score_gates(dU, torch.from_numpy(wu).to(dev))
     for sp in ((1, 1), (1, 3), (3, 3)):
-        lib().macr_score_tc_set_splits(*sp)
         ei, es = ops.score_topk_exact(dU, dI, si, su, 40.0, None, None, K)
         st = torch.zeros(2, dtype=torch.int64, device=dev)
         ti, ts = ops.score_topk_tc(dU, dI, si, su, 40.0, None, None, K, stats=st)
@@ -102,7 +100,6 @@ def run_special():
         print(f"xavier-init scale=1 splits={sp}:", "ok" if good else "MISMATCH", "fallback", st[0].item(),
               f"cand/row {st[1].item() / max(1, 300 - st[0].item()):.1f}", flush=True)
         ok &= good
-    lib().macr_score_tc_set_splits(1, 1)
     return ok
 
 

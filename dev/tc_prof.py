@@ -16,7 +16,10 @@ dev = torch.device("cuda")
 dU, dI = torch.from_numpy(U).to(dev), torch.from_numpy(I).to(dev)
 si, su = ops.score_gates(dI, torch.from_numpy(w).to(dev)), ops.score_gates(dU, torch.from_numpy(wu).to(dev))
 mrp, mcol = torch.from_numpy(rowptr).to(dev), torch.from_numpy(col).to(dev)
-lib().macr_score_tc_set_splits(*splits)
+import ctypes
+dbg = int(os.environ.get("TC_DBG", "0"))
+h = ctypes.CDLL(lib()._name)
+h.macr_score_tc_debug(dbg)
 for _ in range(3):
     ops.score_topk_tc(dU, dI, si, su, c, mrp, mcol, K)
 torch.cuda.synchronize()

@@ -254,9 +254,7 @@ int macr_score_topk(const float *Uq, int T, const float *It, int64_t n_items, in
  * re-rank of the ~1.5 K candidates per row; rows whose candidate list overflows are re-done by
  * the exact kernel (macr_b200/csrc/score_tc.cu).  Needs 2048 <= n_items <~ 1.5 M per call
  * (smaller catalogues: macr_score_topk; larger: shard).  ws must be 1024-byte aligned.  stats (nullable, device int64[2]) is
- * incremented by {rows re-done by the exact kernel, candidates re-ranked}.
- * macr_score_tc_set_splits: tf32 operand splits (1 = hi*hi, 3 = hi*hi+hi*lo+lo*hi ~ fp32) of
- * the maxima pass and of the filter pass; results are exact for every setting. */
+ * incremented by {rows re-done by the exact kernel, candidates re-ranked}. */
 size_t macr_score_topk_tc_workspace_bytes(int T, int64_t n_items, int K);
 int macr_score_topk_tc(const float *Uq, int T, const float *It, int64_t n_items, int d,
                        const float *sig_i, const float *sig_u, float c,
@@ -264,7 +262,6 @@ int macr_score_topk_tc(const float *Uq, int T, const float *It, int64_t n_items,
                        int K, int32_t item_id_offset,
                        int32_t *out_ids, float *out_scores,
                        void *ws, size_t ws_bytes, int64_t *stats, macr_stream_t stream);
-int macr_score_tc_set_splits(int nsplit_max, int nsplit_filter);
 /* dense score matrix, the literal rubi_ratings_both fetch ([T][n_items] fp32, no mask) */
 int macr_score_matrix(const float *Uq, int T, const float *It, int64_t n_items, int d,
                       const float *sig_i, const float *sig_u, float c,

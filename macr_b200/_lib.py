@@ -77,7 +77,6 @@ PROTOTYPES = {
     "macr_score_topk_tc_workspace_bytes": (sz, [i32, i64, i32]),
     "macr_score_topk_tc": (i32, [vp, i32, vp, i64, i32, vp, vp, f32, vp, vp, i32, C.c_int32, vp, vp,
                                  vp, sz, vp, vp]),
-    "macr_score_tc_set_splits": (i32, [i32, i32]),
     "macr_score_matrix": (i32, [vp, i32, vp, i64, i32, vp, vp, f32, vp, vp]),
     "macr_topk_merge": (i32, [vp, vp, i32, i32, i32, vp, vp, vp]),
     "macr_topk_rows": (i32, [vp, i32, i32, i32, vp, vp]),

@@ -1,4 +1,5 @@
-// score_tc.cu -- K7+K8 on the 5th-generation tensor cores: TMA-fed tcgen05 (kind::tf32) tiles with
+// score_tc.cu -- K7+K8 on the 5th-generation tensor cores: TMA-fed tcgen05 (kind::f16, bf16 operands,
+// fp32 accumulation; kind::tf32 with -DMACR_TC_TF32) tiles with
 // the accumulator in TMEM and the counterfactual correction ((y - c) * sig_i) fused into the
 // TMEM->register epilogue, followed by an EXACT fp32 re-rank, so the emitted ids and scores are
 // bit-identical to the fp32 path of score.cu (and to the CPU oracle).
@@ -23,18 +24,22 @@
 //   fallback     a row whose candidate list overflowed (degenerate score distributions) is
 //                re-done by the exact fp32 kernel (score.cu) -- never silently wrong.
 // eps_* are rigorous bounds of |approximate - exact| (see row_threshold_kernel).  Operands are
-// split x = hi + lo (hi = tf32(x), lo = tf32(x - hi)); NSPLIT=3 accumulates hi*hi + hi*lo + lo*hi
-// (~fp32 accuracy), NSPLIT=1 only hi*hi.
+// rounded once to bf16 (measured on B200: a 128x128 SS-mode MMA instruction takes ~124 cycles
+// whatever the kind, so bf16's K=16 per instruction halves the tensor time of tf32's K=8, and
+// it halves the TMA bytes); a looser bound only means more candidates, never a wrong id.
 //
-// Kernel anatomy (one CTA per SM, persistent over (user tile, item chunk) work items):
-//   warp 0      TMA producer   cp.async.bulk.tensor.2d, 128B-swizzled K-major boxes of 128 rows x 32 fp32
-//   warp 1      MMA issuer     tcgen05.mma.cta_group::1.kind::tf32, M=128 N=128 K=8, D in TMEM
-//                              (2 accumulator buffers x 128 columns); also owns TMEM alloc/dealloc
-//   warps 2..9  epilogue       two warpgroups, warpgroup g owns TMEM buffer g (tiles alternate):
+// Kernel anatomy (one CTA per SM, persistent over (256-user tile, item chunk) work items):
+//   warp 0      TMA producer   cp.async.bulk.tensor.2d, 128B-swizzled K-major boxes of 128 rows x 128 B;
+//                              two 128-row user tiles stay resident, item tiles stream through a
+//                              ring (each item tile is read from L2 once per 256 users)
+//   warp 1      MMA issuer     tcgen05.mma.cta_group::1.kind::f16, M=128 N=128 K=16, D in TMEM:
+//                              4 accumulator buffers x 128 columns (user tile g, item-tile parity);
+//                              also owns TMEM alloc/dealloc
+//   warps 2..9  epilogue       two warpgroups, warpgroup g owns user tile g and TMEM buffers 2g, 2g+1:
 //                              tcgen05.ld.32x32b.x32 (thread = user row), fused correction,
 //                              batch maxima / threshold filter, train-item mask from a per-row
 //                              cursor into the sorted CSR mask
-// mbarrier pipelines: user tile full/empty, item stages full/empty, TMEM full/empty.
+// mbarrier pipelines: user tiles full/empty, item stages full/empty, TMEM full/empty.
 #include <cuda.h>
 #include <math.h>
 
@@ -46,23 +51,25 @@ namespace tc {
 
 constexpr int BM = 128;              // user rows per tile (UMMA M, TMEM lanes)
 constexpr int BN = 128;              // items per tile (UMMA N, TMEM columns per buffer)
-constexpr int KB = 32;               // fp32 per 128-byte swizzle row
-constexpr int NKB = kD / KB;         // K blocks per operand tile (2)
+#ifdef MACR_TC_TF32
+constexpr bool kBf16 = false;
+typedef float oper_t;                // operands rounded to tf32, stored in fp32 containers
+#else
+constexpr bool kBf16 = true;
+typedef unsigned short oper_t;       // operands rounded to bf16
+#endif
+constexpr int KB = 128 / (int)sizeof(oper_t);  // elements per 128-byte swizzle row
+constexpr int NKB = kD / KB;         // K blocks per operand tile (bf16: 1, tf32: 2)
 constexpr int KBLK_BYTES = BM * 128; // one K block of one operand tile: 128 rows x 128 B
-constexpr int OPER_BYTES = NKB * KBLK_BYTES;  // 32 KiB: a 128 x 64 fp32 operand tile
-constexpr int kCap = 32;             // candidate slots per (row, item chunk, epilogue warpgroup)
-constexpr int kThreads = 320;           // producer, MMA issuer, 2 epilogue warpgroups
-constexpr int kTmemCols = 256;
+constexpr int OPER_BYTES = NKB * KBLK_BYTES;  // a 128 x 64 operand tile (bf16: 16 KiB)
+constexpr int kCap = 64;             // candidate slots per (row, item chunk)
+constexpr int kThreads = 320;        // producer, MMA issuer, 2 epilogue warpgroups
+constexpr int kTmemCols = 512;       // 4 accumulator buffers x 128 columns
+constexpr int UT = 2;                // user tiles per CTA (one per epilogue warpgroup)
+constexpr int STAGES = kBf16 ? 8 : 4; // item-tile ring (128 KiB)
+constexpr int A_BYTES = UT * OPER_BYTES;
+constexpr int SMEM_BYTES = 1024 /*align*/ + A_BYTES + STAGES * OPER_BYTES;
 constexpr int MODE_MAX = 0, MODE_FILTER = 1;
-
-template <int NSPLIT>
-struct Cfg {
-  static constexpr int PARTS = NSPLIT == 1 ? 1 : 2;             // hi (, lo)
-  static constexpr int STAGES = NSPLIT == 1 ? 4 : 2;            // item-tile ring
-  static constexpr int A_BYTES = PARTS * OPER_BYTES;
-  static constexpr int STAGE_BYTES = PARTS * OPER_BYTES;
-  static constexpr int SMEM_BYTES = 1024 /*align*/ + A_BYTES + STAGES * STAGE_BYTES + 2048;
-};
 
 // ---- PTX wrappers ----------------------------------------------------------------------------
 __device__ __forceinline__ uint32_t smem_u32(const void *p) {
@@ -116,12 +123,16 @@ __device__ __forceinline__ void tc_commit(uint32_t bar) {
                : "memory");
 }
 // D[tmem] (+)= A[smem] * B[smem]^T, tf32 inputs, fp32 accumulate
-__device__ __forceinline__ void tc_mma_tf32(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc,
-                                            uint32_t idesc, uint32_t accumulate) {
+__device__ __forceinline__ void tc_mma(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc,
+                                       uint32_t idesc, uint32_t accumulate) {
   asm volatile(
       "{\n\t.reg .pred p;\n\t"
       "setp.ne.b32 p, %4, 0;\n\t"
+#ifdef MACR_TC_TF32
       "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}"
+#else
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+#endif
       ::"r"(d_tmem), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
       : "memory");
 }
@@ -135,8 +146,10 @@ __device__ __forceinline__ uint64_t umma_desc(uint32_t smem_addr) {
   d |= (uint64_t)2 << 61;            // SWIZZLE_128B
   return d;
 }
-// kind::tf32, fp32 accumulate, A and B K-major, M=128, N=128
-constexpr uint32_t kIdesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(BN >> 3) << 17) |
+// fp32 accumulate (bit 4), A/B format (bits 7-9 / 10-12: 1 = bf16, 2 = tf32), both K-major,
+// N >> 3 at bit 17, M >> 4 at bit 24
+constexpr uint32_t kFmt = kBf16 ? 1u : 2u;
+constexpr uint32_t kIdesc = (1u << 4) | (kFmt << 7) | (kFmt << 10) | ((uint32_t)(BN >> 3) << 17) |
                             ((uint32_t)(BM >> 4) << 24);
 
 #define MACR_R32(v)                                                                              \
@@ -170,9 +183,13 @@ __device__ __forceinline__ void tmem_ld_wait(uint32_t (&v)[32]) {
 struct TileParams {
   int T;            // query rows in this row block
   int n_items;      // items in this shard
-  int n_utiles, n_itiles, n_chunks, tiles_per_chunk;
+  int n_utiles;     // 256-row user tile pairs
+  int n_itiles, n_chunks, tiles_per_chunk;
   int id_off;       // global id of local item 0 (mask_col holds global ids)
   int ld_tm;        // row pitch of the batch maxima (floats), 4 per item tile
+  int dbg;          // developer timing experiments (0 = product path): bit0 skip the TMEM loads,
+                    // bit1 skip the epilogue arithmetic, bit2 skip the MMAs (results are then
+                    // meaningless)
 };
 
 // max over 32 accumulator columns of (acc - c*sig): 4 independent chains
@@ -197,27 +214,26 @@ __device__ __forceinline__ float batch_max(const uint32_t (&v)[32], const float 
 //                the threshold kernel leaves batches holding a train item of the row out)
 //   MODE_FILTER  batches with bmax >= thr.y are re-read; unmasked scores >= thr.x are appended
 // ---------------------------------------------------------------------------------------------
-template <int MODE, int NSPLIT>
+template <int MODE>
 __global__ void __launch_bounds__(kThreads, 1)
-score_tc_kernel(const __grid_constant__ CUtensorMap tmUhi, const __grid_constant__ CUtensorMap tmUlo,
-                const __grid_constant__ CUtensorMap tmIhi, const __grid_constant__ CUtensorMap tmIlo,
+score_tc_kernel(const __grid_constant__ CUtensorMap tmU, const __grid_constant__ CUtensorMap tmI,
                 const TileParams P, const float *__restrict__ csig,
                 const int32_t *__restrict__ mask_rowptr, const int32_t *__restrict__ mask_col,
                 float *__restrict__ bmax, const float2 *__restrict__ thr,
                 uint2 *__restrict__ cand, int *__restrict__ cand_cnt) {
-  using C = Cfg<NSPLIT>;
   extern __shared__ unsigned char smem_raw[];
   // 1024-byte alignment: the 128B swizzle pattern repeats every 8 rows x 128 B
   unsigned char *smem = reinterpret_cast<unsigned char *>(
       (reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
-  unsigned char *sA = smem;                 // [PARTS][NKB][128 x 128 B]
-  unsigned char *sB = smem + C::A_BYTES;    // [STAGES][PARTS][NKB][128 x 128 B]
-  unsigned char *tail = sB + C::STAGES * C::STAGE_BYTES;
-  uint64_t *bars = reinterpret_cast<uint64_t *>(tail);  // see indices below
-  float *sCs = reinterpret_cast<float *>(tail + 256);   // [2 warpgroups][2][BN]  c*sig of the tile
-  uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(tail + 256 + 4 * BN * 4);
+  unsigned char *sA = smem;              // [UT][NKB][128 x 128 B]
+  unsigned char *sB = smem + A_BYTES;    // [STAGES][NKB][128 x 128 B]
+  // small arrays are static so that their accesses stay LDS/STS (pointers derived from the
+  // re-aligned dynamic buffer decay to generic loads, which do not broadcast)
+  __shared__ __align__(16) float sCs[4 * BN];  // [2 warpgroups][2][BN]  c*sig of the tile
+  __shared__ __align__(8) uint64_t bars[32];   // see indices below
+  __shared__ uint32_t tmem_slot[1];
 
-  enum { A_FULL = 0, A_EMPTY = 1, TM_FULL = 2, TM_EMPTY = 4, B_FULL = 6, B_EMPTY = 6 + C::STAGES };
+  enum { A_FULL = 0, A_EMPTY = 1, TM_FULL = 2, TM_EMPTY = 6, B_FULL = 10, B_EMPTY = 10 + STAGES };
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const uint32_t bar0 = smem_u32(bars);
   auto BAR = [&](int i) { return bar0 + 8u * (uint32_t)i; };
@@ -225,17 +241,17 @@ score_tc_kernel(const __grid_constant__ CUtensorMap tmUhi, const __grid_constant
   if (threadIdx.x == 0) {
     mbar_init(BAR(A_FULL), 1);
     mbar_init(BAR(A_EMPTY), 1);
-    for (int b = 0; b < 2; ++b) {
+    for (int b = 0; b < 4; ++b) {
       mbar_init(BAR(TM_FULL + b), 1);
       mbar_init(BAR(TM_EMPTY + b), 4);  // one arrive per warp of the owning epilogue warpgroup
     }
-    for (int s = 0; s < C::STAGES; ++s) {
+    for (int s = 0; s < STAGES; ++s) {
       mbar_init(BAR(B_FULL + s), 1);
       mbar_init(BAR(B_EMPTY + s), 1);
     }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
-  if (warp == 1) {  // TMEM: 2 accumulator buffers of 128 columns
+  if (warp == 1) {  // TMEM: all 512 columns (one CTA per SM)
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(
                      smem_u32(tmem_slot)),
                  "r"(kTmemCols)
@@ -245,14 +261,12 @@ score_tc_kernel(const __grid_constant__ CUtensorMap tmUhi, const __grid_constant
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
-  const uint32_t tmem_base = *tmem_slot;
+  const uint32_t tmem_base = tmem_slot[0];
   const int n_work = P.n_utiles * P.n_chunks;
 
   if (warp == 0) {
     // =============================== TMA producer ===============================
     if (lane == 0) {
-      const CUtensorMap *mapsU[2] = {&tmUhi, &tmUlo};
-      const CUtensorMap *mapsI[2] = {&tmIhi, &tmIlo};
       int stage = 0;
       uint32_t phase = 0, a_phase = 0;
       for (int w = blockIdx.x; w < n_work; w += gridDim.x) {
@@ -260,21 +274,19 @@ score_tc_kernel(const __grid_constant__ CUtensorMap tmUhi, const __grid_constant
         const int t_begin = ch * P.tiles_per_chunk;
         const int t_end = min(P.n_itiles, t_begin + P.tiles_per_chunk);
         mbar_wait(BAR(A_EMPTY), a_phase ^ 1);
-        mbar_expect_tx(BAR(A_FULL), C::A_BYTES);
-        for (int p = 0; p < C::PARTS; ++p)
+        mbar_expect_tx(BAR(A_FULL), A_BYTES);
+        for (int a = 0; a < UT; ++a)
           for (int kb = 0; kb < NKB; ++kb)
-            tma_load_2d(smem_u32(sA + (p * NKB + kb) * KBLK_BYTES), mapsU[p], BAR(A_FULL), kb * KB,
-                        ut * BM);
+            tma_load_2d(smem_u32(sA + (a * NKB + kb) * KBLK_BYTES), &tmU, BAR(A_FULL), kb * KB,
+                        (ut * UT + a) * BM);
         a_phase ^= 1;
         for (int t = t_begin; t < t_end; ++t) {
           mbar_wait(BAR(B_EMPTY + stage), phase ^ 1);
-          mbar_expect_tx(BAR(B_FULL + stage), C::STAGE_BYTES);
-          unsigned char *dst = sB + stage * C::STAGE_BYTES;
-          for (int p = 0; p < C::PARTS; ++p)
-            for (int kb = 0; kb < NKB; ++kb)
-              tma_load_2d(smem_u32(dst + (p * NKB + kb) * KBLK_BYTES), mapsI[p],
-                          BAR(B_FULL + stage), kb * KB, t * BN);
-          if (++stage == C::STAGES) {
+          mbar_expect_tx(BAR(B_FULL + stage), OPER_BYTES);
+          unsigned char *dst = sB + stage * OPER_BYTES;
+          for (int kb = 0; kb < NKB; ++kb)
+            tma_load_2d(smem_u32(dst + kb * KBLK_BYTES), &tmI, BAR(B_FULL + stage), kb * KB, t * BN);
+          if (++stage == STAGES) {
             stage = 0;
             phase ^= 1;
           }
@@ -286,7 +298,7 @@ score_tc_kernel(const __grid_constant__ CUtensorMap tmUhi, const __grid_constant
     if (lane == 0) {
       int stage = 0;
       uint32_t phase = 0, a_phase = 0;
-      uint32_t n = 0;  // running tile counter -> TMEM buffer ring
+      uint32_t n = 0;  // running tile counter -> TMEM buffer parity
       const uint32_t a_addr = smem_u32(sA);
       for (int w = blockIdx.x; w < n_work; w += gridDim.x) {
         const int ut = w / P.n_chunks, ch = w - ut * P.n_chunks;
@@ -295,36 +307,28 @@ score_tc_kernel(const __grid_constant__ CUtensorMap tmUhi, const __grid_constant
         mbar_wait(BAR(A_FULL), a_phase);
         a_phase ^= 1;
         for (int t = t_begin; t < t_end; ++t, ++n) {
-          const uint32_t buf = n & 1;
-          mbar_wait(BAR(TM_EMPTY + buf), ((n >> 1) & 1) ^ 1);
           mbar_wait(BAR(B_FULL + stage), phase);
-          tc_fence_after();
-          const uint32_t b_addr = smem_u32(sB + stage * C::STAGE_BYTES);
-          const uint32_t d_tmem = tmem_base + buf * BN;
-          uint32_t acc = 0;
-          // (A part, B part): lo*hi, hi*lo, then hi*hi
-          constexpr int NP = NSPLIT == 1 ? 1 : 3;
-          const int pa[3] = {NSPLIT == 1 ? 0 : 1, 0, 0};
-          const int pb[3] = {0, 1, 0};
+          const uint32_t b_addr = smem_u32(sB + stage * OPER_BYTES);
 #pragma unroll
-          for (int sp = 0; sp < NP; ++sp) {
+          for (int a = 0; a < UT; ++a) {
+            const uint32_t buf = a * 2 + (n & 1);
+            mbar_wait(BAR(TM_EMPTY + buf), ((n >> 1) & 1) ^ 1);
+            tc_fence_after();
+            const uint32_t d_tmem = tmem_base + buf * BN;
 #pragma unroll
             for (int kb = 0; kb < NKB; ++kb) {
 #pragma unroll
-              for (int ks = 0; ks < KB / 8; ++ks) {
-                const uint64_t ad =
-                    umma_desc(a_addr + (pa[sp] * NKB + kb) * KBLK_BYTES + ks * 32);
-                const uint64_t bd =
-                    umma_desc(b_addr + (pb[sp] * NKB + kb) * KBLK_BYTES + ks * 32);
-                tc_mma_tf32(d_tmem, ad, bd, kIdesc, acc);
-                acc = 1;
+              for (int ks = 0; ks < 4; ++ks) {  // 32-byte K steps inside the 128-byte row
+                const uint64_t ad = umma_desc(a_addr + (a * NKB + kb) * KBLK_BYTES + ks * 32);
+                const uint64_t bd = umma_desc(b_addr + kb * KBLK_BYTES + ks * 32);
+                if (!(P.dbg & 4)) tc_mma(d_tmem, ad, bd, kIdesc, (kb | ks) ? 1u : 0u);
               }
             }
+            tc_commit(BAR(TM_FULL + buf));  // accumulator ready for warpgroup a
           }
-          tc_commit(BAR(B_EMPTY + stage));   // item stage may be refilled
-          tc_commit(BAR(TM_FULL + buf));     // accumulator ready for the epilogue
+          tc_commit(BAR(B_EMPTY + stage));  // item stage may be refilled
           if (t == t_end - 1) tc_commit(BAR(A_EMPTY));
-          if (++stage == C::STAGES) {
+          if (++stage == STAGES) {
             stage = 0;
             phase ^= 1;
           }
@@ -332,18 +336,18 @@ score_tc_kernel(const __grid_constant__ CUtensorMap tmUhi, const __grid_constant
       }
     }
   } else {
-    // ============ epilogue: 2 warpgroups of 128 threads, warpgroup g owns TMEM buffer g ============
-    const int g = (warp - 2) >> 2;          // warpgroup: tiles with (n & 1) == g
+    // ===== epilogue: 2 warpgroups of 128 threads, warpgroup g owns user tile g of the pair =====
+    const int g = (warp - 2) >> 2;          // warpgroup
     const int q = warp & 3;                 // TMEM lane quarter this warp may read
     const int r_in = q * 32 + lane;         // row inside the user tile
     const int te = (threadIdx.x - 64) & 127;
-    const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + g * BN;
+    const uint32_t taddr0 = tmem_base + ((uint32_t)(q * 32) << 16) + (g * 2) * BN;
     uint32_t n = 0;
     for (int w = blockIdx.x; w < n_work; w += gridDim.x) {
       const int ut = w / P.n_chunks, ch = w - ut * P.n_chunks;
       const int t_begin = ch * P.tiles_per_chunk;
       const int t_end = min(P.n_itiles, t_begin + P.tiles_per_chunk);
-      const int row = ut * BM + r_in;
+      const int row = (ut * UT + g) * BM + r_in;
       const bool valid = row < P.T;
       int mptr = 0, mend = 0, nxt = 0x7fffffff, nxt2 = 0x7fffffff;
       float2 th = make_float2(INFINITY, INFINITY);
@@ -366,29 +370,47 @@ score_tc_kernel(const __grid_constant__ CUtensorMap tmUhi, const __grid_constant
           nxt2 = mptr + 1 < mend ? mask_col[mptr + 1] : 0x7fffffff;
         }
         th = thr[row];
-        my_cand = cand + (((size_t)row * P.n_chunks + ch) * 2 + g) * kCap;  // one list per warpgroup
+        my_cand = cand + ((size_t)row * P.n_chunks + ch) * kCap;
       }
-      // c*sig of column te of this warpgroup's next tile (prefetched one tile ahead);
-      // +inf beyond the catalogue, so those columns score -inf
-      int t_mine = t_begin + ((g ^ (int)n) & 1);
+      // c*sig of column te of the next tile (prefetched one tile ahead); +inf beyond the
+      // catalogue, so those columns score -inf
       float cs_next = INFINITY;
-      if (t_mine < t_end && t_mine * BN + te < P.n_items) cs_next = csig[t_mine * BN + te];
+      if (t_begin * BN + te < P.n_items) cs_next = csig[t_begin * BN + te];
 
       for (int t = t_begin; t < t_end; ++t, ++n) {
-        if ((int)(n & 1) != g) continue;
         // double-buffered by tile parity: one barrier per tile then orders the writes of tile
         // k+2 after every read of tile k
-        float *cs = sCs + (g * 2 + ((n >> 1) & 1)) * BN;
+        float *cs = sCs + (g * 2 + (n & 1)) * BN;
         cs[te] = cs_next;
         cs_next = INFINITY;
-        if (t + 2 < t_end && (t + 2) * BN + te < P.n_items) cs_next = csig[(t + 2) * BN + te];
+        if (t + 1 < t_end && (t + 1) * BN + te < P.n_items) cs_next = csig[(t + 1) * BN + te];
         asm volatile("bar.sync %0, 128;" ::"r"(1 + g) : "memory");
         const uint32_t full_parity = (n >> 1) & 1;
+        const int buf = g * 2 + (int)(n & 1);
+        const uint32_t taddr = taddr0 + (n & 1) * BN;
         uint32_t va[32], vb[32];
         if (MODE == MODE_MAX) {
-          mbar_wait(BAR(TM_FULL + g), full_parity);
+          mbar_wait(BAR(TM_FULL + buf), full_parity);
           tc_fence_after();
           __syncwarp();
+          if (P.dbg) {  // timing experiments only
+#pragma unroll
+            for (int j = 0; j < 32; ++j) va[j] = vb[j] = j + lane;
+            float acc = 0.f;
+            for (int cb = 0; cb < 4; ++cb) {
+              if (!(P.dbg & 1)) {
+                tmem_ld32(taddr + cb * 32, va);
+                tmem_ld_wait(va);
+              }
+              if (!(P.dbg & 2)) acc += batch_max(va, cs + cb * 32);
+              else acc += __uint_as_float(va[cb]);
+            }
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(BAR(TM_EMPTY + buf));
+            if (valid) bmax[(size_t)row * P.ld_tm + 4 * t] = acc;
+            continue;
+          }
           tmem_ld32(taddr + 0, va);
           tmem_ld_wait(va);
           tmem_ld32(taddr + 32, vb);
@@ -403,7 +425,7 @@ score_tc_kernel(const __grid_constant__ CUtensorMap tmUhi, const __grid_constant
           // all TMEM reads of this buffer are complete: hand it back to the MMA warp
           tc_fence_before();
           __syncwarp();
-          if (lane == 0) mbar_arrive(BAR(TM_EMPTY + g));
+          if (lane == 0) mbar_arrive(BAR(TM_EMPTY + buf));
           const float b3 = batch_max(vb, cs + 96);
           if (valid)
             *reinterpret_cast<float4 *>(bmax + (size_t)row * P.ld_tm + 4 * t) =
@@ -438,7 +460,7 @@ score_tc_kernel(const __grid_constant__ CUtensorMap tmUhi, const __grid_constant
           float4 bm = make_float4(-INFINITY, -INFINITY, -INFINITY, -INFINITY);
           if (valid) bm = *reinterpret_cast<const float4 *>(bmax + (size_t)row * P.ld_tm + 4 * t);
           const float bmv[4] = {bm.x, bm.y, bm.z, bm.w};
-          mbar_wait(BAR(TM_FULL + g), full_parity);
+          mbar_wait(BAR(TM_FULL + buf), full_parity);
           tc_fence_after();
 #pragma unroll
           for (int cb = 0; cb < 4; ++cb) {
@@ -476,10 +498,10 @@ score_tc_kernel(const __grid_constant__ CUtensorMap tmUhi, const __grid_constant
           }
           tc_fence_before();
           __syncwarp();
-          if (lane == 0) mbar_arrive(BAR(TM_EMPTY + g));
+          if (lane == 0) mbar_arrive(BAR(TM_EMPTY + buf));
         }
       }
-      if (MODE == MODE_FILTER && valid) cand_cnt[((size_t)row * P.n_chunks + ch) * 2 + g] = cnt;
+      if (MODE == MODE_FILTER && valid) cand_cnt[(size_t)row * P.n_chunks + ch] = cnt;
     }
   }
 
@@ -494,21 +516,26 @@ score_tc_kernel(const __grid_constant__ CUtensorMap tmUhi, const __grid_constant
 }
 
 // ---------------------------------------------------------------------------------------------
-// operand preparation: x' = x * scale[row] (items: the gate sig_i; users: 1), hi = tf32(x')
-// (round to nearest), lo = tf32(x' - hi); row norm of x'; csig[row] = c * scale[row]
+// operand preparation: x' = x * scale[row] (items: the gate sig_i; users: 1), out = bf16(x')
+// (round to nearest; tf32 with -DMACR_TC_TF32); row norm of x'; csig[row] = c * scale[row]
 // ---------------------------------------------------------------------------------------------
 __device__ __forceinline__ float to_tf32(float x) {
   uint32_t r;
   asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(x));
   return __uint_as_float(r);
 }
+__device__ __forceinline__ unsigned short to_bf16(float x) {
+  unsigned short r;
+  asm("cvt.rn.bf16.f32 %0, %1;" : "=h"(r) : "f"(x));
+  return r;
+}
 
 // one half-warp per row (float4 per lane); norm_out[row] = ||row||_2 rounded up a little;
 // norm_max (nullable): max over rows via atomicMax on the bit pattern (non-negative floats)
 __global__ void __launch_bounds__(256)
 split_rows_kernel(const float *__restrict__ X, long long n, const float *__restrict__ scale,
-                  float c, float *__restrict__ hi, float *__restrict__ lo,
-                  float *__restrict__ csig, float *__restrict__ norm_out,
+                  float c, oper_t *__restrict__ hi, float *__restrict__ csig,
+                  float *__restrict__ norm_out,
                   unsigned int *__restrict__ norm_max) {
   const long long r = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 4;
   const int hl = threadIdx.x & 15;
@@ -521,12 +548,15 @@ split_rows_kernel(const float *__restrict__ X, long long n, const float *__restr
       v.w = __fmul_rn(v.w, sc);
       if (hl == 0) csig[r] = __fmul_rn(c, sc);
     }
-    float4 h, l;
+#ifdef MACR_TC_TF32
+    float4 h;
     h.x = to_tf32(v.x), h.y = to_tf32(v.y), h.z = to_tf32(v.z), h.w = to_tf32(v.w);
-    l.x = to_tf32(v.x - h.x), l.y = to_tf32(v.y - h.y), l.z = to_tf32(v.z - h.z),
-    l.w = to_tf32(v.w - h.w);
     reinterpret_cast<float4 *>(hi + r * kD)[hl] = h;
-    reinterpret_cast<float4 *>(lo + r * kD)[hl] = l;
+#else
+    ushort4 h;
+    h.x = to_bf16(v.x), h.y = to_bf16(v.y), h.z = to_bf16(v.z), h.w = to_bf16(v.w);
+    reinterpret_cast<ushort4 *>(hi + r * kD)[hl] = h;
+#endif
     ss = v.x * v.x + v.y * v.y + v.z * v.z + v.w * v.w;
   }
 #pragma unroll
@@ -544,9 +574,9 @@ split_rows_kernel(const float *__restrict__ X, long long n, const float *__restr
 // disjoint batches, so K of them exceed the K-th largest lane maximum m_K: the exact K-th best
 // score of the row is >= m_K - eps.  With y~ the tensor-core dot product of the gate-scaled item
 // row and y the fp32 FMA chain:  |y~ - sig*y| <= kappa * |u| * |sig*i|
-//   kappa(NSPLIT=1) = 2^-9   (two tf32 roundings 2^-11 each, products exact, fp32 accumulation)
-//   kappa(NSPLIT=3) = 2^-15  (dropped lo*lo 2^-22, tf32 rounding of lo 2 x 2^-22, fp32 accumulation
-//                             of 192 products, the 64-term reference chain and the gate pre-scale)
+//   bf16: kappa = 1.5 * 2^-8  (two roundings 2^-9 each -> 2^-8 (1 + 2^-10) per product, products
+//         exact in fp32, plus fp32 accumulation of 64 terms on both sides and the gate pre-scale)
+//   tf32: kappa = 2^-9        (two roundings 2^-11 each)
 // and the roundings of (acc - c*sig) versus ((y - c) * sig) add at most 2^-22 * (|c| + |u||i|)
 // per pass.  eps = eps(maxima pass) + eps(filter pass).
 __global__ void __launch_bounds__(256)
@@ -705,16 +735,17 @@ static EncodeTiledFn encode_fn() {
   return fn;
 }
 
-// [rows][64] fp32 row-major -> boxes of 128 rows x 32 fp32 (128 B), 128-byte swizzle;
+// [rows][64] operands row-major -> boxes of 128 rows x 128 B, 128-byte swizzle;
 // rows beyond `rows` read as zeros
-static int make_map(CUtensorMap *m, const float *base, long long rows) {
+static int make_map(CUtensorMap *m, const oper_t *base, long long rows) {
   EncodeTiledFn fn = encode_fn();
   if (!fn) return fail(MACR_ERR_CUDA, "cuTensorMapEncodeTiled is not available from the driver");
   cuuint64_t dims[2] = {(cuuint64_t)kD, (cuuint64_t)rows};
-  cuuint64_t strides[1] = {(cuuint64_t)kD * sizeof(float)};
+  cuuint64_t strides[1] = {(cuuint64_t)kD * sizeof(oper_t)};
   cuuint32_t box[2] = {(cuuint32_t)KB, (cuuint32_t)BM};
   cuuint32_t estr[2] = {1, 1};
-  CUresult r = fn(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float *>(base), dims, strides,
+  CUresult r = fn(m, kBf16 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2,
+                  const_cast<oper_t *>(base), dims, strides,
                   box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
                   CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) return fail(MACR_ERR_CUDA, "cuTensorMapEncodeTiled failed (%d)", (int)r);
@@ -724,7 +755,7 @@ static int make_map(CUtensorMap *m, const float *base, long long rows) {
 struct Plan {
   int TB;        // query rows per row block
   int n_itiles, n_chunks, tiles_per_chunk, ld_tm;
-  size_t off_uhi, off_ulo, off_ihi, off_ilo, off_csig, off_unorm, off_misc, off_tilemax, off_thr, off_cand,
+  size_t off_uhi, off_ihi, off_csig, off_unorm, off_misc, off_tilemax, off_thr, off_cand,
       off_cnt, off_fbrows, off_exact, total;
   size_t exact_bytes;
 };
@@ -741,12 +772,12 @@ static Plan make_plan(int T, long long n_items, int K) {
   if (tb < 1024) tb = 1024;
   if (tb > T) tb = T;
   p.TB = (int)tb;
-  const int utiles = (p.TB + BM - 1) / BM;
+  const int utiles = (p.TB + UT * BM - 1) / (UT * BM);
   // item chunks: enough work items to balance the SMs, every chunk non-empty
   const int sms = sm_count();
   int best = 1;
   double best_cost = 1e30;
-  for (int nc = 1; nc <= 8 && nc * 4 <= p.n_itiles; ++nc) {
+  for (int nc = 1; nc <= 16 && nc * 4 <= p.n_itiles; ++nc) {
     const int tpc = (p.n_itiles + nc - 1) / nc;
     const int ncr = (p.n_itiles + tpc - 1) / tpc;
     const long long work = (long long)utiles * ncr;
@@ -765,17 +796,15 @@ static Plan make_plan(int T, long long n_items, int K) {
     o = align_up(o + bytes, 1024);
     return at;
   };
-  p.off_uhi = take((size_t)p.TB * kD * 4);
-  p.off_ulo = take((size_t)p.TB * kD * 4);
-  p.off_ihi = take((size_t)n_items * kD * 4);
-  p.off_ilo = take((size_t)n_items * kD * 4);
+  p.off_uhi = take((size_t)p.TB * kD * sizeof(oper_t));
+  p.off_ihi = take((size_t)n_items * kD * sizeof(oper_t));
   p.off_csig = take((size_t)n_items * 4);
   p.off_unorm = take((size_t)p.TB * 4);
   p.off_misc = take(64);  // [0] item norm max (uint bits) [1] fb_count [2..3] cand_total (u64)
   p.off_tilemax = take((size_t)p.TB * p.ld_tm * 4);
   p.off_thr = take((size_t)p.TB * 8);
-  p.off_cand = take((size_t)p.TB * p.n_chunks * 2 * kCap * 8);
-  p.off_cnt = take((size_t)p.TB * p.n_chunks * 2 * 4);
+  p.off_cand = take((size_t)p.TB * p.n_chunks * kCap * 8);
+  p.off_cnt = take((size_t)p.TB * p.n_chunks * 4);
   p.off_fbrows = take((size_t)p.TB * 4);
   p.exact_bytes = score_exact_workspace_bytes(p.TB, n_items, K);
   p.off_exact = take(p.exact_bytes);
@@ -783,24 +812,22 @@ static Plan make_plan(int T, long long n_items, int K) {
   return p;
 }
 
-static int g_nsplit_max = 1, g_nsplit_filter = 1;
+static int g_dbg = 0;
 
-template <int MODE, int NSPLIT>
-static int launch_pass(const CUtensorMap &uh, const CUtensorMap &ul, const CUtensorMap &ih,
-                       const CUtensorMap &il, const TileParams &P, const float *sig_i,
-                       const int32_t *mrp, const int32_t *mcol, float *tilemax, const float2 *thr,
-                       uint2 *cand, int *cnt, cudaStream_t s) {
+template <int MODE>
+static int launch_pass(const CUtensorMap &mu, const CUtensorMap &mi, const TileParams &P,
+                       const float *csig, const int32_t *mrp, const int32_t *mcol, float *bmax,
+                       const float2 *thr, uint2 *cand, int *cnt, cudaStream_t s) {
   static bool opted = false;
   if (!opted) {
-    MACR_CUDA(cudaFuncSetAttribute(score_tc_kernel<MODE, NSPLIT>,
-                                   cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                   Cfg<NSPLIT>::SMEM_BYTES));
+    MACR_CUDA(cudaFuncSetAttribute(score_tc_kernel<MODE>,
+                                   cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
     opted = true;
   }
   const int n_work = P.n_utiles * P.n_chunks;
   const int grid = n_work < sm_count() ? n_work : sm_count();
-  score_tc_kernel<MODE, NSPLIT><<<grid, kThreads, Cfg<NSPLIT>::SMEM_BYTES, s>>>(
-      uh, ul, ih, il, P, sig_i, mrp, mcol, tilemax, thr, cand, cnt);
+  score_tc_kernel<MODE><<<grid, kThreads, SMEM_BYTES, s>>>(mu, mi, P, csig, mrp, mcol, bmax, thr,
+                                                           cand, cnt);
   MACR_LAUNCH_CHECK();
   return MACR_OK;
 }
@@ -810,11 +837,9 @@ static int launch_pass(const CUtensorMap &uh, const CUtensorMap &ul, const CUten
 
 using namespace macr;
 
-extern "C" int macr_score_tc_set_splits(int nsplit_max, int nsplit_filter) {
-  MACR_CHECK_ARG((nsplit_max == 1 || nsplit_max == 3) && (nsplit_filter == 1 || nsplit_filter == 3),
-                 "macr_score_tc_set_splits: splits must be 1 or 3");
-  tc::g_nsplit_max = nsplit_max;
-  tc::g_nsplit_filter = nsplit_filter;
+// developer hook (not in the public header): timing experiments of the maxima pass
+extern "C" int macr_score_tc_debug(int dbg) {
+  tc::g_dbg = dbg;
   return MACR_OK;
 }
 
@@ -849,8 +874,8 @@ extern "C" int macr_score_topk_tc(const float *Uq, int T, const float *It, int64
                 p.total);
   cudaStream_t s = as_stream(stream);
   unsigned char *w = reinterpret_cast<unsigned char *>(ws);
-  float *uhi = reinterpret_cast<float *>(w + p.off_uhi), *ulo = reinterpret_cast<float *>(w + p.off_ulo);
-  float *ihi = reinterpret_cast<float *>(w + p.off_ihi), *ilo = reinterpret_cast<float *>(w + p.off_ilo);
+  oper_t *uhi = reinterpret_cast<oper_t *>(w + p.off_uhi);
+  oper_t *ihi = reinterpret_cast<oper_t *>(w + p.off_ihi);
   float *unorm = reinterpret_cast<float *>(w + p.off_unorm);
   unsigned int *misc = reinterpret_cast<unsigned int *>(w + p.off_misc);
   float *tilemax = reinterpret_cast<float *>(w + p.off_tilemax);
@@ -864,59 +889,47 @@ extern "C" int macr_score_topk_tc(const float *Uq, int T, const float *It, int64
 
   MACR_CUDA(cudaMemsetAsync(misc, 0, 64, s));
   split_rows_kernel<<<(unsigned)((n_items * 16 + 255) / 256), 256, 0, s>>>(
-      It, n_items, sig_i, c, ihi, ilo, csig, nullptr, misc);
+      It, n_items, sig_i, c, ihi, csig, nullptr, misc);
   MACR_LAUNCH_CHECK();
-  CUtensorMap mih, mil;
+  CUtensorMap mih;
   int rc = make_map(&mih, ihi, n_items);
   if (rc) return rc;
-  rc = make_map(&mil, ilo, n_items);
-  if (rc) return rc;
-  const float kappa1 = 1.953125e-3f /*2^-9*/, kappa3 = 3.0517578125e-5f /*2^-15*/;
-  const float kappa_sum = (g_nsplit_max == 1 ? kappa1 : kappa3) + (g_nsplit_filter == 1 ? kappa1 : kappa3);
+  // maxima pass + filter pass, see row_threshold_kernel
+  const float kappa_sum = 2.f * (kBf16 ? 1.5f * 3.90625e-3f : 1.953125e-3f);
 
   for (int t0 = 0; t0 < T; t0 += p.TB) {
     const int nb = T - t0 < p.TB ? T - t0 : p.TB;
     const float *Ub = Uq + (size_t)t0 * kD;
     const int32_t *mrp = mask_rowptr ? mask_rowptr + t0 : nullptr;
     split_rows_kernel<<<(unsigned)(((long long)nb * 16 + 255) / 256), 256, 0, s>>>(
-        Ub, nb, nullptr, 0.f, uhi, ulo, nullptr, unorm, nullptr);
+        Ub, nb, nullptr, 0.f, uhi, nullptr, unorm, nullptr);
     MACR_LAUNCH_CHECK();
-    CUtensorMap muh, mul;
+    CUtensorMap muh;
     rc = make_map(&muh, uhi, nb);
-    if (rc) return rc;
-    rc = make_map(&mul, ulo, nb);
     if (rc) return rc;
     TileParams P;
     P.T = nb;
     P.n_items = (int)n_items;
-    P.n_utiles = (nb + BM - 1) / BM;
+    P.n_utiles = (nb + UT * BM - 1) / (UT * BM);
     P.n_itiles = p.n_itiles;
     P.n_chunks = p.n_chunks;
     P.tiles_per_chunk = p.tiles_per_chunk;
     P.id_off = item_id_offset;
     P.ld_tm = p.ld_tm;
-    if (g_nsplit_max == 1)
-      rc = launch_pass<MODE_MAX, 1>(muh, mul, mih, mil, P, csig, mrp, mask_col, tilemax, nullptr,
-                                    nullptr, nullptr, s);
-    else
-      rc = launch_pass<MODE_MAX, 3>(muh, mul, mih, mil, P, csig, mrp, mask_col, tilemax, nullptr,
-                                    nullptr, nullptr, s);
+    P.dbg = g_dbg;
+    rc = launch_pass<MODE_MAX>(muh, mih, P, csig, mrp, mask_col, tilemax, nullptr, nullptr, nullptr,
+                               s);
     if (rc) return rc;
     const int n_batches = 4 * p.n_itiles, bm_words = (n_batches + 31) / 32;
     row_threshold_kernel<<<(nb + 7) / 8, 256, (size_t)8 * bm_words * 4, s>>>(
         tilemax, nb, n_batches, p.ld_tm, K, mrp, mask_col, item_id_offset, (int)n_items, unorm,
         misc, c, kappa_sum, bm_words, thr);
     MACR_LAUNCH_CHECK();
-    if (g_nsplit_filter == 1)
-      rc = launch_pass<MODE_FILTER, 1>(muh, mul, mih, mil, P, csig, mrp, mask_col, tilemax, thr,
-                                       cand, cnt, s);
-    else
-      rc = launch_pass<MODE_FILTER, 3>(muh, mul, mih, mil, P, csig, mrp, mask_col, tilemax, thr,
-                                       cand, cnt, s);
+    rc = launch_pass<MODE_FILTER>(muh, mih, P, csig, mrp, mask_col, tilemax, thr, cand, cnt, s);
     if (rc) return rc;
     MACR_CUDA(cudaMemsetAsync(fb_count, 0, sizeof(int), s));
     rerank_kernel<<<(nb + 7) / 8, 256, 0, s>>>(Ub, nb, It, sig_i, sig_u + t0, c, item_id_offset,
-                                               cand, cnt, 2 * p.n_chunks, K,
+                                               cand, cnt, p.n_chunks, K,
                                                out_ids + (size_t)t0 * K, out_scores + (size_t)t0 * K,
                                                fb_rows, fb_count, cand_total);
     MACR_LAUNCH_CHECK();
