@@ -19,7 +19,17 @@ mrp, mcol = torch.from_numpy(rowptr).to(dev), torch.from_numpy(col).to(dev)
 import ctypes
 dbg = int(os.environ.get("TC_DBG", "0"))
 h = ctypes.CDLL(lib()._name)
-h.macr_score_tc_debug(dbg)
+prof = torch.zeros(64, dtype=torch.int64, device=dev)
+h.macr_score_tc_debug.argtypes = [ctypes.c_int, ctypes.c_void_p]
+h.macr_score_tc_debug(dbg, ctypes.c_void_p(prof.data_ptr()) if os.environ.get("TC_PROF") else None)
 for _ in range(3):
     ops.score_topk_tc(dU, dI, si, su, c, mrp, mcol, K)
 torch.cuda.synchronize()
+if os.environ.get("TC_PROF"):
+    pr = prof.cpu().tolist()
+    for mode, name in ((0, "MAX"), (1, "FILTER")):
+        b = 32 * mode
+        print(f"{name}: producer  wait A_EMPTY {pr[b+0]}  wait B_EMPTY {pr[b+1]}  total {pr[b+2]}")
+        print(f"{name}: mma       wait A_FULL {pr[b+4]}  wait B_FULL {pr[b+5]}  wait TM_EMPTY wg0 {pr[b+6]} wg1 {pr[b+7]}  total {pr[b+8]}  tiles {pr[b+9]}")
+        for g in (0, 1):
+            print(f"{name}: epilogue wg{g}  bar.sync {pr[b+12+4*g]}  wait TM_FULL {pr[b+13+4*g]}  total {pr[b+14+4*g]}")

@@ -29,19 +29,22 @@
 // it halves the TMA bytes); a looser bound only means more candidates, never a wrong id.
 //
 // Kernel anatomy (one CTA per SM, persistent over (256-user tile, item chunk) work items):
-//   warp 0      TMA producer   cp.async.bulk.tensor.2d, 128B-swizzled K-major boxes of 128 rows x 128 B;
-//                              two 128-row user tiles stay resident, item tiles stream through a
-//                              ring (each item tile is read from L2 once per 256 users)
-//   warp 1      MMA issuer     tcgen05.mma.cta_group::1.kind::f16, M=128 N=128 K=16, D in TMEM:
-//                              4 accumulator buffers x 128 columns (user tile g, item-tile parity);
-//                              also owns TMEM alloc/dealloc
-//   warps 2..9  epilogue       two warpgroups, warpgroup g owns user tile g and TMEM buffers 2g, 2g+1:
+//   warp 0      TMA producer   cp.async.bulk.tensor.2d, 128B-swizzled K-major boxes of 128 B rows;
+//                              two 128-row user tiles stay resident, 256-item tiles stream through
+//                              a 4-stage ring (each item tile is read from L2 once per 256 users)
+//   warp 1      MMA issuer     tcgen05.mma.cta_group::1.kind::f16, M=128 N=256 K=16, D in TMEM:
+//                              2 accumulators x 256 columns (one per user tile); the tensor pipe
+//                              works on one user tile while the other is drained; also owns
+//                              TMEM alloc/dealloc
+//   warps 2..9  epilogue       two warpgroups, warpgroup g owns user tile g and accumulator g:
 //                              tcgen05.ld.32x32b.x32 (thread = user row), fused correction,
 //                              batch maxima / threshold filter, train-item mask from a per-row
 //                              cursor into the sorted CSR mask
 // mbarrier pipelines: user tiles full/empty, item stages full/empty, TMEM full/empty.
 #include <cuda.h>
 #include <math.h>
+
+#include <type_traits>
 
 #include "common.cuh"
 #include "score.cuh"
@@ -50,26 +53,27 @@ namespace macr {
 namespace tc {
 
 constexpr int BM = 128;              // user rows per tile (UMMA M, TMEM lanes)
-constexpr int BN = 128;              // items per tile (UMMA N, TMEM columns per buffer)
-#ifdef MACR_TC_TF32
-constexpr bool kBf16 = false;
-typedef float oper_t;                // operands rounded to tf32, stored in fp32 containers
-#else
-constexpr bool kBf16 = true;
+constexpr int BN = 256;              // items per tile (UMMA N, TMEM columns per accumulator)
+constexpr int NB = BN / 32;          // 32-column batches per tile
 typedef unsigned short oper_t;       // operands rounded to bf16
-#endif
-constexpr int KB = 128 / (int)sizeof(oper_t);  // elements per 128-byte swizzle row
-constexpr int NKB = kD / KB;         // K blocks per operand tile (bf16: 1, tf32: 2)
-constexpr int KBLK_BYTES = BM * 128; // one K block of one operand tile: 128 rows x 128 B
-constexpr int OPER_BYTES = NKB * KBLK_BYTES;  // a 128 x 64 operand tile (bf16: 16 KiB)
+constexpr int KB = 64;               // bf16 per 128-byte swizzle row = the whole embedding row
+constexpr int A_TILE_BYTES = BM * 128;   // a 128 x 64 bf16 user tile, 128B-swizzled
+constexpr int B_TILE_BYTES = BN * 128;   // a 256 x 64 bf16 item tile
+// The "- c*sig_i" term rides on one extra K=16 step: user side [1,1,1,0..0], item side the three
+// bf16 pieces of -c*sig_i (exact to 24 bits), 32-byte rows, 32B-swizzled.
+constexpr int KA = 16;
+constexpr int A_AUG_BYTES = BM * 32;
+constexpr int B_AUG_BYTES = BN * 32;
+constexpr int B_BYTES = B_TILE_BYTES + B_AUG_BYTES;  // one ring stage (40 KiB)
 constexpr int kCap = 64;             // candidate slots per (row, item chunk)
 constexpr int kThreads = 320;        // producer, MMA issuer, 2 epilogue warpgroups
-constexpr int kTmemCols = 512;       // 4 accumulator buffers x 128 columns
+constexpr int kTmemCols = 512;       // 2 accumulators (one per user tile) x 256 columns
 constexpr int UT = 2;                // user tiles per CTA (one per epilogue warpgroup)
-constexpr int STAGES = kBf16 ? 8 : 4; // item-tile ring (128 KiB)
-constexpr int A_BYTES = UT * OPER_BYTES;
-constexpr int SMEM_BYTES = 1024 /*align*/ + A_BYTES + STAGES * OPER_BYTES;
+constexpr int STAGES = 4;            // item-tile ring (160 KiB)
+constexpr int A_BYTES = UT * (A_TILE_BYTES + A_AUG_BYTES);
+constexpr int SMEM_BYTES = 1024 /*align*/ + A_BYTES + STAGES * B_BYTES;
 constexpr int MODE_MAX = 0, MODE_FILTER = 1;
+constexpr int kPf = 2;               // filter pass: prefetch distance of the batch maxima, in tiles
 
 // ---- PTX wrappers ----------------------------------------------------------------------------
 __device__ __forceinline__ uint32_t smem_u32(const void *p) {
@@ -128,11 +132,7 @@ __device__ __forceinline__ void tc_mma(uint32_t d_tmem, uint64_t adesc, uint64_t
   asm volatile(
       "{\n\t.reg .pred p;\n\t"
       "setp.ne.b32 p, %4, 0;\n\t"
-#ifdef MACR_TC_TF32
-      "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}"
-#else
       "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
-#endif
       ::"r"(d_tmem), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
       : "memory");
 }
@@ -146,10 +146,19 @@ __device__ __forceinline__ uint64_t umma_desc(uint32_t smem_addr) {
   d |= (uint64_t)2 << 61;            // SWIZZLE_128B
   return d;
 }
-// fp32 accumulate (bit 4), A/B format (bits 7-9 / 10-12: 1 = bf16, 2 = tf32), both K-major,
+// K-major, 32-byte swizzle (rows of 32 B): 8-row groups 256 B apart, layout type 6
+__device__ __forceinline__ uint64_t umma_desc32(uint32_t smem_addr) {
+  uint64_t d = 0;
+  d |= (uint64_t)((smem_addr >> 4) & 0x3FFF);
+  d |= (uint64_t)1 << 16;
+  d |= (uint64_t)(256 >> 4) << 32;
+  d |= (uint64_t)1 << 46;
+  d |= (uint64_t)6 << 61;  // SWIZZLE_32B
+  return d;
+}
+// fp32 accumulate (bit 4), A/B format bf16 (1 at bits 7-9 / 10-12), both K-major,
 // N >> 3 at bit 17, M >> 4 at bit 24
-constexpr uint32_t kFmt = kBf16 ? 1u : 2u;
-constexpr uint32_t kIdesc = (1u << 4) | (kFmt << 7) | (kFmt << 10) | ((uint32_t)(BN >> 3) << 17) |
+constexpr uint32_t kIdesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(BN >> 3) << 17) |
                             ((uint32_t)(BM >> 4) << 24);
 
 #define MACR_R32(v)                                                                              \
@@ -180,60 +189,75 @@ __device__ __forceinline__ void tmem_ld_wait(uint32_t (&v)[32]) {
   asm volatile("tcgen05.wait::ld.sync.aligned;" : MACR_R32(v)::"memory");
 }
 
+// 64 consecutive accumulator columns of this thread's TMEM lane: fewer, longer loads hide the
+// TMEM latency behind two batches of arithmetic
+__device__ __forceinline__ void tmem_ld64(uint32_t taddr, uint32_t (&v)[64]) {
+  asm volatile("tcgen05.ld.sync.aligned.32x32b.x64.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31, %32, %33, %34, %35, %36, %37, %38, %39, %40, %41, %42, %43, %44, %45, %46, %47, %48, %49, %50, %51, %52, %53, %54, %55, %56, %57, %58, %59, %60, %61, %62, %63}, [%64];"
+               : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]), "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]), "=r"(v[16]), "=r"(v[17]), "=r"(v[18]), "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]), "=r"(v[24]), "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31]), "=r"(v[32]), "=r"(v[33]), "=r"(v[34]), "=r"(v[35]), "=r"(v[36]), "=r"(v[37]), "=r"(v[38]), "=r"(v[39]), "=r"(v[40]), "=r"(v[41]), "=r"(v[42]), "=r"(v[43]), "=r"(v[44]), "=r"(v[45]), "=r"(v[46]), "=r"(v[47]), "=r"(v[48]), "=r"(v[49]), "=r"(v[50]), "=r"(v[51]), "=r"(v[52]), "=r"(v[53]), "=r"(v[54]), "=r"(v[55]), "=r"(v[56]), "=r"(v[57]), "=r"(v[58]), "=r"(v[59]), "=r"(v[60]), "=r"(v[61]), "=r"(v[62]), "=r"(v[63])
+               : "r"(taddr)
+               : "memory");
+}
+__device__ __forceinline__ void tmem_ld_wait64(uint32_t (&v)[64]) {
+  asm volatile("tcgen05.wait::ld.sync.aligned;" : "+r"(v[0]), "+r"(v[1]), "+r"(v[2]), "+r"(v[3]), "+r"(v[4]), "+r"(v[5]), "+r"(v[6]), "+r"(v[7]), "+r"(v[8]), "+r"(v[9]), "+r"(v[10]), "+r"(v[11]), "+r"(v[12]), "+r"(v[13]), "+r"(v[14]), "+r"(v[15]), "+r"(v[16]), "+r"(v[17]), "+r"(v[18]), "+r"(v[19]), "+r"(v[20]), "+r"(v[21]), "+r"(v[22]), "+r"(v[23]), "+r"(v[24]), "+r"(v[25]), "+r"(v[26]), "+r"(v[27]), "+r"(v[28]), "+r"(v[29]), "+r"(v[30]), "+r"(v[31]), "+r"(v[32]), "+r"(v[33]), "+r"(v[34]), "+r"(v[35]), "+r"(v[36]), "+r"(v[37]), "+r"(v[38]), "+r"(v[39]), "+r"(v[40]), "+r"(v[41]), "+r"(v[42]), "+r"(v[43]), "+r"(v[44]), "+r"(v[45]), "+r"(v[46]), "+r"(v[47]), "+r"(v[48]), "+r"(v[49]), "+r"(v[50]), "+r"(v[51]), "+r"(v[52]), "+r"(v[53]), "+r"(v[54]), "+r"(v[55]), "+r"(v[56]), "+r"(v[57]), "+r"(v[58]), "+r"(v[59]), "+r"(v[60]), "+r"(v[61]), "+r"(v[62]), "+r"(v[63])::"memory");
+}
+
 struct TileParams {
   int T;            // query rows in this row block
   int n_items;      // items in this shard
   int n_utiles;     // 256-row user tile pairs
   int n_itiles, n_chunks, tiles_per_chunk;
   int id_off;       // global id of local item 0 (mask_col holds global ids)
-  int ld_tm;        // row pitch of the batch maxima (floats), 4 per item tile
+  int ld_tm;        // row pitch of the batch maxima (floats), NB per item tile
   int dbg;          // developer timing experiments (0 = product path): bit0 skip the TMEM loads,
                     // bit1 skip the epilogue arithmetic, bit2 skip the MMAs (results are then
                     // meaningless)
 };
 
-// max over 32 accumulator columns of (acc - c*sig): 4 independent chains
-__device__ __forceinline__ float batch_max(const uint32_t (&v)[32], const float *cs) {
-  const float4 *c4 = reinterpret_cast<const float4 *>(cs);
+// max over the 32 accumulator columns v[OFF .. OFF+32): 4 independent chains
+template <int OFF, int N>
+__device__ __forceinline__ float batch_max(const uint32_t (&v)[N]) {
   float m0 = -INFINITY, m1 = -INFINITY, m2 = -INFINITY, m3 = -INFINITY;
 #pragma unroll
   for (int j4 = 0; j4 < 8; ++j4) {
-    const float4 g = c4[j4];
-    m0 = fmaxf(m0, __uint_as_float(v[4 * j4 + 0]) - g.x);
-    m1 = fmaxf(m1, __uint_as_float(v[4 * j4 + 1]) - g.y);
-    m2 = fmaxf(m2, __uint_as_float(v[4 * j4 + 2]) - g.z);
-    m3 = fmaxf(m3, __uint_as_float(v[4 * j4 + 3]) - g.w);
+    m0 = fmaxf(m0, __uint_as_float(v[OFF + 4 * j4 + 0]));
+    m1 = fmaxf(m1, __uint_as_float(v[OFF + 4 * j4 + 1]));
+    m2 = fmaxf(m2, __uint_as_float(v[OFF + 4 * j4 + 2]));
+    m3 = fmaxf(m3, __uint_as_float(v[OFF + 4 * j4 + 3]));
   }
   return fmaxf(fmaxf(m0, m1), fmaxf(m2, m3));
 }
 
 // ---------------------------------------------------------------------------------------------
-// The item operand is pre-scaled by its gate (rows sig_i * I_i), so the accumulator holds
-// sig_i * y and the approximate score is  acc - c*sig_i  (one FADD per score in the epilogue).
-//   MODE_MAX     bmax[row][4*tile + b] = max over the 32 columns of batch b (masked items included;
-//                the threshold kernel leaves batches holding a train item of the row out)
+// The item operand is pre-scaled by its gate (rows sig_i * I_i) and one extra K step adds
+// -c*sig_i, so the accumulator IS the approximate score (y - c) * sig_i: the epilogue is a bare
+// maximum / compare, half an instruction per score, with no shared-memory traffic.
+//   MODE_MAX     bmax[row][NB*tile + b] = max over the 32 columns of batch b (masked items
+//                included; the threshold kernel leaves batches holding a train item of the row out)
 //   MODE_FILTER  batches with bmax >= thr.y are re-read; unmasked scores >= thr.x are appended
+// Pipeline per CTA: the MMA warp alternates between the two user tiles (A0 x B -> TMEM[0:256),
+// A1 x B -> TMEM[256:512)); while warpgroup 0 drains its accumulator the tensor pipe computes
+// warpgroup 1's, so with epilogue <= MMA time the tensor pipe never idles.
 // ---------------------------------------------------------------------------------------------
 template <int MODE>
 __global__ void __launch_bounds__(kThreads, 1)
 score_tc_kernel(const __grid_constant__ CUtensorMap tmU, const __grid_constant__ CUtensorMap tmI,
-                const TileParams P, const float *__restrict__ csig,
+                const __grid_constant__ CUtensorMap tmUa, const __grid_constant__ CUtensorMap tmIa,
+                const TileParams P,
                 const int32_t *__restrict__ mask_rowptr, const int32_t *__restrict__ mask_col,
                 float *__restrict__ bmax, const float2 *__restrict__ thr,
-                uint2 *__restrict__ cand, int *__restrict__ cand_cnt) {
+                uint2 *__restrict__ cand, int *__restrict__ cand_cnt,
+                long long *__restrict__ prof /* developer cycle counters of CTA 0, nullable */) {
   extern __shared__ unsigned char smem_raw[];
   // 1024-byte alignment: the 128B swizzle pattern repeats every 8 rows x 128 B
   unsigned char *smem = reinterpret_cast<unsigned char *>(
       (reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
-  unsigned char *sA = smem;              // [UT][NKB][128 x 128 B]
-  unsigned char *sB = smem + A_BYTES;    // [STAGES][NKB][128 x 128 B]
-  // small arrays are static so that their accesses stay LDS/STS (pointers derived from the
-  // re-aligned dynamic buffer decay to generic loads, which do not broadcast)
-  __shared__ __align__(16) float sCs[4 * BN];  // [2 warpgroups][2][BN]  c*sig of the tile
+  unsigned char *sA = smem;              // [UT][128 rows x 128 B] then [UT][128 rows x 32 B]
+  unsigned char *sAaug = smem + UT * A_TILE_BYTES;
+  unsigned char *sB = smem + A_BYTES;    // [STAGES]{[256 rows x 128 B], [256 rows x 32 B]}
   __shared__ __align__(8) uint64_t bars[32];   // see indices below
   __shared__ uint32_t tmem_slot[1];
 
-  enum { A_FULL = 0, A_EMPTY = 1, TM_FULL = 2, TM_EMPTY = 6, B_FULL = 10, B_EMPTY = 10 + STAGES };
+  enum { A_FULL = 0, A_EMPTY = 1, TM_FULL = 2, TM_EMPTY = 4, B_FULL = 6, B_EMPTY = 6 + STAGES };
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const uint32_t bar0 = smem_u32(bars);
   auto BAR = [&](int i) { return bar0 + 8u * (uint32_t)i; };
@@ -241,7 +265,7 @@ score_tc_kernel(const __grid_constant__ CUtensorMap tmU, const __grid_constant__
   if (threadIdx.x == 0) {
     mbar_init(BAR(A_FULL), 1);
     mbar_init(BAR(A_EMPTY), 1);
-    for (int b = 0; b < 4; ++b) {
+    for (int b = 0; b < 2; ++b) {
       mbar_init(BAR(TM_FULL + b), 1);
       mbar_init(BAR(TM_EMPTY + b), 4);  // one arrive per warp of the owning epilogue warpgroup
     }
@@ -263,6 +287,18 @@ score_tc_kernel(const __grid_constant__ CUtensorMap tmU, const __grid_constant__
   tc_fence_after();
   const uint32_t tmem_base = tmem_slot[0];
   const int n_work = P.n_utiles * P.n_chunks;
+  const bool profiling = prof != nullptr && blockIdx.x == 0;
+  long long pc[6] = {0, 0, 0, 0, 0, 0};
+  auto timed_wait = [&](uint32_t bar, uint32_t parity, int slot) {
+    if (profiling) {
+      const long long t0 = clock64();
+      mbar_wait(bar, parity);
+      pc[slot] += clock64() - t0;
+    } else {
+      mbar_wait(bar, parity);
+    }
+  };
+  const long long t_start = profiling ? clock64() : 0;
 
   if (warp == 0) {
     // =============================== TMA producer ===============================
@@ -273,24 +309,27 @@ score_tc_kernel(const __grid_constant__ CUtensorMap tmU, const __grid_constant__
         const int ut = w / P.n_chunks, ch = w - ut * P.n_chunks;
         const int t_begin = ch * P.tiles_per_chunk;
         const int t_end = min(P.n_itiles, t_begin + P.tiles_per_chunk);
-        mbar_wait(BAR(A_EMPTY), a_phase ^ 1);
+        timed_wait(BAR(A_EMPTY), a_phase ^ 1, 0);
         mbar_expect_tx(BAR(A_FULL), A_BYTES);
-        for (int a = 0; a < UT; ++a)
-          for (int kb = 0; kb < NKB; ++kb)
-            tma_load_2d(smem_u32(sA + (a * NKB + kb) * KBLK_BYTES), &tmU, BAR(A_FULL), kb * KB,
-                        (ut * UT + a) * BM);
+        for (int a = 0; a < UT; ++a) {
+          tma_load_2d(smem_u32(sA + a * A_TILE_BYTES), &tmU, BAR(A_FULL), 0, (ut * UT + a) * BM);
+          tma_load_2d(smem_u32(sAaug + a * A_AUG_BYTES), &tmUa, BAR(A_FULL), 0, 0);
+        }
         a_phase ^= 1;
         for (int t = t_begin; t < t_end; ++t) {
-          mbar_wait(BAR(B_EMPTY + stage), phase ^ 1);
-          mbar_expect_tx(BAR(B_FULL + stage), OPER_BYTES);
-          unsigned char *dst = sB + stage * OPER_BYTES;
-          for (int kb = 0; kb < NKB; ++kb)
-            tma_load_2d(smem_u32(dst + kb * KBLK_BYTES), &tmI, BAR(B_FULL + stage), kb * KB, t * BN);
+          timed_wait(BAR(B_EMPTY + stage), phase ^ 1, 1);
+          mbar_expect_tx(BAR(B_FULL + stage), B_BYTES);
+          unsigned char *dst = sB + stage * B_BYTES;
+          tma_load_2d(smem_u32(dst), &tmI, BAR(B_FULL + stage), 0, t * BN);
+          tma_load_2d(smem_u32(dst + B_TILE_BYTES), &tmIa, BAR(B_FULL + stage), 0, t * BN);
           if (++stage == STAGES) {
             stage = 0;
             phase ^= 1;
           }
         }
+      }
+      if (profiling) {
+        prof[0] = pc[0], prof[1] = pc[1], prof[2] = clock64() - t_start;
       }
     }
   } else if (warp == 1) {
@@ -298,33 +337,33 @@ score_tc_kernel(const __grid_constant__ CUtensorMap tmU, const __grid_constant__
     if (lane == 0) {
       int stage = 0;
       uint32_t phase = 0, a_phase = 0;
-      uint32_t n = 0;  // running tile counter -> TMEM buffer parity
-      const uint32_t a_addr = smem_u32(sA);
+      uint32_t n = 0;  // running tile counter -> TMEM barrier parity
+      const uint32_t a_addr = smem_u32(sA), aaug_addr = smem_u32(sAaug);
       for (int w = blockIdx.x; w < n_work; w += gridDim.x) {
         const int ut = w / P.n_chunks, ch = w - ut * P.n_chunks;
         const int t_begin = ch * P.tiles_per_chunk;
         const int t_end = min(P.n_itiles, t_begin + P.tiles_per_chunk);
-        mbar_wait(BAR(A_FULL), a_phase);
+        timed_wait(BAR(A_FULL), a_phase, 0);
         a_phase ^= 1;
         for (int t = t_begin; t < t_end; ++t, ++n) {
-          mbar_wait(BAR(B_FULL + stage), phase);
-          const uint32_t b_addr = smem_u32(sB + stage * OPER_BYTES);
+          timed_wait(BAR(B_FULL + stage), phase, 1);
+          const uint32_t b_addr = smem_u32(sB + stage * B_BYTES);
 #pragma unroll
           for (int a = 0; a < UT; ++a) {
-            const uint32_t buf = a * 2 + (n & 1);
-            mbar_wait(BAR(TM_EMPTY + buf), ((n >> 1) & 1) ^ 1);
+            timed_wait(BAR(TM_EMPTY + a), (n & 1) ^ 1, 2 + a);
             tc_fence_after();
-            const uint32_t d_tmem = tmem_base + buf * BN;
+            const uint32_t d_tmem = tmem_base + a * BN;
 #pragma unroll
-            for (int kb = 0; kb < NKB; ++kb) {
-#pragma unroll
-              for (int ks = 0; ks < 4; ++ks) {  // 32-byte K steps inside the 128-byte row
-                const uint64_t ad = umma_desc(a_addr + (a * NKB + kb) * KBLK_BYTES + ks * 32);
-                const uint64_t bd = umma_desc(b_addr + kb * KBLK_BYTES + ks * 32);
-                if (!(P.dbg & 4)) tc_mma(d_tmem, ad, bd, kIdesc, (kb | ks) ? 1u : 0u);
-              }
+            for (int ks = 0; ks < 4; ++ks) {  // 32-byte K steps inside the 128-byte row
+              const uint64_t ad = umma_desc(a_addr + a * A_TILE_BYTES + ks * 32);
+              const uint64_t bd = umma_desc(b_addr + ks * 32);
+              if (!(P.dbg & 4)) tc_mma(d_tmem, ad, bd, kIdesc, ks ? 1u : 0u);
             }
-            tc_commit(BAR(TM_FULL + buf));  // accumulator ready for warpgroup a
+            // + 1 * (-c * sig_i)
+            if (!(P.dbg & 4))
+              tc_mma(d_tmem, umma_desc32(aaug_addr + a * A_AUG_BYTES),
+                     umma_desc32(b_addr + B_TILE_BYTES), kIdesc, 1u);
+            tc_commit(BAR(TM_FULL + a));  // accumulator ready for warpgroup a
           }
           tc_commit(BAR(B_EMPTY + stage));  // item stage may be refilled
           if (t == t_end - 1) tc_commit(BAR(A_EMPTY));
@@ -334,14 +373,17 @@ score_tc_kernel(const __grid_constant__ CUtensorMap tmU, const __grid_constant__
           }
         }
       }
+      if (profiling) {
+        prof[4] = pc[0], prof[5] = pc[1], prof[6] = pc[2], prof[7] = pc[3];
+        prof[8] = clock64() - t_start, prof[9] = n;
+      }
     }
   } else {
     // ===== epilogue: 2 warpgroups of 128 threads, warpgroup g owns user tile g of the pair =====
     const int g = (warp - 2) >> 2;          // warpgroup
     const int q = warp & 3;                 // TMEM lane quarter this warp may read
     const int r_in = q * 32 + lane;         // row inside the user tile
-    const int te = (threadIdx.x - 64) & 127;
-    const uint32_t taddr0 = tmem_base + ((uint32_t)(q * 32) << 16) + (g * 2) * BN;
+    const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + g * BN;
     uint32_t n = 0;
     for (int w = blockIdx.x; w < n_work; w += gridDim.x) {
       const int ut = w / P.n_chunks, ch = w - ut * P.n_chunks;
@@ -372,67 +414,83 @@ score_tc_kernel(const __grid_constant__ CUtensorMap tmU, const __grid_constant__
         th = thr[row];
         my_cand = cand + ((size_t)row * P.n_chunks + ch) * kCap;
       }
-      // c*sig of column te of the next tile (prefetched one tile ahead); +inf beyond the
-      // catalogue, so those columns score -inf
-      float cs_next = INFINITY;
-      if (t_begin * BN + te < P.n_items) cs_next = csig[t_begin * BN + te];
+      // the filter pass prefetches its row's NB batch maxima of the coming tiles (an L2 round
+      // trip is not short against a tile)
+      float4 bmq[kPf][2];
+      const float4 kNegInf4 = make_float4(-INFINITY, -INFINITY, -INFINITY, -INFINITY);
+      auto fetch = [&](int tt, float4 (&bq)[2]) {
+        bq[0] = bq[1] = kNegInf4;
+        if (MODE == MODE_FILTER && valid && tt < t_end) {
+          const float4 *bp = reinterpret_cast<const float4 *>(bmax + (size_t)row * P.ld_tm + NB * tt);
+          bq[0] = bp[0];
+          bq[1] = bp[1];
+        }
+      };
+#pragma unroll
+      for (int d = 0; d < kPf; ++d) fetch(t_begin + d, bmq[d]);
 
       for (int t = t_begin; t < t_end; ++t, ++n) {
-        // double-buffered by tile parity: one barrier per tile then orders the writes of tile
-        // k+2 after every read of tile k
-        float *cs = sCs + (g * 2 + (n & 1)) * BN;
-        cs[te] = cs_next;
-        cs_next = INFINITY;
-        if (t + 1 < t_end && (t + 1) * BN + te < P.n_items) cs_next = csig[(t + 1) * BN + te];
-        asm volatile("bar.sync %0, 128;" ::"r"(1 + g) : "memory");
-        const uint32_t full_parity = (n >> 1) & 1;
-        const int buf = g * 2 + (int)(n & 1);
-        const uint32_t taddr = taddr0 + (n & 1) * BN;
-        uint32_t va[32], vb[32];
+        const float bmv[NB] = {bmq[0][0].x, bmq[0][0].y, bmq[0][0].z, bmq[0][0].w,
+                               bmq[0][1].x, bmq[0][1].y, bmq[0][1].z, bmq[0][1].w};
+#pragma unroll
+        for (int d = 0; d + 1 < kPf; ++d) bmq[d][0] = bmq[d + 1][0], bmq[d][1] = bmq[d + 1][1];
+        fetch(t + kPf, bmq[kPf - 1]);
+        const uint32_t full_parity = n & 1;
         if (MODE == MODE_MAX) {
-          mbar_wait(BAR(TM_FULL + buf), full_parity);
+          uint32_t va[64], vb[64];
+          timed_wait(BAR(TM_FULL + g), full_parity, 1);
           tc_fence_after();
           __syncwarp();
-          if (P.dbg) {  // timing experiments only
+          float bm[NB];
+          if (P.dbg) {  // developer timing experiments only
 #pragma unroll
-            for (int j = 0; j < 32; ++j) va[j] = vb[j] = j + lane;
-            float acc = 0.f;
-            for (int cb = 0; cb < 4; ++cb) {
+            for (int j = 0; j < 64; ++j) va[j] = vb[j] = j + lane;
+#pragma unroll
+            for (int cb = 0; cb < NB; cb += 2) {
               if (!(P.dbg & 1)) {
-                tmem_ld32(taddr + cb * 32, va);
-                tmem_ld_wait(va);
+                tmem_ld64(taddr + cb * 32, va);
+                tmem_ld_wait64(va);
               }
-              if (!(P.dbg & 2)) acc += batch_max(va, cs + cb * 32);
-              else acc += __uint_as_float(va[cb]);
+              bm[cb] = (P.dbg & 2) ? __uint_as_float(va[cb]) : batch_max<0>(va);
+              bm[cb + 1] = (P.dbg & 2) ? __uint_as_float(va[cb + 32]) : batch_max<32>(va);
             }
             tc_fence_before();
             __syncwarp();
-            if (lane == 0) mbar_arrive(BAR(TM_EMPTY + buf));
-            if (valid) bmax[(size_t)row * P.ld_tm + 4 * t] = acc;
-            continue;
+            if (lane == 0) mbar_arrive(BAR(TM_EMPTY + g));
+          } else {
+            // 64-column loads, one in flight while the previous 64 columns are reduced
+            tmem_ld64(taddr, va);
+            tmem_ld_wait64(va);
+#pragma unroll
+            for (int c4 = 0; c4 < NB / 4; ++c4) {
+              const int cb = 4 * c4;  // va holds batches cb, cb+1
+              tmem_ld64(taddr + (cb + 2) * 32, vb);
+              bm[cb] = batch_max<0>(va);
+              bm[cb + 1] = batch_max<32>(va);
+              tmem_ld_wait64(vb);
+              if (cb + 4 < NB) {
+                tmem_ld64(taddr + (cb + 4) * 32, va);
+              } else {
+                // all TMEM reads of this accumulator are complete: hand it back to the MMA warp
+                tc_fence_before();
+                __syncwarp();
+                if (lane == 0) mbar_arrive(BAR(TM_EMPTY + g));
+              }
+              bm[cb + 2] = batch_max<0>(vb);
+              bm[cb + 3] = batch_max<32>(vb);
+              if (cb + 4 < NB) tmem_ld_wait64(va);
+            }
           }
-          tmem_ld32(taddr + 0, va);
-          tmem_ld_wait(va);
-          tmem_ld32(taddr + 32, vb);
-          const float b0 = batch_max(va, cs + 0);
-          tmem_ld_wait(vb);
-          tmem_ld32(taddr + 64, va);
-          const float b1 = batch_max(vb, cs + 32);
-          tmem_ld_wait(va);
-          tmem_ld32(taddr + 96, vb);
-          const float b2 = batch_max(va, cs + 64);
-          tmem_ld_wait(vb);
-          // all TMEM reads of this buffer are complete: hand it back to the MMA warp
-          tc_fence_before();
-          __syncwarp();
-          if (lane == 0) mbar_arrive(BAR(TM_EMPTY + buf));
-          const float b3 = batch_max(vb, cs + 96);
-          if (valid)
-            *reinterpret_cast<float4 *>(bmax + (size_t)row * P.ld_tm + 4 * t) =
-                make_float4(b0, b1, b2, b3);
+          if (valid) {
+            float4 *bp = reinterpret_cast<float4 *>(bmax + (size_t)row * P.ld_tm + NB * t);
+            bp[0] = make_float4(bm[0], bm[1], bm[2], bm[3]);
+            bp[1] = make_float4(bm[4], bm[5], bm[6], bm[7]);
+          }
         } else {
           // mask words of this tile: train items of the row + columns beyond the catalogue
-          uint32_t mw[4] = {0u, 0u, 0u, 0u};
+          uint32_t mw[NB];
+#pragma unroll
+          for (int i = 0; i < NB; ++i) mw[i] = 0u;
           {
             const int g0 = P.id_off + t * BN, g1 = g0 + BN;
             while (nxt < g1) {
@@ -440,10 +498,8 @@ score_tc_kernel(const __grid_constant__ CUtensorMap tmU, const __grid_constant__
               if (b >= 0) {
                 const uint32_t bit = 1u << (b & 31);
                 const int ws = b >> 5;
-                mw[0] |= ws == 0 ? bit : 0u;
-                mw[1] |= ws == 1 ? bit : 0u;
-                mw[2] |= ws == 2 ? bit : 0u;
-                mw[3] |= ws == 3 ? bit : 0u;
+#pragma unroll
+                for (int i = 0; i < NB; ++i) mw[i] |= ws == i ? bit : 0u;
               }
               nxt = nxt2;
               ++mptr;
@@ -451,35 +507,34 @@ score_tc_kernel(const __grid_constant__ CUtensorMap tmU, const __grid_constant__
             }
             const int nv = P.n_items - t * BN;  // valid columns of this tile
             if (nv < BN) {
-              mw[0] |= nv <= 0 ? 0xffffffffu : (nv < 32 ? ~((1u << nv) - 1u) : 0u);
-              mw[1] |= nv <= 32 ? 0xffffffffu : (nv < 64 ? ~((1u << (nv - 32)) - 1u) : 0u);
-              mw[2] |= nv <= 64 ? 0xffffffffu : (nv < 96 ? ~((1u << (nv - 64)) - 1u) : 0u);
-              mw[3] |= nv <= 96 ? 0xffffffffu : ~((1u << (nv - 96)) - 1u);
+#pragma unroll
+              for (int i = 0; i < NB; ++i) {
+                const int r = nv - 32 * i;  // valid columns of batch i
+                mw[i] |= r <= 0 ? 0xffffffffu : (r < 32 ? ~((1u << r) - 1u) : 0u);
+              }
             }
           }
-          float4 bm = make_float4(-INFINITY, -INFINITY, -INFINITY, -INFINITY);
-          if (valid) bm = *reinterpret_cast<const float4 *>(bmax + (size_t)row * P.ld_tm + 4 * t);
-          const float bmv[4] = {bm.x, bm.y, bm.z, bm.w};
-          mbar_wait(BAR(TM_FULL + buf), full_parity);
+          // only batches whose maximum reached the threshold for some row of the warp are read
+          // back from TMEM, and only the lanes concerned look at their 32 scores
+          uint32_t va[32];
+          timed_wait(BAR(TM_FULL + g), full_parity, 1);
           tc_fence_after();
 #pragma unroll
-          for (int cb = 0; cb < 4; ++cb) {
+          for (int cb = 0; cb < NB; ++cb) {
             const bool need = bmv[cb] >= th.y;
             __syncwarp();
             if (__any_sync(0xffffffffu, need)) {
               tmem_ld32(taddr + cb * 32, va);
               tmem_ld_wait(va);
               if (need) {
-                const float4 *c4 = reinterpret_cast<const float4 *>(cs + cb * 32);
                 const int gbase = P.id_off + t * BN + cb * 32;
                 const uint32_t mwb = mw[cb];
 #pragma unroll
                 for (int j4 = 0; j4 < 8; ++j4) {
-                  const float4 gg = c4[j4];
-                  const float s0 = __uint_as_float(va[4 * j4 + 0]) - gg.x;
-                  const float s1 = __uint_as_float(va[4 * j4 + 1]) - gg.y;
-                  const float s2 = __uint_as_float(va[4 * j4 + 2]) - gg.z;
-                  const float s3 = __uint_as_float(va[4 * j4 + 3]) - gg.w;
+                  const float s0 = __uint_as_float(va[4 * j4 + 0]);
+                  const float s1 = __uint_as_float(va[4 * j4 + 1]);
+                  const float s2 = __uint_as_float(va[4 * j4 + 2]);
+                  const float s3 = __uint_as_float(va[4 * j4 + 3]);
                   if (fmaxf(fmaxf(s0, s1), fmaxf(s2, s3)) >= th.x) {
                     const float ss[4] = {s0, s1, s2, s3};
 #pragma unroll
@@ -498,10 +553,13 @@ score_tc_kernel(const __grid_constant__ CUtensorMap tmU, const __grid_constant__
           }
           tc_fence_before();
           __syncwarp();
-          if (lane == 0) mbar_arrive(BAR(TM_EMPTY + buf));
+          if (lane == 0) mbar_arrive(BAR(TM_EMPTY + g));
         }
       }
       if (MODE == MODE_FILTER && valid) cand_cnt[(size_t)row * P.n_chunks + ch] = cnt;
+    }
+    if (profiling && lane == 0 && q == 0) {  // one thread per warpgroup
+      prof[12 + 4 * g] = pc[0], prof[13 + 4 * g] = pc[1], prof[14 + 4 * g] = clock64() - t_start;
     }
   }
 
@@ -517,25 +575,25 @@ score_tc_kernel(const __grid_constant__ CUtensorMap tmU, const __grid_constant__
 
 // ---------------------------------------------------------------------------------------------
 // operand preparation: x' = x * scale[row] (items: the gate sig_i; users: 1), out = bf16(x')
-// (round to nearest; tf32 with -DMACR_TC_TF32); row norm of x'; csig[row] = c * scale[row]
+// (round to nearest); row norm of x'.  Items also get their augmented-K row: the three bf16
+// pieces of -c*sig_i, and rows n .. n_pad-1 (padding to a whole tile) are zeros with the
+// augmented entry -inf, so padded columns score -inf.
 // ---------------------------------------------------------------------------------------------
-__device__ __forceinline__ float to_tf32(float x) {
-  uint32_t r;
-  asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(x));
-  return __uint_as_float(r);
-}
 __device__ __forceinline__ unsigned short to_bf16(float x) {
   unsigned short r;
   asm("cvt.rn.bf16.f32 %0, %1;" : "=h"(r) : "f"(x));
   return r;
 }
+__device__ __forceinline__ float from_bf16(unsigned short h) {
+  return __uint_as_float((uint32_t)h << 16);
+}
 
 // one half-warp per row (float4 per lane); norm_out[row] = ||row||_2 rounded up a little;
 // norm_max (nullable): max over rows via atomicMax on the bit pattern (non-negative floats)
 __global__ void __launch_bounds__(256)
-split_rows_kernel(const float *__restrict__ X, long long n, const float *__restrict__ scale,
-                  float c, oper_t *__restrict__ hi, float *__restrict__ csig,
-                  float *__restrict__ norm_out,
+split_rows_kernel(const float *__restrict__ X, long long n, long long n_pad,
+                  const float *__restrict__ scale, float c, oper_t *__restrict__ out,
+                  oper_t *__restrict__ aug, float *__restrict__ norm_out,
                   unsigned int *__restrict__ norm_max) {
   const long long r = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 4;
   const int hl = threadIdx.x & 15;
@@ -546,18 +604,27 @@ split_rows_kernel(const float *__restrict__ X, long long n, const float *__restr
       const float sc = scale[r];
       v.x = __fmul_rn(v.x, sc), v.y = __fmul_rn(v.y, sc), v.z = __fmul_rn(v.z, sc),
       v.w = __fmul_rn(v.w, sc);
-      if (hl == 0) csig[r] = __fmul_rn(c, sc);
+      if (hl == 0) {
+        const float t0 = -__fmul_rn(c, sc);
+        const unsigned short p1 = to_bf16(t0);
+        const float t1 = t0 - from_bf16(p1);  // exact
+        const unsigned short p2 = to_bf16(t1);
+        const unsigned short p3 = to_bf16(t1 - from_bf16(p2));
+        uint4 lo = make_uint4((uint32_t)p1 | ((uint32_t)p2 << 16), (uint32_t)p3, 0u, 0u);
+        reinterpret_cast<uint4 *>(aug + r * KA)[0] = lo;
+        reinterpret_cast<uint4 *>(aug + r * KA)[1] = make_uint4(0u, 0u, 0u, 0u);
+      }
     }
-#ifdef MACR_TC_TF32
-    float4 h;
-    h.x = to_tf32(v.x), h.y = to_tf32(v.y), h.z = to_tf32(v.z), h.w = to_tf32(v.w);
-    reinterpret_cast<float4 *>(hi + r * kD)[hl] = h;
-#else
     ushort4 h;
     h.x = to_bf16(v.x), h.y = to_bf16(v.y), h.z = to_bf16(v.z), h.w = to_bf16(v.w);
-    reinterpret_cast<ushort4 *>(hi + r * kD)[hl] = h;
-#endif
+    reinterpret_cast<ushort4 *>(out + r * kD)[hl] = h;
     ss = v.x * v.x + v.y * v.y + v.z * v.z + v.w * v.w;
+  } else if (r < n_pad) {
+    reinterpret_cast<ushort4 *>(out + r * kD)[hl] = make_ushort4(0, 0, 0, 0);
+    if (hl == 0 && aug) {
+      reinterpret_cast<uint4 *>(aug + r * KA)[0] = make_uint4(0xFF80u /* -inf */, 0u, 0u, 0u);
+      reinterpret_cast<uint4 *>(aug + r * KA)[1] = make_uint4(0u, 0u, 0u, 0u);
+    }
   }
 #pragma unroll
   for (int o = 8; o > 0; o >>= 1) ss += __shfl_xor_sync(0xffffffffu, ss, o);
@@ -568,17 +635,22 @@ split_rows_kernel(const float *__restrict__ X, long long n, const float *__restr
   }
 }
 
+// user-side augmented rows: [1, 1, 1, 0 .. 0] x 128 (the same tile for every user tile)
+__global__ void fill_user_aug_kernel(oper_t *__restrict__ aug) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < BM * KA) aug[i] = (i % KA) < 3 ? (oper_t)0x3F80 /* 1.0 */ : (oper_t)0;
+}
+
 // thr[row] = {filter threshold, batch-skip threshold}, one warp per row.
 // Lane l takes the maximum over the batches b = l (mod 32) that hold no train item of the row
 // (bitmap in shared memory built from the row's mask list).  The 32 lane maxima come from
 // disjoint batches, so K of them exceed the K-th largest lane maximum m_K: the exact K-th best
 // score of the row is >= m_K - eps.  With y~ the tensor-core dot product of the gate-scaled item
 // row and y the fp32 FMA chain:  |y~ - sig*y| <= kappa * |u| * |sig*i|
-//   bf16: kappa = 1.5 * 2^-8  (two roundings 2^-9 each -> 2^-8 (1 + 2^-10) per product, products
-//         exact in fp32, plus fp32 accumulation of 64 terms on both sides and the gate pre-scale)
-//   tf32: kappa = 2^-9        (two roundings 2^-11 each)
-// and the roundings of (acc - c*sig) versus ((y - c) * sig) add at most 2^-22 * (|c| + |u||i|)
-// per pass.  eps = eps(maxima pass) + eps(filter pass).
+//   kappa = 1.5 * 2^-8  (two bf16 roundings 2^-9 each -> 2^-8 (1 + 2^-10) per product, products
+//   exact in fp32, plus fp32 accumulation of 64 terms on both sides and the gate pre-scale)
+// and the roundings of (sig*y - c*sig), with c*sig carried as three bf16 pieces (24 bits), versus
+// ((y - c) * sig) add at most 2^-22 * (|c| + |u||i|) per pass.  eps = eps(maxima pass) + eps(filter pass).
 __global__ void __launch_bounds__(256)
 row_threshold_kernel(const float *__restrict__ bmax, int T, int n_batches, int ld_tm, int K,
                      const int32_t *__restrict__ mask_rowptr, const int32_t *__restrict__ mask_col,
@@ -737,16 +809,17 @@ static EncodeTiledFn encode_fn() {
 
 // [rows][64] operands row-major -> boxes of 128 rows x 128 B, 128-byte swizzle;
 // rows beyond `rows` read as zeros
-static int make_map(CUtensorMap *m, const oper_t *base, long long rows) {
+// cols = 64 (128-byte rows, 128B swizzle) or 16 (32-byte augmented rows, 32B swizzle)
+static int make_map(CUtensorMap *m, const oper_t *base, long long rows, int box_rows, int cols) {
   EncodeTiledFn fn = encode_fn();
   if (!fn) return fail(MACR_ERR_CUDA, "cuTensorMapEncodeTiled is not available from the driver");
-  cuuint64_t dims[2] = {(cuuint64_t)kD, (cuuint64_t)rows};
-  cuuint64_t strides[1] = {(cuuint64_t)kD * sizeof(oper_t)};
-  cuuint32_t box[2] = {(cuuint32_t)KB, (cuuint32_t)BM};
+  cuuint64_t dims[2] = {(cuuint64_t)cols, (cuuint64_t)rows};
+  cuuint64_t strides[1] = {(cuuint64_t)cols * sizeof(oper_t)};
+  cuuint32_t box[2] = {(cuuint32_t)cols, (cuuint32_t)box_rows};
   cuuint32_t estr[2] = {1, 1};
-  CUresult r = fn(m, kBf16 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2,
-                  const_cast<oper_t *>(base), dims, strides,
-                  box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+  CUresult r = fn(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<oper_t *>(base), dims, strides,
+                  box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                  cols == kD ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_32B,
                   CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) return fail(MACR_ERR_CUDA, "cuTensorMapEncodeTiled failed (%d)", (int)r);
   return MACR_OK;
@@ -755,7 +828,7 @@ static int make_map(CUtensorMap *m, const oper_t *base, long long rows) {
 struct Plan {
   int TB;        // query rows per row block
   int n_itiles, n_chunks, tiles_per_chunk, ld_tm;
-  size_t off_uhi, off_ihi, off_csig, off_unorm, off_misc, off_tilemax, off_thr, off_cand,
+  size_t off_uhi, off_ihi, off_iaug, off_uaug, off_unorm, off_misc, off_tilemax, off_thr, off_cand,
       off_cnt, off_fbrows, off_exact, total;
   size_t exact_bytes;
 };
@@ -765,7 +838,7 @@ static size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
 static Plan make_plan(int T, long long n_items, int K) {
   Plan p;
   p.n_itiles = (int)((n_items + BN - 1) / BN);
-  p.ld_tm = (4 * p.n_itiles + 31) / 32 * 32;  // 4 batch maxima per item tile
+  p.ld_tm = (NB * p.n_itiles + 31) / 32 * 32;  // NB batch maxima per item tile
   // row block: tile maxima at most ~256 MiB
   long long tb = (256LL << 20) / (4LL * p.ld_tm);
   tb = tb / BM * BM;
@@ -777,7 +850,7 @@ static Plan make_plan(int T, long long n_items, int K) {
   const int sms = sm_count();
   int best = 1;
   double best_cost = 1e30;
-  for (int nc = 1; nc <= 16 && nc * 4 <= p.n_itiles; ++nc) {
+  for (int nc = 1; nc <= 16 && nc * 2 <= p.n_itiles; ++nc) {
     const int tpc = (p.n_itiles + nc - 1) / nc;
     const int ncr = (p.n_itiles + tpc - 1) / tpc;
     const long long work = (long long)utiles * ncr;
@@ -797,8 +870,10 @@ static Plan make_plan(int T, long long n_items, int K) {
     return at;
   };
   p.off_uhi = take((size_t)p.TB * kD * sizeof(oper_t));
-  p.off_ihi = take((size_t)n_items * kD * sizeof(oper_t));
-  p.off_csig = take((size_t)n_items * 4);
+  const size_t n_pad = (size_t)p.n_itiles * BN;  // items padded to whole tiles
+  p.off_ihi = take(n_pad * kD * sizeof(oper_t));
+  p.off_iaug = take(n_pad * KA * sizeof(oper_t));
+  p.off_uaug = take((size_t)BM * KA * sizeof(oper_t));
   p.off_unorm = take((size_t)p.TB * 4);
   p.off_misc = take(64);  // [0] item norm max (uint bits) [1] fb_count [2..3] cand_total (u64)
   p.off_tilemax = take((size_t)p.TB * p.ld_tm * 4);
@@ -813,12 +888,14 @@ static Plan make_plan(int T, long long n_items, int K) {
 }
 
 static int g_dbg = 0;
+static long long *g_prof = nullptr;  // device int64[64]: cycle counters of CTA 0, per pass
 
 template <int MODE>
-static int launch_pass(const CUtensorMap &mu, const CUtensorMap &mi, const TileParams &P,
-                       const float *csig, const int32_t *mrp, const int32_t *mcol, float *bmax,
+static int launch_pass(const CUtensorMap &mu, const CUtensorMap &mi, const CUtensorMap &mua,
+                       const CUtensorMap &mia, const TileParams &P, const int32_t *mrp, const int32_t *mcol, float *bmax,
                        const float2 *thr, uint2 *cand, int *cnt, cudaStream_t s) {
   static bool opted = false;
+  long long *prof = g_prof ? g_prof + 32 * MODE : nullptr;
   if (!opted) {
     MACR_CUDA(cudaFuncSetAttribute(score_tc_kernel<MODE>,
                                    cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
@@ -826,8 +903,8 @@ static int launch_pass(const CUtensorMap &mu, const CUtensorMap &mi, const TileP
   }
   const int n_work = P.n_utiles * P.n_chunks;
   const int grid = n_work < sm_count() ? n_work : sm_count();
-  score_tc_kernel<MODE><<<grid, kThreads, SMEM_BYTES, s>>>(mu, mi, P, csig, mrp, mcol, bmax, thr,
-                                                           cand, cnt);
+  score_tc_kernel<MODE><<<grid, kThreads, SMEM_BYTES, s>>>(mu, mi, mua, mia, P, mrp, mcol, bmax,
+                                                           thr, cand, cnt, prof);
   MACR_LAUNCH_CHECK();
   return MACR_OK;
 }
@@ -838,8 +915,9 @@ static int launch_pass(const CUtensorMap &mu, const CUtensorMap &mi, const TileP
 using namespace macr;
 
 // developer hook (not in the public header): timing experiments of the maxima pass
-extern "C" int macr_score_tc_debug(int dbg) {
+extern "C" int macr_score_tc_debug(int dbg, long long *prof_dev) {
   tc::g_dbg = dbg;
+  tc::g_prof = prof_dev;
   return MACR_OK;
 }
 
@@ -862,7 +940,7 @@ extern "C" int macr_score_topk_tc(const float *Uq, int T, const float *It, int64
   MACR_CHECK_ARG(n_items >= 2048 && n_items < (1LL << 31) - BN,
                  "macr_score_topk_tc: needs at least 2048 items (got %lld): use macr_score_topk",
                  (long long)n_items);
-  MACR_CHECK_ARG((8LL * ((4 * ((n_items + BN - 1) / BN) + 31) / 32) * 4) <= 48 * 1024,
+  MACR_CHECK_ARG((8LL * ((NB * ((n_items + BN - 1) / BN) + 31) / 32) * 4) <= 48 * 1024,
                  "macr_score_topk_tc: more than ~1.5M items per shard: shard the catalogue");
   MACR_CHECK_ARG(Uq && It && sig_i && sig_u && out_ids && out_scores && ws,
                  "macr_score_topk_tc: null pointer");
@@ -880,7 +958,8 @@ extern "C" int macr_score_topk_tc(const float *Uq, int T, const float *It, int64
   unsigned int *misc = reinterpret_cast<unsigned int *>(w + p.off_misc);
   float *tilemax = reinterpret_cast<float *>(w + p.off_tilemax);
   float2 *thr = reinterpret_cast<float2 *>(w + p.off_thr);
-  float *csig = reinterpret_cast<float *>(w + p.off_csig);
+  oper_t *iaug = reinterpret_cast<oper_t *>(w + p.off_iaug);
+  oper_t *uaug = reinterpret_cast<oper_t *>(w + p.off_uaug);
   uint2 *cand = reinterpret_cast<uint2 *>(w + p.off_cand);
   int *cnt = reinterpret_cast<int *>(w + p.off_cnt);
   int32_t *fb_rows = reinterpret_cast<int32_t *>(w + p.off_fbrows);
@@ -888,24 +967,31 @@ extern "C" int macr_score_topk_tc(const float *Uq, int T, const float *It, int64
   unsigned long long *cand_total = reinterpret_cast<unsigned long long *>(misc + 2);
 
   MACR_CUDA(cudaMemsetAsync(misc, 0, 64, s));
-  split_rows_kernel<<<(unsigned)((n_items * 16 + 255) / 256), 256, 0, s>>>(
-      It, n_items, sig_i, c, ihi, csig, nullptr, misc);
+  const long long n_pad = (long long)p.n_itiles * BN;
+  split_rows_kernel<<<(unsigned)((n_pad * 16 + 255) / 256), 256, 0, s>>>(
+      It, n_items, n_pad, sig_i, c, ihi, iaug, nullptr, misc);
   MACR_LAUNCH_CHECK();
-  CUtensorMap mih;
-  int rc = make_map(&mih, ihi, n_items);
+  fill_user_aug_kernel<<<(BM * KA + 255) / 256, 256, 0, s>>>(uaug);
+  MACR_LAUNCH_CHECK();
+  CUtensorMap mih, mia, mua;
+  int rc = make_map(&mih, ihi, n_pad, BN, kD);
+  if (rc) return rc;
+  rc = make_map(&mia, iaug, n_pad, BN, KA);
+  if (rc) return rc;
+  rc = make_map(&mua, uaug, BM, BM, KA);
   if (rc) return rc;
   // maxima pass + filter pass, see row_threshold_kernel
-  const float kappa_sum = 2.f * (kBf16 ? 1.5f * 3.90625e-3f : 1.953125e-3f);
+  const float kappa_sum = 2.f * 1.5f * 3.90625e-3f;
 
   for (int t0 = 0; t0 < T; t0 += p.TB) {
     const int nb = T - t0 < p.TB ? T - t0 : p.TB;
     const float *Ub = Uq + (size_t)t0 * kD;
     const int32_t *mrp = mask_rowptr ? mask_rowptr + t0 : nullptr;
     split_rows_kernel<<<(unsigned)(((long long)nb * 16 + 255) / 256), 256, 0, s>>>(
-        Ub, nb, nullptr, 0.f, uhi, nullptr, unorm, nullptr);
+        Ub, nb, nb, nullptr, 0.f, uhi, nullptr, unorm, nullptr);
     MACR_LAUNCH_CHECK();
     CUtensorMap muh;
-    rc = make_map(&muh, uhi, nb);
+    rc = make_map(&muh, uhi, nb, BM, kD);
     if (rc) return rc;
     TileParams P;
     P.T = nb;
@@ -917,15 +1003,15 @@ extern "C" int macr_score_topk_tc(const float *Uq, int T, const float *It, int64
     P.id_off = item_id_offset;
     P.ld_tm = p.ld_tm;
     P.dbg = g_dbg;
-    rc = launch_pass<MODE_MAX>(muh, mih, P, csig, mrp, mask_col, tilemax, nullptr, nullptr, nullptr,
-                               s);
+    rc = launch_pass<MODE_MAX>(muh, mih, mua, mia, P, mrp, mask_col, tilemax, nullptr, nullptr,
+                               nullptr, s);
     if (rc) return rc;
-    const int n_batches = 4 * p.n_itiles, bm_words = (n_batches + 31) / 32;
+    const int n_batches = NB * p.n_itiles, bm_words = (n_batches + 31) / 32;
     row_threshold_kernel<<<(nb + 7) / 8, 256, (size_t)8 * bm_words * 4, s>>>(
         tilemax, nb, n_batches, p.ld_tm, K, mrp, mask_col, item_id_offset, (int)n_items, unorm,
         misc, c, kappa_sum, bm_words, thr);
     MACR_LAUNCH_CHECK();
-    rc = launch_pass<MODE_FILTER>(muh, mih, P, csig, mrp, mask_col, tilemax, thr, cand, cnt, s);
+    rc = launch_pass<MODE_FILTER>(muh, mih, mua, mia, P, mrp, mask_col, tilemax, thr, cand, cnt, s);
     if (rc) return rc;
     MACR_CUDA(cudaMemsetAsync(fb_count, 0, sizeof(int), s));
     rerank_kernel<<<(nb + 7) / 8, 256, 0, s>>>(Ub, nb, It, sig_i, sig_u + t0, c, item_id_offset,
