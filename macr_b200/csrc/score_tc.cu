@@ -15,10 +15,9 @@
 //                train item of the row; thr[row] = m_K - (eps_max + eps_filter + slack).  K
 //                distinct unmasked items score >= m_K, so the exact K-th best score is
 //                >= thr + eps_filter: every item of the true top-K passes the filter.
-//   pass FILTER  same tiles again, but only batches whose maximum reaches the threshold are
-//                read back from TMEM; unmasked items with score >= thr are appended to the
-//                (row, item-chunk) candidate list (a register counter per thread: no atomics).
-//                Expected ~1.5 K candidates per row.
+//   pass FILTER  same tiles again; batches whose maximum reaches the threshold are scanned and
+//                items with score >= thr are appended to the row's candidate list (one atomic
+//                per append: ~1.3 K appends per row over the whole catalogue).
 //   re-rank      one warp per row: exact fp32 FMA-chain score of every candidate (the arithmetic
 //                of score.cu), sorted insert (score desc, lower id first) -> out.
 //   fallback     a row whose candidate list overflowed (degenerate score distributions) is
@@ -65,7 +64,7 @@ constexpr int KA = 16;
 constexpr int A_AUG_BYTES = BM * 32;
 constexpr int B_AUG_BYTES = BN * 32;
 constexpr int B_BYTES = B_TILE_BYTES + B_AUG_BYTES;  // one ring stage (40 KiB)
-constexpr int kCap = 64;             // candidate slots per (row, item chunk)
+constexpr int kCap = 128;            // candidate slots per row (4 x 32 lanes of the re-rank warp)
 constexpr int kThreads = 320;        // producer, MMA issuer, 2 epilogue warpgroups
 constexpr int kTmemCols = 512;       // 2 accumulators (one per user tile) x 256 columns
 constexpr int UT = 2;                // user tiles per CTA (one per epilogue warpgroup)
@@ -391,28 +390,11 @@ score_tc_kernel(const __grid_constant__ CUtensorMap tmU, const __grid_constant__
       const int t_end = min(P.n_itiles, t_begin + P.tiles_per_chunk);
       const int row = (ut * UT + g) * BM + r_in;
       const bool valid = row < P.T;
-      int mptr = 0, mend = 0, nxt = 0x7fffffff, nxt2 = 0x7fffffff;
       float2 th = make_float2(INFINITY, INFINITY);
-      int cnt = 0;
       uint2 *my_cand = nullptr;
       if (MODE == MODE_FILTER && valid) {
-        // cursor into this row's sorted train-item list, positioned at the chunk's first item
-        if (mask_rowptr) {
-          mptr = mask_rowptr[row];
-          mend = mask_rowptr[row + 1];
-          const int first = P.id_off + t_begin * BN;
-          int lo = mptr, hi = mend;
-          while (lo < hi) {
-            const int mid = (lo + hi) >> 1;
-            if (mask_col[mid] < first) lo = mid + 1;
-            else hi = mid;
-          }
-          mptr = lo;
-          nxt = mptr < mend ? mask_col[mptr] : 0x7fffffff;
-          nxt2 = mptr + 1 < mend ? mask_col[mptr + 1] : 0x7fffffff;
-        }
         th = thr[row];
-        my_cand = cand + ((size_t)row * P.n_chunks + ch) * kCap;
+        my_cand = cand + (size_t)row * kCap;
       }
       // the filter pass prefetches its row's NB batch maxima of the coming tiles (an L2 round
       // trip is not short against a tile)
@@ -487,76 +469,65 @@ score_tc_kernel(const __grid_constant__ CUtensorMap tmU, const __grid_constant__
             bp[1] = make_float4(bm[4], bm[5], bm[6], bm[7]);
           }
         } else {
-          // mask words of this tile: train items of the row + columns beyond the catalogue
-          uint32_t mw[NB];
-#pragma unroll
-          for (int i = 0; i < NB; ++i) mw[i] = 0u;
-          {
-            const int g0 = P.id_off + t * BN, g1 = g0 + BN;
-            while (nxt < g1) {
-              const int b = nxt - g0;
-              if (b >= 0) {
-                const uint32_t bit = 1u << (b & 31);
-                const int ws = b >> 5;
-#pragma unroll
-                for (int i = 0; i < NB; ++i) mw[i] |= ws == i ? bit : 0u;
-              }
-              nxt = nxt2;
-              ++mptr;
-              nxt2 = mptr + 1 < mend ? mask_col[mptr + 1] : 0x7fffffff;
-            }
-            const int nv = P.n_items - t * BN;  // valid columns of this tile
-            if (nv < BN) {
-#pragma unroll
-              for (int i = 0; i < NB; ++i) {
-                const int r = nv - 32 * i;  // valid columns of batch i
-                mw[i] |= r <= 0 ? 0xffffffffu : (r < 32 ? ~((1u << r) - 1u) : 0u);
-              }
-            }
-          }
-          // only batches whose maximum reached the threshold for some row of the warp are read
-          // back from TMEM, and only the lanes concerned look at their 32 scores
-          uint32_t va[32];
-          timed_wait(BAR(TM_FULL + g), full_parity, 1);
-          tc_fence_after();
-#pragma unroll
-          for (int cb = 0; cb < NB; ++cb) {
+          // Same 64-column load pipeline as the maxima pass.  A batch is looked at only if its
+          // maximum reached the threshold for some row of the warp, and then only by the lanes
+          // concerned.  Train items are NOT filtered here (the re-rank kernel drops them): they
+          // only occupy candidate slots.  Padded columns score -inf.
+          auto scan = [&](const uint32_t *v, int cb) {
             const bool need = bmv[cb] >= th.y;
-            __syncwarp();
             if (__any_sync(0xffffffffu, need)) {
-              tmem_ld32(taddr + cb * 32, va);
-              tmem_ld_wait(va);
               if (need) {
                 const int gbase = P.id_off + t * BN + cb * 32;
-                const uint32_t mwb = mw[cb];
 #pragma unroll
                 for (int j4 = 0; j4 < 8; ++j4) {
-                  const float s0 = __uint_as_float(va[4 * j4 + 0]);
-                  const float s1 = __uint_as_float(va[4 * j4 + 1]);
-                  const float s2 = __uint_as_float(va[4 * j4 + 2]);
-                  const float s3 = __uint_as_float(va[4 * j4 + 3]);
+                  const float s0 = __uint_as_float(v[4 * j4 + 0]);
+                  const float s1 = __uint_as_float(v[4 * j4 + 1]);
+                  const float s2 = __uint_as_float(v[4 * j4 + 2]);
+                  const float s3 = __uint_as_float(v[4 * j4 + 3]);
                   if (fmaxf(fmaxf(s0, s1), fmaxf(s2, s3)) >= th.x) {
                     const float ss[4] = {s0, s1, s2, s3};
 #pragma unroll
                     for (int e = 0; e < 4; ++e) {
-                      const int j = 4 * j4 + e;
-                      if (ss[e] >= th.x && !((mwb >> j) & 1u)) {
-                        if (cnt < kCap)
-                          my_cand[cnt] = make_uint2(__float_as_uint(ss[e]), (uint32_t)(gbase + j));
-                        ++cnt;
+                      if (ss[e] >= th.x) {
+                        // ~1.5 K appends per row over the whole catalogue: the atomic is rare
+                        const int pos = atomicAdd(cand_cnt + row, 1);
+                        if (pos < kCap)
+                          my_cand[pos] =
+                              make_uint2(__float_as_uint(ss[e]), (uint32_t)(gbase + 4 * j4 + e));
                       }
                     }
                   }
                 }
               }
+              __syncwarp();
             }
-          }
-          tc_fence_before();
+          };
+          uint32_t va[64], vb[64];
+          timed_wait(BAR(TM_FULL + g), full_parity, 1);
+          tc_fence_after();
           __syncwarp();
-          if (lane == 0) mbar_arrive(BAR(TM_EMPTY + g));
+          tmem_ld64(taddr, va);
+          tmem_ld_wait64(va);
+#pragma unroll
+          for (int c4 = 0; c4 < NB / 4; ++c4) {
+            const int cb = 4 * c4;  // va holds batches cb, cb+1
+            tmem_ld64(taddr + (cb + 2) * 32, vb);
+            scan(va, cb);
+            scan(va + 32, cb + 1);
+            tmem_ld_wait64(vb);
+            if (cb + 4 < NB) {
+              tmem_ld64(taddr + (cb + 4) * 32, va);
+            } else {
+              tc_fence_before();
+              __syncwarp();
+              if (lane == 0) mbar_arrive(BAR(TM_EMPTY + g));
+            }
+            scan(vb, cb + 2);
+            scan(vb + 32, cb + 3);
+            if (cb + 4 < NB) tmem_ld_wait64(va);
+          }
         }
       }
-      if (MODE == MODE_FILTER && valid) cand_cnt[(size_t)row * P.n_chunks + ch] = cnt;
     }
     if (profiling && lane == 0 && q == 0) {  // one thread per warpgroup
       prof[12 + 4 * g] = pc[0], prof[13 + 4 * g] = pc[1], prof[14 + 4 * g] = clock64() - t_start;
@@ -642,16 +613,16 @@ __global__ void fill_user_aug_kernel(oper_t *__restrict__ aug) {
 }
 
 // thr[row] = {filter threshold, batch-skip threshold}, one warp per row.
-// Lane l takes the maximum over the batches b = l (mod 32) that hold no train item of the row
-// (bitmap in shared memory built from the row's mask list).  The 32 lane maxima come from
-// disjoint batches, so K of them exceed the K-th largest lane maximum m_K: the exact K-th best
-// score of the row is >= m_K - eps.  With y~ the tensor-core dot product of the gate-scaled item
+// The batches that hold no train item of the row (bitmap in shared memory built from the row's
+// mask list) are dealt round-robin into 64 groups, two per lane.  The 64 group maxima come from
+// disjoint batches, so K distinct unmasked items score at least the K-th largest group maximum
+// m_K: the exact K-th best score of the row is >= m_K - eps.  With y~ the tensor-core dot product of the gate-scaled item
 // row and y the fp32 FMA chain:  |y~ - sig*y| <= kappa * |u| * |sig*i|
 //   kappa = 1.5 * 2^-8  (two bf16 roundings 2^-9 each -> 2^-8 (1 + 2^-10) per product, products
 //   exact in fp32, plus fp32 accumulation of 64 terms on both sides and the gate pre-scale)
 // and the roundings of (sig*y - c*sig), with c*sig carried as three bf16 pieces (24 bits), versus
 // ((y - c) * sig) add at most 2^-22 * (|c| + |u||i|) per pass.  eps = eps(maxima pass) + eps(filter pass).
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(256, 4)
 row_threshold_kernel(const float *__restrict__ bmax, int T, int n_batches, int ld_tm, int K,
                      const int32_t *__restrict__ mask_rowptr, const int32_t *__restrict__ mask_col,
                      int id_off, int n_items, const float *__restrict__ unorm,
@@ -673,21 +644,34 @@ row_threshold_kernel(const float *__restrict__ bmax, int T, int n_batches, int l
     __syncwarp();
   }
   const float *row = bmax + (size_t)t * ld_tm;
-  float m = -INFINITY;
-  for (int b0 = 0; b0 < n_batches; b0 += 32) {
+  // 64 disjoint groups of batches, two per lane: group (b / 32) & 1 of lane b & 31
+  float m0 = -INFINITY, m1 = -INFINITY;
+  // unconditional (clamped) loads, 8 in flight per lane: this kernel is a latency-bound stream
+#pragma unroll 4
+  for (int b0 = 0; b0 < n_batches; b0 += 64) {
     const int b = b0 + lane;
-    const uint32_t word = bits[b0 >> 5];
-    if (b < n_batches && !((word >> lane) & 1u)) m = fmaxf(m, row[b]);
+    const float v0 = row[min(b, n_batches - 1)];
+    const float v1 = row[min(b + 32, n_batches - 1)];
+    const uint32_t w0 = bits[b0 >> 5];
+    const uint32_t w1 = bits[min((b0 >> 5) + 1, bm_words - 1)];
+    if (b < n_batches && !((w0 >> lane) & 1u)) m0 = fmaxf(m0, v0);
+    if (b + 32 < n_batches && !((w1 >> lane) & 1u)) m1 = fmaxf(m1, v1);
   }
-  // rank of this lane's maximum among the 32 (ties broken by lane) -> K-th largest
-  int rank = 0;
+  // rank of each group maximum among the 64 (ties broken by group index) -> K-th largest
+  int r0 = 0, r1 = 0;
 #pragma unroll
   for (int o = 0; o < 32; ++o) {
-    const float mo = __shfl_sync(0xffffffffu, m, o);
-    rank += (mo > m || (mo == m && o < lane)) ? 1 : 0;
+    const float a0 = __shfl_sync(0xffffffffu, m0, o);
+    const float a1 = __shfl_sync(0xffffffffu, m1, o);
+    r0 += (a0 > m0 || (a0 == m0 && o < lane)) ? 1 : 0;
+    r0 += (a1 > m0) ? 1 : 0;
+    r1 += (a0 > m1 || a0 == m1) ? 1 : 0;
+    r1 += (a1 > m1 || (a1 == m1 && o < lane)) ? 1 : 0;
   }
-  const unsigned who = __ballot_sync(0xffffffffu, rank == K - 1);
-  const float mk = __shfl_sync(0xffffffffu, m, __ffs(who) - 1);
+  const unsigned who0 = __ballot_sync(0xffffffffu, r0 == K - 1);
+  const unsigned who1 = __ballot_sync(0xffffffffu, r1 == K - 1);
+  const float mk = who0 ? __shfl_sync(0xffffffffu, m0, __ffs(who0) - 1)
+                        : __shfl_sync(0xffffffffu, m1, __ffs(who1) - 1);
   if (lane == 0) {
     float2 out = make_float2(-INFINITY, -INFINITY);
     if (mk > -INFINITY) {
@@ -701,12 +685,15 @@ row_threshold_kernel(const float *__restrict__ bmax, int T, int n_batches, int l
   }
 }
 
-// exact re-rank of the candidates of one row (one warp per row); rows whose lists overflowed are
-// queued for the exact fp32 kernel instead
-__global__ void __launch_bounds__(256)
+// exact re-rank of the candidates of one row (one warp per row): each lane fetches, mask-checks
+// (binary search in the row's sorted train list) and re-scores one candidate per round with the
+// fp32 FMA chain of score.cu; ranks come from counting.  Rows whose list overflowed are queued
+// for the exact fp32 kernel.
+__global__ void __launch_bounds__(256, 4)
 rerank_kernel(const float *__restrict__ Uq, int T, const float *__restrict__ It,
               const float *__restrict__ sig_i, const float *__restrict__ sig_u, float c, int id_off,
-              const uint2 *__restrict__ cand, const int *__restrict__ cand_cnt, int n_chunks, int K,
+              const int32_t *__restrict__ mask_rowptr, const int32_t *__restrict__ mask_col,
+              const uint2 *__restrict__ cand, const int *__restrict__ cand_cnt, int K,
               int32_t *__restrict__ out_ids, float *__restrict__ out_scores,
               int32_t *__restrict__ fb_rows, int *__restrict__ fb_count,
               unsigned long long *__restrict__ cand_total) {
@@ -714,39 +701,40 @@ rerank_kernel(const float *__restrict__ Uq, int T, const float *__restrict__ It,
   const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
   const int t = blockIdx.x * 8 + wib;
   if (t >= T) return;
-  const unsigned kmask = (K >= 32) ? 0xffffffffu : ((1u << K) - 1u);
-  bool overflow = false;
-  int total = 0;
-  for (int ch = lane; ch < n_chunks; ch += 32) {
-    const int cn = cand_cnt[(size_t)t * n_chunks + ch];
-    overflow |= cn > kCap;
-    total += min(cn, kCap);
-  }
-  overflow = __any_sync(0xffffffffu, overflow);
-  if (overflow) {
+  constexpr int kRounds = kCap / 32;  // candidates live in registers, 32 per round
+  const int total = cand_cnt[t];
+  if (total > kCap) {
     if (lane == 0) fb_rows[atomicAdd(fb_count, 1)] = t;
     return;
   }
-  if (cand_total) {
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) total += __shfl_xor_sync(0xffffffffu, total, o);
-    if (lane == 0) atomicAdd(cand_total, (unsigned long long)total);
-  }
+  if (cand_total && lane == 0) atomicAdd(cand_total, (unsigned long long)total);
   su[wib][lane] = Uq[(size_t)t * kD + lane];
   su[wib][lane + 32] = Uq[(size_t)t * kD + lane + 32];
   __syncwarp();
   const float sgu = sig_u[t];
-  float ls = -INFINITY;
-  int li = 0x7fffffff;
-  for (int ch = 0; ch < n_chunks; ++ch) {
-    const int cn = cand_cnt[(size_t)t * n_chunks + ch];
-    const uint2 *cl = cand + ((size_t)t * n_chunks + ch) * kCap;
-    for (int b0 = 0; b0 < cn; b0 += 32) {
-      const int e = b0 + lane;
-      float s = -INFINITY;
-      int gid = -1;
-      if (e < cn) {
-        gid = (int)cl[e].y;
+  const int mlo = mask_rowptr ? mask_rowptr[t] : 0, mhi = mask_rowptr ? mask_rowptr[t + 1] : 0;
+  float cs_[kRounds];
+  int cg_[kRounds];
+#pragma unroll
+  for (int r = 0; r < kRounds; ++r) {
+    cs_[r] = -INFINITY;
+    cg_[r] = 0x7fffffff;
+    const int e = r * 32 + lane;
+    if (e < total) {
+      const int gid = (int)cand[(size_t)t * kCap + e].y;
+      int lo = mlo, hi = mhi;
+      bool masked = false;
+      while (lo < hi) {
+        const int mid = (lo + hi) >> 1;
+        const int v = mask_col[mid];
+        if (v == gid) {
+          masked = true;
+          break;
+        }
+        if (v < gid) lo = mid + 1;
+        else hi = mid;
+      }
+      if (!masked) {
         const float4 *ip = reinterpret_cast<const float4 *>(It + (size_t)(gid - id_off) * kD);
         float acc = 0.f;
 #pragma unroll
@@ -757,22 +745,38 @@ rerank_kernel(const float *__restrict__ Uq, int T, const float *__restrict__ It,
           acc = fmaf(su[wib][4 * q4 + 2], v.z, acc);
           acc = fmaf(su[wib][4 * q4 + 3], v.w, acc);
         }
-        s = __fmul_rn(__fmul_rn(__fsub_rn(acc, c), sig_i[gid - id_off]), sgu);
+        cs_[r] = __fmul_rn(__fmul_rn(__fsub_rn(acc, c), sig_i[gid - id_off]), sgu);
+        cg_[r] = gid;
       }
-      const int nb = min(32, cn - b0);
-      for (int k = 0; k < nb; ++k) {
-        const float cs = __shfl_sync(0xffffffffu, s, k);
-        const int cid = __shfl_sync(0xffffffffu, gid, k);
-        const float ws = __shfl_sync(0xffffffffu, ls, K - 1);
-        const int wi = __shfl_sync(0xffffffffu, li, K - 1);
-        if (score_better(cs, cid, ws, wi)) score_list_insert(ls, li, cs, cid, lane, kmask, K);
+    }
+  }
+  // rank by counting: the order (score desc, lower id first) is strict among valid candidates
+  const int nr = (total + 31) >> 5;
+  int rank[kRounds];
+#pragma unroll
+  for (int r = 0; r < kRounds; ++r) rank[r] = 0;
+#pragma unroll
+  for (int r2 = 0; r2 < kRounds; ++r2) {
+    if (r2 < nr) {
+      for (int l2 = 0; l2 < 32; ++l2) {
+        const float os = __shfl_sync(0xffffffffu, cs_[r2], l2);
+        const int og = __shfl_sync(0xffffffffu, cg_[r2], l2);
+#pragma unroll
+        for (int r = 0; r < kRounds; ++r) rank[r] += score_better(os, og, cs_[r], cg_[r]) ? 1 : 0;
       }
     }
   }
   if (lane < K) {
-    const bool empty = li == 0x7fffffff;
-    out_ids[(size_t)t * K + lane] = empty ? -1 : li;
-    out_scores[(size_t)t * K + lane] = empty ? -INFINITY : ls;
+    out_ids[(size_t)t * K + lane] = -1;
+    out_scores[(size_t)t * K + lane] = -INFINITY;
+  }
+  __syncwarp();
+#pragma unroll
+  for (int r = 0; r < kRounds; ++r) {
+    if (cg_[r] != 0x7fffffff && rank[r] < K) {
+      out_ids[(size_t)t * K + rank[r]] = cg_[r];
+      out_scores[(size_t)t * K + rank[r]] = cs_[r];
+    }
   }
 }
 
@@ -878,8 +882,8 @@ static Plan make_plan(int T, long long n_items, int K) {
   p.off_misc = take(64);  // [0] item norm max (uint bits) [1] fb_count [2..3] cand_total (u64)
   p.off_tilemax = take((size_t)p.TB * p.ld_tm * 4);
   p.off_thr = take((size_t)p.TB * 8);
-  p.off_cand = take((size_t)p.TB * p.n_chunks * kCap * 8);
-  p.off_cnt = take((size_t)p.TB * p.n_chunks * 4);
+  p.off_cand = take((size_t)p.TB * kCap * 8);
+  p.off_cnt = take((size_t)p.TB * 4);
   p.off_fbrows = take((size_t)p.TB * 4);
   p.exact_bytes = score_exact_workspace_bytes(p.TB, n_items, K);
   p.off_exact = take(p.exact_bytes);
@@ -1011,11 +1015,12 @@ extern "C" int macr_score_topk_tc(const float *Uq, int T, const float *It, int64
         tilemax, nb, n_batches, p.ld_tm, K, mrp, mask_col, item_id_offset, (int)n_items, unorm,
         misc, c, kappa_sum, bm_words, thr);
     MACR_LAUNCH_CHECK();
+    MACR_CUDA(cudaMemsetAsync(cnt, 0, (size_t)nb * sizeof(int), s));
     rc = launch_pass<MODE_FILTER>(muh, mih, mua, mia, P, mrp, mask_col, tilemax, thr, cand, cnt, s);
     if (rc) return rc;
     MACR_CUDA(cudaMemsetAsync(fb_count, 0, sizeof(int), s));
     rerank_kernel<<<(nb + 7) / 8, 256, 0, s>>>(Ub, nb, It, sig_i, sig_u + t0, c, item_id_offset,
-                                               cand, cnt, p.n_chunks, K,
+                                               mrp, mask_col, cand, cnt, K,
                                                out_ids + (size_t)t0 * K, out_scores + (size_t)t0 * K,
                                                fb_rows, fb_count, cand_total);
     MACR_LAUNCH_CHECK();
