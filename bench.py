@@ -19,8 +19,9 @@ users = first B of rng.permutation(U), pos ~ Zipf(1.0) truncated to [0,I), neg ~
 
 N>1: the training step of this configuration does not shard profitably (a 40 us step), so the
 ranks run independent replicas ("replicas only", e.g. the c / alpha / beta sweep of tune.py) and
-`value` is their aggregate; `scoring` is item-sharded across the ranks with one NCCL all-gather of
-the per-shard top-K candidates and an on-device merge.
+`value` is their aggregate; `scoring` partitions the query users across the ranks (item table replicated, one
+all-gather of the [T,K] result); the item-partitioned layout (all-gather of per-shard candidates
++ on-device merge) is timed beside it.
 """
 import argparse
 import json
@@ -333,44 +334,90 @@ def main():
                          "frac": step_bytes / (ms_per_step * 1e-3) / 1e9 / peaks["hbm_gbs"],
                          "note": "whole step; the BxB grid kernel is MUFU-bound, not HBM-bound"}}
 
-    # ---------------- scoring: full catalogue, item-sharded across ranks ----------------
+    # ---------------- scoring: full catalogue counterfactual top-K ----------------
+    # headline: query users partitioned across the ranks, item table replicated (10.5 MB), no
+    # data-path collective, one all-gather of the [T,K] result; also timed: the item-partitioned
+    # layout (all-gather of the per-shard candidates + on-device merge).
     scoring = None
     if not args.no_scoring:
         T_q = N_TEST_USERS
         Us, Is, ws_, wus = synth_model(777)  # same model on every rank
         Us *= 10
         Is *= 10
-        from macr_b200.host.dist import ShardedScorer
+        from macr_b200.host.dist import ShardedScorer, UserShardedScorer
 
         dU = torch.from_numpy(Us).to(dev)
         q = torch.from_numpy(np.random.RandomState(5).permutation(N_USERS)[:T_q].astype(np.int32)).to(dev)
         mrp, mcol = synth_mask(9, T_q, 27)
         dmrp, dmcol = torch.from_numpy(mrp).to(dev), torch.from_numpy(mcol).to(dev)
         dw, dwu = torch.from_numpy(ws_).to(dev), torch.from_numpy(wus).to(dev)
-        # item table row-partitioned across the ranks (each rank keeps only its shard + its gates)
-        scorer = ShardedScorer(torch.from_numpy(Is).to(dev), dw, rank=rank, world=world)
+        dI = torch.from_numpy(Is).to(dev)
+        by_users = UserShardedScorer(dI, dw, rank=rank, world=world)
+        by_items = ShardedScorer(dI, dw, rank=rank, world=world)
 
-        def score_once():
-            Uq = ops.gather_rows(dU, q)
-            su = ops.score_gates(Uq, dwu)
-            return scorer.topk(Uq, su, 40.0, dmrp, dmcol, TOPK)
+        def time_scorer(scorer, reps=10):
+            def once():
+                Uq = ops.gather_rows(dU, q)
+                su = ops.score_gates(Uq, dwu)
+                return scorer.topk(Uq, su, 40.0, dmrp, dmcol, TOPK)
 
-        for _ in range(3):
-            score_once()
-        reps = 10
-        barrier()
-        s0, s1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        s0.record()
-        for _ in range(reps):
-            ids, sc = score_once()
-        s1.record()
-        barrier()
-        t_sc = max_over_ranks(s0.elapsed_time(s1) * 1e-3) / reps
+            for _ in range(3):
+                once()
+            barrier()
+            s0, s1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            s0.record()
+            for _ in range(reps):
+                ids, sc = once()
+            s1.record()
+            barrier()
+            return max_over_ranks(s0.elapsed_time(s1) * 1e-3) / reps, ids
+
+        t_sc, ids = time_scorer(by_users)
+        checksum = int(ids.to(torch.int64).sum().item())
+        # what the tensor-core pipeline did on this rank's slice (developer counters)
+        lo_u, hi_u = by_users.local_rows(T_q)
+        Uq_l = ops.gather_rows(dU, q)[lo_u:hi_u].contiguous()
+        su_l = ops.score_gates(Uq_l, dwu)
+        stats = torch.zeros(2, dtype=torch.int64, device=dev)
+        ops.score_topk_tc(Uq_l, dI, by_users.sig_i, su_l, 40.0, dmrp[lo_u:hi_u + 1].contiguous(), dmcol,
+                          TOPK, stats=stats)
+        st = stats.cpu().tolist()
+        n_pad = (N_ITEMS + 255) // 256 * 256
+        tc_flops = 2 * 2.0 * (D + 16) * T_q * n_pad  # two passes, K = 64 + 16 (augmented step)
         scoring = {"metric": "full_catalog_scores_per_sec", "value": T_q * N_ITEMS / t_sc,
                    "unit": "scores/s", "ms_per_eval": 1e3 * t_sc, "test_users": T_q,
-                   "items": N_ITEMS, "topk": TOPK, "sharding": f"items/{world}",
-                   "gflops": 2.0 * D * T_q * N_ITEMS / t_sc / 1e9,
-                   "checksum": int(ids.to(torch.int64).sum().item())}
+                   "items": N_ITEMS, "topk": TOPK, "sharding": f"users/{world}",
+                   "path": "tcgen05 bf16 maxima pass + filter pass, exact fp32 re-rank (bit-identical "
+                           "to the fp32 kernel)",
+                   "rows_redone_by_exact_kernel": st[0],
+                   "candidates_per_row": st[1] / max(1, hi_u - lo_u - st[0]),
+                   "roofline": {"bound": "tensor", "achieved": tc_flops / t_sc / 1e12,
+                                "peak": peaks.get("bf16_tflops"), "peak_kind": peak_kind,
+                                "unit": "TFLOP/s",
+                                "frac": tc_flops / t_sc / 1e12 / peaks["bf16_tflops"],
+                                "note": "whole call incl. operand prep, threshold and re-rank kernels; "
+                                        "flops = 2 passes x 2*(64+16)*T*I_pad"},
+                   "checksum": checksum}
+        if world > 1:
+            t_it, ids_it = time_scorer(by_items)
+            scoring["item_sharded"] = {"value": T_q * N_ITEMS / t_it, "ms_per_eval": 1e3 * t_it,
+                                       "sharding": f"items/{world}",
+                                       "checksum": int(ids_it.to(torch.int64).sum().item())}
+        else:
+            def exact_once():
+                Uq = ops.gather_rows(dU, q)
+                su = ops.score_gates(Uq, dwu)
+                return ops.score_topk_exact(Uq, dI, by_users.sig_i, su, 40.0, dmrp, dmcol, TOPK)
+
+            exact_once()
+            x0, x1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            x0.record()
+            for _ in range(3):
+                eids, _ = exact_once()
+            x1.record()
+            torch.cuda.synchronize()
+            scoring["exact_fp32_kernel"] = {"ms_per_eval": x0.elapsed_time(x1) / 3,
+                                            "checksum": int(eids.to(torch.int64).sum().item())}
 
     # ---------------- CPU baseline (rank 0, N=1 only) ----------------
     cpu = None

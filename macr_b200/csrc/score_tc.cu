@@ -843,8 +843,8 @@ static Plan make_plan(int T, long long n_items, int K) {
   Plan p;
   p.n_itiles = (int)((n_items + BN - 1) / BN);
   p.ld_tm = (NB * p.n_itiles + 31) / 32 * 32;  // NB batch maxima per item tile
-  // row block: tile maxima at most ~256 MiB
-  long long tb = (256LL << 20) / (4LL * p.ld_tm);
+  // row block: batch maxima at most ~1 GiB
+  long long tb = (1024LL << 20) / (4LL * p.ld_tm);
   tb = tb / BM * BM;
   if (tb < 1024) tb = 1024;
   if (tb > T) tb = T;

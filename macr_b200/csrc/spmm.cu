@@ -9,6 +9,9 @@
 // HBM/L2-bound: algorithmic bytes = 8*nnz + 4*(N+1) + 8*N*d.
 #include "spmm.cuh"
 
+#include <algorithm>
+#include <vector>
+
 namespace macr {
 
 __device__ __forceinline__ const float4 *row_ptr2(const RowSrc &s, long long r, int hl) {
@@ -16,33 +19,12 @@ __device__ __forceinline__ const float4 *row_ptr2(const RowSrc &s, long long r, 
   return reinterpret_cast<const float4 *>(base) + hl;
 }
 
-__global__ void __launch_bounds__(256)
-spmm_csr_kernel(const int32_t *__restrict__ rowptr, const int32_t *__restrict__ col,
-                const float *__restrict__ val, long long n_rows, RowSrc X,
-                const float *__restrict__ add, float *Y, RowSrc acc_in, float *acc_out,
-                float acc_div) {
-  const int lane = threadIdx.x & 31, hl = lane & 15;
-  const unsigned hmask = (lane < 16) ? 0x0000ffffu : 0xffff0000u;
-  const long long r = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 4;
-  if (r >= n_rows) return;
-  const int start = rowptr[r], end = rowptr[r + 1];
-  float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
-  for (int base = start; base < end; base += 16) {
-    const int e = base + hl;
-    const int c = e < end ? col[e] : 0;
-    const float a = e < end ? val[e] : 0.f;
-    const int cnt = min(16, end - base);
-#pragma unroll 4
-    for (int k = 0; k < cnt; ++k) {
-      const int cc = __shfl_sync(hmask, c, k, 16);
-      const float aa = __shfl_sync(hmask, a, k, 16);
-      const float4 x = *row_ptr2(X, cc, hl);
-      acc.x = fmaf(aa, x.x, acc.x);
-      acc.y = fmaf(aa, x.y, acc.y);
-      acc.z = fmaf(aa, x.z, acc.z);
-      acc.w = fmaf(aa, x.w, acc.w);
-    }
-  }
+constexpr int kLongRow = 256;  // rows with more nonzeros are summed by the whole CTA
+
+// Y[r] (+ epilogue) from the accumulated row `acc` (lane hl holds columns 4*hl .. 4*hl+3)
+__device__ __forceinline__ void spmm_epilogue(float4 acc, long long r, int hl,
+                                              const float *__restrict__ add, float *Y,
+                                              const RowSrc &acc_in, float *acc_out, float acc_div) {
   if (add) {
     const float4 t = reinterpret_cast<const float4 *>(add + r * kD)[hl];
     acc.x += t.x;
@@ -67,6 +49,209 @@ spmm_csr_kernel(const int32_t *__restrict__ rowptr, const int32_t *__restrict__ 
   }
 }
 
+// nonzeros [start, end) taken in groups of 16 with stride `stride` (in nonzeros)
+__device__ __forceinline__ float4 spmm_accumulate(const int32_t *__restrict__ col,
+                                                  const float *__restrict__ val, int start, int end,
+                                                  int stride, const RowSrc &X, int hl,
+                                                  unsigned hmask) {
+  float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+  for (int base = start; base < end; base += stride) {
+    const int e = base + hl;
+    const int c = e < end ? col[e] : 0;
+    const float a = e < end ? val[e] : 0.f;
+    const int cnt = min(16, end - base);
+#pragma unroll 4
+    for (int k = 0; k < cnt; ++k) {
+      const int cc = __shfl_sync(hmask, c, k, 16);
+      const float aa = __shfl_sync(hmask, a, k, 16);
+      const float4 x = *row_ptr2(X, cc, hl);
+      acc.x = fmaf(aa, x.x, acc.x);
+      acc.y = fmaf(aa, x.y, acc.y);
+      acc.z = fmaf(aa, x.z, acc.z);
+      acc.w = fmaf(aa, x.w, acc.w);
+    }
+  }
+  return acc;
+}
+
+// One CTA owns 16 consecutive rows.  Rows of at most kLongRow nonzeros: one half-warp per row,
+// nonzeros in order (the oracle's chain).  Longer rows (popular items: 27 504 nonzeros in
+// ml_10m) would leave one half-warp working long after the rest of the grid has drained, so
+// the 16 half-warps of the CTA take their 16-nonzero groups round-robin and the 16 partial rows
+// are summed through shared memory in a fixed order (deterministic; differs from the sequential
+// chain only in rounding).
+__global__ void __launch_bounds__(256)
+spmm_csr_kernel(const int32_t *__restrict__ rowptr, const int32_t *__restrict__ col,
+                const float *__restrict__ val, long long n_rows, RowSrc X,
+                const float *__restrict__ add, float *Y, RowSrc acc_in, float *acc_out,
+                float acc_div) {
+  __shared__ int s_start[16], s_end[16];
+  __shared__ float4 s_part[16][16];
+  const int lane = threadIdx.x & 31, hl = lane & 15, hw = threadIdx.x >> 4;
+  const unsigned hmask = (lane < 16) ? 0x0000ffffu : 0xffff0000u;
+  const long long r0 = (long long)blockIdx.x * 16;
+  const long long r = r0 + hw;
+  int start = 0, end = 0;
+  if (r < n_rows) {
+    start = rowptr[r];
+    end = rowptr[r + 1];
+  }
+  if (hl == 0) {
+    s_start[hw] = start;
+    s_end[hw] = end;
+  }
+  if (r < n_rows && end - start <= kLongRow) {
+    const float4 acc = spmm_accumulate(col, val, start, end, 16, X, hl, hmask);
+    spmm_epilogue(acc, r, hl, add, Y, acc_in, acc_out, acc_div);
+  }
+  __syncthreads();
+#pragma unroll 1
+  for (int j = 0; j < 16; ++j) {
+    const int st = s_start[j], en = s_end[j];
+    if (en - st <= kLongRow) continue;  // uniform across the CTA
+    s_part[hw][hl] = spmm_accumulate(col, val, st + hw * 16, en, 256, X, hl, hmask);
+    __syncthreads();
+    if (hw == 0) {
+      float4 acc = s_part[0][hl];
+#pragma unroll
+      for (int k = 1; k < 16; ++k) {
+        const float4 p = s_part[k][hl];
+        acc.x += p.x;
+        acc.y += p.y;
+        acc.z += p.z;
+        acc.w += p.w;
+      }
+      spmm_epilogue(acc, r0 + j, hl, add, Y, acc_in, acc_out, acc_div);
+    }
+    __syncthreads();
+  }
+}
+
+// ---- planned (segmented) variant ------------------------------------------------------------
+constexpr int kSegNnz = 64;
+
+// one half-warp per segment (<= 64 nonzeros: 4 groups of 16 gathers, all 16 of a group in flight)
+__global__ void __launch_bounds__(256)
+spmm_seg_kernel(const int32_t *__restrict__ seg_row, const int32_t *__restrict__ seg_start,
+                const int32_t *__restrict__ seg_end, const int32_t *__restrict__ seg_slot, int n_seg,
+                const int32_t *__restrict__ col, const float *__restrict__ val, RowSrc X,
+                const uint32_t *__restrict__ x_nonzero, const float *__restrict__ add, float *Y,
+                RowSrc acc_in, float *acc_out, float acc_div, float *__restrict__ partial) {
+  const int lane = threadIdx.x & 31, hl = lane & 15;
+  const unsigned hmask = (lane < 16) ? 0x0000ffffu : 0xffff0000u;
+  const int sg = (int)(((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 4);
+  if (sg >= n_seg) return;
+  const int start = seg_start[sg], end = seg_end[sg];
+  float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+  for (int base = start; base < end; base += 16) {
+    const int e = base + hl;
+    int c = e < end ? col[e] : -1;
+    const float a = e < end ? val[e] : 0.f;
+    if (x_nonzero && c >= 0 && !((x_nonzero[c >> 5] >> (c & 31)) & 1u)) c = -1;  // X row is zero
+#pragma unroll
+    for (int k = 0; k < 16; ++k) {
+      const int cc = __shfl_sync(hmask, c, k, 16);
+      const float aa = __shfl_sync(hmask, a, k, 16);
+      if (cc >= 0) {  // uniform across the half-warp
+        const float4 x = *row_ptr2(X, cc, hl);
+        acc.x = fmaf(aa, x.x, acc.x);
+        acc.y = fmaf(aa, x.y, acc.y);
+        acc.z = fmaf(aa, x.z, acc.z);
+        acc.w = fmaf(aa, x.w, acc.w);
+      }
+    }
+  }
+  const int slot = seg_slot[sg];
+  if (slot < 0) spmm_epilogue(acc, seg_row[sg], hl, add, Y, acc_in, acc_out, acc_div);
+  else reinterpret_cast<float4 *>(partial + (long long)slot * kD)[hl] = acc;
+}
+
+// rows cut into several segments: partial rows summed in segment order, then the epilogue
+__global__ void __launch_bounds__(256)
+spmm_combine_kernel(const int32_t *__restrict__ multi_row, const int32_t *__restrict__ multi_slot0,
+                    const int32_t *__restrict__ multi_nseg, int n_multi,
+                    const float *__restrict__ partial, const float *__restrict__ add, float *Y,
+                    RowSrc acc_in, float *acc_out, float acc_div) {
+  const int hl = threadIdx.x & 15;
+  const int m = (int)(((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 4);
+  if (m >= n_multi) return;
+  const float4 *p = reinterpret_cast<const float4 *>(partial + (long long)multi_slot0[m] * kD) + hl;
+  const int n = multi_nseg[m];
+  float4 acc = p[0];
+  for (int k = 1; k < n; ++k) {
+    const float4 t = p[(long long)k * (kD / 4)];
+    acc.x += t.x;
+    acc.y += t.y;
+    acc.z += t.z;
+    acc.w += t.w;
+  }
+  spmm_epilogue(acc, multi_row[m], hl, add, Y, acc_in, acc_out, acc_div);
+}
+
+// one-off, host side: the adjacency of a run never changes (LightGCN.py:257-269 builds it once)
+int build_spmm_plan(const int32_t *d_rowptr, int64_t n_rows, SpmmPlan *out) {
+  std::vector<int32_t> rp((size_t)n_rows + 1);
+  MACR_CUDA(cudaMemcpy(rp.data(), d_rowptr, sizeof(int32_t) * rp.size(), cudaMemcpyDeviceToHost));
+  std::vector<int32_t> srow, sstart, send, sslot, mrow, mslot0, mnseg;
+  int32_t n_slots = 0;
+  for (int64_t r = 0; r < n_rows; ++r) {
+    const int32_t st = rp[r], en = rp[r + 1];
+    const int32_t nseg = en - st <= kSegNnz ? 1 : (en - st + kSegNnz - 1) / kSegNnz;
+    if (nseg > 1) {
+      mrow.push_back((int32_t)r);
+      mslot0.push_back(n_slots);
+      mnseg.push_back(nseg);
+    }
+    for (int32_t k = 0; k < nseg; ++k) {
+      srow.push_back((int32_t)r);
+      sstart.push_back(st + k * kSegNnz);
+      send.push_back(std::min(en, st + (k + 1) * kSegNnz));
+      sslot.push_back(nseg > 1 ? n_slots++ : -1);
+    }
+  }
+  SpmmPlan p;
+  p.n_seg = (int)srow.size();
+  p.n_multi = (int)mrow.size();
+  auto up = [&](const std::vector<int32_t> &v, int32_t **dst) -> int {
+    MACR_CUDA(cudaMalloc(dst, sizeof(int32_t) * (v.size() + 1)));
+    MACR_CUDA(cudaMemcpy(*dst, v.data(), sizeof(int32_t) * v.size(), cudaMemcpyHostToDevice));
+    return MACR_OK;
+  };
+  int rc;
+  if ((rc = up(srow, &p.seg_row)) || (rc = up(sstart, &p.seg_start)) || (rc = up(send, &p.seg_end)) ||
+      (rc = up(sslot, &p.seg_slot)) || (rc = up(mrow, &p.multi_row)) ||
+      (rc = up(mslot0, &p.multi_slot0)) || (rc = up(mnseg, &p.multi_nseg)))
+    return rc;
+  MACR_CUDA(cudaMalloc(&p.partial, sizeof(float) * kD * ((size_t)n_slots + 1)));
+  *out = p;
+  return MACR_OK;
+}
+
+void free_spmm_plan(SpmmPlan *p) {
+  cudaFree(p->seg_row), cudaFree(p->seg_start), cudaFree(p->seg_end), cudaFree(p->seg_slot);
+  cudaFree(p->multi_row), cudaFree(p->multi_slot0), cudaFree(p->multi_nseg), cudaFree(p->partial);
+  *p = SpmmPlan();
+}
+
+int launch_spmm_planned(const SpmmPlan *plan, const int32_t *rowptr, const int32_t *col,
+                        const float *val, int64_t n_rows, RowSrc X, const float *add, float *Y,
+                        RowSrc acc_in, float *acc_out, float acc_div, const uint32_t *x_nonzero,
+                        cudaStream_t s) {
+  if (!plan) return launch_spmm(rowptr, col, val, n_rows, X, add, Y, acc_in, acc_out, acc_div, s);
+  if (plan->n_seg == 0) return MACR_OK;
+  spmm_seg_kernel<<<(unsigned)(((long long)plan->n_seg * 16 + 255) / 256), 256, 0, s>>>(
+      plan->seg_row, plan->seg_start, plan->seg_end, plan->seg_slot, plan->n_seg, col, val, X,
+      x_nonzero, add, Y, acc_in, acc_out, acc_div, plan->partial);
+  MACR_LAUNCH_CHECK();
+  if (plan->n_multi) {
+    spmm_combine_kernel<<<(unsigned)(((long long)plan->n_multi * 16 + 255) / 256), 256, 0, s>>>(
+        plan->multi_row, plan->multi_slot0, plan->multi_nseg, plan->n_multi, plan->partial, add, Y,
+        acc_in, acc_out, acc_div);
+    MACR_LAUNCH_CHECK();
+  }
+  return MACR_OK;
+}
+
 int launch_spmm(const int32_t *rowptr, const int32_t *col, const float *val, int64_t n_rows,
                 RowSrc X, const float *add, float *Y, RowSrc acc_in, float *acc_out,
                 float acc_div, cudaStream_t s) {
@@ -81,7 +266,8 @@ int launch_spmm(const int32_t *rowptr, const int32_t *col, const float *val, int
 
 int launch_lgcn_propagate(const int32_t *rowptr, const int32_t *col, const float *val,
                           const float *U, int64_t n_users, const float *I, int64_t n_items,
-                          int n_layers, float *Emean, float *tmp, cudaStream_t s) {
+                          int n_layers, float *Emean, float *tmp, cudaStream_t s,
+                          const SpmmPlan *plan) {
   const int64_t N = n_users + n_items;
   RowSrc e0{U, I, n_users};
   if (n_layers == 0) {
@@ -96,8 +282,8 @@ int launch_lgcn_propagate(const int32_t *rowptr, const int32_t *col, const float
     const bool last = k == n_layers - 1;
     float *y = last ? nullptr : buf[k & 1];
     RowSrc accin = (k == 0) ? e0 : RowSrc{Emean, Emean, N};
-    int rc = launch_spmm(rowptr, col, val, N, x, nullptr, y, accin, Emean,
-                         last ? (float)(n_layers + 1) : 0.f, s);
+    int rc = launch_spmm_planned(plan, rowptr, col, val, N, x, nullptr, y, accin, Emean,
+                                 last ? (float)(n_layers + 1) : 0.f, nullptr, s);
     if (rc) return rc;
     if (!last) x = RowSrc{y, y, N};
   }
@@ -108,7 +294,7 @@ int launch_lgcn_propagate(const int32_t *rowptr, const int32_t *col, const float
 __global__ void __launch_bounds__(256)
 scatter_rows_kernel(PlanBufs planU, const float *__restrict__ gU, PlanBufs planI,
                     const float *__restrict__ gI, int maxU, long long n_users, float div,
-                    float *__restrict__ out) {
+                    float *__restrict__ out, uint32_t *__restrict__ nz_bitmap) {
   const int lane = threadIdx.x & 31;
   const int wid = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   const bool item = wid >= maxU;
@@ -120,12 +306,15 @@ scatter_rows_kernel(PlanBufs planU, const float *__restrict__ gU, PlanBufs planI
   g.x = __fdiv_rn(g.x, div);
   g.y = __fdiv_rn(g.y, div);
   reinterpret_cast<float2 *>(out + r * kD)[lane] = g;
+  if (nz_bitmap && lane == 0) atomicOr(nz_bitmap + (r >> 5), 1u << (r & 31));
 }
 
 int launch_scatter_rows(PlanBufs planU, const float *gU, PlanBufs planI, const float *gI, int B,
-                        int64_t n_users, float div, float *out, cudaStream_t s) {
+                        int64_t n_users, float div, float *out, uint32_t *nz_bitmap,
+                        cudaStream_t s) {
   const int warps = 3 * B;
-  scatter_rows_kernel<<<(warps + 7) / 8, 256, 0, s>>>(planU, gU, planI, gI, B, n_users, div, out);
+  scatter_rows_kernel<<<(warps + 7) / 8, 256, 0, s>>>(planU, gU, planI, gI, B, n_users, div, out,
+                                                      nz_bitmap);
   MACR_LAUNCH_CHECK();
   return MACR_OK;
 }

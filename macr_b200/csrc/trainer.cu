@@ -372,6 +372,8 @@ struct macr_lgcn_trainer : macr::TrainerBase {
   const float *val;
   int L;
   float *Emean, *tmp, *g3;  // [N][64], 2x[N][64], [N][64]
+  uint32_t *g3_nz;          // bitmap: rows of g3 that hold a gradient this step
+  macr::SpmmPlan plan;      // static segment decomposition of the adjacency
   bool emb_dirty;
   int launches;
 };
@@ -395,13 +397,14 @@ static int lgcn_enqueue_impl(macr_lgcn_trainer *h, int B, int train) {
                             h->ni, h->planI, nullptr, side);
     if (rc) return rc;
     MACR_CUDA(cudaMemsetAsync(h->g3, 0, sizeof(float) * N * kD, side));
+    MACR_CUDA(cudaMemsetAsync(h->g3_nz, 0, sizeof(uint32_t) * ((N + 31) / 32), side));
     MACR_CUDA(cudaEventRecord(h->ev_join, side));
     launches += 1;
   }
   rc = launch_lgcn_propagate(h->rowptr, h->col, h->val, h->U, h->nu, h->I, h->ni, h->L, h->Emean,
-                             h->tmp, s);
+                             h->tmp, s, &h->plan);
   if (rc) return rc;
-  launches += h->L;
+  launches += h->L * (h->plan.n_multi ? 2 : 1);
   rc = launch_gather_dots(Ue, Ie, h->U, h->I, h->w, h->wu, nullptr, nullptr, nullptr, h->st, B, yp,
                           yn, sp, sn, su, rq, h->snap, &g, s);
   if (rc) return rc;
@@ -416,7 +419,7 @@ static int lgcn_enqueue_impl(macr_lgcn_trainer *h, int B, int train) {
                           nullptr, nullptr, s);
     if (rc) return rc;
     rc = launch_scatter_rows(h->planU, h->gU, h->planI, h->gI, B, h->nu, (float)(h->L + 1), h->g3,
-                             s);
+                             h->g3_nz, s);
     if (rc) return rc;
     launches += 2;
     // backward through the layer stack: acc_L = g3; acc_{k-1} = g3 + A^T acc_k  (A symmetric)
@@ -424,10 +427,12 @@ static int lgcn_enqueue_impl(macr_lgcn_trainer *h, int B, int train) {
     const float *acc = h->g3;
     for (int k = 0; k < h->L; ++k) {
       RowSrc x{acc, acc, N};
-      rc = launch_spmm(h->rowptr, h->col, h->val, N, x, h->g3, buf[k & 1], x, nullptr, 0.f, s);
+      // acc_L = g3 is row-sparse (<= 3B rows): nonzeros pointing at all-zero rows are skipped
+      rc = launch_spmm_planned(&h->plan, h->rowptr, h->col, h->val, N, x, h->g3, buf[k & 1], x,
+                               nullptr, 0.f, k == 0 ? h->g3_nz : nullptr, s);
       if (rc) return rc;
       acc = buf[k & 1];
-      launches += 1;
+      launches += h->plan.n_multi ? 2 : 1;
     }
     float *grad = const_cast<float *>(acc);
     const float lam = hp.decay / (float)hp.batch_size_flag;
@@ -487,6 +492,9 @@ extern "C" int macr_lgcn_trainer_create(macr_lgcn_trainer **out, const int32_t *
   MACR_CUDA(cudaMalloc(&h->Emean, sizeof(float) * ne));
   MACR_CUDA(cudaMalloc(&h->tmp, sizeof(float) * ne * 2));
   MACR_CUDA(cudaMalloc(&h->g3, sizeof(float) * ne));
+  MACR_CUDA(cudaMalloc(&h->g3_nz, sizeof(uint32_t) * ((size_t)(n_users + n_items + 31) / 32 + 1)));
+  rc = build_spmm_plan(rowptr, n_users + n_items, &h->plan);
+  if (rc) return rc;
   h->emb_dirty = true;
   MACR_CUDA(cudaStreamSynchronize(h->s));
   *out = h;
@@ -557,7 +565,7 @@ extern "C" int macr_lgcn_trainer_embeddings(macr_lgcn_trainer *h, const float **
   MACR_CHECK_ARG(h && Emean, "macr_lgcn_trainer_embeddings: null argument");
   if (h->emb_dirty) {
     int rc = launch_lgcn_propagate(h->rowptr, h->col, h->val, h->U, h->nu, h->I, h->ni, h->L,
-                                   h->Emean, h->tmp, h->s);
+                                   h->Emean, h->tmp, h->s, &h->plan);
     if (rc) return rc;
     h->emb_dirty = false;
   }
@@ -584,6 +592,8 @@ extern "C" int macr_lgcn_trainer_destroy(macr_lgcn_trainer *h) {
   cudaFree(h->Emean);
   cudaFree(h->tmp);
   cudaFree(h->g3);
+  cudaFree(h->g3_nz);
+  free_spmm_plan(&h->plan);
   delete h;
   return MACR_OK;
 }

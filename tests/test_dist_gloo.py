@@ -28,7 +28,7 @@ def _worker(rank, world, port, out_dir):
     os.environ["MASTER_ADDR"], os.environ["MASTER_PORT"] = "127.0.0.1", str(port)
     dist.init_process_group("gloo", rank=rank, world_size=world)
     try:
-        n_users, n_items, T, K = 120, 1001, 64, 20
+        n_users, n_items, T, K = 120, 1001, 63, 20  # odd T: ragged user slices
         U, I, w, wu = make_model(3, n_users, n_items, scale=8.0)
         q = np.random.RandomState(4).permutation(n_users)[:T]
         Uq = np.ascontiguousarray(U[q])
@@ -49,6 +49,16 @@ def _worker(rank, world, port, out_dir):
         want_i, want_s = oracle.score_topk(Uq, I, oracle.score_gates(I, w), sig_u, 40.0, mrp, mcol, K)
         np.testing.assert_array_equal(mi, want_i)
         np.testing.assert_array_equal(ms, want_s)
+        # user-partitioned layout: ragged row slices -> the full [T,K] result on every rank
+        ub = mdist.user_shard_bounds(T, world)
+        ulo, uhi = int(ub[rank]), int(ub[rank + 1])
+        sub_rp = (mrp[ulo:uhi + 1]).copy()  # absolute offsets into mcol stay valid
+        li, lsc = oracle.score_topk(np.ascontiguousarray(Uq[ulo:uhi]), I, oracle.score_gates(I, w),
+                                    np.ascontiguousarray(sig_u[ulo:uhi]), 40.0, sub_rp, mcol, K)
+        full_i = mdist.all_gather_rows(torch.from_numpy(li), T, world, rank)
+        full_s = mdist.all_gather_rows(torch.from_numpy(lsc), T, world, rank)
+        np.testing.assert_array_equal(full_i.numpy(), want_i)
+        np.testing.assert_array_equal(full_s.numpy(), want_s)
         # every rank ends with the same global list
         chk = torch.tensor([int(mi.astype(np.int64).sum())])
         both = [torch.zeros_like(chk) for _ in range(world)]
