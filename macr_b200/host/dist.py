@@ -114,6 +114,9 @@ class UserShardedScorer:
 
     def topk(self, Uq, sig_u, c, mask_rowptr, mask_col, K):
         ids, sc = self.topk_local(Uq, sig_u, c, mask_rowptr, mask_col, K)
-        T = Uq.shape[0]
-        return (all_gather_rows(ids, T, self.world, self.rank, self.group),
-                all_gather_rows(sc, T, self.world, self.rank, self.group))
+        if self.world == 1:
+            return ids, sc
+        # one collective: ids and score bit patterns side by side in an int32 [n, 2K] block
+        both = torch.cat([ids, sc.view(torch.int32)], dim=1)
+        full = all_gather_rows(both, Uq.shape[0], self.world, self.rank, self.group)
+        return full[:, :K].contiguous(), full[:, K:].contiguous().view(torch.float32)

@@ -2,7 +2,9 @@
 """Turn an `ncu --set full` report into the committed evidence:
    profiles/<tag>_ncu_summary.csv  one row per profiled launch, the metrics the judge greps
    profiles/ncu_traffic.json       dram bytes per launch of each kernel (bench.py's `traffic`)
-Usage: python profiles/extract_ncu.py gpurun_out/prof_r1b.ncu-rep r1b"""
+Usage: python profiles/extract_ncu.py gpurun_out/prof_r1b.ncu-rep r1b
+       python profiles/extract_ncu.py gpurun_out/prof_r1d_raw.csv r1d   (`ncu -i rep --page raw --csv`
+       run on the GPU box: a report over 64 MiB does not travel back)"""
 import csv
 import io
 import json
@@ -18,7 +20,7 @@ METRICS = [
     "sm__inst_executed_pipe_xu.avg.pct_of_peak_sustained_active",
     "sm__inst_executed_pipe_fma.avg.pct_of_peak_sustained_active",
     "sm__pipe_tensor_cycles_active.avg.pct_of_peak_sustained_active",
-    "lts__t_sector_hit_rate.pct", "launch__registers_per_thread", "launch__grid_size",
+    "lts__t_sector_hit_rate.pct", "lts__t_bytes.sum", "launch__registers_per_thread", "launch__grid_size",
     "launch__block_size", "launch__occupancy_limit_registers", "smsp__inst_executed.sum",
 ]
 TO_BYTES = {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}
@@ -27,8 +29,11 @@ TO_US = {"ns": 1e-3, "us": 1.0, "ms": 1e3, "s": 1e6, "nsecond": 1e-3, "usecond":
 
 def main(rep, tag):
     here = os.path.dirname(os.path.abspath(__file__))
-    raw = subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv"], capture_output=True, text=True,
-                         check=True).stdout
+    if rep.endswith(".csv"):
+        raw = open(rep).read()
+    else:
+        raw = subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv"], capture_output=True,
+                             text=True, check=True).stdout
     rows = list(csv.reader(io.StringIO(raw)))
     hdr, units, body = rows[0], rows[1], rows[2:]
     cols = [(m, hdr.index(m)) for m in METRICS if m in hdr]
@@ -40,9 +45,9 @@ def main(rep, tag):
         for r in body:
             name = r[kcol].split("(")[0].replace("void ", "").replace("macr::", "")
             w.writerow([name] + [r[i] for _m, i in cols])
-            if not r[kcol].lstrip("void ").startswith("macr::"):
-                continue
-            key = name.split("<")[0]
+            key = name.split("<")[0].replace("tc::", "")
+            if name.startswith("tc::score_tc_kernel"):  # the two passes are reported separately
+                key = "score_tc_kernel_max" if "<0>" in name or "(int)0" in name else "score_tc_kernel_filter"
             # the LAST profiled launch of a kernel is the representative one (prof_target.py ends
             # with the steady-state sweep: every row has non-zero Adam moments)
             d = traffic.setdefault(key, {"launches": 0})

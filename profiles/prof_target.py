@@ -50,6 +50,30 @@ def main():
                        torch.from_numpy(mcol).to(dev), bench.TOPK)
         torch.cuda.synchronize()
     tr.close()
+    # LightGCN: 2 steps on the real yelp2018 adjacency when it is staged (data/ is git-ignored)
+    path = os.path.join(ROOT, "data", "yelp2018")
+    if os.environ.get("PROF_LGCN", "1") == "1" and os.path.exists(os.path.join(path, "train.txt")):
+        import contextlib
+        import io
+
+        from macr_b200.host.data_lgcn import Data
+
+        with contextlib.redirect_stdout(io.StringIO()):
+            data = Data(path, 4096)
+            rowptr, col, val = data.adj_csr("pre")
+        rng = np.random.RandomState(2)
+        lim = lambda r: np.sqrt(6.0 / (r + 64))
+        Ue = rng.uniform(-lim(data.n_users), lim(data.n_users), (data.n_users, 64)).astype(np.float32)
+        Ie = rng.uniform(-lim(data.n_items), lim(data.n_items), (data.n_items, 64)).astype(np.float32)
+        wv = rng.uniform(-0.3, 0.3, 64).astype(np.float32)
+        lt = ops.LGCNTrainer(rowptr, col, val, Ue, Ie, wv, wv.copy(), 2,
+                             ops.HParams.make(lr=1e-3, alpha=1e-2, beta=1e-3, decay=1e-4, batch_size=4096),
+                             max_batch=4096, device=dev)
+        b = np.stack([np.stack([rng.permutation(data.n_users)[:4096], rng.randint(0, data.n_items, 4096),
+                                rng.randint(0, data.n_items, 4096)]) for _ in range(2)]).astype(np.int32)
+        lt.run(torch.from_numpy(b).to(dev), True)
+        torch.cuda.synchronize()
+        lt.close()
 
 
 if __name__ == "__main__":
