@@ -167,6 +167,13 @@ int macr_mf_trainer_step_host(macr_mf_trainer *h, const int32_t *users_host,
  * float [n_steps][4].  Replays the captured step graph n_steps times; asynchronous.  */
 int macr_mf_trainer_run(macr_mf_trainer *h, const int32_t *batches, int n_steps, int B,
                         float *losses);
+/* the same epoch with the batches in HOST memory (pinned recommended): one H2D copy of
+ * [n_steps][3][B] ids, n_steps graph replays, one D2H copy of the [n_steps][4] losses
+ * {loss, mf_loss, reg_loss, L_ori}, stream-synchronised before return.  The sampler of
+ * train.py:471 consumes only its own RNG streams, so staging an epoch of sampled batches
+ * and running them in one call gives the results of the per-step loop.              */
+int macr_mf_trainer_run_host(macr_mf_trainer *h, const int32_t *batches_host, int n_steps, int B,
+                             float *losses_host);
 /* number of this library's kernels launched by one step (for bench gpu_launches) */
 int macr_mf_trainer_launches_per_step(const macr_mf_trainer *h);
 int64_t macr_mf_trainer_steps_done(const macr_mf_trainer *h);
@@ -209,6 +216,9 @@ int macr_lgcn_trainer_step_host(macr_lgcn_trainer *h, const int32_t *users_host,
                                 int train, float *losses_host /*[3]*/);
 int macr_lgcn_trainer_run(macr_lgcn_trainer *h, const int32_t *batches, int n_steps, int B,
                           int train, float *losses);
+/* host-memory variant of macr_lgcn_trainer_run, see macr_mf_trainer_run_host */
+int macr_lgcn_trainer_run_host(macr_lgcn_trainer *h, const int32_t *batches_host, int n_steps,
+                               int B, int train, float *losses_host);
 /* propagated tables of the current parameters (device, owned by the handle):
  * users at Emean, items at Emean + n_users*d                                     */
 int macr_lgcn_trainer_embeddings(macr_lgcn_trainer *h, const float **Emean);

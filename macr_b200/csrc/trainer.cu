@@ -57,6 +57,10 @@ struct TrainerBase {
   const int32_t *cur_ids_base;
   float *cur_loss_base;
   bool single_mode_set;
+  // epoch staging of *_run_host: device copies of the host batches / losses, grown on demand
+  int32_t *epoch_ids = nullptr;
+  float *epoch_losses = nullptr, *epoch_losses_pinned = nullptr;
+  size_t epoch_ids_cap = 0, epoch_loss_cap = 0;
   std::map<int, cudaGraphExec_t> graphs;       // train step, keyed by B
   std::map<int, cudaGraphExec_t> graphs_eval;  // loss-only step (LightGCN test loss)
 
@@ -125,6 +129,7 @@ struct TrainerBase {
     cudaFree(st); cudaFree(ids_stage); cudaFree(loss_stage); cudaFree(scal); cudaFree(gridws);
     cudaFree(plan_mem); cudaFree(snap); cudaFree(tail_ticket); cudaFree(unit_part); cudaFree(gU); cudaFree(gI); cudaFree(gw_part); cudaFree(gwu_part);
     cudaFreeHost(pinned_losses);
+    cudaFree(epoch_ids); cudaFree(epoch_losses); cudaFreeHost(epoch_losses_pinned);
     cudaEventDestroy(ev_fork); cudaEventDestroy(ev_join);
     cudaEventDestroy(ev_join2);
     cudaStreamDestroy(side);
@@ -331,6 +336,51 @@ extern "C" int macr_mf_trainer_step_host(macr_mf_trainer *h, const int32_t *user
                             cudaMemcpyDeviceToHost, h->s));
   MACR_CUDA(cudaStreamSynchronize(h->s));
   if (losses_host) memcpy(losses_host, h->pinned_losses, sizeof(float) * 3);
+  return MACR_OK;
+}
+
+// host batches [n_steps][3][B] -> device (one copy), n_steps graph replays, losses [n_steps][4]
+// back to the host (one copy), one synchronisation
+template <class H, class F>
+static int run_steps_host(H *h, std::map<int, cudaGraphExec_t> &cache, F enq,
+                          const int32_t *batches_host, int n_steps, int B, float *losses_host) {
+  MACR_CHECK_ARG(B > 0 && B <= h->maxB, "trainer: batch %d outside (0,%d]", B, h->maxB);
+  MACR_CHECK_ARG(n_steps >= 0, "trainer: negative step count");
+  if (n_steps == 0) return MACR_OK;
+  const size_t n_ids = (size_t)n_steps * 3 * (size_t)B, n_loss = (size_t)n_steps * 4;
+  if (n_ids > h->epoch_ids_cap) {
+    cudaFree(h->epoch_ids);
+    h->epoch_ids = nullptr;
+    h->epoch_ids_cap = 0;
+    MACR_CUDA(cudaMalloc(&h->epoch_ids, sizeof(int32_t) * n_ids));
+    h->epoch_ids_cap = n_ids;
+  }
+  if (n_loss > h->epoch_loss_cap) {
+    cudaFree(h->epoch_losses);
+    cudaFreeHost(h->epoch_losses_pinned);
+    h->epoch_losses = h->epoch_losses_pinned = nullptr;
+    h->epoch_loss_cap = 0;
+    MACR_CUDA(cudaMalloc(&h->epoch_losses, sizeof(float) * n_loss));
+    MACR_CUDA(cudaMallocHost(&h->epoch_losses_pinned, sizeof(float) * n_loss));
+    h->epoch_loss_cap = n_loss;
+  }
+  MACR_CUDA(cudaMemcpyAsync(h->epoch_ids, batches_host, sizeof(int32_t) * n_ids,
+                            cudaMemcpyHostToDevice, h->s));
+  int rc = run_steps(h, cache, enq, h->epoch_ids, n_steps, B, h->epoch_losses);
+  if (rc) return rc;
+  MACR_CUDA(cudaMemcpyAsync(h->epoch_losses_pinned, h->epoch_losses, sizeof(float) * n_loss,
+                            cudaMemcpyDeviceToHost, h->s));
+  MACR_CUDA(cudaStreamSynchronize(h->s));
+  if (losses_host) memcpy(losses_host, h->epoch_losses_pinned, sizeof(float) * n_loss);
+  return MACR_OK;
+}
+
+extern "C" int macr_mf_trainer_run_host(macr_mf_trainer *h, const int32_t *batches_host,
+                                        int n_steps, int B, float *losses_host) {
+  MACR_CHECK_ARG(h && batches_host, "macr_mf_trainer_run_host: null argument");
+  int rc = run_steps_host(h, h->graphs, mf_enqueue, batches_host, n_steps, B, losses_host);
+  if (rc) return rc;
+  h->steps_done += n_steps;
   return MACR_OK;
 }
 
@@ -553,6 +603,21 @@ extern "C" int macr_lgcn_trainer_run(macr_lgcn_trainer *h, const int32_t *batche
   MACR_CHECK_ARG(h && batches && losses, "macr_lgcn_trainer_run: null argument");
   int rc = train ? run_steps(h, h->graphs, lgcn_enqueue_train, batches, n_steps, B, losses)
                  : run_steps(h, h->graphs_eval, lgcn_enqueue_eval, batches, n_steps, B, losses);
+  if (rc) return rc;
+  if (train && n_steps > 0) {
+    h->steps_done += n_steps;
+    h->emb_dirty = true;
+  }
+  return MACR_OK;
+}
+
+extern "C" int macr_lgcn_trainer_run_host(macr_lgcn_trainer *h, const int32_t *batches_host,
+                                          int n_steps, int B, int train, float *losses_host) {
+  MACR_CHECK_ARG(h && batches_host, "macr_lgcn_trainer_run_host: null argument");
+  int rc = train ? run_steps_host(h, h->graphs, lgcn_enqueue_train, batches_host, n_steps, B,
+                                  losses_host)
+                 : run_steps_host(h, h->graphs_eval, lgcn_enqueue_eval, batches_host, n_steps, B,
+                                  losses_host);
   if (rc) return rc;
   if (train && n_steps > 0) {
     h->steps_done += n_steps;

@@ -236,6 +236,9 @@ class _Tables:
 class MFTrainer:
     """Handle around macr_mf_trainer_* (one `--train rubibceboth` model)."""
 
+    def _run_host(self, n, B, ids_ptr, loss_ptr):
+        return lib().macr_mf_trainer_run_host(self._h, ids_ptr, n, B, loss_ptr)
+
     def __init__(self, U, I, w, wu, hp, max_batch, device="cuda:0"):
         self.dev = torch.device(device)
         torch.cuda.set_device(self.dev)
@@ -295,6 +298,17 @@ class MFTrainer:
               "macr_mf_trainer_run")
         return losses
 
+    def run_host(self, batches_host, losses_host=None):
+        """Epoch call with HOST buffers: `batches_host` int32 [n,3,B] (pinned recommended) ->
+        float32 [n,4] host losses; one H2D, n graph replays, one D2H, synchronised."""
+        n, three, B = batches_host.shape
+        assert three == 3 and batches_host.dtype == torch.int32 and not batches_host.is_cuda
+        if losses_host is None:
+            losses_host = torch.empty((n, 4), dtype=torch.float32)
+        check(self._run_host(n, B, C.c_void_p(batches_host.data_ptr()),
+                             C.c_void_p(losses_host.data_ptr())), "trainer_run_host")
+        return losses_host
+
     @property
     def launches_per_step(self):
         return int(lib().macr_mf_trainer_launches_per_step(self._h))
@@ -320,6 +334,9 @@ class MFTrainer:
 
 class LGCNTrainer:
     """Handle around macr_lgcn_trainer_* (one `--loss bceboth` LightGCN model)."""
+
+    def _run_host(self, n, B, ids_ptr, loss_ptr, train=True):
+        return lib().macr_lgcn_trainer_run_host(self._h, ids_ptr, n, B, 1 if train else 0, loss_ptr)
 
     def __init__(self, rowptr, col, val, U, I, w, wu, n_layers, hp, max_batch, device="cuda:0"):
         self.dev = torch.device(device)
@@ -380,6 +397,17 @@ class LGCNTrainer:
         nu, ni, d = self.tab.U.shape[0], self.tab.I.shape[0], self.tab.U.shape[1]
         E = _wrap_device_ptr(out.value, (nu + ni, d), self.dev)
         return E[:nu], E[nu:]
+
+    def run_host(self, batches_host, losses_host=None):
+        """Epoch call with HOST buffers: `batches_host` int32 [n,3,B] (pinned recommended) ->
+        float32 [n,4] host losses; one H2D, n graph replays, one D2H, synchronised."""
+        n, three, B = batches_host.shape
+        assert three == 3 and batches_host.dtype == torch.int32 and not batches_host.is_cuda
+        if losses_host is None:
+            losses_host = torch.empty((n, 4), dtype=torch.float32)
+        check(self._run_host(n, B, C.c_void_p(batches_host.data_ptr()),
+                             C.c_void_p(losses_host.data_ptr())), "trainer_run_host")
+        return losses_host
 
     @property
     def launches_per_step(self):

@@ -201,3 +201,27 @@ def test_cli_drivers_run_end_to_end(tmp_path, monkeypatch, capsys):
     out = capsys.readouterr().out
     assert "c:2.00 recall=[" in out and "use the pre adjcency matrix" in out
     assert res["last"] is not None and 0 <= res["best_hr"] <= 1
+
+
+def test_epoch_run_host_equals_device_run():
+    """`macr_mf_trainer_run_host` (host batches, one H2D / D2H) == `macr_mf_trainer_run`."""
+    import torch
+
+    from helpers import make_batch, make_model
+    from macr_b200 import ops
+
+    n_users, n_items, B, n = 900, 500, 256, 5
+    U, I, w, wu = make_model(31, n_users, n_items, scale=4.0)
+    rng = np.random.RandomState(32)
+    batches = np.stack([np.stack(make_batch(rng, n_users, n_items, B)) for _ in range(n)]).astype(np.int32)
+    hp = ops.HParams.make(lr=1e-3, alpha=1e-2, beta=1e-3, decay=1e-5, batch_size=B)
+    a = ops.MFTrainer(U, I, w, wu, hp, max_batch=B)
+    b = ops.MFTrainer(U, I, w, wu, hp, max_batch=B)
+    la = a.run(torch.from_numpy(batches).cuda()).cpu().numpy()
+    lb = b.run_host(torch.from_numpy(batches).pin_memory()).numpy()
+    np.testing.assert_array_equal(la, lb)
+    for x, y in zip(a.tab.all(), b.tab.all()):
+        assert torch.equal(x, y)
+    assert b.steps_done == n
+    a.close()
+    b.close()
