@@ -43,6 +43,8 @@ N_TEST_USERS = 15424
 TOPK = 20
 HP = dict(lr=1e-3, alpha=1e-2, beta=1e-3, decay=1e-5, batch_size=BATCH)  # README.md:40
 N_BATCHES = 200
+WORKLOAD = ("MACR-MF gowalla-shape U=29858 I=40981 d=64 B=4096 rubibceboth alpha=1e-2 beta=1e-3 "
+            "regs=1e-5 lr=1e-3 (BASELINE configs[1])")
 
 
 def synth_model(seed):
@@ -98,7 +100,7 @@ class ClockSampler(threading.Thread):
                 self.rows.append([x.strip() for x in out.strip().split(",")])
             except Exception:
                 pass
-            self._stop_evt.wait(0.2)
+            self._stop_evt.wait(0.05)
 
     def stop(self):
         self._stop_evt.set()
@@ -170,8 +172,8 @@ def run_reference(args):
         "unit": "interactions/s", "n_gpus": args.gpus, "steps": steps, "warmup": 1,
         "ms_per_step": ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "f32", "data": "synthetic",
-        "config": {"workload": "MACR-MF gowalla-shape U=29858 I=40981 d=64 B=4096 rubibceboth "
-                               "(one training step; oracle port of the TF-1.14 CPU path)"},
+        "config": {"workload": WORKLOAD,
+                   "arm": "oracle port (C + OpenMP) of the TF-1.14 CPU path, one training step per step"},
         "cpu_baseline": {"value": val, "unit": "interactions/s", "cores": threads, "kind": "port",
                          "sample": f"{steps} steps of B=4096 after 1 warm-up step"},
         "e2e": {"value": val, "unit": "interactions/s", "h2d_bytes_per_step": 0,
@@ -446,8 +448,7 @@ def main():
             "unit": "interactions/s", "n_gpus": world, "steps": K, "warmup": W,
             "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": {"workload": "MACR-MF gowalla-shape U=29858 I=40981 d=64 B=4096 rubibceboth "
-                                   "alpha=1e-2 beta=1e-3 regs=1e-5 lr=1e-3 (BASELINE configs[1])",
+            "config": {"workload": WORKLOAD,
                        "l2": "256 MiB memset between timed steps (tables fit the 126 MB L2)",
                        "parallelism": "replicas only" if world > 1 else "single GPU",
                        "batches_resident": nb},

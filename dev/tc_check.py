@@ -49,6 +49,38 @@ def run(T_users, n_items, K, c, mask_deg, splits, scale=10.0, seed=0, time_it=Fa
     return bad_rows == 0 and bad_sc == 0
 
 
+def run_trained_like():
+    """large norms, low-rank + popularity structure (what trained tables look like), c sweep"""
+    dev = torch.device("cuda")
+    rng = np.random.RandomState(3)
+    T_users, n_items, K = 4096, 40981, 20
+    ok = True
+    for scale, rank in ((1.0, 8), (3.0, 16), (0.3, 64)):
+        Z = rng.randn(T_users, rank).astype(np.float32)
+        Wm = rng.randn(rank, 64).astype(np.float32)
+        U = (Z @ Wm * scale / np.sqrt(rank)).astype(np.float32)
+        pop = rng.pareto(1.2, n_items).astype(np.float32)
+        I = ((rng.randn(n_items, rank).astype(np.float32) @ Wm) * scale / np.sqrt(rank) *
+             (1.0 + 0.2 * np.log1p(pop))[:, None]).astype(np.float32)
+        w = (rng.randn(64) * 0.1).astype(np.float32)
+        wu = (rng.randn(64) * 0.1).astype(np.float32)
+        lists = make_interactions(11, T_users, n_items, 40)
+        a, b = lists_to_csr(lists)
+        dU, dI = torch.from_numpy(U).to(dev), torch.from_numpy(I).to(dev)
+        si, su = ops.score_gates(dI, torch.from_numpy(w).to(dev)), ops.score_gates(dU, torch.from_numpy(wu).to(dev))
+        mrp, mcol = torch.from_numpy(a).to(dev), torch.from_numpy(b).to(dev)
+        for c in (40.0, 0.0, 10.0):
+            ei, es = ops.score_topk_exact(dU, dI, si, su, c, mrp, mcol, K)
+            st = torch.zeros(2, dtype=torch.int64, device=dev)
+            ti, ts = ops.score_topk_tc(dU, dI, si, su, c, mrp, mcol, K, stats=st)
+            good = bool((ti == ei).all().item() and (ts == es).all().item())
+            print(f"trained-like scale={scale} rank={rank} c={c}: {'ok' if good else 'MISMATCH'} "
+                  f"|u|~{np.linalg.norm(U, axis=1).mean():.2f} |i|~{np.linalg.norm(I, axis=1).mean():.2f} "
+                  f"fallback {st[0].item()} cand/row {st[1].item() / max(1, T_users - st[0].item()):.1f}", flush=True)
+            ok &= good
+    return ok
+
+
 def run_special():
     """heavy train lists, all-equal scores (overflow -> exact fallback), sharded ids, negative c"""
     dev = torch.device("cuda")
@@ -114,4 +146,5 @@ if __name__ == "__main__":
     ok &= run(15424, 40981, 20, 40.0, 27, (1, 1), time_it=True)
     ok &= run(15424, 40981, 20, 40.0, 27, (3, 3), time_it=True)
     ok &= run_special()
+    ok &= run_trained_like()
     print("ALL OK" if ok else "FAILURES")
