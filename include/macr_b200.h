@@ -303,6 +303,29 @@ int macr_foldout_metrics(const int32_t *topk_ids, int T, int K,
                          const int32_t *truth_rowptr, const int32_t *truth_col,
                          const double *inv_log2, float *out, macr_stream_t stream);
 
+/* ------------------------------------------------------------------------- *
+ * Batch samplers (host code, no GPU work): bit-exact twins of
+ *   Data.sample()  macr_mf/load_data.py:543-566            (CPython `random`)
+ *   Data.sample()  macr_lightgcn/utility/load_data.py:174-212
+ *                  (`random.sample` for users, legacy `np.random.randint(size=1)` for items)
+ * py_state / np_state: uint32[625] = the 624 Mersenne-Twister words + the position, i.e.
+ * random.getstate()[1] and np.random.get_state()[1:3]; advanced in place -- put them back with
+ * random.setstate / np.random.set_state and the interpreter-side generators continue exactly
+ * where the reference's would.  users_pop: the population list (`self.users` /
+ * `self.exist_users`, list order); n_users: the `batch_size <= n_users` test of the reference.
+ * rowptr/order: per-user positive lists in the reference's list order (int64 CSR over user id);
+ * sorted / ban_sorted: the ids the negative draw rejects, ascending per user.
+ * Out: users, pos, neg int32[B].
+ * ------------------------------------------------------------------------- */
+int macr_sample_mf(uint32_t *py_state, const int32_t *users_pop, int n_pop, int n_users,
+                   int n_items, const int64_t *rowptr, const int32_t *order,
+                   const int32_t *sorted, int B, int32_t *users, int32_t *pos, int32_t *neg);
+int macr_sample_lgcn(uint32_t *py_state, uint32_t *np_state, const int32_t *users_pop, int n_pop,
+                     int n_users, int n_items, const int64_t *pos_rowptr,
+                     const int32_t *pos_order, const int64_t *ban_rowptr,
+                     const int32_t *ban_sorted, int B, int32_t *users, int32_t *pos,
+                     int32_t *neg);
+
 #ifdef __cplusplus
 }
 #endif

@@ -83,6 +83,8 @@ PROTOTYPES = {
     "macr_topk_merge": (i32, [vp, vp, i32, i32, i32, vp, vp, vp]),
     "macr_topk_rows": (i32, [vp, i32, i32, i32, vp, vp]),
     "macr_foldout_metrics": (i32, [vp, i32, i32, vp, vp, vp, vp, vp]),
+    "macr_sample_mf": (i32, [vp, vp, i32, i32, i32, vp, vp, vp, i32, vp, vp, vp]),
+    "macr_sample_lgcn": (i32, [vp, vp, vp, i32, i32, i32, vp, vp, vp, vp, i32, vp, vp, vp]),
 }
 
 

@@ -74,15 +74,23 @@ def main(argv=None):
         t1 = time()
         loss, mf_loss, reg_loss = 0.0, 0.0, 0.0
         n_batch = data.n_train // args.batch_size + 1
-        for _ in range(n_batch):
-            users, pos_items, neg_items = data.sample()
-            _, batch_loss, batch_mf_loss, batch_reg_loss = sess.run(
-                [model.opt_two_bce_both, model.loss_two_bce_both, model.mf_loss_two_bce_both,
-                 model.reg_loss_two_bce_both],
-                feed_dict={model.users: users, model.pos_items: pos_items, model.neg_items: neg_items})
-            loss += batch_loss / n_batch
-            mf_loss += batch_mf_loss / n_batch
-            reg_loss += batch_reg_loss / n_batch
+        if os.environ.get("MACR_STEPWISE") == "1":  # the literal loop of train.py:470-499
+            for _ in range(n_batch):
+                users, pos_items, neg_items = data.sample()
+                _, batch_loss, batch_mf_loss, batch_reg_loss = sess.run(
+                    [model.opt_two_bce_both, model.loss_two_bce_both, model.mf_loss_two_bce_both,
+                     model.reg_loss_two_bce_both],
+                    feed_dict={model.users: users, model.pos_items: pos_items, model.neg_items: neg_items})
+                loss += batch_loss / n_batch
+                mf_loss += batch_mf_loss / n_batch
+                reg_loss += batch_reg_loss / n_batch
+        else:
+            # same triples (the sampler consumes only its own RNG stream), same steps, same sums:
+            # the epoch is sampled natively, staged once and run as one call
+            for bl in model.train_epoch(data.sample_epoch(n_batch)):
+                loss += float(bl[0]) / n_batch
+                mf_loss += float(bl[1]) / n_batch
+                reg_loss += float(bl[2]) / n_batch
         if np.isnan(loss):
             print("ERROR: loss is nan.")
             sys.exit()

@@ -146,6 +146,28 @@ class Data:
         return users, pos_items, neg_items
 
     def sample(self):
+        """utility/load_data.py:174-212 through the native sampler (same `random` and
+        `np.random` streams, bit-identical triples); `sample_py` is the Python restatement."""
+        from . import native_sampler as ns
+
+        if getattr(self, "_ns_train", None) is None:
+            self._ns_train = ns.ListCSR(self.train_items, self.n_users)
+            self._ns_pop = np.asarray(self.exist_users, np.int32)
+        u, p, n = ns.sample_lgcn(self._ns_pop, self.n_users, self.n_items, self._ns_train,
+                                 self._ns_train, self.batch_size)
+        return u.tolist(), p.tolist(), n.tolist()
+
+    def sample_epoch(self, n_batches, out=None):
+        """`n_batches` consecutive sample() calls -> int32 [n_batches, 3, B]."""
+        from . import native_sampler as ns
+
+        if getattr(self, "_ns_train", None) is None:
+            self._ns_train = ns.ListCSR(self.train_items, self.n_users)
+            self._ns_pop = np.asarray(self.exist_users, np.int32)
+        return ns.sample_lgcn_epoch(self._ns_pop, self.n_users, self.n_items, self._ns_train,
+                                    self._ns_train, self.batch_size, n_batches, out)
+
+    def sample_py(self):
         B = self.batch_size
         if B <= self.n_users:
             users = random.sample(self.exist_users, B)
@@ -154,9 +176,21 @@ class Data:
         return self._draw(users, self.train_items, self._train_set)
 
     def sample_test(self):
-        """load_data.py:214-257 (the test-loss pass of LightGCN.py:799-819).  The reference
-        passes dict_keys to random.sample -- a TypeError on Python >= 3.11; list(keys) draws the
-        same stream."""
+        """load_data.py:214-257 (the test-loss pass of LightGCN.py:799-819) through the native
+        sampler.  The reference passes dict_keys to random.sample -- a TypeError on Python >=
+        3.11; list(keys) draws the same stream."""
+        from . import native_sampler as ns
+
+        if getattr(self, "_ns_test", None) is None:
+            self._ns_test = ns.ListCSR(self.test_set, self.n_users)
+            both = {u: list(set(v) | set(self.train_items.get(u, ()))) for u, v in self.test_set.items()}
+            self._ns_test_ban = ns.ListCSR(both, self.n_users)
+            self._ns_test_pop = np.asarray(list(self.test_set.keys()), np.int32)
+        u, p, n = ns.sample_lgcn(self._ns_test_pop, self.n_users, self.n_items, self._ns_test,
+                                 self._ns_test_ban, self.batch_size)
+        return u.tolist(), p.tolist(), n.tolist()
+
+    def sample_test_py(self):
         B = self.batch_size
         keys = list(self.test_set.keys())
         if B <= self.n_users:

@@ -151,6 +151,17 @@ class BPRMF(_ScoringMixin):
         with torch.cuda.device(self.dev):
             return self.trainer.step_host(users, pos_items, neg_items)
 
+    def train_epoch(self, batches):
+        """`batches` int32 [n,3,B] on the host (e.g. `Data.sample_epoch`) -> float32 [n,4] host
+        losses {loss, mf_loss, reg_loss, L_ori}: the inner loop of train.py:470-499 as ONE call
+        (one H2D, n step graphs, one D2H) -- same results as n `sess.run` fetches."""
+        b = torch.as_tensor(np.ascontiguousarray(batches, dtype=np.int32))
+        if getattr(self, "_pin", None) is None or self._pin.shape != b.shape:
+            self._pin = torch.empty(b.shape, dtype=torch.int32).pin_memory()
+        self._pin.copy_(b)
+        with torch.cuda.device(self.dev):
+            return self.trainer.run_host(self._pin).numpy()
+
     def _score_tables(self):
         t = self.trainer.tab
         return t.U, t.I, t.w, t.wu

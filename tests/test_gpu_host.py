@@ -225,3 +225,36 @@ def test_epoch_run_host_equals_device_run():
     assert b.steps_done == n
     a.close()
     b.close()
+
+
+def test_epoch_path_equals_stepwise_session_loop():
+    """`Data.sample_epoch` + `BPRMF.train_epoch` (what the CLI runs) == the literal loop of
+    train.py:470-499 (`data.sample()` + `sess.run([...opt...])` per step): losses and tables."""
+    import torch
+
+    from macr_b200.host.data_mf import Data
+    from macr_b200.host.model_mf import BPRMF
+    from macr_b200.host.session import Session
+
+    args = mf_args()
+    data = Data(args)
+    cfg = {"n_users": data.n_users, "n_items": data.n_items}
+    n = 6
+    random.seed(21)
+    a = BPRMF(args, cfg)
+    sess = Session()
+    want = []
+    for _ in range(n):
+        u, p, ng = data.sample()
+        _, l, m, r = sess.run([a.opt_two_bce_both, a.loss_two_bce_both, a.mf_loss_two_bce_both,
+                               a.reg_loss_two_bce_both],
+                              feed_dict={a.users: u, a.pos_items: p, a.neg_items: ng})
+        want.append((l, m, r))
+    random.seed(21)
+    b = BPRMF(args, cfg)
+    got = b.train_epoch(data.sample_epoch(n))
+    assert [tuple(float(x) for x in row[:3]) for row in got] == want
+    for x, y in zip(a.trainer.tab.all(), b.trainer.tab.all()):
+        assert torch.equal(x, y)
+    a.close()
+    b.close()

@@ -130,3 +130,85 @@ def test_flag_defaults_match_reference_parsers():
     b = flags.parse_lgcn_args("--dataset addressa --batch_size 1024 --layer_size [64,64] --loss bceboth "
                               "--test rubiboth --c 40 --alpha 1e-2 --beta 1e-3 --epoch 2000".split())
     assert flags.as_list(b.layer_size) == [64, 64] and b.loss == "bceboth"
+
+
+@pytest.mark.skipif(not os.path.isdir(os.path.join(REF_DATA, "addressa")), reason="reference data not mounted")
+@pytest.mark.parametrize("batch_size", [1024, 8192, 20000])
+def test_native_mf_sampler_equals_python_restatement(batch_size):
+    """C sampler (macr_sample_mf) vs the line-by-line Python sampler on the same `random` stream:
+    identical triples AND identical stream position afterwards.  1024: set-based random.sample,
+    8192: pool-based (n <= setsize), 20000 > n_users: choice with replacement."""
+    from macr_b200.host.data_mf import Data
+
+    data = Data(_mf_args(REF_DATA + "/", "addressa", batch_size))
+    for seed in (12345, 7):
+        random.seed(seed)
+        want = [data.sample_py() for _ in range(3)]
+        tail_py = random.random()
+        random.seed(seed)
+        got = [data.sample() for _ in range(3)]
+        assert random.random() == tail_py
+        for (wu, wp, wn), (gu, gp, gn) in zip(want, got):
+            assert wu == gu and wp == gp and wn == gn
+
+
+@pytest.mark.skipif(not os.path.isdir(os.path.join(REF_DATA, "addressa")), reason="reference data not mounted")
+def test_native_lgcn_samplers_equal_python_restatement():
+    """macr_sample_lgcn vs the Python sampler: `random` (users) and legacy `np.random.randint`
+    (items) streams, train sampler and the test-loss sampler, stream positions included."""
+    from macr_b200.host.data_lgcn import Data
+
+    data = Data(os.path.join(REF_DATA, "addressa"), 1024, types.SimpleNamespace(valid_set="test"))
+    for fn_py, fn_c in ((data.sample_py, data.sample), (data.sample_test_py, data.sample_test)):
+        random.seed(99)
+        np.random.seed(99)
+        want = [fn_py() for _ in range(3)]
+        tails = (random.random(), np.random.randint(0, 1 << 30))
+        random.seed(99)
+        np.random.seed(99)
+        got = [fn_c() for _ in range(3)]
+        assert (random.random(), np.random.randint(0, 1 << 30)) == tails
+        for w, g in zip(want, got):
+            assert [list(map(int, x)) for x in w] == [list(x) for x in g]
+
+
+def test_native_numpy_randint_twin_small_ranges():
+    """legacy np.random.randint(0, n, size=1): n = 1 draws nothing, powers of two never reject."""
+    from macr_b200.host import native_sampler as ns
+
+    for n_items in (1, 2, 3, 64, 65, 1000):
+        lists = {0: list(range(0))}  # user 0 bans nothing
+        pos = ns.ListCSR({0: [5]}, 1)
+        ban = ns.ListCSR(lists, 1)
+        random.seed(1)
+        np.random.seed(5)
+        want = [int(np.random.randint(low=0, high=1, size=1)[0]) * 0 + int(
+            np.random.randint(low=0, high=n_items, size=1)[0]) for _ in range(50)]
+        tail = np.random.randint(0, 1 << 30)
+        np.random.seed(5)
+        got = []
+        for _ in range(50):
+            _, p, n = ns.sample_lgcn(np.zeros(1, np.int32), 1, n_items, pos, ban, 1)
+            assert p[0] == 5
+            got.append(int(n[0]))
+        assert got == want and np.random.randint(0, 1 << 30) == tail
+
+
+def test_sample_epoch_equals_consecutive_samples():
+    from macr_b200.host.data_lgcn import Data as LData
+    from macr_b200.host.data_mf import Data
+
+    data = Data(_mf_args(GOLD + "/", "tiny", 16))
+    random.seed(3)
+    want = np.array([data.sample() for _ in range(5)], np.int32)
+    tail = random.random()
+    random.seed(3)
+    np.testing.assert_array_equal(data.sample_epoch(5), want)
+    assert random.random() == tail
+    ld = LData(os.path.join(GOLD, "tiny"), 16, types.SimpleNamespace(valid_set="test"))
+    random.seed(4)
+    np.random.seed(4)
+    want = np.array([ld.sample() for _ in range(5)], np.int32)
+    random.seed(4)
+    np.random.seed(4)
+    np.testing.assert_array_equal(ld.sample_epoch(5), want)
