@@ -82,42 +82,80 @@ def synth_mask(seed, n_rows, avg):
 
 
 class ClockSampler(threading.Thread):
-    """nvidia-smi clocks + throttle reasons during the timed region (B200_PROFILING.md)."""
+    """SM clock + throttle reasons during the timed region (B200_PROFILING.md): NVML in-process
+    every 2 ms (an `nvidia-smi` invocation takes longer than the whole timed region), falling
+    back to polling `nvidia-smi` when pynvml is unavailable."""
 
     Q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,"
          "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
          "clocks_event_reasons.sw_power_cap")
+    BITS = {"sw_power_cap": 0x4, "hw_slowdown": 0x8, "sw_thermal_slowdown": 0x20,
+            "hw_thermal_slowdown": 0x40}
 
     def __init__(self, index):
         super().__init__(daemon=True)
-        self.index, self.rows, self._stop_evt = index, [], threading.Event()
+        self.index, self.sm, self.mx, self.reasons = index, [], 0.0, set()
+        self._stop_evt = threading.Event()
+        self.nvml = None
+        try:
+            import pynvml
+
+            pynvml.nvmlInit()
+            # CUDA_VISIBLE_DEVICES may renumber: resolve through the CUDA device's PCI bus id
+            import torch
+
+            bus = torch.cuda.get_device_properties(index).pci_bus_id if hasattr(
+                torch.cuda.get_device_properties(index), "pci_bus_id") else None
+            self.h = pynvml.nvmlDeviceGetHandleByIndex(index)
+            if bus is not None:
+                for i in range(pynvml.nvmlDeviceGetCount()):
+                    hh = pynvml.nvmlDeviceGetHandleByIndex(i)
+                    if pynvml.nvmlDeviceGetPciInfo(hh).bus == bus:
+                        self.h = hh
+                        break
+            self.mx = float(pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM))
+            self.nvml = pynvml
+        except Exception:
+            self.nvml = None
+
+    def _poll_nvml(self):
+        n = self.nvml
+        self.sm.append(float(n.nvmlDeviceGetClockInfo(self.h, n.NVML_CLOCK_SM)))
+        try:
+            r = n.nvmlDeviceGetCurrentClocksEventReasons(self.h)
+        except Exception:
+            r = n.nvmlDeviceGetCurrentClocksThrottleReasons(self.h)
+        for name, bit in self.BITS.items():
+            if r & bit:
+                self.reasons.add(name)
+
+    def _poll_smi(self):
+        out = subprocess.run(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                              "-i", str(self.index)], capture_output=True, text=True, timeout=5).stdout
+        r = [x.strip() for x in out.strip().split(",")]
+        self.sm.append(float(r[0]))
+        self.mx = max(self.mx, float(r[1]))
+        for name, v in zip(["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"], r[2:6]):
+            if v.lower().startswith("active"):
+                self.reasons.add(name)
 
     def run(self):
         while not self._stop_evt.is_set():
             try:
-                out = subprocess.run(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
-                                      "-i", str(self.index)], capture_output=True, text=True, timeout=5).stdout
-                self.rows.append([x.strip() for x in out.strip().split(",")])
+                if self.nvml is not None:
+                    self._poll_nvml()
+                else:
+                    self._poll_smi()
             except Exception:
                 pass
-            self._stop_evt.wait(0.05)
+            self._stop_evt.wait(0.002 if self.nvml is not None else 0.05)
 
     def stop(self):
         self._stop_evt.set()
         self.join(timeout=3)
-        sm, mx, reasons = [], 0, set()
-        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        for r in self.rows:
-            try:
-                sm.append(float(r[0]))
-                mx = max(mx, float(r[1]))
-                for nme, v in zip(names, r[2:6]):
-                    if v.lower().startswith("active"):
-                        reasons.add(nme)
-            except Exception:
-                continue
-        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": mx or None,
-                "reasons": sorted(reasons), "samples": len(sm)}
+        return {"sm_mhz": float(np.median(self.sm)) if self.sm else None, "sm_max_mhz": self.mx or None,
+                "reasons": sorted(self.reasons), "samples": len(self.sm),
+                "source": "nvml" if self.nvml is not None else "nvidia-smi"}
 
 
 def measured_peaks():
