@@ -62,6 +62,8 @@ def main():
     ap.add_argument("--synth-users", type=int, default=262144)
     ap.add_argument("--synth-items", type=int, default=1000000)
     ap.add_argument("--lgcn-datasets", default="yelp2018,gowalla,ml_10m")
+    ap.add_argument("--train-users", type=int, default=10_000_000)
+    ap.add_argument("--train-items", type=int, default=1_000_000)
     args = ap.parse_args()
     what = set(args.what.split(","))
 
@@ -233,6 +235,60 @@ def main():
              spot_parity_vs_exact_fp32_kernel=same,
              roofline={"bound": "tensor", "achieved": flops / t / 1e12, "unit": "TFLOP/s",
                        "peak": pk["bf16_tflops"] * world, "frac": flops / t / 1e12 / (pk["bf16_tflops"] * world)})
+
+    # ---------------- config 5, training side: MF step on 10 M x 1 M tables (HBM-bound) ----------------
+    train_cfgs = []
+    if "synth_train" in what and world == 1:
+        train_cfgs.append(("synthetic (config 5 tables)", args.train_users, args.train_items, 8192))
+    if "ml10m_train" in what and world == 1:
+        train_cfgs.append(("ml_10m-shape (config 4 tables, L2-resident: back-to-back replay)", 69166, 8790, 8192))
+    for tname, U_n, I_n, B in train_cfgs:
+        gen = torch.Generator(device=dev).manual_seed(1)
+        lim_u, lim_i = float(np.sqrt(6.0 / (U_n + D))), float(np.sqrt(6.0 / (I_n + D)))
+        # tables are created on the device (8.45 GB of var/m/v); the trainer adopts host arrays, so
+        # it is built on 1-row placeholders and its table tensors are swapped before the first step
+        rng = np.random.RandomState(3)
+        w = rng.uniform(-0.3, 0.3, D).astype(np.float32)
+        wu = rng.uniform(-0.3, 0.3, D).astype(np.float32)
+        hp = ops.HParams.make(lr=1e-3, alpha=1e-3, beta=1e-3, decay=1e-5, batch_size=B)
+        Uh = np.zeros((U_n, D), np.float32)
+        Ih = np.zeros((I_n, D), np.float32)
+        tr = ops.MFTrainer(Uh, Ih, w, wu, hp, max_batch=B, device=dev)
+        del Uh, Ih
+        t = tr.tab
+        t.U.uniform_(-lim_u, lim_u, generator=gen)
+        t.I.uniform_(-lim_i, lim_i, generator=gen)
+        for m_, v_ in ((t.mU, t.vU), (t.mI, t.vI)):  # steady state: every row has non-zero moments
+            m_.normal_(0.0, 1e-4, generator=gen)
+            v_.uniform_(1e-9, 1e-7, generator=gen)
+        nb = 24
+        batches = np.empty((nb, 3, B), np.int32)
+        for s_ in range(nb):
+            batches[s_, 0] = rng.permutation(np.unique(rng.randint(0, U_n, 2 * B)))[:B]  # distinct users
+            batches[s_, 1] = rng.randint(0, I_n, B)
+            batches[s_, 2] = rng.randint(0, I_n, B)
+        d_b = torch.from_numpy(batches).to(dev)
+        losses = torch.zeros((nb, 4), dtype=torch.float32, device=dev)
+        tr.run(d_b[:4], losses[:4])
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        tr.run(d_b[4:], losses[4:])
+        e1.record()
+        torch.cuda.synchronize()
+        t_step = e0.elapsed_time(e1) * 1e-3 / (nb - 4)
+        step_bytes = 24.0 * D * (U_n + I_n) + 12.0 * D * B + 12.0 * B + 48.0 * D
+        emit(config="MACR-MF %s U=%d I=%d d=64 B=8192 rubibceboth, %.3f GB of var/m/v"
+                    % (tname, U_n, I_n, 12.0 * D * (U_n + I_n) / 1e9),
+             metric="train_interactions_per_sec", value=B / t_step, unit="interactions/s", ms_per_step=1e3 * t_step,
+             roofline={"bound": "hbm", "bytes_per_step": step_bytes, "achieved": step_bytes / t_step / 1e9,
+                       "peak": pk["hbm_gbs"], "unit": "GB/s", "frac": step_bytes / t_step / 1e9 / pk["hbm_gbs"],
+                       "note": "whole fused step (gather + dots + BxB BCE + row gradients + dense Adam) against "
+                               "its algorithmic bytes 24*64*(U+I) + 780*B + 3072"},
+             final_loss=float(losses[nb - 1, 0].item()))
+        tr.close()
+        del tr
+        torch.cuda.empty_cache()
 
     if "ml10m" in what:
         scoring("MACR-MF ml_10m-shape scoring T=13878 I=8790 K=20 c=40", 13878, 8790, 71, 20)
