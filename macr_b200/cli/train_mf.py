@@ -35,7 +35,10 @@ def ckpt_dir(args):
     return "{}_{}_checkpoint/wd_{}_lr_{}_{}/".format(args.model, args.dataset, args.wd, args.lr, args.saveID)
 
 
-def main(argv=None):
+def main(argv=None, tune=False):
+    """tune=True is `python ./macr_mf/tune.py ...` (macr_mf/tune.py:536-575, README.md:101-105):
+    the same run, but every evaluation sweeps c over np.linspace(--start, --end, --step) and
+    keeps the c with the best HR@Ks[0]."""
     args = flags.parse_mf_args(argv)
     logging.getLogger().setLevel(logging.INFO)
     if args.train != "rubibceboth":
@@ -106,7 +109,28 @@ def main(argv=None):
             users_to_test = list(data.valid_user_list.keys())
         else:
             users_to_test = list(data.test_user_list.keys())
-        if args.test == "rubi":
+        if args.test == "rubi" and tune:
+            print("Epoch %d" % epoch)
+            best = None
+            for c in np.linspace(args.start, args.end, args.step):
+                model.update_c(sess, c)
+                r = evaluator.test(sess, model, users_to_test, model_type="rubi_both", valid_set=args.valid_set)
+                t3 = time()
+                if args.verbose > 0:
+                    perf_str = ("c:%.2f [%.1fs + %.1fs]: train==[%.8f=%.8f + %.8f], recall=[%.5f, %.5f], "
+                                "precision=[%.5f, %.5f], hit=[%.5f, %.5f], ndcg=[%.5f, %.5f]") % (
+                        c, t2 - t1, t3 - t2, loss, mf_loss, reg_loss, r["recall"][0], r["recall"][-1],
+                        r["precision"][0], r["precision"][-1], r["hit_ratio"][0], r["hit_ratio"][-1],
+                        r["ndcg"][0], r["ndcg"][-1])
+                    print(perf_str)
+                    logging.info(perf_str)
+                if best is None or r["hit_ratio"][0] > best[1]["hit_ratio"][0]:
+                    best = (float(c), r)
+            ret = best[1]
+            if ret["hit_ratio"][0] >= config["best_hr"]:
+                config["best_c"] = best[0]
+            head = "best c:%.2f" % best[0]
+        elif args.test == "rubi":
             print("Epoch %d" % epoch)
             c = args.c
             model.update_c(sess, c)

@@ -195,6 +195,14 @@ def test_cli_drivers_run_end_to_end(tmp_path, monkeypatch, capsys):
     assert "c:2.00 [" in out and "hit=[" in out and "Epoch 0 [" in out
     assert os.path.exists("mf_tiny_checkpoint/wd_1e-05_lr_0.01_t/3_ckpt.npz")
     assert 0 <= cfg["best_hr"] <= 1
+    # tune.py: the c sweep of README.md:101-105 at every evaluation
+    cfg = train_mf.main(["--data_path", GOLD + "/", "--dataset", "tiny", "--batch_size", "32", "--epoch", "2",
+                         "--log_interval", "2", "--train", "rubibceboth", "--test", "rubi", "--start", "0",
+                         "--end", "4", "--step", "3", "--lr", "0.01", "--saveID", "u", "--save_flag", "0"],
+                        tune=True)
+    out = capsys.readouterr().out
+    assert "c:0.00 [" in out and "c:2.00 [" in out and "c:4.00 [" in out and "best c:" in out
+    assert cfg["best_c"] in (0.0, 2.0, 4.0)
     res = lightgcn.main(["--data_path", GOLD + "/", "--dataset", "tiny", "--batch_size", "32", "--epoch", "2",
                          "--log_interval", "1", "--layer_size", "[64,64]", "--Ks", "[20]", "--loss", "bceboth",
                          "--test", "rubiboth", "--c", "2", "--lr", "0.001", "--weights_path", str(tmp_path) + "/"])
