@@ -374,6 +374,25 @@ def main():
     torch.cuda.synchronize()
     sw_single_ms = float(np.mean([a.elapsed_time(b) for a, b in one_ev]))
     del sets
+    # the kernel that takes the most time of the step is the B x B grid: MUFU-bound (4 per pair: 2
+    # ex2, 1 rcp, 1 lg2; 16 lanes per SM per clock), timed alone through its stateless entry point
+    gsc = [torch.randn(BATCH, device=dev) * sd for sd in (0.05, 0.05, 0.1, 0.1, 0.1)]
+    for _ in range(3):
+        ops.grid_bce(*gsc, HP["alpha"], HP["beta"])
+    g0, g1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    g0.record()
+    for _ in range(20):
+        ops.grid_bce(*gsc, HP["alpha"], HP["beta"])
+    g1.record()
+    torch.cuda.synchronize()
+    grid_ms = g0.elapsed_time(g1) / 20
+    mufu_ops = 4.0 * BATCH * BATCH
+    mufu_peak = 148 * 16 * (clocks.get("sm_max_mhz") or 1965.0) * 1e6
+    grid_info = {"bound": "mufu", "ms_per_launch": grid_ms, "pairs": BATCH * BATCH,
+                 "achieved_gops": mufu_ops / (grid_ms * 1e-3) / 1e9, "peak_gops": mufu_peak / 1e9,
+                 "frac": mufu_ops / (grid_ms * 1e-3) / mufu_peak,
+                 "note": "stateless macr_grid_bce_fwd_bwd incl. its workspace allocation and launch gaps; "
+                         "inside the step graph the kernel takes ~25 us (profiles/r1d_launches.txt)"}
     step_bytes = 24.0 * D * rows + 12.0 * D * BATCH + 12.0 * BATCH + 48.0 * D
     ms_per_step = 1e3 * t_flushed / K
     roofline = {"bound": "hbm", "kernel": "adam_sweep_kernel", "achieved": achieved,
@@ -383,6 +402,7 @@ def main():
                 "ms_per_launch_single_flushed": sw_single_ms,
                 "method": "60 launches (10 replays of a 6-launch CUDA graph) round-robin over 6 table "
                           "sets (326 MB > L2) between one event pair on the launching stream",
+                "grid_bce_kernel": grid_info,
                 "step": {"bytes_per_step": step_bytes,
                          "achieved": step_bytes / (ms_per_step * 1e-3) / 1e9,
                          "frac": step_bytes / (ms_per_step * 1e-3) / 1e9 / peaks["hbm_gbs"],

@@ -174,6 +174,13 @@ int macr_mf_trainer_run(macr_mf_trainer *h, const int32_t *batches, int n_steps,
  * and running them in one call gives the results of the per-step loop.              */
 int macr_mf_trainer_run_host(macr_mf_trainer *h, const int32_t *batches_host, int n_steps, int B,
                              float *losses_host);
+/* Which `--train` graph the trainer steps (default MACR_TRAIN_RUBIBCEBOTH, the MACR hot path).
+ * MACR_TRAIN_NORMALBCE is the README's baseline command (README.md:30, model.py:277-287,:100):
+ * element-wise BCE on (y_pos, y_neg) with "+1e-9", same L2 term, TF Adam on the two embedding
+ * tables only (w, w_user are not part of that graph).  Call before the first step of a run. */
+#define MACR_TRAIN_RUBIBCEBOTH 0
+#define MACR_TRAIN_NORMALBCE 1
+int macr_mf_trainer_set_mode(macr_mf_trainer *h, int mode);
 /* number of this library's kernels launched by one step (for bench gpu_launches) */
 int macr_mf_trainer_launches_per_step(const macr_mf_trainer *h);
 int64_t macr_mf_trainer_steps_done(const macr_mf_trainer *h);

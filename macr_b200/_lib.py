@@ -54,6 +54,7 @@ PROTOTYPES = {
     "macr_mf_trainer_step_host": (i32, [vp, vp, vp, vp, i32, vp]),
     "macr_mf_trainer_run": (i32, [vp, vp, i32, i32, vp]),
     "macr_mf_trainer_run_host": (i32, [vp, vp, i32, i32, vp]),
+    "macr_mf_trainer_set_mode": (i32, [vp, i32]),
     "macr_mf_trainer_launches_per_step": (i32, [vp]),
     "macr_mf_trainer_steps_done": (i64, [vp]),
     "macr_mf_trainer_set_steps_done": (i32, [vp, i64]),

@@ -1,7 +1,8 @@
 """`python ./macr_mf/train.py ...` -- the MF driver of the reference (macr_mf/train.py:332-611)
 on the B200 path: same flags, same epoch / evaluation / early-stopping structure, same log
-lines.  Only `--train rubibceboth` (with `--test rubi` or `--test normal`) is implemented; the
-other --train modes of the reference are outside the MACR hot path and fail loudly."""
+lines.  `--train rubibceboth` (MACR, with `--test rubi` or `--test normal`) and `--train normalbce`
+(the README's baseline command, `--test normal`) are implemented; the other --train modes of the
+reference are outside the MACR hot path and fail loudly."""
 import logging
 import os
 import random
@@ -41,9 +42,9 @@ def main(argv=None, tune=False):
     keeps the c with the best HR@Ks[0]."""
     args = flags.parse_mf_args(argv)
     logging.getLogger().setLevel(logging.INFO)
-    if args.train != "rubibceboth":
-        raise SystemExit(f"--train {args.train}: only rubibceboth is implemented on the B200 path "
-                         "(DESIGN.md section 8)")
+    if args.train not in ("rubibceboth", "normalbce"):
+        raise SystemExit(f"--train {args.train}: rubibceboth (MACR) and normalbce (the README's baseline) "
+                         "are implemented on the B200 path (DESIGN.md section 8)")
     if args.model != "mf":
         raise SystemExit(f"--model {args.model}: only mf is on the MACR hot path")
     data = Data(args)
@@ -56,6 +57,10 @@ def main(argv=None, tune=False):
     config = {"n_users": data.n_users, "n_items": data.n_items}
     model = BPRMF(args, config)
     print("MF model.")
+    model.set_train_mode(args.train)
+    opt_fetches = ([model.opt_two_bce_both, model.loss_two_bce_both, model.mf_loss_two_bce_both,
+                    model.reg_loss_two_bce_both] if args.train == "rubibceboth" else
+                   [model.opt_bce, model.loss_bce, model.mf_loss_bce, model.reg_loss_bce])  # train.py:487-496
     sess = Session()
     sess.run(global_variables_initializer())
     evaluator = MFEvaluator(data, Ks, args.batch_size, eval_mode=args.eval_mode)
@@ -81,8 +86,7 @@ def main(argv=None, tune=False):
             for _ in range(n_batch):
                 users, pos_items, neg_items = data.sample()
                 _, batch_loss, batch_mf_loss, batch_reg_loss = sess.run(
-                    [model.opt_two_bce_both, model.loss_two_bce_both, model.mf_loss_two_bce_both,
-                     model.reg_loss_two_bce_both],
+                    opt_fetches,
                     feed_dict={model.users: users, model.pos_items: pos_items, model.neg_items: neg_items})
                 loss += batch_loss / n_batch
                 mf_loss += batch_mf_loss / n_batch

@@ -630,6 +630,68 @@ int launch_grid_bce(const float *yp, const float *yn, int B, const macr_hparams 
 }
 
 // ---------------------------------------------------------------------------------------------
+// `--train normalbce` (the README's baseline command; macr_mf/model.py:277-287): element-wise
+//   mf = mean_b( -log(sig(yp_b) + 1e-9) - log(1 - sig(yn_b) + 1e-9) )
+//   d mf / d yp_b = -s(1-s)/(s+1e-9)/B      d mf / d yn_b = t(1-t)/((1-t)+1e-9)/B
+// One CTA: B scalars.  The gate gradients are zero in this graph (w, w_user are not part of it),
+// so the row-gradient kernel runs unchanged.  Losses {loss, mf, reg, mf} go where the grid
+// kernel's loss folder puts them.
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(1024)
+plain_bce_kernel(const float *__restrict__ yp, const float *__restrict__ yn, int B,
+                 macr_hparams hp, const float *__restrict__ regsq, const StepState *st,
+                 float *losses_direct, float *__restrict__ d_yp, float *__restrict__ d_yn,
+                 float *__restrict__ d_sp, float *__restrict__ d_sn, float *__restrict__ d_su) {
+  __shared__ double sh[32][2];
+  const float eps9 = 1e-9f, invB = 1.0f / (float)B;
+  double a0 = 0, a1 = 0;
+  for (int b = threadIdx.x; b < B; b += blockDim.x) {
+    const float s = 1.0f / (1.0f + expf(-yp[b])), t = 1.0f / (1.0f + expf(-yn[b]));
+    const float se = s + eps9, q = (1.0f - t) + eps9;
+    a0 += (double)(-logf(se)) + (double)(-logf(q));
+    a1 += regsq[b];
+    d_yp[b] = -(s * (1.0f - s)) / se * invB;
+    d_yn[b] = (t * (1.0f - t)) / q * invB;
+    d_sp[b] = 0.f;
+    d_sn[b] = 0.f;
+    d_su[b] = 0.f;
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    a0 += __shfl_xor_sync(0xffffffffu, a0, o);
+    a1 += __shfl_xor_sync(0xffffffffu, a1, o);
+  }
+  if ((threadIdx.x & 31) == 0) {
+    sh[threadIdx.x >> 5][0] = a0;
+    sh[threadIdx.x >> 5][1] = a1;
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    a0 = a1 = 0;
+    for (int k = 0; k < (int)(blockDim.x >> 5); ++k) {
+      a0 += sh[k][0];
+      a1 += sh[k][1];
+    }
+    const float mf = (float)(a0 / (double)B);
+    const float reg = hp.decay * ((float)(a1 * 0.5) / (float)hp.batch_size_flag);
+    float *dst = st ? st->loss_base + st->step_idx * 4 : losses_direct;
+    dst[0] = mf + reg;
+    dst[1] = mf;
+    dst[2] = reg;
+    dst[3] = mf;
+  }
+}
+
+int launch_plain_bce(const float *yp, const float *yn, int B, const macr_hparams &hp,
+                     const float *regsq, const StepState *st, float *losses_direct, float *d_yp,
+                     float *d_yn, float *d_sp, float *d_sn, float *d_su, cudaStream_t s) {
+  plain_bce_kernel<<<1, 1024, 0, s>>>(yp, yn, B, hp, regsq, st, losses_direct, d_yp, d_yn, d_sp,
+                                      d_sn, d_su);
+  MACR_LAUNCH_CHECK();
+  return MACR_OK;
+}
+
+// ---------------------------------------------------------------------------------------------
 // K5a: batch plan -- group the batch positions that hit the same table row, deterministically.
 // One CTA per table runs a stable LSD radix sort (8-bit digits) of the row ids in shared memory
 // (n <= 16384 ids; a few microseconds, and it occupies 2 of the 148 SMs while the B x B grid

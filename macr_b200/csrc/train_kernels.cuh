@@ -62,6 +62,10 @@ int launch_grid_bce(const float *yp, const float *yn, int B, const macr_hparams 
                     const GridWs &ws, float *d_yp, float *d_yn, float *d_sp, float *d_sn,
                     float *d_su, int want_grad, const float *regsq, const StepState *st,
                     float *losses3, cudaStream_t s);
+// `--train normalbce`: element-wise BCE on (yp, yn) instead of the B x B grid
+int launch_plain_bce(const float *yp, const float *yn, int B, const macr_hparams &hp,
+                     const float *regsq, const StepState *st, float *losses_direct, float *d_yp,
+                     float *d_yn, float *d_sp, float *d_sn, float *d_su, cudaStream_t s);
 size_t plan_ws_bytes(int n_ids);
 int plan_init();
 // two tables in one launch (table 1 optional: n_ids1 == 0)

@@ -166,6 +166,7 @@ struct TrainerBase {
 struct macr_mf_trainer : macr::TrainerBase {
   uint32_t *bmU, *bmI;
   int launches;
+  int mode = MACR_TRAIN_RUBIBCEBOTH;
 };
 
 namespace macr {
@@ -196,7 +197,10 @@ static int mf_enqueue(macr_mf_trainer *h, int B) {
   rc = launch_gather_dots(h->U, h->I, h->U, h->I, h->w, h->wu, nullptr, nullptr, nullptr, h->st, B,
                           yp, yn, sp, sn, su, rq, h->snap, &g, s);
   if (rc) return rc;
-  rc = launch_grid_bce(yp, yn, B, hp, g, dyp, dyn, dsp, dsn, dsu, 1, rq, h->st, nullptr, s);
+  if (h->mode == MACR_TRAIN_NORMALBCE)
+    rc = launch_plain_bce(yp, yn, B, hp, rq, h->st, nullptr, dyp, dyn, dsp, dsn, dsu, s);
+  else
+    rc = launch_grid_bce(yp, yn, B, hp, g, dyp, dyn, dsp, dsn, dsu, 1, rq, h->st, nullptr, s);
   if (rc) return rc;
   MACR_CUDA(cudaStreamWaitEvent(s, h->ev_join, 0));
   MACR_CUDA(cudaStreamWaitEvent(s, h->ev_join2, 0));
@@ -390,6 +394,19 @@ extern "C" int macr_mf_trainer_run(macr_mf_trainer *h, const int32_t *batches, i
   int rc = run_steps(h, h->graphs, mf_enqueue, batches, n_steps, B, losses);
   if (rc) return rc;
   h->steps_done += n_steps;
+  return MACR_OK;
+}
+
+extern "C" int macr_mf_trainer_set_mode(macr_mf_trainer *h, int mode) {
+  MACR_CHECK_ARG(h, "macr_mf_trainer_set_mode: null handle");
+  MACR_CHECK_ARG(mode == MACR_TRAIN_RUBIBCEBOTH || mode == MACR_TRAIN_NORMALBCE,
+                 "macr_mf_trainer_set_mode: unknown mode %d", mode);
+  if (mode != h->mode) {  // the captured step graphs belong to the old mode
+    cudaStreamSynchronize(h->s);
+    for (auto &kv : h->graphs) cudaGraphExecDestroy(kv.second);
+    h->graphs.clear();
+    h->mode = mode;
+  }
   return MACR_OK;
 }
 

@@ -7,6 +7,8 @@ in HBM) behind `ops.MFTrainer`.  Fetching
   [opt_two_bce_both, loss_two_bce_both, mf_loss_two_bce_both, reg_loss_two_bce_both]
         -> one fused training step (gather -> dots -> B x B gated BCE -> row gradients ->
            TF-faithful Adam), returns (None, loss, mf_loss, reg_loss)      model.py:72-74,185-222
+  [opt_bce, loss_bce, mf_loss_bce, reg_loss_bce]
+        -> one `--train normalbce` step (element-wise BCE, the README's baseline)  model.py:99-101,277-287
   rubi_ratings_both  -> ((u.i) - c) * sig(i.w) * sig(u.w_user)  as float32 [B_u, I]  model.py:199
   batch_ratings      -> u.i                                                            model.py:45
 
@@ -21,10 +23,11 @@ from .. import ops
 from .session import Fetch, Placeholder, Unsupported
 
 _TRAIN = ("opt_two_bce_both", "loss_two_bce_both", "mf_loss_two_bce_both", "reg_loss_two_bce_both")
+# `--train normalbce` (README.md:30, the baseline the MACR rows are compared with): model.py:99-101
+_TRAIN_BCE = ("opt_bce", "loss_bce", "mf_loss_bce", "reg_loss_bce")
 _UNSUPPORTED = (
     "opt", "loss", "mf_loss", "reg_loss", "opt_two", "loss_two", "mf_loss_two", "reg_loss_two",
-    "opt_two_bce", "loss_two_bce", "mf_loss_two_bce", "reg_loss_two_bce", "opt_bce", "loss_bce",
-    "mf_loss_bce", "reg_loss_bce", "opt2", "loss2", "opt2_bce", "loss2_bce", "opt3", "opt3_bce",
+    "opt_two_bce", "loss_two_bce", "mf_loss_two_bce", "reg_loss_two_bce", "opt2", "loss2", "opt2_bce", "loss2_bce", "opt3", "opt3_bce",
     "opt_userc_bce", "loss_userc_bce", "user_const_ratings", "item_const_ratings",
     "user_rand_ratings", "item_rand_ratings", "rubi_ratings", "rubi_ratings_userc",
     "direct_minus_ratings", "direct_minus_ratings_both", "rubi_ratings_both_poptest",
@@ -126,7 +129,7 @@ class BPRMF(_ScoringMixin):
                                      device=self.dev)
         for name in ("users", "pos_items", "neg_items"):
             setattr(self, name, Placeholder(self, name))
-        for name in _TRAIN + ("rubi_ratings_both", "batch_ratings"):
+        for name in _TRAIN + _TRAIN_BCE + ("rubi_ratings_both", "batch_ratings"):
             setattr(self, name, Fetch(self, name))
         for name in _UNSUPPORTED:
             setattr(self, name, Unsupported(self, name))
@@ -137,14 +140,26 @@ class BPRMF(_ScoringMixin):
     # ---- session dispatch -----------------------------------------------------------------
     def _run(self, names, feeds):
         if any(n.startswith("opt") for n in names):
+            normal = any(n in _TRAIN_BCE for n in names)
+            if normal and any(n in _TRAIN for n in names):
+                raise NotImplementedError("one optimizer op per sess.run")
+            self.set_train_mode("normalbce" if normal else "rubibceboth")
             loss, mf, reg = self.train_step(feeds["users"], feeds["pos_items"], feeds["neg_items"])
             val = {"opt_two_bce_both": None, "loss_two_bce_both": loss, "mf_loss_two_bce_both": mf,
-                   "reg_loss_two_bce_both": reg}
+                   "reg_loss_two_bce_both": reg, "opt_bce": None, "loss_bce": loss, "mf_loss_bce": mf,
+                   "reg_loss_bce": reg}
             return [val[n] for n in names]
-        if any(n in _TRAIN for n in names):
+        if any(n in _TRAIN or n in _TRAIN_BCE for n in names):
             raise NotImplementedError("loss fetches without the optimizer op are not used by "
                                       "macr_mf/train.py and are not implemented for MF")
         return [self._run_scores(n, feeds) for n in names]
+
+    def set_train_mode(self, train):
+        """which optimizer op steps run: "rubibceboth" (default) or "normalbce"."""
+        mode = {"rubibceboth": ops.MFTrainer.RUBIBCEBOTH, "normalbce": ops.MFTrainer.NORMALBCE}[train]
+        if getattr(self, "_mode", ops.MFTrainer.RUBIBCEBOTH) != mode:
+            self.trainer.set_mode(mode)
+            self._mode = mode
 
     def train_step(self, users, pos_items, neg_items):
         """One `rubibceboth` step from host id sequences -> (loss, mf_loss, reg_loss)."""

@@ -236,6 +236,12 @@ class _Tables:
 class MFTrainer:
     """Handle around macr_mf_trainer_* (one `--train rubibceboth` model)."""
 
+    RUBIBCEBOTH, NORMALBCE = 0, 1
+
+    def set_mode(self, mode):
+        """RUBIBCEBOTH (default) or NORMALBCE (`--train normalbce`, the README's baseline)."""
+        check(lib().macr_mf_trainer_set_mode(self._h, int(mode)), "macr_mf_trainer_set_mode")
+
     def _run_host(self, n, B, ids_ptr, loss_ptr):
         return lib().macr_mf_trainer_run_host(self._h, ids_ptr, n, B, loss_ptr)
 

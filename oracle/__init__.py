@@ -20,6 +20,7 @@ from .capi import (  # noqa: F401
     adam_dense_vec,
     adam_lr_t,
     mf_step,
+    mf_step_normal,
     spmm_csr,
     lgcn_propagate,
     lgcn_step,

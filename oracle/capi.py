@@ -148,6 +148,20 @@ def mf_step(st, u, p, n, hp):
     return losses
 
 
+def mf_step_normal(st, u, p, n, hp):
+    """One `--train normalbce` step (model.py:277-287) on MFState `st` (in place)."""
+    u, p, n = _ids(u), _ids(p), _ids(n)
+    if st.t == 0:
+        st.pw[:] = (hp.beta1, hp.beta2)
+    losses = np.empty(4, np.float32)
+    lib().oracle_mf_step_normal(_f(st.U), _f(st.mU), _f(st.vU), C.c_int64(st.U.shape[0]), _f(st.I),
+                                _f(st.mI), _f(st.vI), C.c_int64(st.I.shape[0]),
+                                C.c_int(st.U.shape[1]), _i(u), _i(p), _i(n), C.c_int(len(u)),
+                                C.byref(hp), _f(st.pw), _f(losses))
+    st.t += 1
+    return losses
+
+
 def spmm_csr(rowptr, col, val, X):
     n, d = X.shape
     Y = np.empty_like(X)

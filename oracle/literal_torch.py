@@ -36,6 +36,17 @@ def bce_two_branch_both(users, pos_items, neg_items, w, w_user, alpha, beta, dec
     return mf_loss, reg_loss, mf_loss_ori, mf_loss_item, mf_loss_user
 
 
+def bce_plain(users, pos_items, neg_items, decay, batch_size):
+    """macr_mf/model.py:277-287 (create_bce_loss, `--train normalbce`)."""
+    pos_scores = torch.sum(users * pos_items, dim=1)                      # :278
+    neg_scores = torch.sum(users * neg_items, dim=1)                      # :279
+    mf_loss = torch.mean(-torch.log(torch.sigmoid(pos_scores) + 1e-9)
+                         - torch.log(1 - torch.sigmoid(neg_scores) + 1e-9))               # :282
+    l2 = lambda x: torch.sum(x * x) / 2
+    regularizer = (l2(users) + l2(pos_items) + l2(neg_items)) / batch_size                # :284-285
+    return mf_loss, decay * regularizer                                                   # :286
+
+
 def rubi_ratings_both(user_rows, item_rows, w, w_user, c):
     """macr_mf/model.py:45,199: (batch_ratings - rubi_c) * sigmoid(items@w)^T * sigmoid(users@w_user)."""
     batch_ratings = user_rows @ item_rows.t()

@@ -303,6 +303,66 @@ void oracle_mf_step(float *U, float *mU, float *vU, int64_t n_users, float *I, f
   free(pn);
 }
 
+/* ---- `--train normalbce` (the README's baseline command, README.md:30): model.py:277-287 ----
+ * mf_loss = mean_b( -log(sig(yp_b) + 1e-9) - log(1 - sig(yn_b) + 1e-9) ), reg as above;
+ * model.py:100 `self.opt = AdamOptimizer(lr).minimize(self.loss)`: only the two embedding tables
+ * receive gradients (w, w_user are not in this graph and stay untouched). */
+void oracle_plain_bce(const float *yp, const float *yn, int B, float *mf_loss, float *dyp,
+                      float *dyn) {
+  const float eps9 = 1e-9f;
+  double acc = 0.0;
+  for (int b = 0; b < B; ++b) {
+    const float s = sigmoidf_(yp[b]), t = sigmoidf_(yn[b]);
+    const float se = s + eps9, q = (1.0f - t) + eps9;
+    acc += (double)(-logf(se)) + (double)(-logf(q));
+    if (dyp) {
+      dyp[b] = -(s * (1.0f - s)) / se / (float)B;
+      dyn[b] = (t * (1.0f - t)) / q / (float)B;
+    }
+  }
+  *mf_loss = (float)(acc / (double)B);
+}
+
+void oracle_mf_step_normal(float *U, float *mU, float *vU, int64_t n_users, float *I, float *mI,
+                           float *vI, int64_t n_items, int d, const int32_t *u, const int32_t *p,
+                           const int32_t *n, int B, const oracle_hparams *hp, float *pw,
+                           float *losses) {
+  float *sc = (float *)malloc(sizeof(float) * (size_t)B * 11);
+  float *yp = sc, *yn = sc + B, *sp = sc + 2 * B, *sn = sc + 3 * B, *su = sc + 4 * B,
+        *rq = sc + 5 * B, *dyp = sc + 6 * B, *dyn = sc + 7 * B, *dz = sc + 8 * B;
+  float *zero_w = (float *)calloc((size_t)d, sizeof(float));
+  oracle_gather_dots(U, I, U, I, zero_w, zero_w, u, p, n, B, d, yp, yn, sp, sn, su, rq);
+  float mf;
+  oracle_plain_bce(yp, yn, B, &mf, dyp, dyn);
+  double rs = 0.0;
+  for (int b = 0; b < B; ++b) rs += rq[b];
+  const float reg = hp->decay * ((float)(rs * 0.5) / (float)hp->batch_size_flag);
+  losses[0] = mf + reg;
+  losses[1] = mf;
+  losses[2] = reg;
+  losses[3] = mf;
+  memset(dz, 0, sizeof(float) * (size_t)B);
+  float *gU = (float *)malloc(sizeof(float) * (size_t)B * d * 3);
+  float *gPN = gU + (size_t)B * d;
+  float gw[256], gwu[256];
+  const float lam = hp->decay / (float)hp->batch_size_flag;
+  row_grads(U, I, U, I, zero_w, zero_w, u, p, n, B, d, dyp, dyn, dz, dz, dz, lam, 1, gU, gPN, gw,
+            gwu);
+  int32_t *pn = (int32_t *)malloc(sizeof(int32_t) * (size_t)B * 2);
+  memcpy(pn, p, sizeof(int32_t) * B);
+  memcpy(pn + B, n, sizeof(int32_t) * B);
+  const float lr_t = oracle_adam_lr_t(hp->lr, pw[0], pw[1]);
+  oracle_adam_sparse(U, mU, vU, n_users, d, u, gU, B, lr_t, hp->beta1, hp->beta2, hp->eps);
+  oracle_adam_sparse(I, mI, vI, n_items, d, pn, gPN, 2 * B, lr_t, hp->beta1, hp->beta2,
+                     hp->eps);
+  pw[0] = pw[0] * hp->beta1;
+  pw[1] = pw[1] * hp->beta2;
+  free(sc);
+  free(zero_w);
+  free(gU);
+  free(pn);
+}
+
 /* ---- LightGCN.py:297-305: side = A_hat @ ego (all 100 row folds concatenated) ---- */
 void oracle_spmm_csr(const int32_t *rowptr, const int32_t *col, const float *val,
                      int64_t n_rows, const float *X, int d, float *Y) {

@@ -60,6 +60,13 @@ void oracle_mf_step(float *U, float *mU, float *vU, int64_t n_users, float *I, f
                     float *mwu, float *vwu, int d, const int32_t *u, const int32_t *p,
                     const int32_t *n, int B, const oracle_hparams *hp, float *pw,
                     float *losses);
+/* `--train normalbce` (model.py:277-287, :100): element-wise BCE, Adam on the two tables only */
+void oracle_plain_bce(const float *yp, const float *yn, int B, float *mf_loss, float *dyp,
+                      float *dyn);
+void oracle_mf_step_normal(float *U, float *mU, float *vU, int64_t n_users, float *I, float *mI,
+                           float *vI, int64_t n_items, int d, const int32_t *u, const int32_t *p,
+                           const int32_t *n, int B, const oracle_hparams *hp, float *pw,
+                           float *losses);
 
 /* macr_lightgcn/LightGCN.py:297-305 (one layer, all folds) */
 void oracle_spmm_csr(const int32_t *rowptr, const int32_t *col, const float *val,

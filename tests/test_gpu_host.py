@@ -195,6 +195,12 @@ def test_cli_drivers_run_end_to_end(tmp_path, monkeypatch, capsys):
     assert "c:2.00 [" in out and "hit=[" in out and "Epoch 0 [" in out
     assert os.path.exists("mf_tiny_checkpoint/wd_1e-05_lr_0.01_t/3_ckpt.npz")
     assert 0 <= cfg["best_hr"] <= 1
+    # the README's baseline command (README.md:30): --train normalbce --test normal
+    cfg = train_mf.main(["--data_path", GOLD + "/", "--dataset", "tiny", "--batch_size", "32", "--epoch", "4",
+                         "--log_interval", "2", "--train", "normalbce", "--test", "normal", "--lr", "0.01",
+                         "--saveID", "n", "--save_flag", "0"])
+    out = capsys.readouterr().out
+    assert "Epoch 1 [" in out and "hit=[" in out and 0 <= cfg["best_hr"] <= 1
     # tune.py: the c sweep of README.md:101-105 at every evaluation
     cfg = train_mf.main(["--data_path", GOLD + "/", "--dataset", "tiny", "--batch_size", "32", "--epoch", "2",
                          "--log_interval", "2", "--train", "rubibceboth", "--test", "rubi", "--start", "0",

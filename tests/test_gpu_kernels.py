@@ -340,3 +340,32 @@ def test_errors_are_loud(T, ops):
         ops.topk_rows(T.zeros((2, 100), dtype=T.float32, device="cuda"), 64)  # K > 32
     with pytest.raises(MacrError):
         ops.gather_dots(x.cpu(), x, x, x, x, x, x, x, x)  # host tensor
+
+
+def test_normalbce_trainer_steps_match_oracle(T, ops, oracle):
+    """`--train normalbce` (README.md:30; model.py:277-287,:100): element-wise BCE step on the
+    same plan / row-gradient / TF-Adam machinery; w and w_user stay untouched."""
+    n_users, n_items, B, steps = 900, 500, 256, 5
+    U, I, w, wu = make_model(41, n_users, n_items, scale=4.0)
+    hp_kw = dict(lr=1e-2, alpha=1e-2, beta=1e-3, decay=1e-4, batch_size=B)
+    st = oracle.MFState(U, I, w, wu)
+    tr = ops.MFTrainer(U, I, w, wu, ops.HParams.make(**hp_kw), max_batch=B)
+    tr.set_mode(ops.MFTrainer.NORMALBCE)
+    rng = np.random.RandomState(42)
+    for s in range(steps):
+        u, p, n = make_batch(rng, n_users, n_items, B)
+        want = oracle.mf_step_normal(st, u, p, n, oracle.HParams.make(**hp_kw))
+        got = tr.step_host(u.tolist(), p.tolist(), n.tolist())
+        np.testing.assert_allclose(np.array(got), want[:3], rtol=1e-4, atol=1e-5, err_msg=f"step {s}")
+    t = tr.tab
+    for name, g, o in (("U", t.U, st.U), ("I", t.I, st.I), ("mU", t.mU, st.mU), ("vI", t.vI, st.vI)):
+        np.testing.assert_allclose(g.cpu().numpy(), o, rtol=1e-4, atol=1e-5, err_msg=name)
+    np.testing.assert_array_equal(t.w.cpu().numpy(), w)
+    np.testing.assert_array_equal(t.wu.cpu().numpy(), wu)
+    # switching back re-captures the MACR graph
+    tr.set_mode(ops.MFTrainer.RUBIBCEBOTH)
+    u, p, n = make_batch(rng, n_users, n_items, B)
+    want = oracle.mf_step(st, u, p, n, oracle.HParams.make(**hp_kw))
+    got = tr.step_host(u.tolist(), p.tolist(), n.tolist())
+    np.testing.assert_allclose(np.array(got), want[:3], rtol=1e-4, atol=1e-4)
+    tr.close()

@@ -242,3 +242,32 @@ def test_mf_metrics_hand_checked():
     agg = mf_metrics.evaluate([[10, 1, 2, 11, 3], [4, 5, 6, 7, 8]], [[10, 11, 12], [99]], [5])
     assert agg["hit_ratio"][0] == pytest.approx(0.5)
     assert agg["recall"][0] == pytest.approx((2 / 3) / 2)
+
+
+def test_normalbce_step_matches_literal_graph(oracle):
+    """`--train normalbce` (model.py:277-287, :100): the oracle's closed-form step vs torch
+    autograd of the literal graph + TF Adam; w / w_user are not part of this graph."""
+    n_users, n_items, B = 60, 40, 96
+    U, I, w, wu = make_model(15, n_users, n_items, scale=4.0)
+    hp_kw = dict(lr=1e-2, alpha=1e-2, beta=1e-3, decay=1e-3, batch_size=B)
+    rng = np.random.RandomState(16)
+    batches = [make_batch(rng, n_users, n_items, B) for _ in range(3)]
+    st = oracle.MFState(U, I, w, wu)
+    hp = oracle.HParams.make(**hp_kw)
+    got = [oracle.mf_step_normal(st, *b, hp) for b in batches]
+    P = [t64(U).requires_grad_(True), t64(I).requires_grad_(True)]
+    opt = lit.TFAdam(P, hp_kw["lr"])
+    want = []
+    for u, p, n in batches:
+        for q in P:
+            q.grad = None
+        ui, pi, ni = (torch.as_tensor(x, dtype=torch.long) for x in (u, p, n))
+        mf, reg = lit.bce_plain(P[0][ui], P[1][pi], P[1][ni], hp_kw["decay"], hp_kw["batch_size"])
+        (mf + reg).backward()
+        opt.step([q.grad for q in P], [True, True])
+        want.append(((mf + reg).item(), mf.item(), reg.item()))
+    np.testing.assert_allclose(np.array(got)[:, :3], np.array(want), rtol=1e-5, atol=1e-6)
+    for name, a, b in (("U", st.U, P[0]), ("I", st.I, P[1]), ("mU", st.mU, opt.m[0]), ("vI", st.vI, opt.v[1])):
+        np.testing.assert_allclose(a, b.detach().numpy().reshape(a.shape), rtol=2e-3, atol=2e-6, err_msg=name)
+    np.testing.assert_array_equal(st.w, w)  # untouched
+    np.testing.assert_array_equal(st.wu, wu)
