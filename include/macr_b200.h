@@ -226,6 +226,9 @@ int macr_lgcn_trainer_run(macr_lgcn_trainer *h, const int32_t *batches, int n_st
 /* host-memory variant of macr_lgcn_trainer_run, see macr_mf_trainer_run_host */
 int macr_lgcn_trainer_run_host(macr_lgcn_trainer *h, const int32_t *batches_host, int n_steps,
                                int B, int train, float *losses_host);
+/* MACR_TRAIN_RUBIBCEBOTH = `--loss bceboth` (default), MACR_TRAIN_NORMALBCE = `--loss bce`
+ * (README.md:59, LightGCN.py:415-429,:186); see macr_mf_trainer_set_mode */
+int macr_lgcn_trainer_set_mode(macr_lgcn_trainer *h, int mode);
 /* propagated tables of the current parameters (device, owned by the handle):
  * users at Emean, items at Emean + n_users*d                                     */
 int macr_lgcn_trainer_embeddings(macr_lgcn_trainer *h, const float **Emean);

@@ -67,6 +67,7 @@ PROTOTYPES = {
     "macr_lgcn_trainer_step_host": (i32, [vp, vp, vp, vp, i32, i32, vp]),
     "macr_lgcn_trainer_run": (i32, [vp, vp, i32, i32, i32, vp]),
     "macr_lgcn_trainer_run_host": (i32, [vp, vp, i32, i32, i32, vp]),
+    "macr_lgcn_trainer_set_mode": (i32, [vp, i32]),
     "macr_lgcn_trainer_embeddings": (i32, [vp, C.POINTER(vp)]),
     "macr_lgcn_trainer_launches_per_step": (i32, [vp]),
     "macr_lgcn_trainer_steps_done": (i64, [vp]),

@@ -57,9 +57,9 @@ class _Worker(threading.Thread):
 def main(argv=None):
     args = flags.parse_lgcn_args(argv)
     logging.getLogger().setLevel(logging.INFO)
-    if args.alg_type != "lightgcn" or args.loss != "bceboth":
-        raise SystemExit(f"--alg_type {args.alg_type} --loss {args.loss}: only lightgcn / bceboth is "
-                         "implemented on the B200 path (DESIGN.md section 8)")
+    if args.alg_type != "lightgcn" or args.loss not in ("bceboth", "bce"):
+        raise SystemExit(f"--alg_type {args.alg_type} --loss {args.loss}: only lightgcn with bceboth (MACR) or bce "
+                         "(the README's baseline) is implemented on the B200 path (DESIGN.md section 8)")
     data_generator = Data(path=args.data_path + args.dataset, batch_size=args.batch_size, args=args)
     seed = 12345  # LightGCN.py:651-655
     random.seed(seed)
@@ -98,9 +98,13 @@ def main(argv=None):
     if args.save_flag == 1:
         os.makedirs(weights_save_path, exist_ok=True)
 
-    train_fetch = [model.opt_two_bce_both, model.loss_two_bce_both, model.mf_loss_two_bce_both,
-                   model.emb_loss_two_bce_both, model.reg_loss_two_bce_both]
-    test_fetch = [model.loss_two_bce_both, model.mf_loss_two_bce_both, model.emb_loss_two_bce_both]
+    if args.loss == "bce":  # LightGCN.py:592-593,625-626
+        train_fetch = [model.opt_bce, model.loss_bce, model.mf_loss_bce, model.emb_loss_bce, model.reg_loss_bce]
+        test_fetch = [model.loss_bce, model.mf_loss_bce, model.emb_loss_bce]
+    else:
+        train_fetch = [model.opt_two_bce_both, model.loss_two_bce_both, model.mf_loss_two_bce_both,
+                       model.emb_loss_two_bce_both, model.reg_loss_two_bce_both]
+        test_fetch = [model.loss_two_bce_both, model.mf_loss_two_bce_both, model.emb_loss_two_bce_both]
     drops = {model.node_dropout: flags.as_list(args.node_dropout),
              model.mess_dropout: flags.as_list(args.mess_dropout)}
 

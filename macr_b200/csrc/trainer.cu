@@ -443,6 +443,7 @@ struct macr_lgcn_trainer : macr::TrainerBase {
   macr::SpmmPlan plan;      // static segment decomposition of the adjacency
   bool emb_dirty;
   int launches;
+  int mode = MACR_TRAIN_RUBIBCEBOTH;  // MACR_TRAIN_NORMALBCE: `--loss bce`
 };
 
 namespace macr {
@@ -475,7 +476,10 @@ static int lgcn_enqueue_impl(macr_lgcn_trainer *h, int B, int train) {
   rc = launch_gather_dots(Ue, Ie, h->U, h->I, h->w, h->wu, nullptr, nullptr, nullptr, h->st, B, yp,
                           yn, sp, sn, su, rq, h->snap, &g, s);
   if (rc) return rc;
-  rc = launch_grid_bce(yp, yn, B, hp, g, dyp, dyn, dsp, dsn, dsu, train, rq, h->st, nullptr, s);
+  if (h->mode == MACR_TRAIN_NORMALBCE)  // LightGCN.py:415-429: element-wise BCE, loss = mf + emb
+    rc = launch_plain_bce(yp, yn, B, hp, rq, h->st, nullptr, dyp, dyn, dsp, dsn, dsu, s);
+  else
+    rc = launch_grid_bce(yp, yn, B, hp, g, dyp, dyn, dsp, dsn, dsu, train, rq, h->st, nullptr, s);
   if (rc) return rc;
   launches += 2;
   if (train) {
@@ -639,6 +643,21 @@ extern "C" int macr_lgcn_trainer_run_host(macr_lgcn_trainer *h, const int32_t *b
   if (train && n_steps > 0) {
     h->steps_done += n_steps;
     h->emb_dirty = true;
+  }
+  return MACR_OK;
+}
+
+extern "C" int macr_lgcn_trainer_set_mode(macr_lgcn_trainer *h, int mode) {
+  MACR_CHECK_ARG(h, "macr_lgcn_trainer_set_mode: null handle");
+  MACR_CHECK_ARG(mode == MACR_TRAIN_RUBIBCEBOTH || mode == MACR_TRAIN_NORMALBCE,
+                 "macr_lgcn_trainer_set_mode: unknown mode %d", mode);
+  if (mode != h->mode) {
+    cudaStreamSynchronize(h->s);
+    for (auto &kv : h->graphs) cudaGraphExecDestroy(kv.second);
+    for (auto &kv : h->graphs_eval) cudaGraphExecDestroy(kv.second);
+    h->graphs.clear();
+    h->graphs_eval.clear();
+    h->mode = mode;
   }
   return MACR_OK;
 }

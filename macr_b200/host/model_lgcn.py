@@ -22,9 +22,10 @@ from .session import Fetch, Placeholder, Unsupported
 
 _TRAIN = ("opt_two_bce_both", "loss_two_bce_both", "mf_loss_two_bce_both", "emb_loss_two_bce_both",
           "reg_loss_two_bce_both")
+# `--loss bce` (README.md:59, the baseline): LightGCN.py:183-186,415-429
+_TRAIN_BCE = ("opt_bce", "loss_bce", "mf_loss_bce", "emb_loss_bce", "reg_loss_bce")
 _UNSUPPORTED = (
-    "opt", "loss", "mf_loss", "emb_loss", "reg_loss", "opt_bce", "loss_bce", "mf_loss_bce",
-    "emb_loss_bce", "reg_loss_bce", "opt_two_bce1", "loss_two_bce1", "mf_loss_two_bce1",
+    "opt", "loss", "mf_loss", "emb_loss", "reg_loss", "opt_two_bce1", "loss_two_bce1", "mf_loss_two_bce1",
     "emb_loss_two_bce1", "reg_loss_two_bce1", "opt_two_bce2", "loss_two_bce2", "mf_loss_two_bce2",
     "emb_loss_two_bce2", "reg_loss_two_bce2", "rubi_ratings1", "rubi_ratings2",
     "batch_ratings_causal_c", "direct_minus_ratings_both",
@@ -70,17 +71,27 @@ class LightGCN(_ScoringMixin):
                                        max_batch=min(max(self.batch_size, 1), 8192), device=self.dev)
         for name in ("users", "pos_items", "neg_items", "node_dropout", "mess_dropout"):
             setattr(self, name, Placeholder(self, name))
-        for name in _TRAIN + ("rubi_ratings_both", "batch_ratings"):
+        for name in _TRAIN + _TRAIN_BCE + ("rubi_ratings_both", "batch_ratings"):
             setattr(self, name, Fetch(self, name))
         for name in _UNSUPPORTED:
             setattr(self, name, Unsupported(self, name))
 
     def _run(self, names, feeds):
-        if any(n in _TRAIN for n in names):
+        if any(n in _TRAIN or n in _TRAIN_BCE for n in names):
+            normal = any(n in _TRAIN_BCE for n in names)
+            if normal and any(n in _TRAIN for n in names):
+                raise NotImplementedError("fetches of two different loss graphs in one sess.run")
+            mode = ops.LGCNTrainer.NORMALBCE if normal else ops.LGCNTrainer.RUBIBCEBOTH
+            if getattr(self, "_mode", ops.LGCNTrainer.RUBIBCEBOTH) != mode:
+                self.trainer.set_mode(mode)
+                self._mode = mode
             train = any(n.startswith("opt") for n in names)
             loss, mf, emb = self.step(feeds["users"], feeds["pos_items"], feeds["neg_items"], train)
+            zero = np.zeros(1, np.float32)  # reg_loss is a constant [0.] (:427, :530)
             val = {"opt_two_bce_both": None, "loss_two_bce_both": loss, "mf_loss_two_bce_both": mf,
-                   "emb_loss_two_bce_both": emb, "reg_loss_two_bce_both": np.zeros(1, np.float32)}
+                   "emb_loss_two_bce_both": emb, "reg_loss_two_bce_both": zero,
+                   "opt_bce": None, "loss_bce": loss, "mf_loss_bce": mf, "emb_loss_bce": emb,
+                   "reg_loss_bce": zero}
             return [val[n] for n in names]
         return [self._run_scores(n, feeds) for n in names]
 

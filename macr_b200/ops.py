@@ -341,6 +341,12 @@ class MFTrainer:
 class LGCNTrainer:
     """Handle around macr_lgcn_trainer_* (one `--loss bceboth` LightGCN model)."""
 
+    RUBIBCEBOTH, NORMALBCE = 0, 1
+
+    def set_mode(self, mode):
+        """RUBIBCEBOTH (`--loss bceboth`, default) or NORMALBCE (`--loss bce`, the baseline)."""
+        check(lib().macr_lgcn_trainer_set_mode(self._h, int(mode)), "macr_lgcn_trainer_set_mode")
+
     def _run_host(self, n, B, ids_ptr, loss_ptr, train=True):
         return lib().macr_lgcn_trainer_run_host(self._h, ids_ptr, n, B, 1 if train else 0, loss_ptr)
 

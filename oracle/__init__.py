@@ -24,6 +24,7 @@ from .capi import (  # noqa: F401
     spmm_csr,
     lgcn_propagate,
     lgcn_step,
+    lgcn_step_normal,
     score_gates,
     score_matrix,
     score_topk,

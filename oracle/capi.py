@@ -194,6 +194,23 @@ def lgcn_step(st, rowptr, col, val, n_layers, u, p, n, hp, train=True):
     return losses
 
 
+def lgcn_step_normal(st, rowptr, col, val, n_layers, u, p, n, hp, train=True):
+    """One `--loss bce` LightGCN step (LightGCN.py:415-429,:186) on MFState `st` (in place)."""
+    u, p, n = _ids(u), _ids(p), _ids(n)
+    if st.t == 0:
+        st.pw[:] = (hp.beta1, hp.beta2)
+    losses = np.empty(4, np.float32)
+    lib().oracle_lgcn_step_normal(_i(rowptr), _i(col), _f(val), _f(st.U), _f(st.mU), _f(st.vU),
+                                  C.c_int64(st.U.shape[0]), _f(st.I), _f(st.mI), _f(st.vI),
+                                  C.c_int64(st.I.shape[0]), _f(st.w), _f(st.wu),
+                                  C.c_int(st.U.shape[1]), C.c_int(n_layers), _i(u), _i(p), _i(n),
+                                  C.c_int(len(u)), C.c_int(1 if train else 0), C.byref(hp),
+                                  _f(st.pw), _f(losses))
+    if train:
+        st.t += 1
+    return losses
+
+
 def score_gates(rows, wvec):
     sig = np.empty(rows.shape[0], np.float32)
     lib().oracle_score_gates(_f(rows), C.c_int64(rows.shape[0]), C.c_int(rows.shape[1]),

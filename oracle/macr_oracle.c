@@ -422,12 +422,14 @@ void oracle_lgcn_propagate(const int32_t *rowptr, const int32_t *col, const floa
   free(E0);
 }
 
-void oracle_lgcn_step(const int32_t *rowptr, const int32_t *col, const float *val, float *U,
-                      float *mU, float *vU, int64_t n_users, float *I, float *mI, float *vI,
-                      int64_t n_items, float *w, float *mw, float *vw, float *wu, float *mwu,
-                      float *vwu, int d, int L, const int32_t *u, const int32_t *p,
-                      const int32_t *n, int B, int train, const oracle_hparams *hp, float *pw,
-                      float *losses) {
+/* normal != 0: `--loss bce` (LightGCN.py:415-429,:186): element-wise BCE with "+1e-9" on the
+ * propagated rows, same L2 on the raw rows, w / w_user not part of the graph */
+static void lgcn_step_impl(const int32_t *rowptr, const int32_t *col, const float *val, float *U,
+                           float *mU, float *vU, int64_t n_users, float *I, float *mI, float *vI,
+                           int64_t n_items, float *w, float *mw, float *vw, float *wu, float *mwu,
+                           float *vwu, int d, int L, const int32_t *u, const int32_t *p,
+                           const int32_t *n, int B, int train, const oracle_hparams *hp, float *pw,
+                           float *losses, int normal) {
   const int64_t N = n_users + n_items, ne = N * d;
   float *Em = (float *)malloc(sizeof(float) * (size_t)ne * 2), *E0 = Em + ne;
   lgcn_layers(rowptr, col, val, U, n_users, I, n_items, d, L, Em, E0);
@@ -440,9 +442,22 @@ void oracle_lgcn_step(const int32_t *rowptr, const int32_t *col, const float *va
   float l3[3];
   /* scores from propagated rows (LightGCN.py:145-147), L2 from raw rows (:148-150,525-526) */
   oracle_gather_dots(Ue, Ie, U, I, w, wu, u, p, n, B, d, yp, yn, sp, sn, su, rq);
-  oracle_grid_bce(yp, yn, sp, sn, su, B, hp->alpha, hp->beta, l3, train ? dyp : NULL, dyn, dsp,
-                  dsn, dsu);
-  batch_losses(l3, rq, B, hp, losses); /* loss = mf_loss + emb_loss (LightGCN.py:200) */
+  if (normal) {
+    float mf;
+    oracle_plain_bce(yp, yn, B, &mf, dyp, dyn);
+    memset(dsp, 0, sizeof(float) * (size_t)B * 3); /* dsp, dsn, dsu are contiguous */
+    double rs = 0.0;
+    for (int b = 0; b < B; ++b) rs += rq[b];
+    const float emb = hp->decay * ((float)(rs * 0.5) / (float)hp->batch_size_flag);
+    losses[0] = mf + emb; /* LightGCN.py:185 loss_bce = mf_loss_bce + emb_loss_bce */
+    losses[1] = mf;
+    losses[2] = emb;
+    losses[3] = mf;
+  } else {
+    oracle_grid_bce(yp, yn, sp, sn, su, B, hp->alpha, hp->beta, l3, train ? dyp : NULL, dyn, dsp,
+                    dsn, dsu);
+    batch_losses(l3, rq, B, hp, losses); /* loss = mf_loss + emb_loss (LightGCN.py:200) */
+  }
   if (!train) {
     free(Em);
     free(sc);
@@ -500,14 +515,35 @@ void oracle_lgcn_step(const int32_t *rowptr, const int32_t *col, const float *va
       var[e] = var[e] - (lr_t * m[e]) / (sqrtf(v[e]) + hp->eps);
     }
   }
-  oracle_adam_dense_vec(w, mw, vw, gw, d, lr_t, hp->beta1, hp->beta2, hp->eps);
-  oracle_adam_dense_vec(wu, mwu, vwu, gwu, d, lr_t, hp->beta1, hp->beta2, hp->eps);
+  if (!normal) {
+    oracle_adam_dense_vec(w, mw, vw, gw, d, lr_t, hp->beta1, hp->beta2, hp->eps);
+    oracle_adam_dense_vec(wu, mwu, vwu, gwu, d, lr_t, hp->beta1, hp->beta2, hp->eps);
+  }
   pw[0] = pw[0] * hp->beta1;
   pw[1] = pw[1] * hp->beta2;
   free(Em);
   free(sc);
   free(gU);
   free(dEm);
+}
+
+void oracle_lgcn_step(const int32_t *rowptr, const int32_t *col, const float *val, float *U,
+                      float *mU, float *vU, int64_t n_users, float *I, float *mI, float *vI,
+                      int64_t n_items, float *w, float *mw, float *vw, float *wu, float *mwu,
+                      float *vwu, int d, int L, const int32_t *u, const int32_t *p,
+                      const int32_t *n, int B, int train, const oracle_hparams *hp, float *pw,
+                      float *losses) {
+  lgcn_step_impl(rowptr, col, val, U, mU, vU, n_users, I, mI, vI, n_items, w, mw, vw, wu, mwu, vwu,
+                 d, L, u, p, n, B, train, hp, pw, losses, 0);
+}
+
+void oracle_lgcn_step_normal(const int32_t *rowptr, const int32_t *col, const float *val, float *U,
+                             float *mU, float *vU, int64_t n_users, float *I, float *mI,
+                             float *vI, int64_t n_items, float *w, float *wu, int d, int L,
+                             const int32_t *u, const int32_t *p, const int32_t *n, int B, int train,
+                             const oracle_hparams *hp, float *pw, float *losses) {
+  lgcn_step_impl(rowptr, col, val, U, mU, vU, n_users, I, mI, vI, n_items, w, NULL, NULL, wu, NULL,
+                 NULL, d, L, u, p, n, B, train, hp, pw, losses, 1);
 }
 
 /* ---- scoring: model.py:45 batch_ratings, :199 rubi_ratings_both ---- */

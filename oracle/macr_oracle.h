@@ -86,6 +86,12 @@ void oracle_lgcn_step(const int32_t *rowptr, const int32_t *col, const float *va
                       float *vwu, int d, int n_layers, const int32_t *u, const int32_t *p,
                       const int32_t *n, int B, int train, const oracle_hparams *hp, float *pw,
                       float *losses);
+/* `--loss bce` (LightGCN.py:415-429,:186) */
+void oracle_lgcn_step_normal(const int32_t *rowptr, const int32_t *col, const float *val, float *U,
+                             float *mU, float *vU, int64_t n_users, float *I, float *mI,
+                             float *vI, int64_t n_items, float *w, float *wu, int d, int L,
+                             const int32_t *u, const int32_t *p, const int32_t *n, int B, int train,
+                             const oracle_hparams *hp, float *pw, float *losses);
 
 /* model.py:199 scoring */
 void oracle_score_gates(const float *rows, int64_t n, int d, const float *wvec, float *sig);

@@ -369,3 +369,27 @@ def test_normalbce_trainer_steps_match_oracle(T, ops, oracle):
     got = tr.step_host(u.tolist(), p.tolist(), n.tolist())
     np.testing.assert_allclose(np.array(got), want[:3], rtol=1e-4, atol=1e-4)
     tr.close()
+
+
+def test_lgcn_bce_trainer_steps_match_oracle(T, ops, oracle):
+    """`--loss bce` (README.md:59; LightGCN.py:415-429,:186) on the LightGCN trainer."""
+    n_users, n_items, L, B, steps = 1200, 500, 2, 256, 4
+    _, (rowptr, col, val) = _graph(L, n_users, n_items, 10)
+    U, I, w, wu = make_model(29, n_users, n_items, scale=4.0)
+    hp_kw = dict(lr=1e-3, alpha=1e-2, beta=1e-3, decay=1e-5, batch_size=B)
+    st = oracle.MFState(U, I, w, wu)
+    tr = ops.LGCNTrainer(rowptr, col, val, U, I, w, wu, L, ops.HParams.make(**hp_kw), max_batch=B)
+    tr.set_mode(ops.LGCNTrainer.NORMALBCE)
+    rng = np.random.RandomState(30)
+    for s in range(steps):
+        u, p, n = make_batch(rng, n_users, n_items, B)
+        lo_eval = tr.step_host(u.tolist(), p.tolist(), n.tolist(), train=False)
+        want = oracle.lgcn_step_normal(st, rowptr, col, val, L, u, p, n, oracle.HParams.make(**hp_kw))
+        got = tr.step_host(u.tolist(), p.tolist(), n.tolist())
+        np.testing.assert_allclose(np.array(got), want[:3], rtol=1e-4, atol=1e-5, err_msg=f"step {s}")
+        np.testing.assert_allclose(np.array(lo_eval), want[:3], rtol=1e-4, atol=1e-5)
+    t = tr.tab
+    for name, g, o in (("U", t.U, st.U), ("I", t.I, st.I)):
+        np.testing.assert_allclose(g.cpu().numpy(), o, rtol=1e-4, atol=1e-5, err_msg=name)
+    np.testing.assert_array_equal(t.w.cpu().numpy(), w)
+    tr.close()

@@ -271,3 +271,41 @@ def test_normalbce_step_matches_literal_graph(oracle):
         np.testing.assert_allclose(a, b.detach().numpy().reshape(a.shape), rtol=2e-3, atol=2e-6, err_msg=name)
     np.testing.assert_array_equal(st.w, w)  # untouched
     np.testing.assert_array_equal(st.wu, wu)
+
+
+def test_lgcn_bce_step_matches_literal_graph(oracle):
+    """`--loss bce` (LightGCN.py:415-429,:186): element-wise BCE on the propagated rows, L2 on the
+    raw rows; oracle step vs torch autograd through the propagation."""
+    n_users, n_items, B, L = 50, 30, 64, 2
+    lists = make_interactions(13, n_users, n_items, 5)
+    rowptr, col, val = norm_adj_csr(lists, n_users, n_items)
+    U, I, w, wu = make_model(19, n_users, n_items, scale=4.0)
+    hp_kw = dict(lr=1e-2, alpha=1e-2, beta=1e-3, decay=1e-3, batch_size=B)
+    rng = np.random.RandomState(20)
+    batches = [make_batch(rng, n_users, n_items, B) for _ in range(3)]
+    st = oracle.MFState(U, I, w, wu)
+    hp = oracle.HParams.make(**hp_kw)
+    N = n_users + n_items
+    A = torch.zeros(N, N, dtype=torch.float64)
+    for r in range(N):
+        A[r, col[rowptr[r]:rowptr[r + 1]]] = t64(val[rowptr[r]:rowptr[r + 1]])
+    P = [t64(U).requires_grad_(True), t64(I).requires_grad_(True)]
+    opt = lit.TFAdam(P, hp_kw["lr"])
+    for u, p, n in batches:
+        lo_eval = oracle.lgcn_step_normal(st, rowptr, col, val, L, u, p, n, hp, train=False)
+        lo = oracle.lgcn_step_normal(st, rowptr, col, val, L, u, p, n, hp, train=True)
+        np.testing.assert_allclose(lo_eval, lo, rtol=1e-6)
+        for q in P:
+            q.grad = None
+        ui, pi, ni = (torch.as_tensor(x, dtype=torch.long) for x in (u, p, n))
+        ua, ia = lit.lightgcn_embed(A, P[0], P[1], L)
+        ps, ns = torch.sum(ua[ui] * ia[pi], 1), torch.sum(ua[ui] * ia[ni], 1)
+        mf = torch.mean(-torch.log(torch.sigmoid(ps) + 1e-9) - torch.log(1 - torch.sigmoid(ns) + 1e-9))  # :423
+        l2 = lambda x: torch.sum(x * x) / 2
+        emb = hp_kw["decay"] * (l2(P[0][ui]) + l2(P[1][pi]) + l2(P[1][ni])) / B                      # :419-425
+        (mf + emb).backward()
+        opt.step([q.grad for q in P], [True, True])
+        np.testing.assert_allclose(lo[:3], [(mf + emb).item(), mf.item(), emb.item()], rtol=1e-5, atol=1e-6)
+    for name, a, b in (("U", st.U, P[0]), ("I", st.I, P[1])):
+        np.testing.assert_allclose(a, b.detach().numpy().reshape(a.shape), rtol=2e-3, atol=2e-6, err_msg=name)
+    np.testing.assert_array_equal(st.w, w)
