@@ -54,7 +54,10 @@ class _Worker(threading.Thread):
         return self.data
 
 
-def main(argv=None):
+def main(argv=None, tune=False):
+    """tune=True is `python macr_lightgcn/LightGCN_tune.py ...` (LightGCN_tune.py:848-871): every
+    evaluation sweeps c over np.linspace(--start, --end, --step); the propagated embeddings are
+    computed once per parameter version, so a sweep costs one scoring pass per c."""
     args = flags.parse_lgcn_args(argv)
     logging.getLogger().setLevel(logging.INFO)
     if args.alg_type != "lightgcn" or args.loss not in ("bceboth", "bce"):
@@ -179,6 +182,23 @@ def main(argv=None):
                     ", ".join("%.5f" % r for r in ret["ndcg"]))
                 print(perf_str, end="")
                 logging.info(perf_str)
+        elif args.test == "rubiboth" and tune:
+            print("Epoch %d" % epoch)
+            best = None
+            for c in np.linspace(args.start, args.end, args.step):
+                model.update_c(sess, c)
+                r = evaluator.test(sess, model, users_to_test, method=args.test)
+                if best is None or r["hr"][0] > best[1]["hr"][0]:
+                    best = (float(c), r)
+                if args.verbose > 0:
+                    perf_str += "c:%.2f recall=[%.5f, %.5f], hit=[%.5f, %.5f], ndcg=[%.5f, %.5f]\n" % (
+                        c, r["recall"][0], r["recall"][-1], r["hr"][0], r["hr"][-1],
+                        r["ndcg"][0], r["ndcg"][-1])
+            ret = best[1]
+            if ret["hr"][0] > config["best_c_hr"]:
+                config.update(best_c_hr=ret["hr"][0], best_c_epoch=epoch, best_c=best[0])
+            print(perf_str, end="")
+            logging.info(perf_str)
         elif args.test == "rubiboth":
             print("Epoch %d" % epoch)
             c = args.c

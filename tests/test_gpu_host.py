@@ -215,6 +215,13 @@ def test_cli_drivers_run_end_to_end(tmp_path, monkeypatch, capsys):
     out = capsys.readouterr().out
     assert "c:2.00 recall=[" in out and "use the pre adjcency matrix" in out
     assert res["last"] is not None and 0 <= res["best_hr"] <= 1
+    # LightGCN_tune.py: c sweep at every evaluation
+    lightgcn.main(["--data_path", GOLD + "/", "--dataset", "tiny", "--batch_size", "32", "--epoch", "1",
+                   "--log_interval", "1", "--layer_size", "[64,64]", "--Ks", "[20]", "--loss", "bceboth",
+                   "--test", "rubiboth", "--start", "0", "--end", "4", "--step", "3", "--lr", "0.001",
+                   "--weights_path", str(tmp_path) + "/"], tune=True)
+    out = capsys.readouterr().out
+    assert "c:0.00 recall=[" in out and "c:2.00 recall=[" in out and "c:4.00 recall=[" in out
     # the README's LightGCN baseline (README.md:59): --loss bce --test normal
     res = lightgcn.main(["--data_path", GOLD + "/", "--dataset", "tiny", "--batch_size", "32", "--epoch", "2",
                          "--log_interval", "1", "--layer_size", "[64,64]", "--Ks", "[20]", "--loss", "bce",
