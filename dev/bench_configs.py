@@ -154,10 +154,13 @@ def main():
                 ts.append(a.elapsed_time(b) * 1e-3)
             return float(np.mean(ts))
 
-        t_spmm = flushed(lambda: ops.spmm_csr(d_rp, d_col, d_val, X))
+        plan = ops.SpmmPlan(d_rp)  # static segment decomposition, built once per graph
+        t_spmm = flushed(lambda: ops.spmm_csr(d_rp, d_col, d_val, X, plan=plan))
+        t_spmm_stateless = flushed(lambda: ops.spmm_csr(d_rp, d_col, d_val, X), reps=5)
         spmm_bytes = 8.0 * nnz + 4.0 * (N + 1) + 8.0 * N * D
+        gather_bytes = 8.0 * nnz + 4.0 * D * nnz + 4.0 * N * D  # every nonzero reads a 256-byte row (L2)
         dU, dI = torch.from_numpy(Ue).to(dev), torch.from_numpy(Ie).to(dev)
-        t_prop = flushed(lambda: ops.lgcn_propagate(d_rp, d_col, d_val, dU, dI, L))
+        t_prop = flushed(lambda: ops.lgcn_propagate(d_rp, d_col, d_val, dU, dI, L, plan=plan))
         hp = ops.HParams.make(lr=1e-3, alpha=1e-2, beta=1e-3, decay=1e-4, batch_size=B)
         tr = ops.LGCNTrainer(rowptr, col, val, Ue, Ie, w, wu, L, hp, max_batch=B, device=dev)
         nb = 64
@@ -180,8 +183,12 @@ def main():
         emit(config="MACR-LightGCN %s U=%d I=%d nnz(A)=%d max row %d L=2 d=64 B=4096 bceboth" %
                     (ds, U_n, I_n, nnz, max_deg), graph=src,
              l2="256 MiB memset before every timed call",
-             spmm={"ms": 1e3 * t_spmm, "bytes": spmm_bytes, "achieved_gbs": spmm_bytes / t_spmm / 1e9,
-                   "peak_gbs": pk["hbm_gbs"], "frac": spmm_bytes / t_spmm / 1e9 / pk["hbm_gbs"]},
+             spmm={"ms": 1e3 * t_spmm, "ms_stateless_kernel": 1e3 * t_spmm_stateless,
+                   "bytes": spmm_bytes, "achieved_gbs": spmm_bytes / t_spmm / 1e9,
+                   "peak_gbs": pk["hbm_gbs"], "frac": spmm_bytes / t_spmm / 1e9 / pk["hbm_gbs"],
+                   "l2_gather_bytes": gather_bytes, "l2_gather_gbs": gather_bytes / t_spmm / 1e9,
+                   "note": "algorithmic bytes assume X is read once; each nonzero actually gathers a "
+                           "256-byte row from L2 (X is L2-resident), which is what bounds the kernel"},
              propagate={"ms": 1e3 * t_prop, "layers": L},
              step={"ms": 1e3 * t_step, "interactions_per_s": B / t_step, "launches": tr.launches_per_step,
                    "bytes": step_bytes, "achieved_gbs": step_bytes / t_step / 1e9,

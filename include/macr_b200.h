@@ -203,6 +203,22 @@ int macr_spmm_csr(const int32_t *rowptr, const int32_t *col, const float *val, i
 int macr_lgcn_propagate(const int32_t *rowptr, const int32_t *col, const float *val,
                         const float *U, int64_t n_users, const float *I, int64_t n_items,
                         int d, int n_layers, float *Emean, float *tmp, macr_stream_t stream);
+/* The same two operations on a static work decomposition of the adjacency: every row is cut
+ * once into segments of <= 64 nonzeros (one half-warp each; rows of several segments are summed
+ * in segment order), so popular items (27 504 nonzeros in ml_10m) do not serialise the launch.
+ * The adjacency of a run never changes (LightGCN.py:257-269 builds it once): create the plan
+ * once from the device rowptr (one D2H copy, host-side construction), reuse it for every call.
+ * Results differ from the unplanned entry points only in the rounding of long rows. */
+typedef struct macr_spmm_plan macr_spmm_plan;
+int macr_spmm_plan_create(const int32_t *rowptr, int64_t n_rows, macr_spmm_plan **out);
+int macr_spmm_plan_destroy(macr_spmm_plan *plan);
+int macr_spmm_csr_planned(const macr_spmm_plan *plan, const int32_t *rowptr, const int32_t *col,
+                          const float *val, int64_t n_rows, const float *X, int d, float *Y,
+                          macr_stream_t stream);
+int macr_lgcn_propagate_planned(const macr_spmm_plan *plan, const int32_t *rowptr,
+                                const int32_t *col, const float *val, const float *U,
+                                int64_t n_users, const float *I, int64_t n_items, int d,
+                                int n_layers, float *Emean, float *tmp, macr_stream_t stream);
 
 typedef struct macr_lgcn_trainer macr_lgcn_trainer;
 int macr_lgcn_trainer_create(macr_lgcn_trainer **out,

@@ -61,6 +61,10 @@ PROTOTYPES = {
     "macr_mf_trainer_destroy": (i32, [vp]),
     "macr_spmm_csr": (i32, [vp, vp, vp, i64, vp, i32, vp, vp]),
     "macr_lgcn_propagate": (i32, [vp, vp, vp, vp, i64, vp, i64, i32, i32, vp, vp, vp]),
+    "macr_spmm_plan_create": (i32, [vp, i64, C.POINTER(vp)]),
+    "macr_spmm_plan_destroy": (i32, [vp]),
+    "macr_spmm_csr_planned": (i32, [vp, vp, vp, vp, i64, vp, i32, vp, vp]),
+    "macr_lgcn_propagate_planned": (i32, [vp, vp, vp, vp, vp, i64, vp, i64, i32, i32, vp, vp, vp]),
     "macr_lgcn_trainer_create": (i32, [C.POINTER(vp), vp, vp, vp, vp, vp, vp, i64, vp, vp, vp, i64] +
                                  [vp] * 6 + [i32, i32, i32, C.POINTER(HParams), vp]),
     "macr_lgcn_trainer_step": (i32, [vp, vp, vp, vp, i32, i32, vp]),

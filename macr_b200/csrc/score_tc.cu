@@ -762,7 +762,8 @@ rerank_kernel(const float *__restrict__ Uq, int T, const float *__restrict__ It,
         const float os = __shfl_sync(0xffffffffu, cs_[r2], l2);
         const int og = __shfl_sync(0xffffffffu, cg_[r2], l2);
 #pragma unroll
-        for (int r = 0; r < kRounds; ++r) rank[r] += score_better(os, og, cs_[r], cg_[r]) ? 1 : 0;
+        for (int r = 0; r < kRounds; ++r)
+          if (r < nr) rank[r] += score_better(os, og, cs_[r], cg_[r]) ? 1 : 0;  // warp-uniform
       }
     }
   }

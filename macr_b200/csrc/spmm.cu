@@ -10,6 +10,7 @@
 #include "spmm.cuh"
 
 #include <algorithm>
+#include <new>
 #include <vector>
 
 namespace macr {
@@ -362,6 +363,60 @@ extern "C" int macr_spmm_csr(const int32_t *rowptr, const int32_t *col, const fl
   MACR_CHECK_ARG(rowptr && col && val && X && Y, "macr_spmm_csr: null pointer");
   RowSrc x{X, X, n_rows};
   return launch_spmm(rowptr, col, val, n_rows, x, nullptr, Y, x, nullptr, 0.f, as_stream(stream));
+}
+
+struct macr_spmm_plan {
+  macr::SpmmPlan plan;
+  int64_t n_rows;
+};
+
+extern "C" int macr_spmm_plan_create(const int32_t *rowptr, int64_t n_rows, macr_spmm_plan **out) {
+  MACR_CHECK_ARG(rowptr && out && n_rows >= 0, "macr_spmm_plan_create: bad argument");
+  macr_spmm_plan *h = new (std::nothrow) macr_spmm_plan();
+  MACR_CHECK_ARG(h, "macr_spmm_plan_create: out of host memory");
+  h->n_rows = n_rows;
+  int rc = build_spmm_plan(rowptr, n_rows, &h->plan);
+  if (rc) {
+    delete h;
+    return rc;
+  }
+  *out = h;
+  return MACR_OK;
+}
+
+extern "C" int macr_spmm_plan_destroy(macr_spmm_plan *h) {
+  if (!h) return MACR_OK;
+  free_spmm_plan(&h->plan);
+  delete h;
+  return MACR_OK;
+}
+
+extern "C" int macr_spmm_csr_planned(const macr_spmm_plan *plan, const int32_t *rowptr,
+                                     const int32_t *col, const float *val, int64_t n_rows,
+                                     const float *X, int d, float *Y, macr_stream_t stream) {
+  MACR_CHECK_ARG(d == kD, "macr_spmm_csr_planned: d must be %d (got %d)", kD, d);
+  MACR_CHECK_ARG(plan && rowptr && col && val && X && Y, "macr_spmm_csr_planned: null pointer");
+  MACR_CHECK_ARG(plan->n_rows == n_rows, "macr_spmm_csr_planned: plan was built for %lld rows",
+                 (long long)plan->n_rows);
+  RowSrc x{X, X, n_rows};
+  return launch_spmm_planned(&plan->plan, rowptr, col, val, n_rows, x, nullptr, Y, x, nullptr, 0.f,
+                             nullptr, as_stream(stream));
+}
+
+extern "C" int macr_lgcn_propagate_planned(const macr_spmm_plan *plan, const int32_t *rowptr,
+                                           const int32_t *col, const float *val, const float *U,
+                                           int64_t n_users, const float *I, int64_t n_items, int d,
+                                           int n_layers, float *Emean, float *tmp,
+                                           macr_stream_t stream) {
+  MACR_CHECK_ARG(d == kD, "macr_lgcn_propagate_planned: d must be %d (got %d)", kD, d);
+  MACR_CHECK_ARG(plan && rowptr && col && val && U && I && Emean && tmp,
+                 "macr_lgcn_propagate_planned: null pointer");
+  MACR_CHECK_ARG(plan->n_rows == n_users + n_items,
+                 "macr_lgcn_propagate_planned: plan was built for %lld rows", (long long)plan->n_rows);
+  MACR_CHECK_ARG(n_layers >= 0 && n_layers <= 16, "macr_lgcn_propagate_planned: bad n_layers %d",
+                 n_layers);
+  return launch_lgcn_propagate(rowptr, col, val, U, n_users, I, n_items, n_layers, Emean, tmp,
+                               as_stream(stream), &plan->plan);
 }
 
 extern "C" int macr_lgcn_propagate(const int32_t *rowptr, const int32_t *col, const float *val,

@@ -102,17 +102,47 @@ def adam_vec(var, m, v, grad, lr_t, beta1=0.9, beta2=0.999, eps=1e-8):
                               eps, stream_ptr()), "macr_adam_vec")
 
 
-def spmm_csr(rowptr, col, val, X):
+class SpmmPlan:
+    """Static segment decomposition of one adjacency (macr_spmm_plan_*): build once per graph."""
+
+    def __init__(self, rowptr):
+        self._h = C.c_void_p()
+        self.n_rows = rowptr.numel() - 1
+        check(lib().macr_spmm_plan_create(_i(rowptr), self.n_rows, C.byref(self._h)),
+              "macr_spmm_plan_create")
+
+    def close(self):
+        if self._h:
+            lib().macr_spmm_plan_destroy(self._h)
+            self._h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+def spmm_csr(rowptr, col, val, X, plan=None):
     Y = torch.empty_like(X)
+    if plan is not None:
+        check(lib().macr_spmm_csr_planned(plan._h, _i(rowptr), _i(col), _f(val), X.shape[0], _f(X),
+                                          X.shape[1], _f(Y), stream_ptr()), "macr_spmm_csr_planned")
+        return Y
     check(lib().macr_spmm_csr(_i(rowptr), _i(col), _f(val), X.shape[0], _f(X), X.shape[1], _f(Y),
                               stream_ptr()), "macr_spmm_csr")
     return Y
 
 
-def lgcn_propagate(rowptr, col, val, U, I, n_layers):
+def lgcn_propagate(rowptr, col, val, U, I, n_layers, plan=None):
     N = U.shape[0] + I.shape[0]
     E = torch.empty((N, U.shape[1]), dtype=torch.float32, device=U.device)
     tmp = torch.empty((2 * N, U.shape[1]), dtype=torch.float32, device=U.device)
+    if plan is not None:
+        check(lib().macr_lgcn_propagate_planned(plan._h, _i(rowptr), _i(col), _f(val), _f(U), U.shape[0],
+                                                _f(I), I.shape[0], U.shape[1], n_layers, _f(E), _f(tmp),
+                                                stream_ptr()), "macr_lgcn_propagate_planned")
+        return E
     check(lib().macr_lgcn_propagate(_i(rowptr), _i(col), _f(val), _f(U), U.shape[0], _f(I),
                                     I.shape[0], U.shape[1], n_layers, _f(E), _f(tmp), stream_ptr()),
           "macr_lgcn_propagate")

@@ -393,3 +393,42 @@ def test_lgcn_bce_trainer_steps_match_oracle(T, ops, oracle):
         np.testing.assert_allclose(g.cpu().numpy(), o, rtol=1e-4, atol=1e-5, err_msg=name)
     np.testing.assert_array_equal(t.w.cpu().numpy(), w)
     tr.close()
+
+
+def test_planned_spmm_with_hub_rows_matches_oracle(T, ops, oracle):
+    """macr_spmm_plan_* / *_planned: rows far longer than one 64-nonzero segment (a hub item
+    adjacent to every user) and empty rows; same results as the oracle up to the rounding of the
+    segment-wise summation, and identical between two calls (deterministic combine order)."""
+    import scipy.sparse as sp
+
+    n_users, n_items = 900, 300
+    rng = np.random.RandomState(3)
+    R = sp.random(n_users, n_items, density=0.02, random_state=rng, format="lil", dtype=np.float32)
+    R[:, 7] = 1.0          # hub: 900 nonzeros in one row of A
+    R[5, :] = 0.0          # a user with no interaction -> empty row
+    R = (R.tocsr() != 0).astype(np.float32)
+    A = sp.bmat([[None, R], [R.T, None]], format="csr", dtype=np.float32)
+    deg = np.asarray(A.sum(1)).ravel()
+    with np.errstate(divide="ignore"):
+        dinv = np.power(deg, -0.5)
+    dinv[np.isinf(dinv)] = 0
+    N = sp.diags(dinv).dot(A).dot(sp.diags(dinv)).tocsr().astype(np.float32)
+    N.sort_indices()
+    rowptr, col, val = N.indptr.astype(np.int32), N.indices.astype(np.int32), N.data.astype(np.float32)
+    assert np.diff(rowptr).max() >= 890 and np.diff(rowptr).min() == 0
+    U, I, _, _ = make_model(8, n_users, n_items, scale=3.0)
+    X = np.concatenate([U, I], 0)
+    d_rp, d_col, d_val = dev(T, rowptr), dev(T, col), dev(T, val)
+    plan = ops.SpmmPlan(d_rp)
+    want = oracle.spmm_csr(rowptr, col, val, X)
+    got = ops.spmm_csr(d_rp, d_col, d_val, dev(T, X), plan=plan)
+    np.testing.assert_allclose(got.cpu().numpy(), want, rtol=3e-6, atol=2e-7)
+    again = ops.spmm_csr(d_rp, d_col, d_val, dev(T, X), plan=plan)
+    assert T.equal(got, again)
+    plain = ops.spmm_csr(d_rp, d_col, d_val, dev(T, X))  # stateless kernel, CTA-cooperative hub
+    np.testing.assert_allclose(plain.cpu().numpy(), want, rtol=3e-6, atol=2e-7)
+    for L in (1, 2):
+        wantE = oracle.lgcn_propagate(rowptr, col, val, U, I, L)
+        gotE = ops.lgcn_propagate(d_rp, d_col, d_val, dev(T, U), dev(T, I), L, plan=plan)
+        np.testing.assert_allclose(gotE.cpu().numpy(), wantE, rtol=5e-6, atol=2e-7)
+    plan.close()

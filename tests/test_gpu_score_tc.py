@@ -42,6 +42,7 @@ def _gates(T, ops, U, I, w, wu):
     (300, 6000, 32, 0.0, 30, 10.0),     # K = 32, c = 0
     (257, 8790, 20, 40.0, 71, 10.0),    # ml_10m catalogue, dense train lists
     (200, 5000, 1, -3.0, 5, 10.0),      # K = 1, negative c
+    (1, 3000, 5, 40.0, 3, 10.0),        # a single query row
     (300, 6000, 20, 40.0, 0, 1.0),      # Xavier-scale tables (epoch-0 evaluation), no mask
 ])
 def test_tc_bit_exact_vs_oracle(T, ops, oracle, T_users, n_items, K, c, deg, scale):
