@@ -1,44 +1,46 @@
-// score_tc.cu -- K7+K8 on the 5th-generation tensor cores: TMA-fed tcgen05 (kind::f16, bf16 operands,
-// fp32 accumulation; kind::tf32 with -DMACR_TC_TF32) tiles with
-// the accumulator in TMEM and the counterfactual correction ((y - c) * sig_i) fused into the
-// TMEM->register epilogue, followed by an EXACT fp32 re-rank, so the emitted ids and scores are
+// score_tc.cu -- K7+K8 on the 5th-generation tensor cores: TMA-fed tcgen05 tiles (kind::f16, bf16
+// operands, fp32 accumulators in TMEM) whose accumulator IS the approximate counterfactual score
+// (y - c) * sig_i, followed by an EXACT fp32 re-rank, so the emitted ids and scores are
 // bit-identical to the fp32 path of score.cu (and to the CPU oracle).
 //   replaces sess.run(model.rubi_ratings_both, ...) + host top-K
 //   (macr_mf/train.py:249-251,89-104; macr_lightgcn/utility/batch_test.py:85-134; model.py:45,199).
 //
 // Why two tensor-core passes.  A running per-row top-K in the epilogue costs ~K(1+ln(n/K)) list
-// insertions per row, serialised across the 32 rows a warp owns: far more than the 4 instructions
-// per score of the pass itself.  Instead:
-//   pass MAX     per (row, batch of 32 items): max of the approximate score (2 instructions per
-//                score: the gate is folded into the item operand, see score_tc_kernel).
-//   threshold    m_K = K-th largest of 32 maxima over disjoint groups of batches that hold no
-//                train item of the row; thr[row] = m_K - (eps_max + eps_filter + slack).  K
+// insertions per row, serialised across the 32 rows a warp owns: far more than the pass itself
+// (half an instruction per score).  Instead:
+//   prep         items: bf16(sig_i * I_i) and the three bf16 pieces of -c*sig_i as an augmented K
+//                step (rows padded to whole tiles with -inf there); users: bf16(U), |u|.
+//   pass MAX     per (row, batch of 32 items): max of the approximate score.
+//   threshold    batches holding no train item of the row are dealt into 64 disjoint groups;
+//                m_K = K-th largest group maximum; thr = m_K - (eps_max + eps_filter + slack).  K
 //                distinct unmasked items score >= m_K, so the exact K-th best score is
 //                >= thr + eps_filter: every item of the true top-K passes the filter.
-//   pass FILTER  same tiles again; batches whose maximum reaches the threshold are scanned and
-//                items with score >= thr are appended to the row's candidate list (one atomic
-//                per append: ~1.3 K appends per row over the whole catalogue).
-//   re-rank      one warp per row: exact fp32 FMA-chain score of every candidate (the arithmetic
-//                of score.cu), sorted insert (score desc, lower id first) -> out.
-//   fallback     a row whose candidate list overflowed (degenerate score distributions) is
-//                re-done by the exact fp32 kernel (score.cu) -- never silently wrong.
+//   pass FILTER  same MMAs again; batches whose maximum reaches the threshold are scanned and the
+//                items with score >= thr appended to the row's candidate list (one atomic per
+//                append: ~1.3 K appends per row over the whole catalogue).
+//   re-rank      one warp per row: train items dropped (binary search in the row's sorted list),
+//                exact fp32 FMA-chain score of the rest (the arithmetic of score.cu), ranks by
+//                counting under the order (score desc, lower id first).
+//   fallback     a row whose candidate list overflowed (degenerate score distributions, users whose
+//                train list covers the catalogue) is re-done by the exact fp32 kernel (score.cu)
+//                -- never silently wrong.
 // eps_* are rigorous bounds of |approximate - exact| (see row_threshold_kernel).  Operands are
-// rounded once to bf16 (measured on B200: a 128x128 SS-mode MMA instruction takes ~124 cycles
-// whatever the kind, so bf16's K=16 per instruction halves the tensor time of tf32's K=8, and
-// it halves the TMA bytes); a looser bound only means more candidates, never a wrong id.
+// rounded once to bf16: measured on B200, a 128-row SS-mode MMA instruction takes the same time
+// for tf32 (K=8) and bf16 (K=16), so bf16 halves the tensor time and the TMA bytes; a looser
+// bound only means more candidates, never a wrong id.
 //
 // Kernel anatomy (one CTA per SM, persistent over (256-user tile, item chunk) work items):
-//   warp 0      TMA producer   cp.async.bulk.tensor.2d, 128B-swizzled K-major boxes of 128 B rows;
-//                              two 128-row user tiles stay resident, 256-item tiles stream through
-//                              a 4-stage ring (each item tile is read from L2 once per 256 users)
+//   warp 0      TMA producer   cp.async.bulk.tensor.2d: 128B-swizzled K-major boxes of 128-byte
+//                              rows, 32B-swizzled boxes for the augmented step; two 128-row user
+//                              tiles stay resident, 256-item tiles stream through a 4-stage ring
+//                              (each item tile is read from L2 once per 256 users)
 //   warp 1      MMA issuer     tcgen05.mma.cta_group::1.kind::f16, M=128 N=256 K=16, D in TMEM:
 //                              2 accumulators x 256 columns (one per user tile); the tensor pipe
 //                              works on one user tile while the other is drained; also owns
 //                              TMEM alloc/dealloc
 //   warps 2..9  epilogue       two warpgroups, warpgroup g owns user tile g and accumulator g:
-//                              tcgen05.ld.32x32b.x32 (thread = user row), fused correction,
-//                              batch maxima / threshold filter, train-item mask from a per-row
-//                              cursor into the sorted CSR mask
+//                              tcgen05.ld.32x32b.x64 (thread = user row), batch maxima (FMNMX3)
+//                              or threshold filter
 // mbarrier pipelines: user tiles full/empty, item stages full/empty, TMEM full/empty.
 #include <cuda.h>
 #include <math.h>
@@ -205,7 +207,7 @@ struct TileParams {
   int n_items;      // items in this shard
   int n_utiles;     // 256-row user tile pairs
   int n_itiles, n_chunks, tiles_per_chunk;
-  int id_off;       // global id of local item 0 (mask_col holds global ids)
+  int id_off;       // global id of local item 0 (candidates carry global ids)
   int ld_tm;        // row pitch of the batch maxima (floats), NB per item tile
   int dbg;          // developer timing experiments (0 = product path): bit0 skip the TMEM loads,
                     // bit1 skip the epilogue arithmetic, bit2 skip the MMAs (results are then
@@ -232,7 +234,8 @@ __device__ __forceinline__ float batch_max(const uint32_t (&v)[N]) {
 // maximum / compare, half an instruction per score, with no shared-memory traffic.
 //   MODE_MAX     bmax[row][NB*tile + b] = max over the 32 columns of batch b (masked items
 //                included; the threshold kernel leaves batches holding a train item of the row out)
-//   MODE_FILTER  batches with bmax >= thr.y are re-read; unmasked scores >= thr.x are appended
+//   MODE_FILTER  batches with bmax >= thr.y are scanned; scores >= thr.x are appended (train items
+//                included: the re-rank kernel drops them)
 // Pipeline per CTA: the MMA warp alternates between the two user tiles (A0 x B -> TMEM[0:256),
 // A1 x B -> TMEM[256:512)); while warpgroup 0 drains its accumulator the tensor pipe computes
 // warpgroup 1's, so with epilogue <= MMA time the tensor pipe never idles.
@@ -241,9 +244,7 @@ template <int MODE>
 __global__ void __launch_bounds__(kThreads, 1)
 score_tc_kernel(const __grid_constant__ CUtensorMap tmU, const __grid_constant__ CUtensorMap tmI,
                 const __grid_constant__ CUtensorMap tmUa, const __grid_constant__ CUtensorMap tmIa,
-                const TileParams P,
-                const int32_t *__restrict__ mask_rowptr, const int32_t *__restrict__ mask_col,
-                float *__restrict__ bmax, const float2 *__restrict__ thr,
+                const TileParams P, float *__restrict__ bmax, const float2 *__restrict__ thr,
                 uint2 *__restrict__ cand, int *__restrict__ cand_cnt,
                 long long *__restrict__ prof /* developer cycle counters of CTA 0, nullable */) {
   extern __shared__ unsigned char smem_raw[];
@@ -897,8 +898,8 @@ static long long *g_prof = nullptr;  // device int64[64]: cycle counters of CTA 
 
 template <int MODE>
 static int launch_pass(const CUtensorMap &mu, const CUtensorMap &mi, const CUtensorMap &mua,
-                       const CUtensorMap &mia, const TileParams &P, const int32_t *mrp, const int32_t *mcol, float *bmax,
-                       const float2 *thr, uint2 *cand, int *cnt, cudaStream_t s) {
+                       const CUtensorMap &mia, const TileParams &P, float *bmax, const float2 *thr,
+                       uint2 *cand, int *cnt, cudaStream_t s) {
   static bool opted = false;
   long long *prof = g_prof ? g_prof + 32 * MODE : nullptr;
   if (!opted) {
@@ -908,8 +909,8 @@ static int launch_pass(const CUtensorMap &mu, const CUtensorMap &mi, const CUten
   }
   const int n_work = P.n_utiles * P.n_chunks;
   const int grid = n_work < sm_count() ? n_work : sm_count();
-  score_tc_kernel<MODE><<<grid, kThreads, SMEM_BYTES, s>>>(mu, mi, mua, mia, P, mrp, mcol, bmax,
-                                                           thr, cand, cnt, prof);
+  score_tc_kernel<MODE><<<grid, kThreads, SMEM_BYTES, s>>>(mu, mi, mua, mia, P, bmax, thr, cand,
+                                                           cnt, prof);
   MACR_LAUNCH_CHECK();
   return MACR_OK;
 }
@@ -1008,8 +1009,7 @@ extern "C" int macr_score_topk_tc(const float *Uq, int T, const float *It, int64
     P.id_off = item_id_offset;
     P.ld_tm = p.ld_tm;
     P.dbg = g_dbg;
-    rc = launch_pass<MODE_MAX>(muh, mih, mua, mia, P, mrp, mask_col, tilemax, nullptr, nullptr,
-                               nullptr, s);
+    rc = launch_pass<MODE_MAX>(muh, mih, mua, mia, P, tilemax, nullptr, nullptr, nullptr, s);
     if (rc) return rc;
     const int n_batches = NB * p.n_itiles, bm_words = (n_batches + 31) / 32;
     row_threshold_kernel<<<(nb + 7) / 8, 256, (size_t)8 * bm_words * 4, s>>>(
@@ -1017,7 +1017,7 @@ extern "C" int macr_score_topk_tc(const float *Uq, int T, const float *It, int64
         misc, c, kappa_sum, bm_words, thr);
     MACR_LAUNCH_CHECK();
     MACR_CUDA(cudaMemsetAsync(cnt, 0, (size_t)nb * sizeof(int), s));
-    rc = launch_pass<MODE_FILTER>(muh, mih, mua, mia, P, mrp, mask_col, tilemax, thr, cand, cnt, s);
+    rc = launch_pass<MODE_FILTER>(muh, mih, mua, mia, P, tilemax, thr, cand, cnt, s);
     if (rc) return rc;
     MACR_CUDA(cudaMemsetAsync(fb_count, 0, sizeof(int), s));
     rerank_kernel<<<(nb + 7) / 8, 256, 0, s>>>(Ub, nb, It, sig_i, sig_u + t0, c, item_id_offset,
