@@ -106,7 +106,15 @@ void py_pick_users(MT &g, const int32_t *pop, int n, int B, int n_users_flag, in
   }
 }
 
+// membership in an ascending id list: short lists (the common case: tens of train items) are
+// scanned without branches (vectorisable), long ones binary-searched
 inline bool in_sorted(const int32_t *b, const int32_t *e, int32_t v) {
+  const long n = e - b;
+  if (n <= 64) {
+    int hit = 0;
+    for (long k = 0; k < n; ++k) hit |= (b[k] == v);
+    return hit != 0;
+  }
   return std::binary_search(b, e, v);
 }
 
@@ -131,9 +139,12 @@ extern "C" int macr_sample_mf(uint32_t *py_state /*[625]: 624 words + index*/,
     // the batch's users are known up front: pull their list heads into cache ahead of use
     if (i + 16 < B) __builtin_prefetch(rowptr + users[i + 16]);
     if (i + 8 < B) {
-      const int64_t l8 = rowptr[users[i + 8]];
-      __builtin_prefetch(order + l8);
-      __builtin_prefetch(sorted + l8);
+      const int64_t l8 = rowptr[users[i + 8]], h8 = rowptr[users[i + 8] + 1];
+      const int64_t e8 = h8 < l8 + 128 ? h8 : l8 + 128;  // up to 8 cache lines of each list
+      for (int64_t k = l8; k < e8; k += 16) {
+        __builtin_prefetch(order + k);
+        __builtin_prefetch(sorted + k);
+      }
     }
     const int32_t u = users[i];
     const int64_t lo = rowptr[u], hi = rowptr[u + 1];
@@ -172,8 +183,11 @@ extern "C" int macr_sample_lgcn(uint32_t *py_state /*[625]*/, uint32_t *np_state
       __builtin_prefetch(ban_rowptr + users[i + 16]);
     }
     if (i + 8 < B) {
-      __builtin_prefetch(pos_order + pos_rowptr[users[i + 8]]);
-      __builtin_prefetch(ban_sorted + ban_rowptr[users[i + 8]]);
+      const int32_t u8 = users[i + 8];
+      const int64_t pl = pos_rowptr[u8], ph = pos_rowptr[u8 + 1];
+      const int64_t bl = ban_rowptr[u8], bh = ban_rowptr[u8 + 1];
+      for (int64_t k = pl; k < (ph < pl + 128 ? ph : pl + 128); k += 16) __builtin_prefetch(pos_order + k);
+      for (int64_t k = bl; k < (bh < bl + 128 ? bh : bl + 128); k += 16) __builtin_prefetch(ban_sorted + k);
     }
     const int32_t u = users[i];
     const int64_t lo = pos_rowptr[u], hi = pos_rowptr[u + 1];
