@@ -65,6 +65,28 @@ def test_argument_validation_needs_no_gpu():
         _lib.check(rc, "macr_score_topk")
 
 
+def test_new_entry_points_validate_arguments_without_a_gpu():
+    from macr_b200 import _lib
+
+    lib = _lib.lib()
+    # tensor-core scoring: K outside [1,32], catalogue below 2048 items, misaligned workspace
+    rc = lib.macr_score_topk_tc(None, 4, None, 5000, 64, None, None, 0.0, None, None, 40, 0, None, None,
+                                None, 0, None, None)
+    assert rc == -1 and b"K" in lib.macr_last_error()
+    rc = lib.macr_score_topk_tc(None, 4, None, 100, 64, None, None, 0.0, None, None, 20, 0, None, None,
+                                None, 0, None, None)
+    assert rc == -1 and b"2048" in lib.macr_last_error()
+    assert lib.macr_score_topk_tc_workspace_bytes(0, 0, 20) > 0
+    # trainers / plans / samplers reject null handles and pointers
+    assert lib.macr_mf_trainer_set_mode(None, 1) == -1
+    assert lib.macr_lgcn_trainer_set_mode(None, 0) == -1
+    assert lib.macr_mf_trainer_run_host(None, None, 1, 1, None) == -1
+    assert lib.macr_spmm_plan_create(None, 10, None) == -1
+    assert lib.macr_spmm_plan_destroy(None) == 0
+    assert lib.macr_sample_mf(None, None, 0, 0, 0, None, None, None, 0, None, None, None) == -1
+    assert b"macr_sample_mf" in lib.macr_last_error()
+
+
 def test_product_never_imports_the_oracle():
     """oracle/ is test infrastructure: no module of the product package may reference it."""
     pkg = os.path.join(ROOT, "macr_b200")
