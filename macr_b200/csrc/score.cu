@@ -20,16 +20,34 @@ namespace macr {
 constexpr int kTU = 128, kTN = 128;
 constexpr int kMaxKFast = 32;
 
-__device__ __forceinline__ bool is_masked(const int32_t *__restrict__ mask_col, int lo, int hi,
-                                          int gid) {
-  while (lo < hi) {
+// Train-item cursor of one row: narrows [lo, hi) of the row's ascending train list until at most
+// 32 entries below `key` remain in front (the tile loop consumes those without marking).
+__device__ __forceinline__ int mask_seek(const int32_t *__restrict__ mask_col, int lo, int hi,
+                                         int key) {
+  while (hi - lo > 32) {
     const int mid = (lo + hi) >> 1;
-    const int v = mask_col[mid];
-    if (v == gid) return true;
-    if (v < gid) lo = mid + 1;
+    if (mask_col[mid] < key) lo = mid + 1;
     else hi = mid;
   }
-  return false;
+  return lo;
+}
+
+// Shape of a launch over the overflow queue of the tcgen05 path.  The host sizes the grid for all
+// T rows (the queue length lives on the device); the few rows actually queued re-divide the same
+// CTAs into more item chunks so the whole GPU works on them.  chunks * pitch never exceeds the
+// host's chunks_full * roundup(T, 128), which is what the partial-list workspace holds.
+struct QueueShape {
+  int rows, utiles, chunks, pitch;
+};
+__device__ __forceinline__ QueueShape queue_shape(int T, int chunks_full, long long itiles,
+                                                  const int *__restrict__ n_rows_dev) {
+  QueueShape q;
+  q.rows = min(T, *n_rows_dev);
+  q.utiles = (q.rows + kTU - 1) / kTU;
+  const long long ctas = (long long)((T + kTU - 1) / kTU) * chunks_full;
+  q.chunks = q.utiles ? (int)min(min(ctas / q.utiles, itiles), 64LL) : 0;
+  q.pitch = q.utiles * kTU;
+  return q;
 }
 
 struct ScoreSmem {
@@ -50,15 +68,24 @@ score_kernel(const float *__restrict__ Uq, int T, const float *__restrict__ It, 
              const int32_t *__restrict__ row_map, const int *__restrict__ n_rows_dev) {
   // row_map != nullptr: slot t of this launch is query row row_map[t], and only the first
   // *n_rows_dev slots exist (overflow queue of the tcgen05 path); outputs stay in slot order
-  const int Tpitch = T;  // partial lists keep the pitch of the full launch
-  if (row_map) T = min(T, *n_rows_dev);
-  if ((int)blockIdx.x * kTU >= T) return;
+  int Tpitch = T, ut_idx = blockIdx.x, chunk_idx = blockIdx.y;
+  if (row_map) {
+    const QueueShape q = queue_shape(T, gridDim.y, (n_items + kTN - 1) / kTN, n_rows_dev);
+    const int lin = blockIdx.y * gridDim.x + blockIdx.x;
+    if (lin >= q.utiles * q.chunks) return;
+    ut_idx = lin % q.utiles;
+    chunk_idx = lin / q.utiles;
+    T = q.rows;
+    Tpitch = q.pitch;
+    chunk_items = (((n_items + kTN - 1) / kTN + q.chunks - 1) / q.chunks) * kTN;
+  }
+  if (ut_idx * kTU >= T) return;
   extern __shared__ __align__(16) unsigned char smem_raw[];
   ScoreSmem &sm = *reinterpret_cast<ScoreSmem *>(smem_raw);
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int tx = tid & 15, ty = tid >> 4;
-  const int u0 = blockIdx.x * kTU;
-  const long long i_begin = (long long)blockIdx.y * chunk_items;
+  const int u0 = ut_idx * kTU;
+  const long long i_begin = (long long)chunk_idx * chunk_items;
   const long long i_end = min(n_items, i_begin + chunk_items);
 
   // stage the user tile once (transposing: consecutive threads -> consecutive rows)
@@ -91,6 +118,7 @@ score_kernel(const float *__restrict__ Uq, int T, const float *__restrict__ It, 
       const int tr = (row_map && t < T) ? row_map[t] : t;
       mlo[j] = (mask_rowptr && t < T) ? mask_rowptr[tr] : 0;
       mhi[j] = (mask_rowptr && t < T) ? mask_rowptr[tr + 1] : 0;
+      if (id_off + i_begin > 0) mlo[j] = mask_seek(mask_col, mlo[j], mhi[j], id_off + (int)i_begin);
     }
   }
 
@@ -165,6 +193,32 @@ score_kernel(const float *__restrict__ Uq, int T, const float *__restrict__ It, 
     if (!kTopK) continue;
     __syncthreads();
 
+    // ---- train items of this tile never compete: a well-trained model ranks exactly those on
+    // top, so they are struck out of the score tile (NaN compares false everywhere) before the
+    // fold instead of being looked up one candidate at a time.  mlo[j] is a cursor into row j's
+    // ascending train list; 32 entries per row are fetched at once, all 16 rows in flight.
+    if (mask_rowptr) {
+      const int tile_end = id_off + (int)min(it0 + kTN, i_end);  // first global id past the tile
+      int mv[16];
+#pragma unroll
+      for (int j = 0; j < 16; ++j)
+        mv[j] = (mlo[j] + lane < mhi[j]) ? mask_col[mlo[j] + lane] : 0x7fffffff;
+#pragma unroll
+      for (int j = 0; j < 16; ++j) {
+        int v = mv[j];
+        for (;;) {
+          const bool take = v < tile_end;
+          const int loc = v - id_off - (int)it0;
+          if (take && loc >= 0) sm.sS[warp * 16 + j][loc] = __int_as_float(0x7fc00000);
+          const int cnt = __popc(__ballot_sync(0xffffffffu, take));
+          mlo[j] += cnt;
+          if (cnt < 32) break;
+          v = (mlo[j] + lane < mhi[j]) ? mask_col[mlo[j] + lane] : 0x7fffffff;
+        }
+      }
+      __syncwarp();
+    }
+
     // ---- phase 2: each warp folds its 16 user rows into the register lists ------------------
 #pragma unroll
     for (int j = 0; j < 16; ++j) {
@@ -186,7 +240,6 @@ score_kernel(const float *__restrict__ Uq, int T, const float *__restrict__ It, 
           const float cs = __shfl_sync(0xffffffffu, s, src);
           const int cid = id_off + (int)(it0 + src + 32 * e);
           if (!score_better(cs, cid, ws, wi)) continue;
-          if (is_masked(mask_col, mlo[j], mhi[j], cid)) continue;
           score_list_insert(ls[j], li[j], cs, cid, lane, kmask, K);
           ws = __shfl_sync(0xffffffffu, ls[j], K - 1);
           wi = __shfl_sync(0xffffffffu, li[j], K - 1);
@@ -200,7 +253,7 @@ score_kernel(const float *__restrict__ Uq, int T, const float *__restrict__ It, 
     for (int j = 0; j < 16; ++j) {
       const int t = u0 + warp * 16 + j;
       if (t < T && lane < K) {
-        const long long o = ((long long)blockIdx.y * Tpitch + t) * K + lane;
+        const long long o = ((long long)chunk_idx * Tpitch + t) * K + lane;
         const bool empty = li[j] == 0x7fffffff;
         part_ids[o] = empty ? -1 : li[j];
         part_scores[o] = empty ? -INFINITY : ls[j];
@@ -213,10 +266,17 @@ score_kernel(const float *__restrict__ Uq, int T, const float *__restrict__ It, 
 __global__ void __launch_bounds__(256)
 topk_merge_kernel(const int32_t *__restrict__ ids, const float *__restrict__ scores, int T, int K,
                   int G, int32_t *__restrict__ out_ids, float *__restrict__ out_scores,
-                  const int32_t *__restrict__ row_map, const int *__restrict__ n_rows_dev) {
+                  const int32_t *__restrict__ row_map, const int *__restrict__ n_rows_dev,
+                  long long itiles) {
   const int lane = threadIdx.x & 31;
   const int t = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
-  if (t >= T || (row_map && t >= *n_rows_dev)) return;
+  if (row_map) {  // overflow queue: the lists were written in the queue's own shape
+    const QueueShape q = queue_shape(T, G, itiles, n_rows_dev);
+    if (t >= q.rows) return;
+    G = q.chunks;
+    T = q.pitch;
+  }
+  if (t >= T) return;
   const int to = row_map ? row_map[t] : t;  // output row
   const unsigned kmask = (K >= 32) ? 0xffffffffu : ((1u << K) - 1u);
   float ls = -INFINITY;
@@ -345,7 +405,8 @@ extern "C" int macr_gather_rows(const float *table, const int32_t *ids, int n, i
 extern "C" size_t macr_score_topk_workspace_bytes(int T, int64_t n_items, int K) {
   if (T <= 0 || n_items < 0 || K <= 0) return 16;
   const int chunks = pick_chunks(T, n_items);
-  return (size_t)chunks * T * K * (sizeof(int32_t) + sizeof(float)) + 256;
+  const size_t Tpad = ((size_t)T + kTU - 1) / kTU * kTU;  // the overflow-queue shape may use the pad
+  return (size_t)chunks * Tpad * K * (sizeof(int32_t) + sizeof(float)) + 256;
 }
 
 static int score_smem_opt_in() {
@@ -392,7 +453,7 @@ extern "C" int macr_score_topk(const float *Uq, int T, const float *It, int64_t 
                                                           nullptr, nullptr);
   MACR_LAUNCH_CHECK();
   topk_merge_kernel<<<(T + 7) / 8, 256, 0, s>>>(pids, psc, T, K, chunks, out_ids, out_scores,
-                                                nullptr, nullptr);
+                                                nullptr, nullptr, 0);
   MACR_LAUNCH_CHECK();
   return MACR_OK;
 }
@@ -416,16 +477,18 @@ int score_exact_rows(const float *Uq, int T, const float *It, long long n_items,
   const long long itiles = (n_items + kTN - 1) / kTN;
   const long long chunk_items = ((itiles + chunks - 1) / chunks) * kTN;
   int32_t *pids = reinterpret_cast<int32_t *>(ws);
-  float *psc = reinterpret_cast<float *>(pids + (size_t)chunks * T * K);
+  const size_t Tpad = ((size_t)T + kTU - 1) / kTU * kTU;
+  float *psc = reinterpret_cast<float *>(pids + (size_t)chunks * Tpad * K);
   dim3 grid((T + kTU - 1) / kTU, chunks);
-  // partial lists are indexed [chunk][slot][K] with the full-T pitch
+  // partial lists are indexed [chunk][slot][K]; with a row queue the pitch and the number of
+  // chunks are the queue's own (queue_shape), within chunks * Tpad lists
   score_kernel<true><<<grid, 256, sizeof(ScoreSmem), s>>>(Uq, T, It, n_items, sig_i, sig_u, c,
                                                           mask_rowptr, mask_col, K, id_off,
                                                           chunk_items, pids, psc, nullptr, row_map,
                                                           n_rows_dev);
   MACR_LAUNCH_CHECK();
   topk_merge_kernel<<<(T + 7) / 8, 256, 0, s>>>(pids, psc, T, K, chunks, out_ids, out_scores,
-                                                row_map, n_rows_dev);
+                                                row_map, n_rows_dev, itiles);
   MACR_LAUNCH_CHECK();
   return MACR_OK;
 }
@@ -459,7 +522,7 @@ extern "C" int macr_topk_merge(const int32_t *ids, const float *scores, int T, i
   if (T == 0) return MACR_OK;
   MACR_CHECK_ARG(ids && scores && out_ids && out_scores, "macr_topk_merge: null pointer");
   topk_merge_kernel<<<(T + 7) / 8, 256, 0, as_stream(stream)>>>(ids, scores, T, K, G, out_ids,
-                                                                out_scores, nullptr, nullptr);
+                                                                out_scores, nullptr, nullptr, 0);
   MACR_LAUNCH_CHECK();
   return MACR_OK;
 }

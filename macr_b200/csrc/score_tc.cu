@@ -67,7 +67,10 @@ constexpr int A_AUG_BYTES = BM * 32;
 constexpr int B_AUG_BYTES = BN * 32;
 constexpr int B_BYTES = B_TILE_BYTES + B_AUG_BYTES;  // one ring stage (40 KiB)
 constexpr int kCap = 128;            // candidate slots per row (4 x 32 lanes of the re-rank warp)
-constexpr int kThreads = 320;        // producer, MMA issuer, 2 epilogue warpgroups
+// 3 warpgroups: {TMA producer, MMA issuer, 2 idle warps} + 2 epilogue warpgroups.  The register
+// file is re-split with setmaxnreg once the roles part: 384 x 168 = 128 x 56 + 256 x 224.
+constexpr int kThreads = 384;
+constexpr int kCtrlRegs = 56, kEpiRegs = 224;
 constexpr int kTmemCols = 512;       // 2 accumulators (one per user tile) x 256 columns
 constexpr int UT = 2;                // user tiles per CTA (one per epilogue warpgroup)
 constexpr int STAGES = 4;            // item-tile ring (160 KiB)
@@ -240,11 +243,12 @@ __device__ __forceinline__ float batch_max(const uint32_t (&v)[N]) {
 // A1 x B -> TMEM[256:512)); while warpgroup 0 drains its accumulator the tensor pipe computes
 // warpgroup 1's, so with epilogue <= MMA time the tensor pipe never idles.
 // ---------------------------------------------------------------------------------------------
-template <int MODE>
+template <int MODE, bool MASKED>
 __global__ void __launch_bounds__(kThreads, 1)
 score_tc_kernel(const __grid_constant__ CUtensorMap tmU, const __grid_constant__ CUtensorMap tmI,
                 const __grid_constant__ CUtensorMap tmUa, const __grid_constant__ CUtensorMap tmIa,
-                const TileParams P, float *__restrict__ bmax, const float2 *__restrict__ thr,
+                const TileParams P, const int32_t *__restrict__ mask_rowptr,
+                const int32_t *__restrict__ mask_col, float *__restrict__ bmax, const float2 *__restrict__ thr,
                 uint2 *__restrict__ cand, int *__restrict__ cand_cnt,
                 long long *__restrict__ prof /* developer cycle counters of CTA 0, nullable */) {
   extern __shared__ unsigned char smem_raw[];
@@ -300,6 +304,8 @@ score_tc_kernel(const __grid_constant__ CUtensorMap tmU, const __grid_constant__
   };
   const long long t_start = profiling ? clock64() : 0;
 
+  if (warp < 4) {
+    asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(kCtrlRegs));
   if (warp == 0) {
     // =============================== TMA producer ===============================
     if (lane == 0) {
@@ -378,9 +384,11 @@ score_tc_kernel(const __grid_constant__ CUtensorMap tmU, const __grid_constant__
         prof[8] = clock64() - t_start, prof[9] = n;
       }
     }
+  }
   } else {
+    asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(kEpiRegs));
     // ===== epilogue: 2 warpgroups of 128 threads, warpgroup g owns user tile g of the pair =====
-    const int g = (warp - 2) >> 2;          // warpgroup
+    const int g = (warp - 4) >> 2;          // warpgroup
     const int q = warp & 3;                 // TMEM lane quarter this warp may read
     const int r_in = q * 32 + lane;         // row inside the user tile
     const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + g * BN;
@@ -393,9 +401,31 @@ score_tc_kernel(const __grid_constant__ CUtensorMap tmU, const __grid_constant__
       const bool valid = row < P.T;
       float2 th = make_float2(INFINITY, INFINITY);
       uint2 *my_cand = nullptr;
+      // MASKED: cursor into the row's sorted train-item list, positioned at the chunk's first
+      // item and advanced tile by tile (kAhead entries are kept in flight).  Rows the threshold
+      // kernel sent straight to the exact kernel (thr = +inf) append nothing and walk nothing.
+      constexpr int kAhead = 4;
+      int mptr = 0, mend = 0, nxt[kAhead];
+#pragma unroll
+      for (int d = 0; d < kAhead; ++d) nxt[d] = 0x7fffffff;
       if (MODE == MODE_FILTER && valid) {
         th = thr[row];
         my_cand = cand + (size_t)row * kCap;
+        if (MASKED && th.x < INFINITY) {
+          mptr = mask_rowptr[row];
+          mend = mask_rowptr[row + 1];
+          const int first = P.id_off + t_begin * BN;
+          int lo = mptr, hi = mend;
+          while (lo < hi) {
+            const int mid = (lo + hi) >> 1;
+            if (mask_col[mid] < first) lo = mid + 1;
+            else hi = mid;
+          }
+          mptr = lo;
+#pragma unroll
+          for (int d = 0; d < kAhead; ++d)
+            nxt[d] = mptr + d < mend ? mask_col[mptr + d] : 0x7fffffff;
+        }
       }
       // the filter pass prefetches its row's NB batch maxima of the coming tiles (an L2 round
       // trip is not short against a tile)
@@ -472,8 +502,29 @@ score_tc_kernel(const __grid_constant__ CUtensorMap tmU, const __grid_constant__
         } else {
           // Same 64-column load pipeline as the maxima pass.  A batch is looked at only if its
           // maximum reached the threshold for some row of the warp, and then only by the lanes
-          // concerned.  Train items are NOT filtered here (the re-rank kernel drops them): they
-          // only occupy candidate slots.  Padded columns score -inf.
+          // concerned.  MASKED: the row's train items of this tile are marked in 8 mask words
+          // (a well-trained model ranks exactly those items on top: unfiltered they would flood
+          // the candidate list); otherwise the re-rank kernel drops them.  Padded columns score
+          // -inf.
+          uint32_t mw[NB];
+#pragma unroll
+          for (int i = 0; i < NB; ++i) mw[i] = 0u;
+          if (MASKED) {
+            const int g0 = P.id_off + t * BN, g1 = g0 + BN;
+            while (nxt[0] < g1) {
+              const int b = nxt[0] - g0;
+              if (b >= 0) {
+                const uint32_t bit = 1u << (b & 31);
+                const int ws = b >> 5;
+#pragma unroll
+                for (int i = 0; i < NB; ++i) mw[i] |= ws == i ? bit : 0u;
+              }
+#pragma unroll
+              for (int d = 0; d + 1 < kAhead; ++d) nxt[d] = nxt[d + 1];
+              ++mptr;
+              nxt[kAhead - 1] = mptr + kAhead - 1 < mend ? mask_col[mptr + kAhead - 1] : 0x7fffffff;
+            }
+          }
           auto scan = [&](const uint32_t *v, int cb) {
             const bool need = bmv[cb] >= th.y;
             if (__any_sync(0xffffffffu, need)) {
@@ -489,7 +540,7 @@ score_tc_kernel(const __grid_constant__ CUtensorMap tmU, const __grid_constant__
                     const float ss[4] = {s0, s1, s2, s3};
 #pragma unroll
                     for (int e = 0; e < 4; ++e) {
-                      if (ss[e] >= th.x) {
+                      if (ss[e] >= th.x && !(MASKED && ((mw[cb] >> (4 * j4 + e)) & 1u))) {
                         // ~1.5 K appends per row over the whole catalogue: the atomic is rare
                         const int pos = atomicAdd(cand_cnt + row, 1);
                         if (pos < kCap)
@@ -628,7 +679,7 @@ row_threshold_kernel(const float *__restrict__ bmax, int T, int n_batches, int l
                      const int32_t *__restrict__ mask_rowptr, const int32_t *__restrict__ mask_col,
                      int id_off, int n_items, const float *__restrict__ unorm,
                      const unsigned int *__restrict__ inorm_max, float c, float kappa_sum,
-                     int bm_words, float2 *__restrict__ thr) {
+                     int bm_words, float2 *__restrict__ thr, int *__restrict__ cand_cnt) {
   extern __shared__ uint32_t s_bits[];  // [8 warps][bm_words]
   const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
   const int t = blockIdx.x * 8 + wib;
@@ -636,8 +687,10 @@ row_threshold_kernel(const float *__restrict__ bmax, int T, int n_batches, int l
   uint32_t *bits = s_bits + (size_t)wib * bm_words;
   for (int i = lane; i < bm_words; i += 32) bits[i] = 0u;
   __syncwarp();
+  int mask_len = 0;
   if (mask_rowptr) {
     const int lo = mask_rowptr[t], hi = mask_rowptr[t + 1];
+    mask_len = hi - lo;
     for (int e = lo + lane; e < hi; e += 32) {
       const int loc = mask_col[e] - id_off;
       if (loc >= 0 && loc < n_items) atomicOr(&bits[loc >> 10], 1u << ((loc >> 5) & 31));
@@ -674,8 +727,15 @@ row_threshold_kernel(const float *__restrict__ bmax, int T, int n_batches, int l
   const float mk = who0 ? __shfl_sync(0xffffffffu, m0, __ffs(who0) - 1)
                         : __shfl_sync(0xffffffffu, m1, __ffs(who1) - 1);
   if (lane == 0) {
-    float2 out = make_float2(-INFINITY, -INFINITY);
-    if (mk > -INFINITY) {
+    // Straight to the exact kernel (which strikes train items out tile by tile): rows without K
+    // unmasked groups -- no usable threshold, every item would be a candidate -- and rows whose
+    // train list is dense enough (> 1/16 of the catalogue) that walking it costs the filter
+    // pass more than the exact kernel costs the row.  +inf keeps the filter pass off the row;
+    // the over-full count makes the re-rank kernel queue it.
+    float2 out = make_float2(INFINITY, INFINITY);
+    if (!(mk > -INFINITY) || mask_len > (n_items >> 4) + 64) {
+      cand_cnt[t] = kCap + 1;
+    } else {
       const float yb = unorm[t] * __uint_as_float(*inorm_max);
       const float eps = kappa_sum * yb + 9.5367431640625e-7f /*2^-20*/ * (fabsf(c) + yb);
       out.x = mk - eps - 9.5367431640625e-7f * fabsf(mk);
@@ -896,21 +956,22 @@ static Plan make_plan(int T, long long n_items, int K) {
 static int g_dbg = 0;
 static long long *g_prof = nullptr;  // device int64[64]: cycle counters of CTA 0, per pass
 
-template <int MODE>
+template <int MODE, bool MASKED>
 static int launch_pass(const CUtensorMap &mu, const CUtensorMap &mi, const CUtensorMap &mua,
-                       const CUtensorMap &mia, const TileParams &P, float *bmax, const float2 *thr,
-                       uint2 *cand, int *cnt, cudaStream_t s) {
+                       const CUtensorMap &mia, const TileParams &P, const int32_t *mrp,
+                       const int32_t *mcol, float *bmax, const float2 *thr, uint2 *cand, int *cnt,
+                       cudaStream_t s) {
   static bool opted = false;
   long long *prof = g_prof ? g_prof + 32 * MODE : nullptr;
   if (!opted) {
-    MACR_CUDA(cudaFuncSetAttribute(score_tc_kernel<MODE>,
+    MACR_CUDA(cudaFuncSetAttribute(score_tc_kernel<MODE, MASKED>,
                                    cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
     opted = true;
   }
   const int n_work = P.n_utiles * P.n_chunks;
   const int grid = n_work < sm_count() ? n_work : sm_count();
-  score_tc_kernel<MODE><<<grid, kThreads, SMEM_BYTES, s>>>(mu, mi, mua, mia, P, bmax, thr, cand,
-                                                           cnt, prof);
+  score_tc_kernel<MODE, MASKED><<<grid, kThreads, SMEM_BYTES, s>>>(mu, mi, mua, mia, P, mrp, mcol,
+                                                                   bmax, thr, cand, cnt, prof);
   MACR_LAUNCH_CHECK();
   return MACR_OK;
 }
@@ -1009,15 +1070,20 @@ extern "C" int macr_score_topk_tc(const float *Uq, int T, const float *It, int64
     P.id_off = item_id_offset;
     P.ld_tm = p.ld_tm;
     P.dbg = g_dbg;
-    rc = launch_pass<MODE_MAX>(muh, mih, mua, mia, P, tilemax, nullptr, nullptr, nullptr, s);
+    rc = launch_pass<MODE_MAX, false>(muh, mih, mua, mia, P, nullptr, nullptr, tilemax, nullptr,
+                                      nullptr, nullptr, s);
     if (rc) return rc;
     const int n_batches = NB * p.n_itiles, bm_words = (n_batches + 31) / 32;
+    MACR_CUDA(cudaMemsetAsync(cnt, 0, (size_t)nb * sizeof(int), s));
     row_threshold_kernel<<<(nb + 7) / 8, 256, (size_t)8 * bm_words * 4, s>>>(
         tilemax, nb, n_batches, p.ld_tm, K, mrp, mask_col, item_id_offset, (int)n_items, unorm,
-        misc, c, kappa_sum, bm_words, thr);
+        misc, c, kappa_sum, bm_words, thr, cnt);
     MACR_LAUNCH_CHECK();
-    MACR_CUDA(cudaMemsetAsync(cnt, 0, (size_t)nb * sizeof(int), s));
-    rc = launch_pass<MODE_FILTER>(muh, mih, mua, mia, P, tilemax, thr, cand, cnt, s);
+    // train items are filtered inside the pass whenever a mask is given (see the kernel comment)
+    rc = mrp ? launch_pass<MODE_FILTER, true>(muh, mih, mua, mia, P, mrp, mask_col, tilemax, thr,
+                                              cand, cnt, s)
+             : launch_pass<MODE_FILTER, false>(muh, mih, mua, mia, P, nullptr, nullptr, tilemax, thr,
+                                               cand, cnt, s);
     if (rc) return rc;
     MACR_CUDA(cudaMemsetAsync(fb_count, 0, sizeof(int), s));
     rerank_kernel<<<(nb + 7) / 8, 256, 0, s>>>(Ub, nb, It, sig_i, sig_u + t0, c, item_id_offset,
