@@ -16,14 +16,15 @@
 //                distinct unmasked items score >= m_K, so the exact K-th best score is
 //                >= thr + eps_filter: every item of the true top-K passes the filter.
 //   pass FILTER  same MMAs again; batches whose maximum reaches the threshold are scanned and the
-//                items with score >= thr appended to the row's candidate list (one atomic per
-//                append: ~1.3 K appends per row over the whole catalogue).
-//   re-rank      one warp per row: train items dropped (binary search in the row's sorted list),
-//                exact fp32 FMA-chain score of the rest (the arithmetic of score.cu), ranks by
-//                counting under the order (score desc, lower id first).
-//   fallback     a row whose candidate list overflowed (degenerate score distributions, users whose
-//                train list covers the catalogue) is re-done by the exact fp32 kernel (score.cu)
-//                -- never silently wrong.
+//                items with score >= thr that are not train items of the row (a trained model
+//                ranks exactly those on top: a per-row cursor into the sorted train list marks
+//                them tile by tile) appended to the row's candidate list (one atomic per append).
+//   re-rank      one warp per row: exact fp32 FMA-chain score of the candidates (the arithmetic
+//                of score.cu; train items re-checked by binary search), ranks by counting under
+//                the order (score desc, lower id first).
+//   fallback     a row whose candidate list overflowed (degenerate score distributions), a row
+//                without K unmasked groups, or a row whose train list exceeds 1/16 of the
+//                catalogue is done by the exact fp32 kernel (score.cu) -- never silently wrong.
 // eps_* are rigorous bounds of |approximate - exact| (see row_threshold_kernel).  Operands are
 // rounded once to bf16: measured on B200, a 128-row SS-mode MMA instruction takes the same time
 // for tf32 (K=8) and bf16 (K=16), so bf16 halves the tensor time and the TMA bytes; a looser
@@ -38,10 +39,12 @@
 //                              2 accumulators x 256 columns (one per user tile); the tensor pipe
 //                              works on one user tile while the other is drained; also owns
 //                              TMEM alloc/dealloc
-//   warps 2..9  epilogue       two warpgroups, warpgroup g owns user tile g and accumulator g:
+//   warps 2..3  idle           (complete the control warpgroup; they only give up registers)
+//   warps 4..11 epilogue       two warpgroups, warpgroup g owns user tile g and accumulator g:
 //                              tcgen05.ld.32x32b.x64 (thread = user row), batch maxima (FMNMX3)
 //                              or threshold filter
 // mbarrier pipelines: user tiles full/empty, item stages full/empty, TMEM full/empty.
+// setmaxnreg re-splits the register file once the roles part (control 56, epilogue 224).
 #include <cuda.h>
 #include <math.h>
 
