@@ -177,9 +177,15 @@ int macr_mf_trainer_run_host(macr_mf_trainer *h, const int32_t *batches_host, in
 /* Which `--train` graph the trainer steps (default MACR_TRAIN_RUBIBCEBOTH, the MACR hot path).
  * MACR_TRAIN_NORMALBCE is the README's baseline command (README.md:30, model.py:277-287,:100):
  * element-wise BCE on (y_pos, y_neg) with "+1e-9", same L2 term, TF Adam on the two embedding
- * tables only (w, w_user are not part of that graph).  Call before the first step of a run. */
+ * tables only (w, w_user are not part of that graph).
+ * MACR_TRAIN_RUBIBCE is `--train rubibce` (model.py:158-183, :83-85; LightGCN `--loss bce1`,
+ * LightGCN.py:431-461, :190-194): the item gate only -- grid P[i,j] = y_pos[j]*sig(s_pos[i]),
+ * mf = L_ori + alpha*L_item, TF Adam on the two tables and w; w_user and its slots are never
+ * written.  losses[] keep their layout (loss, mf, reg|emb, L_ori).
+ * Call before the first step of a run. */
 #define MACR_TRAIN_RUBIBCEBOTH 0
 #define MACR_TRAIN_NORMALBCE 1
+#define MACR_TRAIN_RUBIBCE 2
 int macr_mf_trainer_set_mode(macr_mf_trainer *h, int mode);
 /* number of this library's kernels launched by one step (for bench gpu_launches) */
 int macr_mf_trainer_launches_per_step(const macr_mf_trainer *h);
@@ -242,7 +248,8 @@ int macr_lgcn_trainer_run(macr_lgcn_trainer *h, const int32_t *batches, int n_st
 /* host-memory variant of macr_lgcn_trainer_run, see macr_mf_trainer_run_host */
 int macr_lgcn_trainer_run_host(macr_lgcn_trainer *h, const int32_t *batches_host, int n_steps,
                                int B, int train, float *losses_host);
-/* MACR_TRAIN_RUBIBCEBOTH = `--loss bceboth` (default), MACR_TRAIN_NORMALBCE = `--loss bce`
+/* MACR_TRAIN_RUBIBCEBOTH = `--loss bceboth` (default), MACR_TRAIN_RUBIBCE = `--loss bce1`,
+ * MACR_TRAIN_NORMALBCE = `--loss bce`
  * (README.md:59, LightGCN.py:415-429,:186); see macr_mf_trainer_set_mode */
 int macr_lgcn_trainer_set_mode(macr_lgcn_trainer *h, int mode);
 /* propagated tables of the current parameters (device, owned by the handle):

@@ -60,9 +60,10 @@ def main(argv=None, tune=False):
     computed once per parameter version, so a sweep costs one scoring pass per c."""
     args = flags.parse_lgcn_args(argv)
     logging.getLogger().setLevel(logging.INFO)
-    if args.alg_type != "lightgcn" or args.loss not in ("bceboth", "bce"):
-        raise SystemExit(f"--alg_type {args.alg_type} --loss {args.loss}: only lightgcn with bceboth (MACR) or bce "
-                         "(the README's baseline) is implemented on the B200 path (DESIGN.md section 8)")
+    if args.alg_type != "lightgcn" or args.loss not in ("bceboth", "bce", "bce1"):
+        raise SystemExit(f"--alg_type {args.alg_type} --loss {args.loss}: only lightgcn with bceboth (MACR), bce1 "
+                         "(item gate only) or bce (the README's baseline) is implemented on the B200 path "
+                         "(DESIGN.md section 8)")
     data_generator = Data(path=args.data_path + args.dataset, batch_size=args.batch_size, args=args)
     seed = 12345  # LightGCN.py:651-655
     random.seed(seed)
@@ -104,6 +105,10 @@ def main(argv=None, tune=False):
     if args.loss == "bce":  # LightGCN.py:592-593,625-626
         train_fetch = [model.opt_bce, model.loss_bce, model.mf_loss_bce, model.emb_loss_bce, model.reg_loss_bce]
         test_fetch = [model.loss_bce, model.mf_loss_bce, model.emb_loss_bce]
+    elif args.loss == "bce1":  # LightGCN.py:594-595,627-628
+        train_fetch = [model.opt_two_bce1, model.loss_two_bce1, model.mf_loss_two_bce1, model.emb_loss_two_bce1,
+                       model.reg_loss_two_bce1]
+        test_fetch = [model.loss_two_bce1, model.mf_loss_two_bce1, model.emb_loss_two_bce1]
     else:
         train_fetch = [model.opt_two_bce_both, model.loss_two_bce_both, model.mf_loss_two_bce_both,
                        model.emb_loss_two_bce_both, model.reg_loss_two_bce_both]
@@ -182,7 +187,7 @@ def main(argv=None, tune=False):
                     ", ".join("%.5f" % r for r in ret["ndcg"]))
                 print(perf_str, end="")
                 logging.info(perf_str)
-        elif args.test == "rubiboth" and tune:
+        elif args.test in ("rubiboth", "rubi1") and tune:
             print("Epoch %d" % epoch)
             best = None
             for c in np.linspace(args.start, args.end, args.step):
@@ -199,7 +204,7 @@ def main(argv=None, tune=False):
                 config.update(best_c_hr=ret["hr"][0], best_c_epoch=epoch, best_c=best[0])
             print(perf_str, end="")
             logging.info(perf_str)
-        elif args.test == "rubiboth":
+        elif args.test in ("rubiboth", "rubi1"):  # LightGCN.py:848
             print("Epoch %d" % epoch)
             c = args.c
             model.update_c(sess, c)
@@ -211,7 +216,7 @@ def main(argv=None, tune=False):
             print(perf_str, end="")
             logging.info(perf_str)
         else:
-            raise SystemExit(f"--test {args.test}: only rubiboth / normal are implemented")
+            raise SystemExit(f"--test {args.test}: only rubiboth / rubi1 / normal are implemented")
 
         cur_best_pre_0, stopping_step, should_stop = early_stopping(
             ret["hr"][0], cur_best_pre_0, stopping_step, expected_order="acc", flag_step=10)

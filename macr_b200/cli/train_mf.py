@@ -42,9 +42,9 @@ def main(argv=None, tune=False):
     keeps the c with the best HR@Ks[0]."""
     args = flags.parse_mf_args(argv)
     logging.getLogger().setLevel(logging.INFO)
-    if args.train not in ("rubibceboth", "normalbce"):
-        raise SystemExit(f"--train {args.train}: rubibceboth (MACR) and normalbce (the README's baseline) "
-                         "are implemented on the B200 path (DESIGN.md section 8)")
+    if args.train not in ("rubibceboth", "normalbce", "rubibce"):
+        raise SystemExit(f"--train {args.train}: rubibceboth (MACR), rubibce (item gate only) and normalbce "
+                         "(the README's baseline) are implemented on the B200 path (DESIGN.md section 8)")
     if args.model != "mf":
         raise SystemExit(f"--model {args.model}: only mf is on the MACR hot path")
     data = Data(args)
@@ -58,9 +58,13 @@ def main(argv=None, tune=False):
     model = BPRMF(args, config)
     print("MF model.")
     model.set_train_mode(args.train)
-    opt_fetches = ([model.opt_two_bce_both, model.loss_two_bce_both, model.mf_loss_two_bce_both,
-                    model.reg_loss_two_bce_both] if args.train == "rubibceboth" else
-                   [model.opt_bce, model.loss_bce, model.mf_loss_bce, model.reg_loss_bce])  # train.py:487-496
+    opt_fetches = {  # train.py:482-496
+        "rubibceboth": [model.opt_two_bce_both, model.loss_two_bce_both, model.mf_loss_two_bce_both,
+                        model.reg_loss_two_bce_both],
+        "rubibce": [model.opt_two_bce, model.loss_two_bce, model.mf_loss_two_bce, model.reg_loss_two_bce],
+        "normalbce": [model.opt_bce, model.loss_bce, model.mf_loss_bce, model.reg_loss_bce]}[args.train]
+    # `--test rubi` ranks with the head of the trained graph (train.py:548-556)
+    rubi_type = "rubi_both" if args.train == "rubibceboth" else "rubi_c"
     sess = Session()
     sess.run(global_variables_initializer())
     evaluator = MFEvaluator(data, Ks, args.batch_size, eval_mode=args.eval_mode)
@@ -118,7 +122,7 @@ def main(argv=None, tune=False):
             best = None
             for c in np.linspace(args.start, args.end, args.step):
                 model.update_c(sess, c)
-                r = evaluator.test(sess, model, users_to_test, model_type="rubi_both", valid_set=args.valid_set)
+                r = evaluator.test(sess, model, users_to_test, model_type=rubi_type, valid_set=args.valid_set)
                 t3 = time()
                 if args.verbose > 0:
                     perf_str = ("c:%.2f [%.1fs + %.1fs]: train==[%.8f=%.8f + %.8f], recall=[%.5f, %.5f], "
@@ -138,7 +142,7 @@ def main(argv=None, tune=False):
             print("Epoch %d" % epoch)
             c = args.c
             model.update_c(sess, c)
-            ret = evaluator.test(sess, model, users_to_test, model_type="rubi_both", valid_set=args.valid_set)
+            ret = evaluator.test(sess, model, users_to_test, model_type=rubi_type, valid_set=args.valid_set)
             head = "c:%.2f" % c
         elif args.test == "normal":
             ret = evaluator.test(sess, model, users_to_test, model_type="o", valid_set=args.valid_set)

@@ -47,6 +47,7 @@ __device__ __forceinline__ const int32_t *step_ids(const StepState *st, const in
 
 struct GateOut {
   float *gA, *gAN, *gG, *litem, *luser;
+  int item_only;
 };
 __device__ __forceinline__ void gate_values(float sp, float sn, float su, float &a, float &an,
                                             float &g, float &litem, float &luser);
@@ -109,6 +110,7 @@ gather_dots_kernel(const float *__restrict__ Ue, const float *__restrict__ Ie,
     if (gates.gA) {  // gates + branch losses for the B x B grid (computed once per position)
       float a, an, g, li, lu;
       gate_values(a2, a3, a4, a, an, g, li, lu);
+      if (gates.item_only) g = 1.0f, lu = 0.0f;  // no user branch in this graph
       gates.gA[b] = a;
       gates.gAN[b] = an;
       gates.gG[b] = g;
@@ -125,7 +127,9 @@ int launch_gather_dots(const float *Ue, const float *Ie, const float *Ur, const 
                        const GridWs *gates, cudaStream_t s) {
   const int wpb = 8;
   GateOut go{};
-  if (gates) go = GateOut{gates->gA, gates->gAN, gates->gG, gates->litem, gates->luser};
+  if (gates)
+    go = GateOut{gates->gA, gates->gAN, gates->gG, gates->litem, gates->luser,
+                 gates->item_gate_only};
   gather_dots_kernel<<<(B + wpb - 1) / wpb, wpb * 32, 0, s>>>(
       Ue, Ie, Ur, Ir, w, wu, u, p, n, st, B, yp, yn, sp, sn, su, regsq, snap, go);
   MACR_LAUNCH_CHECK();
@@ -551,6 +555,7 @@ GridWs grid_ws_layout(int B, void *base) {
   w.gA = w.luser + w.Bpad;
   w.gAN = w.gA + w.Bpad;
   w.gG = w.gAN + w.Bpad;
+  w.item_gate_only = 0;
   w.part_bytes = (2 * band_r + 2 * band_c + lp) * sizeof(float);  // rowP..losspart: armed slots
   w.bytes = (2 * band_r + 2 * band_c + lp + 5 * (size_t)w.Bpad) * sizeof(float);
   return w;
@@ -1092,6 +1097,10 @@ __device__ void step_tail_body(float *w, float *mw, float *vw, float *wu, float 
   constexpr int GR = NT / (2 * kD);  // partial groups per vector
   const int tid = threadIdx.x;
   const float lr_t = step_lr_t(st, hp.lr);
+  // bit 0: training step; bits 1..2: vectors without a gradient in this graph (minimize() skips
+  // them: neither the variable nor its slots are written)
+  const int frozen = train >> 1;
+  train &= 1;
   if (train) {
     const int k = tid & 63, which = (tid >> 6) & 1, grp = tid / (2 * kD);
     const float *src = which ? gwu_part : gw_part;
@@ -1100,7 +1109,7 @@ __device__ void step_tail_body(float *w, float *mw, float *vw, float *wu, float 
     shg[which * GR + grp][k] = a;
   }
   __syncthreads();
-  if (train && tid < 2 * kD) {
+  if (train && tid < 2 * kD && !((frozen >> (tid >> 6)) & 1)) {
     const int k = tid & 63, which = tid >> 6;
     float g = 0.f;
 #pragma unroll
@@ -1332,7 +1341,8 @@ row_grads_kernel(const float *__restrict__ snap, const float *__restrict__ w,
   __syncthreads();
   if (!sLast) return;
   step_tail_body<kRowWarps * 32>(tail.w, tail.mw, tail.vw, tail.wu, tail.mwu, tail.vwu, gw_part,
-                                 gwu_part, gridDim.x - pos_ctas, tail.hp, tail.st, 1, sTailG);
+                                 gwu_part, gridDim.x - pos_ctas, tail.hp, tail.st,
+                                 1 | (tail.frozen << 1), sTailG);
 }
 
 int row_grads_max_parts(int B) { return (B + kWgradPerCta - 1) / kWgradPerCta; }

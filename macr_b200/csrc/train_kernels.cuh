@@ -28,6 +28,8 @@ struct GridWs {  // carve-up of the grid kernel's partial-sum workspace
   float *losspart;     // [nblk_i*nblk_j]
   float *litem, *luser;  // [Bpad] branch losses per position (model.py:213,215)
   float *gA, *gAN, *gG;  // [Bpad] sig(sp), sig(sn), sig(su)
+  int item_gate_only;    // `--train rubibce` / `--loss bce1` (model.py:158-183): gather_dots writes
+                         // gG = 1, luser = 0, so the grid is yp_j*sig(sp_i), L_user and d_su vanish
   size_t part_bytes;     // leading bytes of the workspace that must be 0xff before the first launch
   size_t bytes;
 };
@@ -92,6 +94,7 @@ struct TailArgs {
   macr_hparams hp;
   StepState *st;
   unsigned *ticket;
+  int frozen;  // bit 0: w, bit 1: w_user receive no gradient in this graph -> left untouched
 };
 // summed gradient rows of the unique touched rows (MF: + L2 term, + Adam on those rows) and
 // per-CTA partials of grad(w), grad(w_user); rows come from the gather_dots snapshot

@@ -177,7 +177,8 @@ static int mf_enqueue(macr_mf_trainer *h, int B) {
   float *yp = h->sc(0, B), *yn = h->sc(1, B), *sp = h->sc(2, B), *sn = h->sc(3, B),
         *su = h->sc(4, B), *rq = h->sc(5, B), *dyp = h->sc(6, B), *dyn = h->sc(7, B),
         *dsp = h->sc(8, B), *dsn = h->sc(9, B), *dsu = h->sc(10, B);
-  const GridWs g = grid_ws_layout(B, h->gridws);
+  GridWs g = grid_ws_layout(B, h->gridws);
+  g.item_gate_only = h->mode == MACR_TRAIN_RUBIBCE;
   int rc;
   // fork: the plan (2 CTAs) and the dense sweep need only the ids and the step state
   MACR_CUDA(cudaEventRecord(h->ev_fork, s));
@@ -207,7 +208,10 @@ static int mf_enqueue(macr_mf_trainer *h, int B) {
   const float lam = hp.decay / (float)hp.batch_size_flag;
   const AdamTabs tabs{h->U, h->mU, h->vU, h->I, h->mI, h->vI, h->bmU, h->bmI,
                       hp.beta1, hp.beta2, hp.eps, hp.lr, h->st};
-  const TailArgs tail{1, h->w, h->mw, h->vw, h->wu, h->mwu, h->vwu, hp, h->st, h->tail_ticket};
+  // vectors outside the mode's graph get no gradient: TF's minimize() leaves them and their slots
+  const int frozen = h->mode == MACR_TRAIN_NORMALBCE ? 3 : h->mode == MACR_TRAIN_RUBIBCE ? 2 : 0;
+  const TailArgs tail{1, h->w, h->mw, h->vw, h->wu, h->mwu, h->vwu, hp, h->st, h->tail_ticket,
+                      frozen};
   rc = launch_row_grads(h->snap, h->w, h->wu, B, dyp, dyn, dsp, dsn, dsu, lam, h->planU, h->planI,
                         h->gU, h->gI, h->unit_part, h->gw_part, h->gwu_part, nullptr, &tabs, &tail, s);
   if (rc) return rc;
@@ -399,7 +403,8 @@ extern "C" int macr_mf_trainer_run(macr_mf_trainer *h, const int32_t *batches, i
 
 extern "C" int macr_mf_trainer_set_mode(macr_mf_trainer *h, int mode) {
   MACR_CHECK_ARG(h, "macr_mf_trainer_set_mode: null handle");
-  MACR_CHECK_ARG(mode == MACR_TRAIN_RUBIBCEBOTH || mode == MACR_TRAIN_NORMALBCE,
+  MACR_CHECK_ARG(mode == MACR_TRAIN_RUBIBCEBOTH || mode == MACR_TRAIN_NORMALBCE ||
+                     mode == MACR_TRAIN_RUBIBCE,
                  "macr_mf_trainer_set_mode: unknown mode %d", mode);
   if (mode != h->mode) {  // the captured step graphs belong to the old mode
     cudaStreamSynchronize(h->s);
@@ -455,7 +460,8 @@ static int lgcn_enqueue_impl(macr_lgcn_trainer *h, int B, int train) {
   float *yp = h->sc(0, B), *yn = h->sc(1, B), *sp = h->sc(2, B), *sn = h->sc(3, B),
         *su = h->sc(4, B), *rq = h->sc(5, B), *dyp = h->sc(6, B), *dyn = h->sc(7, B),
         *dsp = h->sc(8, B), *dsn = h->sc(9, B), *dsu = h->sc(10, B);
-  const GridWs g = grid_ws_layout(B, h->gridws);
+  GridWs g = grid_ws_layout(B, h->gridws);
+  g.item_gate_only = h->mode == MACR_TRAIN_RUBIBCE;  // `--loss bce1`, LightGCN.py:431-461
   const float *Ue = h->Emean, *Ie = h->Emean + h->nu * kD;
   int rc, launches = 0;
   if (train) {
@@ -516,8 +522,9 @@ static int lgcn_enqueue_impl(macr_lgcn_trainer *h, int B, int train) {
                            hp.beta1, hp.beta2, hp.eps, s);
     if (rc) return rc;
     launches += 3;
+    const int frozen = h->mode == MACR_TRAIN_NORMALBCE ? 3 : h->mode == MACR_TRAIN_RUBIBCE ? 2 : 0;
     rc = launch_step_tail(h->w, h->mw, h->vw, h->wu, h->mwu, h->vwu, h->gw_part, h->gwu_part,
-                          n_part, hp, h->st, 1, s);
+                          n_part, hp, h->st, 1 | (frozen << 1), s);
     if (rc) return rc;
   } else {
     rc = launch_step_tail(h->w, h->mw, h->vw, h->wu, h->mwu, h->vwu, h->gw_part, h->gwu_part, 0,
@@ -649,7 +656,8 @@ extern "C" int macr_lgcn_trainer_run_host(macr_lgcn_trainer *h, const int32_t *b
 
 extern "C" int macr_lgcn_trainer_set_mode(macr_lgcn_trainer *h, int mode) {
   MACR_CHECK_ARG(h, "macr_lgcn_trainer_set_mode: null handle");
-  MACR_CHECK_ARG(mode == MACR_TRAIN_RUBIBCEBOTH || mode == MACR_TRAIN_NORMALBCE,
+  MACR_CHECK_ARG(mode == MACR_TRAIN_RUBIBCEBOTH || mode == MACR_TRAIN_NORMALBCE ||
+                     mode == MACR_TRAIN_RUBIBCE,
                  "macr_lgcn_trainer_set_mode: unknown mode %d", mode);
   if (mode != h->mode) {
     cudaStreamSynchronize(h->s);

@@ -20,7 +20,10 @@ from .. import ops
 from .data_mf import lists_to_csr
 
 _FETCH_OF = {"rubi_both": "rubi_ratings_both", "rubiboth": "rubi_ratings_both", "o": "batch_ratings",
-             "normal": "batch_ratings"}
+             "normal": "batch_ratings",
+             "rubi_c": "rubi_ratings",    # MF `--train rubibce --test rubi` (train.py:241,551)
+             "rubi1": "rubi_ratings1"}    # LightGCN `--test rubi1` (batch_test.py:66-74)
+_HEAD_OF = {"rubi_ratings_both": "both", "rubi_ratings": "item", "rubi_ratings1": "item", "batch_ratings": "plain"}
 
 
 def _batches(seq, size):
@@ -72,14 +75,11 @@ class MFEvaluator:
         truth_of = self.data.test_user_list if valid_set == "test" else self.data.valid_user_list
         sums = {k: np.zeros(len(self.Ks)) for k in ("precision", "recall", "ndcg", "hit_ratio")}
         n_test_users, count = len(test_users), 0
-        gated = _FETCH_OF[model_type] == "rubi_ratings_both"
+        head = _HEAD_OF[_FETCH_OF[model_type]]
         for user_batch in _batches(test_users, self.batch_size):
             mrp, mcol = self.data.train_csr(user_batch)  # all_items - train_items, train.py:132-133
             if self.eval_mode == "fused":
-                if gated:
-                    ids, _ = model.topk(user_batch, Kmax, mrp, mcol)
-                else:
-                    ids, _ = _plain_topk(model, user_batch, Kmax, mrp, mcol)
+                ids, _ = model.topk(user_batch, Kmax, mrp, mcol, head=head)
                 ids = ids.cpu().numpy()
             else:  # literal: fetch the matrix, mask, rank on the host (heapq.nlargest order)
                 rate = sess.run(getattr(model, _FETCH_OF[model_type]),
@@ -92,17 +92,6 @@ class MFEvaluator:
             count += len(user_batch)
         assert count == n_test_users  # train.py:309
         return {k: v / n_test_users for k, v in sums.items()}
-
-
-def _plain_topk(model, users, K, mrp, mcol):
-    """top-K of batch_ratings (no gates): same fused kernel with sig = 1, c = 0."""
-    Ut, It, _w, _wu = model._score_tables()
-    with torch.cuda.device(model.dev):
-        Uq = ops.gather_rows(Ut, model._ids(users))
-        si = torch.ones(It.shape[0], dtype=torch.float32, device=model.dev)
-        su = torch.ones(Uq.shape[0], dtype=torch.float32, device=model.dev)
-        mc = model._ids(mcol) if len(mcol) else torch.zeros(1, dtype=torch.int32, device=model.dev)
-        return ops.score_topk(Uq, It, si, su, 0.0, model._ids(mrp), mc, K)
 
 
 def host_topk(rate, mask_rowptr, mask_col, K):
@@ -131,17 +120,14 @@ class LGCNEvaluator:
             raise NotImplementedError(f"method {method!r} is outside the MACR hot path")
         top_show = np.sort(model.Ks)
         max_top = int(max(top_show))
-        gated = _FETCH_OF[method] == "rubi_ratings_both"
+        head = _HEAD_OF[_FETCH_OF[method]]
         all_result, count = [], 0
         for user_batch in _batches(users_to_test, self.batch_size):
             mrp, mcol = self.data.train_csr(user_batch) if train_set_flag == 0 else \
                 (np.zeros(len(user_batch) + 1, np.int32), np.zeros(0, np.int32))
             trp, tcol = self.data.truth_csr(user_batch)
             if self.eval_mode == "fused":
-                if gated:
-                    ids, _ = model.topk(user_batch, max_top, mrp, mcol)
-                else:
-                    ids, _ = _plain_topk(model, user_batch, max_top, mrp, mcol)
+                ids, _ = model.topk(user_batch, max_top, mrp, mcol, head=head)
                 with torch.cuda.device(model.dev):
                     res = ops.foldout_metrics(ids, model._ids(trp), model._ids(tcol)).cpu().numpy()
             else:

@@ -9,7 +9,10 @@ Fetching
    (None, loss, mf_loss, emb_loss, [0.])                       (reg_loss is a constant, :530)
   [loss_two_bce_both, mf_loss_two_bce_both, emb_loss_two_bce_both] -> the same losses without an
    update (train_thread_test, LightGCN.py:616-647)
-  rubi_ratings_both / batch_ratings -> score matrix on the propagated tables (:166,509)
+  [opt_bce, ...] (`--loss bce`, :183-186,415-429) and [opt_two_bce1, ...] (`--loss bce1`: item gate
+   only, :190-194,431-461) step the neighbouring loss graphs with the same kernels
+  rubi_ratings_both / rubi_ratings1 / batch_ratings -> score matrix on the propagated tables
+   (:166,442,509)
 """
 import ast
 
@@ -24,10 +27,11 @@ _TRAIN = ("opt_two_bce_both", "loss_two_bce_both", "mf_loss_two_bce_both", "emb_
           "reg_loss_two_bce_both")
 # `--loss bce` (README.md:59, the baseline): LightGCN.py:183-186,415-429
 _TRAIN_BCE = ("opt_bce", "loss_bce", "mf_loss_bce", "emb_loss_bce", "reg_loss_bce")
+# `--loss bce1` (item gate only): LightGCN.py:190-194,431-461
+_TRAIN_BCE1 = ("opt_two_bce1", "loss_two_bce1", "mf_loss_two_bce1", "emb_loss_two_bce1", "reg_loss_two_bce1")
 _UNSUPPORTED = (
-    "opt", "loss", "mf_loss", "emb_loss", "reg_loss", "opt_two_bce1", "loss_two_bce1", "mf_loss_two_bce1",
-    "emb_loss_two_bce1", "reg_loss_two_bce1", "opt_two_bce2", "loss_two_bce2", "mf_loss_two_bce2",
-    "emb_loss_two_bce2", "reg_loss_two_bce2", "rubi_ratings1", "rubi_ratings2",
+    "opt", "loss", "mf_loss", "emb_loss", "reg_loss", "opt_two_bce2", "loss_two_bce2", "mf_loss_two_bce2",
+    "emb_loss_two_bce2", "reg_loss_two_bce2", "rubi_ratings2",
     "batch_ratings_causal_c", "direct_minus_ratings_both",
 )
 
@@ -71,17 +75,18 @@ class LightGCN(_ScoringMixin):
                                        max_batch=min(max(self.batch_size, 1), 8192), device=self.dev)
         for name in ("users", "pos_items", "neg_items", "node_dropout", "mess_dropout"):
             setattr(self, name, Placeholder(self, name))
-        for name in _TRAIN + _TRAIN_BCE + ("rubi_ratings_both", "batch_ratings"):
+        for name in _TRAIN + _TRAIN_BCE + _TRAIN_BCE1 + ("rubi_ratings_both", "rubi_ratings1", "batch_ratings"):
             setattr(self, name, Fetch(self, name))
         for name in _UNSUPPORTED:
             setattr(self, name, Unsupported(self, name))
 
     def _run(self, names, feeds):
-        if any(n in _TRAIN or n in _TRAIN_BCE for n in names):
-            normal = any(n in _TRAIN_BCE for n in names)
-            if normal and any(n in _TRAIN for n in names):
+        if any(n in _TRAIN or n in _TRAIN_BCE or n in _TRAIN_BCE1 for n in names):
+            modes = [m for m, group in ((ops.LGCNTrainer.RUBIBCEBOTH, _TRAIN), (ops.LGCNTrainer.NORMALBCE, _TRAIN_BCE),
+                                        (ops.LGCNTrainer.RUBIBCE, _TRAIN_BCE1)) if any(n in group for n in names)]
+            if len(modes) != 1:
                 raise NotImplementedError("fetches of two different loss graphs in one sess.run")
-            mode = ops.LGCNTrainer.NORMALBCE if normal else ops.LGCNTrainer.RUBIBCEBOTH
+            mode = modes[0]
             if getattr(self, "_mode", ops.LGCNTrainer.RUBIBCEBOTH) != mode:
                 self.trainer.set_mode(mode)
                 self._mode = mode
@@ -91,7 +96,8 @@ class LightGCN(_ScoringMixin):
             val = {"opt_two_bce_both": None, "loss_two_bce_both": loss, "mf_loss_two_bce_both": mf,
                    "emb_loss_two_bce_both": emb, "reg_loss_two_bce_both": zero,
                    "opt_bce": None, "loss_bce": loss, "mf_loss_bce": mf, "emb_loss_bce": emb,
-                   "reg_loss_bce": zero}
+                   "reg_loss_bce": zero, "opt_two_bce1": None, "loss_two_bce1": loss, "mf_loss_two_bce1": mf,
+                   "emb_loss_two_bce1": emb, "reg_loss_two_bce1": zero}
             return [val[n] for n in names]
         return [self._run_scores(n, feeds) for n in names]
 

@@ -9,7 +9,10 @@ in HBM) behind `ops.MFTrainer`.  Fetching
            TF-faithful Adam), returns (None, loss, mf_loss, reg_loss)      model.py:72-74,185-222
   [opt_bce, loss_bce, mf_loss_bce, reg_loss_bce]
         -> one `--train normalbce` step (element-wise BCE, the README's baseline)  model.py:99-101,277-287
+  [opt_two_bce, loss_two_bce, mf_loss_two_bce, reg_loss_two_bce]
+        -> one `--train rubibce` step (item gate only; w_user untouched)           model.py:83-85,158-183
   rubi_ratings_both  -> ((u.i) - c) * sig(i.w) * sig(u.w_user)  as float32 [B_u, I]  model.py:199
+  rubi_ratings       -> ((u.i) - c) * sig(i.w)   (`--train rubibce --test rubi`)      model.py:141
   batch_ratings      -> u.i                                                            model.py:45
 
 Everything else in the reference graph (other --train modes, baselines) is an `Unsupported`
@@ -25,11 +28,15 @@ from .session import Fetch, Placeholder, Unsupported
 _TRAIN = ("opt_two_bce_both", "loss_two_bce_both", "mf_loss_two_bce_both", "reg_loss_two_bce_both")
 # `--train normalbce` (README.md:30, the baseline the MACR rows are compared with): model.py:99-101
 _TRAIN_BCE = ("opt_bce", "loss_bce", "mf_loss_bce", "reg_loss_bce")
+# `--train rubibce` (item gate only): model.py:83-85,158-183
+_TRAIN_ITEM = ("opt_two_bce", "loss_two_bce", "mf_loss_two_bce", "reg_loss_two_bce")
+# score fetch -> head of the fused kernel: which gates multiply (y - c)
+_HEAD_OF = {"rubi_ratings_both": "both", "rubi_ratings": "item", "rubi_ratings1": "item", "batch_ratings": "plain"}
 _UNSUPPORTED = (
     "opt", "loss", "mf_loss", "reg_loss", "opt_two", "loss_two", "mf_loss_two", "reg_loss_two",
-    "opt_two_bce", "loss_two_bce", "mf_loss_two_bce", "reg_loss_two_bce", "opt2", "loss2", "opt2_bce", "loss2_bce", "opt3", "opt3_bce",
+    "opt2", "loss2", "opt2_bce", "loss2_bce", "opt3", "opt3_bce",
     "opt_userc_bce", "loss_userc_bce", "user_const_ratings", "item_const_ratings",
-    "user_rand_ratings", "item_rand_ratings", "rubi_ratings", "rubi_ratings_userc",
+    "user_rand_ratings", "item_rand_ratings", "rubi_ratings_userc",
     "direct_minus_ratings", "direct_minus_ratings_both", "rubi_ratings_both_poptest",
 )
 
@@ -68,33 +75,42 @@ class _ScoringMixin:
     def _ids(self, seq):
         return torch.as_tensor(np.ascontiguousarray(np.asarray(seq, dtype=np.int32))).to(self.dev)
 
-    def score_matrix(self, users, items=None, c=None, gated=True):
-        """rubi_ratings_both (gated) or batch_ratings (plain) as a device tensor [B_u, n]."""
+    def _gates(self, Uq, Iq, w, wu, head, c):
+        """(sig_i, sig_u, c) of a score head: "both" = rubi_ratings_both (model.py:199), "item" =
+        rubi_ratings / rubi_ratings1 (model.py:141, LightGCN.py:442; x * 1.0 is exact, so the user
+        gate is a vector of ones), "plain" = batch_ratings (((y - 0) * 1) * 1 == y exactly)."""
+        ones = lambda n: torch.ones(n, dtype=torch.float32, device=self.dev)
+        if head == "plain":
+            return ones(Iq.shape[0]), ones(Uq.shape[0]), 0.0
+        cc = self.rubi_c if c is None else float(c)
+        if head == "item":
+            return ops.score_gates(Iq, w), ones(Uq.shape[0]), cc
+        if head != "both":
+            raise ValueError(f"unknown score head {head!r}")
+        return ops.score_gates(Iq, w), ops.score_gates(Uq, wu), cc
+
+    def score_matrix(self, users, items=None, c=None, gated=True, head=None):
+        """A score head (`head`; `gated` is the older both/plain switch) as a device tensor [B_u, n]."""
+        head = head or ("both" if gated else "plain")
         Ut, It, w, wu = self._score_tables()
         with torch.cuda.device(self.dev):
             Uq = ops.gather_rows(Ut, self._ids(users))
             Iq = It if items is None else ops.gather_rows(It, self._ids(items))
-            if gated:
-                si, su = ops.score_gates(Iq, w), ops.score_gates(Uq, wu)
-                cc = self.rubi_c if c is None else float(c)
-            else:
-                si = torch.ones(Iq.shape[0], dtype=torch.float32, device=self.dev)
-                su = torch.ones(Uq.shape[0], dtype=torch.float32, device=self.dev)
-                cc = 0.0  # ((y - 0) * 1) * 1 == y exactly
+            si, su, cc = self._gates(Uq, Iq, w, wu, head, c)
             return ops.score_matrix(Uq, Iq, si, su, cc)
 
-    def topk(self, users, K, mask_rowptr=None, mask_col=None, c=None):
+    def topk(self, users, K, mask_rowptr=None, mask_col=None, c=None, head="both"):
         """Fused score + mask + top-K over the whole catalogue -> (ids [T,K], scores [T,K])
         device tensors; masked = CSR over `users` of item ids to exclude (their train items)."""
         Ut, It, w, wu = self._score_tables()
         with torch.cuda.device(self.dev):
             Uq = ops.gather_rows(Ut, self._ids(users))
-            si, su = ops.score_gates(It, w), ops.score_gates(Uq, wu)
+            si, su, cc = self._gates(Uq, It, w, wu, head, c)
             mrp = None if mask_rowptr is None else self._ids(mask_rowptr)
             mcol = None if mask_col is None else self._ids(mask_col)
             if mcol is not None and mcol.numel() == 0:
                 mcol = torch.zeros(1, dtype=torch.int32, device=self.dev)
-            return ops.score_topk(Uq, It, si, su, self.rubi_c if c is None else float(c), mrp, mcol, K)
+            return ops.score_topk(Uq, It, si, su, cc, mrp, mcol, K)
 
     def _is_full_range(self, items):
         n = self.n_items
@@ -106,7 +122,7 @@ class _ScoringMixin:
     def _run_scores(self, name, feeds):
         users, items = feeds["users"], feeds["pos_items"]
         sub = None if self._is_full_range(items) else items
-        M = self.score_matrix(users, sub, gated=(name == "rubi_ratings_both"))
+        M = self.score_matrix(users, sub, head=_HEAD_OF[name])
         return M.cpu().numpy()
 
 
@@ -129,7 +145,7 @@ class BPRMF(_ScoringMixin):
                                      device=self.dev)
         for name in ("users", "pos_items", "neg_items"):
             setattr(self, name, Placeholder(self, name))
-        for name in _TRAIN + _TRAIN_BCE + ("rubi_ratings_both", "batch_ratings"):
+        for name in _TRAIN + _TRAIN_BCE + _TRAIN_ITEM + ("rubi_ratings_both", "rubi_ratings", "batch_ratings"):
             setattr(self, name, Fetch(self, name))
         for name in _UNSUPPORTED:
             setattr(self, name, Unsupported(self, name))
@@ -140,23 +156,26 @@ class BPRMF(_ScoringMixin):
     # ---- session dispatch -----------------------------------------------------------------
     def _run(self, names, feeds):
         if any(n.startswith("opt") for n in names):
-            normal = any(n in _TRAIN_BCE for n in names)
-            if normal and any(n in _TRAIN for n in names):
+            graphs = [g for g, group in (("rubibceboth", _TRAIN), ("normalbce", _TRAIN_BCE), ("rubibce", _TRAIN_ITEM))
+                      if any(n in group for n in names)]
+            if len(graphs) != 1:
                 raise NotImplementedError("one optimizer op per sess.run")
-            self.set_train_mode("normalbce" if normal else "rubibceboth")
+            self.set_train_mode(graphs[0])
             loss, mf, reg = self.train_step(feeds["users"], feeds["pos_items"], feeds["neg_items"])
             val = {"opt_two_bce_both": None, "loss_two_bce_both": loss, "mf_loss_two_bce_both": mf,
                    "reg_loss_two_bce_both": reg, "opt_bce": None, "loss_bce": loss, "mf_loss_bce": mf,
-                   "reg_loss_bce": reg}
+                   "reg_loss_bce": reg, "opt_two_bce": None, "loss_two_bce": loss, "mf_loss_two_bce": mf,
+                   "reg_loss_two_bce": reg}
             return [val[n] for n in names]
-        if any(n in _TRAIN or n in _TRAIN_BCE for n in names):
+        if any(n in _TRAIN or n in _TRAIN_BCE or n in _TRAIN_ITEM for n in names):
             raise NotImplementedError("loss fetches without the optimizer op are not used by "
                                       "macr_mf/train.py and are not implemented for MF")
         return [self._run_scores(n, feeds) for n in names]
 
     def set_train_mode(self, train):
-        """which optimizer op steps run: "rubibceboth" (default) or "normalbce"."""
-        mode = {"rubibceboth": ops.MFTrainer.RUBIBCEBOTH, "normalbce": ops.MFTrainer.NORMALBCE}[train]
+        """which optimizer op steps run: "rubibceboth" (default), "normalbce" or "rubibce"."""
+        mode = {"rubibceboth": ops.MFTrainer.RUBIBCEBOTH, "normalbce": ops.MFTrainer.NORMALBCE,
+                "rubibce": ops.MFTrainer.RUBIBCE}[train]
         if getattr(self, "_mode", ops.MFTrainer.RUBIBCEBOTH) != mode:
             self.trainer.set_mode(mode)
             self._mode = mode

@@ -266,10 +266,11 @@ class _Tables:
 class MFTrainer:
     """Handle around macr_mf_trainer_* (one `--train rubibceboth` model)."""
 
-    RUBIBCEBOTH, NORMALBCE = 0, 1
+    RUBIBCEBOTH, NORMALBCE, RUBIBCE = 0, 1, 2
 
     def set_mode(self, mode):
-        """RUBIBCEBOTH (default) or NORMALBCE (`--train normalbce`, the README's baseline)."""
+        """RUBIBCEBOTH (default), NORMALBCE (`--train normalbce`, the README's baseline) or
+        RUBIBCE (`--train rubibce`: item gate only, w_user untouched)."""
         check(lib().macr_mf_trainer_set_mode(self._h, int(mode)), "macr_mf_trainer_set_mode")
 
     def _run_host(self, n, B, ids_ptr, loss_ptr):
@@ -371,10 +372,11 @@ class MFTrainer:
 class LGCNTrainer:
     """Handle around macr_lgcn_trainer_* (one `--loss bceboth` LightGCN model)."""
 
-    RUBIBCEBOTH, NORMALBCE = 0, 1
+    RUBIBCEBOTH, NORMALBCE, RUBIBCE = 0, 1, 2
 
     def set_mode(self, mode):
-        """RUBIBCEBOTH (`--loss bceboth`, default) or NORMALBCE (`--loss bce`, the baseline)."""
+        """RUBIBCEBOTH (`--loss bceboth`, default), NORMALBCE (`--loss bce`, the baseline) or
+        RUBIBCE (`--loss bce1`: item gate only)."""
         check(lib().macr_lgcn_trainer_set_mode(self._h, int(mode)), "macr_lgcn_trainer_set_mode")
 
     def _run_host(self, n, B, ids_ptr, loss_ptr, train=True):

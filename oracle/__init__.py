@@ -21,10 +21,13 @@ from .capi import (  # noqa: F401
     adam_lr_t,
     mf_step,
     mf_step_normal,
+    mf_step_item,
+    grid_bce_item,
     spmm_csr,
     lgcn_propagate,
     lgcn_step,
     lgcn_step_normal,
+    lgcn_step_item,
     score_gates,
     score_matrix,
     score_topk,

@@ -162,6 +162,32 @@ def mf_step_normal(st, u, p, n, hp):
     return losses
 
 
+def mf_step_item(st, u, p, n, hp):
+    """One `--train rubibce` step (model.py:158-183: item gate only) on MFState `st` (in place)."""
+    u, p, n = _ids(u), _ids(p), _ids(n)
+    if st.t == 0:
+        st.pw[:] = (hp.beta1, hp.beta2)
+    losses = np.empty(4, np.float32)
+    lib().oracle_mf_step_item(_f(st.U), _f(st.mU), _f(st.vU), C.c_int64(st.U.shape[0]), _f(st.I),
+                              _f(st.mI), _f(st.vI), C.c_int64(st.I.shape[0]), _f(st.w), _f(st.mw),
+                              _f(st.vw), _f(st.wu), C.c_int(st.U.shape[1]), _i(u), _i(p), _i(n),
+                              C.c_int(len(u)), C.byref(hp), _f(st.pw), _f(losses))
+    st.t += 1
+    return losses
+
+
+def grid_bce_item(yp, yn, sp, sn, alpha, want_grad=True):
+    """model.py:172-177 grid + item branch; returns (losses3, d_yp, d_yn, d_sp, d_sn)."""
+    B = len(yp)
+    c = lambda a: np.ascontiguousarray(a, dtype=np.float32)
+    yp, yn, sp, sn = c(yp), c(yn), c(sp), c(sn)
+    l3 = np.zeros(3, np.float32)
+    outs = [np.zeros(B, np.float32) for _ in range(4)]
+    lib().oracle_grid_bce_item(_f(yp), _f(yn), _f(sp), _f(sn), C.c_int(B), C.c_float(alpha), _f(l3),
+                               *( [_f(o) for o in outs] if want_grad else [None] * 4))
+    return (l3, *outs)
+
+
 def spmm_csr(rowptr, col, val, X):
     n, d = X.shape
     Y = np.empty_like(X)
@@ -206,6 +232,23 @@ def lgcn_step_normal(st, rowptr, col, val, n_layers, u, p, n, hp, train=True):
                                   C.c_int(st.U.shape[1]), C.c_int(n_layers), _i(u), _i(p), _i(n),
                                   C.c_int(len(u)), C.c_int(1 if train else 0), C.byref(hp),
                                   _f(st.pw), _f(losses))
+    if train:
+        st.t += 1
+    return losses
+
+
+def lgcn_step_item(st, rowptr, col, val, n_layers, u, p, n, hp, train=True):
+    """One `--loss bce1` LightGCN step (LightGCN.py:431-461) on MFState `st` (in place)."""
+    u, p, n = _ids(u), _ids(p), _ids(n)
+    if st.t == 0:
+        st.pw[:] = (hp.beta1, hp.beta2)
+    losses = np.empty(4, np.float32)
+    lib().oracle_lgcn_step_item(_i(rowptr), _i(col), _f(val), _f(st.U), _f(st.mU), _f(st.vU),
+                                C.c_int64(st.U.shape[0]), _f(st.I), _f(st.mI), _f(st.vI),
+                                C.c_int64(st.I.shape[0]), _f(st.w), _f(st.mw), _f(st.vw),
+                                _f(st.wu), C.c_int(st.U.shape[1]), C.c_int(n_layers), _i(u), _i(p),
+                                _i(n), C.c_int(len(u)), C.c_int(1 if train else 0), C.byref(hp),
+                                _f(st.pw), _f(losses))
     if train:
         st.t += 1
     return losses

@@ -47,6 +47,32 @@ def bce_plain(users, pos_items, neg_items, decay, batch_size):
     return mf_loss, decay * regularizer                                                   # :286
 
 
+def bce_two_branch(users, pos_items, neg_items, w, alpha, decay, batch_size, reg_rows=None):
+    """macr_mf/model.py:158-183 (create_bce_loss_two_brach, `--train rubibce`; LightGCN.py:431-461
+    `--loss bce1` is the same with the L2 term on the raw rows)."""
+    pos_scores = torch.sum(users * pos_items, dim=1)                      # :159
+    neg_scores = torch.sum(users * neg_items, dim=1)                      # :160
+    pos_item_scores = pos_items @ w                                       # :166  [B,1]
+    neg_item_scores = neg_items @ w                                       # :167
+    pos_scores = pos_scores * torch.sigmoid(pos_item_scores)              # :172  [B]*[B,1] -> [B,B]
+    neg_scores = neg_scores * torch.sigmoid(neg_item_scores)              # :173
+    mf_loss_ori = torch.mean(-torch.log(torch.sigmoid(pos_scores) + 1e-10)
+                             - torch.log(1 - torch.sigmoid(neg_scores) + 1e-10))          # :174
+    mf_loss_item = torch.mean(-torch.log(torch.sigmoid(pos_item_scores) + 1e-10)
+                              - torch.log(1 - torch.sigmoid(neg_item_scores) + 1e-10))    # :176
+    mf_loss = mf_loss_ori + alpha * mf_loss_item                                          # :178
+    l2 = lambda x: torch.sum(x * x) / 2
+    ru, rp, rn = reg_rows if reg_rows is not None else (users, pos_items, neg_items)      # LightGCN: raw rows
+    regularizer = (l2(ru) + l2(rp) + l2(rn)) / batch_size                                 # :180-181
+    return mf_loss, decay * regularizer, mf_loss_ori, mf_loss_item
+
+
+def rubi_ratings(user_rows, item_rows, w, c):
+    """macr_mf/model.py:45,141: (batch_ratings - rubi_c) * squeeze(sigmoid(items@w))  (`rubi_c` head)."""
+    batch_ratings = user_rows @ item_rows.t()
+    return (batch_ratings - c) * torch.sigmoid(item_rows @ w).squeeze(-1)
+
+
 def rubi_ratings_both(user_rows, item_rows, w, w_user, c):
     """macr_mf/model.py:45,199: (batch_ratings - rubi_c) * sigmoid(items@w)^T * sigmoid(users@w_user)."""
     batch_ratings = user_rows @ item_rows.t()

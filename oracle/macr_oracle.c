@@ -73,15 +73,19 @@ void oracle_gather_dots(const float *Ue, const float *Ie, const float *Ur, const
 
 /* ---- model.py:204-217: the [B]*[B,1] broadcast grid, its three means, and the gradient
  *      of  L_ori + alpha*L_item + beta*L_user  w.r.t. the five [B] vectors ---- */
-void oracle_grid_bce(const float *yp, const float *yn, const float *sp, const float *sn,
-                     const float *su, int B, float alpha, float beta, float *losses3,
-                     float *d_yp, float *d_yn, float *d_sp, float *d_sn, float *d_su) {
+/* item_only != 0: `--train rubibce` / `--loss bce1` (model.py:158-183; LightGCN.py:431-461): the
+ * grid is pos_scores*sigmoid(pos_item_scores) only -- no user branch in the product, no L_user,
+ * nothing flows to user_scores / w_user */
+static void grid_bce_impl(const float *yp, const float *yn, const float *sp, const float *sn,
+                          const float *su, int B, float alpha, float beta, float *losses3,
+                          float *d_yp, float *d_yn, float *d_sp, float *d_sn, float *d_su,
+                          int item_only) {
   float *a = (float *)malloc(sizeof(float) * B * 3);
   float *an = a + B, *g = a + 2 * B;
   for (int i = 0; i < B; ++i) {
     a[i] = sigmoidf_(sp[i]);  /* tf.nn.sigmoid(self.pos_item_scores) */
     an[i] = sigmoidf_(sn[i]); /* tf.nn.sigmoid(self.neg_item_scores) */
-    g[i] = sigmoidf_(su[i]);  /* tf.nn.sigmoid(self.user_scores)     */
+    g[i] = item_only ? 1.0f : sigmoidf_(su[i]); /* tf.nn.sigmoid(self.user_scores) */
   }
   double *colP = (double *)calloc((size_t)B * 2, sizeof(double));
   double *colN = colP + B;
@@ -102,8 +106,8 @@ void oracle_grid_bce(const float *yp, const float *yn, const float *sp, const fl
       for (int j = 0; j < B; ++j) {
         /* model.py:204  pos_scores*sigmoid(pos_item_scores)*sigmoid(user_scores),
          * evaluated left to right: ([B]*[B,1])*[B,1] -> element [i,j] */
-        const float P = (yp[j] * ai) * gi;
-        const float N = (yn[j] * ani) * gi;
+        const float P = item_only ? yp[j] * ai : (yp[j] * ai) * gi; /* model.py:172 */
+        const float N = item_only ? yn[j] * ani : (yn[j] * ani) * gi;
         const float s = sigmoidf_(P);
         const float t = sigmoidf_(N);
         const float sp_e = s + kEps;          /* sigmoid(pos)+1e-10   */
@@ -135,7 +139,7 @@ void oracle_grid_bce(const float *yp, const float *yn, const float *sp, const fl
     const float ea = a[i] + kEps, ean = (1.0f - an[i]) + kEps;
     const float eg = g[i] + kEps, eg1 = (1.0f - g[i]) + kEps;
     l_item += (double)(-logf(ea)) + (double)(-logf(ean)); /* model.py:213 */
-    l_user += (double)(-logf(eg)) + (double)(-logf(eg1)); /* model.py:215 */
+    if (!item_only) l_user += (double)(-logf(eg)) + (double)(-logf(eg1)); /* model.py:215 */
     if (want_grad) {
       d_yp[i] = (float)(colP[i] * invBB);
       d_yn[i] = (float)(colN[i] * invBB);
@@ -145,7 +149,7 @@ void oracle_grid_bce(const float *yp, const float *yn, const float *sp, const fl
                   (double)beta * invB * (-1.0 / eg + 1.0 / eg1);
       d_sp[i] = (float)(da * ((double)a[i] * (1.0f - a[i])));
       d_sn[i] = (float)(dan * ((double)an[i] * (1.0f - an[i])));
-      d_su[i] = (float)(dg * ((double)g[i] * (1.0f - g[i])));
+      d_su[i] = item_only ? 0.0f : (float)(dg * ((double)g[i] * (1.0f - g[i])));
     }
   }
   losses3[0] = (float)(loss_sum * invBB);
@@ -154,6 +158,21 @@ void oracle_grid_bce(const float *yp, const float *yn, const float *sp, const fl
   free(a);
   free(colP);
   free(rowP);
+}
+
+void oracle_grid_bce(const float *yp, const float *yn, const float *sp, const float *sn,
+                     const float *su, int B, float alpha, float beta, float *losses3,
+                     float *d_yp, float *d_yn, float *d_sp, float *d_sn, float *d_su) {
+  grid_bce_impl(yp, yn, sp, sn, su, B, alpha, beta, losses3, d_yp, d_yn, d_sp, d_sn, d_su, 0);
+}
+
+void oracle_grid_bce_item(const float *yp, const float *yn, const float *sp, const float *sn,
+                          int B, float alpha, float *losses3, float *d_yp, float *d_yn,
+                          float *d_sp, float *d_sn) {
+  float *dsu = (float *)malloc(sizeof(float) * (size_t)B);
+  grid_bce_impl(yp, yn, sp, sn, sp /*unused*/, B, alpha, 0.0f, losses3, d_yp, d_yn, d_sp, d_sn, dsu,
+                1);
+  free(dsu);
 }
 
 /* ---- TF-1.14 adam.py: lr_t = lr * sqrt(1 - beta2_power) / (1 - beta1_power), fp32 ---- */
@@ -266,19 +285,20 @@ static void batch_losses(const float *losses3, const float *regsq, int B,
   losses[3] = losses3[0];
 }
 
-void oracle_mf_step(float *U, float *mU, float *vU, int64_t n_users, float *I, float *mI,
-                    float *vI, int64_t n_items, float *w, float *mw, float *vw, float *wu,
-                    float *mwu, float *vwu, int d, const int32_t *u, const int32_t *p,
-                    const int32_t *n, int B, const oracle_hparams *hp, float *pw,
-                    float *losses) {
+static void mf_step_impl(float *U, float *mU, float *vU, int64_t n_users, float *I, float *mI,
+                         float *vI, int64_t n_items, float *w, float *mw, float *vw, float *wu,
+                         float *mwu, float *vwu, int d, const int32_t *u, const int32_t *p,
+                         const int32_t *n, int B, const oracle_hparams *hp, float *pw,
+                         float *losses, int item_only) {
   float *sc = (float *)malloc(sizeof(float) * (size_t)B * 11);
   float *yp = sc, *yn = sc + B, *sp = sc + 2 * B, *sn = sc + 3 * B, *su = sc + 4 * B,
         *rq = sc + 5 * B, *dyp = sc + 6 * B, *dyn = sc + 7 * B, *dsp = sc + 8 * B,
         *dsn = sc + 9 * B, *dsu = sc + 10 * B;
   float l3[3];
   oracle_gather_dots(U, I, U, I, w, wu, u, p, n, B, d, yp, yn, sp, sn, su, rq);
-  oracle_grid_bce(yp, yn, sp, sn, su, B, hp->alpha, hp->beta, l3, dyp, dyn, dsp, dsn, dsu);
-  batch_losses(l3, rq, B, hp, losses);
+  grid_bce_impl(yp, yn, sp, sn, su, B, hp->alpha, hp->beta, l3, dyp, dyn, dsp, dsn, dsu,
+                item_only);
+  batch_losses(l3, rq, B, hp, losses); /* item_only: l3[2] = 0 -> mf = L_ori + alpha*L_item */
 
   float *gU = (float *)malloc(sizeof(float) * (size_t)B * d * 3);
   float *gPN = gU + (size_t)B * d;
@@ -295,12 +315,32 @@ void oracle_mf_step(float *U, float *mU, float *vU, int64_t n_users, float *I, f
   oracle_adam_sparse(I, mI, vI, n_items, d, pn, gPN, 2 * B, lr_t, hp->beta1, hp->beta2,
                      hp->eps);
   oracle_adam_dense_vec(w, mw, vw, gw, d, lr_t, hp->beta1, hp->beta2, hp->eps);
-  oracle_adam_dense_vec(wu, mwu, vwu, gwu, d, lr_t, hp->beta1, hp->beta2, hp->eps);
+  if (!item_only) /* no gradient reaches user_branch: minimize() leaves it and its slots alone */
+    oracle_adam_dense_vec(wu, mwu, vwu, gwu, d, lr_t, hp->beta1, hp->beta2, hp->eps);
   pw[0] = pw[0] * hp->beta1; /* adam.py _finish */
   pw[1] = pw[1] * hp->beta2;
   free(sc);
   free(gU);
   free(pn);
+}
+
+void oracle_mf_step(float *U, float *mU, float *vU, int64_t n_users, float *I, float *mI,
+                    float *vI, int64_t n_items, float *w, float *mw, float *vw, float *wu,
+                    float *mwu, float *vwu, int d, const int32_t *u, const int32_t *p,
+                    const int32_t *n, int B, const oracle_hparams *hp, float *pw,
+                    float *losses) {
+  mf_step_impl(U, mU, vU, n_users, I, mI, vI, n_items, w, mw, vw, wu, mwu, vwu, d, u, p, n, B, hp,
+               pw, losses, 0);
+}
+
+/* `--train rubibce` (model.py:83-85 opt_two_bce, :158-183): wu is read by nothing that matters
+ * (the user logits are computed and dropped) and is never written */
+void oracle_mf_step_item(float *U, float *mU, float *vU, int64_t n_users, float *I, float *mI,
+                         float *vI, int64_t n_items, float *w, float *mw, float *vw, float *wu,
+                         int d, const int32_t *u, const int32_t *p, const int32_t *n, int B,
+                         const oracle_hparams *hp, float *pw, float *losses) {
+  mf_step_impl(U, mU, vU, n_users, I, mI, vI, n_items, w, mw, vw, wu, NULL, NULL, d, u, p, n, B, hp,
+               pw, losses, 1);
 }
 
 /* ---- `--train normalbce` (the README's baseline command, README.md:30): model.py:277-287 ----
@@ -429,7 +469,8 @@ static void lgcn_step_impl(const int32_t *rowptr, const int32_t *col, const floa
                            int64_t n_items, float *w, float *mw, float *vw, float *wu, float *mwu,
                            float *vwu, int d, int L, const int32_t *u, const int32_t *p,
                            const int32_t *n, int B, int train, const oracle_hparams *hp, float *pw,
-                           float *losses, int normal) {
+                           float *losses, int mode) {
+  const int normal = mode == 1, item_only = mode == 2; /* 2: `--loss bce1`, LightGCN.py:431-461 */
   const int64_t N = n_users + n_items, ne = N * d;
   float *Em = (float *)malloc(sizeof(float) * (size_t)ne * 2), *E0 = Em + ne;
   lgcn_layers(rowptr, col, val, U, n_users, I, n_items, d, L, Em, E0);
@@ -454,8 +495,8 @@ static void lgcn_step_impl(const int32_t *rowptr, const int32_t *col, const floa
     losses[2] = emb;
     losses[3] = mf;
   } else {
-    oracle_grid_bce(yp, yn, sp, sn, su, B, hp->alpha, hp->beta, l3, train ? dyp : NULL, dyn, dsp,
-                    dsn, dsu);
+    grid_bce_impl(yp, yn, sp, sn, su, B, hp->alpha, hp->beta, l3, train ? dyp : NULL, dyn, dsp,
+                  dsn, dsu, item_only);
     batch_losses(l3, rq, B, hp, losses); /* loss = mf_loss + emb_loss (LightGCN.py:200) */
   }
   if (!train) {
@@ -517,7 +558,8 @@ static void lgcn_step_impl(const int32_t *rowptr, const int32_t *col, const floa
   }
   if (!normal) {
     oracle_adam_dense_vec(w, mw, vw, gw, d, lr_t, hp->beta1, hp->beta2, hp->eps);
-    oracle_adam_dense_vec(wu, mwu, vwu, gwu, d, lr_t, hp->beta1, hp->beta2, hp->eps);
+    if (!item_only)
+      oracle_adam_dense_vec(wu, mwu, vwu, gwu, d, lr_t, hp->beta1, hp->beta2, hp->eps);
   }
   pw[0] = pw[0] * hp->beta1;
   pw[1] = pw[1] * hp->beta2;
@@ -544,6 +586,15 @@ void oracle_lgcn_step_normal(const int32_t *rowptr, const int32_t *col, const fl
                              const oracle_hparams *hp, float *pw, float *losses) {
   lgcn_step_impl(rowptr, col, val, U, mU, vU, n_users, I, mI, vI, n_items, w, NULL, NULL, wu, NULL,
                  NULL, d, L, u, p, n, B, train, hp, pw, losses, 1);
+}
+
+void oracle_lgcn_step_item(const int32_t *rowptr, const int32_t *col, const float *val, float *U,
+                           float *mU, float *vU, int64_t n_users, float *I, float *mI, float *vI,
+                           int64_t n_items, float *w, float *mw, float *vw, float *wu, int d,
+                           int L, const int32_t *u, const int32_t *p, const int32_t *n, int B,
+                           int train, const oracle_hparams *hp, float *pw, float *losses) {
+  lgcn_step_impl(rowptr, col, val, U, mU, vU, n_users, I, mI, vI, n_items, w, mw, vw, wu, NULL,
+                 NULL, d, L, u, p, n, B, train, hp, pw, losses, 2);
 }
 
 /* ---- scoring: model.py:45 batch_ratings, :199 rubi_ratings_both ---- */

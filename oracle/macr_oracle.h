@@ -68,6 +68,16 @@ void oracle_mf_step_normal(float *U, float *mU, float *vU, int64_t n_users, floa
                            const int32_t *n, int B, const oracle_hparams *hp, float *pw,
                            float *losses);
 
+/* `--train rubibce` (model.py:158-183, :83-85): item gate only -- grid P[i,j] = yp_j*sig(sp_i),
+ * mf = L_ori + alpha*L_item, Adam on the two tables and w; w_user is never written */
+void oracle_grid_bce_item(const float *yp, const float *yn, const float *sp, const float *sn,
+                          int B, float alpha, float *losses3, float *d_yp, float *d_yn,
+                          float *d_sp, float *d_sn);
+void oracle_mf_step_item(float *U, float *mU, float *vU, int64_t n_users, float *I, float *mI,
+                         float *vI, int64_t n_items, float *w, float *mw, float *vw, float *wu,
+                         int d, const int32_t *u, const int32_t *p, const int32_t *n, int B,
+                         const oracle_hparams *hp, float *pw, float *losses);
+
 /* macr_lightgcn/LightGCN.py:297-305 (one layer, all folds) */
 void oracle_spmm_csr(const int32_t *rowptr, const int32_t *col, const float *val,
                      int64_t n_rows, const float *X, int d, float *Y);
@@ -92,6 +102,13 @@ void oracle_lgcn_step_normal(const int32_t *rowptr, const int32_t *col, const fl
                              float *vI, int64_t n_items, float *w, float *wu, int d, int L,
                              const int32_t *u, const int32_t *p, const int32_t *n, int B, int train,
                              const oracle_hparams *hp, float *pw, float *losses);
+
+/* `--loss bce1` (LightGCN.py:431-461, :190-194) */
+void oracle_lgcn_step_item(const int32_t *rowptr, const int32_t *col, const float *val, float *U,
+                           float *mU, float *vU, int64_t n_users, float *I, float *mI, float *vI,
+                           int64_t n_items, float *w, float *mw, float *vw, float *wu, int d,
+                           int L, const int32_t *u, const int32_t *p, const int32_t *n, int B,
+                           int train, const oracle_hparams *hp, float *pw, float *losses);
 
 /* model.py:199 scoring */
 void oracle_score_gates(const float *rows, int64_t n, int d, const float *wvec, float *sig);

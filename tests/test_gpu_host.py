@@ -86,6 +86,31 @@ def test_mf_facade_steps_scores_and_eval_match_oracle(oracle):
     for k in want:
         np.testing.assert_allclose(fused[k], want[k], rtol=1e-9, atol=1e-12, err_msg=k)
         np.testing.assert_allclose(literal[k], want[k], rtol=1e-9, atol=1e-12, err_msg=k)
+    # the item-gate-only head (`--train rubibce --test rubi` -> model_type rubi_c, train.py:241,551)
+    ones = np.ones(len(test_users), np.float32)
+    M1 = sess.run(model.rubi_ratings, {model.users: test_users[:10], model.pos_items: list(range(data.n_items))})
+    want_M1 = oracle.score_matrix(np.ascontiguousarray(Ud[test_users[:10]]), Id, oracle.score_gates(Id, wd),
+                                  ones[:10], args.c)
+    np.testing.assert_allclose(M1, want_M1, rtol=1e-4, atol=1e-5)
+    ids1, _ = oracle.score_topk(Uq, Id, oracle.score_gates(Id, wd), ones, args.c, mrp, mcol, 20)
+    want1 = mf_metrics.evaluate(ids1, [data.test_user_list[u] for u in test_users], Ks)
+    fused1 = MFEvaluator(data, Ks, 32, "fused").test(sess, model, test_users, model_type="rubi_c")
+    literal1 = MFEvaluator(data, Ks, 32, "matrix").test(sess, model, test_users, model_type="rubi_c")
+    for k in want1:
+        np.testing.assert_allclose(fused1[k], want1[k], rtol=1e-9, atol=1e-12, err_msg=k)
+        np.testing.assert_allclose(literal1[k], want1[k], rtol=1e-9, atol=1e-12, err_msg=k)
+    # and its training fetch list (train.py:482-486)
+    st2 = oracle.MFState(Ud, Id, wd, wud)
+    for k in ("mU", "vU", "mI", "vI", "mw", "vw", "mwu", "vwu"):
+        getattr(st2, k)[...] = getattr(t, k).cpu().numpy().reshape(getattr(st2, k).shape)
+    st2.t = model.trainer.steps_done
+    st2.pw[:] = (hp.beta1 ** (st2.t + 1), hp.beta2 ** (st2.t + 1))
+    users, pos, neg = data.sample()
+    got = sess.run([model.opt_two_bce, model.loss_two_bce, model.mf_loss_two_bce, model.reg_loss_two_bce],
+                   feed_dict={model.users: users, model.pos_items: pos, model.neg_items: neg})
+    want = oracle.mf_step_item(st2, users, pos, neg, hp)
+    assert got[0] is None
+    np.testing.assert_allclose(got[1:], want[:3], rtol=1e-4, atol=1e-4)
     model.close()
 
 
@@ -228,6 +253,17 @@ def test_cli_drivers_run_end_to_end(tmp_path, monkeypatch, capsys):
                          "--test", "normal", "--lr", "0.001", "--weights_path", str(tmp_path) + "/"])
     out = capsys.readouterr().out
     assert "recall=[" in out and res["last"] is not None
+    # the item-gate-only neighbours: MF `--train rubibce --test rubi` (head rubi_c), LightGCN `--loss bce1 --test rubi1`
+    cfg = train_mf.main(["--data_path", GOLD + "/", "--dataset", "tiny", "--batch_size", "32", "--epoch", "2",
+                         "--log_interval", "2", "--train", "rubibce", "--test", "rubi", "--c", "2", "--lr", "0.01",
+                         "--saveID", "i", "--save_flag", "0"])
+    out = capsys.readouterr().out
+    assert "c:2.00 [" in out and 0 <= cfg["best_hr"] <= 1
+    res = lightgcn.main(["--data_path", GOLD + "/", "--dataset", "tiny", "--batch_size", "32", "--epoch", "1",
+                         "--log_interval", "1", "--layer_size", "[64,64]", "--Ks", "[20]", "--loss", "bce1",
+                         "--test", "rubi1", "--c", "2", "--lr", "0.001", "--weights_path", str(tmp_path) + "/"])
+    out = capsys.readouterr().out
+    assert "c:2.00 recall=[" in out and res["last"] is not None
 
 
 def test_epoch_run_host_equals_device_run():

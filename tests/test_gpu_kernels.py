@@ -432,3 +432,90 @@ def test_planned_spmm_with_hub_rows_matches_oracle(T, ops, oracle):
         gotE = ops.lgcn_propagate(d_rp, d_col, d_val, dev(T, U), dev(T, I), L, plan=plan)
         np.testing.assert_allclose(gotE.cpu().numpy(), wantE, rtol=5e-6, atol=2e-7)
     plan.close()
+
+
+def test_rubibce_trainer_steps_match_oracle(T, ops, oracle):
+    """`--train rubibce` (model.py:158-183,:83-85): the B x B grid with the item gate only, on the
+    same kernels (gather_dots writes gate 1 / user loss 0); w_user and its slots are never written,
+    also after steps of the two-gate graph left a momentum in them."""
+    n_users, n_items, B, steps = 900, 500, 256, 5
+    U, I, w, wu = make_model(51, n_users, n_items, scale=4.0)
+    hp_kw = dict(lr=1e-2, alpha=1e-2, beta=1e-3, decay=1e-4, batch_size=B)
+    st = oracle.MFState(U, I, w, wu)
+    tr = ops.MFTrainer(U, I, w, wu, ops.HParams.make(**hp_kw), max_batch=B)
+    tr.set_mode(ops.MFTrainer.RUBIBCE)
+    rng = np.random.RandomState(52)
+    for s in range(steps):
+        u, p, n = make_batch(rng, n_users, n_items, B)
+        want = oracle.mf_step_item(st, u, p, n, oracle.HParams.make(**hp_kw))
+        got = tr.step_host(u.tolist(), p.tolist(), n.tolist())
+        np.testing.assert_allclose(np.array(got), want[:3], rtol=1e-4, atol=1e-5, err_msg=f"step {s}")
+    t = tr.tab
+    for name, g, o in (("U", t.U, st.U), ("I", t.I, st.I), ("w", t.w, st.w), ("mU", t.mU, st.mU),
+                       ("vI", t.vI, st.vI), ("mw", t.mw, st.mw)):
+        np.testing.assert_allclose(g.cpu().numpy(), o, rtol=1e-4, atol=1e-5, err_msg=name)
+    np.testing.assert_array_equal(t.wu.cpu().numpy(), wu)
+    assert not t.mwu.any().item() and not t.vwu.any().item()
+    assert np.abs(t.w.cpu().numpy() - w).max() > 0
+    # one two-gate step gives w_user a momentum; the item-only graph must then leave all three alone
+    tr.set_mode(ops.MFTrainer.RUBIBCEBOTH)
+    u, p, n = make_batch(rng, n_users, n_items, B)
+    want = oracle.mf_step(st, u, p, n, oracle.HParams.make(**hp_kw))
+    got = tr.step_host(u.tolist(), p.tolist(), n.tolist())
+    np.testing.assert_allclose(np.array(got), want[:3], rtol=1e-4, atol=1e-4)
+    frozen = [x.clone() for x in (t.wu, t.mwu, t.vwu)]
+    assert frozen[1].any().item()
+    tr.set_mode(ops.MFTrainer.RUBIBCE)
+    u, p, n = make_batch(rng, n_users, n_items, B)
+    want = oracle.mf_step_item(st, u, p, n, oracle.HParams.make(**hp_kw))
+    got = tr.step_host(u.tolist(), p.tolist(), n.tolist())
+    np.testing.assert_allclose(np.array(got), want[:3], rtol=1e-4, atol=1e-4)
+    for a, b in zip(frozen, (t.wu, t.mwu, t.vwu)):
+        assert T.equal(a, b)
+    np.testing.assert_allclose(t.U.cpu().numpy(), st.U, rtol=1e-4, atol=1e-5)
+    tr.close()
+
+
+def test_lgcn_bce1_trainer_steps_match_oracle(T, ops, oracle):
+    """`--loss bce1` (LightGCN.py:431-461,:190-194) on the LightGCN trainer."""
+    n_users, n_items, L, B, steps = 1200, 500, 2, 256, 4
+    _, (rowptr, col, val) = _graph(L, n_users, n_items, 10)
+    U, I, w, wu = make_model(39, n_users, n_items, scale=4.0)
+    hp_kw = dict(lr=1e-3, alpha=1e-2, beta=1e-3, decay=1e-5, batch_size=B)
+    st = oracle.MFState(U, I, w, wu)
+    tr = ops.LGCNTrainer(rowptr, col, val, U, I, w, wu, L, ops.HParams.make(**hp_kw), max_batch=B)
+    tr.set_mode(ops.LGCNTrainer.RUBIBCE)
+    rng = np.random.RandomState(40)
+    for s in range(steps):
+        u, p, n = make_batch(rng, n_users, n_items, B)
+        lo_eval = tr.step_host(u.tolist(), p.tolist(), n.tolist(), train=False)
+        want = oracle.lgcn_step_item(st, rowptr, col, val, L, u, p, n, oracle.HParams.make(**hp_kw))
+        got = tr.step_host(u.tolist(), p.tolist(), n.tolist())
+        np.testing.assert_allclose(np.array(got), want[:3], rtol=1e-4, atol=1e-5, err_msg=f"step {s}")
+        np.testing.assert_allclose(np.array(lo_eval), want[:3], rtol=1e-4, atol=1e-5)
+    t = tr.tab
+    for name, g, o in (("U", t.U, st.U), ("I", t.I, st.I), ("w", t.w, st.w)):
+        np.testing.assert_allclose(g.cpu().numpy(), o, rtol=1e-4, atol=1e-5, err_msg=name)
+    np.testing.assert_array_equal(t.wu.cpu().numpy(), wu)
+    tr.close()
+
+
+def test_item_gate_score_head_matches_literal(T, ops, oracle):
+    """`rubi_ratings` (model.py:141; LightGCN.py:442): (y - c) * sig(i.w) -- the fused kernel with a
+    user gate of ones is bit-identical to the oracle's two-gate score with sig_u = 1 and agrees
+    with the literal restatement."""
+    import torch
+
+    from oracle import literal_torch as lit
+
+    U, I, w, wu = make_model(61, 300, 5000, scale=6.0)
+    si = oracle.score_gates(I, w)
+    ones = np.ones(300, np.float32)
+    want_ids, want_sc = oracle.score_topk(U, I, si, ones, 3.0, None, None, 20)
+    dU, dI = dev(T, U), dev(T, I)
+    ids, sc = ops.score_topk(dU, dI, ops.score_gates(dI, dev(T, w)), dev(T, ones), 3.0, None, None, 20)
+    np.testing.assert_array_equal(ids.cpu().numpy(), want_ids)
+    np.testing.assert_array_equal(sc.cpu().numpy(), want_sc)
+    M = lit.rubi_ratings(torch.tensor(U, dtype=torch.float64), torch.tensor(I, dtype=torch.float64),
+                         torch.tensor(w, dtype=torch.float64).reshape(-1, 1), 3.0).numpy()
+    np.testing.assert_allclose(np.take_along_axis(M, want_ids.astype(np.int64), 1), want_sc, rtol=2e-5, atol=2e-5)

@@ -87,6 +87,6 @@ def test_drivers_reject_modes_outside_the_hot_path():
     from macr_b200.cli import lightgcn, train_mf
 
     with pytest.raises(SystemExit):
-        train_mf.main(["--dataset", "tiny", "--train", "rubibce"])  # item-gate-only variant: not implemented
+        train_mf.main(["--dataset", "tiny", "--train", "rubi"])  # BPR two-branch variant: not implemented
     with pytest.raises(SystemExit):
         lightgcn.main(["--dataset", "tiny", "--loss", "bpr"])

@@ -309,3 +309,79 @@ def test_lgcn_bce_step_matches_literal_graph(oracle):
     for name, a, b in (("U", st.U, P[0]), ("I", st.I, P[1])):
         np.testing.assert_allclose(a, b.detach().numpy().reshape(a.shape), rtol=2e-3, atol=2e-6, err_msg=name)
     np.testing.assert_array_equal(st.w, w)
+
+
+def test_rubibce_step_matches_literal_graph(oracle):
+    """`--train rubibce` (model.py:158-183, :83-85): item gate only.  Oracle closed form vs torch
+    autograd of the literal graph + TF Adam; w_user receives no gradient and is never written."""
+    n_users, n_items, B = 60, 40, 96
+    U, I, w, wu = make_model(25, n_users, n_items, scale=4.0)
+    hp_kw = dict(lr=1e-2, alpha=1e-2, beta=1e-3, decay=1e-3, batch_size=B)
+    rng = np.random.RandomState(26)
+    batches = [make_batch(rng, n_users, n_items, B) for _ in range(3)]
+    st = oracle.MFState(U, I, w, wu)
+    hp = oracle.HParams.make(**hp_kw)
+    got = [oracle.mf_step_item(st, *b, hp) for b in batches]
+    P = [t64(U).requires_grad_(True), t64(I).requires_grad_(True), t64(w).reshape(-1, 1).requires_grad_(True)]
+    opt = lit.TFAdam(P, hp_kw["lr"])
+    want = []
+    for u, p, n in batches:
+        for q in P:
+            q.grad = None
+        ui, pi, ni = (torch.as_tensor(x, dtype=torch.long) for x in (u, p, n))
+        mf, reg, l_ori, _ = lit.bce_two_branch(P[0][ui], P[1][pi], P[1][ni], P[2], hp_kw["alpha"],
+                                               hp_kw["decay"], hp_kw["batch_size"])
+        (mf + reg).backward()
+        opt.step([q.grad for q in P], [True, True, False])
+        want.append(((mf + reg).item(), mf.item(), reg.item(), l_ori.item()))
+    np.testing.assert_allclose(np.array(got), np.array(want), rtol=1e-5, atol=1e-6)
+    for name, a, b in (("U", st.U, P[0]), ("I", st.I, P[1]), ("w", st.w, P[2]), ("mU", st.mU, opt.m[0]),
+                       ("vI", st.vI, opt.v[1])):
+        np.testing.assert_allclose(a, b.detach().numpy().reshape(a.shape), rtol=2e-3, atol=2e-6, err_msg=name)
+    np.testing.assert_array_equal(st.wu, wu)  # untouched
+    assert np.abs(st.w - w).max() > 0
+    # the stand-alone grid: with sig(su) = 1 and beta = 0 the two-gate grid reduces to this one
+    yp, yn, sp, sn = (rng.randn(B).astype(np.float32) for _ in range(4))
+    l3, dyp, dyn, dsp, dsn = oracle.grid_bce_item(yp, yn, sp, sn, 0.01)
+    big = np.full(B, 80.0, np.float32)  # sigmoid(80) == 1.0f
+    l3b, (dyp_b, dyn_b, dsp_b, dsn_b, dsu_b) = oracle.grid_bce(yp, yn, sp, sn, big, 0.01, 0.0)
+    np.testing.assert_array_equal(l3[:2], l3b[:2])
+    for a, b in ((dyp, dyp_b), (dyn, dyn_b), (dsp, dsp_b), (dsn, dsn_b)):
+        np.testing.assert_array_equal(a, b)
+    assert l3[2] == 0.0 and not dsu_b.any()
+
+
+def test_lgcn_bce1_step_matches_literal_graph(oracle):
+    """`--loss bce1` (LightGCN.py:431-461,:190-194): item gate only on the propagated rows, L2 on
+    the raw rows; oracle step vs torch autograd through the propagation."""
+    n_users, n_items, B, L = 50, 30, 64, 2
+    lists = make_interactions(23, n_users, n_items, 5)
+    rowptr, col, val = norm_adj_csr(lists, n_users, n_items)
+    U, I, w, wu = make_model(29, n_users, n_items, scale=4.0)
+    hp_kw = dict(lr=1e-2, alpha=1e-2, beta=1e-3, decay=1e-3, batch_size=B)
+    rng = np.random.RandomState(30)
+    batches = [make_batch(rng, n_users, n_items, B) for _ in range(3)]
+    st = oracle.MFState(U, I, w, wu)
+    hp = oracle.HParams.make(**hp_kw)
+    N = n_users + n_items
+    A = torch.zeros(N, N, dtype=torch.float64)
+    for r in range(N):
+        A[r, col[rowptr[r]:rowptr[r + 1]]] = t64(val[rowptr[r]:rowptr[r + 1]])
+    P = [t64(U).requires_grad_(True), t64(I).requires_grad_(True), t64(w).reshape(-1, 1).requires_grad_(True)]
+    opt = lit.TFAdam(P, hp_kw["lr"])
+    for u, p, n in batches:
+        lo_eval = oracle.lgcn_step_item(st, rowptr, col, val, L, u, p, n, hp, train=False)
+        lo = oracle.lgcn_step_item(st, rowptr, col, val, L, u, p, n, hp, train=True)
+        np.testing.assert_allclose(lo_eval, lo, rtol=1e-6)
+        for q in P:
+            q.grad = None
+        ui, pi, ni = (torch.as_tensor(x, dtype=torch.long) for x in (u, p, n))
+        ua, ia = lit.lightgcn_embed(A, P[0], P[1], L)
+        mf, emb, *_ = lit.bce_two_branch(ua[ui], ia[pi], ia[ni], P[2], hp_kw["alpha"], hp_kw["decay"], B,
+                                         reg_rows=(P[0][ui], P[1][pi], P[1][ni]))
+        (mf + emb).backward()
+        opt.step([q.grad for q in P], [True, True, False])
+        np.testing.assert_allclose(lo[:3], [(mf + emb).item(), mf.item(), emb.item()], rtol=1e-5, atol=1e-6)
+    for name, a, b in (("U", st.U, P[0]), ("I", st.I, P[1]), ("w", st.w, P[2])):
+        np.testing.assert_allclose(a, b.detach().numpy().reshape(a.shape), rtol=2e-3, atol=2e-6, err_msg=name)
+    np.testing.assert_array_equal(st.wu, wu)
