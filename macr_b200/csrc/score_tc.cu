@@ -20,8 +20,7 @@
 //                ranks exactly those on top: a per-row cursor into the sorted train list marks
 //                them tile by tile) appended to the row's candidate list (one atomic per append).
 //   re-rank      one warp per row: exact fp32 FMA-chain score of the candidates (the arithmetic
-//                of score.cu; train items re-checked by binary search), ranks by counting under
-//                the order (score desc, lower id first).
+//                of score.cu), ranks by counting under the order (score desc, lower id first).
 //   fallback     a row whose candidate list overflowed (degenerate score distributions), a row
 //                without K unmasked groups, or a row whose train list exceeds 1/16 of the
 //                catalogue is done by the exact fp32 kernel (score.cu) -- never silently wrong.
@@ -61,6 +60,7 @@ constexpr int BN = 256;              // items per tile (UMMA N, TMEM columns per
 constexpr int NB = BN / 32;          // 32-column batches per tile
 typedef unsigned short oper_t;       // operands rounded to bf16
 constexpr int KB = 64;               // bf16 per 128-byte swizzle row = the whole embedding row
+static_assert(KB == kD && KB * sizeof(oper_t) == 128, "one swizzle row holds one embedding row");
 constexpr int A_TILE_BYTES = BM * 128;   // a 128 x 64 bf16 user tile, 128B-swizzled
 constexpr int B_TILE_BYTES = BN * 128;   // a 256 x 64 bf16 item tile
 // The "- c*sig_i" term rides on one extra K=16 step: user side [1,1,1,0..0], item side the three
@@ -749,14 +749,13 @@ row_threshold_kernel(const float *__restrict__ bmax, int T, int n_batches, int l
   }
 }
 
-// exact re-rank of the candidates of one row (one warp per row): each lane fetches, mask-checks
-// (binary search in the row's sorted train list) and re-scores one candidate per round with the
-// fp32 FMA chain of score.cu; ranks come from counting.  Rows whose list overflowed are queued
-// for the exact fp32 kernel.
+// exact re-rank of the candidates of one row (one warp per row): each lane fetches and re-scores
+// one candidate per round with the fp32 FMA chain of score.cu; ranks come from counting.  (Train
+// items never get here: the filter pass marks every entry of the row's sorted train list that
+// falls into a tile.)  Rows whose list overflowed are queued for the exact fp32 kernel.
 __global__ void __launch_bounds__(256, 4)
 rerank_kernel(const float *__restrict__ Uq, int T, const float *__restrict__ It,
               const float *__restrict__ sig_i, const float *__restrict__ sig_u, float c, int id_off,
-              const int32_t *__restrict__ mask_rowptr, const int32_t *__restrict__ mask_col,
               const uint2 *__restrict__ cand, const int *__restrict__ cand_cnt, int K,
               int32_t *__restrict__ out_ids, float *__restrict__ out_scores,
               int32_t *__restrict__ fb_rows, int *__restrict__ fb_count,
@@ -776,7 +775,6 @@ rerank_kernel(const float *__restrict__ Uq, int T, const float *__restrict__ It,
   su[wib][lane + 32] = Uq[(size_t)t * kD + lane + 32];
   __syncwarp();
   const float sgu = sig_u[t];
-  const int mlo = mask_rowptr ? mask_rowptr[t] : 0, mhi = mask_rowptr ? mask_rowptr[t + 1] : 0;
   float cs_[kRounds];
   int cg_[kRounds];
 #pragma unroll
@@ -786,32 +784,18 @@ rerank_kernel(const float *__restrict__ Uq, int T, const float *__restrict__ It,
     const int e = r * 32 + lane;
     if (e < total) {
       const int gid = (int)cand[(size_t)t * kCap + e].y;
-      int lo = mlo, hi = mhi;
-      bool masked = false;
-      while (lo < hi) {
-        const int mid = (lo + hi) >> 1;
-        const int v = mask_col[mid];
-        if (v == gid) {
-          masked = true;
-          break;
-        }
-        if (v < gid) lo = mid + 1;
-        else hi = mid;
-      }
-      if (!masked) {
-        const float4 *ip = reinterpret_cast<const float4 *>(It + (size_t)(gid - id_off) * kD);
-        float acc = 0.f;
+      const float4 *ip = reinterpret_cast<const float4 *>(It + (size_t)(gid - id_off) * kD);
+      float acc = 0.f;
 #pragma unroll
-        for (int q4 = 0; q4 < kD / 4; ++q4) {
-          const float4 v = ip[q4];
-          acc = fmaf(su[wib][4 * q4 + 0], v.x, acc);
-          acc = fmaf(su[wib][4 * q4 + 1], v.y, acc);
-          acc = fmaf(su[wib][4 * q4 + 2], v.z, acc);
-          acc = fmaf(su[wib][4 * q4 + 3], v.w, acc);
-        }
-        cs_[r] = __fmul_rn(__fmul_rn(__fsub_rn(acc, c), sig_i[gid - id_off]), sgu);
-        cg_[r] = gid;
+      for (int q4 = 0; q4 < kD / 4; ++q4) {
+        const float4 v = ip[q4];
+        acc = fmaf(su[wib][4 * q4 + 0], v.x, acc);
+        acc = fmaf(su[wib][4 * q4 + 1], v.y, acc);
+        acc = fmaf(su[wib][4 * q4 + 2], v.z, acc);
+        acc = fmaf(su[wib][4 * q4 + 3], v.w, acc);
       }
+      cs_[r] = __fmul_rn(__fmul_rn(__fsub_rn(acc, c), sig_i[gid - id_off]), sgu);
+      cg_[r] = gid;
     }
   }
   // rank by counting: the order (score desc, lower id first) is strict among valid candidates
@@ -1090,7 +1074,7 @@ extern "C" int macr_score_topk_tc(const float *Uq, int T, const float *It, int64
     if (rc) return rc;
     MACR_CUDA(cudaMemsetAsync(fb_count, 0, sizeof(int), s));
     rerank_kernel<<<(nb + 7) / 8, 256, 0, s>>>(Ub, nb, It, sig_i, sig_u + t0, c, item_id_offset,
-                                               mrp, mask_col, cand, cnt, K,
+                                               cand, cnt, K,
                                                out_ids + (size_t)t0 * K, out_scores + (size_t)t0 * K,
                                                fb_rows, fb_count, cand_total);
     MACR_LAUNCH_CHECK();

@@ -118,6 +118,32 @@ def test_tc_overflow_rows_fall_back_to_exact(T, ops, oracle):
     assert 0 < int(stats[0].item()) <= 30
 
 
+def test_tc_train_items_ranked_on_top(T, ops, oracle):
+    """What a trained model looks like: every user's train items are exactly its top-scoring items.
+    The filter pass masks them in place (they never reach the 128-slot candidate lists), rows with
+    a train list longer than 1/16 of the catalogue go straight to the exact kernel, and the result
+    stays bit-identical to the oracle."""
+    T_users, n_items, K, c = 400, 6000, 20, 40.0
+    U, I, w, wu = make_model(21, T_users, n_items, scale=10.0)
+    sig_i, sig_u = oracle.score_gates(I, w), oracle.score_gates(U, wu)
+    S = oracle.score_matrix(U, I, sig_i, sig_u, c)
+    order = np.argsort(-S, axis=1, kind="stable")
+    lens = np.array([5, 40, 150, 500])[np.arange(T_users) % 4]  # 500 > 6000/16 + 64: straight to exact
+    lists = [np.sort(order[t, :lens[t]]).astype(np.int32) for t in range(T_users)]
+    mrp, mcol = lists_to_csr(lists)
+    want_ids, want_sc = oracle.score_topk(U, I, sig_i, sig_u, c, mrp, mcol, K)
+    assert not set(want_ids[2].tolist()) & set(lists[2].tolist())
+    dU, dI, gsi, gsu = _gates(T, ops, U, I, w, wu)
+    stats = T.zeros(2, dtype=T.int64, device="cuda")
+    ids, sc = ops.score_topk_tc(dU, dI, gsi, gsu, c, dev(T, mrp), dev(T, mcol), K, stats=stats)
+    np.testing.assert_array_equal(ids.cpu().numpy(), want_ids)
+    np.testing.assert_array_equal(sc.cpu().numpy(), want_sc)
+    n_direct = int((lens == 500).sum())
+    assert n_direct <= int(stats[0].item()) <= n_direct + 20
+    # the lists held the top-K survivors, not the (up to 150) train items above them
+    assert stats[1].item() / (T_users - stats[0].item()) < 6 * K + 40
+
+
 def test_tc_item_shards_merge_to_single(T, ops):
     """item-sharded tcgen05 scoring + macr_topk_merge == unsharded exact kernel (the N-GPU path)."""
     T_users, n_items, K, G = 500, 20000, 20, 4
