@@ -81,3 +81,74 @@ def test_shard_bounds_cover_everything():
     for n, g in ((8790, 8), (40981, 8), (7, 8), (1_000_000, 4)):
         b = item_shard_bounds(n, g)
         assert b[0] == 0 and b[-1] == n and len(b) == g + 1 and np.all(np.diff(b) >= 0)
+
+
+# ------------------------------------------------------------------------------------------------
+# row-sharded MF training: ownership, ghost slots, the one all-reduce -- with the CPU oracle as the
+# step engine (the checker) in place of macr_mf_trainer_step
+# ------------------------------------------------------------------------------------------------
+class _OracleOps:
+    """Stand-in for `macr_b200.ops` on the CPU: same surface as far as RowShardedMFTrainer uses it."""
+
+    class MFTrainer:
+        def __init__(self, U, I, w, wu, hp, max_batch, device="cpu"):
+            import oracle
+
+            self.oracle, self.hp, self.dev = oracle, hp, torch.device("cpu")
+            self.st = oracle.MFState(U, I, w, wu)
+
+            class Tab:
+                pass
+
+            self.tab = Tab()
+            for k in ("U", "mU", "vU", "I", "mI", "vI", "w", "wu"):
+                setattr(self.tab, k, torch.from_numpy(getattr(self.st, k)))  # shares memory
+
+        def step_device(self, u, p, n):
+            return torch.from_numpy(self.oracle.mf_step(self.st, u.numpy(), p.numpy(), n.numpy(), self.hp))
+
+        def close(self):
+            pass
+
+    @staticmethod
+    def gather_rows(table, ids):
+        return table[ids.long()].clone()
+
+
+def _train_worker(rank, world, port, out_dir):
+    import oracle
+    from helpers import make_batch
+    from macr_b200.host import dist as mdist
+
+    os.environ["MASTER_ADDR"], os.environ["MASTER_PORT"] = "127.0.0.1", str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        n_users, n_items, B, steps = 101, 77, 96, 4  # odd sizes: ragged shards; B > n_items: duplicates
+        U, I, w, wu = make_model(7, n_users, n_items, scale=4.0)
+        hp = oracle.HParams.make(lr=1e-2, alpha=1e-2, beta=1e-3, decay=1e-3, batch_size=B)
+        rng = np.random.RandomState(8)
+        batches = [make_batch(rng, n_users, n_items, B) for _ in range(steps)]
+        sh = mdist.RowShardedMFTrainer(U, I, w, wu, hp, B, rank=rank, world=world, device="cpu",
+                                       ops_module=_OracleOps)
+        single = oracle.MFState(U, I, w, wu)
+        for u, p, n in batches:
+            want = oracle.mf_step(single, u, p, n, hp)
+            got = sh.step_device(*(torch.from_numpy(np.asarray(x, np.int32)) for x in (u, p, n)))
+            np.testing.assert_array_equal(got.numpy(), want)  # replicated part: identical everywhere
+        loc = sh.local_tables()
+        for k, full, lo, hi in (("U", single.U, sh.u_lo, sh.u_hi), ("mU", single.mU, sh.u_lo, sh.u_hi),
+                                ("vU", single.vU, sh.u_lo, sh.u_hi), ("I", single.I, sh.i_lo, sh.i_hi),
+                                ("mI", single.mI, sh.i_lo, sh.i_hi), ("vI", single.vI, sh.i_lo, sh.i_hi)):
+            np.testing.assert_array_equal(loc[k].numpy(), full[lo:hi], err_msg=k)
+        np.testing.assert_array_equal(loc["w"].numpy(), single.w)
+        np.testing.assert_array_equal(loc["wu"].numpy(), single.wu)
+        assert (sh.u_hi - sh.u_lo) in (50, 51) and sh.trainer.tab.U.shape[0] == sh.n_lu + B
+        open(os.path.join(out_dir, f"train_ok{rank}"), "w").write("ok")
+    finally:
+        dist.destroy_process_group()
+
+
+def test_row_sharded_training_plumbing_world2(tmp_path, oracle):
+    world = 2
+    mp.spawn(_train_worker, args=(world, _free_port(), str(tmp_path)), nprocs=world, join=True)
+    assert all(os.path.exists(tmp_path / f"train_ok{r}") for r in range(world))

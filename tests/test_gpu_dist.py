@@ -1,0 +1,89 @@
+"""GPU test of the row-sharded MF trainer (macr_b200/host/dist.py:RowShardedMFTrainer): two ranks
+share cuda:0 (gloo moves the CUDA exchange buffer, so one GPU is enough), each owns half of the
+rows of both tables and their Adam slots, and after several steps the owned slices, w, w_user and
+the losses are BIT-identical to a single-GPU `MFTrainer` run on the full tables (SURVEY 8e rows
+"dense Adam sweep" / "gather + grid + row grads").  On a multi-GPU box the same class runs one
+rank per GPU over NCCL (dev/bench_sharded_train.py)."""
+import os
+import socket
+
+import numpy as np
+import pytest
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+from helpers import make_batch, make_model
+
+pytestmark = pytest.mark.gpu
+
+N_USERS, N_ITEMS, B, STEPS = 201, 745, 256, 5  # ragged shards; B > N_USERS: users repeat inside a batch
+HP = dict(lr=1e-2, alpha=1e-2, beta=1e-3, decay=1e-4, batch_size=B)
+
+
+def _free_port():
+    with socket.socket() as s:
+        s.bind(("127.0.0.1", 0))
+        return s.getsockname()[1]
+
+
+def _batches():
+    rng = np.random.RandomState(72)
+    return [make_batch(rng, N_USERS, N_ITEMS, B) for _ in range(STEPS)]
+
+
+def _worker(rank, world, port, out_dir):
+    import torch
+
+    from macr_b200 import ops
+    from macr_b200.host import dist as mdist
+
+    os.environ["MASTER_ADDR"], os.environ["MASTER_PORT"] = "127.0.0.1", str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        U, I, w, wu = make_model(71, N_USERS, N_ITEMS, scale=4.0)
+        sh = mdist.RowShardedMFTrainer(U, I, w, wu, ops.HParams.make(**HP), B, rank=rank, world=world,
+                                       device="cuda:0")
+        losses = []
+        for u, p, n in _batches():
+            ids = [torch.from_numpy(np.asarray(x, np.int32)).cuda() for x in (u, p, n)]
+            losses.append(sh.step_device(*ids).cpu().numpy().copy())
+        out = {k: v.cpu().numpy() for k, v in sh.local_tables().items()}
+        out["losses"] = np.stack(losses)
+        out["bounds"] = np.array([sh.u_lo, sh.u_hi, sh.i_lo, sh.i_hi])
+        np.savez(os.path.join(out_dir, f"rank{rank}.npz"), **out)
+        sh.close()
+    finally:
+        dist.destroy_process_group()
+
+
+def test_row_sharded_mf_training_equals_single_gpu(tmp_path):
+    import torch
+
+    from macr_b200 import ops
+
+    world = 2
+    mp.spawn(_worker, args=(world, _free_port(), str(tmp_path)), nprocs=world, join=True)
+    U, I, w, wu = make_model(71, N_USERS, N_ITEMS, scale=4.0)
+    tr = ops.MFTrainer(U, I, w, wu, ops.HParams.make(**HP), max_batch=B)
+    want_losses = []
+    for u, p, n in _batches():
+        ids = [torch.from_numpy(np.asarray(x, np.int32)).cuda() for x in (u, p, n)]
+        want_losses.append(tr.step_device(*ids).cpu().numpy().copy())
+    t = tr.tab
+    full = {k: getattr(t, k).cpu().numpy() for k in ("U", "mU", "vU", "I", "mI", "vI", "w", "wu")}
+    covered_u = covered_i = 0
+    for r in range(world):
+        z = np.load(tmp_path / f"rank{r}.npz")
+        u_lo, u_hi, i_lo, i_hi = (int(x) for x in z["bounds"])
+        np.testing.assert_array_equal(z["losses"], np.stack(want_losses))
+        for k in ("U", "mU", "vU"):
+            np.testing.assert_array_equal(z[k], full[k][u_lo:u_hi], err_msg=f"rank {r} {k}")
+        for k in ("I", "mI", "vI"):
+            np.testing.assert_array_equal(z[k], full[k][i_lo:i_hi], err_msg=f"rank {r} {k}")
+        np.testing.assert_array_equal(z["w"], full["w"])
+        np.testing.assert_array_equal(z["wu"], full["wu"])
+        covered_u += u_hi - u_lo
+        covered_i += i_hi - i_lo
+    assert covered_u == N_USERS and covered_i == N_ITEMS
+    assert np.abs(full["U"] - U).max() > 0
+    tr.close()
