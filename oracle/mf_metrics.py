@@ -1,6 +1,7 @@
 """numpy restatement of the MF evaluation arithmetic, macr_mf/train.py:32-117,286-290.
 TEST INFRASTRUCTURE ONLY.  (`np.asfarray` of the reference is gone in numpy 2; `np.asarray(..,
-float)` is its definition.)"""
+float)` is its definition.)  Pinned against the reference's own functions run here:
+tests/golden/mf_metrics.npz (tests/golden/make_golden.py:run_mf_metrics), tests/test_host_logic.py."""
 import numpy as np
 
 

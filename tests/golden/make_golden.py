@@ -12,6 +12,9 @@ What is produced (all from reference code, none from this repo's implementation)
   ref_evaluator.npz        the reference's C++ evaluator (oracle/_ref, built from
                            evaluator/cpp/include/*.h) on a seeded score matrix
   parser_defaults.json     defaults of macr_mf/parse.py and macr_lightgcn/utility/parser.py
+  mf_metrics.npz           macr_mf/train.py's own ranklist_by_sorted + get_performance (:32-117) on a
+                           seeded score matrix (the functions are compiled from the reference file at
+                           generation time -- the module itself imports tensorflow and cannot be loaded)
 
 Usage:  python tests/golden/make_golden.py        (needs /root/reference and oracle/_ref)
 """
@@ -166,6 +169,51 @@ def run_evaluator(out):
                                 truth=np.concatenate(truth), rankings=rk, results=res)
 
 
+def run_mf_metrics(out):
+    """Executes the reference's OWN metric functions (macr_mf/train.py:32-117).  train.py imports
+    tensorflow at the top, so the function definitions are lifted out of its syntax tree and
+    compiled as they stand; `np.asfarray` (removed in numpy 2) is given its numpy-1.x meaning."""
+    import ast
+    import heapq
+    import math
+
+    path = os.path.join(REF, "macr_mf", "train.py")
+    tree = ast.parse(open(path).read(), filename=path)
+    want = {"precision_at_k", "dcg_at_k", "ndcg_at_k", "recall_at_k", "hit_at_k", "ranklist_by_sorted",
+            "get_performance"}
+    body = [n for n in tree.body if isinstance(n, ast.FunctionDef) and n.name in want]
+    assert {n.name for n in body} == want
+    np_shim = types.ModuleType("numpy_with_asfarray")
+    np_shim.__dict__.update(np.__dict__)
+    np_shim.asfarray = lambda a, dtype=np.float64: np.asarray(a, dtype=dtype)  # numpy 1.x definition
+    ns = {"np": np_shim, "heapq": heapq, "math": math}
+    exec(compile(ast.Module(body=body, type_ignores=[]), path, "exec"), ns)
+
+    rng = np.random.RandomState(77)
+    n_users, n_items, Ks = 40, 300, [5, 20]
+    rating = rng.randn(n_users, n_items).astype(np.float32)
+    rating[3, 10] = rating[3, 200] = 9.0  # one exact tie on top: heapq.nlargest keeps the lower id first
+    train = [np.sort(rng.choice(n_items, size=int(rng.randint(0, 40)), replace=False)) for _ in range(n_users)]
+    test = []
+    for u in range(n_users):
+        rest = np.setdiff1d(np.arange(n_items), train[u])
+        test.append(np.sort(rng.choice(rest, size=int(rng.randint(1, 12)), replace=False)))
+    test[3] = np.array([10])  # the tied pair decides a hit at K = 1..: id 10 must rank before id 200
+    result = {k: np.zeros(len(Ks)) for k in ("precision", "recall", "ndcg", "hit_ratio")}
+    hits = np.zeros((n_users, max(Ks)), np.int8)
+    for u in range(n_users):  # test_one_user (:119-138) + the accumulation of test() (:286-290)
+        test_items = list(set(range(n_items)) - set(train[u].tolist()))
+        r = ns["ranklist_by_sorted"](test[u].tolist(), test_items, rating[u], Ks)
+        hits[u] = r
+        re = ns["get_performance"](test[u].tolist(), r, Ks)
+        for k in result:
+            result[k] += re[k] / n_users
+    out["mf_metrics"] = dict(rating=rating, Ks=np.array(Ks), hits=hits,
+                             train_len=np.array([len(t) for t in train], np.int32), train=np.concatenate(train).astype(np.int32),
+                             test_len=np.array([len(t) for t in test], np.int32), test=np.concatenate(test).astype(np.int32),
+                             **{"res_" + k: v for k, v in result.items()})
+
+
 def run_parsers(digests):
     out = {}
     for key, path in (("mf", "macr_mf/parse.py"), ("lgcn", "macr_lightgcn/utility/parser.py")):
@@ -193,6 +241,7 @@ def main():
         run_mf(work, digests, out)
         run_lgcn(work, digests, out)
         run_evaluator(out)
+        run_mf_metrics(out)
         for name, d in out.items():
             np.savez_compressed(os.path.join(HERE, name + ".npz"), **d)
         with open(os.path.join(HERE, "digests.json"), "w") as f:

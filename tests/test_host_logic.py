@@ -21,6 +21,34 @@ def test_mf_metrics_from_hits_matches_reference_arithmetic():
         np.testing.assert_allclose(got[k] / T, want[k], rtol=1e-12, atol=1e-15, err_msg=k)
 
 
+def test_mf_evaluation_matches_the_references_own_functions(oracle):
+    """tests/golden/mf_metrics.npz holds outputs of macr_mf/train.py's OWN ranklist_by_sorted +
+    get_performance (:32-117), compiled from the reference file by tests/golden/make_golden.py.
+    Pins, on the same score matrix: the ranking rule (train items removed, score descending,
+    heapq.nlargest keeps the lower id on a tie), the oracle's metric restatement and the product's
+    host-side metric arithmetic."""
+    import os
+
+    g = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "mf_metrics.npz"))
+    rating, Ks = g["rating"], g["Ks"].tolist()
+    split = lambda flat, lens: np.split(flat, np.cumsum(lens)[:-1])
+    train, test = split(g["train"], g["train_len"]), [t.tolist() for t in split(g["test"], g["test_len"])]
+    mrp = np.concatenate([[0], np.cumsum(g["train_len"])]).astype(np.int32)
+    ids = evaluate.host_topk(rating, mrp, g["train"], max(Ks))                 # product: literal eval path
+    np.testing.assert_array_equal(evaluate._hits(ids, test).astype(np.int8), g["hits"])
+    assert rating[3, 10] == rating[3, 200] and ids[3, 0] == 10 and 200 in ids[3, :2]  # the tie: lower id first
+    masked = rating.copy()
+    for u, t in enumerate(train):
+        masked[u, t] = -np.inf
+    np.testing.assert_array_equal(oracle.topk_rows(masked, max(Ks)), ids)      # oracle ranking rule
+    want = {k: g["res_" + k] for k in ("precision", "recall", "ndcg", "hit_ratio")}
+    got_o = mf_metrics.evaluate(ids, test, Ks)                                 # oracle restatement
+    got_p = evaluate.mf_metrics_from_hits(evaluate._hits(ids, test), [len(t) for t in test], Ks)
+    for k in want:
+        np.testing.assert_allclose(got_o[k], want[k], rtol=1e-12, atol=1e-15, err_msg=k)
+        np.testing.assert_allclose(got_p[k] / len(test), want[k], rtol=1e-12, atol=1e-15, err_msg=k)
+
+
 def test_host_topk_masks_and_breaks_ties_by_id():
     rate = np.array([[1.0, 3.0, 3.0, 2.0, 0.5], [5.0, 4.0, 3.0, 2.0, 1.0]], np.float32)
     mrp, mcol = np.array([0, 1, 4], np.int32), np.array([1, 0, 1, 2], np.int32)
