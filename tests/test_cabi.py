@@ -96,3 +96,14 @@ def test_product_never_imports_the_oracle():
                 text = open(os.path.join(dirpath, fn)).read()
                 assert not re.search(r"^\s*(from|import)\s+oracle\b", text, flags=re.M), fn
                 assert "macr_oracle" not in text, fn
+
+
+def test_mode_constants_match_the_header():
+    """MACR_TRAIN_* of include/macr_b200.h == the constants the Python host passes."""
+    from macr_b200 import ops
+
+    defs = dict(re.findall(r"#define\s+(MACR_TRAIN_[A-Z0-9]+)\s+(\d+)", open(HEADER).read()))
+    assert set(defs) == {"MACR_TRAIN_RUBIBCEBOTH", "MACR_TRAIN_NORMALBCE", "MACR_TRAIN_RUBIBCE"}
+    for cls in (ops.MFTrainer, ops.LGCNTrainer):
+        assert (cls.RUBIBCEBOTH, cls.NORMALBCE, cls.RUBIBCE) == tuple(
+            int(defs[k]) for k in ("MACR_TRAIN_RUBIBCEBOTH", "MACR_TRAIN_NORMALBCE", "MACR_TRAIN_RUBIBCE"))
