@@ -141,11 +141,19 @@ class LGCNEvaluator:
             all_result.append(res)
             count += len(res)
         assert count == len(users_to_test)  # batch_test.py:139
-        all_result = np.concatenate(all_result, axis=0)
-        K = max_top
-        all_result[:, 2 * K:3 * K] = (all_result[:, K:2 * K] != 0).astype(np.float32)  # :143-149
-        final = np.mean(all_result, axis=0).reshape(5, K)[:, top_show - 1]            # :151-157
-        return {"hr": final[2].copy(), "recall": final[1].copy(), "ndcg": final[3].copy()}
+        return lgcn_result_from_curves(np.concatenate(all_result, axis=0), top_show)
+
+
+def lgcn_result_from_curves(all_result, top_show):
+    """batch_test.py:141-161: per-user fold-out curves float32 [n, 5*K] -> the reported dict.  Slot 2
+    (ap in the C++ evaluator) is overwritten with `recall@k != 0`, i.e. the hit ratio; then the
+    user mean, taken at the cut-offs `top_show` (= sorted Ks)."""
+    all_result = np.array(all_result, dtype=np.float32, copy=True)
+    top_show = np.asarray(top_show)
+    K = all_result.shape[1] // 5
+    all_result[:, 2 * K:3 * K] = (all_result[:, K:2 * K] != 0).astype(np.float32)  # :143-149
+    final = np.mean(all_result, axis=0).reshape(5, K)[:, top_show - 1]            # :151-157
+    return {"hr": final[2].copy(), "recall": final[1].copy(), "ndcg": final[3].copy()}
 
 
 def eval_score_matrix_foldout(score_matrix, test_items, top_k=20, thread_num=None, device="cuda:0"):

@@ -12,6 +12,9 @@ What is produced (all from reference code, none from this repo's implementation)
   ref_evaluator.npz        the reference's C++ evaluator (oracle/_ref, built from
                            evaluator/cpp/include/*.h) on a seeded score matrix
   parser_defaults.json     defaults of macr_mf/parse.py and macr_lightgcn/utility/parser.py
+  lgcn_test.npz            macr_lightgcn/utility/batch_test.py's own test() (:26-162: train items := -inf,
+                           the C++ evaluator -- here the reference's, oracle/_ref --, the hit-ratio rewrite
+                           of slot 2, the user mean at the cut-offs Ks) on seeded score matrices of `tiny`
   mf_metrics.npz           macr_mf/train.py's own ranklist_by_sorted + get_performance (:32-117) on a
                            seeded score matrix (the functions are compiled from the reference file at
                            generation time -- the module itself imports tensorflow and cannot be loaded)
@@ -169,6 +172,54 @@ def run_evaluator(out):
                                 truth=np.concatenate(truth), rankings=rk, results=res)
 
 
+def run_lgcn_test(workdir, out):
+    """Executes the reference's OWN LightGCN `test()` (utility/batch_test.py:26-162).  The module
+    parses flags, loads data and imports the Cython evaluator on import, so `test` is lifted out of
+    its syntax tree and compiled as it stands into a namespace holding the reference's own `Data`
+    object, the reference's own C++ evaluator (oracle/_ref) and a session stub that returns seeded
+    score matrices."""
+    import ast
+    import heapq
+
+    from oracle import ref_eval
+
+    mod = load_module("ref_lgcn_load_data_t", os.path.join(REF, "macr_lightgcn", "utility", "load_data.py"))
+    data = mod.Data(path=os.path.join(workdir, "data", "tiny"), batch_size=16,
+                    args=types.SimpleNamespace(valid_set="test"))
+    path = os.path.join(REF, "macr_lightgcn", "utility", "batch_test.py")
+    tree = ast.parse(open(path).read(), filename=path)
+    body = [n for n in tree.body if isinstance(n, ast.FunctionDef) and n.name == "test"]
+    assert len(body) == 1
+    ns = {"np": np, "heapq": heapq, "data_generator": data, "BATCH_SIZE": 16, "ITEM_NUM": data.n_items,
+          "USR_NUM": data.n_users, "args": types.SimpleNamespace(layer_size="[64,64]"),
+          "eval_score_matrix_foldout": ref_eval.eval_score_matrix_foldout}
+    exec(compile(ast.Module(body=body, type_ignores=[]), path, "exec"), ns)
+
+    rng = np.random.RandomState(55)
+    mats = {"batch_ratings": rng.randn(data.n_users, data.n_items).astype(np.float32),
+            "rubi_ratings_both": rng.randn(data.n_users, data.n_items).astype(np.float32)}
+
+    class Model:
+        Ks = [20, 5]  # unsorted on purpose: test() sorts them (:30)
+        users, pos_items, node_dropout, mess_dropout = "users", "pos_items", "node_dropout", "mess_dropout"
+        batch_ratings, rubi_ratings_both = "batch_ratings", "rubi_ratings_both"
+
+    class Sess:
+        def run(self, fetch, feed):
+            return mats[fetch][np.asarray(feed["users"], dtype=np.int64)].copy()
+
+    users_to_test = list(data.test_set.keys())
+    cwd = os.getcwd()
+    os.chdir(workdir)  # test() writes Lightgcn_macr.txt into the cwd (:116-117)
+    try:
+        res = {m: ns["test"](Sess(), Model(), users_to_test, method=m) for m in ("normal", "rubiboth")}
+    finally:
+        os.chdir(cwd)
+    out["lgcn_test"] = dict(users_to_test=np.array(users_to_test, np.int32), Ks=np.array(Model.Ks),
+                            batch_ratings=mats["batch_ratings"], rubi_ratings_both=mats["rubi_ratings_both"],
+                            **{f"{m}_{k}": np.asarray(v, np.float64) for m, r in res.items() for k, v in r.items()})
+
+
 def run_mf_metrics(out):
     """Executes the reference's OWN metric functions (macr_mf/train.py:32-117).  train.py imports
     tensorflow at the top, so the function definitions are lifted out of its syntax tree and
@@ -242,6 +293,7 @@ def main():
         run_lgcn(work, digests, out)
         run_evaluator(out)
         run_mf_metrics(out)
+        run_lgcn_test(work, out)
         for name, d in out.items():
             np.savez_compressed(os.path.join(HERE, name + ".npz"), **d)
         with open(os.path.join(HERE, "digests.json"), "w") as f:

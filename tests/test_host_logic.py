@@ -49,6 +49,38 @@ def test_mf_evaluation_matches_the_references_own_functions(oracle):
         np.testing.assert_allclose(got_p[k] / len(test), want[k], rtol=1e-12, atol=1e-15, err_msg=k)
 
 
+def test_lgcn_evaluation_matches_the_references_own_test_function(oracle):
+    """tests/golden/lgcn_test.npz holds the outputs of macr_lightgcn/utility/batch_test.py's OWN
+    test() (:26-162), run by tests/golden/make_golden.py with the reference's own Data object and
+    C++ evaluator on seeded score matrices of the `tiny` data set.  Pins the whole evaluation
+    chain around the score matrix: train items := -inf, top-K, fold-out curves (oracle), the
+    hit-ratio rewrite and the user mean at the cut-offs (product: lgcn_result_from_curves), with
+    the product's own loader supplying the train / test lists."""
+    import os
+    import types
+
+    from macr_b200.host.data_lgcn import Data
+
+    gold = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+    g = np.load(os.path.join(gold, "lgcn_test.npz"))
+    data = Data(os.path.join(gold, "tiny"), 16, types.SimpleNamespace(valid_set="test"))
+    users = g["users_to_test"].tolist()
+    assert users == list(data.test_set.keys())  # same users, same order as the reference's loader
+    Ks = np.sort(g["Ks"])
+    K = int(Ks.max())
+    mrp, mcol = data.train_csr(users)
+    trp, tcol = data.truth_csr(users)
+    for method, fetch in (("normal", "batch_ratings"), ("rubiboth", "rubi_ratings_both")):
+        rate = g[fetch][users].copy()
+        for i in range(len(users)):  # batch_test.py:124-129
+            rate[i, mcol[mrp[i]:mrp[i + 1]]] = -np.inf
+        curves = oracle.foldout_metrics(oracle.topk_rows(rate, K), trp, tcol)
+        got = evaluate.lgcn_result_from_curves(curves, Ks)
+        for k in ("hr", "recall", "ndcg"):
+            np.testing.assert_allclose(got[k], g[f"{method}_{k}"], rtol=1e-6, atol=1e-7, err_msg=f"{method} {k}")
+    assert got["hr"].dtype == np.float32 and got["hr"].shape == (2,)
+
+
 def test_host_topk_masks_and_breaks_ties_by_id():
     rate = np.array([[1.0, 3.0, 3.0, 2.0, 0.5], [5.0, 4.0, 3.0, 2.0, 1.0]], np.float32)
     mrp, mcol = np.array([0, 1, 4], np.int32), np.array([1, 0, 1, 2], np.int32)
