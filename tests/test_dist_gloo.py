@@ -152,3 +152,25 @@ def test_row_sharded_training_plumbing_world2(tmp_path, oracle):
     world = 2
     mp.spawn(_train_worker, args=(world, _free_port(), str(tmp_path)), nprocs=world, join=True)
     assert all(os.path.exists(tmp_path / f"train_ok{r}") for r in range(world))
+
+
+def test_row_sharded_trainer_world1_needs_no_process_group(oracle):
+    """world = 1: no collective, the whole tables are local, ghost rows exist but are never read."""
+    from helpers import make_batch
+    from macr_b200.host import dist as mdist
+
+    n_users, n_items, B = 37, 29, 48
+    U, I, w, wu = make_model(17, n_users, n_items, scale=4.0)
+    hp = oracle.HParams.make(lr=1e-2, alpha=1e-2, beta=1e-3, decay=1e-3, batch_size=B)
+    sh = mdist.RowShardedMFTrainer(U, I, w, wu, hp, B, rank=0, world=1, device="cpu", ops_module=_OracleOps)
+    single = oracle.MFState(U, I, w, wu)
+    rng = np.random.RandomState(18)
+    for _ in range(3):
+        u, p, n = make_batch(rng, n_users, n_items, B)
+        want = oracle.mf_step(single, u, p, n, hp)
+        got = sh.step_device(*(torch.from_numpy(np.asarray(x, np.int32)) for x in (u, p, n)))
+        np.testing.assert_array_equal(got.numpy(), want)
+    loc = sh.local_tables()
+    np.testing.assert_array_equal(loc["U"].numpy(), single.U)
+    np.testing.assert_array_equal(loc["vI"].numpy(), single.vI)
+    assert (sh.u_lo, sh.u_hi, sh.i_lo, sh.i_hi) == (0, n_users, 0, n_items)
