@@ -8,6 +8,7 @@ What is produced (all from reference code, none from this repo's implementation)
   mf_sampler.npz           macr_mf/load_data.py Data.sample()      (:543-566) on tiny + addressa digests
   lgcn_sampler.npz         macr_lightgcn/utility/load_data.py Data.sample() (:174-212)
   lgcn_adj_tiny.npz        Data.get_adj_mat() `pre` adjacency (:95-124) of tiny, full CSR
+  lgcn_adj_variants_tiny.npz  the plain / norm / mean members of the same 4-tuple (:126-164)
   digests.json             sha1 / statistics of the same objects on the real addressa data
   ref_evaluator.npz        the reference's C++ evaluator (oracle/_ref, built from
                            evaluator/cpp/include/*.h) on a seeded score matrix
@@ -130,11 +131,20 @@ def run_lgcn(workdir, digests, out):
     out["lgcn_sampler"] = dict(n_users=data.n_users, n_items=data.n_items, n_train=data.n_train,
                                n_test=data.n_test, exist_users=np.array(data.exist_users, np.int64),
                                b1=np.array(b1, np.int64), b2=np.array(b2, np.int64))
-    _, _, _, pre = data.get_adj_mat()
+    plain, norm, mean, pre = data.get_adj_mat()
     pre = pre.tocsr()
     pre.sort_indices()
     out["lgcn_adj_tiny"] = dict(indptr=pre.indptr.astype(np.int32), indices=pre.indices.astype(np.int32),
                                 data=pre.data.astype(np.float32), shape=np.array(pre.shape))
+    # the other members of the 4-tuple (--adj_type plain | norm | gcmc, LightGCN.py:666-681); the
+    # reference's `norm` is float64, the session feeds float32 (LightGCN.py:537-540)
+    variants = {}
+    for name, M in (("plain", plain), ("norm", norm), ("mean", mean)):
+        M = M.tocsr()
+        M.sort_indices()
+        variants.update({name + "_indptr": M.indptr.astype(np.int32), name + "_indices": M.indices.astype(np.int32),
+                         name + "_data": M.data.astype(np.float32)})
+    out["lgcn_adj_variants_tiny"] = variants
     adir = os.path.join(workdir, "data", "addressa")
     if os.path.isdir(adir):
         data = mod.Data(path=adir, batch_size=1024, args=args)

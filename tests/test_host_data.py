@@ -68,6 +68,25 @@ def test_lgcn_loader_sampler_adjacency_tiny():
     assert M[7].nnz == 0
 
 
+def test_lgcn_adjacency_variants_tiny():
+    """--adj_type plain | norm | gcmc (LightGCN.py:666-681): the other three members of
+    get_adj_mat()'s 4-tuple (load_data.py:126-164) against the reference's own, bit for bit in the
+    float32 the session feeds."""
+    from macr_b200.host.data_lgcn import Data
+
+    g = np.load(os.path.join(GOLD, "lgcn_adj_variants_tiny.npz"))
+    data = Data(os.path.join(GOLD, "tiny"), 16, types.SimpleNamespace(valid_set="test"))
+    for ref_name, adj_type in (("plain", "plain"), ("norm", "norm"), ("mean", "gcmc")):
+        rowptr, col, val = data.adj_csr(adj_type)
+        np.testing.assert_array_equal(rowptr, g[ref_name + "_indptr"], err_msg=adj_type)
+        np.testing.assert_array_equal(col, g[ref_name + "_indices"], err_msg=adj_type)
+        np.testing.assert_array_equal(val, g[ref_name + "_data"], err_msg=adj_type)
+    # the default branch (any other --adj_type): mean + I
+    rowptr, col, val = data.adj_csr("anything")
+    n = len(rowptr) - 1
+    assert len(val) == len(g["mean_data"]) + n
+
+
 def test_lgcn_sample_test_runs_and_excludes_known_items():
     from macr_b200.host.data_lgcn import Data
 
