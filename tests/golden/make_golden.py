@@ -7,6 +7,7 @@ What is produced (all from reference code, none from this repo's implementation)
   tiny/{train,test}.txt    a synthetic data set in the reference's text format (seeded here)
   mf_sampler.npz           macr_mf/load_data.py Data.sample()      (:543-566) on tiny + addressa digests
   lgcn_sampler.npz         macr_lightgcn/utility/load_data.py Data.sample() (:174-212)
+  lgcn_sample_test.npz     Data.sample_test() (:213-257), run with random.sample's pre-3.11 Set handling
   lgcn_adj_tiny.npz        Data.get_adj_mat() `pre` adjacency (:95-124) of tiny, full CSR
   lgcn_adj_variants_tiny.npz  the plain / norm / mean members of the same 4-tuple (:126-164)
   digests.json             sha1 / statistics of the same objects on the real addressa data
@@ -131,6 +132,21 @@ def run_lgcn(workdir, digests, out):
     out["lgcn_sampler"] = dict(n_users=data.n_users, n_items=data.n_items, n_train=data.n_train,
                                n_test=data.n_test, exist_users=np.array(data.exist_users, np.int64),
                                b1=np.array(b1, np.int64), b2=np.array(b2, np.int64))
+    # sample_test() (:213-257) calls random.sample on dict keys: a TypeError since Python 3.11.  Up to
+    # 3.10 random.sample turned any Set into tuple(population) first; with exactly that conversion
+    # restored the reference's own code runs and is pinned here.
+    import collections.abc
+
+    orig_sample = random.sample
+    random.sample = lambda pop, k: orig_sample(tuple(pop) if isinstance(pop, collections.abc.Set) else pop, k)
+    try:
+        random.seed(4321)
+        np.random.seed(4321)
+        t1 = data.sample_test()
+        t2 = data.sample_test()
+    finally:
+        random.sample = orig_sample
+    out["lgcn_sample_test"] = dict(t1=np.array(t1, np.int64), t2=np.array(t2, np.int64))
     plain, norm, mean, pre = data.get_adj_mat()
     pre = pre.tocsr()
     pre.sort_indices()

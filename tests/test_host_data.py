@@ -87,6 +87,21 @@ def test_lgcn_adjacency_variants_tiny():
     assert len(val) == len(g["mean_data"]) + n
 
 
+def test_lgcn_sample_test_matches_reference():
+    """Data.sample_test() (load_data.py:213-257) against the reference's own code (run by
+    make_golden.py with random.sample's pre-3.11 handling of dict keys): native sampler and the
+    Python restatement, both bit-exact, two consecutive batches."""
+    from macr_b200.host.data_lgcn import Data
+
+    g = np.load(os.path.join(GOLD, "lgcn_sample_test.npz"))
+    data = Data(os.path.join(GOLD, "tiny"), 16, types.SimpleNamespace(valid_set="test"))
+    for fn in (data.sample_test, data.sample_test_py):
+        random.seed(4321)
+        np.random.seed(4321)
+        np.testing.assert_array_equal(np.array(fn(), np.int64), g["t1"])
+        np.testing.assert_array_equal(np.array(fn(), np.int64), g["t2"])
+
+
 def test_lgcn_sample_test_runs_and_excludes_known_items():
     from macr_b200.host.data_lgcn import Data
 
