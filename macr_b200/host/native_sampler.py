@@ -59,8 +59,17 @@ def _np_restore(buf, meta):
     np.random.set_state((meta[0], buf[:624].copy(), int(buf[624]), meta[1], meta[2]))
 
 
+def _check_population(B, n_users, n_pop):
+    """`random.sample(pop, B)` of the reference (taken when B <= n_users) raises ValueError when
+    the population is smaller than B (users without a train line are not in it): same error here,
+    before any generator state moves."""
+    if B <= n_users and B > n_pop:
+        raise ValueError("Sample larger than population or is negative")
+
+
 def sample_mf(users_pop, n_users, n_items, csr, B):
     """-> (users, pos, neg) int32 arrays; advances `random` exactly like load_data.py:543-566."""
+    _check_population(B, n_users, len(users_pop))
     st, meta = _py_state()
     out = np.empty((3, B), np.int32)
     check(lib().macr_sample_mf(_p(st), _p(users_pop), len(users_pop), n_users, n_items,
@@ -73,6 +82,7 @@ def sample_mf(users_pop, n_users, n_items, csr, B):
 def sample_mf_epoch(users_pop, n_users, n_items, csr, B, n_batches, out=None):
     """n_batches consecutive `sample()` calls in one go -> int32 [n_batches, 3, B] (the layout
     `MFTrainer.run_host` takes); the generator state crosses the boundary once."""
+    _check_population(B, n_users, len(users_pop))
     st, meta = _py_state()
     if out is None:
         out = np.empty((n_batches, 3, B), np.int32)
@@ -86,6 +96,7 @@ def sample_mf_epoch(users_pop, n_users, n_items, csr, B, n_batches, out=None):
 
 
 def sample_lgcn_epoch(users_pop, n_users, n_items, pos_csr, ban_csr, B, n_batches, out=None):
+    _check_population(B, n_users, len(users_pop))
     st, meta = _py_state()
     nst, nmeta = _np_state()
     if out is None:
@@ -102,6 +113,7 @@ def sample_lgcn_epoch(users_pop, n_users, n_items, pos_csr, ban_csr, B, n_batche
 
 def sample_lgcn(users_pop, n_users, n_items, pos_csr, ban_csr, B):
     """-> (users, pos, neg); advances `random` and `np.random` like utility/load_data.py:174-212."""
+    _check_population(B, n_users, len(users_pop))
     st, meta = _py_state()
     nst, nmeta = _np_state()
     out = np.empty((3, B), np.int32)
