@@ -199,6 +199,49 @@ def cpu_step_baseline(steps, threads=None):
     return BATCH / (ms * 1e-3), ms, threads
 
 
+def cpu_scoring_baseline(sample_users=2048, reps=3):
+    """The reference's CPU evaluation path on a bounded sample of the scoring workload:
+    score matrix = ((U I^T) - c) * sig(I w)^T * sig(U w_user) with numpy (BLAS SGEMM + element-wise
+    passes stand in for TF's CPU kernels, model.py:45,199), train items := -inf
+    (batch_test.py:124-129), then the reference's OWN C++ evaluator (top-K + fold-out curves,
+    compiled from /root/reference into oracle/_ref) with its default 5 x cores threads.  Falls back
+    to the oracle port's fused scorer when oracle/_ref is not on the box."""
+    import oracle
+    from oracle import ref_eval
+
+    oracle.build()
+    cores = os.cpu_count() or 1
+    Us, Is, ws_, wus = synth_model(777)
+    Us, Is = Us * 10, Is * 10
+    q = np.random.RandomState(5).permutation(N_USERS)[:sample_users]
+    Uq = np.ascontiguousarray(Us[q])
+    mrp, mcol = synth_mask(9, sample_users, 27)
+    truth = [np.sort(np.random.RandomState(11 + t).randint(0, N_ITEMS, 5)).astype(np.int32)
+             for t in range(sample_users)]
+    sig = lambda x: (1.0 / (1.0 + np.exp(-x))).astype(np.float32)
+    kind = "reference" if ref_eval.available() else "port"
+    times = []
+    for _ in range(reps + 1):
+        t0 = time.perf_counter()
+        if kind == "reference":
+            rate = ((Uq @ Is.T) - np.float32(40.0)) * sig(Is @ ws_)[None, :] * sig(Uq @ wus)[:, None]
+            for t in range(sample_users):
+                rate[t, mcol[mrp[t]:mrp[t + 1]]] = -np.inf
+            ref_eval.eval_score_matrix_foldout(rate, truth, TOPK)
+        else:
+            oracle.set_threads(cores)
+            oracle.score_topk(Uq, Is, oracle.score_gates(Is, ws_), oracle.score_gates(Uq, wus), 40.0,
+                              mrp, mcol, TOPK)
+        times.append(time.perf_counter() - t0)
+    t = float(np.mean(times[1:]))  # first pass is the warm-up
+    return {"value": sample_users * N_ITEMS / t, "unit": "scores/s", "cores": cores, "kind": kind,
+            "ms_per_eval_of_sample": 1e3 * t,
+            "sample": f"{sample_users} of the {N_TEST_USERS} test users x {N_ITEMS} items, {reps} passes after "
+                      "1 warm-up; numpy SGEMM + gates + train-item mask, then the reference's C++ "
+                      "top-K / fold-out evaluator (5 x cores threads)" if kind == "reference" else
+                      f"{sample_users} test users x {N_ITEMS} items through the oracle's fused scorer"}
+
+
 def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
@@ -524,6 +567,11 @@ def main():
         cv, cms, cth = cpu_step_baseline(8)
         cpu = {"value": cv, "unit": "interactions/s", "cores": cth, "kind": "port",
                "ms_per_step": cms, "sample": "8 steps of the same B=4096 workload after 1 warm-up step"}
+        if scoring is not None:
+            try:  # a reported baseline: never allowed to take the bench line down
+                scoring["cpu_baseline"] = cpu_scoring_baseline()
+            except Exception as e:  # noqa: BLE001
+                scoring["cpu_baseline"] = {"unavailable": f"{type(e).__name__}: {e}"}
 
     if rank == 0:
         line = {
