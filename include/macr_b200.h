@@ -292,12 +292,15 @@ int macr_score_topk(const float *Uq, int T, const float *It, int64_t n_items, in
                     int32_t *out_ids, float *out_scores,
                     void *ws, size_t ws_bytes, macr_stream_t stream);
 /* Same contract and bit-identical results as macr_score_topk, computed on the tensor cores:
- * two TMA-fed tcgen05 (kind::tf32, accumulator in TMEM) passes over the T x n_items tile grid
- * -- per-batch maxima -> a proven per-row threshold -> candidate filter -- then an exact fp32
- * re-rank of the ~1.5 K candidates per row; rows whose candidate list overflows are re-done by
- * the exact kernel (macr_b200/csrc/score_tc.cu).  Needs 2048 <= n_items <~ 1.5 M per call
- * (smaller catalogues: macr_score_topk; larger: shard).  ws must be 1024-byte aligned.  stats (nullable, device int64[2]) is
- * incremented by {rows re-done by the exact kernel, candidates re-ranked}. */
+ * two TMA-fed tcgen05 (kind::f16, bf16 operands, fp32 accumulators in TMEM) passes over the
+ * T x n_items tile grid -- per-batch maxima -> a proven per-row threshold -> candidate filter
+ * (train items of the row are masked inside the pass: mask columns MUST ascend inside a row) --
+ * then an exact fp32 re-rank of the few dozen candidates per row.  Rows whose candidate list
+ * overflows, rows without K unmasked groups and rows whose train list exceeds 1/16 of the
+ * catalogue are done by the exact kernel (macr_b200/csrc/score_tc.cu, score.cu).  Needs
+ * 2048 <= n_items <~ 1.5 M per call (smaller catalogues: macr_score_topk; larger: shard).
+ * ws must be 1024-byte aligned.  stats (nullable, device int64[2]) is incremented by
+ * {rows done by the exact kernel, candidates re-ranked}. */
 size_t macr_score_topk_tc_workspace_bytes(int T, int64_t n_items, int K);
 int macr_score_topk_tc(const float *Uq, int T, const float *It, int64_t n_items, int d,
                        const float *sig_i, const float *sig_u, float c,
