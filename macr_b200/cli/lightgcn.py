@@ -64,6 +64,7 @@ def main(argv=None, tune=False):
         raise SystemExit(f"--alg_type {args.alg_type} --loss {args.loss}: only lightgcn with bceboth (MACR), bce1 "
                          "(item gate only) or bce (the README's baseline) is implemented on the B200 path "
                          "(DESIGN.md section 8)")
+    flags.check_device_limits(args.batch_size, flags.as_list(args.Ks))
     data_generator = Data(path=args.data_path + args.dataset, batch_size=args.batch_size, args=args)
     seed = 12345  # LightGCN.py:651-655
     random.seed(seed)
@@ -101,6 +102,32 @@ def main(argv=None, tune=False):
         "-".join(str(r) for r in flags.as_list(args.regs)))
     if args.save_flag == 1:
         os.makedirs(weights_save_path, exist_ok=True)
+
+    if args.pretrain not in (0, -1, 1):
+        raise SystemExit(f"--pretrain {args.pretrain}: only 0, -1 (pretrained embeddings) and 1 (restore + test) exist")
+    if args.pretrain == 1:
+        # LightGCN.py:707-719 restores a hard-coded "Your Path" and tests c in [0, best_c]; here the
+        # file is $MACR_MODEL_FILE or the newest weights_<saveID>-<epoch>.npz under the save path
+        import glob
+
+        model_file = os.environ.get("MACR_MODEL_FILE") or next(iter(sorted(
+            glob.glob(weights_save_path + "/weights_{}-*.npz".format(args.saveID)),
+            key=lambda f: int(f.rsplit("-", 1)[1][:-4]), reverse=True)), None)
+        if not model_file:
+            raise SystemExit("--pretrain 1: no checkpoint (set MACR_MODEL_FILE or train with --save_flag 1)")
+        checkpoint.load(model_file, model, restore_rng=False)
+        users_to_test = list(data_generator.test_set.keys())
+        ret = None
+        for c in [0, args.c]:
+            model.update_c(sess, c)
+            ret = evaluator.test(sess, model, users_to_test, method="rubiboth")
+            print("c:{}: recall={}, hit={}, ndcg={}".format(c, str(ret["recall"]), str(ret["hr"]), str(ret["ndcg"])))
+        model.close()
+        return {"last": ret, "model_file": model_file}
+    if args.only_test != 0:  # LightGCN.py:752 gates the whole training loop on only_test == 0
+        print("--only_test %d: training loop skipped (LightGCN.py:752)" % args.only_test)
+        model.close()
+        return {"best_epoch": 0, "best_hr": 0.0, "last": None}
 
     if args.loss == "bce":  # LightGCN.py:592-593,625-626
         train_fetch = [model.opt_bce, model.loss_bce, model.mf_loss_bce, model.emb_loss_bce, model.reg_loss_bce]

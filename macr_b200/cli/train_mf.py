@@ -49,6 +49,7 @@ def main(argv=None, tune=False):
         raise SystemExit(f"--model {args.model}: only mf is on the MACR hot path")
     data = Data(args)
     Ks = flags.as_list(args.Ks)
+    flags.check_device_limits(args.batch_size, Ks)
     seed = 12345  # train.py:333-337 (after Data() is built; Data.__init__ draws nothing)
     random.seed(seed)
     os.environ["PYTHONHASHSEED"] = str(seed)

@@ -12,7 +12,7 @@ import random
 import numpy as np
 import scipy.sparse as sp
 
-from .data_mf import lists_to_csr
+from .data_mf import cached_sorted_csr, lists_to_csr
 
 
 class Data:
@@ -205,7 +205,7 @@ class Data:
 
     # ---- CSR views for the device-side evaluation -----------------------------------------------
     def train_csr(self, users):
-        return lists_to_csr([self.train_items.get(u, []) for u in users], len(users))
+        return cached_sorted_csr(self, "_train_sorted", self.train_items, users)
 
     def truth_csr(self, users):
         return lists_to_csr([self.test_set.get(u, []) for u in users], len(users), sort_unique=False)

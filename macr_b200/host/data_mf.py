@@ -42,6 +42,21 @@ def lists_to_csr(lists, n_rows, sort_unique=True):
     return rowptr.astype(np.int32), np.ascontiguousarray(col, np.int32)
 
 
+def cached_sorted_csr(owner, attr, lists, users):
+    """CSR of `np.unique(lists[u])` for `users`; the per-user sorted arrays are computed once per
+    Data object (every evaluation re-reads the same train lists)."""
+    cache = owner.__dict__.setdefault(attr, {})
+    cols, rowptr = [], np.zeros(len(users) + 1, np.int64)
+    for r, u in enumerate(users):
+        a = cache.get(u)
+        if a is None:
+            a = cache[u] = np.unique(np.asarray(lists.get(u, ()), np.int32))
+        cols.append(a)
+        rowptr[r + 1] = rowptr[r] + a.size
+    col = np.concatenate(cols) if cols else np.zeros(0, np.int32)
+    return rowptr.astype(np.int32), np.ascontiguousarray(col, np.int32)
+
+
 class Data:
     """`Data(args)` of macr_mf/load_data.py:504-541 restricted to the hot path's configuration
     (`--data_type ori --source normal --model mf`, load_data.py:26-118)."""
@@ -150,7 +165,7 @@ class Data:
     def train_csr(self, users):
         """train items of `users` (sorted unique global item ids): the top-K exclusion mask,
         i.e. `all_items - set(training_items)` of train.py:132-133."""
-        return lists_to_csr([self.train_user_list.get(u, []) for u in users], len(users))
+        return cached_sorted_csr(self, "_train_sorted", self.train_user_list, users)
 
     def truth_csr(self, users, valid_set="test"):
         src = self.test_user_list if valid_set == "test" else self.valid_user_list

@@ -35,18 +35,22 @@ def _batches(seq, size):
 # ------------------------------------------------------------------------------------------------
 # MF: precision / recall / ndcg / hit_ratio @Ks in float64 (train.py:32-117)
 # ------------------------------------------------------------------------------------------------
-def mf_metrics_from_hits(hits, n_pos, Ks):
+def mf_metrics_from_hits(hits, n_pos, Ks, n_ranked=None):
     """hits [T, Kmax] 0/1 in rank order, n_pos [T] = len(user_pos_test) -> dict of sums over users
-    of the per-user metrics (train.py:106-117; dcg at :44-57, ndcg_at_k method 1 at :60-75)."""
+    of the per-user metrics (train.py:106-117; dcg at :44-57, ndcg_at_k method 1 at :60-75).
+    n_ranked [T]: length of the user's rank list (< Kmax when fewer unmasked items exist);
+    `precision_at_k` is `np.mean(r[:k])` (train.py:32-36), i.e. divides by min(k, len(r))."""
     hits = np.asarray(hits, dtype=np.float64)
     n_pos = np.asarray(n_pos, dtype=np.float64)
+    n_ranked = np.full(hits.shape[0], hits.shape[1], np.float64) if n_ranked is None else \
+        np.asarray(n_ranked, dtype=np.float64)
     out = {k: np.zeros(len(Ks)) for k in ("precision", "recall", "ndcg", "hit_ratio")}
     Kmax = hits.shape[1]
     discount = 1.0 / np.log2(np.arange(2, Kmax + 2))
     for j, K in enumerate(Ks):
         h = hits[:, :K]
         got = h.sum(1)
-        out["precision"][j] = np.sum(got / K)
+        out["precision"][j] = np.sum(got / np.maximum(np.minimum(n_ranked, K), 1.0))
         out["recall"][j] = np.sum(got / n_pos)
         dcg = (h * discount[:K]).sum(1)
         ideal = np.minimum(n_pos, K).astype(np.int64)
@@ -86,7 +90,8 @@ class MFEvaluator:
                                 {model.users: user_batch, model.pos_items: range(self.data.n_items)})
                 ids = host_topk(rate, mrp, mcol, Kmax)
             truth = [truth_of[u] for u in user_batch]
-            part = mf_metrics_from_hits(_hits(ids, truth), [len(t) for t in truth], self.Ks)
+            part = mf_metrics_from_hits(_hits(ids, truth), [len(t) for t in truth], self.Ks,
+                                        n_ranked=(np.asarray(ids) >= 0).sum(1))
             for k in sums:
                 sums[k] += part[k]
             count += len(user_batch)

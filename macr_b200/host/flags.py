@@ -80,3 +80,15 @@ def as_list(text):
     """`eval(args.Ks)` of the reference, without eval."""
     value = ast.literal_eval(text) if isinstance(text, str) else text
     return list(value) if isinstance(value, (list, tuple)) else [value]
+
+
+MAX_BATCH, MAX_TOPK = 8192, 32  # macr_*_trainer_create (csrc/trainer.cu), kMaxKFast / the tcgen05 re-rank (csrc/score*.cu)
+
+
+def check_device_limits(batch_size, Ks):
+    """Fail at start-up, not at the first step / first evaluation, when a flag exceeds what the
+    device path was built for."""
+    if not 0 < int(batch_size) <= MAX_BATCH:
+        raise SystemExit(f"--batch_size {batch_size}: the B200 step supports 1..{MAX_BATCH}")
+    if max(Ks) > MAX_TOPK or min(Ks) < 1:
+        raise SystemExit(f"--Ks {list(Ks)}: the fused top-K supports cut-offs in 1..{MAX_TOPK}")

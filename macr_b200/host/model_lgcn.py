@@ -68,11 +68,13 @@ class LightGCN(_ScoringMixin):
         else:
             U, I, w, wu = init_weights(self.n_users, self.n_items, self.emb_dim,
                                        getattr(args, "init_seed", 12345), getattr(args, "init_npz", ""))
+        if not 0 < int(self.batch_size) <= 8192:
+            raise ops.MacrError(f"batch_size {self.batch_size}: the B200 step supports 1..8192")
         self.hp = ops.HParams.make(lr=self.lr, alpha=self.alpha, beta=self.beta, decay=self.decay,
                                    batch_size=self.batch_size)
         self.trainer = ops.LGCNTrainer(A.indptr.astype(np.int32), A.indices.astype(np.int32),
                                        A.data.astype(np.float32), U, I, w, wu, self.n_layers, self.hp,
-                                       max_batch=min(max(self.batch_size, 1), 8192), device=self.dev)
+                                       max_batch=self.batch_size, device=self.dev)
         for name in ("users", "pos_items", "neg_items", "node_dropout", "mess_dropout"):
             setattr(self, name, Placeholder(self, name))
         for name in _TRAIN + _TRAIN_BCE + _TRAIN_BCE1 + ("rubi_ratings_both", "rubi_ratings1", "batch_ratings"):

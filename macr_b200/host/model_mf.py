@@ -139,9 +139,11 @@ class BPRMF(_ScoringMixin):
         self.dev = torch.device("cuda", dev_index) if isinstance(dev_index, int) else torch.device(dev_index)
         U, I, w, wu = init_weights(self.n_users, self.n_items, self.emb_dim,
                                    getattr(args, "init_seed", 12345), getattr(args, "init_npz", ""))
+        if not 0 < int(self.batch_size) <= 8192:
+            raise ops.MacrError(f"batch_size {self.batch_size}: the B200 step supports 1..8192")
         self.hp = ops.HParams.make(lr=self.lr, alpha=self.alpha, beta=self.beta, decay=self.decay,
                                    batch_size=self.batch_size)
-        self.trainer = ops.MFTrainer(U, I, w, wu, self.hp, max_batch=min(max(self.batch_size, 1), 8192),
+        self.trainer = ops.MFTrainer(U, I, w, wu, self.hp, max_batch=self.batch_size,
                                      device=self.dev)
         for name in ("users", "pos_items", "neg_items"):
             setattr(self, name, Placeholder(self, name))

@@ -21,6 +21,18 @@ def test_mf_metrics_from_hits_matches_reference_arithmetic():
         np.testing.assert_allclose(got[k] / T, want[k], rtol=1e-12, atol=1e-15, err_msg=k)
 
 
+def test_mf_precision_divides_by_the_rank_list_length_for_short_lists():
+    """train.py:32-36: precision_at_k = np.mean(r[:k]); a user with fewer than K unmasked items has a
+    shorter r (padding ids -1 are not ranks), so the divisor is min(k, len(r))."""
+    ids = np.array([[4, 7, 9, -1, -1], [1, 2, 3, 5, 6]], np.int32)
+    truth = [[7, 9], [1]]
+    hits = evaluate._hits(ids, truth)
+    got = evaluate.mf_metrics_from_hits(hits, [2, 1], [2, 5], n_ranked=(ids >= 0).sum(1))
+    want_p = [np.mean([0, 1]) + np.mean([1, 0]), np.mean([0, 1, 1]) + np.mean([1, 0, 0, 0, 0])]
+    np.testing.assert_allclose(got["precision"], want_p, rtol=1e-15)
+    np.testing.assert_allclose(got["recall"], [0.5 + 1.0, 1.0 + 1.0], rtol=1e-15)
+
+
 def test_mf_evaluation_matches_the_references_own_functions(oracle):
     """tests/golden/mf_metrics.npz holds outputs of macr_mf/train.py's OWN ranklist_by_sorted +
     get_performance (:32-117), compiled from the reference file by tests/golden/make_golden.py.
