@@ -3,30 +3,29 @@
 
 Contract: `python bench.py --gpus N --steps K --warmup W [--impl reference]` prints ONE JSON line.
 
-Workload at N=1 (BASELINE.json configs[1]): MACR-MF, Gowalla shapes (U=29 858, I=40 981, d=64),
-B=4096, `--train rubibceboth`, synthetic triples per SURVEY.md section 8(d):
-users = first B of rng.permutation(U), pos ~ Zipf(1.0) truncated to [0,I), neg ~ U[0,I), seed 12345.
+Headline workload (every N; STRONG scaling -- the same tables and the same batches at every N):
+BASELINE.json configs[4] shapes, 10 M users x 1 M items, d=64, B=8192, `--train rubibceboth`:
+8.45 GB of var/m/v, 16.9 GB of dense-Adam traffic per step (TF-1.14 semantics) -- the largest
+configuration that fits one GPU and the one where the fused step is HBM-bound.
 
-  value        device-resident throughput: batches pre-staged in HBM, one captured step graph per
-               step, CUDA events on the launching stream around the K steps; inputs larger than
-               L2: three independent models (326 MB of tables and Adam state) are stepped
-               round-robin, so every step finds its tables evicted.  `value_memset_flushed` is
-               the single-model step after a 256 MiB memset, `value_back_to_back` the single-model
-               replay with L2-resident tables (a real epoch at this size).
-  e2e          same steps through the epoch call with HOST buffers (`MFTrainer.run_host`): the K
-               batches sit in pinned host memory; H2D copy + K steps + D2H of the losses + stream
-               sync inside the timed region.  `per_step_call` is the session-style call
-               (`MFTrainer.step_pinned`: H2D + step + D2H + sync every step).
-  roofline     the Adam dense sweep (the HBM-bound kernel of the step), timed alone with CUDA
-               events, L2 flushed between launches; algorithmic bytes = 24*d*(U+I) per launch.
-  cpu_baseline the oracle port of the step (C + OpenMP) on this box's host cores, bounded sample.
-  scoring      full-catalogue counterfactual score + mask + top-20, scores/sec (T test users x I).
-
-N>1: the training step of this configuration does not shard profitably (a 40 us step), so the
-ranks run independent replicas ("replicas only", e.g. the c / alpha / beta sweep of tune.py) and
-`value` is their aggregate; `scoring` partitions the query users across the ranks (item table replicated, one
-all-gather of the [T,K] result); the item-partitioned layout (all-gather of per-shard candidates
-+ on-device merge) is timed beside it.
+  value        whole-job interactions/s, batches resident in HBM.  Both tables and their Adam slots
+               are row-partitioned over the N ranks (`RowShardedMFTrainer`): per step ONE exchange
+               of the batch's rows (fused NVLink push into the peers' ghost rows + flag barrier;
+               NCCL all-reduce if peer memory cannot be mapped) and the single-GPU step graph on
+               the local slice.  CUDA events around the K steps, max over ranks.  The tables are
+               far larger than L2 (8.45 GB / N per rank vs 126 MB).
+  e2e          the same K steps through `RowShardedMFTrainer.run_host` with HOST buffers: the ids
+               in pinned host memory, H2D + K exchanges/steps + D2H of the losses + sync, wall clock.
+  roofline     the Adam dense sweep (the HBM-bound kernel of the step) timed alone with CUDA events
+               on this rank's slice; `roofline.step` = the whole fused step against its algorithmic
+               bytes 24*64*(U+I) + 780*B + 3072 (north-star: >= 0.70 of the HBM peak).
+  scoring      full-catalogue counterfactual score + mask + top-20 of a FIXED query set (262 144
+               users x 1 M items) with the ITEM table partitioned over the ranks: local tcgen05
+               scoring of the shard, all-gather of the [T,K] candidates and the on-device K-way
+               merge inside the timed region.  `roofline.frac` counts ALGORITHMIC flops 2*64*T*I.
+  cpu_baseline the oracle port of the same step (C + OpenMP) on this box's host cores (N=1).
+  gowalla      (N=1 only) BASELINE configs[1]: gowalla shapes B=4096 -- the small-table regime where
+               the B x B grid (MUFU-bound) sets the pace; device value, e2e, kernel rooflines, scoring.
 """
 import argparse
 import json
@@ -41,49 +40,105 @@ import numpy as np
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
-N_USERS, N_ITEMS, D, BATCH = 29858, 40981, 64, 4096  # gowalla, README.md:40
+D, TOPK = 64, 20
+# ---- headline: BASELINE configs[4] shapes (SURVEY 8d config 5) ----
+_SCALE = float(os.environ.get("MACR_BENCH_SCALE", "1"))  # < 1 only for the CPU contract test / dry runs
+C5_USERS, C5_ITEMS, C5_BATCH = int(10_000_000 * _SCALE), int(1_000_000 * _SCALE), 8192
+C5_HP = dict(lr=1e-3, alpha=1e-3, beta=1e-3, decay=1e-5, batch_size=C5_BATCH)
+C5_QUERY = max(1024, int(262_144 * _SCALE))
+WORKLOAD = (f"MACR-MF synthetic {C5_USERS} users x {C5_ITEMS} items d=64 B=8192 rubibceboth alpha=1e-3 beta=1e-3 "
+            "regs=1e-5 lr=1e-3, tables + Adam slots row-partitioned over the GPUs (BASELINE configs[4] shapes"
+            + (")" if _SCALE == 1 else f", scaled by {_SCALE} via MACR_BENCH_SCALE)"))
+# ---- secondary: BASELINE configs[1] (gowalla shapes, README.md:40) ----
+N_USERS, N_ITEMS, BATCH = 29858, 40981, 4096
 N_TEST_USERS = 15424
-TOPK = 20
-HP = dict(lr=1e-3, alpha=1e-2, beta=1e-3, decay=1e-5, batch_size=BATCH)  # README.md:40
-N_BATCHES = 200
-WORKLOAD = ("MACR-MF gowalla-shape U=29858 I=40981 d=64 B=4096 rubibceboth alpha=1e-2 beta=1e-3 "
-            "regs=1e-5 lr=1e-3 (BASELINE configs[1])")
+HP = dict(lr=1e-3, alpha=1e-2, beta=1e-3, decay=1e-5, batch_size=BATCH)
+N_BATCHES = 64
+GOWALLA = "MACR-MF gowalla-shape U=29858 I=40981 d=64 B=4096 rubibceboth alpha=1e-2 beta=1e-3 (BASELINE configs[1])"
 
 
-def synth_model(seed):
+# ------------------------------------------------------------------------------------------------
+# synthetic inputs
+# ------------------------------------------------------------------------------------------------
+def synth_model(seed, n_users=N_USERS, n_items=N_ITEMS):
     rng = np.random.RandomState(seed)
-    lim_u, lim_i, lim_w = np.sqrt(6.0 / (N_USERS + D)), np.sqrt(6.0 / (N_ITEMS + D)), np.sqrt(6.0 / (D + 1))
-    U = rng.uniform(-lim_u, lim_u, (N_USERS, D)).astype(np.float32)
-    I = rng.uniform(-lim_i, lim_i, (N_ITEMS, D)).astype(np.float32)
+    lim_u, lim_i, lim_w = np.sqrt(6.0 / (n_users + D)), np.sqrt(6.0 / (n_items + D)), np.sqrt(6.0 / (D + 1))
+    U = rng.uniform(-lim_u, lim_u, (n_users, D)).astype(np.float32)
+    I = rng.uniform(-lim_i, lim_i, (n_items, D)).astype(np.float32)
     w = rng.uniform(-lim_w, lim_w, D).astype(np.float32)
     wu = rng.uniform(-lim_w, lim_w, D).astype(np.float32)
     return U, I, w, wu
 
 
-def synth_batches(seed, n):
+def zipf_cdf(n_items):
+    cdf = np.cumsum(1.0 / np.arange(1, n_items + 1, dtype=np.float64))
+    return cdf / cdf[-1]
+
+
+def synth_batches(seed, n, n_users=N_USERS, n_items=N_ITEMS, batch=BATCH):
+    """[n,3,B] int32: distinct users per batch, Zipf(1.0) positives, uniform negatives."""
     rng = np.random.RandomState(seed)
-    ranks = np.arange(1, N_ITEMS + 1, dtype=np.float64)
-    cdf = np.cumsum(1.0 / ranks)
-    cdf /= cdf[-1]
-    out = np.empty((n, 3, BATCH), np.int32)
+    cdf = zipf_cdf(n_items)
+    out = np.empty((n, 3, batch), np.int32)
     for s in range(n):
-        out[s, 0] = rng.permutation(N_USERS)[:BATCH]
-        out[s, 1] = np.minimum(np.searchsorted(cdf, rng.rand(BATCH)), N_ITEMS - 1)
-        out[s, 2] = rng.randint(0, N_ITEMS, BATCH)
+        if n_users <= 1_000_000:
+            out[s, 0] = rng.permutation(n_users)[:batch]
+        else:  # a permutation of 10 M ids per batch is wasteful: distinct ids from an oversampled draw
+            out[s, 0] = rng.permutation(np.unique(rng.randint(0, n_users, 2 * batch)))[:batch]
+        out[s, 1] = np.minimum(np.searchsorted(cdf, rng.rand(batch)), n_items - 1)
+        out[s, 2] = rng.randint(0, n_items, batch)
     return out
 
 
-def synth_mask(seed, n_rows, avg):
+def synth_mask(seed, n_rows, avg, n_items=N_ITEMS):
+    """train-item mask as CSR: Poisson(avg) sorted distinct items per row (vectorised)."""
     rng = np.random.RandomState(seed)
     cnt = np.maximum(1, rng.poisson(avg, n_rows)).astype(np.int64)
-    rowptr = np.zeros(n_rows + 1, np.int32)
-    rowptr[1:] = np.cumsum(cnt)
-    col = np.empty(rowptr[-1], np.int32)
-    for r in range(n_rows):
-        col[rowptr[r]:rowptr[r + 1]] = np.sort(rng.choice(N_ITEMS, size=cnt[r], replace=False))
-    return rowptr, col
+    row = np.repeat(np.arange(n_rows, dtype=np.int64), cnt)
+    key = np.unique(row * n_items + rng.randint(0, n_items, row.size))  # sorted by (row, item), distinct
+    rowptr = np.zeros(n_rows + 1, np.int64)
+    rowptr[1:] = np.cumsum(np.bincount(key // n_items, minlength=n_rows))
+    return rowptr.astype(np.int32), (key % n_items).astype(np.int32)
 
 
+class DeviceRows:
+    """[rows, 64] Xavier-uniform table generated on the device in fixed 2^18-row chunks, each from
+    its own seed, so any slice holds the same values whatever the number of ranks."""
+
+    CH = 1 << 18
+
+    def __init__(self, rows, seed, dev, scale=1.0):
+        self.shape, self.seed, self.dev = (rows, D), seed, dev
+        self.lim = float(np.sqrt(6.0 / (rows + D))) * scale
+
+    def __getitem__(self, sl):
+        import torch
+
+        lo, hi = sl.start or 0, self.shape[0] if sl.stop is None else sl.stop
+        out = torch.empty((hi - lo, D), dtype=torch.float32, device=self.dev)
+        g = torch.Generator(device=self.dev)
+        for c in range(lo // self.CH, (hi + self.CH - 1) // self.CH if hi > lo else 0):
+            a, b = c * self.CH, min((c + 1) * self.CH, self.shape[0])
+            g.manual_seed(self.seed * 1_000_003 + c)
+            x = torch.rand((b - a, D), generator=g, dtype=torch.float32, device=self.dev)
+            x = x * (2 * self.lim) - self.lim
+            s, e = max(a, lo), min(b, hi)
+            out[s - lo:e - lo] = x[s - a:e - a]
+        return out
+
+
+def host_rows(rows, seed, scale=1.0):
+    """CPU arm: same shape and scale (the values need not match the GPU arm's generator)."""
+    lim = np.float32(np.sqrt(6.0 / (rows + D)) * scale)
+    x = np.random.default_rng(seed).random((rows, D), dtype=np.float32)
+    x *= 2 * lim
+    x -= lim
+    return x
+
+
+# ------------------------------------------------------------------------------------------------
+# clocks
+# ------------------------------------------------------------------------------------------------
 class ClockSampler(threading.Thread):
     """SM clock + throttle reasons during the timed region (B200_PROFILING.md): NVML in-process
     every 2 ms (an `nvidia-smi` invocation takes longer than the whole timed region), falling
@@ -178,8 +233,40 @@ def ncu_traffic(kernel):
     return None
 
 
-def cpu_step_baseline(steps, threads=None):
-    """oracle port of the step on the host cores; bounded sample of the same workload."""
+# ------------------------------------------------------------------------------------------------
+# CPU legs (the only places that touch oracle/)
+# ------------------------------------------------------------------------------------------------
+def cpu_c5_state(threads):
+    import oracle
+
+    oracle.build()
+    oracle.set_threads(threads)
+    w, wu = synth_model(12345, 8, 8)[2:]
+    st = oracle.MFState(host_rows(C5_USERS, 11), host_rows(C5_ITEMS, 13), w, wu)
+    for x in (st.mU, st.mI):  # steady state: every row carries moments, the dense sweep moves 24 B / element
+        x.fill(1e-9)
+    for x in (st.vU, st.vI):
+        x.fill(1e-12)
+    return oracle, st, oracle.HParams.make(**C5_HP)
+
+
+def cpu_c5_steps(steps, warmup, threads=None):
+    """oracle port of the headline step on the host cores: `warmup` untimed + `steps` timed steps."""
+    threads = threads or os.cpu_count() or 1
+    oracle, st, hp = cpu_c5_state(threads)
+    batches = synth_batches(12345, steps + warmup, C5_USERS, C5_ITEMS, C5_BATCH)
+    for s in range(warmup):
+        oracle.mf_step(st, *batches[s], hp)
+    times = []
+    for s in range(steps):
+        t0 = time.perf_counter()
+        oracle.mf_step(st, *batches[warmup + s], hp)
+        times.append(time.perf_counter() - t0)
+    ms = 1e3 * float(np.mean(times))
+    return C5_BATCH / (ms * 1e-3), ms, threads
+
+
+def cpu_gowalla_steps(steps, threads=None):
     import oracle
 
     oracle.build()
@@ -200,9 +287,9 @@ def cpu_step_baseline(steps, threads=None):
 
 
 def cpu_scoring_baseline(sample_users=2048, reps=3):
-    """The reference's CPU evaluation path on a bounded sample of the scoring workload:
-    score matrix = ((U I^T) - c) * sig(I w)^T * sig(U w_user) with numpy (BLAS SGEMM + element-wise
-    passes stand in for TF's CPU kernels, model.py:45,199), train items := -inf
+    """The reference's CPU evaluation path on a bounded sample of the gowalla scoring workload
+    (SURVEY 8d): score matrix = ((U I^T) - c) * sig(I w)^T * sig(U w_user) with numpy (BLAS SGEMM +
+    element-wise passes stand in for TF's CPU kernels, model.py:45,199), train items := -inf
     (batch_test.py:124-129), then the reference's OWN C++ evaluator (top-K + fold-out curves,
     compiled from /root/reference into oracle/_ref) with its default 5 x cores threads.  Falls back
     to the oracle port's fused scorer when oracle/_ref is not on the box."""
@@ -243,124 +330,281 @@ def cpu_scoring_baseline(sample_users=2048, reps=3):
 
 
 def run_reference(args):
-    rank = int(os.environ.get("RANK", "0"))
-    if rank != 0:
+    """--impl reference: the reference's CPU path for the headline step on this box's host cores --
+    the oracle port (C + OpenMP; TF 1.14 cannot be installed: no wheel for Python 3.12, no network)
+    on the SAME config, `--warmup` untimed + `--steps` timed steps.  Rank 0 only."""
+    if int(os.environ.get("RANK", "0")) != 0:
         return
-    steps = max(1, min(args.steps, 20))
     t_all = time.perf_counter()
-    for _ in range(max(0, min(args.warmup, 2))):
-        pass  # warm-up is the untimed first step inside cpu_step_baseline
-    val, ms, threads = cpu_step_baseline(steps)
+    steps, warmup = max(1, args.steps), max(0, args.warmup)
+    val, ms, threads = cpu_c5_steps(steps, warmup)
     line = {
         "impl": "reference", "metric": "train_interactions_per_sec", "value": val,
-        "unit": "interactions/s", "n_gpus": args.gpus, "steps": steps, "warmup": 1,
-        "ms_per_step": ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-        "dtype": "f32", "data": "synthetic",
-        "config": {"workload": WORKLOAD,
-                   "arm": "oracle port (C + OpenMP) of the TF-1.14 CPU path, one training step per step"},
+        "unit": "interactions/s", "n_gpus": args.gpus, "steps": steps, "warmup": warmup,
+        "ms_per_step": ms, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
+        "dtype": "f32", "data": "synthetic", "config": {"workload": WORKLOAD},
+        "arm": "oracle port (C + OpenMP) of the TF-1.14 CPU path: B x B grid loss, closed-form gradients, "
+               "dense TF Adam over all 11 M rows; one full training step per step",
         "cpu_baseline": {"value": val, "unit": "interactions/s", "cores": threads, "kind": "port",
-                         "sample": f"{steps} steps of B=4096 after 1 warm-up step"},
-        "e2e": {"value": val, "unit": "interactions/s", "h2d_bytes_per_step": 0,
-                "d2h_bytes_per_step": 0},
+                         "sample": f"{steps} full steps of B={C5_BATCH} on the 10M x 1M tables after "
+                                   f"{warmup} warm-up steps"},
+        "e2e": {"value": val, "unit": "interactions/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "wall_s": time.perf_counter() - t_all,
     }
     print(json.dumps(line))
 
 
-def main():
-    ap = argparse.ArgumentParser()
-    ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=100)
-    ap.add_argument("--warmup", type=int, default=20)
-    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--no-scoring", action="store_true")
-    args = ap.parse_args()
-    if args.impl == "reference":
-        return run_reference(args)
+# ------------------------------------------------------------------------------------------------
+# the GPU arm
+# ------------------------------------------------------------------------------------------------
+class Ctx:
+    def __init__(self):
+        import torch
+        import torch.distributed as dist
 
-    import torch
-    import torch.distributed as dist
+        self.torch, self.dist = torch, dist
+        self.world = int(os.environ.get("WORLD_SIZE", "1"))
+        self.rank = int(os.environ.get("RANK", "0"))
+        self.local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+        if not torch.cuda.is_available():
+            raise SystemExit("bench.py needs a CUDA device (no CPU fallback)")
+        torch.cuda.set_device(self.local_rank)
+        self.dev = torch.device("cuda", self.local_rank)
+        if self.world > 1:
+            dist.init_process_group("nccl", device_id=self.dev)
+        self.peaks, self.peak_kind = measured_peaks()
 
-    from macr_b200 import ops
+    def barrier(self):
+        if self.world > 1:
+            self.dist.barrier()
+        self.torch.cuda.synchronize()
 
-    world = int(os.environ.get("WORLD_SIZE", "1"))
-    rank = int(os.environ.get("RANK", "0"))
-    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
-    if not torch.cuda.is_available():
-        raise SystemExit("bench.py needs a CUDA device (no CPU fallback)")
-    torch.cuda.set_device(local_rank)
-    dev = torch.device("cuda", local_rank)
-    if world > 1:
-        dist.init_process_group("nccl", device_id=dev)
-    K, W = args.steps, max(3, args.warmup)
-
-    def barrier():
-        if world > 1:
-            dist.barrier()
-        torch.cuda.synchronize()
-
-    def max_over_ranks(x):
-        if world == 1:
+    def max_over_ranks(self, x):
+        if self.world == 1:
             return x
-        t = torch.tensor([x], dtype=torch.float64, device=dev)
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        t = self.torch.tensor([x], dtype=self.torch.float64, device=self.dev)
+        self.dist.all_reduce(t, op=self.dist.ReduceOp.MAX)
         return float(t.item())
 
-    # ---------------- model + batches resident in HBM ----------------
-    U, I, w, wu = synth_model(12345 + rank)
-    hp = ops.HParams.make(**HP)
-    tr = ops.MFTrainer(U, I, w, wu, hp, max_batch=BATCH, device=dev)
-    nb = min(N_BATCHES, max(K, W))
-    batches_h = synth_batches(12345 + rank, nb)
-    batches = torch.from_numpy(batches_h).to(dev)
-    flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)  # > 126 MB L2
-    losses = torch.zeros((nb, 4), dtype=torch.float32, device=dev)
+    def events(self):
+        return self.torch.cuda.Event(enable_timing=True), self.torch.cuda.Event(enable_timing=True)
 
-    def one_step(s):
-        tr.run(batches[s % nb:s % nb + 1], losses[s % nb:s % nb + 1])
+
+def sharded_train(cx, K, W):
+    """Headline: row-sharded MF step on the 10M x 1M tables, strong scaling."""
+    torch = cx.torch
+    from macr_b200 import ops
+    from macr_b200.host.dist import RowShardedMFTrainer
+
+    w, wu = synth_model(12345, 8, 8)[2:]
+    hp = ops.HParams.make(**C5_HP)
+    sh = RowShardedMFTrainer(DeviceRows(C5_USERS, 11, cx.dev), DeviceRows(C5_ITEMS, 13, cx.dev), w, wu, hp,
+                             C5_BATCH, rank=cx.rank, world=cx.world, device=cx.dev)
+    t = sh.trainer.tab
+    for x in (t.mU[: sh.n_lu], t.mI[: sh.n_li]):  # steady state: every owned row carries moments
+        x.fill_(1e-9)
+    for x in (t.vU[: sh.n_lu], t.vI[: sh.n_li]):
+        x.fill_(1e-12)
+    nb = min(N_BATCHES, W + K)
+    batches_h = synth_batches(12345, nb, C5_USERS, C5_ITEMS, C5_BATCH)  # identical on every rank
+    ids = torch.from_numpy(batches_h).to(cx.dev)
+    losses = torch.zeros((nb, 4), dtype=torch.float32, device=cx.dev)
+    B = C5_BATCH
+
+    def step(s):
+        sh.step_ids3(ids[s % nb].view(-1), B, losses[s % nb:s % nb + 1])
 
     for s in range(W):
-        one_step(s)
-    barrier()
-    sampler = ClockSampler(local_rank)
+        step(s)
+    cx.barrier()
+    sampler = ClockSampler(cx.local_rank)
     sampler.start()
-    # (1) device-resident, L2 flushed between timed steps
-    evs = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(K)]
-    barrier()
+    e0, e1 = cx.events()
+    cx.barrier()
+    e0.record()
     for s in range(K):
-        flush.zero_()
-        evs[s][0].record()
-        one_step(W + s)
-        evs[s][1].record()
-    barrier()
-    step_ms = [a.elapsed_time(b) for a, b in evs]
-    t_flushed = max_over_ranks(sum(step_ms) * 1e-3)
-    # (1b) inputs larger than L2 instead of a flush: 3 independent models (3 x 108.8 MB of var/m/v
-    # = 326 MB > 126 MB L2) stepped round-robin, one CUDA-event pair around the K steps; each
-    # step finds its tables evicted by the other two models' traffic (the c / alpha / beta sweeps
-    # of tune.py train several models side by side)
-    others = []
-    for k in (1, 2):
-        Uo, Io, wo, wuo = synth_model(777 + 31 * k + rank)
-        others.append(ops.MFTrainer(Uo, Io, wo, wuo, hp, max_batch=BATCH, device=dev))
-    ring = [tr] + others
+        step(W + s)
+    e1.record()
+    cx.barrier()
+    t_dev = cx.max_over_ranks(e0.elapsed_time(e1) * 1e-3)
+    final_loss = [float(x) for x in losses[(W + K - 1) % nb].cpu().tolist()]
+    # end to end with host buffers: pinned ids -> H2D, K exchanges + steps, D2H of the losses, sync
+    pin = torch.from_numpy(np.concatenate([batches_h] * ((K + nb - 1) // nb))[:K].copy()).pin_memory()
+    host_losses = torch.empty((K, 4), dtype=torch.float32).pin_memory()
+    sh.run_host(pin[:min(K, 4)], host_losses[:min(K, 4)])  # warm-up (allocates the staging)
+    cx.barrier()
+    t0 = time.perf_counter()
+    sh.run_host(pin, host_losses)
+    t_e2e_local = time.perf_counter() - t0
+    cx.barrier()
+    t_e2e = cx.max_over_ranks(t_e2e_local)
+    clocks = sampler.stop()
+    # the exchange alone (renumber + push + barrier, or pack + all-reduce + unpack)
+    x0, x1 = cx.events()
+    for s in range(3):
+        sh.exchange_rows(ids[s % nb].view(-1), B)
+    cx.barrier()
+    x0.record()
+    for s in range(K):
+        sh.exchange_rows(ids[s % nb].view(-1), B)
+    x1.record()
+    cx.barrier()
+    t_ex = cx.max_over_ranks(x0.elapsed_time(x1) * 1e-3) / K
+    sh.check_peers()
+    # roofline of the HBM-bound kernel: the dense sweep over this rank's user slice, alone
+    rows_u = t.U.shape[0]
+    r0, r1 = cx.events()
+    ops.adam_sweep_untouched(t.U, t.mU, t.vU, None, 1e-6)
+    cx.barrier()
+    n_sw = 4 if cx.world == 1 else 8
+    r0.record()
+    for _ in range(n_sw):
+        ops.adam_sweep_untouched(t.U, t.mU, t.vU, None, 1e-6)
+    r1.record()
+    cx.barrier()
+    sw_ms = cx.max_over_ranks(r0.elapsed_time(r1)) / n_sw
+    sweep_bytes = 24.0 * D * rows_u
+    achieved = sweep_bytes / (sw_ms * 1e-3) / 1e9
+    step_bytes = 24.0 * D * (C5_USERS + C5_ITEMS) + 780.0 * B + 3072.0  # SURVEY 8d
+    ms_step = 1e3 * t_dev / K
+    pk = cx.peaks["hbm_gbs"]
+    roofline = {"bound": "hbm", "kernel": "adam_sweep_kernel", "achieved": achieved, "peak": pk,
+                "peak_kind": cx.peak_kind, "unit": "GB/s", "frac": achieved / pk,
+                "traffic": ncu_traffic("adam_sweep_kernel_c5"), "bytes_per_launch": sweep_bytes,
+                "ms_per_launch": sw_ms,
+                "method": f"{n_sw} launches over this rank's user slice ({rows_u} rows x 3 tensors, far larger "
+                          "than L2) between one event pair on the launching stream; max over ranks",
+                "step": {"bytes_per_step": step_bytes, "achieved_per_gpu": step_bytes / cx.world / (ms_step * 1e-3) / 1e9,
+                         "frac": step_bytes / cx.world / (ms_step * 1e-3) / 1e9 / pk,
+                         "note": "whole fused step (exchange + gather + dots + BxB BCE + row gradients + dense "
+                                 "Adam) against its algorithmic bytes, per GPU"}}
+    out = {"t_dev": t_dev, "ms_per_step": ms_step, "t_e2e": t_e2e, "clocks": clocks, "roofline": roofline,
+           "final_loss": final_loss, "launches": sh.trainer.launches_per_step + (3 if sh.exchange == "push" else 2),
+           "sharding": {"tables": f"rows/{cx.world}", "exchange": sh.exchange,
+                        "exchange_ms": 1e3 * t_ex, "exchange_bytes_per_step": 3 * B * D * 4,
+                        "rows_per_rank": [sh.n_lu, sh.n_li],
+                        "hbm_bytes_per_rank_step": 24.0 * D * (sh.n_lu + sh.n_li),
+                        "replicated": "dots + BxB grid + w/w_user gradients (batch positions only)"}}
+    sh.close()
+    del sh, ids
+    torch.cuda.empty_cache()
+    return out
+
+
+def sharded_scoring(cx, reps=3):
+    """Item-partitioned full-catalogue top-20 of a fixed query set (262 144 x 1 M)."""
+    torch = cx.torch
+    from macr_b200 import ops
+    from macr_b200.host.dist import ShardedScorer
+
+    T, n_items = C5_QUERY, C5_ITEMS
+    w, wu = synth_model(777, 8, 8)[2:]
+    dw, dwu = torch.from_numpy(w).to(cx.dev), torch.from_numpy(wu).to(cx.dev)
+    sc = ShardedScorer(DeviceRows(n_items, 21, cx.dev, scale=10.0), dw, rank=cx.rank, world=cx.world)
+    Uq = DeviceRows(T, 23, cx.dev, scale=10.0 * np.sqrt((T + D) / (C5_USERS + D)))[0:T]  # same rows on every rank
+    su = ops.score_gates(Uq, dwu)
+    mrp, mcol = synth_mask(9, T, 20, n_items)
+    dmrp, dmcol = torch.from_numpy(mrp).to(cx.dev), torch.from_numpy(mcol).to(cx.dev)
+    dmrp_l, dmcol_l = dmrp, dmcol  # global ids: the shard kernels re-base them by item_id_offset
+
+    def once():
+        return sc.topk(Uq, su, 40.0, dmrp_l, dmcol_l, TOPK)
+
+    for _ in range(2):
+        ids, _ = once()
+    cx.barrier()
+    s0, s1 = cx.events()
+    s0.record()
+    for _ in range(reps):
+        ids, scs = once()
+    s1.record()
+    cx.barrier()
+    t = cx.max_over_ranks(s0.elapsed_time(s1) * 1e-3) / reps
+    # local part alone (no collective, no merge): what the shard kernel pipeline takes
+    l0, l1 = cx.events()
+    l0.record()
+    for _ in range(reps):
+        ops.score_topk(Uq, sc.items, sc.sig_i, su, 40.0, dmrp_l, dmcol_l, TOPK, item_id_offset=sc.lo)
+    l1.record()
+    cx.barrier()
+    t_local = cx.max_over_ranks(l0.elapsed_time(l1) * 1e-3) / reps
+    stats = torch.zeros(2, dtype=torch.int64, device=cx.dev)
+    ops.score_topk_tc(Uq, sc.items, sc.sig_i, su, 40.0, dmrp_l, dmcol_l, TOPK, item_id_offset=sc.lo, stats=stats)
+    st = stats.cpu().tolist()
+    flops = 2.0 * D * T * n_items  # SURVEY 8d: algorithmic, not executed
+    pk = cx.peaks["bf16_tflops"]
+    out = {"metric": "full_catalog_scores_per_sec", "value": T * n_items / t, "unit": "scores/s",
+           "ms_per_eval": 1e3 * t, "ms_local_scoring": 1e3 * t_local, "query_users": T, "items": n_items,
+           "topk": TOPK, "sharding": f"items/{cx.world}", "scaling": "strong",
+           "exchange": "all-gather of the [T,K] (id, score) candidates + on-device K-way merge, inside the timed region",
+           "exchange_bytes_per_rank": T * TOPK * 8,
+           "rows_redone_by_exact_kernel_rank0": st[0], "candidates_per_row_rank0": st[1] / max(1, T - st[0]),
+           "roofline": {"bound": "tensor", "achieved": flops / t / 1e12, "peak": pk * cx.world,
+                        "peak_kind": cx.peak_kind, "unit": "TFLOP/s", "frac": flops / t / 1e12 / (pk * cx.world),
+                        "note": "ALGORITHMIC flops 2*64*T*I over the whole call (operand prep, threshold, "
+                                "filter, re-rank, all-gather, merge) against N x the measured bf16 peak"},
+           "checksum": int(ids.to(torch.int64).sum().item()),
+           "score_checksum": float(scs.double().sum().item())}
+    if cx.world == 1:  # spot parity against the exact fp32 kernel on 256 rows
+        sel = torch.arange(0, T, T // 256, device=cx.dev)[:256]
+        lens = (dmrp[sel.long() + 1] - dmrp[sel.long()]).long()
+        sub_rp = torch.zeros(len(sel) + 1, dtype=torch.int32, device=cx.dev)
+        sub_rp[1:] = torch.cumsum(lens, 0)
+        sub_col = torch.cat([dmcol[int(dmrp[r]):int(dmrp[r + 1])] for r in sel.tolist()])
+        ei, es = ops.score_topk_exact(Uq[sel.long()].contiguous(), sc.items, sc.sig_i, su[sel.long()].contiguous(),
+                                      40.0, sub_rp, sub_col, TOPK)
+        out["spot_parity_vs_exact_fp32_kernel"] = bool((ei == ids[sel.long()]).all().item()
+                                                       and (es == scs[sel.long()]).all().item())
+    del sc, Uq
+    torch.cuda.empty_cache()
+    return out
+
+
+def gowalla_block(cx, K, W, with_cpu):
+    """BASELINE configs[1] on one GPU: the small-table regime (tables L2-sized, B x B grid MUFU-bound)."""
+    torch = cx.torch
+    dev = cx.dev
+    from macr_b200 import ops
+
+    U, I, w, wu = synth_model(12345)
+    hp = ops.HParams.make(**HP)
+    nb = min(N_BATCHES, max(K, W))
+    batches_h = synth_batches(12345, nb)
+    batches = torch.from_numpy(batches_h).to(dev)
+    losses = torch.zeros((nb, 4), dtype=torch.float32, device=dev)
+    # inputs larger than L2: 3 independent models (3 x 108.8 MB of var/m/v = 326 MB > 126 MB L2) stepped
+    # round-robin, so every step finds its tables evicted (tune.py trains several models side by side)
+    ring = [ops.MFTrainer(*synth_model(12345 + 31 * k), hp, max_batch=BATCH, device=dev) for k in range(3)]
+    tr = ring[0]
     for s in range(max(W, 9)):
         ring[s % 3].run(batches[s % nb:s % nb + 1], losses[s % nb:s % nb + 1])
-    r0, r1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    barrier()
+    r0, r1 = cx.events()
+    torch.cuda.synchronize()
     r0.record()
     for s in range(K):
         ring[s % 3].run(batches[s % nb:s % nb + 1], losses[s % nb:s % nb + 1])
     r1.record()
-    barrier()
-    t_ring = max_over_ranks(r0.elapsed_time(r1) * 1e-3)
-    for o in others:
-        o.close()
-    del others, ring
-    # (2) back-to-back replay (tables stay L2-resident between steps, as in a real epoch)
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    barrier()
+    torch.cuda.synchronize()
+    t_ring = r0.elapsed_time(r1) * 1e-3
+    # e2e in the SAME cache regime: the session-style per-step call (H2D ids + step + D2H losses + sync,
+    # what one `sess.run` of train.py:492-496 is) round-robin over the same three models ...
+    pin = torch.from_numpy(batches_h[:min(nb, 32)].copy()).pin_memory()
+    for s in range(6):
+        ring[s % 3].step_pinned(pin[s % pin.shape[0]])
+    t0 = time.perf_counter()
+    for s in range(K):
+        ring[s % 3].step_pinned(pin[s % pin.shape[0]])
+    torch.cuda.synchronize()
+    t_e2e_step = time.perf_counter() - t0
+    # ... and the epoch call (one H2D, K graph replays, one D2H, one sync) on a single model,
+    # beside its device-only twin (back-to-back replay, tables L2-resident as in a real epoch)
+    pin_epoch = torch.from_numpy(np.concatenate([batches_h] * ((K + nb - 1) // nb))[:K].copy()).pin_memory()
+    host_losses = torch.empty((K, 4), dtype=torch.float32).pin_memory()
+    tr.run_host(pin_epoch[:min(K, 8)], host_losses[:min(K, 8)])
+    t0 = time.perf_counter()
+    tr.run_host(pin_epoch, host_losses)
+    t_epoch = time.perf_counter() - t0
+    e0, e1 = cx.events()
     e0.record()
     done = 0
     while done < K:
@@ -368,51 +612,21 @@ def main():
         tr.run(batches[:n], losses[:n])
         done += n
     e1.record()
-    barrier()
-    t_b2b = max_over_ranks(e0.elapsed_time(e1) * 1e-3)
-    # (3) end to end with HOST buffers.  (a) the epoch call: K batches in pinned host memory ->
-    # one H2D copy, K step graphs, one D2H copy of the K x 4 losses, one sync -- all inside the
-    # timed region.  (b) the session-style per-step call (H2D + step + D2H + sync every step).
-    pin = torch.from_numpy(batches_h[:min(nb, 32)].copy()).pin_memory()  # [n,3,B] int32, pinned
-    pin_epoch = torch.from_numpy(np.concatenate([batches_h] * ((K + nb - 1) // nb))[:K].copy()).pin_memory()
-    host_losses = torch.empty((K, 4), dtype=torch.float32).pin_memory()
-    tr.run_host(pin_epoch[:min(K, 8)], host_losses[:min(K, 8)])  # warm-up (allocates the staging)
-    tr.run_host(pin_epoch, host_losses)
-    barrier()
-    t0 = time.perf_counter()
-    tr.run_host(pin_epoch, host_losses)
-    t_e2e_local = time.perf_counter() - t0
-    barrier()
-    t_e2e = max_over_ranks(t_e2e_local)
-    for s in range(3):
-        tr.step_pinned(pin[s % pin.shape[0]])
-    barrier()
-    t0 = time.perf_counter()
-    for s in range(K):
-        tr.step_pinned(pin[s % pin.shape[0]])
     torch.cuda.synchronize()
-    t_e2e_step_local = time.perf_counter() - t0
-    barrier()
-    t_e2e_step = max_over_ranks(t_e2e_step_local)
-    clocks = sampler.stop()
-    final_loss = float(losses[(W + K - 1) % nb, 0].item())
-
-    # ---------------- roofline of the HBM-bound kernel: the Adam dense sweep ----------------
-    peaks, peak_kind = measured_peaks()
+    t_b2b = e0.elapsed_time(e1) * 1e-3
+    launches = tr.launches_per_step
+    for o in ring:
+        o.close()
+    del ring
+    # the sweep alone at this size: 6 table sets (326 MB > L2) round-robin inside one CUDA graph
     rows = N_USERS + N_ITEMS
     sweep_bytes = 24.0 * D * rows
-    # steady-state tables: every row has non-zero Adam moments (no all-zero-row shortcut).
-    # NSETS independent (var, m, v) sets, 6 x 54 MB = 326 MB > the 126 MB L2, swept round-robin
-    # between ONE pair of events: every launch finds its operands evicted (inputs larger than
-    # L2), and no per-launch event / launch-gap overhead is folded into an 18 us kernel.
     NSETS, ROUNDS = 6, 10
-    sets = []
-    for _ in range(NSETS):
-        sets.append((torch.randn((rows, D), dtype=torch.float32, device=dev) * 0.05,
-                     torch.randn((rows, D), dtype=torch.float32, device=dev) * 1e-4,
-                     torch.rand((rows, D), dtype=torch.float32, device=dev) * 1e-7 + 1e-9))
+    sets = [(torch.randn((rows, D), dtype=torch.float32, device=dev) * 0.05,
+             torch.randn((rows, D), dtype=torch.float32, device=dev) * 1e-4,
+             torch.rand((rows, D), dtype=torch.float32, device=dev) * 1e-7 + 1e-9) for _ in range(NSETS)]
     side = torch.cuda.Stream(device=dev)
-    with torch.cuda.stream(side):  # warm-up, then capture one round-robin pass as a CUDA graph
+    with torch.cuda.stream(side):
         for a, b, c in sets:
             ops.adam_sweep_untouched(a, b, c, None, 1e-4)
     torch.cuda.synchronize()
@@ -422,192 +636,160 @@ def main():
             ops.adam_sweep_untouched(a, b, c, None, 1e-4)
     g_sweep.replay()
     torch.cuda.synchronize()
-    se0, se1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    se0.record()
+    s0, s1 = cx.events()
+    s0.record()
     for _ in range(ROUNDS):
         g_sweep.replay()
-    se1.record()
+    s1.record()
     torch.cuda.synchronize()
-    sw_ms = se0.elapsed_time(se1) / (NSETS * ROUNDS)
-    achieved = sweep_bytes / (sw_ms * 1e-3) / 1e9
-    # one launch alone between two events, L2 flushed before it (includes launch latency)
-    one_ev = []
-    for k in range(10):
-        flush.zero_()
-        a0, a1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        a0.record()
-        ops.adam_sweep_untouched(*sets[k % NSETS], None, 1e-4)
-        a1.record()
-        one_ev.append((a0, a1))
-    torch.cuda.synchronize()
-    sw_single_ms = float(np.mean([a.elapsed_time(b) for a, b in one_ev]))
-    del sets
-    # the kernel that takes the most time of the step is the B x B grid: MUFU-bound (4 per pair: 2
-    # ex2, 1 rcp, 1 lg2; 16 lanes per SM per clock), timed alone through its stateless entry point
+    sw_ms = s0.elapsed_time(s1) / (NSETS * ROUNDS)
+    del sets, g_sweep
+    # the B x B grid alone (MUFU-bound: 4 per pair), buffers allocated once outside the timed region
     gsc = [torch.randn(BATCH, device=dev) * sd for sd in (0.05, 0.05, 0.1, 0.1, 0.1)]
+    nbytes = ops.lib().macr_grid_bce_workspace_bytes(BATCH)
+    bufs = (torch.empty(nbytes, dtype=torch.uint8, device=dev), torch.empty(3, dtype=torch.float32, device=dev),
+            torch.empty((5, BATCH), dtype=torch.float32, device=dev))
     for _ in range(3):
-        ops.grid_bce(*gsc, HP["alpha"], HP["beta"])
-    g0, g1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        ops.grid_bce(*gsc, HP["alpha"], HP["beta"], bufs=bufs)
+    g0, g1 = cx.events()
     g0.record()
     for _ in range(20):
-        ops.grid_bce(*gsc, HP["alpha"], HP["beta"])
+        ops.grid_bce(*gsc, HP["alpha"], HP["beta"], bufs=bufs)
     g1.record()
     torch.cuda.synchronize()
     grid_ms = g0.elapsed_time(g1) / 20
-    mufu_ops = 4.0 * BATCH * BATCH
-    mufu_peak = 148 * 16 * (clocks.get("sm_max_mhz") or 1965.0) * 1e6
-    grid_info = {"bound": "mufu", "ms_per_launch": grid_ms, "pairs": BATCH * BATCH,
-                 "achieved_gops": mufu_ops / (grid_ms * 1e-3) / 1e9, "peak_gops": mufu_peak / 1e9,
-                 "frac": mufu_ops / (grid_ms * 1e-3) / mufu_peak,
-                 "note": "stateless macr_grid_bce_fwd_bwd incl. its workspace allocation and launch gaps; "
-                         "inside the step graph the kernel takes ~25 us (profiles/r1d_launches.txt)"}
-    step_bytes = 24.0 * D * rows + 12.0 * D * BATCH + 12.0 * BATCH + 48.0 * D
-    ms_per_step = 1e3 * t_ring / K
-    roofline = {"bound": "hbm", "kernel": "adam_sweep_kernel", "achieved": achieved,
-                "peak": peaks["hbm_gbs"], "peak_kind": peak_kind, "unit": "GB/s",
-                "frac": achieved / peaks["hbm_gbs"], "traffic": ncu_traffic("adam_sweep_kernel"),
-                "bytes_per_launch": sweep_bytes, "ms_per_launch": sw_ms,
-                "ms_per_launch_single_flushed": sw_single_ms,
-                "method": "60 launches (10 replays of a 6-launch CUDA graph) round-robin over 6 table "
-                          "sets (326 MB > L2) between one event pair on the launching stream",
-                "grid_bce_kernel": grid_info,
-                "step": {"bytes_per_step": step_bytes,
-                         "achieved": step_bytes / (ms_per_step * 1e-3) / 1e9,
-                         "frac": step_bytes / (ms_per_step * 1e-3) / 1e9 / peaks["hbm_gbs"],
-                         "note": "whole step; the BxB grid kernel is MUFU-bound, not HBM-bound"}}
+    mufu_peak = 148 * 16 * 1965.0e6
+    pk = cx.peaks["hbm_gbs"]
+    step_bytes = 24.0 * D * rows + 780.0 * BATCH + 3072.0
+    ms_step = 1e3 * t_ring / K
+    out = {"workload": GOWALLA, "value": BATCH * K / t_ring, "unit": "interactions/s", "ms_per_step": ms_step,
+           "l2": "inputs larger than L2: 3 models (326 MB of var/m/v) stepped round-robin",
+           "ms_per_step_back_to_back": 1e3 * t_b2b / K, "launches_per_step": launches,
+           "e2e": {"value": BATCH * K / t_e2e_step, "ms_per_step": 1e3 * t_e2e_step / K,
+                   "api": "MFTrainer.step_pinned -> macr_mf_trainer_step_host (H2D ids + step + D2H losses + sync "
+                          "per step), same 3-model ring as `value`",
+                   "h2d_bytes_per_step": 3 * 4 * BATCH, "d2h_bytes_per_step": 16,
+                   "epoch_call": {"value": BATCH * K / t_epoch, "ms_per_step": 1e3 * t_epoch / K,
+                                  "api": "MFTrainer.run_host (one H2D, K steps, one D2H, one sync; single model, "
+                                         "tables L2-resident -- compare with ms_per_step_back_to_back)"}},
+           "roofline": {"adam_sweep_kernel": {"bound": "hbm", "achieved": sweep_bytes / (sw_ms * 1e-3) / 1e9,
+                                              "peak": pk, "frac": sweep_bytes / (sw_ms * 1e-3) / 1e9 / pk,
+                                              "ms_per_launch": sw_ms, "bytes_per_launch": sweep_bytes,
+                                              "traffic": ncu_traffic("adam_sweep_kernel")},
+                        "grid_bce_kernel": {"bound": "mufu", "ms_per_launch": grid_ms,
+                                            "achieved_gops": 4.0 * BATCH * BATCH / (grid_ms * 1e-3) / 1e9,
+                                            "peak_gops": mufu_peak / 1e9,
+                                            "frac": 4.0 * BATCH * BATCH / (grid_ms * 1e-3) / mufu_peak,
+                                            "note": "stateless macr_grid_bce_fwd_bwd (memset + gates + grid), "
+                                                    "buffers preallocated; 4 MUFU per pair, 16 / clk / SM"},
+                        "step": {"bytes_per_step": step_bytes, "frac": step_bytes / (ms_step * 1e-3) / 1e9 / pk,
+                                 "note": "whole step vs its HBM floor; the BxB grid is MUFU-bound (floor 14.4 us)"}}}
+    out["scoring"] = gowalla_scoring(cx)
+    if with_cpu:
+        cv, cms, cth = cpu_gowalla_steps(8)
+        out["cpu_baseline"] = {"value": cv, "unit": "interactions/s", "cores": cth, "kind": "port",
+                               "ms_per_step": cms, "sample": "8 steps of B=4096 after 1 warm-up step"}
+        try:  # a reported baseline: never allowed to take the bench line down
+            out["scoring"]["cpu_baseline"] = cpu_scoring_baseline()
+        except Exception as e:  # noqa: BLE001
+            out["scoring"]["cpu_baseline"] = {"unavailable": f"{type(e).__name__}: {e}"}
+    return out
 
-    # ---------------- scoring: full catalogue counterfactual top-K ----------------
-    # headline: query users partitioned across the ranks, item table replicated (10.5 MB), no
-    # data-path collective, one all-gather of the [T,K] result; also timed: the item-partitioned
-    # layout (all-gather of the per-shard candidates + on-device merge).
-    scoring = None
-    if not args.no_scoring:
-        T_q = N_TEST_USERS
-        Us, Is, ws_, wus = synth_model(777)  # same model on every rank
-        Us *= 10
-        Is *= 10
-        from macr_b200.host.dist import ShardedScorer, UserShardedScorer
 
-        dU = torch.from_numpy(Us).to(dev)
-        q = torch.from_numpy(np.random.RandomState(5).permutation(N_USERS)[:T_q].astype(np.int32)).to(dev)
-        mrp, mcol = synth_mask(9, T_q, 27)
-        dmrp, dmcol = torch.from_numpy(mrp).to(dev), torch.from_numpy(mcol).to(dev)
-        dw, dwu = torch.from_numpy(ws_).to(dev), torch.from_numpy(wus).to(dev)
-        dI = torch.from_numpy(Is).to(dev)
-        by_users = UserShardedScorer(dI, dw, rank=rank, world=world)
-        by_items = ShardedScorer(dI, dw, rank=rank, world=world)
+def gowalla_scoring(cx, reps=10):
+    torch = cx.torch
+    dev = cx.dev
+    from macr_b200 import ops
 
-        def time_scorer(scorer, reps=10):
-            def once():
-                Uq = ops.gather_rows(dU, q)
-                su = ops.score_gates(Uq, dwu)
-                return scorer.topk(Uq, su, 40.0, dmrp, dmcol, TOPK)
+    T_q = N_TEST_USERS
+    Us, Is, ws_, wus = synth_model(777)
+    Us *= 10
+    Is *= 10
+    dU, dI = torch.from_numpy(Us).to(dev), torch.from_numpy(Is).to(dev)
+    q = torch.from_numpy(np.random.RandomState(5).permutation(N_USERS)[:T_q].astype(np.int32)).to(dev)
+    mrp, mcol = synth_mask(9, T_q, 27)
+    dmrp, dmcol = torch.from_numpy(mrp).to(dev), torch.from_numpy(mcol).to(dev)
+    dw, dwu = torch.from_numpy(ws_).to(dev), torch.from_numpy(wus).to(dev)
+    sig_i = ops.score_gates(dI, dw)
 
-            for _ in range(5):
-                once()
-            barrier()
-            s0, s1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-            s0.record()
-            for _ in range(reps):
-                ids, sc = once()
-            s1.record()
-            barrier()
-            return max_over_ranks(s0.elapsed_time(s1) * 1e-3) / reps, ids
+    def once(fn):
+        Uq = ops.gather_rows(dU, q)
+        return fn(Uq, dI, sig_i, ops.score_gates(Uq, dwu), 40.0, dmrp, dmcol, TOPK)
 
-        t_sc, ids = time_scorer(by_users)
-        checksum = int(ids.to(torch.int64).sum().item())
-        # what the tensor-core pipeline did on this rank's slice (developer counters)
-        lo_u, hi_u = by_users.local_rows(T_q)
-        Uq_l = ops.gather_rows(dU, q)[lo_u:hi_u].contiguous()
-        su_l = ops.score_gates(Uq_l, dwu)
-        stats = torch.zeros(2, dtype=torch.int64, device=dev)
-        ops.score_topk_tc(Uq_l, dI, by_users.sig_i, su_l, 40.0, dmrp[lo_u:hi_u + 1].contiguous(), dmcol,
-                          TOPK, stats=stats)
-        st = stats.cpu().tolist()
-        n_pad = (N_ITEMS + 255) // 256 * 256
-        tc_flops = 2 * 2.0 * (D + 16) * T_q * n_pad  # two passes, K = 64 + 16 (augmented step)
-        scoring = {"metric": "full_catalog_scores_per_sec", "value": T_q * N_ITEMS / t_sc,
-                   "unit": "scores/s", "ms_per_eval": 1e3 * t_sc, "test_users": T_q,
-                   "items": N_ITEMS, "topk": TOPK, "sharding": f"users/{world}",
-                   "path": "tcgen05 bf16 maxima pass + filter pass, exact fp32 re-rank (bit-identical "
-                           "to the fp32 kernel)",
-                   "rows_redone_by_exact_kernel": st[0],
-                   "candidates_per_row": st[1] / max(1, hi_u - lo_u - st[0]),
-                   "roofline": {"bound": "tensor", "achieved": tc_flops / t_sc / 1e12,
-                                "peak": peaks.get("bf16_tflops"), "peak_kind": peak_kind,
-                                "unit": "TFLOP/s",
-                                "frac": tc_flops / t_sc / 1e12 / peaks["bf16_tflops"],
-                                "note": "whole call incl. operand prep, threshold and re-rank kernels; "
-                                        "flops = 2 passes x 2*(64+16)*T*I_pad"},
-                   "checksum": checksum}
-        if world > 1:
-            t_it, ids_it = time_scorer(by_items)
-            scoring["item_sharded"] = {"value": T_q * N_ITEMS / t_it, "ms_per_eval": 1e3 * t_it,
-                                       "sharding": f"items/{world}",
-                                       "checksum": int(ids_it.to(torch.int64).sum().item())}
-        else:
-            def exact_once():
-                Uq = ops.gather_rows(dU, q)
-                su = ops.score_gates(Uq, dwu)
-                return ops.score_topk_exact(Uq, dI, by_users.sig_i, su, 40.0, dmrp, dmcol, TOPK)
+    def timed(fn, n):
+        for _ in range(3):
+            once(fn)
+        s0, s1 = cx.events()
+        s0.record()
+        for _ in range(n):
+            ids, _ = once(fn)
+        s1.record()
+        torch.cuda.synchronize()
+        return s0.elapsed_time(s1) * 1e-3 / n, ids
 
-            exact_once()
-            x0, x1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-            x0.record()
-            for _ in range(3):
-                eids, _ = exact_once()
-            x1.record()
-            torch.cuda.synchronize()
-            scoring["exact_fp32_kernel"] = {"ms_per_eval": x0.elapsed_time(x1) / 3,
-                                            "checksum": int(eids.to(torch.int64).sum().item())}
+    t_sc, ids = timed(ops.score_topk, reps)
+    t_ex, eids = timed(ops.score_topk_exact, 3)
+    stats = torch.zeros(2, dtype=torch.int64, device=dev)
+    Uq = ops.gather_rows(dU, q)
+    ops.score_topk_tc(Uq, dI, sig_i, ops.score_gates(Uq, dwu), 40.0, dmrp, dmcol, TOPK, stats=stats)
+    st = stats.cpu().tolist()
+    flops = 2.0 * D * T_q * N_ITEMS
+    pk = cx.peaks["bf16_tflops"]
+    return {"metric": "full_catalog_scores_per_sec", "value": T_q * N_ITEMS / t_sc, "unit": "scores/s",
+            "ms_per_eval": 1e3 * t_sc, "test_users": T_q, "items": N_ITEMS, "topk": TOPK,
+            "rows_redone_by_exact_kernel": st[0], "candidates_per_row": st[1] / max(1, T_q - st[0]),
+            "roofline": {"bound": "tensor", "achieved": flops / t_sc / 1e12, "peak": pk, "unit": "TFLOP/s",
+                         "frac": flops / t_sc / 1e12 / pk, "note": "algorithmic flops 2*64*T*I, whole call"},
+            "checksum": int(ids.to(torch.int64).sum().item()),
+            "exact_fp32_kernel": {"ms_per_eval": 1e3 * t_ex, "checksum": int(eids.to(torch.int64).sum().item())}}
 
-    # ---------------- CPU baseline (rank 0, N=1 only) ----------------
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-scoring", action="store_true")
+    ap.add_argument("--no-gowalla", action="store_true")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        return run_reference(args)
+
+    cx = Ctx()
+    K, W = max(1, args.steps), max(3, args.warmup)
+    tr = sharded_train(cx, K, W)
+    scoring = None if args.no_scoring else sharded_scoring(cx)
+    gow = None
+    if cx.world == 1 and not args.no_gowalla:
+        gow = gowalla_block(cx, max(K, 60), max(W, 9), with_cpu=not args.no_cpu_baseline)
     cpu = None
-    if rank == 0 and world == 1 and not args.no_cpu_baseline:
-        cv, cms, cth = cpu_step_baseline(8)
-        cpu = {"value": cv, "unit": "interactions/s", "cores": cth, "kind": "port",
-               "ms_per_step": cms, "sample": "8 steps of the same B=4096 workload after 1 warm-up step"}
-        if scoring is not None:
-            try:  # a reported baseline: never allowed to take the bench line down
-                scoring["cpu_baseline"] = cpu_scoring_baseline()
-            except Exception as e:  # noqa: BLE001
-                scoring["cpu_baseline"] = {"unavailable": f"{type(e).__name__}: {e}"}
-
-    if rank == 0:
+    if cx.rank == 0 and cx.world == 1 and not args.no_cpu_baseline:
+        cv, cms, cth = cpu_c5_steps(4, 1)
+        cpu = {"value": cv, "unit": "interactions/s", "cores": cth, "kind": "port", "ms_per_step": cms,
+               "sample": "4 full steps of the same B=8192 workload on the 10M x 1M tables after 1 warm-up step "
+                         "(oracle port, C + OpenMP)"}
+    if cx.rank == 0:
+        B = C5_BATCH
         line = {
-            "metric": "train_interactions_per_sec", "value": world * BATCH * K / t_ring,
-            "unit": "interactions/s", "n_gpus": world, "steps": K, "warmup": W,
-            "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak",
-            "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": {"workload": WORKLOAD,
-                       "l2": "inputs larger than L2: 3 independent models (3 x 108.8 MB of var/m/v = 326 MB > "
-                             "126 MB L2) stepped round-robin, so every timed step finds its tables evicted; "
-                             "value_memset_flushed is the same step after a 256 MiB memset (which also "
-                             "charges the write-back of the memset's dirty lines to the step)",
-                       "parallelism": "replicas only" if world > 1 else "single GPU",
-                       "batches_resident": nb},
-            "value_memset_flushed": world * BATCH * K / t_flushed,
-            "ms_per_step_memset_flushed": 1e3 * t_flushed / K,
-            "value_back_to_back": world * BATCH * K / t_b2b,
-            "ms_per_step_back_to_back": 1e3 * t_b2b / K,
-            "e2e": {"value": world * BATCH * K / t_e2e, "unit": "interactions/s",
-                    "ms_per_step": 1e3 * t_e2e / K, "h2d_bytes_per_step": 3 * 4 * BATCH,
-                    "d2h_bytes_per_step": 16,
-                    "api": "MFTrainer.run_host -> macr_mf_trainer_run_host (K batches in pinned host "
-                           "memory, one call: H2D + K steps + D2H of the losses + sync, wall clock)",
-                    "per_step_call": {"value": world * BATCH * K / t_e2e_step,
-                                      "ms_per_step": 1e3 * t_e2e_step / K,
-                                      "api": "MFTrainer.step_pinned -> macr_mf_trainer_step_host "
-                                             "(H2D + step + D2H + sync every step)"}},
-            "gpu_launches": tr.launches_per_step * K,
-            "launches_per_step": tr.launches_per_step,
-            "roofline": roofline, "cpu_baseline": cpu, "scoring": scoring, "clocks": clocks,
-            "final_loss": final_loss,
+            "metric": "train_interactions_per_sec", "value": B * K / tr["t_dev"], "unit": "interactions/s",
+            "n_gpus": cx.world, "steps": K, "warmup": W, "ms_per_step": tr["ms_per_step"],
+            "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32",
+            "data": "synthetic", "config": {"workload": WORKLOAD},
+            "l2": "inputs far larger than L2: 8.45 GB of var/m/v (1/N per rank) swept every step",
+            "final_loss": tr["final_loss"], "gpu_launches": tr["launches"] * K, "launches_per_step": tr["launches"],
+            "gowalla": gow,
+            "sharding": tr["sharding"],
+            "e2e": {"value": B * K / tr["t_e2e"], "unit": "interactions/s", "ms_per_step": 1e3 * tr["t_e2e"] / K,
+                    "h2d_bytes_per_step": 3 * 4 * B, "d2h_bytes_per_step": 16,
+                    "api": "RowShardedMFTrainer.run_host: K batches of ids in pinned host memory -> one H2D, "
+                           "K x (row exchange + macr_mf_trainer_run step graph), one D2H of the losses, sync; wall clock"},
+            "roofline": tr["roofline"], "cpu_baseline": cpu, "scoring": scoring, "clocks": tr["clocks"],
         }
         print(json.dumps(line))
-    tr.close()
-    if world > 1:
-        dist.destroy_process_group()
+    if cx.world > 1:
+        cx.dist.destroy_process_group()
 
 
 if __name__ == "__main__":

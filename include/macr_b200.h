@@ -362,6 +362,52 @@ int macr_sample_lgcn(uint32_t *py_state, uint32_t *np_state, const int32_t *user
                      const int32_t *ban_sorted, int B, int32_t *users, int32_t *pos,
                      int32_t *neg);
 
+/* ------------------------------------------------------------------------- *
+ * Row-partitioned training over the GPUs of one box (SURVEY.md 8e rows "dense Adam
+ * sweep" and "gather + grid + row grads"): every rank owns a contiguous id range
+ * of both tables (with their Adam slots); the rows of the batch are exchanged once
+ * per step and the unchanged single-GPU step runs on local ids.
+ * replaces (distributed form of): tf.nn.embedding_lookup x3  macr_mf/model.py:35-37
+ *   on a variable that lives on one device in the reference.
+ * Local table layout: [n_local owned rows | 2 parities x max_batch (users) or
+ *   2*max_batch (items) ghost rows]; ghost slot of batch position b: users b, pos b,
+ *   neg B+b.  local_ids3 = users|pos|neg renumbered (owned: id-lo, foreign: ghost).
+ *  macr_shard_pack   : owned rows -> ex[3B][64], zeros elsewhere (sum over ranks by
+ *                      the caller, e.g. ncclAllReduce; exact: one owner per row)
+ *  macr_shard_unpack : ex -> ghost slots (two device copies)
+ *  macr_shard_push   : the fused form: owned rows are stored straight into the ghost
+ *                      slots of every peer over NVLink; peer_*_ghost_host[r] = address
+ *                      in THIS process (macr_ipc_open) of row n_local of rank r's table
+ *  macr_shard_barrier: flag barrier over peer memory after the push; peer_flags_host[r]
+ *                      = rank r's uint64[world] flag array (zero-initialised, IPC memory);
+ *                      epoch must grow by one per call; *err_flag (device int) becomes
+ *                      1+r if peer r did not arrive within ~10 s (no device hang).
+ * macr_ipc_* : cudaMalloc'ed memory with its cudaIpcMemHandle_t (64 opaque bytes) so the
+ *   other ranks of the box can map it.
+ * ------------------------------------------------------------------------- */
+#define MACR_SHARD_MAX_RANKS 16
+#define MACR_IPC_HANDLE_BYTES 64
+typedef struct macr_shard_desc {
+  int32_t rank, world;
+  int64_t u_lo, u_hi, i_lo, i_hi; /* owned global id ranges [lo, hi) */
+  int32_t max_batch;
+} macr_shard_desc;
+int macr_shard_pack(const float *U_local, const float *I_local, const macr_shard_desc *desc,
+                    const int32_t *ids3, int B, int parity, int32_t *local_ids3, float *ex,
+                    macr_stream_t stream);
+int macr_shard_unpack(float *U_local, float *I_local, const macr_shard_desc *desc,
+                      const float *ex, int B, int parity, macr_stream_t stream);
+int macr_shard_push(const float *U_local, const float *I_local, const macr_shard_desc *desc,
+                    const int32_t *ids3, int B, int parity, int32_t *local_ids3,
+                    float *const *peer_U_ghost_host, float *const *peer_I_ghost_host,
+                    macr_stream_t stream);
+int macr_shard_barrier(uint64_t *const *peer_flags_host, int rank, int world, uint64_t epoch,
+                       int *err_flag, macr_stream_t stream);
+int macr_ipc_alloc(size_t bytes, void **dev_ptr, unsigned char handle_out[MACR_IPC_HANDLE_BYTES]);
+int macr_ipc_open(const unsigned char handle[MACR_IPC_HANDLE_BYTES], void **peer_ptr);
+int macr_ipc_close(void *peer_ptr);
+int macr_ipc_free(void *dev_ptr);
+
 #ifdef __cplusplus
 }
 #endif

@@ -18,6 +18,13 @@ f32 = C.c_float
 sz = C.c_size_t
 
 
+class ShardDesc(C.Structure):
+    """macr_shard_desc of include/macr_b200.h."""
+
+    _fields_ = [("rank", C.c_int32), ("world", C.c_int32), ("u_lo", i64), ("u_hi", i64),
+                ("i_lo", i64), ("i_hi", i64), ("max_batch", C.c_int32)]
+
+
 class MacrError(RuntimeError):
     pass
 
@@ -91,6 +98,15 @@ PROTOTYPES = {
     "macr_foldout_metrics": (i32, [vp, i32, i32, vp, vp, vp, vp, vp]),
     "macr_sample_mf": (i32, [vp, vp, i32, i32, i32, vp, vp, vp, i32, vp, vp, vp]),
     "macr_sample_lgcn": (i32, [vp, vp, vp, i32, i32, i32, vp, vp, vp, vp, i32, vp, vp, vp]),
+    "macr_shard_pack": (i32, [vp, vp, C.POINTER(ShardDesc), vp, i32, i32, vp, vp, vp]),
+    "macr_shard_unpack": (i32, [vp, vp, C.POINTER(ShardDesc), vp, i32, i32, vp]),
+    "macr_shard_push": (i32, [vp, vp, C.POINTER(ShardDesc), vp, i32, i32, vp, C.POINTER(vp),
+                              C.POINTER(vp), vp]),
+    "macr_shard_barrier": (i32, [C.POINTER(vp), i32, i32, C.c_uint64, vp, vp]),
+    "macr_ipc_alloc": (i32, [sz, C.POINTER(vp), C.c_char_p]),
+    "macr_ipc_open": (i32, [C.c_char_p, C.POINTER(vp)]),
+    "macr_ipc_close": (i32, [vp]),
+    "macr_ipc_free": (i32, [vp]),
 }
 
 

@@ -1,0 +1,205 @@
+// shard.cu -- row-partitioned tables over the GPUs of one box: the exchange of the
+// batch's rows between the ranks, fused with the id renumbering.
+//
+// Every rank owns a contiguous id range of both embedding tables (and of their Adam slots).  A
+// training step needs the 3B rows of the batch on every rank; every row has exactly one owner.
+// Behind the owned rows each local table carries GHOST rows, two parities of them:
+//
+//     U_local : [ n_local_u owned rows | parity 0: maxB ghosts  | parity 1: maxB ghosts  ]
+//     I_local : [ n_local_i owned rows | parity 0: 2maxB ghosts | parity 1: 2maxB ghosts ]
+//
+// Batch position b of the user column lives in ghost `b`, of the pos column in ghost `b`, of the
+// neg column in ghost `B + b`.  The step graph then runs on local ids unchanged.
+//
+// Two transports:
+//   * push (NVLink peer stores): ONE kernel renumbers the ids and stores each owned row straight
+//     into the ghost slot of every peer's table (pointers from cudaIpcOpenMemHandle), then a
+//     one-warp flag barrier over peer memory (st.release.sys / ld.acquire.sys).  No staging
+//     buffer, no reduction, no copy: gather + all-gather in one pass over the owned rows.  Ghost
+//     parities alternate per step, so a fast peer may already push step t+1 while this rank still
+//     runs step t (it cannot reach t+2 before this rank has passed barrier t+1).
+//   * pack (for an NCCL all-reduce by the caller): owned rows -> ex[3B][64], zeros elsewhere;
+//     after the sum macr_shard_unpack copies ex into the ghost slots.
+#include "train_kernels.cuh"
+
+namespace macr {
+
+constexpr int kMaxRanks = MACR_SHARD_MAX_RANKS;
+
+struct PeerTabs {
+  float *u[kMaxRanks];  // ghost base (row n_local_u of rank r's U_local) as mapped in THIS process
+  float *i[kMaxRanks];
+};
+struct PeerFlags {
+  unsigned long long *p[kMaxRanks];  // rank r's flag array [world]
+};
+
+template <bool PUSH>
+__global__ void __launch_bounds__(256)
+shard_exchange_kernel(const float *__restrict__ U, const float *__restrict__ I, macr_shard_desc a,
+                      const int32_t *__restrict__ ids3, int B, int parity,
+                      int32_t *__restrict__ local3, float *__restrict__ ex, PeerTabs peers) {
+  const int q = (blockIdx.x * blockDim.x + threadIdx.x) >> 4, hl = threadIdx.x & 15;
+  if (q >= 3 * B) return;
+  const bool is_user = q < B;
+  const long long id = ids3[q];
+  const long long lo = is_user ? a.u_lo : a.i_lo, hi = is_user ? a.u_hi : a.i_hi;
+  const bool own = id >= lo && id < hi;
+  const long long ghost = is_user ? (long long)parity * a.max_batch + q
+                                  : (long long)parity * 2 * a.max_batch + (q - B);
+  if (hl == 0) local3[q] = (int32_t)(own ? id - lo : (hi - lo) + ghost);
+  const float4 *src = reinterpret_cast<const float4 *>((is_user ? U : I) + (id - lo) * kD) + hl;
+  if (PUSH) {
+    if (!own) return;
+    const float4 v = *src;
+#pragma unroll 1
+    for (int r = 0; r < a.world; ++r) {
+      if (r == a.rank) continue;
+      float *dst = is_user ? peers.u[r] : peers.i[r];
+      st_stream(reinterpret_cast<float4 *>(dst + ghost * kD) + hl, v);
+    }
+  } else {
+    reinterpret_cast<float4 *>(ex + (long long)q * kD)[hl] = own ? *src : make_float4(0.f, 0.f, 0.f, 0.f);
+  }
+}
+
+// one warp: lane r signals peer r (flags_r[me] = epoch) and waits for peer r (flags_me[r] >= epoch).
+// A peer that never arrives raises *err instead of hanging the GPU.
+__global__ void shard_barrier_kernel(PeerFlags f, int rank, int world, unsigned long long epoch,
+                                     long long spin_limit, int *err) {
+  const int r = threadIdx.x;
+  if (r >= world || r == rank) return;
+  __threadfence_system();
+  asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(f.p[r] + rank), "l"(epoch) : "memory");
+  const unsigned long long *mine = f.p[rank] + r;
+  const long long t0 = clock64();
+  for (;;) {
+    unsigned long long v;
+    asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(mine) : "memory");
+    if (v >= epoch) break;
+    if (clock64() - t0 > spin_limit) {
+      atomicExch(err, 1 + r);
+      break;
+    }
+  }
+}
+
+static int check_desc(const macr_shard_desc *d, int B, const char *who) {
+  MACR_CHECK_ARG(d, "%s: null descriptor", who);
+  MACR_CHECK_ARG(d->world >= 1 && d->world <= kMaxRanks && d->rank >= 0 && d->rank < d->world,
+                 "%s: rank %d / world %d outside [0,%d]", who, d->rank, d->world, kMaxRanks);
+  MACR_CHECK_ARG(d->u_lo <= d->u_hi && d->i_lo <= d->i_hi && d->u_lo >= 0 && d->i_lo >= 0,
+                 "%s: bad id ranges", who);
+  MACR_CHECK_ARG(d->max_batch > 0 && B > 0 && B <= d->max_batch, "%s: batch %d outside (0,%d]", who, B,
+                 d->max_batch);
+  return MACR_OK;
+}
+
+}  // namespace macr
+
+using namespace macr;
+
+extern "C" int macr_shard_pack(const float *U_local, const float *I_local, const macr_shard_desc *desc,
+                               const int32_t *ids3, int B, int parity, int32_t *local_ids3, float *ex,
+                               macr_stream_t stream) {
+  int rc = check_desc(desc, B, "macr_shard_pack");
+  if (rc) return rc;
+  MACR_CHECK_ARG(U_local && I_local && ids3 && local_ids3 && ex, "macr_shard_pack: null pointer");
+  MACR_CHECK_ARG(parity == 0 || parity == 1, "macr_shard_pack: parity must be 0 or 1");
+  PeerTabs none{};
+  shard_exchange_kernel<false><<<(unsigned)((3LL * B * 16 + 255) / 256), 256, 0, as_stream(stream)>>>(
+      U_local, I_local, *desc, ids3, B, parity, local_ids3, ex, none);
+  MACR_LAUNCH_CHECK();
+  return MACR_OK;
+}
+
+extern "C" int macr_shard_unpack(float *U_local, float *I_local, const macr_shard_desc *desc,
+                                 const float *ex, int B, int parity, macr_stream_t stream) {
+  int rc = check_desc(desc, B, "macr_shard_unpack");
+  if (rc) return rc;
+  MACR_CHECK_ARG(U_local && I_local && ex, "macr_shard_unpack: null pointer");
+  MACR_CHECK_ARG(parity == 0 || parity == 1, "macr_shard_unpack: parity must be 0 or 1");
+  const long long mb = desc->max_batch;
+  float *ug = U_local + ((desc->u_hi - desc->u_lo) + parity * mb) * kD;
+  float *ig = I_local + ((desc->i_hi - desc->i_lo) + parity * 2 * mb) * kD;
+  cudaStream_t s = as_stream(stream);
+  MACR_CUDA(cudaMemcpyAsync(ug, ex, sizeof(float) * kD * (size_t)B, cudaMemcpyDeviceToDevice, s));
+  MACR_CUDA(cudaMemcpyAsync(ig, ex + (size_t)B * kD, sizeof(float) * kD * 2 * (size_t)B,
+                            cudaMemcpyDeviceToDevice, s));
+  return MACR_OK;
+}
+
+extern "C" int macr_shard_push(const float *U_local, const float *I_local, const macr_shard_desc *desc,
+                               const int32_t *ids3, int B, int parity, int32_t *local_ids3,
+                               float *const *peer_U_ghost_host, float *const *peer_I_ghost_host,
+                               macr_stream_t stream) {
+  int rc = check_desc(desc, B, "macr_shard_push");
+  if (rc) return rc;
+  MACR_CHECK_ARG(U_local && I_local && ids3 && local_ids3 && peer_U_ghost_host && peer_I_ghost_host,
+                 "macr_shard_push: null pointer");
+  MACR_CHECK_ARG(parity == 0 || parity == 1, "macr_shard_push: parity must be 0 or 1");
+  PeerTabs peers{};
+  for (int r = 0; r < desc->world; ++r) {
+    peers.u[r] = peer_U_ghost_host[r];
+    peers.i[r] = peer_I_ghost_host[r];
+    MACR_CHECK_ARG(r == desc->rank || (peers.u[r] && peers.i[r]), "macr_shard_push: null peer %d", r);
+  }
+  shard_exchange_kernel<true><<<(unsigned)((3LL * B * 16 + 255) / 256), 256, 0, as_stream(stream)>>>(
+      U_local, I_local, *desc, ids3, B, parity, local_ids3, nullptr, peers);
+  MACR_LAUNCH_CHECK();
+  return MACR_OK;
+}
+
+extern "C" int macr_shard_barrier(uint64_t *const *peer_flags_host, int rank, int world, uint64_t epoch,
+                                  int *err_flag, macr_stream_t stream) {
+  MACR_CHECK_ARG(peer_flags_host && err_flag, "macr_shard_barrier: null pointer");
+  MACR_CHECK_ARG(world >= 1 && world <= kMaxRanks && rank >= 0 && rank < world,
+                 "macr_shard_barrier: rank %d / world %d", rank, world);
+  if (world == 1) return MACR_OK;
+  PeerFlags f{};
+  for (int r = 0; r < world; ++r) {
+    MACR_CHECK_ARG(peer_flags_host[r], "macr_shard_barrier: null flags of rank %d", r);
+    f.p[r] = reinterpret_cast<unsigned long long *>(peer_flags_host[r]);
+  }
+  // ~10 s at 2 GHz: ranks are host-synchronised before the first step, so a longer wait means a
+  // dead peer; the step then reports it through macr_shard_check instead of hanging the device
+  shard_barrier_kernel<<<1, 32, 0, as_stream(stream)>>>(f, rank, world, (unsigned long long)epoch,
+                                                        20000000000LL, err_flag);
+  MACR_LAUNCH_CHECK();
+  return MACR_OK;
+}
+
+// ---- peer-mappable device memory (CUDA IPC) ---------------------------------------------------
+extern "C" int macr_ipc_alloc(size_t bytes, void **dev_ptr, unsigned char handle_out[MACR_IPC_HANDLE_BYTES]) {
+  MACR_CHECK_ARG(dev_ptr && handle_out && bytes > 0, "macr_ipc_alloc: bad argument");
+  static_assert(sizeof(cudaIpcMemHandle_t) == MACR_IPC_HANDLE_BYTES, "IPC handle size");
+  void *p = nullptr;
+  MACR_CUDA(cudaMalloc(&p, bytes));
+  cudaIpcMemHandle_t h;
+  cudaError_t e = cudaIpcGetMemHandle(&h, p);
+  if (e != cudaSuccess) {
+    cudaFree(p);
+    return fail(MACR_ERR_CUDA, "cudaIpcGetMemHandle: %s", cudaGetErrorString(e));
+  }
+  memcpy(handle_out, &h, sizeof(h));
+  *dev_ptr = p;
+  return MACR_OK;
+}
+
+extern "C" int macr_ipc_open(const unsigned char handle[MACR_IPC_HANDLE_BYTES], void **peer_ptr) {
+  MACR_CHECK_ARG(handle && peer_ptr, "macr_ipc_open: null argument");
+  cudaIpcMemHandle_t h;
+  memcpy(&h, handle, sizeof(h));
+  MACR_CUDA(cudaIpcOpenMemHandle(peer_ptr, h, cudaIpcMemLazyEnablePeerAccess));
+  return MACR_OK;
+}
+
+extern "C" int macr_ipc_close(void *peer_ptr) {
+  if (peer_ptr) MACR_CUDA(cudaIpcCloseMemHandle(peer_ptr));
+  return MACR_OK;
+}
+
+extern "C" int macr_ipc_free(void *dev_ptr) {
+  if (dev_ptr) MACR_CUDA(cudaFree(dev_ptr));
+  return MACR_OK;
+}

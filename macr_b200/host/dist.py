@@ -20,7 +20,8 @@ The training step does not shard profitably at benchmark sizes (a ~60 us step): 
 replicas.  For tables whose dense-Adam traffic dominates (SURVEY 8e rows "dense Adam sweep" and
 "gather + grid + row grads"; config 5: 16.9 GB per step on one GPU) ``RowShardedMFTrainer``
 row-partitions both tables with their Adam slots: one all-reduce of the 3B gathered rows per step
-is the whole exchange, everything else is the single-GPU step on the local slice.
+is the whole exchange, everything else is the single-GPU step on the local slice; with one rank
+per GPU the exchange is a fused push over NVLink peer memory instead (csrc/shard.cu).
 """
 import numpy as np
 import torch
@@ -130,25 +131,30 @@ class RowShardedMFTrainer:
     """MF training with the two embedding tables AND their Adam slots row-partitioned over the
     ranks (contiguous id ranges, `user_shard_bounds` / `item_shard_bounds`).
 
-    One step = one exchange + the unchanged single-GPU step graph on the local slice:
+    One step = one exchange + the unchanged single-GPU step graph on the local slice.  Behind its
+    owned rows every local table carries ghost rows (two parities, csrc/shard.cu); batch position
+    b of the user / pos / neg column lives in ghost b / b / B+b.  Two transports for the exchange:
 
-    1. every rank gathers the rows it owns among the batch's 3B ids (zeros elsewhere) and ONE
-       all-reduce (sum; exactly one owner per row, so the sum is exact) hands every rank all 3B
-       rows (`3*B*64*4` bytes: 3 MB at B = 4096);
-    2. rows of other ranks are parked in ghost rows appended to the local tables
-       (`n_local + position`), ids are renumbered (owned -> `id - lo`, foreign -> ghost slot);
-    3. `macr_mf_trainer_step` runs as on one GPU.  Dots, the B x B grid, the losses and the
-       gradients of `w` / `w_user` depend on batch positions only, so they come out identical on
-       every rank (replicated work, ~25 us); row gradients and Adam touch owned rows exactly as the
-       single-GPU step does (same segments, same summation order) and the dense sweep covers only
-       the local slice -- the HBM traffic per rank is 1/G of the single-GPU step's.  Ghost rows
-       receive meaningless updates and are overwritten before they are read again.
+    * ``push`` (one rank per GPU, NVLink): ONE kernel renumbers the ids (owned -> `id - lo`,
+      foreign -> ghost slot) and stores every owned row straight into the ghost slot of every
+      peer's table through CUDA-IPC mapped peer memory, then a one-warp flag barrier over peer
+      memory -- gather and all-gather fused, no staging buffer, no reduction.
+    * ``allreduce``: `macr_shard_pack` writes the owned rows (zeros elsewhere) into `ex[3B,64]`,
+      ONE all-reduce (sum; exactly one owner per row, so the sum is exact) hands every rank all 3B
+      rows, `macr_shard_unpack` copies them into the ghost slots.  NCCL, or gloo for the tests.
+
+    Then `macr_mf_trainer_step` runs as on one GPU.  Dots, the B x B grid, the losses and the
+    gradients of `w` / `w_user` depend on batch positions only, so they come out identical on
+    every rank (replicated work); row gradients and Adam touch owned rows exactly as the
+    single-GPU step does (same segments, same summation order) and the dense sweep covers only
+    the local slice -- the HBM traffic per rank is 1/G of the single-GPU step's.  Ghost rows
+    receive meaningless updates and are overwritten before they are read again.
 
     The owned slices are bit-identical to the corresponding rows of a single-GPU run
-    (tests/test_gpu_dist.py).  Batches must be identical on every rank."""
+    (tests/test_gpu_dist.py, tests/test_gpu_multi.py).  Batches must be identical on every rank."""
 
     def __init__(self, U, I, w, wu, hp, max_batch, rank=None, world=None, device="cuda:0", group=None,
-                 ops_module=None):
+                 ops_module=None, exchange="auto"):
         if ops_module is None:  # the CUDA library; the CPU plumbing test injects a stand-in
             from .. import ops as ops_module
         ops = ops_module
@@ -160,41 +166,120 @@ class RowShardedMFTrainer:
         self.u_lo, self.u_hi = int(ub[self.rank]), int(ub[self.rank + 1])
         self.i_lo, self.i_hi = int(ib[self.rank]), int(ib[self.rank + 1])
         self.n_lu, self.n_li = self.u_hi - self.u_lo, self.i_hi - self.i_lo
-        d = U.shape[1]
-        ghost = lambda rows: np.zeros((rows, d), np.float32)
-        Uloc = np.concatenate([np.asarray(U[self.u_lo:self.u_hi], np.float32), ghost(max_batch)])
-        Iloc = np.concatenate([np.asarray(I[self.i_lo:self.i_hi], np.float32), ghost(2 * max_batch)])
+        self.desc = ops.ShardDesc(self.rank, self.world, self.u_lo, self.u_hi, self.i_lo, self.i_hi, max_batch)
+        dev = torch.device(device)
+        if exchange not in ("auto", "push", "allreduce"):
+            raise ValueError(f"exchange {exchange!r}")
+        want_push = (exchange != "allreduce" and self.world > 1 and dev.type == "cuda"
+                     and dist.is_initialized() and dist.get_backend(group) == "nccl")
+        if exchange == "push" and not want_push:
+            raise ValueError("exchange='push' needs world > 1, CUDA and one rank per GPU (NCCL group)")
+        Uloc, self._ipc_u = ops.shard_table(self.n_lu + 2 * max_batch, dev, peer_mappable=want_push)
+        Iloc, self._ipc_i = ops.shard_table(self.n_li + 4 * max_batch, dev, peer_mappable=want_push)
+        as_t = lambda a: a if isinstance(a, torch.Tensor) else torch.from_numpy(np.ascontiguousarray(a, np.float32))
+        Uloc[: self.n_lu].copy_(as_t(U[self.u_lo:self.u_hi]))
+        Iloc[: self.n_li].copy_(as_t(I[self.i_lo:self.i_hi]))
         self.trainer = ops.MFTrainer(Uloc, Iloc, w, wu, hp, max_batch=max_batch, device=device)
         self.dev = self.trainer.dev
-        self._pos = torch.arange(2 * max_batch, dtype=torch.int32, device=self.dev)
+        self._local3 = torch.zeros(3 * max_batch, dtype=torch.int32, device=self.dev)
+        self._ex = torch.zeros((3 * max_batch, Uloc.shape[1]), dtype=torch.float32, device=self.dev)
+        self._step, self._epoch, self._peers = 0, 0, []
+        self._epoch_ids = self._epoch_losses = None
+        self.exchange = "allreduce" if self.world > 1 else "none"
+        if want_push:
+            self._open_peers(strict=exchange == "push")
 
-    def _localize(self, ids, lo, hi, n_local, slot0):
-        """global ids -> (local ids with foreign rows sent to ghost slots, ownership mask)"""
-        own = (ids >= lo) & (ids < hi)
-        ghost = n_local + slot0 + self._pos[: ids.numel()]
-        return torch.where(own, ids - lo, ghost).to(torch.int32), own
+    # ---- peer memory (push transport) ---------------------------------------------------------
+    def _open_peers(self, strict):
+        import ctypes as C
 
-    def step_device(self, users, pos, neg):
-        """users / pos / neg: int32 device tensors [B] of GLOBAL ids, identical on every rank.
-        Returns the device tensor [loss, mf, reg, L_ori] (identical on every rank); no sync."""
-        ops, t = self.ops, self.trainer.tab
-        B = users.numel()
-        lu, own_u = self._localize(users, self.u_lo, self.u_hi, self.n_lu, 0)
-        lp, own_p = self._localize(pos, self.i_lo, self.i_hi, self.n_li, 0)
-        ln, own_n = self._localize(neg, self.i_lo, self.i_hi, self.n_li, B)
-        rows = torch.cat([ops.gather_rows(t.U, lu), ops.gather_rows(t.I, torch.cat([lp, ln]))])
-        own = torch.cat([own_u, own_p, own_n]).unsqueeze(1)
-        ex = torch.where(own, rows, torch.zeros((), dtype=torch.float32, device=self.dev))
+        ops = self.ops
+        self._ipc_flags = ops.IpcBuffer(8 * 16, self.dev)
+        self._err = torch.zeros(1, dtype=torch.int32, device=self.dev)
+        mine = (self._ipc_u.handle, self._ipc_i.handle, self._ipc_flags.handle, self.n_lu, self.n_li)
+        every = [None] * self.world
+        dist.all_gather_object(every, mine, group=self.group)
+        pu, pi, pf = ((C.c_void_p * self.world)() for _ in range(3))
+        ok = 1
+        try:
+            for r, (hu, hi, hf, n_lu, n_li) in enumerate(every):
+                if r == self.rank:
+                    pu[r], pi[r], pf[r] = None, None, self._ipc_flags.ptr
+                    continue
+                bu, bi, bf = (ops.IpcBuffer.open_peer(h) for h in (hu, hi, hf))
+                self._peers += [bu, bi, bf]
+                pu[r], pi[r], pf[r] = bu + n_lu * 256, bi + n_li * 256, bf  # ghost bases: row n_local
+        except ops.MacrError:
+            if strict:
+                raise
+            ok = 0
+        flag = torch.tensor([ok], dtype=torch.int32, device=self.dev)
+        dist.all_reduce(flag, op=dist.ReduceOp.MIN, group=self.group)  # every rank mapped every peer?
+        if int(flag.item()) == 1:
+            self._peer_u, self._peer_i, self._peer_f = pu, pi, pf
+            self.exchange = "push"
+        torch.cuda.synchronize(self.dev)
+        dist.barrier(group=self.group)  # flags are zeroed and mapped everywhere before the first push
+
+    def check_peers(self):
+        """Raise if a flag barrier timed out (a peer died); synchronises."""
+        if self.exchange == "push":
+            e = int(self._err.item())
+            if e:
+                raise self.ops.MacrError(f"rank {self.rank}: peer {e - 1} never reached the exchange barrier")
+
+    # ---- one step -----------------------------------------------------------------------------
+    def exchange_rows(self, ids3, B):
+        """ids3: int32 device tensor [3B] = users | pos | neg, GLOBAL ids, identical on every rank.
+        Leaves the renumbered ids in `self._local3[:3B]` and every foreign row in its ghost slot."""
+        ops, t, par = self.ops, self.trainer.tab, self._step & 1
+        self._step += 1
+        if self.exchange == "push":
+            ops.shard_push(t.U, t.I, self.desc, ids3, B, par, self._local3, self._peer_u, self._peer_i)
+            self._epoch += 1
+            ops.shard_barrier(self._peer_f, self.rank, self.world, self._epoch, self._err)
+            return
+        ex = self._ex[: 3 * B]
+        ops.shard_pack(t.U, t.I, self.desc, ids3, B, par, self._local3, ex)
         if self.world > 1:  # every row has exactly one owner: x + 0 + ... is exact
             if ex.is_cuda and dist.get_backend(self.group) == "gloo":
                 host = ex.cpu()  # gloo (several ranks sharing one GPU in the tests): stage through the host
                 dist.all_reduce(host, group=self.group)
                 ex.copy_(host)
             else:
-                dist.all_reduce(ex, group=self.group)  # NCCL over NVLink, on the step's stream order
-        t.U[self.n_lu:self.n_lu + B].copy_(ex[:B])           # ghost slots (owned positions unused)
-        t.I[self.n_li:self.n_li + 2 * B].copy_(ex[B:])
-        return self.trainer.step_device(lu, lp, ln)
+                dist.all_reduce(ex, group=self.group)  # NCCL over NVLink, in the step's stream order
+            ops.shard_unpack(t.U, t.I, self.desc, ex, B, par)
+
+    def step_ids3(self, ids3, B, loss_out=None):
+        """One training step on the [3B] global ids.  Returns the device tensor [loss, mf, reg,
+        L_ori] (identical on every rank), written to `loss_out` ([1,4] device) if given; no sync."""
+        self.exchange_rows(ids3, B)
+        l3 = self._local3
+        if loss_out is not None:
+            return self.trainer.run(l3[: 3 * B].view(1, 3, B), loss_out)
+        return self.trainer.step_device(l3[:B], l3[B:2 * B], l3[2 * B:3 * B])
+
+    def step_device(self, users, pos, neg):
+        """users / pos / neg: int32 device tensors [B] of GLOBAL ids, identical on every rank."""
+        return self.step_ids3(torch.cat([users, pos, neg]), users.numel())
+
+    def run_host(self, batches_host, losses_host=None):
+        """Epoch call with HOST buffers: `batches_host` int32 [n,3,B] (pinned recommended, identical
+        on every rank) -> float32 [n,4] host losses; one H2D, n exchanges + steps, one D2H, one sync."""
+        n, three, B = batches_host.shape
+        assert three == 3 and batches_host.dtype == torch.int32 and not batches_host.is_cuda
+        if self._epoch_ids is None or self._epoch_ids.shape[0] < n or self._epoch_ids.shape[2] != B:
+            self._epoch_ids = torch.empty((n, 3, B), dtype=torch.int32, device=self.dev)
+            self._epoch_losses = torch.empty((n, 4), dtype=torch.float32, device=self.dev)
+        ids, losses = self._epoch_ids[:n], self._epoch_losses[:n]
+        ids.copy_(batches_host, non_blocking=True)
+        for s in range(n):
+            self.step_ids3(ids[s].view(-1), B, losses[s:s + 1])
+        if losses_host is None:
+            losses_host = torch.empty((n, 4), dtype=torch.float32)
+        losses_host.copy_(losses, non_blocking=True)
+        torch.cuda.current_stream(self.dev).synchronize()
+        return losses_host
 
     def local_tables(self):
         """views of the owned rows: (U[u_lo:u_hi], I[i_lo:i_hi]) and their Adam slots by name"""
@@ -204,4 +289,17 @@ class RowShardedMFTrainer:
                 "w": t.w, "wu": t.wu}
 
     def close(self):
+        if self.trainer is None:
+            return
+        if self.world > 1 and self.dev.type == "cuda":
+            torch.cuda.synchronize(self.dev)
+            if dist.is_initialized():
+                dist.barrier(group=self.group)  # no peer may still be pushing into this rank's tables
         self.trainer.close()
+        self.trainer = None
+        for p in self._peers:
+            self.ops.IpcBuffer.close_peer(p)
+        self._peers = []
+        for buf in (self._ipc_u, self._ipc_i, getattr(self, "_ipc_flags", None)):
+            if buf is not None:
+                buf.free()

@@ -11,7 +11,7 @@ import numpy as np
 import torch
 
 from . import _lib
-from ._lib import HParams, MacrError, check, lib, ptr, stream_ptr
+from ._lib import HParams, MacrError, ShardDesc, check, lib, ptr, stream_ptr
 
 D = 64
 MAX_TOPK = 32
@@ -48,14 +48,18 @@ def gather_dots(Ue, Ie, Ur, Ir, w, wu, users, pos, neg):
     return tuple(out[k, :B] for k in range(6))
 
 
-def grid_bce(yp, yn, sp, sn, su, alpha, beta, want_grad=True):
-    """-> (losses3 [L_ori, L_item, L_user], (d_yp, d_yn, d_sp, d_sn, d_su) or None)."""
+def grid_bce(yp, yn, sp, sn, su, alpha, beta, want_grad=True, bufs=None):
+    """-> (losses3 [L_ori, L_item, L_user], (d_yp, d_yn, d_sp, d_sn, d_su) or None).
+    bufs: optional (ws uint8, losses f32[3], grads f32[5,B]) from an earlier call, reused as they are."""
     B = yp.numel()
     dev = yp.device
     nbytes = lib().macr_grid_bce_workspace_bytes(B)
-    ws = torch.empty(nbytes, dtype=torch.uint8, device=dev)
-    losses = torch.empty(3, dtype=torch.float32, device=dev)
-    grads = torch.empty((5, B), dtype=torch.float32, device=dev) if want_grad else None
+    if bufs is not None:
+        ws, losses, grads = bufs
+    else:
+        ws = torch.empty(nbytes, dtype=torch.uint8, device=dev)
+        losses = torch.empty(3, dtype=torch.float32, device=dev)
+        grads = torch.empty((5, B), dtype=torch.float32, device=dev) if want_grad else None
     gp = [ptr(grads[k]) for k in range(5)] if want_grad else [None] * 5
     check(lib().macr_grid_bce_fwd_bwd(_f(yp), _f(yn), _f(sp), _f(sn), _f(su), B, alpha, beta,
                                       ptr(losses), *gp, ptr(ws), nbytes, stream_ptr()),
@@ -247,7 +251,11 @@ class _Tables:
     """The four trainable tensors + Adam slots of one model, resident in HBM (row-major fp32)."""
 
     def __init__(self, U, I, w, wu, device):
-        t = lambda a: torch.as_tensor(np.ascontiguousarray(a, dtype=np.float32)).to(device).contiguous()
+        def t(a):  # host arrays are copied to the device; resident fp32 CUDA tensors are adopted as they are
+            if isinstance(a, torch.Tensor) and a.is_cuda:
+                return _cuda(a, torch.float32)
+            return torch.as_tensor(np.ascontiguousarray(a, dtype=np.float32)).to(device).contiguous()
+
         self.U, self.I = t(U), t(I)
         self.w, self.wu = t(np.asarray(w).reshape(-1)), t(np.asarray(wu).reshape(-1))
         z = torch.zeros_like
@@ -474,6 +482,70 @@ class LGCNTrainer:
             self.close()
         except Exception:
             pass
+
+
+# ------------------------------------------------------------------------------------------------
+# row-partitioned tables (csrc/shard.cu): peer-mappable memory, the fused exchange kernels
+# ------------------------------------------------------------------------------------------------
+class IpcBuffer:
+    """cudaMalloc'ed, zero-filled device memory with its CUDA IPC handle (64 opaque bytes) so the
+    other ranks of the box can map it (`IpcBuffer.open_peer`)."""
+
+    def __init__(self, nbytes, device):
+        self.dev = torch.device(device)
+        torch.cuda.set_device(self.dev)
+        out, handle = C.c_void_p(), C.create_string_buffer(64)
+        check(lib().macr_ipc_alloc(int(nbytes), C.byref(out), handle), "macr_ipc_alloc")
+        self.ptr, self.handle, self.nbytes = out.value, handle.raw, int(nbytes)
+        self.as_f32((self.nbytes // 4,)).zero_()
+
+    def as_f32(self, shape):
+        return _wrap_device_ptr(self.ptr, tuple(shape), self.dev)
+
+    @staticmethod
+    def open_peer(handle):
+        out = C.c_void_p()
+        check(lib().macr_ipc_open(handle, C.byref(out)), "macr_ipc_open")
+        return out.value
+
+    @staticmethod
+    def close_peer(p):
+        if p:
+            lib().macr_ipc_close(C.c_void_p(p))
+
+    def free(self):
+        if self.ptr:
+            lib().macr_ipc_free(C.c_void_p(self.ptr))
+            self.ptr = None
+
+
+def shard_table(rows, device, peer_mappable=False):
+    """Zero-filled [rows, 64] fp32 table; peer_mappable -> (tensor view, IpcBuffer) else (tensor, None)."""
+    if peer_mappable:
+        buf = IpcBuffer(rows * D * 4, device)
+        return buf.as_f32((rows, D)), buf
+    return torch.zeros((rows, D), dtype=torch.float32, device=device), None
+
+
+def shard_pack(U_local, I_local, desc, ids3, B, parity, local3, ex):
+    check(lib().macr_shard_pack(_f(U_local), _f(I_local), C.byref(desc), _i(ids3), B, parity, _i(local3),
+                                _f(ex), stream_ptr()), "macr_shard_pack")
+
+
+def shard_unpack(U_local, I_local, desc, ex, B, parity):
+    check(lib().macr_shard_unpack(_f(U_local), _f(I_local), C.byref(desc), _f(ex), B, parity, stream_ptr()),
+          "macr_shard_unpack")
+
+
+def shard_push(U_local, I_local, desc, ids3, B, parity, local3, peer_u, peer_i):
+    """peer_u / peer_i: ctypes arrays (c_void_p * world) of the peers' ghost bases in this process."""
+    check(lib().macr_shard_push(_f(U_local), _f(I_local), C.byref(desc), _i(ids3), B, parity, _i(local3),
+                                peer_u, peer_i, stream_ptr()), "macr_shard_push")
+
+
+def shard_barrier(peer_flags, rank, world, epoch, err_flag):
+    check(lib().macr_shard_barrier(peer_flags, rank, world, epoch, _i(err_flag), stream_ptr()),
+          "macr_shard_barrier")
 
 
 class _CudaArrayView:

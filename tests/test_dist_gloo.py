@@ -88,14 +88,17 @@ def test_shard_bounds_cover_everything():
 # step engine (the checker) in place of macr_mf_trainer_step
 # ------------------------------------------------------------------------------------------------
 class _OracleOps:
-    """Stand-in for `macr_b200.ops` on the CPU: same surface as far as RowShardedMFTrainer uses it."""
+    """Stand-in for `macr_b200.ops` on the CPU: same surface as far as RowShardedMFTrainer uses it
+    (the oracle as the step engine, a torch restatement of csrc/shard.cu's pack / unpack)."""
+
+    from macr_b200._lib import ShardDesc  # plain ctypes struct, no GPU needed
 
     class MFTrainer:
         def __init__(self, U, I, w, wu, hp, max_batch, device="cpu"):
             import oracle
 
             self.oracle, self.hp, self.dev = oracle, hp, torch.device("cpu")
-            self.st = oracle.MFState(U, I, w, wu)
+            self.st = oracle.MFState(U.numpy(), I.numpy(), w, wu)
 
             class Tab:
                 pass
@@ -111,8 +114,30 @@ class _OracleOps:
             pass
 
     @staticmethod
-    def gather_rows(table, ids):
-        return table[ids.long()].clone()
+    def shard_table(rows, device, peer_mappable=False):
+        return torch.zeros((rows, 64), dtype=torch.float32), None
+
+    @staticmethod
+    def _slots(desc, B, parity):
+        q = torch.arange(3 * B)
+        return torch.where(q < B, parity * desc.max_batch + q, parity * 2 * desc.max_batch + q - B)
+
+    @classmethod
+    def shard_pack(cls, U, I, desc, ids3, B, parity, local3, ex):
+        ids = ids3.long()
+        lo = torch.where(torch.arange(3 * B) < B, desc.u_lo, desc.i_lo)
+        hi = torch.where(torch.arange(3 * B) < B, desc.u_hi, desc.i_hi)
+        own = (ids >= lo) & (ids < hi)
+        local3[: 3 * B] = torch.where(own, ids - lo, (hi - lo) + cls._slots(desc, B, parity)).int()
+        rows = torch.cat([U[(ids[:B] - desc.u_lo).clamp(0, U.shape[0] - 1)],
+                          I[(ids[B:] - desc.i_lo).clamp(0, I.shape[0] - 1)]])
+        ex.copy_(torch.where(own[:, None], rows, torch.zeros(())))
+
+    @classmethod
+    def shard_unpack(cls, U, I, desc, ex, B, parity):
+        n_lu, n_li, mb = desc.u_hi - desc.u_lo, desc.i_hi - desc.i_lo, desc.max_batch
+        U[n_lu + parity * mb: n_lu + parity * mb + B] = ex[:B]
+        I[n_li + parity * 2 * mb: n_li + parity * 2 * mb + 2 * B] = ex[B:]
 
 
 def _train_worker(rank, world, port, out_dir):
@@ -142,7 +167,7 @@ def _train_worker(rank, world, port, out_dir):
             np.testing.assert_array_equal(loc[k].numpy(), full[lo:hi], err_msg=k)
         np.testing.assert_array_equal(loc["w"].numpy(), single.w)
         np.testing.assert_array_equal(loc["wu"].numpy(), single.wu)
-        assert (sh.u_hi - sh.u_lo) in (50, 51) and sh.trainer.tab.U.shape[0] == sh.n_lu + B
+        assert (sh.u_hi - sh.u_lo) in (50, 51) and sh.trainer.tab.U.shape[0] == sh.n_lu + 2 * B
         open(os.path.join(out_dir, f"train_ok{rank}"), "w").write("ok")
     finally:
         dist.destroy_process_group()

@@ -1,0 +1,152 @@
+"""Multi-GPU parity (skipped unless the box has >= 2 GPUs): one rank per GPU over NCCL.
+
+* `RowShardedMFTrainer` with both exchange transports -- the NCCL all-reduce of the packed rows and
+  the fused NVLink push (peer stores into the ghost rows + flag barrier, csrc/shard.cu) -- must
+  leave owned slices, w, w_user and losses BIT-identical to a single-GPU `MFTrainer` run
+  (SURVEY 8e rows "dense Adam sweep" / "gather + grid + row grads").
+* item-partitioned and user-partitioned full-catalogue scoring (tcgen05 path) must return exactly
+  the ids and scores of the unsharded call (SURVEY 8e row "full-catalogue scoring + top-K").
+"""
+import os
+import socket
+
+import numpy as np
+import pytest
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+from helpers import make_batch, make_model
+
+pytestmark = pytest.mark.gpu
+
+N_USERS, N_ITEMS, B, STEPS = 2001, 4745, 512, 6
+HP = dict(lr=1e-2, alpha=1e-2, beta=1e-3, decay=1e-4, batch_size=B)
+
+
+def _n_gpus():
+    return torch.cuda.device_count() if torch.cuda.is_available() else 0
+
+
+def _free_port():
+    with socket.socket() as s:
+        s.bind(("127.0.0.1", 0))
+        return s.getsockname()[1]
+
+
+def _batches():
+    rng = np.random.RandomState(72)
+    return [make_batch(rng, N_USERS, N_ITEMS, B) for _ in range(STEPS)]
+
+
+def _train_worker(rank, world, port, out_dir, exchange):
+    from macr_b200 import ops
+    from macr_b200.host import dist as mdist
+
+    os.environ["MASTER_ADDR"], os.environ["MASTER_PORT"] = "127.0.0.1", str(port)
+    torch.cuda.set_device(rank)
+    dev = torch.device("cuda", rank)
+    dist.init_process_group("nccl", rank=rank, world_size=world, device_id=dev)
+    try:
+        U, I, w, wu = make_model(71, N_USERS, N_ITEMS, scale=4.0)
+        sh = mdist.RowShardedMFTrainer(U, I, w, wu, ops.HParams.make(**HP), B, rank=rank, world=world,
+                                       device=dev, exchange=exchange)
+        assert sh.exchange == exchange, (sh.exchange, exchange)
+        losses = []
+        bt = _batches()
+        for u, p, n in bt[: STEPS // 2]:  # per-step device call
+            ids = [torch.from_numpy(np.asarray(x, np.int32)).to(dev) for x in (u, p, n)]
+            losses.append(sh.step_device(*ids).cpu().numpy().copy())
+        host = torch.from_numpy(np.stack([np.stack(b) for b in bt[STEPS // 2:]]).astype(np.int32)).pin_memory()
+        hl = sh.run_host(host)  # epoch call with host buffers
+        losses += [x for x in hl.numpy()]
+        sh.check_peers()
+        out = {k: v.cpu().numpy() for k, v in sh.local_tables().items()}
+        out["losses"] = np.stack(losses)
+        out["bounds"] = np.array([sh.u_lo, sh.u_hi, sh.i_lo, sh.i_hi])
+        np.savez(os.path.join(out_dir, f"{exchange}_rank{rank}.npz"), **out)
+        sh.close()
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("exchange", ["allreduce", "push"])
+def test_row_sharded_training_over_nccl_equals_single_gpu(tmp_path, exchange):
+    if _n_gpus() < 2:
+        pytest.skip("needs >= 2 GPUs")
+    from macr_b200 import ops
+
+    world = min(_n_gpus(), 4)
+    mp.spawn(_train_worker, args=(world, _free_port(), str(tmp_path), exchange), nprocs=world, join=True)
+    U, I, w, wu = make_model(71, N_USERS, N_ITEMS, scale=4.0)
+    tr = ops.MFTrainer(U, I, w, wu, ops.HParams.make(**HP), max_batch=B)
+    want = []
+    for u, p, n in _batches():
+        ids = [torch.from_numpy(np.asarray(x, np.int32)).cuda() for x in (u, p, n)]
+        want.append(tr.step_device(*ids).cpu().numpy().copy())
+    t = tr.tab
+    full = {k: getattr(t, k).cpu().numpy() for k in ("U", "mU", "vU", "I", "mI", "vI", "w", "wu")}
+    for r in range(world):
+        z = np.load(tmp_path / f"{exchange}_rank{r}.npz")
+        u_lo, u_hi, i_lo, i_hi = (int(x) for x in z["bounds"])
+        np.testing.assert_array_equal(z["losses"], np.stack(want))
+        for k in ("U", "mU", "vU"):
+            np.testing.assert_array_equal(z[k], full[k][u_lo:u_hi], err_msg=f"rank {r} {k}")
+        for k in ("I", "mI", "vI"):
+            np.testing.assert_array_equal(z[k], full[k][i_lo:i_hi], err_msg=f"rank {r} {k}")
+        np.testing.assert_array_equal(z["w"], full["w"])
+        np.testing.assert_array_equal(z["wu"], full["wu"])
+    tr.close()
+
+
+T_Q, S_ITEMS, K = 700, 9000, 20
+
+
+def _score_inputs():
+    rng = np.random.RandomState(5)
+    U, I, w, wu = make_model(9, T_Q, S_ITEMS, scale=12.0)
+    cnt = rng.randint(1, 40, T_Q)
+    rp = np.zeros(T_Q + 1, np.int32)
+    rp[1:] = np.cumsum(cnt)
+    col = np.concatenate([np.sort(rng.choice(S_ITEMS, c, replace=False)) for c in cnt]).astype(np.int32)
+    return U, I, w, wu, rp, col
+
+
+def _score_worker(rank, world, port, out_dir):
+    from macr_b200 import ops
+    from macr_b200.host import dist as mdist
+
+    os.environ["MASTER_ADDR"], os.environ["MASTER_PORT"] = "127.0.0.1", str(port)
+    torch.cuda.set_device(rank)
+    dev = torch.device("cuda", rank)
+    dist.init_process_group("nccl", rank=rank, world_size=world, device_id=dev)
+    try:
+        U, I, w, wu, rp, col = _score_inputs()
+        to = lambda a: torch.from_numpy(a).to(dev)
+        dU, dI, dw, dwu, drp, dcol = to(U), to(I), to(w), to(wu), to(rp), to(col)
+        su = ops.score_gates(dU, dwu)
+        for name, cls in (("items", mdist.ShardedScorer), ("users", mdist.UserShardedScorer)):
+            ids, sc = cls(dI, dw, rank=rank, world=world).topk(dU, su, 40.0, drp, dcol, K)
+            np.savez(os.path.join(out_dir, f"score_{name}_rank{rank}.npz"), ids=ids.cpu().numpy(),
+                     sc=sc.cpu().numpy())
+    finally:
+        dist.destroy_process_group()
+
+
+def test_sharded_scoring_over_nccl_equals_unsharded(tmp_path):
+    if _n_gpus() < 2:
+        pytest.skip("needs >= 2 GPUs")
+    from macr_b200 import ops
+
+    world = min(_n_gpus(), 4)
+    mp.spawn(_score_worker, args=(world, _free_port(), str(tmp_path)), nprocs=world, join=True)
+    U, I, w, wu, rp, col = _score_inputs()
+    to = lambda a: torch.from_numpy(a).cuda()
+    dU, dI = to(U), to(I)
+    ids, sc = ops.score_topk(dU, dI, ops.score_gates(dI, to(w)), ops.score_gates(dU, to(wu)), 40.0, to(rp),
+                             to(col), K)
+    for name in ("items", "users"):
+        for r in range(world):
+            z = np.load(tmp_path / f"score_{name}_rank{r}.npz")
+            np.testing.assert_array_equal(z["ids"], ids.cpu().numpy(), err_msg=f"{name} rank {r}")
+            np.testing.assert_array_equal(z["sc"], sc.cpu().numpy(), err_msg=f"{name} rank {r}")
