@@ -1033,14 +1033,20 @@ adam_sweep_kernel(SweepTable t0, SweepTable t1, long long per_cta, float lr_or_l
   }
 }
 
-static int sweep_ctas_per_sm() {
-  static int v = 0;
-  if (v == 0) {
-    const char *e = getenv("MACR_SWEEP_CTAS_PER_SM");  // tuning knob, default 3
-    v = e ? atoi(e) : 3;
-    if (v < 1 || v > 8) v = 3;
+// Resident sweep CTAs per SM.  3 fill the register file (85 regs x 256 threads x 3) and are the
+// fastest for L2-sized tables (gowalla: a 21 us sweep beside a 25 us grid).  For tables of GBs the
+// sweep runs for milliseconds and 3 CTAs/SM leave no room for the step's other kernels (gather,
+// B x B grid, row gradients), which then queue behind it: measured on the 10M x 1M tables, B=8192,
+// 3.54 ms/step with 3 CTAs/SM vs 3.02 ms with 2 (profiles/r2a_c5_probe.txt).
+static int sweep_ctas_per_sm(long long total_f4) {
+  static int v = -1;
+  if (v < 0) {
+    const char *e = getenv("MACR_SWEEP_CTAS_PER_SM");  // tuning knob, 0 / unset = by size
+    v = e ? atoi(e) : 0;
+    if (v < 0 || v > 8) v = 0;
   }
-  return v;
+  if (v) return v;
+  return total_f4 * 48 >= (256LL << 20) ? 2 : 3;  // >= 256 MiB of var + m + v
 }
 
 int launch_adam_sweep2(float *var0, float *m0, float *v0, int64_t rows0, const uint32_t *bm0,
@@ -1052,7 +1058,7 @@ int launch_adam_sweep2(float *var0, float *m0, float *v0, int64_t rows0, const u
   const long long total = t0.n4 + t1.n4;
   if (total == 0) return MACR_OK;
   constexpr int UNROLL = 4;
-  long long ctas = (long long)sm_count() * sweep_ctas_per_sm();
+  long long ctas = (long long)sm_count() * sweep_ctas_per_sm(total);
   const long long min_per = (long long)kSweepThreads * UNROLL;
   if (ctas * min_per > total) ctas = (total + min_per - 1) / min_per;
   long long per = (total + ctas - 1) / ctas;
