@@ -141,8 +141,10 @@ def host_rows(rows, seed, scale=1.0):
 # ------------------------------------------------------------------------------------------------
 class ClockSampler(threading.Thread):
     """SM clock + throttle reasons during the timed region (B200_PROFILING.md): NVML in-process
-    every 2 ms (an `nvidia-smi` invocation takes longer than the whole timed region), falling
-    back to polling `nvidia-smi` when pynvml is unavailable."""
+    (an `nvidia-smi` invocation takes longer than the whole timed region), first sample at once,
+    then every 20 ms -- NOT faster: every NVML clock query stalls the device's work for ~0.2 ms
+    (measured at N=2: 2.09 ms/step with a 2 ms period vs 1.60 ms with 50 ms or none,
+    profiles/r2c_nvml_period.txt).  Falls back to polling `nvidia-smi` when pynvml is unavailable."""
 
     Q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,"
          "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
@@ -150,9 +152,9 @@ class ClockSampler(threading.Thread):
     BITS = {"sw_power_cap": 0x4, "hw_slowdown": 0x8, "sw_thermal_slowdown": 0x20,
             "hw_thermal_slowdown": 0x40}
 
-    def __init__(self, index):
+    def __init__(self, index, period=0.02):
         super().__init__(daemon=True)
-        self.index, self.sm, self.mx, self.reasons = index, [], 0.0, set()
+        self.index, self.sm, self.mx, self.reasons, self.period = index, [], 0.0, set(), period
         self._stop_evt = threading.Event()
         self.nvml = None
         try:
@@ -206,7 +208,7 @@ class ClockSampler(threading.Thread):
                     self._poll_smi()
             except Exception:
                 pass
-            self._stop_evt.wait(0.002 if self.nvml is not None else 0.05)
+            self._stop_evt.wait(self.period if self.nvml is not None else 0.05)
 
     def stop(self):
         self._stop_evt.set()
@@ -417,7 +419,7 @@ def sharded_train(cx, K, W):
     for s in range(W):
         step(s)
     cx.barrier()
-    sampler = ClockSampler(cx.local_rank)
+    sampler = ClockSampler(cx.local_rank, period=float(os.environ.get("MACR_BENCH_CLOCK_PERIOD", "0.02")))
     sampler.start()
     e0, e1 = cx.events()
     cx.barrier()

@@ -10,8 +10,10 @@ torch.cuda.set_device(dev)
 w, wu = bench.synth_model(12345, 8, 8)[2:]
 hp = ops.HParams.make(**bench.C5_HP)
 B = bench.C5_BATCH
-U = bench.DeviceRows(bench.C5_USERS, 11, dev)[0:bench.C5_USERS]
-I = bench.DeviceRows(bench.C5_ITEMS, 13, dev)[0:bench.C5_ITEMS]
+DIV = int(os.environ.get("PROBE_DIV", "1"))  # tables of 1/DIV the size (what one of DIV ranks holds)
+NU, NI = bench.C5_USERS // DIV, bench.C5_ITEMS // DIV
+U = bench.DeviceRows(NU, 11, dev)[0:NU]
+I = bench.DeviceRows(NI, 13, dev)[0:NI]
 tr = ops.MFTrainer(U, I, w, wu, hp, max_batch=B, device=dev)
 t = tr.tab
 mode = os.environ.get("PROBE_STATE", "fill")
@@ -23,9 +25,9 @@ else:
     for m_, v_ in ((t.mU, t.vU), (t.mI, t.vI)):
         m_.normal_(0.0, 1e-4, generator=g); v_.uniform_(1e-9, 1e-7, generator=g)
 nb = 24
-bz = bench.synth_batches(12345, nb, bench.C5_USERS, bench.C5_ITEMS, B)
-bu = bz.copy(); bu[:, 1] = np.random.RandomState(3).randint(0, bench.C5_ITEMS, (nb, B))
-out = {}
+bz = bench.synth_batches(12345, nb, NU, NI, B)
+bu = bz.copy(); bu[:, 1] = np.random.RandomState(3).randint(0, NI, (nb, B))
+out = {"div": DIV, "sweep_ctas": os.environ.get("MACR_SWEEP_CTAS_PER_SM", "auto")}
 for name, b in (("zipf", bz), ("uniform", bu)):
     d_b = torch.from_numpy(b).to(dev)
     losses = torch.zeros((nb, 4), device=dev)
@@ -37,4 +39,10 @@ for name, b in (("zipf", bz), ("uniform", bu)):
     for s in range(4, nb): tr.run(d_b[s:s+1], losses[s:s+1])
     e1.record(); torch.cuda.synchronize()
     out[name + "_per_call_ms"] = e0.elapsed_time(e1) / (nb - 4)
+e0.record()
+for _ in range(5):
+    ops.adam_sweep_untouched(t.U, t.mU, t.vU, None, 1e-6)
+    ops.adam_sweep_untouched(t.I, t.mI, t.vI, None, 1e-6)
+e1.record(); torch.cuda.synchronize()
+out["sweep_alone_ms"] = e0.elapsed_time(e1) / 5
 print(json.dumps(out))
