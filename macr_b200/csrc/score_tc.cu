@@ -5,26 +5,33 @@
 //   replaces sess.run(model.rubi_ratings_both, ...) + host top-K
 //   (macr_mf/train.py:249-251,89-104; macr_lightgcn/utility/batch_test.py:85-134; model.py:45,199).
 //
-// Why two tensor-core passes.  A running per-row top-K in the epilogue costs ~K(1+ln(n/K)) list
-// insertions per row, serialised across the 32 rows a warp owns: far more than the pass itself
-// (half an instruction per score).  Instead:
+// Why a sampled threshold + ONE full pass.  A running per-row top-K in the epilogue costs
+// ~K(1+ln(n/K)) list insertions per row, serialised across the 32 rows a warp owns: far more than
+// the pass itself (half an instruction per score).  Instead:
 //   prep         items: bf16(sig_i * I_i) and the three bf16 pieces of -c*sig_i as an augmented K
 //                step (rows padded to whole tiles with -inf there); users: bf16(U), |u|.
-//   pass MAX     per (row, batch of 32 items): max of the approximate score.
-//   threshold    batches holding no train item of the row are dealt into 64 disjoint groups;
-//                m_K = K-th largest group maximum; thr = m_K - (eps_max + eps_filter + slack).  K
-//                distinct unmasked items score >= m_K, so the exact K-th best score is
-//                >= thr + eps_filter: every item of the true top-K passes the filter.
-//   pass FILTER  same MMAs again; batches whose maximum reaches the threshold are scanned and the
-//                items with score >= thr that are not train items of the row (a trained model
-//                ranks exactly those on top: a per-row cursor into the sorted train list marks
-//                them tile by tile) appended to the row's candidate list (one atomic per append).
-//   re-rank      one warp per row: exact fp32 FMA-chain score of the candidates (the arithmetic
-//                of score.cu), ranks by counting under the order (score desc, lower id first).
+//   pass MAX     over a SAMPLE of the item tiles (every `stride`-th tile, stride <= 4): per row and
+//                item chunk, 32 running maxima of the approximate score -- one per (32-column batch
+//                position, column residue mod 4) -- kept in registers, train items of the row left
+//                out.  The groups are disjoint item sets, so nothing but 128 bytes per (row, chunk)
+//                is written: no per-batch maxima matrix.
+//   threshold    m_K = K-th largest of the row's n_chunks*32 group maxima; thr = m_K - 2 eps - slack.
+//                K distinct unmasked items have an approximate score >= m_K, so the exact K-th best
+//                score is >= m_K - eps and every item of the true top-K scores >= thr in the next pass.
+//   pass FILTER  ONE pass over the whole catalogue: every batch's maximum is compared with thr
+//                (the same FMNMX chains as the maxima pass); scores >= thr that are not train items
+//                of the row (a trained model ranks exactly those on top: a per-row cursor into the
+//                sorted train list marks them tile by tile) are appended with their approximate
+//                score to the row's candidate list (~K*stride entries; one atomic per append).
+//   re-rank      one warp per row: a_K = K-th largest APPROXIMATE score of the list (radix select);
+//                K items score >= a_K, so the exact K-th best is >= a_K - eps and only candidates
+//                with approximate score >= a_K - 2 eps (~25) can be in the top-K: those are
+//                re-scored with the exact fp32 FMA chain (the arithmetic of score.cu) and ranked by
+//                counting under the order (score desc, lower id first).
 //   fallback     a row whose candidate list overflowed (degenerate score distributions), a row
-//                without K unmasked groups, or a row whose train list exceeds 1/16 of the
+//                without K finite group maxima, or a row whose train list exceeds 1/16 of the
 //                catalogue is done by the exact fp32 kernel (score.cu) -- never silently wrong.
-// eps_* are rigorous bounds of |approximate - exact| (see row_threshold_kernel).  Operands are
+// eps is a rigorous bound of |approximate - exact| (see row_threshold_kernel).  Operands are
 // rounded once to bf16: measured on B200, a 128-row SS-mode MMA instruction takes the same time
 // for tf32 (K=8) and bf16 (K=16), so bf16 halves the tensor time and the TMA bytes; a looser
 // bound only means more candidates, never a wrong id.
@@ -69,7 +76,10 @@ constexpr int KA = 16;
 constexpr int A_AUG_BYTES = BM * 32;
 constexpr int B_AUG_BYTES = BN * 32;
 constexpr int B_BYTES = B_TILE_BYTES + B_AUG_BYTES;  // one ring stage (40 KiB)
-constexpr int kCap = 128;            // candidate slots per row (4 x 32 lanes of the re-rank warp)
+constexpr int kCap = 256;            // candidate slots per row (approximate score, id)
+constexpr int kKeep = 128;           // candidates re-scored exactly per row (4 x 32 lanes of the re-rank warp)
+constexpr int kMaxStride = 4;        // the maxima pass samples every stride-th item tile
+constexpr int kMaxChunksS = 16;      // item chunks of the maxima pass (32 group maxima each)
 // 3 warpgroups: {TMA producer, MMA issuer, 2 idle warps} + 2 epilogue warpgroups.  The register
 // file is re-split with setmaxnreg once the roles part: 384 x 168 = 128 x 56 + 256 x 224.
 constexpr int kThreads = 384;
@@ -80,7 +90,6 @@ constexpr int STAGES = 4;            // item-tile ring (160 KiB)
 constexpr int A_BYTES = UT * (A_TILE_BYTES + A_AUG_BYTES);
 constexpr int SMEM_BYTES = 1024 /*align*/ + A_BYTES + STAGES * B_BYTES;
 constexpr int MODE_MAX = 0, MODE_FILTER = 1;
-constexpr int kPf = 2;               // filter pass: prefetch distance of the batch maxima, in tiles
 
 // ---- PTX wrappers ----------------------------------------------------------------------------
 __device__ __forceinline__ uint32_t smem_u32(const void *p) {
@@ -214,34 +223,40 @@ struct TileParams {
   int n_utiles;     // 256-row user tile pairs
   int n_itiles, n_chunks, tiles_per_chunk;
   int id_off;       // global id of local item 0 (candidates carry global ids)
-  int ld_tm;        // row pitch of the batch maxima (floats), NB per item tile
-  int dbg;          // developer timing experiments (0 = product path): bit0 skip the TMEM loads,
-                    // bit1 skip the epilogue arithmetic, bit2 skip the MMAs (results are then
-                    // meaningless)
+  int tile_stride;  // item tile visited for tile index t: t * tile_stride (maxima pass: the sample)
+  int ld_g;         // maxima pass: row pitch of the group maxima (floats) = 32 * n_chunks
+  int dbg;          // developer timing experiment: bit2 skips the MMAs (results are then meaningless)
 };
 
-// max over the 32 accumulator columns v[OFF .. OFF+32): 4 independent chains
+// fold the 32 accumulator columns v[OFF .. OFF+32) into the 4 running maxima of their column
+// residues mod 4 (4 independent FMNMX chains: the cost of a plain batch maximum)
 template <int OFF, int N>
-__device__ __forceinline__ float batch_max(const uint32_t (&v)[N]) {
-  float m0 = -INFINITY, m1 = -INFINITY, m2 = -INFINITY, m3 = -INFINITY;
+__device__ __forceinline__ void fold4(const uint32_t (&v)[N], float (&g)[4]) {
 #pragma unroll
   for (int j4 = 0; j4 < 8; ++j4) {
-    m0 = fmaxf(m0, __uint_as_float(v[OFF + 4 * j4 + 0]));
-    m1 = fmaxf(m1, __uint_as_float(v[OFF + 4 * j4 + 1]));
-    m2 = fmaxf(m2, __uint_as_float(v[OFF + 4 * j4 + 2]));
-    m3 = fmaxf(m3, __uint_as_float(v[OFF + 4 * j4 + 3]));
+    g[0] = fmaxf(g[0], __uint_as_float(v[OFF + 4 * j4 + 0]));
+    g[1] = fmaxf(g[1], __uint_as_float(v[OFF + 4 * j4 + 1]));
+    g[2] = fmaxf(g[2], __uint_as_float(v[OFF + 4 * j4 + 2]));
+    g[3] = fmaxf(g[3], __uint_as_float(v[OFF + 4 * j4 + 3]));
   }
-  return fmaxf(fmaxf(m0, m1), fmaxf(m2, m3));
+}
+// the same with the columns flagged in `skip` (train items of the row) left out
+template <int OFF, int N>
+__device__ __forceinline__ void fold4_masked(const uint32_t (&v)[N], float (&g)[4], uint32_t skip) {
+#pragma unroll
+  for (int j = 0; j < 32; ++j)
+    g[j & 3] = fmaxf(g[j & 3], ((skip >> j) & 1u) ? -INFINITY : __uint_as_float(v[OFF + j]));
 }
 
 // ---------------------------------------------------------------------------------------------
 // The item operand is pre-scaled by its gate (rows sig_i * I_i) and one extra K step adds
 // -c*sig_i, so the accumulator IS the approximate score (y - c) * sig_i: the epilogue is a bare
 // maximum / compare, half an instruction per score, with no shared-memory traffic.
-//   MODE_MAX     bmax[row][NB*tile + b] = max over the 32 columns of batch b (masked items
-//                included; the threshold kernel leaves batches holding a train item of the row out)
-//   MODE_FILTER  batches with bmax >= thr.y are scanned; scores >= thr.x are appended (train items
-//                included: the re-rank kernel drops them)
+//   MODE_MAX     visits item tiles t * tile_stride; per (row, chunk) 32 running group maxima
+//                gmax[row][32*chunk + 4*b + r] over the columns of batch position b with residue r
+//                (train items of the row excluded when MASKED), written once per work item
+//   MODE_FILTER  every batch whose maximum reaches thr.x is scanned; scores >= thr.x that are not
+//                train items of the row (MASKED) are appended with their approximate score
 // Pipeline per CTA: the MMA warp alternates between the two user tiles (A0 x B -> TMEM[0:256),
 // A1 x B -> TMEM[256:512)); while warpgroup 0 drains its accumulator the tensor pipe computes
 // warpgroup 1's, so with epilogue <= MMA time the tensor pipe never idles.
@@ -251,7 +266,7 @@ __global__ void __launch_bounds__(kThreads, 1)
 score_tc_kernel(const __grid_constant__ CUtensorMap tmU, const __grid_constant__ CUtensorMap tmI,
                 const __grid_constant__ CUtensorMap tmUa, const __grid_constant__ CUtensorMap tmIa,
                 const TileParams P, const int32_t *__restrict__ mask_rowptr,
-                const int32_t *__restrict__ mask_col, float *__restrict__ bmax, const float2 *__restrict__ thr,
+                const int32_t *__restrict__ mask_col, float *__restrict__ gmax, const float2 *__restrict__ thr,
                 uint2 *__restrict__ cand, int *__restrict__ cand_cnt,
                 long long *__restrict__ prof /* developer cycle counters of CTA 0, nullable */) {
   extern __shared__ unsigned char smem_raw[];
@@ -329,8 +344,9 @@ score_tc_kernel(const __grid_constant__ CUtensorMap tmU, const __grid_constant__
           timed_wait(BAR(B_EMPTY + stage), phase ^ 1, 1);
           mbar_expect_tx(BAR(B_FULL + stage), B_BYTES);
           unsigned char *dst = sB + stage * B_BYTES;
-          tma_load_2d(smem_u32(dst), &tmI, BAR(B_FULL + stage), 0, t * BN);
-          tma_load_2d(smem_u32(dst + B_TILE_BYTES), &tmIa, BAR(B_FULL + stage), 0, t * BN);
+          const int row0 = t * P.tile_stride * BN;
+          tma_load_2d(smem_u32(dst), &tmI, BAR(B_FULL + stage), 0, row0);
+          tma_load_2d(smem_u32(dst + B_TILE_BYTES), &tmIa, BAR(B_FULL + stage), 0, row0);
           if (++stage == STAGES) {
             stage = 0;
             phase ^= 1;
@@ -405,19 +421,25 @@ score_tc_kernel(const __grid_constant__ CUtensorMap tmU, const __grid_constant__
       float2 th = make_float2(INFINITY, INFINITY);
       uint2 *my_cand = nullptr;
       // MASKED: cursor into the row's sorted train-item list, positioned at the chunk's first
-      // item and advanced tile by tile (kAhead entries are kept in flight).  Rows the threshold
-      // kernel sent straight to the exact kernel (thr = +inf) append nothing and walk nothing.
+      // item and advanced tile by tile (kAhead entries are kept in flight).  Rows that go straight
+      // to the exact kernel (filter pass: thr = +inf; maxima pass: the same train-list-length test
+      // as row_threshold_kernel) append nothing and walk nothing.
       constexpr int kAhead = 4;
       int mptr = 0, mend = 0, nxt[kAhead];
 #pragma unroll
       for (int d = 0; d < kAhead; ++d) nxt[d] = 0x7fffffff;
-      if (MODE == MODE_FILTER && valid) {
-        th = thr[row];
-        my_cand = cand + (size_t)row * kCap;
-        if (MASKED && th.x < INFINITY) {
+      if (valid) {
+        bool walk = MASKED;
+        if (MODE == MODE_FILTER) {
+          th = thr[row];
+          my_cand = cand + (size_t)row * kCap;
+          walk = walk && th.x < INFINITY;
+        }
+        if (MASKED && walk) {
           mptr = mask_rowptr[row];
           mend = mask_rowptr[row + 1];
-          const int first = P.id_off + t_begin * BN;
+          if (MODE == MODE_MAX && mend - mptr > (P.n_items >> 4) + 64) mend = mptr;
+          const int first = P.id_off + t_begin * P.tile_stride * BN;
           int lo = mptr, hi = mend;
           while (lo < hi) {
             const int mid = (lo + hi) >> 1;
@@ -430,121 +452,89 @@ score_tc_kernel(const __grid_constant__ CUtensorMap tmU, const __grid_constant__
             nxt[d] = mptr + d < mend ? mask_col[mptr + d] : 0x7fffffff;
         }
       }
-      // the filter pass prefetches its row's NB batch maxima of the coming tiles (an L2 round
-      // trip is not short against a tile)
-      float4 bmq[kPf][2];
-      const float4 kNegInf4 = make_float4(-INFINITY, -INFINITY, -INFINITY, -INFINITY);
-      auto fetch = [&](int tt, float4 (&bq)[2]) {
-        bq[0] = bq[1] = kNegInf4;
-        if (MODE == MODE_FILTER && valid && tt < t_end) {
-          const float4 *bp = reinterpret_cast<const float4 *>(bmax + (size_t)row * P.ld_tm + NB * tt);
-          bq[0] = bp[0];
-          bq[1] = bp[1];
-        }
-      };
+      float gm[NB][4];  // MODE_MAX: running group maxima of this (row, chunk)
 #pragma unroll
-      for (int d = 0; d < kPf; ++d) fetch(t_begin + d, bmq[d]);
+      for (int i = 0; i < NB; ++i) gm[i][0] = gm[i][1] = gm[i][2] = gm[i][3] = -INFINITY;
 
       for (int t = t_begin; t < t_end; ++t, ++n) {
-        const float bmv[NB] = {bmq[0][0].x, bmq[0][0].y, bmq[0][0].z, bmq[0][0].w,
-                               bmq[0][1].x, bmq[0][1].y, bmq[0][1].z, bmq[0][1].w};
-#pragma unroll
-        for (int d = 0; d + 1 < kPf; ++d) bmq[d][0] = bmq[d + 1][0], bmq[d][1] = bmq[d + 1][1];
-        fetch(t + kPf, bmq[kPf - 1]);
         const uint32_t full_parity = n & 1;
-        if (MODE == MODE_MAX) {
-          uint32_t va[64], vb[64];
-          timed_wait(BAR(TM_FULL + g), full_parity, 1);
-          tc_fence_after();
-          __syncwarp();
-          float bm[NB];
-          if (P.dbg) {  // developer timing experiments only
+        // the row's train items of this tile -> 8 mask words (a well-trained model ranks exactly
+        // those items on top: unfiltered they would flood the candidate list / spoil the maxima)
+        uint32_t mw[NB];
 #pragma unroll
-            for (int j = 0; j < 64; ++j) va[j] = vb[j] = j + lane;
+        for (int i = 0; i < NB; ++i) mw[i] = 0u;
+        if (MASKED) {
+          const int g0 = P.id_off + t * P.tile_stride * BN, g1 = g0 + BN;
+          while (nxt[0] < g1) {
+            const int b = nxt[0] - g0;
+            if (b >= 0) {
+              const uint32_t bit = 1u << (b & 31);
+              const int ws = b >> 5;
 #pragma unroll
-            for (int cb = 0; cb < NB; cb += 2) {
-              if (!(P.dbg & 1)) {
-                tmem_ld64(taddr + cb * 32, va);
-                tmem_ld_wait64(va);
-              }
-              bm[cb] = (P.dbg & 2) ? __uint_as_float(va[cb]) : batch_max<0>(va);
-              bm[cb + 1] = (P.dbg & 2) ? __uint_as_float(va[cb + 32]) : batch_max<32>(va);
+              for (int i = 0; i < NB; ++i) mw[i] |= ws == i ? bit : 0u;
             }
-            tc_fence_before();
-            __syncwarp();
-            if (lane == 0) mbar_arrive(BAR(TM_EMPTY + g));
-          } else {
-            // 64-column loads, one in flight while the previous 64 columns are reduced
-            tmem_ld64(taddr, va);
-            tmem_ld_wait64(va);
 #pragma unroll
-            for (int c4 = 0; c4 < NB / 4; ++c4) {
-              const int cb = 4 * c4;  // va holds batches cb, cb+1
-              tmem_ld64(taddr + (cb + 2) * 32, vb);
-              bm[cb] = batch_max<0>(va);
-              bm[cb + 1] = batch_max<32>(va);
-              tmem_ld_wait64(vb);
-              if (cb + 4 < NB) {
-                tmem_ld64(taddr + (cb + 4) * 32, va);
-              } else {
-                // all TMEM reads of this accumulator are complete: hand it back to the MMA warp
-                tc_fence_before();
-                __syncwarp();
-                if (lane == 0) mbar_arrive(BAR(TM_EMPTY + g));
-              }
-              bm[cb + 2] = batch_max<0>(vb);
-              bm[cb + 3] = batch_max<32>(vb);
-              if (cb + 4 < NB) tmem_ld_wait64(va);
-            }
+            for (int d = 0; d + 1 < kAhead; ++d) nxt[d] = nxt[d + 1];
+            ++mptr;
+            nxt[kAhead - 1] = mptr + kAhead - 1 < mend ? mask_col[mptr + kAhead - 1] : 0x7fffffff;
           }
-          if (valid) {
-            float4 *bp = reinterpret_cast<float4 *>(bmax + (size_t)row * P.ld_tm + NB * t);
-            bp[0] = make_float4(bm[0], bm[1], bm[2], bm[3]);
-            bp[1] = make_float4(bm[4], bm[5], bm[6], bm[7]);
+        }
+        uint32_t va[64], vb[64];
+        timed_wait(BAR(TM_FULL + g), full_parity, 1);
+        tc_fence_after();
+        __syncwarp();
+        if (MODE == MODE_MAX) {
+          // 64-column loads, one in flight while the previous 64 columns are folded
+          auto fold = [&](auto off_tag, const uint32_t (&v)[64], int cb) {
+            constexpr int OFF = decltype(off_tag)::value;
+            if (MASKED && mw[cb]) fold4_masked<OFF>(v, gm[cb], mw[cb]);
+            else fold4<OFF>(v, gm[cb]);
+          };
+          tmem_ld64(taddr, va);
+          tmem_ld_wait64(va);
+#pragma unroll
+          for (int c4 = 0; c4 < NB / 4; ++c4) {
+            const int cb = 4 * c4;  // va holds batches cb, cb+1
+            tmem_ld64(taddr + (cb + 2) * 32, vb);
+            fold(std::integral_constant<int, 0>{}, va, cb);
+            fold(std::integral_constant<int, 32>{}, va, cb + 1);
+            tmem_ld_wait64(vb);
+            if (cb + 4 < NB) {
+              tmem_ld64(taddr + (cb + 4) * 32, va);
+            } else {
+              // all TMEM reads of this accumulator are complete: hand it back to the MMA warp
+              tc_fence_before();
+              __syncwarp();
+              if (lane == 0) mbar_arrive(BAR(TM_EMPTY + g));
+            }
+            fold(std::integral_constant<int, 0>{}, vb, cb + 2);
+            fold(std::integral_constant<int, 32>{}, vb, cb + 3);
+            if (cb + 4 < NB) tmem_ld_wait64(va);
           }
         } else {
-          // Same 64-column load pipeline as the maxima pass.  A batch is looked at only if its
+          // Same 64-column load pipeline.  A batch is looked at element by element only if its
           // maximum reached the threshold for some row of the warp, and then only by the lanes
-          // concerned.  MASKED: the row's train items of this tile are marked in 8 mask words
-          // (a well-trained model ranks exactly those items on top: unfiltered they would flood
-          // the candidate list); otherwise the re-rank kernel drops them.  Padded columns score
-          // -inf.
-          uint32_t mw[NB];
-#pragma unroll
-          for (int i = 0; i < NB; ++i) mw[i] = 0u;
-          if (MASKED) {
-            const int g0 = P.id_off + t * BN, g1 = g0 + BN;
-            while (nxt[0] < g1) {
-              const int b = nxt[0] - g0;
-              if (b >= 0) {
-                const uint32_t bit = 1u << (b & 31);
-                const int ws = b >> 5;
-#pragma unroll
-                for (int i = 0; i < NB; ++i) mw[i] |= ws == i ? bit : 0u;
-              }
-#pragma unroll
-              for (int d = 0; d + 1 < kAhead; ++d) nxt[d] = nxt[d + 1];
-              ++mptr;
-              nxt[kAhead - 1] = mptr + kAhead - 1 < mend ? mask_col[mptr + kAhead - 1] : 0x7fffffff;
-            }
-          }
-          auto scan = [&](const uint32_t *v, int cb) {
-            const bool need = bmv[cb] >= th.y;
+          // concerned.  Padded columns score -inf.
+          auto scan = [&](auto off_tag, const uint32_t (&v)[64], int cb) {
+            constexpr int OFF = decltype(off_tag)::value;
+            float m4[4] = {-INFINITY, -INFINITY, -INFINITY, -INFINITY};
+            fold4<OFF>(v, m4);
+            const bool need = fmaxf(fmaxf(m4[0], m4[1]), fmaxf(m4[2], m4[3])) >= th.x;
             if (__any_sync(0xffffffffu, need)) {
               if (need) {
                 const int gbase = P.id_off + t * BN + cb * 32;
 #pragma unroll
                 for (int j4 = 0; j4 < 8; ++j4) {
-                  const float s0 = __uint_as_float(v[4 * j4 + 0]);
-                  const float s1 = __uint_as_float(v[4 * j4 + 1]);
-                  const float s2 = __uint_as_float(v[4 * j4 + 2]);
-                  const float s3 = __uint_as_float(v[4 * j4 + 3]);
+                  const float s0 = __uint_as_float(v[OFF + 4 * j4 + 0]);
+                  const float s1 = __uint_as_float(v[OFF + 4 * j4 + 1]);
+                  const float s2 = __uint_as_float(v[OFF + 4 * j4 + 2]);
+                  const float s3 = __uint_as_float(v[OFF + 4 * j4 + 3]);
                   if (fmaxf(fmaxf(s0, s1), fmaxf(s2, s3)) >= th.x) {
                     const float ss[4] = {s0, s1, s2, s3};
 #pragma unroll
                     for (int e = 0; e < 4; ++e) {
                       if (ss[e] >= th.x && !(MASKED && ((mw[cb] >> (4 * j4 + e)) & 1u))) {
-                        // ~1.5 K appends per row over the whole catalogue: the atomic is rare
+                        // ~K * stride appends per row over the whole catalogue: the atomic is rare
                         const int pos = atomicAdd(cand_cnt + row, 1);
                         if (pos < kCap)
                           my_cand[pos] =
@@ -557,18 +547,14 @@ score_tc_kernel(const __grid_constant__ CUtensorMap tmU, const __grid_constant__
               __syncwarp();
             }
           };
-          uint32_t va[64], vb[64];
-          timed_wait(BAR(TM_FULL + g), full_parity, 1);
-          tc_fence_after();
-          __syncwarp();
           tmem_ld64(taddr, va);
           tmem_ld_wait64(va);
 #pragma unroll
           for (int c4 = 0; c4 < NB / 4; ++c4) {
             const int cb = 4 * c4;  // va holds batches cb, cb+1
             tmem_ld64(taddr + (cb + 2) * 32, vb);
-            scan(va, cb);
-            scan(va + 32, cb + 1);
+            scan(std::integral_constant<int, 0>{}, va, cb);
+            scan(std::integral_constant<int, 32>{}, va, cb + 1);
             tmem_ld_wait64(vb);
             if (cb + 4 < NB) {
               tmem_ld64(taddr + (cb + 4) * 32, va);
@@ -577,11 +563,16 @@ score_tc_kernel(const __grid_constant__ CUtensorMap tmU, const __grid_constant__
               __syncwarp();
               if (lane == 0) mbar_arrive(BAR(TM_EMPTY + g));
             }
-            scan(vb, cb + 2);
-            scan(vb + 32, cb + 3);
+            scan(std::integral_constant<int, 0>{}, vb, cb + 2);
+            scan(std::integral_constant<int, 32>{}, vb, cb + 3);
             if (cb + 4 < NB) tmem_ld_wait64(va);
           }
         }
+      }
+      if (MODE == MODE_MAX && valid) {
+        float4 *gp = reinterpret_cast<float4 *>(gmax + (size_t)row * P.ld_g + 32 * ch);
+#pragma unroll
+        for (int i = 0; i < NB; ++i) gp[i] = make_float4(gm[i][0], gm[i][1], gm[i][2], gm[i][3]);
       }
     }
     if (profiling && lane == 0 && q == 0) {  // one thread per warpgroup
@@ -667,113 +658,147 @@ __global__ void fill_user_aug_kernel(oper_t *__restrict__ aug) {
   if (i < BM * KA) aug[i] = (i % KA) < 3 ? (oper_t)0x3F80 /* 1.0 */ : (oper_t)0;
 }
 
-// thr[row] = {filter threshold, batch-skip threshold}, one warp per row.
-// The batches that hold no train item of the row (bitmap in shared memory built from the row's
-// mask list) are dealt round-robin into 64 groups, two per lane.  The 64 group maxima come from
-// disjoint batches, so K distinct unmasked items score at least the K-th largest group maximum
-// m_K: the exact K-th best score of the row is >= m_K - eps.  With y~ the tensor-core dot product of the gate-scaled item
-// row and y the fp32 FMA chain:  |y~ - sig*y| <= kappa * |u| * |sig*i|
+// orderable key of a float: a larger float has a larger key; key 0 is below every float (-inf
+// included) and marks entries to ignore
+__device__ __forceinline__ uint32_t fkey(float x) {
+  const uint32_t u = __float_as_uint(x);
+  return (u & 0x80000000u) ? ~u : (u | 0x80000000u);
+}
+__device__ __forceinline__ float fkey_inv(uint32_t k) {
+  return __uint_as_float((k & 0x80000000u) ? (k & 0x7fffffffu) : ~k);
+}
+// K-th largest (K >= 1) of the warp's NV x 32 keys by radix select: 32 rounds of (NV compares +
+// one warp reduction).  Returns 0 when fewer than K keys are non-zero.
+template <int NV>
+__device__ __forceinline__ uint32_t warp_kth_largest(const uint32_t (&key)[NV], int K) {
+  uint32_t prefix = 0;
+  int remaining = K;
+#pragma unroll 1
+  for (int bit = 31; bit >= 0; --bit) {
+    const uint32_t want = (prefix | (1u << bit)) >> bit;
+    int cnt = 0;
+#pragma unroll
+    for (int r = 0; r < NV; ++r) cnt += (key[r] >> bit) == want ? 1 : 0;
+    cnt = __reduce_add_sync(0xffffffffu, cnt);
+    if (cnt >= remaining) prefix |= 1u << bit;
+    else remaining -= cnt;
+  }
+  return prefix;
+}
+
+// thr[row] = {filter threshold, eps}, one warp per row.
+// The maxima pass left n_groups = 32 * n_chunks group maxima per row; the groups are disjoint sets
+// of unmasked sampled items, so K distinct unmasked items score at least the K-th largest group
+// maximum m_K in the approximate arithmetic: the exact K-th best score of the row is >= m_K - eps1.
+// With y~ the tensor-core dot product of the gate-scaled item row and y the fp32 FMA chain:
+//   |y~ - sig*y| <= kappa * |u| * |sig*i|
 //   kappa = 1.5 * 2^-8  (two bf16 roundings 2^-9 each -> 2^-8 (1 + 2^-10) per product, products
 //   exact in fp32, plus fp32 accumulation of 64 terms on both sides and the gate pre-scale)
 // and the roundings of (sig*y - c*sig), with c*sig carried as three bf16 pieces (24 bits), versus
-// ((y - c) * sig) add at most 2^-22 * (|c| + |u||i|) per pass.  eps = eps(maxima pass) + eps(filter pass).
+// ((y - c) * sig) add at most 2^-22 * (|c| + |u||i|).  eps = 2 * eps1 covers (a) the sampled
+// maximum vs the exact score plus (b) the exact score vs the filter pass's approximate score.
 __global__ void __launch_bounds__(256, 4)
-row_threshold_kernel(const float *__restrict__ bmax, int T, int n_batches, int ld_tm, int K,
-                     const int32_t *__restrict__ mask_rowptr, const int32_t *__restrict__ mask_col,
-                     int id_off, int n_items, const float *__restrict__ unorm,
-                     const unsigned int *__restrict__ inorm_max, float c, float kappa_sum,
-                     int bm_words, float2 *__restrict__ thr, int *__restrict__ cand_cnt) {
-  extern __shared__ uint32_t s_bits[];  // [8 warps][bm_words]
+row_threshold_kernel(const float *__restrict__ gmax, int T, int n_groups, int ld_g, int K,
+                     const int32_t *__restrict__ mask_rowptr, int n_items,
+                     const float *__restrict__ unorm, const unsigned int *__restrict__ inorm_max,
+                     float c, float kappa_sum, float2 *__restrict__ thr, int *__restrict__ cand_cnt) {
   const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
   const int t = blockIdx.x * 8 + wib;
   if (t >= T) return;
-  uint32_t *bits = s_bits + (size_t)wib * bm_words;
-  for (int i = lane; i < bm_words; i += 32) bits[i] = 0u;
-  __syncwarp();
-  int mask_len = 0;
-  if (mask_rowptr) {
-    const int lo = mask_rowptr[t], hi = mask_rowptr[t + 1];
-    mask_len = hi - lo;
-    for (int e = lo + lane; e < hi; e += 32) {
-      const int loc = mask_col[e] - id_off;
-      if (loc >= 0 && loc < n_items) atomicOr(&bits[loc >> 10], 1u << ((loc >> 5) & 31));
-    }
-    __syncwarp();
-  }
-  const float *row = bmax + (size_t)t * ld_tm;
-  // 64 disjoint groups of batches, two per lane: group (b / 32) & 1 of lane b & 31
-  float m0 = -INFINITY, m1 = -INFINITY;
-  // unconditional (clamped) loads, 8 in flight per lane: this kernel is a latency-bound stream
-#pragma unroll 4
-  for (int b0 = 0; b0 < n_batches; b0 += 64) {
-    const int b = b0 + lane;
-    const float v0 = row[min(b, n_batches - 1)];
-    const float v1 = row[min(b + 32, n_batches - 1)];
-    const uint32_t w0 = bits[b0 >> 5];
-    const uint32_t w1 = bits[min((b0 >> 5) + 1, bm_words - 1)];
-    if (b < n_batches && !((w0 >> lane) & 1u)) m0 = fmaxf(m0, v0);
-    if (b + 32 < n_batches && !((w1 >> lane) & 1u)) m1 = fmaxf(m1, v1);
-  }
-  // rank of each group maximum among the 64 (ties broken by group index) -> K-th largest
-  int r0 = 0, r1 = 0;
+  constexpr int NV = kMaxChunksS;  // 32 groups per chunk: lane l holds groups l, l + 32, ...
+  uint32_t key[NV];
 #pragma unroll
-  for (int o = 0; o < 32; ++o) {
-    const float a0 = __shfl_sync(0xffffffffu, m0, o);
-    const float a1 = __shfl_sync(0xffffffffu, m1, o);
-    r0 += (a0 > m0 || (a0 == m0 && o < lane)) ? 1 : 0;
-    r0 += (a1 > m0) ? 1 : 0;
-    r1 += (a0 > m1 || a0 == m1) ? 1 : 0;
-    r1 += (a1 > m1 || (a1 == m1 && o < lane)) ? 1 : 0;
+  for (int r = 0; r < NV; ++r) {
+    const int idx = r * 32 + lane;
+    key[r] = idx < n_groups ? fkey(gmax[(size_t)t * ld_g + idx]) : 0u;
   }
-  const unsigned who0 = __ballot_sync(0xffffffffu, r0 == K - 1);
-  const unsigned who1 = __ballot_sync(0xffffffffu, r1 == K - 1);
-  const float mk = who0 ? __shfl_sync(0xffffffffu, m0, __ffs(who0) - 1)
-                        : __shfl_sync(0xffffffffu, m1, __ffs(who1) - 1);
+  const uint32_t kk = warp_kth_largest<NV>(key, K);
+  const float mk = kk ? fkey_inv(kk) : -INFINITY;
   if (lane == 0) {
     // Straight to the exact kernel (which strikes train items out tile by tile): rows without K
-    // unmasked groups -- no usable threshold, every item would be a candidate -- and rows whose
-    // train list is dense enough (> 1/16 of the catalogue) that walking it costs the filter
-    // pass more than the exact kernel costs the row.  +inf keeps the filter pass off the row;
+    // finite group maxima -- no usable threshold, every item would be a candidate -- and rows whose
+    // train list is dense enough (> 1/16 of the catalogue) that walking it costs the tensor-core
+    // passes more than the exact kernel costs the row.  +inf keeps the filter pass off the row;
     // the over-full count makes the re-rank kernel queue it.
-    float2 out = make_float2(INFINITY, INFINITY);
+    const int mask_len = mask_rowptr ? mask_rowptr[t + 1] - mask_rowptr[t] : 0;
+    float2 out = make_float2(INFINITY, 0.f);
     if (!(mk > -INFINITY) || mask_len > (n_items >> 4) + 64) {
       cand_cnt[t] = kCap + 1;
     } else {
       const float yb = unorm[t] * __uint_as_float(*inorm_max);
       const float eps = kappa_sum * yb + 9.5367431640625e-7f /*2^-20*/ * (fabsf(c) + yb);
       out.x = mk - eps - 9.5367431640625e-7f * fabsf(mk);
-      out.y = out.x - eps;  // a batch can hold a filter-pass score >= thr.x only if its
-                            // maxima-pass maximum is >= thr.x - eps
+      out.y = eps;
     }
     thr[t] = out;
   }
 }
 
-// exact re-rank of the candidates of one row (one warp per row): each lane fetches and re-scores
-// one candidate per round with the fp32 FMA chain of score.cu; ranks come from counting.  (Train
-// items never get here: the filter pass marks every entry of the row's sorted train list that
-// falls into a tile.)  Rows whose list overflowed are queued for the exact fp32 kernel.
-__global__ void __launch_bounds__(256, 4)
+// Candidates of one row (one warp per row).  (1) a_K = K-th largest approximate score of the list;
+// K unmasked items score >= a_K approximately, hence >= a_K - eps1 exactly, so a member of the true
+// top-K has an approximate score >= a_K - 2 eps1 = a_K - eps: everything below is dropped without
+// being touched.  (2) each lane fetches and re-scores one survivor per round with the fp32 FMA
+// chain of score.cu; ranks come from counting.  (Train items never get here: the filter pass marks
+// every entry of the row's sorted train list that falls into a tile.)  Rows whose list overflowed
+// (or with more than kKeep survivors) are queued for the exact fp32 kernel.
+__global__ void __launch_bounds__(256, 3)
 rerank_kernel(const float *__restrict__ Uq, int T, const float *__restrict__ It,
               const float *__restrict__ sig_i, const float *__restrict__ sig_u, float c, int id_off,
-              const uint2 *__restrict__ cand, const int *__restrict__ cand_cnt, int K,
+              const uint2 *__restrict__ cand, const int *__restrict__ cand_cnt,
+              const float2 *__restrict__ thr, int K,
               int32_t *__restrict__ out_ids, float *__restrict__ out_scores,
               int32_t *__restrict__ fb_rows, int *__restrict__ fb_count,
               unsigned long long *__restrict__ cand_total) {
   __shared__ float su[8][kD];
+  __shared__ int s_keep[8][kKeep];
   const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
   const int t = blockIdx.x * 8 + wib;
   if (t >= T) return;
-  constexpr int kRounds = kCap / 32;  // candidates live in registers, 32 per round
+  constexpr int kRounds = kKeep / 32;  // survivors live in registers, 32 per round
+  constexpr int kLoad = kCap / 32;
   const int total = cand_cnt[t];
   if (total > kCap) {
     if (lane == 0) fb_rows[atomicAdd(fb_count, 1)] = t;
     return;
   }
-  if (cand_total && lane == 0) atomicAdd(cand_total, (unsigned long long)total);
+  // ---- (1) cut on the approximate scores ----
+  uint32_t key[kLoad];
+  int gidv[kLoad];
+#pragma unroll
+  for (int r = 0; r < kLoad; ++r) {
+    const int e = r * 32 + lane;
+    key[r] = 0u;
+    gidv[r] = 0;
+    if (e < total) {
+      const uint2 cv = cand[(size_t)t * kCap + e];
+      key[r] = fkey(__uint_as_float(cv.x));
+      gidv[r] = (int)cv.y;
+    }
+  }
+  uint32_t cut = 1u;  // fewer than K candidates (fewer than K unmasked items exist): keep all
+  if (total > K) {
+    const uint32_t kk = warp_kth_largest<kLoad>(key, K);
+    const float aK = fkey_inv(kk);
+    cut = fkey(aK - thr[t].y - 9.5367431640625e-7f * fabsf(aK));
+  }
+  int n_keep = 0;
+#pragma unroll
+  for (int r = 0; r < kLoad; ++r) {
+    const bool keep = key[r] >= cut && key[r] != 0u;
+    const unsigned bal = __ballot_sync(0xffffffffu, keep);
+    const int pos = n_keep + __popc(bal & ((1u << lane) - 1u));
+    if (keep && pos < kKeep) s_keep[wib][pos] = gidv[r];
+    n_keep += __popc(bal);
+  }
+  if (n_keep > kKeep) {
+    if (lane == 0) fb_rows[atomicAdd(fb_count, 1)] = t;
+    return;
+  }
+  if (cand_total && lane == 0) atomicAdd(cand_total, (unsigned long long)n_keep);
   su[wib][lane] = Uq[(size_t)t * kD + lane];
   su[wib][lane + 32] = Uq[(size_t)t * kD + lane + 32];
   __syncwarp();
+  // ---- (2) exact scores of the survivors ----
   const float sgu = sig_u[t];
   float cs_[kRounds];
   int cg_[kRounds];
@@ -782,8 +807,8 @@ rerank_kernel(const float *__restrict__ Uq, int T, const float *__restrict__ It,
     cs_[r] = -INFINITY;
     cg_[r] = 0x7fffffff;
     const int e = r * 32 + lane;
-    if (e < total) {
-      const int gid = (int)cand[(size_t)t * kCap + e].y;
+    if (e < n_keep) {
+      const int gid = s_keep[wib][e];
       const float4 *ip = reinterpret_cast<const float4 *>(It + (size_t)(gid - id_off) * kD);
       float acc = 0.f;
 #pragma unroll
@@ -799,7 +824,7 @@ rerank_kernel(const float *__restrict__ Uq, int T, const float *__restrict__ It,
     }
   }
   // rank by counting: the order (score desc, lower id first) is strict among valid candidates
-  const int nr = (total + 31) >> 5;
+  const int nr = (n_keep + 31) >> 5;
   int rank[kRounds];
 #pragma unroll
   for (int r = 0; r < kRounds; ++r) rank[r] = 0;
@@ -880,32 +905,23 @@ static int make_map(CUtensorMap *m, const oper_t *base, long long rows, int box_
 
 struct Plan {
   int TB;        // query rows per row block
-  int n_itiles, n_chunks, tiles_per_chunk, ld_tm;
-  size_t off_uhi, off_ihi, off_iaug, off_uaug, off_unorm, off_misc, off_tilemax, off_thr, off_cand,
+  int n_itiles, n_chunks, tiles_per_chunk;          // filter pass: the whole catalogue
+  int stride, n_stiles, n_chunks_s, tiles_per_chunk_s, ld_g;  // maxima pass: the sampled tiles
+  size_t off_uhi, off_ihi, off_iaug, off_uaug, off_unorm, off_misc, off_gmax, off_thr, off_cand,
       off_cnt, off_fbrows, off_exact, total;
   size_t exact_bytes;
 };
 
 static size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
 
-static Plan make_plan(int T, long long n_items, int K) {
-  Plan p;
-  p.n_itiles = (int)((n_items + BN - 1) / BN);
-  p.ld_tm = (NB * p.n_itiles + 31) / 32 * 32;  // NB batch maxima per item tile
-  // row block: batch maxima at most ~1 GiB
-  long long tb = (1024LL << 20) / (4LL * p.ld_tm);
-  tb = tb / BM * BM;
-  if (tb < 1024) tb = 1024;
-  if (tb > T) tb = T;
-  p.TB = (int)tb;
-  const int utiles = (p.TB + UT * BM - 1) / (UT * BM);
-  // item chunks: enough work items to balance the SMs, every chunk non-empty
+// item chunks: enough work items to balance the SMs, every chunk non-empty; -> tiles per chunk
+static int pick_tiles_per_chunk(int utiles, int n_tiles, int nc_min, int nc_max) {
   const int sms = sm_count();
-  int best = 1;
+  int best = nc_min;
   double best_cost = 1e30;
-  for (int nc = 1; nc <= 16 && nc * 2 <= p.n_itiles; ++nc) {
-    const int tpc = (p.n_itiles + nc - 1) / nc;
-    const int ncr = (p.n_itiles + tpc - 1) / tpc;
+  for (int nc = nc_min; nc <= nc_max; ++nc) {
+    const int tpc = (n_tiles + nc - 1) / nc;
+    const int ncr = (n_tiles + tpc - 1) / tpc;
     const long long work = (long long)utiles * ncr;
     const long long rounds = (work + sms - 1) / sms;
     const double cost = (double)rounds * tpc;  // tiles on the busiest SM
@@ -914,8 +930,31 @@ static Plan make_plan(int T, long long n_items, int K) {
       best = ncr;
     }
   }
-  p.tiles_per_chunk = (p.n_itiles + best - 1) / best;
+  return (n_tiles + best - 1) / best;
+}
+
+static Plan make_plan(int T, long long n_items, int K) {
+  Plan p;
+  p.n_itiles = (int)((n_items + BN - 1) / BN);
+  // the maxima pass visits every stride-th tile: the threshold then sits near rank K * stride of
+  // the row instead of K (that many candidates reach the re-rank's approximate cut), for 1/stride
+  // of a pass; small catalogues keep enough sampled batches for tight group maxima
+  p.stride = p.n_itiles >= 32 * kMaxStride ? kMaxStride : p.n_itiles >= 64 ? 2 : 1;
+  p.n_stiles = (p.n_itiles + p.stride - 1) / p.stride;
+  // row block: group maxima + candidate lists at most ~1 GiB
+  long long tb = (1024LL << 20) / (4LL * 32 * kMaxChunksS + 8LL * kCap + 64);
+  tb = tb / (UT * BM) * (UT * BM);
+  if (tb > T) tb = T;
+  p.TB = (int)tb;
+  const int utiles = (p.TB + UT * BM - 1) / (UT * BM);
+  int nc_max = p.n_itiles / 2 < 16 ? p.n_itiles / 2 : 16;
+  p.tiles_per_chunk = pick_tiles_per_chunk(utiles, p.n_itiles, 1, nc_max < 1 ? 1 : nc_max);
   p.n_chunks = (p.n_itiles + p.tiles_per_chunk - 1) / p.tiles_per_chunk;
+  // >= 4 chunks = 128 disjoint groups per row (K <= 32), more when few user tiles must fill the SMs
+  const int ncs_max = p.n_stiles < kMaxChunksS ? p.n_stiles : kMaxChunksS;
+  p.tiles_per_chunk_s = pick_tiles_per_chunk(utiles, p.n_stiles, ncs_max < 4 ? ncs_max : 4, ncs_max);
+  p.n_chunks_s = (p.n_stiles + p.tiles_per_chunk_s - 1) / p.tiles_per_chunk_s;
+  p.ld_g = 32 * p.n_chunks_s;
   size_t o = 0;
   auto take = [&](size_t bytes) {
     const size_t at = o;
@@ -929,7 +968,7 @@ static Plan make_plan(int T, long long n_items, int K) {
   p.off_uaug = take((size_t)BM * KA * sizeof(oper_t));
   p.off_unorm = take((size_t)p.TB * 4);
   p.off_misc = take(64);  // [0] item norm max (uint bits) [1] fb_count [2..3] cand_total (u64)
-  p.off_tilemax = take((size_t)p.TB * p.ld_tm * 4);
+  p.off_gmax = take((size_t)p.TB * p.ld_g * 4);
   p.off_thr = take((size_t)p.TB * 8);
   p.off_cand = take((size_t)p.TB * kCap * 8);
   p.off_cnt = take((size_t)p.TB * 4);
@@ -946,7 +985,7 @@ static long long *g_prof = nullptr;  // device int64[64]: cycle counters of CTA 
 template <int MODE, bool MASKED>
 static int launch_pass(const CUtensorMap &mu, const CUtensorMap &mi, const CUtensorMap &mua,
                        const CUtensorMap &mia, const TileParams &P, const int32_t *mrp,
-                       const int32_t *mcol, float *bmax, const float2 *thr, uint2 *cand, int *cnt,
+                       const int32_t *mcol, float *gmax, const float2 *thr, uint2 *cand, int *cnt,
                        cudaStream_t s) {
   static bool opted = false;
   long long *prof = g_prof ? g_prof + 32 * MODE : nullptr;
@@ -958,7 +997,7 @@ static int launch_pass(const CUtensorMap &mu, const CUtensorMap &mi, const CUten
   const int n_work = P.n_utiles * P.n_chunks;
   const int grid = n_work < sm_count() ? n_work : sm_count();
   score_tc_kernel<MODE, MASKED><<<grid, kThreads, SMEM_BYTES, s>>>(mu, mi, mua, mia, P, mrp, mcol,
-                                                                   bmax, thr, cand, cnt, prof);
+                                                                   gmax, thr, cand, cnt, prof);
   MACR_LAUNCH_CHECK();
   return MACR_OK;
 }
@@ -994,8 +1033,6 @@ extern "C" int macr_score_topk_tc(const float *Uq, int T, const float *It, int64
   MACR_CHECK_ARG(n_items >= 2048 && n_items < (1LL << 31) - BN,
                  "macr_score_topk_tc: needs at least 2048 items (got %lld): use macr_score_topk",
                  (long long)n_items);
-  MACR_CHECK_ARG((8LL * ((NB * ((n_items + BN - 1) / BN) + 31) / 32) * 4) <= 48 * 1024,
-                 "macr_score_topk_tc: more than ~1.5M items per shard: shard the catalogue");
   MACR_CHECK_ARG(Uq && It && sig_i && sig_u && out_ids && out_scores && ws,
                  "macr_score_topk_tc: null pointer");
   MACR_CHECK_ARG((reinterpret_cast<uintptr_t>(ws) & 1023) == 0,
@@ -1010,7 +1047,7 @@ extern "C" int macr_score_topk_tc(const float *Uq, int T, const float *It, int64
   oper_t *ihi = reinterpret_cast<oper_t *>(w + p.off_ihi);
   float *unorm = reinterpret_cast<float *>(w + p.off_unorm);
   unsigned int *misc = reinterpret_cast<unsigned int *>(w + p.off_misc);
-  float *tilemax = reinterpret_cast<float *>(w + p.off_tilemax);
+  float *gmax = reinterpret_cast<float *>(w + p.off_gmax);
   float2 *thr = reinterpret_cast<float2 *>(w + p.off_thr);
   oper_t *iaug = reinterpret_cast<oper_t *>(w + p.off_iaug);
   oper_t *uaug = reinterpret_cast<oper_t *>(w + p.off_uaug);
@@ -1034,7 +1071,7 @@ extern "C" int macr_score_topk_tc(const float *Uq, int T, const float *It, int64
   if (rc) return rc;
   rc = make_map(&mua, uaug, BM, BM, KA);
   if (rc) return rc;
-  // maxima pass + filter pass, see row_threshold_kernel
+  // eps of row_threshold_kernel: the sampled maximum vs exact + exact vs the filter pass's score
   const float kappa_sum = 2.f * 1.5f * 3.90625e-3f;
 
   for (int t0 = 0; t0 < T; t0 += p.TB) {
@@ -1051,30 +1088,36 @@ extern "C" int macr_score_topk_tc(const float *Uq, int T, const float *It, int64
     P.T = nb;
     P.n_items = (int)n_items;
     P.n_utiles = (nb + UT * BM - 1) / (UT * BM);
+    P.id_off = item_id_offset;
+    P.ld_g = p.ld_g;
+    P.dbg = g_dbg;
+    // maxima pass over the sampled tiles (train items of the row excluded inside the pass)
+    P.n_itiles = p.n_stiles;
+    P.n_chunks = p.n_chunks_s;
+    P.tiles_per_chunk = p.tiles_per_chunk_s;
+    P.tile_stride = p.stride;
+    rc = mrp ? launch_pass<MODE_MAX, true>(muh, mih, mua, mia, P, mrp, mask_col, gmax, nullptr,
+                                           nullptr, nullptr, s)
+             : launch_pass<MODE_MAX, false>(muh, mih, mua, mia, P, nullptr, nullptr, gmax, nullptr,
+                                            nullptr, nullptr, s);
+    if (rc) return rc;
+    MACR_CUDA(cudaMemsetAsync(cnt, 0, (size_t)nb * sizeof(int), s));
+    row_threshold_kernel<<<(nb + 7) / 8, 256, 0, s>>>(gmax, nb, p.ld_g, p.ld_g, K, mrp, (int)n_items,
+                                                      unorm, misc, c, kappa_sum, thr, cnt);
+    MACR_LAUNCH_CHECK();
+    // ONE pass over the whole catalogue; train items are filtered inside it whenever a mask is given
     P.n_itiles = p.n_itiles;
     P.n_chunks = p.n_chunks;
     P.tiles_per_chunk = p.tiles_per_chunk;
-    P.id_off = item_id_offset;
-    P.ld_tm = p.ld_tm;
-    P.dbg = g_dbg;
-    rc = launch_pass<MODE_MAX, false>(muh, mih, mua, mia, P, nullptr, nullptr, tilemax, nullptr,
-                                      nullptr, nullptr, s);
-    if (rc) return rc;
-    const int n_batches = NB * p.n_itiles, bm_words = (n_batches + 31) / 32;
-    MACR_CUDA(cudaMemsetAsync(cnt, 0, (size_t)nb * sizeof(int), s));
-    row_threshold_kernel<<<(nb + 7) / 8, 256, (size_t)8 * bm_words * 4, s>>>(
-        tilemax, nb, n_batches, p.ld_tm, K, mrp, mask_col, item_id_offset, (int)n_items, unorm,
-        misc, c, kappa_sum, bm_words, thr, cnt);
-    MACR_LAUNCH_CHECK();
-    // train items are filtered inside the pass whenever a mask is given (see the kernel comment)
-    rc = mrp ? launch_pass<MODE_FILTER, true>(muh, mih, mua, mia, P, mrp, mask_col, tilemax, thr,
+    P.tile_stride = 1;
+    rc = mrp ? launch_pass<MODE_FILTER, true>(muh, mih, mua, mia, P, mrp, mask_col, nullptr, thr,
                                               cand, cnt, s)
-             : launch_pass<MODE_FILTER, false>(muh, mih, mua, mia, P, nullptr, nullptr, tilemax, thr,
+             : launch_pass<MODE_FILTER, false>(muh, mih, mua, mia, P, nullptr, nullptr, nullptr, thr,
                                                cand, cnt, s);
     if (rc) return rc;
     MACR_CUDA(cudaMemsetAsync(fb_count, 0, sizeof(int), s));
     rerank_kernel<<<(nb + 7) / 8, 256, 0, s>>>(Ub, nb, It, sig_i, sig_u + t0, c, item_id_offset,
-                                               cand, cnt, K,
+                                               cand, cnt, thr, K,
                                                out_ids + (size_t)t0 * K, out_scores + (size_t)t0 * K,
                                                fb_rows, fb_count, cand_total);
     MACR_LAUNCH_CHECK();
