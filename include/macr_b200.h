@@ -403,6 +403,24 @@ int macr_shard_push(const float *U_local, const float *I_local, const macr_shard
                     macr_stream_t stream);
 int macr_shard_barrier(uint64_t *const *peer_flags_host, int rank, int world, uint64_t epoch,
                        int *err_flag, macr_stream_t stream);
+/* Row-partitioned LightGCN (SURVEY.md 8e row "LightGCN SpMM": 1-D row partition of A_hat, an
+ * all-gather of E_k per layer): rank r owns user rows [u_lo,u_hi) and item rows [i_lo,i_hi).
+ * replaces (distributed form of): _create_lightgcn_embed's row folds
+ *   macr_lightgcn/LightGCN.py:257-269,297-305, and the dense ApplyAdam of :201 on the owned rows.
+ * Create the trainer with the FULL-size tables (U, I in macr_ipc_alloc memory; only the owned rows
+ * and their Adam slots are kept current here, rows of other ranks are refreshed by their owners)
+ * and a CSR that holds the nonzeros of the owned rows only (rowptr still has N+1 entries).
+ * macr_lgcn_trainer_ipc_export hands out the IPC handles of {E_mean, layer buffers, flags};
+ * macr_lgcn_trainer_shard (before the first step) takes every peer's mapping of {U, I, E_mean,
+ * layer buffers, flags}.  From then on each layer is computed for the owned rows and stored into
+ * the peers' buffers over NVLink (peer stores + flag barrier, inside the step's CUDA graph); owned
+ * rows, losses, w and w_user are bit-identical to the single-GPU trainer.
+ * macr_lgcn_trainer_peer_error: synchronises; *err_out = 1 + r if peer r missed a barrier. */
+int macr_lgcn_trainer_ipc_export(macr_lgcn_trainer *h, unsigned char handles[3][MACR_IPC_HANDLE_BYTES]);
+int macr_lgcn_trainer_shard(macr_lgcn_trainer *h, const macr_shard_desc *desc,
+                            float *const *peer_U, float *const *peer_I, float *const *peer_Emean,
+                            float *const *peer_tmp, uint64_t *const *peer_flags);
+int macr_lgcn_trainer_peer_error(macr_lgcn_trainer *h, int *err_out);
 int macr_ipc_alloc(size_t bytes, void **dev_ptr, unsigned char handle_out[MACR_IPC_HANDLE_BYTES]);
 int macr_ipc_open(const unsigned char handle[MACR_IPC_HANDLE_BYTES], void **peer_ptr);
 int macr_ipc_close(void *peer_ptr);

@@ -705,12 +705,19 @@ row_threshold_kernel(const float *__restrict__ gmax, int T, int n_groups, int ld
   const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
   const int t = blockIdx.x * 8 + wib;
   if (t >= T) return;
-  constexpr int NV = kMaxChunksS;  // 32 groups per chunk: lane l holds groups l, l + 32, ...
+  // 32 groups per chunk; groups g, g + 128, g + 256, ... are merged (a union of disjoint item sets
+  // is one) so the select always runs on 128 values, 4 per lane
+  constexpr int NV = 4;
   uint32_t key[NV];
 #pragma unroll
   for (int r = 0; r < NV; ++r) {
-    const int idx = r * 32 + lane;
-    key[r] = idx < n_groups ? fkey(gmax[(size_t)t * ld_g + idx]) : 0u;
+    float m = -INFINITY;
+    bool any = false;
+    for (int idx = r * 32 + lane; idx < n_groups; idx += 32 * NV) {
+      m = fmaxf(m, gmax[(size_t)t * ld_g + idx]);
+      any = true;
+    }
+    key[r] = any ? fkey(m) : 0u;
   }
   const uint32_t kk = warp_kth_largest<NV>(key, K);
   const float mk = kk ? fkey_inv(kk) : -INFINITY;
@@ -777,7 +784,10 @@ rerank_kernel(const float *__restrict__ Uq, int T, const float *__restrict__ It,
   }
   uint32_t cut = 1u;  // fewer than K candidates (fewer than K unmasked items exist): keep all
   if (total > K) {
-    const uint32_t kk = warp_kth_largest<kLoad>(key, K);
+    // lists are ~K * stride long: select over as many 32-entry rounds as the list fills
+    const uint32_t kk = total <= 64    ? warp_kth_largest<2>(reinterpret_cast<const uint32_t (&)[2]>(key), K)
+                        : total <= 128 ? warp_kth_largest<4>(reinterpret_cast<const uint32_t (&)[4]>(key), K)
+                                       : warp_kth_largest<kLoad>(key, K);
     const float aK = fkey_inv(kk);
     cut = fkey(aK - thr[t].y - 9.5367431640625e-7f * fabsf(aK));
   }

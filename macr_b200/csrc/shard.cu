@@ -20,11 +20,10 @@
 //     runs step t (it cannot reach t+2 before this rank has passed barrier t+1).
 //   * pack (for an NCCL all-reduce by the caller): owned rows -> ex[3B][64], zeros elsewhere;
 //     after the sum macr_shard_unpack copies ex into the ghost slots.
+#include "shard.cuh"
 #include "train_kernels.cuh"
 
 namespace macr {
-
-constexpr int kMaxRanks = MACR_SHARD_MAX_RANKS;
 
 struct PeerTabs {
   float *u[kMaxRanks];  // ghost base (row n_local_u of rank r's U_local) as mapped in THIS process
@@ -82,6 +81,65 @@ __global__ void shard_barrier_kernel(PeerFlags f, int rank, int world, unsigned 
       break;
     }
   }
+}
+
+// ---- all-gather of row ranges by peer stores (row-partitioned LightGCN) --------
+__global__ void __launch_bounds__(256)
+peer_push_kernel(PeerPush p) {
+  const long long n4a = p.rows[0] * (kD / 4), n4 = n4a + p.rows[1] * (kD / 4);
+  for (long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x; e < n4;
+       e += (long long)gridDim.x * blockDim.x) {
+    const int k = e >= n4a;
+    const long long off = k ? e - n4a : e;
+    const float4 v = ld_stream(reinterpret_cast<const float4 *>(p.src[k]) + off);
+#pragma unroll 1
+    for (int r = 0; r < p.world; ++r)
+      if (r != p.rank) st_stream(reinterpret_cast<float4 *>(p.dst[k][r]) + off, v);
+  }
+}
+
+int launch_peer_push(const PeerPush &p, cudaStream_t s) {
+  const long long n4 = (p.rows[0] + p.rows[1]) * (kD / 4);
+  if (n4 == 0 || p.world <= 1) return MACR_OK;
+  long long ctas = (n4 + 255) / 256;
+  const long long cap = (long long)sm_count() * 8;
+  if (ctas > cap) ctas = cap;
+  peer_push_kernel<<<(unsigned)ctas, 256, 0, s>>>(p);
+  MACR_LAUNCH_CHECK();
+  return MACR_OK;
+}
+
+__global__ void peer_barrier_dev_kernel(PeerFlagsDev f, unsigned long long *epoch_ctr, int rank,
+                                        int world, long long spin_limit, int *err) {
+  const int r = threadIdx.x;
+  unsigned long long epoch = 0;
+  if (r == 0) epoch = *epoch_ctr + 1;
+  epoch = __shfl_sync(0xffffffffu, epoch, 0);
+  if (r < world && r != rank) {
+    __threadfence_system();
+    asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(f.p[r] + rank), "l"(epoch) : "memory");
+    const unsigned long long *mine = f.p[rank] + r;
+    const long long t0 = clock64();
+    for (;;) {
+      unsigned long long v;
+      asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(mine) : "memory");
+      if (v >= epoch) break;
+      if (clock64() - t0 > spin_limit) {
+        atomicExch(err, 1 + r);
+        break;
+      }
+    }
+  }
+  __syncwarp();
+  if (r == 0) *epoch_ctr = epoch;
+}
+
+int launch_peer_barrier_dev(const PeerFlagsDev &f, unsigned long long *epoch_ctr, int *err, int rank,
+                            int world, cudaStream_t s) {
+  if (world <= 1) return MACR_OK;
+  peer_barrier_dev_kernel<<<1, 32, 0, s>>>(f, epoch_ctr, rank, world, 20000000000LL, err);
+  MACR_LAUNCH_CHECK();
+  return MACR_OK;
 }
 
 static int check_desc(const macr_shard_desc *d, int B, const char *who) {

@@ -1,0 +1,28 @@
+// shard.cuh -- internal declarations of the peer-memory exchange kernels (shard.cu)
+#pragma once
+#include "common.cuh"
+
+namespace macr {
+
+constexpr int kMaxRanks = MACR_SHARD_MAX_RANKS;
+
+// all-gather by peer stores: up to two contiguous row ranges of a local [rows][64] buffer are
+// copied to the same rows of every peer's buffer (dst[k][r] = address in THIS process of range k's
+// first row in rank r's buffer; dst[k][rank] is ignored)
+struct PeerPush {
+  const float *src[2];
+  long long rows[2];
+  float *dst[2][kMaxRanks];
+  int rank, world;
+};
+int launch_peer_push(const PeerPush &p, cudaStream_t s);
+
+// flag barrier over peer memory whose epoch lives on the device (so it can sit in a CUDA graph):
+// *epoch_ctr is incremented by one per call; flags[r] = rank r's uint64[kMaxRanks] arrival flags
+struct PeerFlagsDev {
+  unsigned long long *p[kMaxRanks];
+};
+int launch_peer_barrier_dev(const PeerFlagsDev &f, unsigned long long *epoch_ctr, int *err, int rank,
+                            int world, cudaStream_t s);
+
+}  // namespace macr

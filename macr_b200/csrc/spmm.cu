@@ -190,12 +190,13 @@ spmm_combine_kernel(const int32_t *__restrict__ multi_row, const int32_t *__rest
 }
 
 // one-off, host side: the adjacency of a run never changes (LightGCN.py:257-269 builds it once)
-int build_spmm_plan(const int32_t *d_rowptr, int64_t n_rows, SpmmPlan *out) {
+int build_spmm_plan(const int32_t *d_rowptr, int64_t n_rows, SpmmPlan *out, const int64_t *ranges) {
   std::vector<int32_t> rp((size_t)n_rows + 1);
   MACR_CUDA(cudaMemcpy(rp.data(), d_rowptr, sizeof(int32_t) * rp.size(), cudaMemcpyDeviceToHost));
   std::vector<int32_t> srow, sstart, send, sslot, mrow, mslot0, mnseg;
   int32_t n_slots = 0;
   for (int64_t r = 0; r < n_rows; ++r) {
+    if (ranges && !((r >= ranges[0] && r < ranges[1]) || (r >= ranges[2] && r < ranges[3]))) continue;
     const int32_t st = rp[r], en = rp[r + 1];
     const int32_t nseg = en - st <= kSegNnz ? 1 : (en - st + kSegNnz - 1) / kSegNnz;
     if (nseg > 1) {

@@ -22,7 +22,10 @@ struct SpmmPlan {
   int32_t *multi_row = nullptr, *multi_slot0 = nullptr, *multi_nseg = nullptr;
   float *partial = nullptr;  // [sum of segments of multi-segment rows][64]
 };
-int build_spmm_plan(const int32_t *d_rowptr, int64_t n_rows, SpmmPlan *out);
+// ranges (nullable): {a0, a1, b0, b1} -- only rows in [a0,a1) or [b0,b1) get segments (the rows a
+// rank owns when the adjacency is row-partitioned); the segmentation of a row never depends on it
+int build_spmm_plan(const int32_t *d_rowptr, int64_t n_rows, SpmmPlan *out,
+                    const int64_t *ranges = nullptr);
 void free_spmm_plan(SpmmPlan *p);
 
 // Y = A X (+ add); optionally acc_out = (acc_in + Y) (/ acc_div when > 0).

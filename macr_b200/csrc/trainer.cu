@@ -14,6 +14,7 @@
 #include <map>
 #include <new>
 
+#include "shard.cuh"
 #include "spmm.cuh"
 
 namespace macr {
@@ -449,9 +450,93 @@ struct macr_lgcn_trainer : macr::TrainerBase {
   bool emb_dirty;
   int launches;
   int mode = MACR_TRAIN_RUBIBCEBOTH;  // MACR_TRAIN_NORMALBCE: `--loss bce`
+  // row-partitioned mode (macr_lgcn_trainer_shard): this rank owns the rows
+  // [u_lo,u_hi) of the user table and [i_lo,i_hi) of the item table; every [N][64] buffer stays
+  // full-size, its owned rows are computed here and stored into the peers' buffers (NVLink peer
+  // stores + flag barrier) wherever the next kernel reads rows of other ranks
+  bool sharded = false;
+  macr_shard_desc sd{};
+  float *peerU[macr::kMaxRanks], *peerI[macr::kMaxRanks], *peerE[macr::kMaxRanks], *peerT[macr::kMaxRanks];
+  macr::PeerFlagsDev peerF{};
+  unsigned long long *flags = nullptr;  // [0..15] arrival flags, [16] barrier epoch, [17] error (int)
 };
 
 namespace macr {
+
+// all-gather of this rank's owned rows of one [N][64] buffer into every peer's copy
+enum { XCH_TABLES = 0, XCH_EMEAN = 1, XCH_TMP0 = 2, XCH_TMP1 = 3 };
+static int lgcn_exchange(macr_lgcn_trainer *h, int which, cudaStream_t s) {
+  if (!h->sharded || h->sd.world <= 1) return MACR_OK;
+  const macr_shard_desc &d = h->sd;
+  const int64_t N = h->nu + h->ni;
+  PeerPush p{};
+  p.rank = d.rank;
+  p.world = d.world;
+  p.rows[0] = d.u_hi - d.u_lo;
+  p.rows[1] = d.i_hi - d.i_lo;
+  const long long uo = d.u_lo * kD, io_tab = d.i_lo * kD, io_buf = (h->nu + d.i_lo) * kD;
+  if (which == XCH_TABLES) {
+    p.src[0] = h->U + uo;
+    p.src[1] = h->I + io_tab;
+  } else {
+    const float *base = which == XCH_EMEAN ? h->Emean : h->tmp + (which - XCH_TMP0) * N * kD;
+    p.src[0] = base + uo;
+    p.src[1] = base + io_buf;
+  }
+  for (int r = 0; r < d.world; ++r) {
+    if (r == d.rank) continue;
+    if (which == XCH_TABLES) {
+      p.dst[0][r] = h->peerU[r] + uo;
+      p.dst[1][r] = h->peerI[r] + io_tab;
+    } else {
+      float *base = which == XCH_EMEAN ? h->peerE[r] : h->peerT[r] + (which - XCH_TMP0) * N * kD;
+      p.dst[0][r] = base + uo;
+      p.dst[1][r] = base + io_buf;
+    }
+  }
+  int rc = launch_peer_push(p, s);
+  if (rc) return rc;
+  return launch_peer_barrier_dev(h->peerF, h->flags + 16, reinterpret_cast<int *>(h->flags + 17), d.rank,
+                                 d.world, s);
+}
+
+// E_mean of the current tables (LightGCN.py:288-309).  Row-partitioned: E0's rows of other ranks are
+// fetched first (their owners have just updated them), every layer is computed for the owned rows
+// and all-gathered, and so is the layer mean.  -> number of kernels launched
+static int lgcn_forward(macr_lgcn_trainer *h, cudaStream_t s, int *launches) {
+  const int per_spmm = h->plan.n_multi ? 2 : 1;
+  if (!h->sharded) {
+    if (launches) *launches += h->L * per_spmm;
+    return launch_lgcn_propagate(h->rowptr, h->col, h->val, h->U, h->nu, h->I, h->ni, h->L, h->Emean,
+                                 h->tmp, s, &h->plan);
+  }
+  const int64_t N = h->nu + h->ni;
+  int rc = lgcn_exchange(h, XCH_TABLES, s);
+  if (rc) return rc;
+  RowSrc e0{h->U, h->I, h->nu};
+  if (h->L == 0) {
+    if (launches) *launches += 2;
+    return launch_lgcn_propagate(h->rowptr, h->col, h->val, h->U, h->nu, h->I, h->ni, 0, h->Emean, h->tmp, s,
+                                 &h->plan);
+  }
+  float *buf[2] = {h->tmp, h->tmp + N * kD};
+  RowSrc x = e0;
+  for (int k = 0; k < h->L; ++k) {
+    const bool last = k == h->L - 1;
+    float *y = last ? nullptr : buf[k & 1];
+    RowSrc accin = (k == 0) ? e0 : RowSrc{h->Emean, h->Emean, N};
+    rc = launch_spmm_planned(&h->plan, h->rowptr, h->col, h->val, N, x, nullptr, y, accin, h->Emean,
+                             last ? (float)(h->L + 1) : 0.f, nullptr, s);
+    if (rc) return rc;
+    if (!last) {
+      rc = lgcn_exchange(h, XCH_TMP0 + (k & 1), s);
+      if (rc) return rc;
+      x = RowSrc{y, y, N};
+    }
+  }
+  if (launches) *launches += h->L * per_spmm + 2 * (h->L + 1);
+  return lgcn_exchange(h, XCH_EMEAN, s);
+}
 
 static int lgcn_enqueue_impl(macr_lgcn_trainer *h, int B, int train) {
   const macr_hparams &hp = h->hp;
@@ -475,10 +560,8 @@ static int lgcn_enqueue_impl(macr_lgcn_trainer *h, int B, int train) {
     MACR_CUDA(cudaEventRecord(h->ev_join, side));
     launches += 1;
   }
-  rc = launch_lgcn_propagate(h->rowptr, h->col, h->val, h->U, h->nu, h->I, h->ni, h->L, h->Emean,
-                             h->tmp, s, &h->plan);
+  rc = lgcn_forward(h, s, &launches);
   if (rc) return rc;
-  launches += h->L * (h->plan.n_multi ? 2 : 1);
   rc = launch_gather_dots(Ue, Ie, h->U, h->I, h->w, h->wu, nullptr, nullptr, nullptr, h->st, B, yp,
                           yn, sp, sn, su, rq, h->snap, &g, s);
   if (rc) return rc;
@@ -510,16 +593,25 @@ static int lgcn_enqueue_impl(macr_lgcn_trainer *h, int B, int train) {
       if (rc) return rc;
       acc = buf[k & 1];
       launches += h->plan.n_multi ? 2 : 1;
+      if (h->sharded && k + 1 < h->L) {  // the next layer reads acc rows of every rank
+        rc = lgcn_exchange(h, XCH_TMP0 + (k & 1), s);
+        if (rc) return rc;
+        launches += 2;
+      }
     }
     float *grad = const_cast<float *>(acc);
     const float lam = hp.decay / (float)hp.batch_size_flag;
     rc = launch_l2_rows(h->planU, h->planI, B, h->U, h->I, h->nu, lam, grad, s);
     if (rc) return rc;
-    rc = launch_adam_dense(h->U, h->mU, h->vU, grad, h->nu * kD, hp.lr, h->st, hp.beta1, hp.beta2,
-                           hp.eps, s);
+    // dense Adam: every row of both tables, or -- row-partitioned -- the rows this rank owns
+    const int64_t u0 = h->sharded ? h->sd.u_lo : 0, u1 = h->sharded ? h->sd.u_hi : h->nu;
+    const int64_t i0 = h->sharded ? h->sd.i_lo : 0, i1 = h->sharded ? h->sd.i_hi : h->ni;
+    rc = launch_adam_dense(h->U + u0 * kD, h->mU + u0 * kD, h->vU + u0 * kD, grad + u0 * kD,
+                           (u1 - u0) * kD, hp.lr, h->st, hp.beta1, hp.beta2, hp.eps, s);
     if (rc) return rc;
-    rc = launch_adam_dense(h->I, h->mI, h->vI, grad + h->nu * kD, h->ni * kD, hp.lr, h->st,
-                           hp.beta1, hp.beta2, hp.eps, s);
+    rc = launch_adam_dense(h->I + i0 * kD, h->mI + i0 * kD, h->vI + i0 * kD,
+                           grad + (h->nu + i0) * kD, (i1 - i0) * kD, hp.lr, h->st, hp.beta1,
+                           hp.beta2, hp.eps, s);
     if (rc) return rc;
     launches += 3;
     const int frozen = h->mode == MACR_TRAIN_NORMALBCE ? 3 : h->mode == MACR_TRAIN_RUBIBCE ? 2 : 0;
@@ -573,6 +665,8 @@ extern "C" int macr_lgcn_trainer_create(macr_lgcn_trainer **out, const int32_t *
   MACR_CUDA(cudaMalloc(&h->g3_nz, sizeof(uint32_t) * ((size_t)(n_users + n_items + 31) / 32 + 1)));
   rc = build_spmm_plan(rowptr, n_users + n_items, &h->plan);
   if (rc) return rc;
+  MACR_CUDA(cudaMalloc(&h->flags, sizeof(unsigned long long) * 32));
+  MACR_CUDA(cudaMemset(h->flags, 0, sizeof(unsigned long long) * 32));
   h->emb_dirty = true;
   MACR_CUDA(cudaStreamSynchronize(h->s));
   *out = h;
@@ -673,8 +767,7 @@ extern "C" int macr_lgcn_trainer_set_mode(macr_lgcn_trainer *h, int mode) {
 extern "C" int macr_lgcn_trainer_embeddings(macr_lgcn_trainer *h, const float **Emean) {
   MACR_CHECK_ARG(h && Emean, "macr_lgcn_trainer_embeddings: null argument");
   if (h->emb_dirty) {
-    int rc = launch_lgcn_propagate(h->rowptr, h->col, h->val, h->U, h->nu, h->I, h->ni, h->L,
-                                   h->Emean, h->tmp, h->s, &h->plan);
+    int rc = lgcn_forward(h, h->s, nullptr);
     if (rc) return rc;
     h->emb_dirty = false;
   }
@@ -693,6 +786,63 @@ extern "C" int macr_lgcn_trainer_set_steps_done(macr_lgcn_trainer *h, int64_t t)
   h->emb_dirty = true;  // checkpoint resume: the caller has just overwritten the tables
   return h->set_steps(t);
 }
+// ---- row-partitioned mode -------------------------------------------------------------------
+extern "C" int macr_lgcn_trainer_ipc_export(macr_lgcn_trainer *h,
+                                            unsigned char handles[3][MACR_IPC_HANDLE_BYTES]) {
+  MACR_CHECK_ARG(h && handles, "macr_lgcn_trainer_ipc_export: null argument");
+  void *bufs[3] = {h->Emean, h->tmp, h->flags};
+  for (int k = 0; k < 3; ++k) {
+    cudaIpcMemHandle_t ih;
+    MACR_CUDA(cudaIpcGetMemHandle(&ih, bufs[k]));
+    memcpy(handles[k], &ih, sizeof(ih));
+  }
+  return MACR_OK;
+}
+
+extern "C" int macr_lgcn_trainer_shard(macr_lgcn_trainer *h, const macr_shard_desc *desc,
+                                       float *const *peer_U, float *const *peer_I,
+                                       float *const *peer_Emean, float *const *peer_tmp,
+                                       uint64_t *const *peer_flags) {
+  MACR_CHECK_ARG(h && desc, "macr_lgcn_trainer_shard: null argument");
+  MACR_CHECK_ARG(desc->world >= 1 && desc->world <= kMaxRanks && desc->rank >= 0 &&
+                     desc->rank < desc->world,
+                 "macr_lgcn_trainer_shard: rank %d / world %d", desc->rank, desc->world);
+  MACR_CHECK_ARG(0 <= desc->u_lo && desc->u_lo <= desc->u_hi && desc->u_hi <= h->nu &&
+                     0 <= desc->i_lo && desc->i_lo <= desc->i_hi && desc->i_hi <= h->ni,
+                 "macr_lgcn_trainer_shard: owned ranges outside the tables");
+  MACR_CHECK_ARG(h->steps_done == 0 && h->graphs.empty() && h->graphs_eval.empty(),
+                 "macr_lgcn_trainer_shard: call it before the first step");
+  for (int r = 0; r < desc->world; ++r) {
+    if (r == desc->rank) continue;
+    MACR_CHECK_ARG(peer_U && peer_I && peer_Emean && peer_tmp && peer_flags && peer_U[r] && peer_I[r] &&
+                       peer_Emean[r] && peer_tmp[r] && peer_flags[r],
+                   "macr_lgcn_trainer_shard: null peer pointer (rank %d)", r);
+    h->peerU[r] = peer_U[r];
+    h->peerI[r] = peer_I[r];
+    h->peerE[r] = peer_Emean[r];
+    h->peerT[r] = peer_tmp[r];
+    h->peerF.p[r] = reinterpret_cast<unsigned long long *>(peer_flags[r]);
+  }
+  h->peerF.p[desc->rank] = h->flags;
+  h->sd = *desc;
+  // the segment plan of the rows this rank owns (a row's segmentation depends on the row alone,
+  // so owned rows come out bit-identical to the single-GPU propagation)
+  free_spmm_plan(&h->plan);
+  const int64_t ranges[4] = {desc->u_lo, desc->u_hi, h->nu + desc->i_lo, h->nu + desc->i_hi};
+  int rc = build_spmm_plan(h->rowptr, h->nu + h->ni, &h->plan, ranges);
+  if (rc) return rc;
+  h->sharded = true;
+  h->emb_dirty = true;
+  return MACR_OK;
+}
+
+extern "C" int macr_lgcn_trainer_peer_error(macr_lgcn_trainer *h, int *err_out) {
+  MACR_CHECK_ARG(h && err_out, "macr_lgcn_trainer_peer_error: null argument");
+  MACR_CUDA(cudaStreamSynchronize(h->s));
+  MACR_CUDA(cudaMemcpy(err_out, h->flags + 17, sizeof(int), cudaMemcpyDeviceToHost));
+  return MACR_OK;
+}
+
 extern "C" int macr_lgcn_trainer_destroy(macr_lgcn_trainer *h) {
   if (!h) return MACR_OK;
   cudaStreamSynchronize(h->s);
@@ -702,6 +852,7 @@ extern "C" int macr_lgcn_trainer_destroy(macr_lgcn_trainer *h) {
   cudaFree(h->tmp);
   cudaFree(h->g3);
   cudaFree(h->g3_nz);
+  cudaFree(h->flags);
   free_spmm_plan(&h->plan);
   delete h;
   return MACR_OK;

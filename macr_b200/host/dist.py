@@ -303,3 +303,115 @@ class RowShardedMFTrainer:
         for buf in (self._ipc_u, self._ipc_i, getattr(self, "_ipc_flags", None)):
             if buf is not None:
                 buf.free()
+
+
+def partition_adjacency(rowptr, col, val, n_users, u_lo, u_hi, i_lo, i_hi):
+    """1-D row partition of the normalised adjacency: the CSR of the rows a rank
+    owns -- user rows [u_lo,u_hi) and item rows n_users + [i_lo,i_hi) -- with the full N+1 row
+    pointer (rows of other ranks are empty) and GLOBAL column ids."""
+    rowptr = np.asarray(rowptr, np.int64)
+    n = len(rowptr) - 1
+    own = np.zeros(n, bool)
+    own[u_lo:u_hi] = True
+    own[n_users + i_lo:n_users + i_hi] = True
+    deg = np.diff(rowptr)
+    new_rp = np.zeros(n + 1, np.int64)
+    new_rp[1:] = np.cumsum(np.where(own, deg, 0))
+    sel = np.repeat(own, deg)
+    return (new_rp.astype(np.int32), np.ascontiguousarray(np.asarray(col)[sel], np.int32),
+            np.ascontiguousarray(np.asarray(val)[sel], np.float32))
+
+
+class RowShardedLGCNTrainer:
+    """LightGCN `bceboth` training with the adjacency, the propagation and the dense Adam
+    row-partitioned over the ranks (SURVEY 8e row "LightGCN SpMM"; LightGCN.py:257-269,297-305).
+
+    Rank r owns contiguous user and item id ranges: it holds the nonzeros of those rows only,
+    computes every propagation layer (forward and backward) for them and applies Adam to them.
+    Each [N,64] layer buffer is full-size on every rank; after a layer the owned rows are stored
+    straight into the peers' buffers over NVLink (CUDA-IPC mapped peer memory, a flag barrier after
+    the stores) -- the all-gather of E_k, inside the step's CUDA graph, no NCCL on the data path.
+    Dots, the B x B grid and the batch's row gradients are replicated (batch positions only).
+    Owned rows, losses, w and w_user are bit-identical to the single-GPU trainer: a row's segment
+    plan depends on the row alone (tests/test_gpu_multi.py).  One rank per GPU (NCCL group for the
+    handle exchange); batches must be identical on every rank."""
+
+    def __init__(self, rowptr, col, val, U, I, w, wu, n_layers, hp, max_batch, rank=None, world=None,
+                 device="cuda:0", group=None):
+        import ctypes as C
+
+        from .. import ops
+
+        self.ops, self.group = ops, group
+        self.rank = dist.get_rank(group) if rank is None else rank
+        self.world = dist.get_world_size(group) if world is None else world
+        self.n_users, self.n_items = U.shape[0], I.shape[0]
+        ub, ib = user_shard_bounds(self.n_users, self.world), item_shard_bounds(self.n_items, self.world)
+        self.u_lo, self.u_hi = int(ub[self.rank]), int(ub[self.rank + 1])
+        self.i_lo, self.i_hi = int(ib[self.rank]), int(ib[self.rank + 1])
+        self.dev = torch.device(device)
+        rp, cl, vl = partition_adjacency(rowptr, col, val, self.n_users, self.u_lo, self.u_hi, self.i_lo, self.i_hi)
+        self.local_nnz = int(len(cl))
+        d = U.shape[1]
+        self._ipc_u = ops.IpcBuffer(self.n_users * d * 4, self.dev)
+        self._ipc_i = ops.IpcBuffer(self.n_items * d * 4, self.dev)
+        tU, tI = self._ipc_u.as_f32((self.n_users, d)), self._ipc_i.as_f32((self.n_items, d))
+        as_t = lambda a: a if isinstance(a, torch.Tensor) else torch.from_numpy(np.ascontiguousarray(a, np.float32))
+        tU.copy_(as_t(U))  # every rank starts from the full tables; from then on owners refresh their rows
+        tI.copy_(as_t(I))
+        self.trainer = ops.LGCNTrainer(rp, cl, vl, tU, tI, w, wu, n_layers, hp, max_batch, device=self.dev)
+        self._peers = []
+        desc = ops.ShardDesc(self.rank, self.world, self.u_lo, self.u_hi, self.i_lo, self.i_hi, max_batch)
+        pu, pi, pe, pt, pf = ((C.c_void_p * self.world)() for _ in range(5))
+        if self.world > 1:
+            mine = [self._ipc_u.handle, self._ipc_i.handle] + self.trainer.ipc_export()
+            every = [None] * self.world
+            dist.all_gather_object(every, mine, group=self.group)
+            for r, hs in enumerate(every):
+                if r == self.rank:
+                    continue
+                ptrs = [ops.IpcBuffer.open_peer(h) for h in hs]
+                self._peers += ptrs
+                pu[r], pi[r], pe[r], pt[r], pf[r] = ptrs
+        self.trainer.shard(desc, pu, pi, pe, pt, pf)
+        if self.world > 1:
+            torch.cuda.synchronize(self.dev)
+            dist.barrier(group=self.group)  # everybody is mapped before the first peer store
+
+    def step_device(self, users, pos, neg, train=True):
+        return self.trainer.step_device(users, pos, neg, train)
+
+    def run(self, batches, train=True, losses=None):
+        return self.trainer.run(batches, train, losses)
+
+    def run_host(self, batches_host, losses_host=None):
+        return self.trainer.run_host(batches_host, losses_host)
+
+    def embeddings(self):
+        """(users [U,64], items [I,64]) propagated tables, complete on every rank."""
+        return self.trainer.embeddings()
+
+    def check_peers(self):
+        e = self.trainer.peer_error()
+        if e:
+            raise self.ops.MacrError(f"rank {self.rank}: peer {e - 1} never reached an exchange barrier")
+
+    def local_tables(self):
+        t = self.trainer.tab
+        return {"U": t.U[self.u_lo:self.u_hi], "mU": t.mU[self.u_lo:self.u_hi], "vU": t.vU[self.u_lo:self.u_hi],
+                "I": t.I[self.i_lo:self.i_hi], "mI": t.mI[self.i_lo:self.i_hi], "vI": t.vI[self.i_lo:self.i_hi],
+                "w": t.w, "wu": t.wu}
+
+    def close(self):
+        if self.trainer is None:
+            return
+        torch.cuda.synchronize(self.dev)
+        if self.world > 1 and dist.is_initialized():
+            dist.barrier(group=self.group)  # no peer may still be storing into this rank's buffers
+        self.trainer.close()
+        self.trainer = None
+        for p in self._peers:
+            self.ops.IpcBuffer.close_peer(p)
+        self._peers = []
+        self._ipc_u.free()
+        self._ipc_i.free()

@@ -461,6 +461,23 @@ class LGCNTrainer:
                              C.c_void_p(losses_host.data_ptr())), "trainer_run_host")
         return losses_host
 
+    # ---- row-partitioned mode (include/macr_b200.h: macr_lgcn_trainer_shard) ----
+    def ipc_export(self):
+        """IPC handles of the trainer's {E_mean, layer buffers, flags}: 3 x 64 bytes."""
+        buf = C.create_string_buffer(3 * 64)
+        check(lib().macr_lgcn_trainer_ipc_export(self._h, buf), "macr_lgcn_trainer_ipc_export")
+        return [buf.raw[64 * k:64 * (k + 1)] for k in range(3)]
+
+    def shard(self, desc, peer_u, peer_i, peer_e, peer_t, peer_f):
+        """peer_*: ctypes arrays (c_void_p * world) of every peer's buffers mapped into this process."""
+        check(lib().macr_lgcn_trainer_shard(self._h, C.byref(desc), peer_u, peer_i, peer_e, peer_t, peer_f),
+              "macr_lgcn_trainer_shard")
+
+    def peer_error(self):
+        out = C.c_int(0)
+        check(lib().macr_lgcn_trainer_peer_error(self._h, C.byref(out)), "macr_lgcn_trainer_peer_error")
+        return out.value
+
     @property
     def launches_per_step(self):
         return int(lib().macr_lgcn_trainer_launches_per_step(self._h))

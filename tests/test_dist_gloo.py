@@ -199,3 +199,32 @@ def test_row_sharded_trainer_world1_needs_no_process_group(oracle):
     np.testing.assert_array_equal(loc["U"].numpy(), single.U)
     np.testing.assert_array_equal(loc["vI"].numpy(), single.vI)
     assert (sh.u_lo, sh.u_hi, sh.i_lo, sh.i_hi) == (0, n_users, 0, n_items)
+
+
+def test_partition_adjacency_rows_cover_the_graph_exactly_once():
+    """SURVEY 8e row 4 host logic: the per-rank CSRs hold disjoint row sets whose union is the
+    adjacency; row pointers stay N+1 long, column ids stay global."""
+    import scipy.sparse as sp
+
+    from macr_b200.host import dist as mdist
+
+    n_users, n_items = 37, 23
+    rng = np.random.RandomState(1)
+    R = sp.random(n_users, n_items, density=0.2, random_state=rng, format="csr", dtype=np.float32)
+    A = sp.bmat([[None, R], [R.T, None]], format="csr", dtype=np.float32)
+    A.sort_indices()
+    world = 3
+    ub, ib = mdist.user_shard_bounds(n_users, world), mdist.item_shard_bounds(n_items, world)
+    total = sp.csr_matrix(A.shape, dtype=np.float32)
+    for r in range(world):
+        rp, cl, vl = mdist.partition_adjacency(A.indptr, A.indices, A.data, n_users, int(ub[r]), int(ub[r + 1]),
+                                               int(ib[r]), int(ib[r + 1]))
+        assert rp.dtype == np.int32 and len(rp) == A.shape[0] + 1 and rp[-1] == len(cl) == len(vl)
+        part = sp.csr_matrix((vl, cl, rp), shape=A.shape)
+        own = np.zeros(A.shape[0], bool)
+        own[ub[r]:ub[r + 1]] = True
+        own[n_users + ib[r]:n_users + ib[r + 1]] = True
+        assert np.all(np.diff(rp)[~own] == 0)
+        np.testing.assert_array_equal(part[own].toarray(), A[own].toarray())
+        total = total + part
+    np.testing.assert_array_equal(total.toarray(), A.toarray())

@@ -87,3 +87,32 @@ def test_row_sharded_mf_training_equals_single_gpu(tmp_path):
     assert covered_u == N_USERS and covered_i == N_ITEMS
     assert np.abs(full["U"] - U).max() > 0
     tr.close()
+
+
+def test_row_partitioned_lightgcn_world1_equals_plain_trainer():
+    """world = 1: the row-partitioned code path (range-restricted segment plan, owned-range Adam,
+    the forward helper) on one GPU must reproduce the plain LightGCN trainer bit for bit."""
+    import torch
+
+    from helpers import make_interactions, norm_adj_csr
+    from macr_b200 import ops
+    from macr_b200.host import dist as mdist
+
+    n_users, n_items, Bq, L = 601, 257, 128, 2
+    lists = make_interactions(3, n_users, n_items, 40)
+    rowptr, col, val = norm_adj_csr(lists, n_users, n_items)
+    U, I, w, wu = make_model(9, n_users, n_items, scale=4.0)
+    hp = dict(lr=1e-3, alpha=1e-2, beta=1e-3, decay=1e-4, batch_size=Bq)
+    rng = np.random.RandomState(6)
+    batches = np.stack([np.stack(make_batch(rng, n_users, n_items, Bq)) for _ in range(3)]).astype(np.int32)
+    db = torch.from_numpy(batches).cuda()
+    tr = ops.LGCNTrainer(rowptr, col, val, U, I, w, wu, L, ops.HParams.make(**hp), max_batch=Bq)
+    sh = mdist.RowShardedLGCNTrainer(rowptr, col, val, U, I, w, wu, L, ops.HParams.make(**hp), Bq, rank=0, world=1)
+    np.testing.assert_array_equal(sh.run(db).cpu().numpy(), tr.run(db).cpu().numpy())
+    for k, v in sh.local_tables().items():
+        np.testing.assert_array_equal(v.cpu().numpy(), getattr(tr.tab, k).cpu().numpy(), err_msg=k)
+    for a, b in zip(sh.embeddings(), tr.embeddings()):
+        np.testing.assert_array_equal(a.cpu().numpy(), b.cpu().numpy())
+    sh.check_peers()
+    sh.close()
+    tr.close()

@@ -99,6 +99,82 @@ def test_row_sharded_training_over_nccl_equals_single_gpu(tmp_path, exchange):
     tr.close()
 
 
+# ---- row-partitioned LightGCN --------------------------------------------------
+LG_USERS, LG_ITEMS, LG_B, LG_L, LG_STEPS = 1201, 503, 256, 2, 4
+LG_HP = dict(lr=1e-3, alpha=1e-2, beta=1e-3, decay=1e-4, batch_size=LG_B)
+
+
+def _lg_inputs():
+    from helpers import make_interactions, norm_adj_csr
+
+    lists = make_interactions(3, LG_USERS, LG_ITEMS, 70)  # popular-enough rows: multi-segment rows exist
+    rowptr, col, val = norm_adj_csr(lists, LG_USERS, LG_ITEMS)
+    U, I, w, wu = make_model(9, LG_USERS, LG_ITEMS, scale=4.0)
+    rng = np.random.RandomState(6)
+    batches = np.stack([np.stack(make_batch(rng, LG_USERS, LG_ITEMS, LG_B)) for _ in range(LG_STEPS)]).astype(np.int32)
+    return rowptr, col, val, U, I, w, wu, batches
+
+
+def _lgcn_worker(rank, world, port, out_dir):
+    from macr_b200 import ops
+    from macr_b200.host import dist as mdist
+
+    os.environ["MASTER_ADDR"], os.environ["MASTER_PORT"] = "127.0.0.1", str(port)
+    torch.cuda.set_device(rank)
+    dev = torch.device("cuda", rank)
+    dist.init_process_group("nccl", rank=rank, world_size=world, device_id=dev)
+    try:
+        rowptr, col, val, U, I, w, wu, batches = _lg_inputs()
+        sh = mdist.RowShardedLGCNTrainer(rowptr, col, val, U, I, w, wu, LG_L, ops.HParams.make(**LG_HP), LG_B,
+                                         rank=rank, world=world, device=dev)
+        assert sh.local_nnz < len(col)
+        db = torch.from_numpy(batches).to(dev)
+        l_eval = sh.run(db[:1], train=False).cpu().numpy()       # loss-only pass: moves nothing
+        losses = sh.run(db[:2]).cpu().numpy()                    # epoch replay of the step graph
+        losses = np.concatenate([losses, sh.run_host(torch.from_numpy(batches[2:]).pin_memory()).numpy()])
+        ue, ie = sh.embeddings()
+        sh.check_peers()
+        out = {k: v.cpu().numpy() for k, v in sh.local_tables().items()}
+        out.update(losses=losses, l_eval=l_eval, ue=ue.cpu().numpy(), ie=ie.cpu().numpy(),
+                   bounds=np.array([sh.u_lo, sh.u_hi, sh.i_lo, sh.i_hi]))
+        np.savez(os.path.join(out_dir, f"lgcn_rank{rank}.npz"), **out)
+        sh.close()
+    finally:
+        dist.destroy_process_group()
+
+
+def test_row_partitioned_lightgcn_equals_single_gpu(tmp_path):
+    if _n_gpus() < 2:
+        pytest.skip("needs >= 2 GPUs")
+    from macr_b200 import ops
+
+    world = min(_n_gpus(), 4)
+    mp.spawn(_lgcn_worker, args=(world, _free_port(), str(tmp_path)), nprocs=world, join=True)
+    rowptr, col, val, U, I, w, wu, batches = _lg_inputs()
+    tr = ops.LGCNTrainer(rowptr, col, val, U, I, w, wu, LG_L, ops.HParams.make(**LG_HP), max_batch=LG_B)
+    db = torch.from_numpy(batches).cuda()
+    l_eval = tr.run(db[:1], train=False).cpu().numpy()
+    want = tr.run(db).cpu().numpy()
+    ue, ie = tr.embeddings()
+    t = tr.tab
+    full = {k: getattr(t, k).cpu().numpy() for k in ("U", "mU", "vU", "I", "mI", "vI", "w", "wu")}
+    assert np.abs(full["U"] - U).max() > 0
+    for r in range(world):
+        z = np.load(tmp_path / f"lgcn_rank{r}.npz")
+        u_lo, u_hi, i_lo, i_hi = (int(x) for x in z["bounds"])
+        np.testing.assert_array_equal(z["l_eval"], l_eval)
+        np.testing.assert_array_equal(z["losses"], want)
+        for k in ("U", "mU", "vU"):
+            np.testing.assert_array_equal(z[k], full[k][u_lo:u_hi], err_msg=f"rank {r} {k}")
+        for k in ("I", "mI", "vI"):
+            np.testing.assert_array_equal(z[k], full[k][i_lo:i_hi], err_msg=f"rank {r} {k}")
+        np.testing.assert_array_equal(z["w"], full["w"])
+        np.testing.assert_array_equal(z["wu"], full["wu"])
+        np.testing.assert_array_equal(z["ue"], ue.cpu().numpy())  # complete on every rank
+        np.testing.assert_array_equal(z["ie"], ie.cpu().numpy())
+    tr.close()
+
+
 T_Q, S_ITEMS, K = 700, 9000, 20
 
 
