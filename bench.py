@@ -24,6 +24,9 @@ configuration that fits one GPU and the one where the fused step is HBM-bound.
                scoring of the shard, all-gather of the [T,K] candidates and the on-device K-way
                merge inside the timed region.  `roofline.frac` counts ALGORITHMIC flops 2*64*T*I.
   cpu_baseline the oracle port of the same step (C + OpenMP) on this box's host cores (N=1).
+  lightgcn     MACR-LightGCN `bceboth` step on a synthetic 1M x 100k graph (nnz 20 M), adjacency,
+               propagation and dense Adam row-partitioned over the ranks (per-layer all-gather by
+               NVLink peer stores inside the step graph), strong scaling.
   gowalla      (N=1 only) BASELINE configs[1]: gowalla shapes B=4096 -- the small-table regime where
                the B x B grid (MUFU-bound) sets the pace; device value, e2e, kernel rooflines, scoring.
 """
@@ -562,6 +565,94 @@ def sharded_scoring(cx, reps=3):
     return out
 
 
+LG_USERS, LG_ITEMS, LG_EDGES, LG_BATCH, LG_LAYERS = 1_000_000, 100_000, 10_000_000, 8192, 2
+
+
+def synth_graph(n_users, n_items, n_edges, seed):
+    """random bipartite train graph with Zipf(1.0)-popular items -> D^-1/2 A D^-1/2 as float32 CSR
+    (the `pre` adjacency of macr_lightgcn/utility/load_data.py:112-124); cached under /tmp because the
+    scaling run rebuilds the same graph at every N."""
+    path = f"/tmp/macr_bench_graph_{n_users}_{n_items}_{n_edges}_{seed}.npz"
+    if os.path.exists(path):
+        try:
+            z = np.load(path)
+            return z["rowptr"], z["col"], z["val"]
+        except Exception:  # noqa: BLE001 -- a half-written cache from a killed run: rebuild
+            pass
+    import scipy.sparse as sp
+
+    rng = np.random.RandomState(seed)
+    u = rng.randint(0, n_users, int(n_edges * 1.1)).astype(np.int64)
+    i = np.minimum(np.searchsorted(zipf_cdf(n_items), rng.rand(len(u))), n_items - 1).astype(np.int64)
+    key = np.unique(u * n_items + i)
+    key = key[rng.permutation(len(key))[:n_edges]]
+    u, i = key // n_items, key % n_items
+    R = sp.csr_matrix((np.ones(len(u), np.float32), (u, i)), shape=(n_users, n_items))
+    A = sp.bmat([[None, R], [R.T, None]], format="csr", dtype=np.float32)
+    deg = np.asarray(A.sum(1)).ravel()
+    with np.errstate(divide="ignore"):
+        dinv = np.power(deg, -0.5).astype(np.float32)
+    dinv[np.isinf(dinv)] = 0
+    A = sp.diags(dinv).dot(A).dot(sp.diags(dinv)).tocsr().astype(np.float32)
+    A.sort_indices()
+    out = A.indptr.astype(np.int32), A.indices.astype(np.int32), A.data.astype(np.float32)
+    tmp = path + f".{os.getpid()}.tmp.npz"
+    np.savez(tmp, rowptr=out[0], col=out[1], val=out[2])
+    os.replace(tmp, path)
+    return out
+
+
+def sharded_lgcn(cx, K, W):
+    """MACR-LightGCN `bceboth` step on a synthetic 1M x 100k graph (nnz(A) = 20 M), adjacency +
+    propagation + dense Adam row-partitioned over the ranks, strong scaling."""
+    torch = cx.torch
+    from macr_b200 import ops
+    from macr_b200.host.dist import RowShardedLGCNTrainer
+
+    rowptr, col, val = synth_graph(LG_USERS, LG_ITEMS, LG_EDGES, 1)
+    N, nnz = LG_USERS + LG_ITEMS, len(col)
+    w, wu = synth_model(12345, 8, 8)[2:]
+    hp = ops.HParams.make(lr=1e-3, alpha=1e-2, beta=1e-3, decay=1e-4, batch_size=LG_BATCH)
+    sh = RowShardedLGCNTrainer(rowptr, col, val, DeviceRows(LG_USERS, 31, cx.dev)[0:LG_USERS],
+                               DeviceRows(LG_ITEMS, 33, cx.dev)[0:LG_ITEMS], w, wu, LG_LAYERS, hp, LG_BATCH,
+                               rank=cx.rank, world=cx.world, device=cx.dev)
+    nb = min(16, W + K)
+    ids = torch.from_numpy(synth_batches(777, nb, LG_USERS, LG_ITEMS, LG_BATCH)).to(cx.dev)
+    losses = torch.zeros((nb, 4), dtype=torch.float32, device=cx.dev)
+    for s in range(W):
+        sh.run(ids[s % nb:s % nb + 1], True, losses[s % nb:s % nb + 1])
+    cx.barrier()
+    e0, e1 = cx.events()
+    e0.record()
+    for s in range(K):
+        sh.run(ids[(W + s) % nb:(W + s) % nb + 1], True, losses[(W + s) % nb:(W + s) % nb + 1])
+    e1.record()
+    cx.barrier()
+    t = cx.max_over_ranks(e0.elapsed_time(e1) * 1e-3) / K
+    sh.check_peers()
+    # SURVEY 8d, gather-honest SpMM bytes (N*d*4 = 282 MB exceeds L2): 8*nnz + 4*nnz*d + 4*N*d per SpMM
+    spmm_bytes = 8.0 * nnz + 4.0 * nnz * D + 4.0 * N * D
+    step_bytes = 2 * LG_LAYERS * spmm_bytes + 24.0 * D * N + 12.0 * D * LG_BATCH
+    pk = cx.peaks["hbm_gbs"]
+    out = {"workload": f"MACR-LightGCN synthetic U={LG_USERS} I={LG_ITEMS} nnz(A)={nnz} L={LG_LAYERS} d=64 "
+                       f"B={LG_BATCH} bceboth, adjacency/propagation/Adam row-partitioned",
+           "metric": "train_interactions_per_sec", "value": LG_BATCH / t, "unit": "interactions/s",
+           "ms_per_step": 1e3 * t, "scaling": "strong", "sharding": f"rows/{cx.world}",
+           "exchange": "per-layer all-gather of the owned E_k rows by NVLink peer stores + flag barrier, "
+                       "inside the step's CUDA graph (2L per step)",
+           "exchange_bytes_per_layer": 4.0 * N * D, "local_nnz_rank0": sh.local_nnz,
+           "launches_per_step": sh.trainer.launches_per_step,
+           "roofline": {"bound": "hbm", "bytes_per_step": step_bytes, "peak": pk * cx.world, "unit": "GB/s",
+                        "achieved": step_bytes / t / 1e9, "frac": step_bytes / t / 1e9 / (pk * cx.world),
+                        "note": "gather-honest bytes (every nonzero reads a 256-byte row; the operand exceeds "
+                                "L2) of 2L SpMMs + the dense Adam, against N x the measured HBM peak"},
+           "final_loss": float(losses[(W + K - 1) % nb, 0].item())}
+    sh.close()
+    del sh, ids
+    torch.cuda.empty_cache()
+    return out
+
+
 def gowalla_block(cx, K, W, with_cpu):
     """BASELINE configs[1] on one GPU: the small-table regime (tables L2-sized, B x B grid MUFU-bound)."""
     torch = cx.torch
@@ -755,6 +846,7 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-scoring", action="store_true")
     ap.add_argument("--no-gowalla", action="store_true")
+    ap.add_argument("--no-lgcn", action="store_true")
     args = ap.parse_args()
     if args.impl == "reference":
         return run_reference(args)
@@ -763,6 +855,14 @@ def main():
     K, W = max(1, args.steps), max(3, args.warmup)
     tr = sharded_train(cx, K, W)
     scoring = None if args.no_scoring else sharded_scoring(cx)
+    lgcn = None
+    if not args.no_lgcn:
+        try:  # secondary block: never allowed to take the headline line down
+            lgcn = sharded_lgcn(cx, min(K, 10), 3)
+        except Exception as e:  # noqa: BLE001
+            lgcn = {"unavailable": f"{type(e).__name__}: {e}"}
+            if cx.world > 1:
+                raise  # a rank that failed alone would leave the others in a barrier
     gow = None
     if cx.world == 1 and not args.no_gowalla:
         gow = gowalla_block(cx, max(K, 60), max(W, 9), with_cpu=not args.no_cpu_baseline)
@@ -781,7 +881,7 @@ def main():
             "data": "synthetic", "config": {"workload": WORKLOAD},
             "l2": "inputs far larger than L2: 8.45 GB of var/m/v (1/N per rank) swept every step",
             "final_loss": tr["final_loss"], "gpu_launches": tr["launches"] * K, "launches_per_step": tr["launches"],
-            "gowalla": gow,
+            "gowalla": gow, "lightgcn": lgcn,
             "sharding": tr["sharding"],
             "e2e": {"value": B * K / tr["t_e2e"], "unit": "interactions/s", "ms_per_step": 1e3 * tr["t_e2e"] / K,
                     "h2d_bytes_per_step": 3 * 4 * B, "d2h_bytes_per_step": 16,
