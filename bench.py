@@ -10,9 +10,9 @@ configuration that fits one GPU and the one where the fused step is HBM-bound.
 
   value        whole-job interactions/s, batches resident in HBM.  Both tables and their Adam slots
                are row-partitioned over the N ranks (`RowShardedMFTrainer`): per step ONE exchange
-               of the batch's rows (fused NVLink push into the peers' ghost rows + flag barrier;
-               NCCL all-reduce if peer memory cannot be mapped) and the single-GPU step graph on
-               the local slice.  CUDA events around the K steps, max over ranks.  The tables are
+               of the batch's rows -- inside the captured step graph: a fused NVLink push into the
+               peers' ghost rows, the dense sweep starts at once and only the gather branch waits
+               at a flag barrier (NCCL all-reduce before the step if peer memory cannot be mapped).  CUDA events around the K steps, max over ranks.  The tables are
                far larger than L2 (8.45 GB / N per rank vs 126 MB).
   e2e          the same K steps through `RowShardedMFTrainer.run_host` with HOST buffers: the ids
                in pinned host memory, H2D + K exchanges/steps + D2H of the losses + sync, wall clock.
@@ -444,17 +444,20 @@ def sharded_train(cx, K, W):
     cx.barrier()
     t_e2e = cx.max_over_ranks(t_e2e_local)
     clocks = sampler.stop()
-    # the exchange alone (renumber + push + barrier, or pack + all-reduce + unpack)
-    x0, x1 = cx.events()
-    for s in range(3):
-        sh.exchange_rows(ids[s % nb].view(-1), B)
-    cx.barrier()
-    x0.record()
-    for s in range(K):
-        sh.exchange_rows(ids[s % nb].view(-1), B)
-    x1.record()
-    cx.barrier()
-    t_ex = cx.max_over_ranks(x0.elapsed_time(x1) * 1e-3) / K
+    # the exchange alone -- all-reduce transport only (pack + all-reduce + unpack); the push transport
+    # lives inside the captured step (standalone: 23 us at N=2, 38 us at N=8, profiles/r2c_nvml_period.txt)
+    t_ex = None
+    if sh.exchange == "allreduce":
+        x0, x1 = cx.events()
+        for s in range(3):
+            sh.exchange_rows(ids[s % nb].view(-1), B)
+        cx.barrier()
+        x0.record()
+        for s in range(K):
+            sh.exchange_rows(ids[s % nb].view(-1), B)
+        x1.record()
+        cx.barrier()
+        t_ex = cx.max_over_ranks(x0.elapsed_time(x1) * 1e-3) / K
     sh.check_peers()
     # roofline of the HBM-bound kernel: the dense sweep over this rank's user slice, alone
     rows_u = t.U.shape[0]
@@ -484,9 +487,10 @@ def sharded_train(cx, K, W):
                          "note": "whole fused step (exchange + gather + dots + BxB BCE + row gradients + dense "
                                  "Adam) against its algorithmic bytes, per GPU"}}
     out = {"t_dev": t_dev, "ms_per_step": ms_step, "t_e2e": t_e2e, "clocks": clocks, "roofline": roofline,
-           "final_loss": final_loss, "launches": sh.trainer.launches_per_step + (3 if sh.exchange == "push" else 2),
+           "final_loss": final_loss, "launches": sh.trainer.launches_per_step + (1 if sh.exchange == "push" else 2),
            "sharding": {"tables": f"rows/{cx.world}", "exchange": sh.exchange,
-                        "exchange_ms": 1e3 * t_ex, "exchange_bytes_per_step": 3 * B * D * 4,
+                        "exchange_ms": None if t_ex is None else 1e3 * t_ex,
+                        "exchange_in_step_graph": sh.exchange == "push", "exchange_bytes_per_step": 3 * B * D * 4,
                         "rows_per_rank": [sh.n_lu, sh.n_li],
                         "hbm_bytes_per_rank_step": 24.0 * D * (sh.n_lu + sh.n_li),
                         "replicated": "dots + BxB grid + w/w_user gradients (batch positions only)"}}

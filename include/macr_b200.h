@@ -403,6 +403,19 @@ int macr_shard_push(const float *U_local, const float *I_local, const macr_shard
                     macr_stream_t stream);
 int macr_shard_barrier(uint64_t *const *peer_flags_host, int rank, int world, uint64_t epoch,
                        int *err_flag, macr_stream_t stream);
+/* The same exchange INSIDE the MF step graph (one rank per GPU): create the trainer on the local
+ * tables (owned rows + ghost rows, U / I in macr_ipc_alloc memory), export the handle of its flag
+ * array, then hand it every peer's ghost bases and flags before the first step.  From then on the
+ * ids given to macr_mf_trainer_step / _run / _run_host are GLOBAL ids, identical on every rank; the
+ * captured step renumbers them, stores the owned rows into the peers' ghost slots, lets the dense
+ * sweep start at once and waits for the peers' rows on the gather branch only.
+ * macr_mf_trainer_peer_error: synchronises; *err_out = 1 + r if peer r missed a barrier. */
+int macr_mf_trainer_ipc_export(macr_mf_trainer *h, unsigned char handle[MACR_IPC_HANDLE_BYTES]);
+int macr_mf_trainer_shard(macr_mf_trainer *h, const macr_shard_desc *desc,
+                          float *const *peer_U_ghost, float *const *peer_I_ghost,
+                          uint64_t *const *peer_flags);
+int macr_mf_trainer_peer_error(macr_mf_trainer *h, int *err_out);
+
 /* Row-partitioned LightGCN (SURVEY.md 8e row "LightGCN SpMM": 1-D row partition of A_hat, an
  * all-gather of E_k per layer): rank r owns user rows [u_lo,u_hi) and item rows [i_lo,i_hi).
  * replaces (distributed form of): _create_lightgcn_embed's row folds

@@ -103,6 +103,9 @@ PROTOTYPES = {
     "macr_shard_push": (i32, [vp, vp, C.POINTER(ShardDesc), vp, i32, i32, vp, C.POINTER(vp),
                               C.POINTER(vp), vp]),
     "macr_shard_barrier": (i32, [C.POINTER(vp), i32, i32, C.c_uint64, vp, vp]),
+    "macr_mf_trainer_ipc_export": (i32, [vp, C.c_char_p]),
+    "macr_mf_trainer_shard": (i32, [vp, C.POINTER(ShardDesc)] + [C.POINTER(vp)] * 3),
+    "macr_mf_trainer_peer_error": (i32, [vp, C.POINTER(i32)]),
     "macr_lgcn_trainer_ipc_export": (i32, [vp, C.c_char_p]),
     "macr_lgcn_trainer_shard": (i32, [vp, C.POINTER(ShardDesc)] + [C.POINTER(vp)] * 5),
     "macr_lgcn_trainer_peer_error": (i32, [vp, C.POINTER(i32)]),

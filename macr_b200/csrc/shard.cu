@@ -25,10 +25,7 @@
 
 namespace macr {
 
-struct PeerTabs {
-  float *u[kMaxRanks];  // ghost base (row n_local_u of rank r's U_local) as mapped in THIS process
-  float *i[kMaxRanks];
-};
+typedef PeerGhosts PeerTabs;  // ghost base (row n_local of rank r's table) as mapped in THIS process
 struct PeerFlags {
   unsigned long long *p[kMaxRanks];  // rank r's flag array [world]
 };
@@ -37,9 +34,15 @@ template <bool PUSH>
 __global__ void __launch_bounds__(256)
 shard_exchange_kernel(const float *__restrict__ U, const float *__restrict__ I, macr_shard_desc a,
                       const int32_t *__restrict__ ids3, int B, int parity,
-                      int32_t *__restrict__ local3, float *__restrict__ ex, PeerTabs peers) {
+                      int32_t *__restrict__ local3, float *__restrict__ ex, PeerTabs peers,
+                      const StepState *__restrict__ st) {
   const int q = (blockIdx.x * blockDim.x + threadIdx.x) >> 4, hl = threadIdx.x & 15;
   if (q >= 3 * B) return;
+  if (st) {  // inside the step graph: this step's slot of the staged epoch, parity from the Adam step
+    ids3 = st->gids_base + st->step_idx * 3LL * B;
+    local3 = const_cast<int32_t *>(st->ids_base) + st->step_idx * 3LL * B;
+    parity = (int)(st->t & 1);
+  }
   const bool is_user = q < B;
   const long long id = ids3[q];
   const long long lo = is_user ? a.u_lo : a.i_lo, hi = is_user ? a.u_hi : a.i_hi;
@@ -81,6 +84,14 @@ __global__ void shard_barrier_kernel(PeerFlags f, int rank, int world, unsigned 
       break;
     }
   }
+}
+
+int launch_shard_push_st(const float *U_local, const float *I_local, const macr_shard_desc &desc,
+                         const StepState *st, int B, const PeerGhosts &peers, cudaStream_t s) {
+  shard_exchange_kernel<true><<<(unsigned)((3LL * B * 16 + 255) / 256), 256, 0, s>>>(
+      U_local, I_local, desc, nullptr, B, 0, nullptr, nullptr, peers, st);
+  MACR_LAUNCH_CHECK();
+  return MACR_OK;
 }
 
 // ---- all-gather of row ranges by peer stores (row-partitioned LightGCN) --------
@@ -166,7 +177,7 @@ extern "C" int macr_shard_pack(const float *U_local, const float *I_local, const
   MACR_CHECK_ARG(parity == 0 || parity == 1, "macr_shard_pack: parity must be 0 or 1");
   PeerTabs none{};
   shard_exchange_kernel<false><<<(unsigned)((3LL * B * 16 + 255) / 256), 256, 0, as_stream(stream)>>>(
-      U_local, I_local, *desc, ids3, B, parity, local_ids3, ex, none);
+      U_local, I_local, *desc, ids3, B, parity, local_ids3, ex, none, nullptr);
   MACR_LAUNCH_CHECK();
   return MACR_OK;
 }
@@ -203,7 +214,7 @@ extern "C" int macr_shard_push(const float *U_local, const float *I_local, const
     MACR_CHECK_ARG(r == desc->rank || (peers.u[r] && peers.i[r]), "macr_shard_push: null peer %d", r);
   }
   shard_exchange_kernel<true><<<(unsigned)((3LL * B * 16 + 255) / 256), 256, 0, as_stream(stream)>>>(
-      U_local, I_local, *desc, ids3, B, parity, local_ids3, nullptr, peers);
+      U_local, I_local, *desc, ids3, B, parity, local_ids3, nullptr, peers, nullptr);
   MACR_LAUNCH_CHECK();
   return MACR_OK;
 }

@@ -17,6 +17,17 @@ struct PeerPush {
 };
 int launch_peer_push(const PeerPush &p, cudaStream_t s);
 
+// row-partitioned MF step, exchange inside the step graph: ids of the step being executed are
+// read from st->gids_base, renumbered into st->ids_base (same step slot) and every owned row is
+// stored into the ghost slot of every peer (parity = st->t & 1); see shard.cu
+struct PeerGhosts {
+  float *u[kMaxRanks];  // row n_local of rank r's local user table, mapped into this process
+  float *i[kMaxRanks];
+};
+struct StepState;
+int launch_shard_push_st(const float *U_local, const float *I_local, const macr_shard_desc &desc,
+                         const StepState *st, int B, const PeerGhosts &peers, cudaStream_t s);
+
 // flag barrier over peer memory whose epoch lives on the device (so it can sit in a CUDA graph):
 // *epoch_ctr is incremented by one per call; flags[r] = rank r's uint64[kMaxRanks] arrival flags
 struct PeerFlagsDev {

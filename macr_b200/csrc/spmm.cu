@@ -167,7 +167,39 @@ spmm_seg_kernel(const int32_t *__restrict__ seg_row, const int32_t *__restrict__
   else reinterpret_cast<float4 *>(partial + (long long)slot * kD)[hl] = acc;
 }
 
-// rows cut into several segments: partial rows summed in segment order, then the epilogue
+// rows cut into several segments: partial rows summed in a fixed order, then the epilogue.
+// A row of up to kCombineWide segments is summed by one half-warp in segment order (4 partial
+// rows in flight).  Longer rows -- a popular item of ml_10m has 430 segments, the head of a Zipf
+// catalogue thousands -- would be one long latency chain (~0.5 us per segment, longer than the
+// whole rest of the SpMM), so a whole CTA takes such a row: half-warp h sums segments h, h+16, ...
+// and the 16 sums are added in half-warp order through shared memory.  Both orders depend on the
+// row's segment count alone (deterministic; the same on every rank of a row-partitioned run).
+constexpr int kCombineWide = 32;
+
+__device__ __forceinline__ void add4(float4 &acc, const float4 &t) {
+  acc.x += t.x;
+  acc.y += t.y;
+  acc.z += t.z;
+  acc.w += t.w;
+}
+
+// acc += p[first], p[first + stride], ... (< n), in that order, four loads in flight
+__device__ __forceinline__ void sum_partials(float4 &acc, const float4 *__restrict__ p, int first,
+                                             int stride, int n) {
+  int k = first;
+  for (; k + 3 * stride < n; k += 4 * stride) {
+    const float4 t0 = p[(long long)k * (kD / 4)];
+    const float4 t1 = p[(long long)(k + stride) * (kD / 4)];
+    const float4 t2 = p[(long long)(k + 2 * stride) * (kD / 4)];
+    const float4 t3 = p[(long long)(k + 3 * stride) * (kD / 4)];
+    add4(acc, t0);
+    add4(acc, t1);
+    add4(acc, t2);
+    add4(acc, t3);
+  }
+  for (; k < n; k += stride) add4(acc, p[(long long)k * (kD / 4)]);
+}
+
 __global__ void __launch_bounds__(256)
 spmm_combine_kernel(const int32_t *__restrict__ multi_row, const int32_t *__restrict__ multi_slot0,
                     const int32_t *__restrict__ multi_nseg, int n_multi,
@@ -176,30 +208,49 @@ spmm_combine_kernel(const int32_t *__restrict__ multi_row, const int32_t *__rest
   const int hl = threadIdx.x & 15;
   const int m = (int)(((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 4);
   if (m >= n_multi) return;
-  const float4 *p = reinterpret_cast<const float4 *>(partial + (long long)multi_slot0[m] * kD) + hl;
   const int n = multi_nseg[m];
+  if (n > kCombineWide) return;  // spmm_combine_wide_kernel's row
+  const float4 *p = reinterpret_cast<const float4 *>(partial + (long long)multi_slot0[m] * kD) + hl;
   float4 acc = p[0];
-  for (int k = 1; k < n; ++k) {
-    const float4 t = p[(long long)k * (kD / 4)];
-    acc.x += t.x;
-    acc.y += t.y;
-    acc.z += t.z;
-    acc.w += t.w;
-  }
+  sum_partials(acc, p, 1, 1, n);
   spmm_epilogue(acc, multi_row[m], hl, add, Y, acc_in, acc_out, acc_div);
+}
+
+// one CTA per row of more than kCombineWide segments (wide_idx: indices into the multi_* arrays)
+__global__ void __launch_bounds__(256)
+spmm_combine_wide_kernel(const int32_t *__restrict__ wide_idx, const int32_t *__restrict__ multi_row,
+                         const int32_t *__restrict__ multi_slot0, const int32_t *__restrict__ multi_nseg,
+                         const float *__restrict__ partial, const float *__restrict__ add, float *Y,
+                         RowSrc acc_in, float *acc_out, float acc_div) {
+  __shared__ float4 s_part[16][16];
+  const int hl = threadIdx.x & 15, hw = threadIdx.x >> 4;
+  const int m = wide_idx[blockIdx.x];
+  const int n = multi_nseg[m];
+  const float4 *p = reinterpret_cast<const float4 *>(partial + (long long)multi_slot0[m] * kD) + hl;
+  float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+  sum_partials(acc, p, hw, 16, n);
+  s_part[hw][hl] = acc;
+  __syncthreads();
+  if (hw == 0) {
+    acc = s_part[0][hl];
+#pragma unroll
+    for (int k = 1; k < 16; ++k) add4(acc, s_part[k][hl]);
+    spmm_epilogue(acc, multi_row[m], hl, add, Y, acc_in, acc_out, acc_div);
+  }
 }
 
 // one-off, host side: the adjacency of a run never changes (LightGCN.py:257-269 builds it once)
 int build_spmm_plan(const int32_t *d_rowptr, int64_t n_rows, SpmmPlan *out, const int64_t *ranges) {
   std::vector<int32_t> rp((size_t)n_rows + 1);
   MACR_CUDA(cudaMemcpy(rp.data(), d_rowptr, sizeof(int32_t) * rp.size(), cudaMemcpyDeviceToHost));
-  std::vector<int32_t> srow, sstart, send, sslot, mrow, mslot0, mnseg;
+  std::vector<int32_t> srow, sstart, send, sslot, mrow, mslot0, mnseg, wide;
   int32_t n_slots = 0;
   for (int64_t r = 0; r < n_rows; ++r) {
     if (ranges && !((r >= ranges[0] && r < ranges[1]) || (r >= ranges[2] && r < ranges[3]))) continue;
     const int32_t st = rp[r], en = rp[r + 1];
     const int32_t nseg = en - st <= kSegNnz ? 1 : (en - st + kSegNnz - 1) / kSegNnz;
     if (nseg > 1) {
+      if (nseg > kCombineWide) wide.push_back((int32_t)mrow.size());
       mrow.push_back((int32_t)r);
       mslot0.push_back(n_slots);
       mnseg.push_back(nseg);
@@ -214,6 +265,7 @@ int build_spmm_plan(const int32_t *d_rowptr, int64_t n_rows, SpmmPlan *out, cons
   SpmmPlan p;
   p.n_seg = (int)srow.size();
   p.n_multi = (int)mrow.size();
+  p.n_wide = (int)wide.size();
   auto up = [&](const std::vector<int32_t> &v, int32_t **dst) -> int {
     MACR_CUDA(cudaMalloc(dst, sizeof(int32_t) * (v.size() + 1)));
     MACR_CUDA(cudaMemcpy(*dst, v.data(), sizeof(int32_t) * v.size(), cudaMemcpyHostToDevice));
@@ -222,7 +274,8 @@ int build_spmm_plan(const int32_t *d_rowptr, int64_t n_rows, SpmmPlan *out, cons
   int rc;
   if ((rc = up(srow, &p.seg_row)) || (rc = up(sstart, &p.seg_start)) || (rc = up(send, &p.seg_end)) ||
       (rc = up(sslot, &p.seg_slot)) || (rc = up(mrow, &p.multi_row)) ||
-      (rc = up(mslot0, &p.multi_slot0)) || (rc = up(mnseg, &p.multi_nseg)))
+      (rc = up(mslot0, &p.multi_slot0)) || (rc = up(mnseg, &p.multi_nseg)) ||
+      (rc = up(wide, &p.wide_idx)))
     return rc;
   MACR_CUDA(cudaMalloc(&p.partial, sizeof(float) * kD * ((size_t)n_slots + 1)));
   *out = p;
@@ -232,6 +285,7 @@ int build_spmm_plan(const int32_t *d_rowptr, int64_t n_rows, SpmmPlan *out, cons
 void free_spmm_plan(SpmmPlan *p) {
   cudaFree(p->seg_row), cudaFree(p->seg_start), cudaFree(p->seg_end), cudaFree(p->seg_slot);
   cudaFree(p->multi_row), cudaFree(p->multi_slot0), cudaFree(p->multi_nseg), cudaFree(p->partial);
+  cudaFree(p->wide_idx);
   *p = SpmmPlan();
 }
 
@@ -249,6 +303,13 @@ int launch_spmm_planned(const SpmmPlan *plan, const int32_t *rowptr, const int32
     spmm_combine_kernel<<<(unsigned)(((long long)plan->n_multi * 16 + 255) / 256), 256, 0, s>>>(
         plan->multi_row, plan->multi_slot0, plan->multi_nseg, plan->n_multi, plan->partial, add, Y,
         acc_in, acc_out, acc_div);
+    MACR_LAUNCH_CHECK();
+  }
+  if (plan->n_wide) {
+    spmm_combine_wide_kernel<<<plan->n_wide, 256, 0, s>>>(plan->wide_idx, plan->multi_row,
+                                                          plan->multi_slot0, plan->multi_nseg,
+                                                          plan->partial, add, Y, acc_in, acc_out,
+                                                          acc_div);
     MACR_LAUNCH_CHECK();
   }
   return MACR_OK;

@@ -17,9 +17,10 @@ struct RowSrc {
 // Rows of one segment are finished in place; the others go through `partial` and a fixed-order
 // combine pass (deterministic).
 struct SpmmPlan {
-  int n_seg = 0, n_multi = 0;
+  int n_seg = 0, n_multi = 0, n_wide = 0;
   int32_t *seg_row = nullptr, *seg_start = nullptr, *seg_end = nullptr, *seg_slot = nullptr;
   int32_t *multi_row = nullptr, *multi_slot0 = nullptr, *multi_nseg = nullptr;
+  int32_t *wide_idx = nullptr;  // multi rows of more than kCombineWide segments: one CTA each
   float *partial = nullptr;  // [sum of segments of multi-segment rows][64]
 };
 // ranges (nullable): {a0, a1, b0, b1} -- only rows in [a0,a1) or [b0,b1) get segments (the rows a

@@ -15,7 +15,8 @@ struct StepState {
   float *loss_base;         // [n_steps][4]
   long long step_idx;       // index into ids_base / loss_base for the step being executed
   long long t;              // Adam steps applied so far
-  const int32_t *cur_ids;   // ids_base + step_idx*3*B
+  const int32_t *gids_base; // row-partitioned MF: the GLOBAL ids [n_steps][3][B]; ids_base then
+                            // points at the renumbered (local) copy the exchange kernel fills
   float *cur_loss;          // loss_base + step_idx*4
 };
 

@@ -19,9 +19,11 @@
 
 namespace macr {
 
-__global__ void set_io_kernel(StepState *st, const int32_t *ids_base, float *loss_base) {
+__global__ void set_io_kernel(StepState *st, const int32_t *ids_base, float *loss_base,
+                              const int32_t *gids_base) {
   if (threadIdx.x == 0 && blockIdx.x == 0) {
     st->ids_base = ids_base;
+    st->gids_base = gids_base;
     st->loss_base = loss_base;
     st->step_idx = 0;
   }
@@ -131,6 +133,7 @@ struct TrainerBase {
     cudaFree(plan_mem); cudaFree(snap); cudaFree(tail_ticket); cudaFree(unit_part); cudaFree(gU); cudaFree(gI); cudaFree(gw_part); cudaFree(gwu_part);
     cudaFreeHost(pinned_losses);
     cudaFree(epoch_ids); cudaFree(epoch_losses); cudaFreeHost(epoch_losses_pinned);
+    cudaFree(local_ids);
     cudaEventDestroy(ev_fork); cudaEventDestroy(ev_join);
     cudaEventDestroy(ev_join2);
     cudaStreamDestroy(side);
@@ -138,8 +141,28 @@ struct TrainerBase {
     cudaStreamDestroy(cs);
   }
 
-  int set_io(const int32_t *ids_base, float *loss_base) {
-    set_io_kernel<<<1, 1, 0, s>>>(st, ids_base, loss_base);
+  // row-partitioned MF (macr_mf_trainer_shard): the caller's ids are GLOBAL; the step graph's
+  // exchange kernel renumbers each step's ids into this buffer, which the other kernels read
+  bool renumber_ids = false;
+  int32_t *local_ids = nullptr;
+  size_t local_ids_cap = 0;
+
+  int set_io(const int32_t *ids_base, float *loss_base, int n_steps, int B) {
+    const int32_t *gids = nullptr;
+    if (renumber_ids) {
+      const size_t need = (size_t)n_steps * 3 * (size_t)B;
+      if (need > local_ids_cap) {
+        MACR_CUDA(cudaStreamSynchronize(s));
+        cudaFree(local_ids);
+        local_ids = nullptr;
+        local_ids_cap = 0;
+        MACR_CUDA(cudaMalloc(&local_ids, sizeof(int32_t) * need));
+        local_ids_cap = need;
+      }
+      gids = ids_base;
+      ids_base = local_ids;
+    }
+    set_io_kernel<<<1, 1, 0, s>>>(st, ids_base, loss_base, gids);
     MACR_LAUNCH_CHECK();
     cur_ids_base = ids_base;
     cur_loss_base = loss_base;
@@ -168,6 +191,13 @@ struct macr_mf_trainer : macr::TrainerBase {
   uint32_t *bmU, *bmI;
   int launches;
   int mode = MACR_TRAIN_RUBIBCEBOTH;
+  // row-partitioned mode (macr_mf_trainer_shard): U / I are this rank's local tables (owned rows +
+  // ghost rows, csrc/shard.cu); the exchange of the batch's rows runs inside the step graph
+  bool sharded = false;
+  macr_shard_desc sd{};
+  macr::PeerGhosts ghosts{};
+  macr::PeerFlagsDev peerF{};
+  unsigned long long *flags = nullptr;  // [0..15] arrival flags, [16] barrier epoch, [17] error (int)
 };
 
 namespace macr {
@@ -181,6 +211,13 @@ static int mf_enqueue(macr_mf_trainer *h, int B) {
   GridWs g = grid_ws_layout(B, h->gridws);
   g.item_gate_only = h->mode == MACR_TRAIN_RUBIBCE;
   int rc;
+  if (h->sharded) {
+    // renumber this step's ids and store every owned row into the peers' ghost slots; the plan and
+    // the sweep need the renumbered ids only, so the flag barrier (peers' rows have landed) sits on
+    // the main branch alone and the HBM-bound sweep never waits for a peer
+    rc = launch_shard_push_st(h->U, h->I, h->sd, h->st, B, h->ghosts, s);
+    if (rc) return rc;
+  }
   // fork: the plan (2 CTAs) and the dense sweep need only the ids and the step state
   MACR_CUDA(cudaEventRecord(h->ev_fork, s));
   MACR_CUDA(cudaStreamWaitEvent(side, h->ev_fork, 0));
@@ -191,11 +228,19 @@ static int mf_enqueue(macr_mf_trainer *h, int B) {
   MACR_CUDA(cudaEventRecord(h->ev_join, side));
   rc = launch_mark_touched(h->st, nullptr, B, h->bmU, h->bmI, side2);
   if (rc) return rc;
-  rc = launch_adam_sweep2(h->U, h->mU, h->vU, h->nu, h->bmU, h->I, h->mI, h->vI, h->ni, h->bmI,
+  // row-partitioned: the owned rows only -- peers store into the ghost rows while this runs
+  const int64_t sweep_u = h->sharded ? h->sd.u_hi - h->sd.u_lo : h->nu;
+  const int64_t sweep_i = h->sharded ? h->sd.i_hi - h->sd.i_lo : h->ni;
+  rc = launch_adam_sweep2(h->U, h->mU, h->vU, sweep_u, h->bmU, h->I, h->mI, h->vI, sweep_i, h->bmI,
                           hp.lr, h->st, hp.beta1, hp.beta2, hp.eps, side2);
   if (rc) return rc;
   MACR_CUDA(cudaEventRecord(h->ev_join2, side2));
   // main: gather (+ row snapshot) -> B x B grid (+ band folds) -> row gradients + Adam + tail
+  if (h->sharded) {
+    rc = launch_peer_barrier_dev(h->peerF, h->flags + 16, reinterpret_cast<int *>(h->flags + 17),
+                                 h->sd.rank, h->sd.world, s);
+    if (rc) return rc;
+  }
   rc = launch_gather_dots(h->U, h->I, h->U, h->I, h->w, h->wu, nullptr, nullptr, nullptr, h->st, B,
                           yp, yn, sp, sn, su, rq, h->snap, &g, s);
   if (rc) return rc;
@@ -216,7 +261,7 @@ static int mf_enqueue(macr_mf_trainer *h, int B) {
   rc = launch_row_grads(h->snap, h->w, h->wu, B, dyp, dyn, dsp, dsn, dsu, lam, h->planU, h->planI,
                         h->gU, h->gI, h->unit_part, h->gw_part, h->gwu_part, nullptr, &tabs, &tail, s);
   if (rc) return rc;
-  h->launches = 6;  // plan, mark, sweep | gather, grid, row-grads(+Adam+tail)
+  h->launches = h->sharded ? 8 : 6;  // [push, barrier |] plan, mark, sweep | gather, grid, row-grads(+Adam+tail)
   return MACR_OK;
 }
 
@@ -296,7 +341,7 @@ static int run_steps(H *h, std::map<int, cudaGraphExec_t> &cache, F enq, const i
   cudaGraphExec_t exec;
   int rc = get_graph(h, cache, B, enq, &exec);
   if (rc) return rc;
-  rc = h->set_io(batches, losses);
+  rc = h->set_io(batches, losses, n_steps, B);
   if (rc) return rc;
   for (int k = 0; k < n_steps; ++k) MACR_CUDA(cudaGraphLaunch(exec, h->s));
   return MACR_OK;
@@ -426,11 +471,66 @@ extern "C" int macr_mf_trainer_set_steps_done(macr_mf_trainer *h, int64_t t) {
   MACR_CHECK_ARG(h && t >= 0, "macr_mf_trainer_set_steps_done: bad argument");
   return h->set_steps(t);
 }
+// ---- row-partitioned mode -------------------------------------------------------------------
+extern "C" int macr_mf_trainer_ipc_export(macr_mf_trainer *h,
+                                          unsigned char handle[MACR_IPC_HANDLE_BYTES]) {
+  MACR_CHECK_ARG(h && handle, "macr_mf_trainer_ipc_export: null argument");
+  if (!h->flags) {
+    MACR_CUDA(cudaMalloc(&h->flags, sizeof(unsigned long long) * 32));
+    MACR_CUDA(cudaMemset(h->flags, 0, sizeof(unsigned long long) * 32));
+  }
+  cudaIpcMemHandle_t ih;
+  MACR_CUDA(cudaIpcGetMemHandle(&ih, h->flags));
+  memcpy(handle, &ih, sizeof(ih));
+  return MACR_OK;
+}
+
+extern "C" int macr_mf_trainer_shard(macr_mf_trainer *h, const macr_shard_desc *desc,
+                                     float *const *peer_U_ghost, float *const *peer_I_ghost,
+                                     uint64_t *const *peer_flags) {
+  MACR_CHECK_ARG(h && desc, "macr_mf_trainer_shard: null argument");
+  MACR_CHECK_ARG(desc->world >= 1 && desc->world <= kMaxRanks && desc->rank >= 0 &&
+                     desc->rank < desc->world,
+                 "macr_mf_trainer_shard: rank %d / world %d", desc->rank, desc->world);
+  MACR_CHECK_ARG(desc->max_batch == h->maxB, "macr_mf_trainer_shard: max_batch %d != trainer's %d",
+                 desc->max_batch, h->maxB);
+  MACR_CHECK_ARG(h->nu == (desc->u_hi - desc->u_lo) + 2LL * h->maxB &&
+                     h->ni == (desc->i_hi - desc->i_lo) + 4LL * h->maxB,
+                 "macr_mf_trainer_shard: the local tables must hold the owned rows + 2 x max_batch "
+                 "(users) / 4 x max_batch (items) ghost rows");
+  MACR_CHECK_ARG(h->steps_done == 0 && h->graphs.empty(), "macr_mf_trainer_shard: call it before the first step");
+  MACR_CHECK_ARG(h->flags, "macr_mf_trainer_shard: call macr_mf_trainer_ipc_export first");
+  for (int r = 0; r < desc->world; ++r) {
+    if (r == desc->rank) continue;
+    MACR_CHECK_ARG(peer_U_ghost && peer_I_ghost && peer_flags && peer_U_ghost[r] && peer_I_ghost[r] &&
+                       peer_flags[r],
+                   "macr_mf_trainer_shard: null peer pointer (rank %d)", r);
+    h->ghosts.u[r] = peer_U_ghost[r];
+    h->ghosts.i[r] = peer_I_ghost[r];
+    h->peerF.p[r] = reinterpret_cast<unsigned long long *>(peer_flags[r]);
+  }
+  h->peerF.p[desc->rank] = h->flags;
+  h->sd = *desc;
+  h->sharded = true;
+  h->renumber_ids = true;
+  return MACR_OK;
+}
+
+extern "C" int macr_mf_trainer_peer_error(macr_mf_trainer *h, int *err_out) {
+  MACR_CHECK_ARG(h && err_out, "macr_mf_trainer_peer_error: null argument");
+  *err_out = 0;
+  if (!h->flags) return MACR_OK;
+  MACR_CUDA(cudaStreamSynchronize(h->s));
+  MACR_CUDA(cudaMemcpy(err_out, h->flags + 17, sizeof(int), cudaMemcpyDeviceToHost));
+  return MACR_OK;
+}
+
 extern "C" int macr_mf_trainer_destroy(macr_mf_trainer *h) {
   if (!h) return MACR_OK;
   cudaStreamSynchronize(h->s);
   cudaStreamSynchronize(h->side);
   h->free_common();
+  cudaFree(h->flags);
   cudaFree(h->bmU);
   cudaFree(h->bmI);
   delete h;

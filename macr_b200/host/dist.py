@@ -67,8 +67,32 @@ class ShardedScorer:
                                       item_id_offset=self.lo)
         if self.world == 1:
             return ids, sc
-        gi, gs = all_gather_candidates(ids, sc, self.group)
-        return self.ops.topk_merge(gi, gs)
+        return merge_shard_candidates(self.ops, ids, sc, self.world, self.group)
+
+
+def merge_shard_candidates(ops, ids, scores, world, group=None):
+    """Per-shard top-K lists `[T,K]` (ids, scores) -> the global `[T,K]` on every rank.
+
+    Row blocks, not replicas: rank j merges rows `[j*Tb, (j+1)*Tb)` only.  One all-to-all hands it
+    those rows of every shard's candidates (`T*K*8/G` bytes from each peer instead of the whole
+    `T*K*8`), the on-device K-way merge (`macr_topk_merge`) runs on `Tb = ceil(T/G)` rows, and one
+    all-gather of the merged blocks assembles the result -- `2*T*K*8` bytes received per rank
+    instead of `G*T*K*8`, and 1/G of the merge work."""
+    T, K = ids.shape
+    Tb = (T + world - 1) // world
+    both = torch.empty((world * Tb, 2 * K), dtype=torch.int32, device=ids.device)
+    both[:T, :K] = ids
+    both[:T, K:] = scores.view(torch.int32)
+    if world * Tb > T:  # padding rows: empty lists
+        both[T:, :K] = -1
+        both[T:, K:] = torch.tensor(float("-inf"), dtype=torch.float32, device=ids.device).view(torch.int32)
+    mine = torch.empty_like(both)  # [G, Tb, 2K]: block j = shard j's candidates for my rows
+    dist.all_to_all_single(mine, both, group=group)
+    mine = mine.view(world, Tb, 2 * K)
+    mi, ms = ops.topk_merge(mine[:, :, :K].contiguous(), mine[:, :, K:].contiguous().view(torch.float32))
+    out = torch.empty((world * Tb, 2 * K), dtype=torch.int32, device=ids.device)
+    dist.all_gather_into_tensor(out, torch.cat([mi, ms.view(torch.int32)], dim=1), group=group)
+    return out[:T, :K].contiguous(), out[:T, K:].contiguous().view(torch.float32)
 
 
 def user_shard_bounds(n_rows, world):
@@ -135,10 +159,12 @@ class RowShardedMFTrainer:
     owned rows every local table carries ghost rows (two parities, csrc/shard.cu); batch position
     b of the user / pos / neg column lives in ghost b / b / B+b.  Two transports for the exchange:
 
-    * ``push`` (one rank per GPU, NVLink): ONE kernel renumbers the ids (owned -> `id - lo`,
-      foreign -> ghost slot) and stores every owned row straight into the ghost slot of every
-      peer's table through CUDA-IPC mapped peer memory, then a one-warp flag barrier over peer
-      memory -- gather and all-gather fused, no staging buffer, no reduction.
+    * ``push`` (one rank per GPU, NVLink): INSIDE the captured step graph ONE kernel renumbers
+      the ids (owned -> `id - lo`, foreign -> ghost slot) and stores every owned row straight
+      into the ghost slot of every peer's table through CUDA-IPC mapped peer memory -- gather and
+      all-gather fused, no staging buffer, no reduction.  The dense sweep of the owned rows starts
+      at once; a one-warp flag barrier over peer memory sits on the gather branch only, so the
+      HBM-bound part of the step never waits for a peer and an epoch is n graph replays.
     * ``allreduce``: `macr_shard_pack` writes the owned rows (zeros elsewhere) into `ex[3B,64]`,
       ONE all-reduce (sum; exactly one owner per row, so the sum is exact) hands every rank all 3B
       rows, `macr_shard_unpack` copies them into the ghost slots.  NCCL, or gloo for the tests.
@@ -194,9 +220,7 @@ class RowShardedMFTrainer:
         import ctypes as C
 
         ops = self.ops
-        self._ipc_flags = ops.IpcBuffer(8 * 16, self.dev)
-        self._err = torch.zeros(1, dtype=torch.int32, device=self.dev)
-        mine = (self._ipc_u.handle, self._ipc_i.handle, self._ipc_flags.handle, self.n_lu, self.n_li)
+        mine = (self._ipc_u.handle, self._ipc_i.handle, self.trainer.ipc_export(), self.n_lu, self.n_li)
         every = [None] * self.world
         dist.all_gather_object(every, mine, group=self.group)
         pu, pi, pf = ((C.c_void_p * self.world)() for _ in range(3))
@@ -204,7 +228,6 @@ class RowShardedMFTrainer:
         try:
             for r, (hu, hi, hf, n_lu, n_li) in enumerate(every):
                 if r == self.rank:
-                    pu[r], pi[r], pf[r] = None, None, self._ipc_flags.ptr
                     continue
                 bu, bi, bf = (ops.IpcBuffer.open_peer(h) for h in (hu, hi, hf))
                 self._peers += [bu, bi, bf]
@@ -216,7 +239,7 @@ class RowShardedMFTrainer:
         flag = torch.tensor([ok], dtype=torch.int32, device=self.dev)
         dist.all_reduce(flag, op=dist.ReduceOp.MIN, group=self.group)  # every rank mapped every peer?
         if int(flag.item()) == 1:
-            self._peer_u, self._peer_i, self._peer_f = pu, pi, pf
+            self.trainer.shard(self.desc, pu, pi, pf)  # the exchange now runs inside the step graph
             self.exchange = "push"
         torch.cuda.synchronize(self.dev)
         dist.barrier(group=self.group)  # flags are zeroed and mapped everywhere before the first push
@@ -224,21 +247,17 @@ class RowShardedMFTrainer:
     def check_peers(self):
         """Raise if a flag barrier timed out (a peer died); synchronises."""
         if self.exchange == "push":
-            e = int(self._err.item())
+            e = self.trainer.peer_error()
             if e:
                 raise self.ops.MacrError(f"rank {self.rank}: peer {e - 1} never reached the exchange barrier")
 
     # ---- one step -----------------------------------------------------------------------------
     def exchange_rows(self, ids3, B):
-        """ids3: int32 device tensor [3B] = users | pos | neg, GLOBAL ids, identical on every rank.
-        Leaves the renumbered ids in `self._local3[:3B]` and every foreign row in its ghost slot."""
+        """all-reduce transport: ids3 = int32 device tensor [3B] = users | pos | neg, GLOBAL ids,
+        identical on every rank.  Leaves the renumbered ids in `self._local3[:3B]` and every foreign
+        row in its ghost slot.  (Push transport: the captured step does all of this itself.)"""
         ops, t, par = self.ops, self.trainer.tab, self._step & 1
         self._step += 1
-        if self.exchange == "push":
-            ops.shard_push(t.U, t.I, self.desc, ids3, B, par, self._local3, self._peer_u, self._peer_i)
-            self._epoch += 1
-            ops.shard_barrier(self._peer_f, self.rank, self.world, self._epoch, self._err)
-            return
         ex = self._ex[: 3 * B]
         ops.shard_pack(t.U, t.I, self.desc, ids3, B, par, self._local3, ex)
         if self.world > 1:  # every row has exactly one owner: x + 0 + ... is exact
@@ -253,6 +272,10 @@ class RowShardedMFTrainer:
     def step_ids3(self, ids3, B, loss_out=None):
         """One training step on the [3B] global ids.  Returns the device tensor [loss, mf, reg,
         L_ori] (identical on every rank), written to `loss_out` ([1,4] device) if given; no sync."""
+        if self.exchange == "push":  # renumbering, peer stores and barrier are part of the step graph
+            if loss_out is not None:
+                return self.trainer.run(ids3[: 3 * B].view(1, 3, B), loss_out)
+            return self.trainer.step_device(ids3[:B], ids3[B:2 * B], ids3[2 * B:3 * B])
         self.exchange_rows(ids3, B)
         l3 = self._local3
         if loss_out is not None:
@@ -263,11 +286,25 @@ class RowShardedMFTrainer:
         """users / pos / neg: int32 device tensors [B] of GLOBAL ids, identical on every rank."""
         return self.step_ids3(torch.cat([users, pos, neg]), users.numel())
 
+    def run(self, batches, losses=None):
+        """Epoch mode: int32 device [n,3,B] GLOBAL ids -> device losses [n,4].  Push transport: n
+        replays of one captured graph, no host work between the steps."""
+        n, three, B = batches.shape
+        if losses is None:
+            losses = torch.empty((n, 4), dtype=torch.float32, device=self.dev)
+        if self.exchange == "push":
+            return self.trainer.run(batches, losses)
+        for s in range(n):
+            self.step_ids3(batches[s].reshape(-1), B, losses[s:s + 1])
+        return losses
+
     def run_host(self, batches_host, losses_host=None):
         """Epoch call with HOST buffers: `batches_host` int32 [n,3,B] (pinned recommended, identical
         on every rank) -> float32 [n,4] host losses; one H2D, n exchanges + steps, one D2H, one sync."""
         n, three, B = batches_host.shape
         assert three == 3 and batches_host.dtype == torch.int32 and not batches_host.is_cuda
+        if self.exchange == "push":  # macr_mf_trainer_run_host: the whole epoch behind one C call
+            return self.trainer.run_host(batches_host, losses_host)
         if self._epoch_ids is None or self._epoch_ids.shape[0] < n or self._epoch_ids.shape[2] != B:
             self._epoch_ids = torch.empty((n, 3, B), dtype=torch.int32, device=self.dev)
             self._epoch_losses = torch.empty((n, 4), dtype=torch.float32, device=self.dev)
@@ -300,9 +337,19 @@ class RowShardedMFTrainer:
         for p in self._peers:
             self.ops.IpcBuffer.close_peer(p)
         self._peers = []
-        for buf in (self._ipc_u, self._ipc_i, getattr(self, "_ipc_flags", None)):
+        for buf in (self._ipc_u, self._ipc_i):
             if buf is not None:
                 buf.free()
+
+
+def balanced_bounds(weights, world):
+    """Contiguous ranges of ~equal total weight: rank r owns [b[r], b[r+1]).  A Zipf catalogue sorted
+    by id puts most nonzeros into the first item rows; equal row counts would leave rank 0 with
+    half of the SpMM work."""
+    c = np.concatenate([[0], np.cumsum(np.asarray(weights, np.int64))])
+    b = np.searchsorted(c, c[-1] * np.arange(world + 1) / world, side="left").astype(np.int64)
+    b[0], b[-1] = 0, len(weights)
+    return np.maximum.accumulate(b)
 
 
 def partition_adjacency(rowptr, col, val, n_users, u_lo, u_hi, i_lo, i_hi):
@@ -346,7 +393,10 @@ class RowShardedLGCNTrainer:
         self.rank = dist.get_rank(group) if rank is None else rank
         self.world = dist.get_world_size(group) if world is None else world
         self.n_users, self.n_items = U.shape[0], I.shape[0]
-        ub, ib = user_shard_bounds(self.n_users, self.world), item_shard_bounds(self.n_items, self.world)
+        # owned ranges balanced by work: a row costs its nonzeros (256-byte gathers) + ~8 (Adam, epilogue)
+        deg = np.diff(np.asarray(rowptr, np.int64))
+        ub = balanced_bounds(deg[: self.n_users] + 8, self.world)
+        ib = balanced_bounds(deg[self.n_users:] + 8, self.world)
         self.u_lo, self.u_hi = int(ub[self.rank]), int(ub[self.rank + 1])
         self.i_lo, self.i_hi = int(ib[self.rank]), int(ib[self.rank + 1])
         self.dev = torch.device(device)

@@ -354,6 +354,24 @@ class MFTrainer:
                              C.c_void_p(losses_host.data_ptr())), "trainer_run_host")
         return losses_host
 
+    # ---- row-partitioned mode (include/macr_b200.h: macr_mf_trainer_shard) ----
+    def ipc_export(self):
+        """IPC handle (64 bytes) of the trainer's barrier flags."""
+        buf = C.create_string_buffer(64)
+        check(lib().macr_mf_trainer_ipc_export(self._h, buf), "macr_mf_trainer_ipc_export")
+        return buf.raw
+
+    def shard(self, desc, peer_u_ghost, peer_i_ghost, peer_flags):
+        """peer_*: ctypes arrays (c_void_p * world): every peer's ghost bases / flags mapped here.
+        From now on step / run / run_host take GLOBAL ids (identical on every rank)."""
+        check(lib().macr_mf_trainer_shard(self._h, C.byref(desc), peer_u_ghost, peer_i_ghost, peer_flags),
+              "macr_mf_trainer_shard")
+
+    def peer_error(self):
+        out = C.c_int(0)
+        check(lib().macr_mf_trainer_peer_error(self._h, C.byref(out)), "macr_mf_trainer_peer_error")
+        return out.value
+
     @property
     def launches_per_step(self):
         return int(lib().macr_mf_trainer_launches_per_step(self._h))

@@ -49,6 +49,16 @@ def _worker(rank, world, port, out_dir):
         want_i, want_s = oracle.score_topk(Uq, I, oracle.score_gates(I, w), sig_u, 40.0, mrp, mcol, K)
         np.testing.assert_array_equal(mi, want_i)
         np.testing.assert_array_equal(ms, want_s)
+        # the product's exchange: all-to-all of row blocks, block merge, all-gather (odd T: one padding row)
+        class _MergeOps:
+            @staticmethod
+            def topk_merge(gi_, gs_):
+                a, b_ = oracle.topk_merge(gi_.numpy().copy(), gs_.numpy().copy())
+                return torch.from_numpy(a), torch.from_numpy(b_)
+
+        bi, bs = mdist.merge_shard_candidates(_MergeOps, torch.from_numpy(ids), torch.from_numpy(sc), world)
+        np.testing.assert_array_equal(bi.numpy(), want_i)
+        np.testing.assert_array_equal(bs.numpy(), want_s)
         # user-partitioned layout: ragged row slices -> the full [T,K] result on every rank
         ub = mdist.user_shard_bounds(T, world)
         ulo, uhi = int(ub[rank]), int(ub[rank + 1])
@@ -228,3 +238,15 @@ def test_partition_adjacency_rows_cover_the_graph_exactly_once():
         np.testing.assert_array_equal(part[own].toarray(), A[own].toarray())
         total = total + part
     np.testing.assert_array_equal(total.toarray(), A.toarray())
+
+
+def test_balanced_bounds_split_weight_not_rows():
+    from macr_b200.host import dist as mdist
+
+    w = np.array([1000, 10, 10, 10, 500, 1, 1, 1, 1, 466], np.int64)  # total 2000
+    b = mdist.balanced_bounds(w, 4)
+    assert b[0] == 0 and b[-1] == len(w) and np.all(np.diff(b) >= 0)
+    loads = [int(w[b[r]:b[r + 1]].sum()) for r in range(4)]
+    assert sum(loads) == 2000 and max(loads) <= 1000  # the heavy head row sits alone
+    assert list(mdist.balanced_bounds(np.ones(12, np.int64), 3)) == [0, 4, 8, 12]
+    assert list(mdist.balanced_bounds(np.ones(5, np.int64), 1)) == [0, 5]
