@@ -4,6 +4,7 @@ lines.  `--train rubibceboth` (MACR, with `--test rubi` or `--test normal`) and 
 (the README's baseline command, `--test normal`) are implemented; the other --train modes of the
 reference are outside the MACR hot path and fail loudly."""
 import logging
+from concurrent.futures import ThreadPoolExecutor
 import os
 import random
 import sys
@@ -83,11 +84,24 @@ def main(argv=None, tune=False):
     config.update(best_hr=0, best_ndcg=0, best_recall=0, best_pre=0, best_epoch=0,
                   best_c_hr=0, best_c_epoch=0, best_c=0.0)
     stopping_step, ret = 0, None
+    n_batch = data.n_train // args.batch_size + 1
+    stepwise = os.environ.get("MACR_STEPWISE") == "1"
+    # The sampler draws from its own RNG stream only, so epoch k+1 can be sampled (native code, GIL
+    # released) on a worker thread while epoch k trains and evaluates: same triples in the same
+    # order as the serial loop.  The RNG state a checkpoint of epoch k must carry is the one right
+    # after epoch k's draws, captured by the worker.
+    sampler_pool = None if stepwise else ThreadPoolExecutor(max_workers=1)
+
+    def sample_job():
+        b = data.sample_epoch(n_batch)
+        return b, (random.getstate(), np.random.get_state())
+
+    pending = None if stepwise else sampler_pool.submit(sample_job)
+    rng_after = None
     for epoch in range(args.epoch):
         t1 = time()
         loss, mf_loss, reg_loss = 0.0, 0.0, 0.0
-        n_batch = data.n_train // args.batch_size + 1
-        if os.environ.get("MACR_STEPWISE") == "1":  # the literal loop of train.py:470-499
+        if stepwise:  # the literal loop of train.py:470-499
             for _ in range(n_batch):
                 users, pos_items, neg_items = data.sample()
                 _, batch_loss, batch_mf_loss, batch_reg_loss = sess.run(
@@ -99,7 +113,9 @@ def main(argv=None, tune=False):
         else:
             # same triples (the sampler consumes only its own RNG stream), same steps, same sums:
             # the epoch is sampled natively, staged once and run as one call
-            for bl in model.train_epoch(data.sample_epoch(n_batch)):
+            batches, rng_after = pending.result()
+            pending = sampler_pool.submit(sample_job) if epoch + 1 < args.epoch else None
+            for bl in model.train_epoch(batches):
                 loss += float(bl[0]) / n_batch
                 mf_loss += float(bl[1]) / n_batch
                 reg_loss += float(bl[2]) / n_batch
@@ -164,7 +180,7 @@ def main(argv=None, tune=False):
             stopping_step)
         if args.save_flag == 1:
             checkpoint.save(os.path.join(ckpt_dir(args), "{}_ckpt.npz".format(epoch)), model,
-                            {"epoch": epoch})
+                            {"epoch": epoch}, rng_state=rng_after)
         if should_stop and args.early_stop == 1:
             msg = "{} dataset best epoch{}: hr:{} ndcg:{} recall:{} precision:{}".format(
                 args.dataset, config["best_epoch"], config["best_hr"], config["best_ndcg"],
@@ -178,6 +194,10 @@ def main(argv=None, tune=False):
                     with open(os.path.join(ckpt_dir(args), "best_c.txt"), "w") as f:
                         print(config["best_c"], file=f)
             break
+    if pending is not None:  # early stop: let the speculative draw of the next epoch finish
+        pending.result()
+    if sampler_pool is not None:
+        sampler_pool.shutdown()
     model.close()
     return config
 

@@ -8,12 +8,14 @@ import random
 import numpy as np
 
 
-def _rng_arrays():
+def _rng_arrays(rng_state=None):
     """Both host RNG states as plain arrays (no pickle in either direction): CPython's
     `random` state is (version, 625 ints = MT19937 key + position, gauss_next); numpy's legacy
-    state is ('MT19937', uint32[624], pos, has_gauss, cached_gaussian)."""
-    ver, key, gauss = random.getstate()
-    name, npkey, pos, has_gauss, cached = np.random.get_state()
+    state is ('MT19937', uint32[624], pos, has_gauss, cached_gaussian).  rng_state: an explicit
+    (random.getstate(), np.random.get_state()) pair instead of the interpreter's current one (a
+    sampler that runs ahead on a worker thread hands in the states as of the epoch being saved)."""
+    ver, key, gauss = rng_state[0] if rng_state else random.getstate()
+    name, npkey, pos, has_gauss, cached = rng_state[1] if rng_state else np.random.get_state()
     if name != "MT19937":
         raise ValueError(f"unsupported numpy bit generator {name!r}")
     return {"py_random_version": np.asarray(ver, np.int64),
@@ -36,10 +38,10 @@ def _restore_rng(z):
                          float(z["np_random_cached"])))
 
 
-def save(path, model, extra=None):
+def save(path, model, extra=None, rng_state=None):
     os.makedirs(os.path.dirname(os.path.abspath(path)), exist_ok=True)
     sd = model.state_dict()
-    sd.update(_rng_arrays())
+    sd.update(_rng_arrays(rng_state))
     for k, v in (extra or {}).items():
         sd["extra_" + k] = np.asarray(v)
     tmp = path + ".tmp.npz"

@@ -209,6 +209,36 @@ def test_eval_score_matrix_foldout_drop_in_matches_reference_golden():
         eval_score_matrix_foldout(g["scores"], truth[:-1])
 
 
+def test_mf_cli_pipelined_sampler_equals_the_stepwise_loop(tmp_path, monkeypatch, capsys):
+    """The MF CLI samples epoch k+1 on a worker thread while epoch k trains: the run must be the
+    literal `data.sample()` / `sess.run` loop of train.py:470-499 (MACR_STEPWISE=1), and a
+    checkpoint of epoch k must carry the sampler stream as of the end of epoch k's draws."""
+    from macr_b200.cli import train_mf
+    from macr_b200.host.data_mf import Data
+
+    monkeypatch.chdir(tmp_path)
+    argv = ["--data_path", GOLD + "/", "--dataset", "tiny", "--batch_size", "32", "--epoch", "4", "--log_interval", "2",
+            "--train", "rubibceboth", "--test", "rubi", "--c", "2", "--lr", "0.01"]
+    a = train_mf.main(argv + ["--saveID", "pipe"])
+    out_a = [l for l in capsys.readouterr().out.splitlines() if "train==" in l]
+    monkeypatch.setenv("MACR_STEPWISE", "1")
+    b = train_mf.main(argv + ["--saveID", "step", "--save_flag", "0"])
+    out_b = [l for l in capsys.readouterr().out.splitlines() if "train==" in l]
+    monkeypatch.delenv("MACR_STEPWISE")
+    strip = lambda l: l.split("]: ", 1)[1]  # drop the wall-clock prefix
+    assert [strip(l) for l in out_a] == [strip(l) for l in out_b] and len(out_a) >= 2
+    assert {k: a[k] for k in ("best_hr", "best_ndcg", "best_recall", "best_epoch")} == \
+           {k: b[k] for k in ("best_hr", "best_ndcg", "best_recall", "best_epoch")}
+    # the checkpoint written after epoch index 1 holds the stream position after 2 epochs of draws,
+    # although the worker had already sampled the third epoch when it was written
+    z = np.load("mf_tiny_checkpoint/wd_1e-05_lr_0.01_pipe/1_ckpt.npz")
+    args = mf_args()
+    data = Data(args)
+    random.seed(12345)
+    data.sample_epoch(2 * (data.n_train // 32 + 1))
+    np.testing.assert_array_equal(z["py_random_key"], np.asarray(random.getstate()[1], np.uint32))
+
+
 def test_cli_drivers_run_end_to_end(tmp_path, monkeypatch, capsys):
     from macr_b200.cli import lightgcn, train_mf
 
