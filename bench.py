@@ -436,7 +436,8 @@ def sharded_train(cx, K, W):
     # end to end with host buffers: pinned ids -> H2D, K exchanges + steps, D2H of the losses, sync
     pin = torch.from_numpy(np.concatenate([batches_h] * ((K + nb - 1) // nb))[:K].copy()).pin_memory()
     host_losses = torch.empty((K, 4), dtype=torch.float32).pin_memory()
-    sh.run_host(pin[:min(K, 4)], host_losses[:min(K, 4)])  # warm-up (allocates the staging)
+    sh.run_host(pin, host_losses)  # warm-up at the full epoch length: every staging buffer reaches its size
+                                   # (a cudaMalloc with peer mappings inside the timed call costs tens of ms)
     cx.barrier()
     t0 = time.perf_counter()
     sh.run_host(pin, host_losses)

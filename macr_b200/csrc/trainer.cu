@@ -156,8 +156,9 @@ struct TrainerBase {
         cudaFree(local_ids);
         local_ids = nullptr;
         local_ids_cap = 0;
-        MACR_CUDA(cudaMalloc(&local_ids, sizeof(int32_t) * need));
-        local_ids_cap = need;
+        const size_t cap = need > 2 * local_ids_cap ? need : 2 * local_ids_cap;  // geometric growth
+        MACR_CUDA(cudaMalloc(&local_ids, sizeof(int32_t) * cap));
+        local_ids_cap = cap;
       }
       gids = ids_base;
       ids_base = local_ids;
