@@ -951,10 +951,16 @@ static Plan make_plan(int T, long long n_items, int K) {
   // of a pass; small catalogues keep enough sampled batches for tight group maxima
   p.stride = p.n_itiles >= 32 * kMaxStride ? kMaxStride : p.n_itiles >= 64 ? 2 : 1;
   p.n_stiles = (p.n_itiles + p.stride - 1) / p.stride;
-  // row block: group maxima + candidate lists at most ~1 GiB
-  long long tb = (1024LL << 20) / (4LL * 32 * kMaxChunksS + 8LL * kCap + 64);
+  // row blocks: group maxima + candidate lists at most ~2 GiB per block, and blocks of equal size
+  // (a short trailing block would leave most SMs idle for a whole pass over the catalogue)
+  long long tb = (2048LL << 20) / (4LL * 32 * kMaxChunksS + 8LL * kCap + 64);
   tb = tb / (UT * BM) * (UT * BM);
-  if (tb > T) tb = T;
+  if (tb >= T) {
+    tb = T;
+  } else {
+    const long long n_blocks = (T + tb - 1) / tb;
+    tb = ((T + n_blocks - 1) / n_blocks + UT * BM - 1) / (UT * BM) * (UT * BM);
+  }
   p.TB = (int)tb;
   const int utiles = (p.TB + UT * BM - 1) / (UT * BM);
   int nc_max = p.n_itiles / 2 < 16 ? p.n_itiles / 2 : 16;
