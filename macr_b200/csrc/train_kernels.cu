@@ -198,6 +198,42 @@ __device__ __forceinline__ void grid_pair(float ypj, float ynj, float agl, float
   }
 }
 
+// Four pairs of one row at once (unchecked, unmasked tiles): the four D = (1+eP)(1+eN) share ONE
+// reciprocal and ONE logarithm -- lg2(D0 D1 D2 D3) is the sum of the four logarithms and
+// 1/D_k = (product of the others) / (D0 D1 D2 D3) -- so a pair costs 2.5 MUFU operations instead
+// of 4 (2 ex2 + 1/4 rcp + 1/4 lg2) for nine extra multiplies per quad on the FMA pipe, which has
+// the slack (the kernel is bound by the 16-lane MUFU pipe).  Range: unchecked tiles have
+// eP <= e^6.2, eN <= e^5.5, so D <= 1.3e5 and the product of four <= 2.4e20: far inside fp32, and
+// its reciprocal is a normal number.  Each 1/D_k carries two more roundings (relative 1.2e-7).
+template <bool kGrad>
+__device__ __forceinline__ void grid_quad(const float *ypj, const float *ynj, float agl, float angl,
+                                          float &lgacc, float *colP, float *colN, float &rowP,
+                                          float &rowN) {
+  float DP[4], DN[4], D[4];
+#pragma unroll
+  for (int k = 0; k < 4; ++k) {
+    DP[k] = 1.0f + ex2_approx(ypj[k] * agl);
+    DN[k] = 1.0f + ex2_approx(ynj[k] * angl);
+    D[k] = DP[k] * DN[k];
+  }
+  const float p01 = D[0] * D[1], p23 = D[2] * D[3], p = p01 * p23;
+  lgacc -= lg2_approx(p);  // + xN, added per tile as a rank-1 sum
+  if (kGrad) {
+    const float inv = rcp_approx(p);
+    const float i01 = p23 * inv, i23 = p01 * inv;  // 1/(D0 D1), 1/(D2 D3)
+    const float rr[4] = {D[1] * i01, D[0] * i01, D[3] * i23, D[2] * i23};
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      const float dN = DP[k] * rr[k];
+      const float dP = fmaf(DN[k], rr[k], -1.0f);
+      colP[k] = fmaf(dP, agl, colP[k]);
+      colN[k] = fmaf(dN, angl, colN[k]);
+      rowP = fmaf(dP, ypj[k], rowP);
+      rowN = fmaf(dN, ynj[k], rowN);
+    }
+  }
+}
+
 // Band folds without any synchronisation cost in the tile CTAs: every partial-sum slot holds a
 // sentinel bit pattern (kPartEmpty, a NaN no arithmetic produces) until its tile CTA stores the
 // value -- a single 4-byte store, so a reader sees either the sentinel or the value.  One extra
@@ -251,7 +287,7 @@ __device__ __forceinline__ float take_partials(float *slot, int n, size_t stride
 // and of the per-position branch losses / L2 squares -> the step's loss scalars (model.py:217-221)
 __device__ void grid_fold_losses(int B, const GridWs &ws, const GridOut &out, double *sh) {
   const int tid = threadIdx.x;
-  const int nparts = ws.nblk_i * ws.nblk_j;
+  const int nparts = ws.nblk_i * ws.ngrp_j;
   // everything that does not depend on the tiles first: destination, per-position sums
   float *dst = out.losses3;
   if (out.st != nullptr) dst = out.st->loss_base + out.st->step_idx * 4;
@@ -322,7 +358,7 @@ __device__ void grid_fold_band(int f, int B, float alpha, float beta, const Grid
     for (int t = tid; t < 2 * TI; t += 256) {
       const int which = t / TI, row = t - which * TI;
       float *src = (which ? ws.rowN : ws.rowP) + i0 + row;
-      scratch[t] = take_partials(src, ws.nblk_j, Bpad);
+      scratch[t] = take_partials(src, ws.ngrp_j, Bpad);
     }
     __syncthreads();
     for (int t = tid; t < TI; t += 256) {
@@ -362,7 +398,6 @@ grid_bce_kernel(const float *__restrict__ yp, const float *__restrict__ yn, int 
   __shared__ float sRed[2][TMAX][17];
   __shared__ float sLoss[8];
   __shared__ float sMax[2][8];
-  __shared__ double sRank1;
 
   const int tid = threadIdx.x, tx = tid & 15, ty = tid >> 4;
   const int Bpad = ws.Bpad;
@@ -374,7 +409,9 @@ grid_bce_kernel(const float *__restrict__ yp, const float *__restrict__ yn, int 
       grid_fold_band<TI, TJ>(f - 1, B, alpha, beta, ws, out, &sRed[0][0][0]);
     return;
   }
-  const int i0 = blockIdx.y * TI, j0 = blockIdx.x * TJ;
+  const int i0 = blockIdx.y * TI;
+  const int jt_begin = blockIdx.x * ws.grp_tiles;
+  const int jt_end = min(ws.nblk_j, jt_begin + ws.grp_tiles);
   // gates sig(sp)*sig(su), sig(sn)*sig(su) of this row band, precomputed once per step by
   // gate_kernel / gather_dots
   for (int t = tid; t < TI; t += 256) {
@@ -384,15 +421,8 @@ grid_bce_kernel(const float *__restrict__ yp, const float *__restrict__ yn, int 
     sAg[t] = ok ? ws.gA[i] * g : 0.f;
     sAng[t] = ok ? ws.gAN[i] * g : 0.f;
   }
-  for (int t = tid; t < TJ; t += 256) {
-    const int j = j0 + t;
-    const bool ok = j < B;
-    sYp[t] = ok ? yp[j] : 0.f;
-    sYn[t] = ok ? yn[j] : 0.f;
-  }
   __syncthreads();
   float agl[RI], angl[RI], wr[RI];
-  float ypj[RJ], ynj[RJ], wc[RJ];
   float mg = 0.f, mgn = 0.f;
 #pragma unroll
   for (int r = 0; r < RI; ++r) {
@@ -404,73 +434,110 @@ grid_bce_kernel(const float *__restrict__ yp, const float *__restrict__ yn, int 
     angl[r] = -kLog2e * ang;
     wr[r] = (i0 + t < B) ? 1.f : 0.f;
   }
+  // largest gate of the band -> can a tile skip the per-pair range test?
 #pragma unroll
-  for (int c = 0; c < RJ; ++c) {
-    const int t = tx + 16 * c;
-    ypj[c] = sYp[t];
-    ynj[c] = sYn[t];
-    wc[c] = (j0 + t < B) ? 1.f : 0.f;
+  for (int o = 16; o > 0; o >>= 1) {
+    mg = fmaxf(mg, __shfl_xor_sync(0xffffffffu, mg, o));
+    mgn = fmaxf(mgn, __shfl_xor_sync(0xffffffffu, mgn, o));
   }
-
-  // largest gate of the band -> can the whole tile skip the per-pair range test?
-  {
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) {
-      mg = fmaxf(mg, __shfl_xor_sync(0xffffffffu, mg, o));
-      mgn = fmaxf(mgn, __shfl_xor_sync(0xffffffffu, mgn, o));
-    }
-    if ((tid & 31) == 0) {
-      sMax[0][tid >> 5] = mg;
-      sMax[1][tid >> 5] = mgn;
-    }
+  if ((tid & 31) == 0) {
+    sMax[0][tid >> 5] = mg;
+    sMax[1][tid >> 5] = mgn;
+  }
+  float sum_ang = 0.f;  // warp 0: sum_i ang_i of the band (rank-1 term of every tile)
+  if (tid < 32) {
+    for (int t = tid; t < TI; t += 32) sum_ang += sAng[t];
+    sum_ang = warp_sum(sum_ang);
   }
   __syncthreads();
-  bool in_range = true;
-  {
-    float mg = 0.f, mgn = 0.f;
+  mg = mgn = 0.f;
 #pragma unroll
-    for (int q = 0; q < 8; ++q) {
-      mg = fmaxf(mg, sMax[0][q]);
-      mgn = fmaxf(mgn, sMax[1][q]);
-    }
-    if (tid < TJ) in_range = fabsf(sYp[tid]) * mg <= 6.2f && fabsf(sYn[tid]) * mgn <= 5.5f;
-  }
-  const bool all_fast = __syncthreads_and(in_range);
-  if (tid < 32) {  // rank-1 term of the tile: sum_ij xN_ij = (sum_i -log2e*ang_i) * (sum_j yn_j)
-    float sa = 0.f, sy = 0.f;
-    for (int t = tid; t < TI; t += 32) sa += sAng[t];
-    for (int t = tid; t < TJ; t += 32) sy += sYn[t];
-    sa = warp_sum(sa);
-    sy = warp_sum(sy);
-    if (tid == 0) sRank1 = -(double)kLog2e * (double)sa * (double)sy;
+  for (int q = 0; q < 8; ++q) {
+    mg = fmaxf(mg, sMax[0][q]);
+    mgn = fmaxf(mgn, sMax[1][q]);
   }
 
-  float colP[RJ], colN[RJ], rowP[RI], rowN[RI];
-#pragma unroll
-  for (int c = 0; c < RJ; ++c) colP[c] = colN[c] = 0.f;
+  float rowP[RI], rowN[RI];
 #pragma unroll
   for (int r = 0; r < RI; ++r) rowP[r] = rowN[r] = 0.f;
   float lgacc = 0.f;  // sum of log2(.) terms; loss = -ln2 * sum
+  double rank1 = 0.0;  // thread 0: sum over the tiles of (sum_i -log2e*ang_i) * (sum_j yn_j)
 
-  if (all_fast) {
+  for (int jt = jt_begin; jt < jt_end; ++jt) {
+    const int j0 = jt * TJ;
+    for (int t = tid; t < TJ; t += 256) {
+      const int j = j0 + t;
+      const bool ok = j < B;
+      sYp[t] = ok ? yp[j] : 0.f;
+      sYn[t] = ok ? yn[j] : 0.f;
+    }
+    __syncthreads();
+    float ypj[RJ], ynj[RJ], wc[RJ];
 #pragma unroll
-    for (int r = 0; r < RI; ++r)
+    for (int c = 0; c < RJ; ++c) {
+      const int t = tx + 16 * c;
+      ypj[c] = sYp[t];
+      ynj[c] = sYn[t];
+      wc[c] = (j0 + t < B) ? 1.f : 0.f;
+    }
+    bool in_range = true;
+    if (tid < TJ) in_range = fabsf(sYp[tid]) * mg <= 6.2f && fabsf(sYn[tid]) * mgn <= 5.5f;
+    const bool all_fast = __syncthreads_and(in_range);
+    if (tid < 32) {  // rank-1 term of the tile: sum_ij xN_ij = (sum_i -log2e*ang_i) * (sum_j yn_j)
+      float sy = 0.f;
+      for (int t = tid; t < TJ; t += 32) sy += sYn[t];
+      sy = warp_sum(sy);
+      rank1 += -(double)kLog2e * (double)sum_ang * (double)sy;
+    }
+    float colP[RJ], colN[RJ];
 #pragma unroll
-      for (int c = 0; c < RJ; ++c)
-        grid_pair<false, kMasked, kGrad>(ypj[c], ynj[c], agl[r], angl[r],
-                                         kMasked ? wr[r] * wc[c] : 1.f, lgacc, colP[c], colN[c],
-                                         rowP[r], rowN[r]);
-  } else {
+    for (int c = 0; c < RJ; ++c) colP[c] = colN[c] = 0.f;
+
+    if (all_fast && !kMasked) {
+      static_assert(RJ % 4 == 0, "grid_quad takes four columns at a time");
 #pragma unroll
-    for (int r = 0; r < RI; ++r)
+      for (int r = 0; r < RI; ++r)
 #pragma unroll
-      for (int c = 0; c < RJ; ++c)
-        grid_pair<true, kMasked, kGrad>(ypj[c], ynj[c], agl[r], angl[r],
-                                        kMasked ? wr[r] * wc[c] : 1.f, lgacc, colP[c], colN[c],
-                                        rowP[r], rowN[r]);
+        for (int c = 0; c < RJ; c += 4)
+          grid_quad<kGrad>(ypj + c, ynj + c, agl[r], angl[r], lgacc, colP + c, colN + c, rowP[r],
+                           rowN[r]);
+    } else if (all_fast) {
+#pragma unroll
+      for (int r = 0; r < RI; ++r)
+#pragma unroll
+        for (int c = 0; c < RJ; ++c)
+          grid_pair<false, kMasked, kGrad>(ypj[c], ynj[c], agl[r], angl[r],
+                                           kMasked ? wr[r] * wc[c] : 1.f, lgacc, colP[c], colN[c],
+                                           rowP[r], rowN[r]);
+    } else {
+#pragma unroll
+      for (int r = 0; r < RI; ++r)
+#pragma unroll
+        for (int c = 0; c < RJ; ++c)
+          grid_pair<true, kMasked, kGrad>(ypj[c], ynj[c], agl[r], angl[r],
+                                          kMasked ? wr[r] * wc[c] : 1.f, lgacc, colP[c], colN[c],
+                                          rowP[r], rowN[r]);
+    }
+    if (kGrad) {  // column sums of this tile: one partial per (row band, column)
+#pragma unroll
+      for (int c = 0; c < RJ; ++c) {
+        sRed[0][tx + 16 * c][ty] = colP[c];
+        sRed[1][tx + 16 * c][ty] = colN[c];
+      }
+      __syncthreads();
+      for (int t = tid; t < 2 * TJ; t += 256) {
+        const int which = t / TJ, colm = t - which * TJ;
+        float acc = 0.f;
+#pragma unroll
+        for (int k = 0; k < 16; ++k) acc += sRed[which][colm][k];
+        float *dst = which ? ws.colN : ws.colP;
+        __stcg(&dst[(size_t)blockIdx.y * Bpad + j0 + colm], not_sentinel(acc * (-1.0f / kLog2e)));
+      }
+    }
+    __syncthreads();  // sYp / sYn / sRed are rewritten by the next tile
   }
 
-  // ---- per-tile reductions -------------------------------------------------------------
+  // ---- per-CTA reductions: row sums over the CTA's column tiles, loss partial ----------------
   if (kGrad) {
 #pragma unroll
     for (int r = 0; r < RI; ++r) {
@@ -486,21 +553,6 @@ grid_bce_kernel(const float *__restrict__ yp, const float *__restrict__ yn, int 
       float *dst = which ? ws.rowN : ws.rowP;
       __stcg(&dst[(size_t)blockIdx.x * Bpad + i0 + row], not_sentinel(acc));
     }
-    __syncthreads();
-#pragma unroll
-    for (int c = 0; c < RJ; ++c) {
-      sRed[0][tx + 16 * c][ty] = colP[c];
-      sRed[1][tx + 16 * c][ty] = colN[c];
-    }
-    __syncthreads();
-    for (int t = tid; t < 2 * TJ; t += 256) {
-      const int which = t / TJ, colm = t - which * TJ;
-      float acc = 0.f;
-#pragma unroll
-      for (int k = 0; k < 16; ++k) acc += sRed[which][colm][k];
-      float *dst = which ? ws.colN : ws.colP;
-      __stcg(&dst[(size_t)blockIdx.y * Bpad + j0 + colm], not_sentinel(acc * (-1.0f / kLog2e)));
-    }
   }
   lgacc = warp_sum(lgacc);
   if ((tid & 31) == 0) sLoss[tid >> 5] = lgacc;
@@ -509,7 +561,7 @@ grid_bce_kernel(const float *__restrict__ yp, const float *__restrict__ yn, int 
     float acc = 0.f;
 #pragma unroll
     for (int q = 0; q < 8; ++q) acc += sLoss[q];
-    __stcg(&ws.losspart[blockIdx.y * gridDim.x + blockIdx.x], not_sentinel((float)((double)acc + sRank1)));
+    __stcg(&ws.losspart[blockIdx.y * gridDim.x + blockIdx.x], not_sentinel((float)((double)acc + rank1)));
   }
 }
 
@@ -540,16 +592,43 @@ GridWs grid_ws_layout(int B, void *base) {
   w.tile_j = 16 * rj;
   w.nblk_i = (B + w.tile_i - 1) / w.tile_i;
   w.nblk_j = (B + w.tile_j - 1) / w.tile_j;
+  {
+    // column tiles per CTA: the fewest tiles on the busiest CTA slot, preferring SHORT walks on a
+    // tie.  Measured at B = 4096 (ncu, profiles/r2l_grid_tpc.txt): 26 us for 1, 2 or 4 tiles per
+    // CTA -- the kernel is bound by MIO/MUFU latency at 4 warps per scheduler (XU pipe 45 %, issue
+    // slots 50 % busy), not by its per-CTA prologue -- and inside the step graph short CTAs
+    // interleave better with the sweep that runs beside them (62.2 vs 65.4 us per step).
+    const int slots = sm_count() * (ri == 8 && rj == 8 ? 2 : ri * rj == 32 ? 3 : 4);
+    int best_t = 1;
+    long long best_cost = -1;
+    for (int tpc = 1; tpc <= w.nblk_j; ++tpc) {
+      const int grp = (w.nblk_j + tpc - 1) / tpc;
+      const long long rounds = ((long long)w.nblk_i * grp + slots - 1) / slots;
+      const long long cost = rounds * tpc;
+      if (best_cost < 0 || cost < best_cost) {
+        best_cost = cost;
+        best_t = tpc;
+      }
+    }
+    static int env_tpc = -1;
+    if (env_tpc < 0) {
+      const char *e = getenv("MACR_GRID_TPC");  // developer knob: column tiles per CTA
+      env_tpc = e ? atoi(e) : 0;
+    }
+    if (env_tpc > 0) best_t = env_tpc < w.nblk_j ? env_tpc : w.nblk_j;
+    w.grp_tiles = best_t;
+    w.ngrp_j = (w.nblk_j + best_t - 1) / best_t;
+  }
   const int tmax = w.tile_i > w.tile_j ? w.tile_i : w.tile_j;
   w.Bpad = (B + tmax - 1) / tmax * tmax;
   float *p = reinterpret_cast<float *>(base);
-  const size_t band_r = (size_t)w.nblk_j * w.Bpad, band_c = (size_t)w.nblk_i * w.Bpad;
+  const size_t band_r = (size_t)w.ngrp_j * w.Bpad, band_c = (size_t)w.nblk_i * w.Bpad;
   w.rowP = p;
   w.rowN = p + band_r;
   w.colP = p + 2 * band_r;
   w.colN = p + 2 * band_r + band_c;
   w.losspart = p + 2 * band_r + 2 * band_c;
-  const size_t lp = ((size_t)w.nblk_i * w.nblk_j + 3) & ~(size_t)3;
+  const size_t lp = ((size_t)w.nblk_i * w.ngrp_j + 3) & ~(size_t)3;
   w.litem = w.losspart + lp;
   w.luser = w.litem + w.Bpad;
   w.gA = w.luser + w.Bpad;
@@ -601,8 +680,8 @@ static void launch_grid_t(const float *yp, const float *yn, int B, float alpha, 
                           const GridWs &ws, const GridOut &out, cudaStream_t s) {
   // tiles, then the loss folder and (grad only) one folder CTA per row band and per column band
   const int folders = 1 + (kGrad ? ws.nblk_i + ws.nblk_j : 0);
-  const int fold_rows = (folders + ws.nblk_j - 1) / ws.nblk_j;
-  dim3 grid(ws.nblk_j, ws.nblk_i + fold_rows);
+  const int fold_rows = (folders + ws.ngrp_j - 1) / ws.ngrp_j;
+  dim3 grid(ws.ngrp_j, ws.nblk_i + fold_rows);
   if (B % ws.tile_i == 0 && B % ws.tile_j == 0)
     grid_bce_kernel<RI, RJ, MINB, false, kGrad><<<grid, 256, 0, s>>>(yp, yn, B, alpha, beta, ws, out);
   else

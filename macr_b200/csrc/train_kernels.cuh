@@ -23,10 +23,13 @@ struct StepState {
 struct GridWs {  // carve-up of the grid kernel's partial-sum workspace
   int tile_i, tile_j;  // rows x columns of one CTA tile
   int nblk_i, nblk_j;  // ceil(B / tile_i), ceil(B / tile_j)
+  int ngrp_j, grp_tiles;  // a CTA walks grp_tiles consecutive column tiles of one row band:
+                          // ngrp_j = ceil(nblk_j / grp_tiles) CTAs per band, sized so that the whole
+                          // grid is resident at once (row sums stay in registers, one prologue per CTA)
   int Bpad;            // B rounded up to the larger tile
-  float *rowP, *rowN;  // [nblk_j][Bpad]
+  float *rowP, *rowN;  // [ngrp_j][Bpad]
   float *colP, *colN;  // [nblk_i][Bpad]
-  float *losspart;     // [nblk_i*nblk_j]
+  float *losspart;     // [nblk_i*ngrp_j]
   float *litem, *luser;  // [Bpad] branch losses per position (model.py:213,215)
   float *gA, *gAN, *gG;  // [Bpad] sig(sp), sig(sn), sig(su)
   int item_gate_only;    // `--train rubibce` / `--loss bce1` (model.py:158-183): gather_dots writes
