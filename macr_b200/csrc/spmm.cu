@@ -136,12 +136,17 @@ __global__ void __launch_bounds__(256)
 spmm_seg_kernel(const int32_t *__restrict__ seg_row, const int32_t *__restrict__ seg_start,
                 const int32_t *__restrict__ seg_end, const int32_t *__restrict__ seg_slot, int n_seg,
                 const int32_t *__restrict__ col, const float *__restrict__ val, RowSrc X,
-                const uint32_t *__restrict__ x_nonzero, const float *__restrict__ add, float *Y,
+                const uint32_t *__restrict__ x_nonzero, const uint32_t *__restrict__ row_needed,
+                const float *__restrict__ add, float *Y,
                 RowSrc acc_in, float *acc_out, float acc_div, float *__restrict__ partial) {
   const int lane = threadIdx.x & 31, hl = lane & 15;
   const unsigned hmask = (lane < 16) ? 0x0000ffffu : 0xffff0000u;
   const int sg = (int)(((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 4);
   if (sg >= n_seg) return;
+  if (row_needed) {  // only the rows somebody reads (the batch's rows in the last forward layer)
+    const int r = seg_row[sg];
+    if (!((row_needed[r >> 5] >> (r & 31)) & 1u)) return;  // uniform across the half-warp
+  }
   const int start = seg_start[sg], end = seg_end[sg];
   float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
   for (int base = start; base < end; base += 16) {
@@ -203,6 +208,7 @@ __device__ __forceinline__ void sum_partials(float4 &acc, const float4 *__restri
 __global__ void __launch_bounds__(256)
 spmm_combine_kernel(const int32_t *__restrict__ multi_row, const int32_t *__restrict__ multi_slot0,
                     const int32_t *__restrict__ multi_nseg, int n_multi,
+                    const uint32_t *__restrict__ row_needed,
                     const float *__restrict__ partial, const float *__restrict__ add, float *Y,
                     RowSrc acc_in, float *acc_out, float acc_div) {
   const int hl = threadIdx.x & 15;
@@ -210,6 +216,10 @@ spmm_combine_kernel(const int32_t *__restrict__ multi_row, const int32_t *__rest
   if (m >= n_multi) return;
   const int n = multi_nseg[m];
   if (n > kCombineWide) return;  // spmm_combine_wide_kernel's row
+  if (row_needed) {
+    const int r = multi_row[m];
+    if (!((row_needed[r >> 5] >> (r & 31)) & 1u)) return;
+  }
   const float4 *p = reinterpret_cast<const float4 *>(partial + (long long)multi_slot0[m] * kD) + hl;
   float4 acc = p[0];
   sum_partials(acc, p, 1, 1, n);
@@ -220,11 +230,16 @@ spmm_combine_kernel(const int32_t *__restrict__ multi_row, const int32_t *__rest
 __global__ void __launch_bounds__(256)
 spmm_combine_wide_kernel(const int32_t *__restrict__ wide_idx, const int32_t *__restrict__ multi_row,
                          const int32_t *__restrict__ multi_slot0, const int32_t *__restrict__ multi_nseg,
+                         const uint32_t *__restrict__ row_needed,
                          const float *__restrict__ partial, const float *__restrict__ add, float *Y,
                          RowSrc acc_in, float *acc_out, float acc_div) {
   __shared__ float4 s_part[16][16];
   const int hl = threadIdx.x & 15, hw = threadIdx.x >> 4;
   const int m = wide_idx[blockIdx.x];
+  if (row_needed) {
+    const int r = multi_row[m];
+    if (!((row_needed[r >> 5] >> (r & 31)) & 1u)) return;  // uniform across the CTA
+  }
   const int n = multi_nseg[m];
   const float4 *p = reinterpret_cast<const float4 *>(partial + (long long)multi_slot0[m] * kD) + hl;
   float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
@@ -292,24 +307,24 @@ void free_spmm_plan(SpmmPlan *p) {
 int launch_spmm_planned(const SpmmPlan *plan, const int32_t *rowptr, const int32_t *col,
                         const float *val, int64_t n_rows, RowSrc X, const float *add, float *Y,
                         RowSrc acc_in, float *acc_out, float acc_div, const uint32_t *x_nonzero,
-                        cudaStream_t s) {
+                        cudaStream_t s, const uint32_t *row_needed) {
   if (!plan) return launch_spmm(rowptr, col, val, n_rows, X, add, Y, acc_in, acc_out, acc_div, s);
   if (plan->n_seg == 0) return MACR_OK;
   spmm_seg_kernel<<<(unsigned)(((long long)plan->n_seg * 16 + 255) / 256), 256, 0, s>>>(
       plan->seg_row, plan->seg_start, plan->seg_end, plan->seg_slot, plan->n_seg, col, val, X,
-      x_nonzero, add, Y, acc_in, acc_out, acc_div, plan->partial);
+      x_nonzero, row_needed, add, Y, acc_in, acc_out, acc_div, plan->partial);
   MACR_LAUNCH_CHECK();
   if (plan->n_multi) {
     spmm_combine_kernel<<<(unsigned)(((long long)plan->n_multi * 16 + 255) / 256), 256, 0, s>>>(
-        plan->multi_row, plan->multi_slot0, plan->multi_nseg, plan->n_multi, plan->partial, add, Y,
-        acc_in, acc_out, acc_div);
+        plan->multi_row, plan->multi_slot0, plan->multi_nseg, plan->n_multi, row_needed, plan->partial,
+        add, Y, acc_in, acc_out, acc_div);
     MACR_LAUNCH_CHECK();
   }
   if (plan->n_wide) {
     spmm_combine_wide_kernel<<<plan->n_wide, 256, 0, s>>>(plan->wide_idx, plan->multi_row,
                                                           plan->multi_slot0, plan->multi_nseg,
-                                                          plan->partial, add, Y, acc_in, acc_out,
-                                                          acc_div);
+                                                          row_needed, plan->partial, add, Y, acc_in,
+                                                          acc_out, acc_div);
     MACR_LAUNCH_CHECK();
   }
   return MACR_OK;
@@ -350,6 +365,22 @@ int launch_lgcn_propagate(const int32_t *rowptr, const int32_t *col, const float
     if (rc) return rc;
     if (!last) x = RowSrc{y, y, N};
   }
+  return MACR_OK;
+}
+
+// bitmap over the N = U + I node rows of the rows the batch reads: users, pos and neg items
+__global__ void __launch_bounds__(256)
+mark_batch_rows_kernel(const StepState *st, int B, long long n_users, uint32_t *__restrict__ bitmap) {
+  const int e = blockIdx.x * blockDim.x + threadIdx.x;
+  if (e >= 3 * B) return;
+  const int32_t *ids = st->ids_base + st->step_idx * 3LL * B;
+  const long long r = ids[e] + (e < B ? 0 : n_users);
+  atomicOr(&bitmap[r >> 5], 1u << (r & 31));
+}
+
+int launch_mark_batch_rows(const StepState *st, int B, int64_t n_users, uint32_t *bitmap, cudaStream_t s) {
+  mark_batch_rows_kernel<<<(3 * B + 255) / 256, 256, 0, s>>>(st, B, n_users, bitmap);
+  MACR_LAUNCH_CHECK();
   return MACR_OK;
 }
 

@@ -32,10 +32,14 @@ void free_spmm_plan(SpmmPlan *p);
 // Y = A X (+ add); optionally acc_out = (acc_in + Y) (/ acc_div when > 0).
 // plan == nullptr: stateless kernel (one CTA per 16 rows).  x_nonzero (nullable): bitmap over
 // the rows of X; nonzeros whose X row is flagged all-zero are skipped (row-sparse gradients).
+// row_needed (nullable, planned path only): bitmap over the output rows; rows whose bit is clear are
+// not computed at all (their outputs keep whatever they held) -- a training step reads the last
+// forward layer at the batch's <= 3B rows only; the rows that are computed are bit-identical.
 int launch_spmm_planned(const SpmmPlan *plan, const int32_t *rowptr, const int32_t *col,
                         const float *val, int64_t n_rows, RowSrc X, const float *add, float *Y,
                         RowSrc acc_in, float *acc_out, float acc_div, const uint32_t *x_nonzero,
-                        cudaStream_t s);
+                        cudaStream_t s, const uint32_t *row_needed = nullptr);
+int launch_mark_batch_rows(const StepState *st, int B, int64_t n_users, uint32_t *bitmap, cudaStream_t s);
 int launch_spmm(const int32_t *rowptr, const int32_t *col, const float *val, int64_t n_rows,
                 RowSrc X, const float *add, float *Y, RowSrc acc_in, float *acc_out,
                 float acc_div, cudaStream_t s);

@@ -547,6 +547,7 @@ struct macr_lgcn_trainer : macr::TrainerBase {
   int L;
   float *Emean, *tmp, *g3;  // [N][64], 2x[N][64], [N][64]
   uint32_t *g3_nz;          // bitmap: rows of g3 that hold a gradient this step
+  uint32_t *need_bm = nullptr;  // bitmap: node rows the batch reads (last forward layer of a training step)
   macr::SpmmPlan plan;      // static segment decomposition of the adjacency
   bool emb_dirty;
   int launches;
@@ -604,15 +605,18 @@ static int lgcn_exchange(macr_lgcn_trainer *h, int which, cudaStream_t s) {
 // E_mean of the current tables (LightGCN.py:288-309).  Row-partitioned: E0's rows of other ranks are
 // fetched first (their owners have just updated them), every layer is computed for the owned rows
 // and all-gathered, and so is the layer mean.  -> number of kernels launched
-static int lgcn_forward(macr_lgcn_trainer *h, cudaStream_t s, int *launches) {
+// batch_rows (nullable): the training step reads E_mean at the batch's rows only, so the LAST layer
+// is computed for those rows alone (E_mean's other rows are left stale: emb_dirty stays set).
+static int lgcn_forward(macr_lgcn_trainer *h, cudaStream_t s, int *launches,
+                        const uint32_t *batch_rows = nullptr) {
   const int per_spmm = h->plan.n_multi ? 2 : 1;
-  if (!h->sharded) {
+  if (!h->sharded && (batch_rows == nullptr || h->L == 0)) {
     if (launches) *launches += h->L * per_spmm;
     return launch_lgcn_propagate(h->rowptr, h->col, h->val, h->U, h->nu, h->I, h->ni, h->L, h->Emean,
                                  h->tmp, s, &h->plan);
   }
   const int64_t N = h->nu + h->ni;
-  int rc = lgcn_exchange(h, XCH_TABLES, s);
+  int rc = h->sharded ? lgcn_exchange(h, XCH_TABLES, s) : MACR_OK;
   if (rc) return rc;
   RowSrc e0{h->U, h->I, h->nu};
   if (h->L == 0) {
@@ -627,16 +631,16 @@ static int lgcn_forward(macr_lgcn_trainer *h, cudaStream_t s, int *launches) {
     float *y = last ? nullptr : buf[k & 1];
     RowSrc accin = (k == 0) ? e0 : RowSrc{h->Emean, h->Emean, N};
     rc = launch_spmm_planned(&h->plan, h->rowptr, h->col, h->val, N, x, nullptr, y, accin, h->Emean,
-                             last ? (float)(h->L + 1) : 0.f, nullptr, s);
+                             last ? (float)(h->L + 1) : 0.f, nullptr, s, last ? batch_rows : nullptr);
     if (rc) return rc;
     if (!last) {
-      rc = lgcn_exchange(h, XCH_TMP0 + (k & 1), s);
+      rc = h->sharded ? lgcn_exchange(h, XCH_TMP0 + (k & 1), s) : MACR_OK;
       if (rc) return rc;
       x = RowSrc{y, y, N};
     }
   }
-  if (launches) *launches += h->L * per_spmm + 2 * (h->L + 1);
-  return lgcn_exchange(h, XCH_EMEAN, s);
+  if (launches) *launches += h->L * per_spmm + (h->sharded ? 2 * (h->L + 1) : 0);
+  return h->sharded ? lgcn_exchange(h, XCH_EMEAN, s) : MACR_OK;
 }
 
 static int lgcn_enqueue_impl(macr_lgcn_trainer *h, int B, int train) {
@@ -658,10 +662,18 @@ static int lgcn_enqueue_impl(macr_lgcn_trainer *h, int B, int train) {
     if (rc) return rc;
     MACR_CUDA(cudaMemsetAsync(h->g3, 0, sizeof(float) * N * kD, side));
     MACR_CUDA(cudaMemsetAsync(h->g3_nz, 0, sizeof(uint32_t) * ((N + 31) / 32), side));
+    // second side branch: the bitmap of the batch's node rows (read by the last forward layer)
+    cudaStream_t side2 = h->side2;
+    MACR_CUDA(cudaStreamWaitEvent(side2, h->ev_fork, 0));
+    MACR_CUDA(cudaMemsetAsync(h->need_bm, 0, sizeof(uint32_t) * ((N + 31) / 32), side2));
+    rc = launch_mark_batch_rows(h->st, B, h->nu, h->need_bm, side2);
+    if (rc) return rc;
+    MACR_CUDA(cudaEventRecord(h->ev_join2, side2));
     MACR_CUDA(cudaEventRecord(h->ev_join, side));
-    launches += 1;
+    launches += 2;
+    MACR_CUDA(cudaStreamWaitEvent(s, h->ev_join2, 0));  // a few microseconds of work, long done
   }
-  rc = lgcn_forward(h, s, &launches);
+  rc = lgcn_forward(h, s, &launches, train ? h->need_bm : nullptr);
   if (rc) return rc;
   rc = launch_gather_dots(Ue, Ie, h->U, h->I, h->w, h->wu, nullptr, nullptr, nullptr, h->st, B, yp,
                           yn, sp, sn, su, rq, h->snap, &g, s);
@@ -764,6 +776,7 @@ extern "C" int macr_lgcn_trainer_create(macr_lgcn_trainer **out, const int32_t *
   MACR_CUDA(cudaMalloc(&h->tmp, sizeof(float) * ne * 2));
   MACR_CUDA(cudaMalloc(&h->g3, sizeof(float) * ne));
   MACR_CUDA(cudaMalloc(&h->g3_nz, sizeof(uint32_t) * ((size_t)(n_users + n_items + 31) / 32 + 1)));
+  MACR_CUDA(cudaMalloc(&h->need_bm, sizeof(uint32_t) * ((size_t)(n_users + n_items + 31) / 32 + 1)));
   rc = build_spmm_plan(rowptr, n_users + n_items, &h->plan);
   if (rc) return rc;
   MACR_CUDA(cudaMalloc(&h->flags, sizeof(unsigned long long) * 32));
@@ -953,6 +966,7 @@ extern "C" int macr_lgcn_trainer_destroy(macr_lgcn_trainer *h) {
   cudaFree(h->tmp);
   cudaFree(h->g3);
   cudaFree(h->g3_nz);
+  cudaFree(h->need_bm);
   cudaFree(h->flags);
   free_spmm_plan(&h->plan);
   delete h;
