@@ -671,10 +671,27 @@ __device__ __forceinline__ float fkey_inv(uint32_t k) {
 // one warp reduction).  Returns 0 when fewer than K keys are non-zero.
 template <int NV>
 __device__ __forceinline__ uint32_t warp_kth_largest(const uint32_t (&key)[NV], int K) {
-  uint32_t prefix = 0;
+  // bits on which all non-zero keys agree need no round: scores above one threshold share their
+  // sign, exponent and leading mantissa bits
+  uint32_t all_and = 0xffffffffu, all_or = 0u;
+  int n_valid = 0;
+#pragma unroll
+  for (int r = 0; r < NV; ++r) {
+    all_and &= key[r] ? key[r] : 0xffffffffu;
+    all_or |= key[r];
+    n_valid += key[r] != 0u;
+  }
+  all_and = __reduce_and_sync(0xffffffffu, all_and);
+  all_or = __reduce_or_sync(0xffffffffu, all_or);
+  n_valid = __reduce_add_sync(0xffffffffu, n_valid);
+  if (n_valid < K) return 0u;
+  const uint32_t differ = all_and ^ all_or;
+  if (differ == 0u) return all_or;  // all valid keys are equal
+  const int top = 31 - __clz(differ);
+  uint32_t prefix = top == 31 ? 0u : (all_or >> (top + 1)) << (top + 1);  // the common leading bits
   int remaining = K;
 #pragma unroll 1
-  for (int bit = 31; bit >= 0; --bit) {
+  for (int bit = top; bit >= 0; --bit) {
     const uint32_t want = (prefix | (1u << bit)) >> bit;
     int cnt = 0;
 #pragma unroll
@@ -709,15 +726,23 @@ row_threshold_kernel(const float *__restrict__ gmax, int T, int n_groups, int ld
   // is one) so the select always runs on 128 values, 4 per lane
   constexpr int NV = 4;
   uint32_t key[NV];
+  {
+    // all (<= kMaxChunksS) loads of the lane issued before any is used: a latency-bound kernel
+    float v[NV][kMaxChunksS / NV];
 #pragma unroll
-  for (int r = 0; r < NV; ++r) {
-    float m = -INFINITY;
-    bool any = false;
-    for (int idx = r * 32 + lane; idx < n_groups; idx += 32 * NV) {
-      m = fmaxf(m, gmax[(size_t)t * ld_g + idx]);
-      any = true;
+    for (int r = 0; r < NV; ++r)
+#pragma unroll
+      for (int q = 0; q < kMaxChunksS / NV; ++q) {
+        const int idx = r * 32 + lane + 32 * NV * q;
+        v[r][q] = idx < n_groups ? gmax[(size_t)t * ld_g + idx] : -INFINITY;
+      }
+#pragma unroll
+    for (int r = 0; r < NV; ++r) {
+      float m = v[r][0];
+#pragma unroll
+      for (int q = 1; q < kMaxChunksS / NV; ++q) m = fmaxf(m, v[r][q]);
+      key[r] = r * 32 + lane < n_groups ? fkey(m) : 0u;
     }
-    key[r] = any ? fkey(m) : 0u;
   }
   const uint32_t kk = warp_kth_largest<NV>(key, K);
   const float mk = kk ? fkey_inv(kk) : -INFINITY;
