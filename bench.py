@@ -635,8 +635,8 @@ def sharded_lgcn(cx, K, W):
     cx.barrier()
     t = cx.max_over_ranks(e0.elapsed_time(e1) * 1e-3) / K
     sh.check_peers()
-    # SURVEY 8d, gather-honest SpMM bytes (N*d*4 = 282 MB exceeds L2): 8*nnz + 4*nnz*d + 4*N*d per SpMM
-    spmm_bytes = 8.0 * nnz + 4.0 * nnz * D + 4.0 * N * D
+    # SURVEY 8d algorithmic SpMM bytes (the dense operand counted once): 8*nnz + 4*(N+1) + 8*N*d per SpMM
+    spmm_bytes = 8.0 * nnz + 4.0 * (N + 1) + 8.0 * N * D
     step_bytes = 2 * LG_LAYERS * spmm_bytes + 24.0 * D * N + 12.0 * D * LG_BATCH
     pk = cx.peaks["hbm_gbs"]
     out = {"workload": f"MACR-LightGCN synthetic U={LG_USERS} I={LG_ITEMS} nnz(A)={nnz} L={LG_LAYERS} d=64 "
@@ -649,8 +649,9 @@ def sharded_lgcn(cx, K, W):
            "launches_per_step": sh.trainer.launches_per_step,
            "roofline": {"bound": "hbm", "bytes_per_step": step_bytes, "peak": pk * cx.world, "unit": "GB/s",
                         "achieved": step_bytes / t / 1e9, "frac": step_bytes / t / 1e9 / (pk * cx.world),
-                        "note": "gather-honest bytes (every nonzero reads a 256-byte row; the operand exceeds "
-                                "L2) of 2L SpMMs + the dense Adam, against N x the measured HBM peak"},
+                        "note": "algorithmic bytes of 2L SpMMs (8*nnz + 4(N+1) + 8*N*d each: the dense operand "
+                                "read once) + the dense Adam, against N x the measured HBM peak; the SpMM is bound "
+                                "by its row gathers (4*d*nnz bytes per SpMM through L2), not by DRAM"},
            "final_loss": float(losses[(W + K - 1) % nb, 0].item())}
     sh.close()
     del sh, ids
@@ -775,11 +776,13 @@ def gowalla_block(cx, K, W, with_cpu):
                                               "ms_per_launch": sw_ms, "bytes_per_launch": sweep_bytes,
                                               "traffic": ncu_traffic("adam_sweep_kernel")},
                         "grid_bce_kernel": {"bound": "mufu", "ms_per_launch": grid_ms,
-                                            "achieved_gops": 4.0 * BATCH * BATCH / (grid_ms * 1e-3) / 1e9,
+                                            "achieved_gops": 2.5 * BATCH * BATCH / (grid_ms * 1e-3) / 1e9,
                                             "peak_gops": mufu_peak / 1e9,
-                                            "frac": 4.0 * BATCH * BATCH / (grid_ms * 1e-3) / mufu_peak,
-                                            "note": "stateless macr_grid_bce_fwd_bwd (memset + gates + grid), "
-                                                    "buffers preallocated; 4 MUFU per pair, 16 / clk / SM"},
+                                            "frac": 2.5 * BATCH * BATCH / (grid_ms * 1e-3) / mufu_peak,
+                                            "note": "stateless macr_grid_bce_fwd_bwd = memset + gates + grid, three "
+                                                    "launches from Python (host-bound at this size); 2.5 MUFU per pair "
+                                                    "(2 ex2 + rcp / lg2 shared by four pairs), 16 / clk / SM; the kernel "
+                                                    "alone: 23.6 us under ncu (profiles/r2l_grid_tpc.txt)"},
                         "step": {"bytes_per_step": step_bytes, "frac": step_bytes / (ms_step * 1e-3) / 1e9 / pk,
                                  "note": "whole step vs its HBM floor; the BxB grid is MUFU-bound (floor 14.4 us)"}}}
     out["scoring"] = gowalla_scoring(cx)
