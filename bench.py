@@ -460,19 +460,25 @@ def sharded_train(cx, K, W):
         cx.barrier()
         t_ex = cx.max_over_ranks(x0.elapsed_time(x1) * 1e-3) / K
     sh.check_peers()
-    # roofline of the HBM-bound kernel: the dense sweep over this rank's user slice, alone
-    rows_u = t.U.shape[0]
+    # roofline of the HBM-bound kernel: the dense sweep over this rank's slices of both tables, alone
+    # (inside the step it is ONE launch over both; the stateless entry point takes a table at a time)
+    rows_u, rows_i = t.U.shape[0], t.I.shape[0]
+
+    def sweep_both():
+        ops.adam_sweep_untouched(t.U, t.mU, t.vU, None, 1e-6)
+        ops.adam_sweep_untouched(t.I, t.mI, t.vI, None, 1e-6)
+
     r0, r1 = cx.events()
-    ops.adam_sweep_untouched(t.U, t.mU, t.vU, None, 1e-6)
+    sweep_both()
     cx.barrier()
     n_sw = 4 if cx.world == 1 else 8
     r0.record()
     for _ in range(n_sw):
-        ops.adam_sweep_untouched(t.U, t.mU, t.vU, None, 1e-6)
+        sweep_both()
     r1.record()
     cx.barrier()
     sw_ms = cx.max_over_ranks(r0.elapsed_time(r1)) / n_sw
-    sweep_bytes = 24.0 * D * rows_u
+    sweep_bytes = 24.0 * D * (rows_u + rows_i)
     achieved = sweep_bytes / (sw_ms * 1e-3) / 1e9
     step_bytes = 24.0 * D * (C5_USERS + C5_ITEMS) + 780.0 * B + 3072.0
     ms_step = 1e3 * t_dev / K
@@ -481,8 +487,9 @@ def sharded_train(cx, K, W):
                 "peak_kind": cx.peak_kind, "unit": "GB/s", "frac": achieved / pk,
                 "traffic": ncu_traffic("adam_sweep_kernel_c5"), "bytes_per_launch": sweep_bytes,
                 "ms_per_launch": sw_ms,
-                "method": f"{n_sw} launches over this rank's user slice ({rows_u} rows x 3 tensors, far larger "
-                          "than L2) between one event pair on the launching stream; max over ranks",
+                "method": f"{n_sw} sweeps of this rank's slices of both tables ({rows_u} + {rows_i} rows x 3 tensors, "
+                          "far larger than L2; two launches each) between one event pair on the launching stream; "
+                          "max over ranks",
                 "step": {"bytes_per_step": step_bytes, "achieved_per_gpu": step_bytes / cx.world / (ms_step * 1e-3) / 1e9,
                          "frac": step_bytes / cx.world / (ms_step * 1e-3) / 1e9 / pk,
                          "note": "whole fused step (exchange + gather + dots + BxB BCE + row gradients + dense "
