@@ -1025,32 +1025,20 @@ int launch_batch_plan2(const int32_t *ids0, const StepState *st, int ids0_off, i
 }
 
 // touched-row bitmaps of both tables straight from the ids (lets the dense sweep start without
-// waiting for the plan).  half_words > 0: each bitmap has TWO halves of that many words, selected by
-// the parity of the Adam step -- this step's rows are marked in half (t & 1) while the other half
-// (the marks of the previous step) is zeroed, so nobody has to clear a bit behind the sweep and the
-// row-gradient kernel can run beside it (large tables, see trainer.cu:mf_enqueue).
+// waiting for the plan)
 __global__ void __launch_bounds__(256)
 mark_touched_kernel(const StepState *st, const int32_t *ids_direct, int B, uint32_t *bmU,
-                    uint32_t *bmI, long long half_u, long long half_i) {
-  const long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-  const int par = (half_u > 0 && st) ? (int)(st->t & 1) : 0;
-  if (e < 3LL * B) {
-    const int32_t *ids = st ? st->ids_base + st->step_idx * 3LL * B : ids_direct;
-    const uint32_t r = (uint32_t)ids[e];
-    uint32_t *bm = e < B ? bmU + par * half_u : bmI + par * half_i;
-    atomicOr(&bm[r >> 5], 1u << (r & 31));
-  }
-  if (half_u > 0) {  // zero the other parity's halves (grid sized for max(3B, half_u + half_i))
-    if (e < half_u) bmU[(1 - par) * half_u + e] = 0u;
-    else if (e < half_u + half_i) bmI[(1 - par) * half_i + (e - half_u)] = 0u;
-  }
+                    uint32_t *bmI) {
+  const int e = blockIdx.x * blockDim.x + threadIdx.x;
+  if (e >= 3 * B) return;
+  const int32_t *ids = st ? st->ids_base + st->step_idx * 3LL * B : ids_direct;
+  const uint32_t r = (uint32_t)ids[e];
+  atomicOr(&(e < B ? bmU : bmI)[r >> 5], 1u << (r & 31));
 }
 
 int launch_mark_touched(const StepState *st, const int32_t *ids, int B, uint32_t *bmU,
-                        uint32_t *bmI, cudaStream_t s, long long half_u, long long half_i) {
-  long long n = 3LL * B;
-  if (half_u + half_i > n) n = half_u + half_i;
-  mark_touched_kernel<<<(unsigned)((n + 255) / 256), 256, 0, s>>>(st, ids, B, bmU, bmI, half_u, half_i);
+                        uint32_t *bmI, cudaStream_t s) {
+  mark_touched_kernel<<<(3 * B + 255) / 256, 256, 0, s>>>(st, ids, B, bmU, bmI);
   MACR_LAUNCH_CHECK();
   return MACR_OK;
 }
@@ -1067,7 +1055,6 @@ struct SweepTable {
   float4 *var, *m, *v;
   long long n4;  // rows * 16
   const uint32_t *bitmap;
-  long long half_words;  // > 0: two halves, the one of parity (st->t & 1) holds this step's marks
 };
 
 constexpr int kSweepThreads = 256;
@@ -1077,10 +1064,6 @@ __global__ void __launch_bounds__(kSweepThreads, 3)
 adam_sweep_kernel(SweepTable t0, SweepTable t1, long long per_cta, float lr_or_lrt,
                   const StepState *st, float b1, float b2, float eps) {
   const float lr_t = step_lr_t(st, lr_or_lrt);
-  if (st && t0.half_words > 0 && (st->t & 1)) {
-    t0.bitmap += t0.half_words;
-    t1.bitmap += t1.half_words;
-  }
   const long long total = t0.n4 + t1.n4;
   const long long beg = (long long)blockIdx.x * per_cta;
   const long long end = min(total, beg + per_cta);
@@ -1148,9 +1131,9 @@ static int sweep_ctas_per_sm(long long total_f4) {
 int launch_adam_sweep2(float *var0, float *m0, float *v0, int64_t rows0, const uint32_t *bm0,
                        float *var1, float *m1, float *v1, int64_t rows1, const uint32_t *bm1,
                        float lr_t, const StepState *st, float b1, float b2, float eps,
-                       cudaStream_t s, long long half0, long long half1) {
-  SweepTable t0{(float4 *)var0, (float4 *)m0, (float4 *)v0, rows0 * (kD / 4), bm0, half0};
-  SweepTable t1{(float4 *)var1, (float4 *)m1, (float4 *)v1, rows1 * (kD / 4), bm1, half1};
+                       cudaStream_t s) {
+  SweepTable t0{(float4 *)var0, (float4 *)m0, (float4 *)v0, rows0 * (kD / 4), bm0};
+  SweepTable t1{(float4 *)var1, (float4 *)m1, (float4 *)v1, rows1 * (kD / 4), bm1};
   const long long total = t0.n4 + t1.n4;
   if (total == 0) return MACR_OK;
   constexpr int UNROLL = 4;

@@ -80,11 +80,11 @@ int launch_batch_plan2(const int32_t *ids0, const StepState *st0, int ids0_off, 
                        int ids1_off, int n_ids1, int64_t rows1, PlanBufs out1, uint32_t *bitmap1,
                        cudaStream_t s);
 int launch_mark_touched(const StepState *st, const int32_t *ids, int B, uint32_t *bmU,
-                        uint32_t *bmI, cudaStream_t s, long long half_u = 0, long long half_i = 0);
+                        uint32_t *bmI, cudaStream_t s);
 int launch_adam_sweep2(float *var0, float *m0, float *v0, int64_t rows0, const uint32_t *bm0,
                        float *var1, float *m1, float *v1, int64_t rows1, const uint32_t *bm1,
                        float lr_t, const StepState *st, float b1, float b2, float eps,
-                       cudaStream_t s, long long half0 = 0, long long half1 = 0);
+                       cudaStream_t s);
 // fused Adam on the touched rows (MF) and fused step tail, both optional
 struct AdamTabs {  // U == nullptr: no fused Adam, summed rows go to gU / gI (LightGCN)
   float *U, *mU, *vU, *I, *mI, *vI;

@@ -194,11 +194,6 @@ struct macr_mf_trainer : macr::TrainerBase {
   int mode = MACR_TRAIN_RUBIBCEBOTH;
   // row-partitioned mode (macr_mf_trainer_shard): U / I are this rank's local tables (owned rows +
   // ghost rows, csrc/shard.cu); the exchange of the batch's rows runs inside the step graph
-  // large tables (>= 256 MiB of var/m/v, or MACR_MF_DECOUPLE=1): the touched-row bitmaps have two
-  // halves alternating with the Adam step, nobody clears a bit behind the sweep, so the row-gradient
-  // kernel runs BESIDE the milliseconds-long sweep and only a one-CTA step tail waits for both
-  bool decoupled = false;
-  long long half_u = 0, half_i = 0;  // words per bitmap half (0: single bitmaps)
   bool sharded = false;
   macr_shard_desc sd{};
   macr::PeerGhosts ghosts{};
@@ -232,13 +227,13 @@ static int mf_enqueue(macr_mf_trainer *h, int B) {
                           h->ni, h->planI, nullptr, side);
   if (rc) return rc;
   MACR_CUDA(cudaEventRecord(h->ev_join, side));
-  rc = launch_mark_touched(h->st, nullptr, B, h->bmU, h->bmI, side2, h->half_u, h->half_i);
+  rc = launch_mark_touched(h->st, nullptr, B, h->bmU, h->bmI, side2);
   if (rc) return rc;
   // row-partitioned: the owned rows only -- peers store into the ghost rows while this runs
   const int64_t sweep_u = h->sharded ? h->sd.u_hi - h->sd.u_lo : h->nu;
   const int64_t sweep_i = h->sharded ? h->sd.i_hi - h->sd.i_lo : h->ni;
   rc = launch_adam_sweep2(h->U, h->mU, h->vU, sweep_u, h->bmU, h->I, h->mI, h->vI, sweep_i, h->bmI,
-                          hp.lr, h->st, hp.beta1, hp.beta2, hp.eps, side2, h->half_u, h->half_i);
+                          hp.lr, h->st, hp.beta1, hp.beta2, hp.eps, side2);
   if (rc) return rc;
   MACR_CUDA(cudaEventRecord(h->ev_join2, side2));
   // main: gather (+ row snapshot) -> B x B grid (+ band folds) -> row gradients + Adam + tail
@@ -256,35 +251,18 @@ static int mf_enqueue(macr_mf_trainer *h, int B) {
     rc = launch_grid_bce(yp, yn, B, hp, g, dyp, dyn, dsp, dsn, dsu, 1, rq, h->st, nullptr, s);
   if (rc) return rc;
   MACR_CUDA(cudaStreamWaitEvent(s, h->ev_join, 0));
+  MACR_CUDA(cudaStreamWaitEvent(s, h->ev_join2, 0));
   const float lam = hp.decay / (float)hp.batch_size_flag;
+  const AdamTabs tabs{h->U, h->mU, h->vU, h->I, h->mI, h->vI, h->bmU, h->bmI,
+                      hp.beta1, hp.beta2, hp.eps, hp.lr, h->st};
   // vectors outside the mode's graph get no gradient: TF's minimize() leaves them and their slots
   const int frozen = h->mode == MACR_TRAIN_NORMALBCE ? 3 : h->mode == MACR_TRAIN_RUBIBCE ? 2 : 0;
-  if (!h->decoupled) {
-    MACR_CUDA(cudaStreamWaitEvent(s, h->ev_join2, 0));
-    const AdamTabs tabs{h->U, h->mU, h->vU, h->I, h->mI, h->vI, h->bmU, h->bmI,
-                        hp.beta1, hp.beta2, hp.eps, hp.lr, h->st};
-    const TailArgs tail{1, h->w, h->mw, h->vw, h->wu, h->mwu, h->vwu, hp, h->st, h->tail_ticket,
-                        frozen};
-    rc = launch_row_grads(h->snap, h->w, h->wu, B, dyp, dyn, dsp, dsn, dsu, lam, h->planU, h->planI,
-                          h->gU, h->gI, h->unit_part, h->gw_part, h->gwu_part, nullptr, &tabs, &tail, s);
-    if (rc) return rc;
-    h->launches = h->sharded ? 8 : 6;  // [push, barrier |] plan, mark, sweep | gather, grid, row-grads(+Adam+tail)
-    return MACR_OK;
-  }
-  // decoupled: touched rows (row gradients + their Adam) and untouched rows (the sweep) are disjoint
-  // and no bitmap bit is cleared here, so the two kernels run side by side; the step tail advances
-  // the step state the sweep's threads read, hence it waits for both
-  const AdamTabs tabs{h->U, h->mU, h->vU, h->I, h->mI, h->vI, nullptr, nullptr,
-                      hp.beta1, hp.beta2, hp.eps, hp.lr, h->st};
-  int n_part = 0;
+  const TailArgs tail{1, h->w, h->mw, h->vw, h->wu, h->mwu, h->vwu, hp, h->st, h->tail_ticket,
+                      frozen};
   rc = launch_row_grads(h->snap, h->w, h->wu, B, dyp, dyn, dsp, dsn, dsu, lam, h->planU, h->planI,
-                        h->gU, h->gI, h->unit_part, h->gw_part, h->gwu_part, &n_part, &tabs, nullptr, s);
+                        h->gU, h->gI, h->unit_part, h->gw_part, h->gwu_part, nullptr, &tabs, &tail, s);
   if (rc) return rc;
-  MACR_CUDA(cudaStreamWaitEvent(s, h->ev_join2, 0));
-  rc = launch_step_tail(h->w, h->mw, h->vw, h->wu, h->mwu, h->vwu, h->gw_part, h->gwu_part, n_part, hp,
-                        h->st, 1 | (frozen << 1), s);
-  if (rc) return rc;
-  h->launches = h->sharded ? 9 : 7;
+  h->launches = h->sharded ? 8 : 6;  // [push, barrier |] plan, mark, sweep | gather, grid, row-grads(+Adam+tail)
   return MACR_OK;
 }
 
@@ -344,17 +322,7 @@ extern "C" int macr_mf_trainer_create(macr_mf_trainer **out, float *U, float *mU
   h->nu = n_users; h->ni = n_items; h->maxB = max_batch; h->hp = *hp; h->launches = 0;
   int rc = h->alloc_common(as_stream(stream));
   if (rc) return rc;
-  size_t wu_words = (size_t)((n_users + 31) / 32), wi_words = (size_t)((n_items + 31) / 32);
-  {
-    const char *e = getenv("MACR_MF_DECOUPLE");  // developer / test knob: 0 or 1, default by size
-    h->decoupled = e ? atoi(e) != 0 : (n_users + n_items) * (int64_t)kD * 12 >= (256LL << 20);
-  }
-  if (h->decoupled) {
-    h->half_u = (long long)wu_words;
-    h->half_i = (long long)wi_words;
-    wu_words *= 2;
-    wi_words *= 2;
-  }
+  const size_t wu_words = (size_t)((n_users + 31) / 32), wi_words = (size_t)((n_items + 31) / 32);
   MACR_CUDA(cudaMalloc(&h->bmU, sizeof(uint32_t) * wu_words));
   MACR_CUDA(cudaMalloc(&h->bmI, sizeof(uint32_t) * wi_words));
   MACR_CUDA(cudaMemsetAsync(h->bmU, 0, sizeof(uint32_t) * wu_words, h->s));
@@ -502,10 +470,6 @@ extern "C" int64_t macr_mf_trainer_steps_done(const macr_mf_trainer *h) {
 }
 extern "C" int macr_mf_trainer_set_steps_done(macr_mf_trainer *h, int64_t t) {
   MACR_CHECK_ARG(h && t >= 0, "macr_mf_trainer_set_steps_done: bad argument");
-  if (h->decoupled) {  // the bitmap half in use follows the parity of t: start from clean halves
-    MACR_CUDA(cudaMemsetAsync(h->bmU, 0, sizeof(uint32_t) * 2 * (size_t)h->half_u, h->s));
-    MACR_CUDA(cudaMemsetAsync(h->bmI, 0, sizeof(uint32_t) * 2 * (size_t)h->half_i, h->s));
-  }
   return h->set_steps(t);
 }
 // ---- row-partitioned mode -------------------------------------------------------------------

@@ -157,33 +157,6 @@ def test_mf_trainer_steps(T, ops, oracle, B, steps):
     _run_mf(T, ops, oracle, 1500, 744, B, steps, 1e-3, 3.0, seed=B)
 
 
-def test_mf_trainer_decoupled_row_grads_and_sweep(T, ops, oracle, monkeypatch):
-    """Large-table structure of the step (two touched-row bitmaps alternating with the Adam step, row
-    gradients beside the dense sweep, stand-alone step tail), forced on small tables: same parity
-    bars as the default structure, incl. a resume at an odd step count (bitmap parity flips)."""
-    monkeypatch.setenv("MACR_MF_DECOUPLE", "1")
-    _run_mf(T, ops, oracle, 1500, 744, 1024, 7, 1e-3, 3.0, seed=3)
-    _run_mf(T, ops, oracle, 700, 300, 2048, 3, 1e-3, 4.0, seed=5)  # duplicate users, multi-unit segments
-    n_users, n_items, B = 900, 400, 256
-    U, I, w, wu = make_model(17, n_users, n_items, scale=3.0)
-    hp = dict(lr=1e-3, alpha=1e-2, beta=1e-3, decay=1e-5, batch_size=B)
-    st = oracle.MFState(U, I, w, wu)
-    a = ops.MFTrainer(U, I, w, wu, ops.HParams.make(**hp), max_batch=B)
-    rng = np.random.RandomState(4)
-    bt = [make_batch(rng, n_users, n_items, B) for _ in range(6)]
-    for u, p, n in bt[:3]:
-        oracle.mf_step(st, u, p, n, oracle.HParams.make(**hp))
-        a.step_device(dev(T, u), dev(T, p), dev(T, n))
-    a.set_steps_done(3)  # what a checkpoint resume does: same count, bitmaps restarted
-    for u, p, n in bt[3:]:
-        oracle.mf_step(st, u, p, n, oracle.HParams.make(**hp))
-        a.step_device(dev(T, u), dev(T, p), dev(T, n))
-    for name in ("U", "I", "mU", "vU", "mI", "vI", "w", "wu"):
-        np.testing.assert_allclose(getattr(a.tab, name).cpu().numpy(), getattr(st, name), rtol=1e-4, atol=1e-5,
-                                   err_msg=name)
-    a.close()
-
-
 def test_mf_trainer_step_host(T, ops, oracle):
     _run_mf(T, ops, oracle, 1500, 744, 512, 4, 1e-2, 3.0, seed=11, host=True)
 
