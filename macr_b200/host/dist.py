@@ -417,12 +417,22 @@ class RowShardedLGCNTrainer:
             mine = [self._ipc_u.handle, self._ipc_i.handle] + self.trainer.ipc_export()
             every = [None] * self.world
             dist.all_gather_object(every, mine, group=self.group)
-            for r, hs in enumerate(every):
-                if r == self.rank:
-                    continue
-                ptrs = [ops.IpcBuffer.open_peer(h) for h in hs]
-                self._peers += ptrs
-                pu[r], pi[r], pe[r], pt[r], pf[r] = ptrs
+            ok = 1
+            try:
+                for r, hs in enumerate(every):
+                    if r == self.rank:
+                        continue
+                    ptrs = [ops.IpcBuffer.open_peer(h) for h in hs]
+                    self._peers += ptrs
+                    pu[r], pi[r], pe[r], pt[r], pf[r] = ptrs
+            except ops.MacrError:
+                ok = 0
+            flag = torch.tensor([ok], dtype=torch.int32, device=self.dev)
+            dist.all_reduce(flag, op=dist.ReduceOp.MIN, group=self.group)
+            if int(flag.item()) != 1:  # fail on EVERY rank, so nobody is left waiting in a barrier
+                self.close()
+                raise ops.MacrError("row-partitioned LightGCN needs CUDA-IPC peer memory between the ranks "
+                                    "(cudaIpcOpenMemHandle failed on at least one rank)")
         self.trainer.shard(desc, pu, pi, pe, pt, pf)
         if self.world > 1:
             torch.cuda.synchronize(self.dev)
