@@ -120,6 +120,31 @@ int launch_peer_push(const PeerPush &p, cudaStream_t s) {
   return MACR_OK;
 }
 
+__global__ void __launch_bounds__(256)
+peer_push_batch_rows_kernel(const float *__restrict__ buf, PeerBufs peers, macr_shard_desc d,
+                            long long n_users, const StepState *__restrict__ st, int B) {
+  const int q = (blockIdx.x * blockDim.x + threadIdx.x) >> 4, hl = threadIdx.x & 15;
+  if (q >= 3 * B) return;
+  const long long id = (st->ids_base + st->step_idx * 3LL * B)[q];
+  const bool is_user = q < B;
+  const bool own = is_user ? (id >= d.u_lo && id < d.u_hi) : (id >= d.i_lo && id < d.i_hi);
+  if (!own) return;
+  const long long off = (id + (is_user ? 0 : n_users)) * kD;
+  const float4 v = reinterpret_cast<const float4 *>(buf + off)[hl];
+#pragma unroll 1
+  for (int r = 0; r < d.world; ++r)
+    if (r != d.rank) st_stream(reinterpret_cast<float4 *>(peers.p[r] + off) + hl, v);
+}
+
+int launch_peer_push_batch_rows(const float *buf, const PeerBufs &peers, const macr_shard_desc &desc,
+                                long long n_users, const StepState *st, int B, cudaStream_t s) {
+  if (desc.world <= 1) return MACR_OK;
+  peer_push_batch_rows_kernel<<<(unsigned)((3LL * B * 16 + 255) / 256), 256, 0, s>>>(buf, peers, desc,
+                                                                                      n_users, st, B);
+  MACR_LAUNCH_CHECK();
+  return MACR_OK;
+}
+
 __global__ void peer_barrier_dev_kernel(PeerFlagsDev f, unsigned long long *epoch_ctr, int rank,
                                         int world, long long spin_limit, int *err) {
   const int r = threadIdx.x;

@@ -28,6 +28,15 @@ struct StepState;
 int launch_shard_push_st(const float *U_local, const float *I_local, const macr_shard_desc &desc,
                          const StepState *st, int B, const PeerGhosts &peers, cudaStream_t s);
 
+// the batch's rows only: for each of the step's 3B ids (users | pos | neg, read from the step state)
+// whose node row this rank owns, the row of `buf` ([N][64], node rows = users then items) is stored
+// to the same row of every peer's buffer -- what a training step reads of the layer mean
+struct PeerBufs {
+  float *p[kMaxRanks];
+};
+int launch_peer_push_batch_rows(const float *buf, const PeerBufs &peers, const macr_shard_desc &desc,
+                                long long n_users, const StepState *st, int B, cudaStream_t s);
+
 // flag barrier over peer memory whose epoch lives on the device (so it can sit in a CUDA graph):
 // *epoch_ctr is incremented by one per call; flags[r] = rank r's uint64[kMaxRanks] arrival flags
 struct PeerFlagsDev {

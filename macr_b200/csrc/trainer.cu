@@ -608,7 +608,7 @@ static int lgcn_exchange(macr_lgcn_trainer *h, int which, cudaStream_t s) {
 // batch_rows (nullable): the training step reads E_mean at the batch's rows only, so the LAST layer
 // is computed for those rows alone (E_mean's other rows are left stale: emb_dirty stays set).
 static int lgcn_forward(macr_lgcn_trainer *h, cudaStream_t s, int *launches,
-                        const uint32_t *batch_rows = nullptr) {
+                        const uint32_t *batch_rows = nullptr, int B = 0) {
   const int per_spmm = h->plan.n_multi ? 2 : 1;
   if (!h->sharded && (batch_rows == nullptr || h->L == 0)) {
     if (launches) *launches += h->L * per_spmm;
@@ -640,7 +640,16 @@ static int lgcn_forward(macr_lgcn_trainer *h, cudaStream_t s, int *launches,
     }
   }
   if (launches) *launches += h->L * per_spmm + (h->sharded ? 2 * (h->L + 1) : 0);
-  return h->sharded ? lgcn_exchange(h, XCH_EMEAN, s) : MACR_OK;
+  if (!h->sharded) return MACR_OK;
+  if (batch_rows == nullptr) return lgcn_exchange(h, XCH_EMEAN, s);
+  // training step: only the batch's rows of the layer mean were computed and only they are read
+  // on the other ranks -- 3B rows (<= 6 MB) instead of the owned range of an [N][64] buffer
+  PeerBufs pe{};
+  for (int r = 0; r < h->sd.world; ++r) pe.p[r] = r == h->sd.rank ? nullptr : h->peerE[r];
+  rc = launch_peer_push_batch_rows(h->Emean, pe, h->sd, h->nu, h->st, B, s);
+  if (rc) return rc;
+  return launch_peer_barrier_dev(h->peerF, h->flags + 16, reinterpret_cast<int *>(h->flags + 17),
+                                 h->sd.rank, h->sd.world, s);
 }
 
 static int lgcn_enqueue_impl(macr_lgcn_trainer *h, int B, int train) {
@@ -673,7 +682,7 @@ static int lgcn_enqueue_impl(macr_lgcn_trainer *h, int B, int train) {
     launches += 2;
     MACR_CUDA(cudaStreamWaitEvent(s, h->ev_join2, 0));  // a few microseconds of work, long done
   }
-  rc = lgcn_forward(h, s, &launches, train ? h->need_bm : nullptr);
+  rc = lgcn_forward(h, s, &launches, train ? h->need_bm : nullptr, B);
   if (rc) return rc;
   rc = launch_gather_dots(Ue, Ie, h->U, h->I, h->w, h->wu, nullptr, nullptr, nullptr, h->st, B, yp,
                           yn, sp, sn, su, rq, h->snap, &g, s);
