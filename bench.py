@@ -793,6 +793,10 @@ def gowalla_block(cx, K, W, with_cpu):
                         "step": {"bytes_per_step": step_bytes, "frac": step_bytes / (ms_step * 1e-3) / 1e9 / pk,
                                  "note": "whole step vs its HBM floor; the BxB grid is MUFU-bound (floor 14.4 us)"}}}
     out["scoring"] = gowalla_scoring(cx)
+    try:  # BASELINE configs[3] shape: ml_10m, 13 878 test users x 8 790 items, ~71 train items per user
+        out["scoring_ml10m_shape"] = shape_scoring(cx, 69166, 8790, 13878, 71)
+    except Exception as e:  # noqa: BLE001
+        out["scoring_ml10m_shape"] = {"unavailable": f"{type(e).__name__}: {e}"}
     try:
         out["cli_epoch"] = gowalla_cli_epoch(cx)
     except Exception as e:  # noqa: BLE001 -- a secondary block never takes the line down
@@ -869,18 +873,18 @@ def gowalla_cli_epoch(cx):
                     "the sampler (single thread, sequential MT19937 stream consumed word for word) is the bound"}
 
 
-def gowalla_scoring(cx, reps=10):
+def shape_scoring(cx, n_users, n_items, T_q, mask_avg, reps=10):
+    """Masked full-catalogue top-20 at one of the reference's data-set shapes (one GPU)."""
     torch = cx.torch
     dev = cx.dev
     from macr_b200 import ops
 
-    T_q = N_TEST_USERS
-    Us, Is, ws_, wus = synth_model(777)
+    Us, Is, ws_, wus = synth_model(777, n_users, n_items)
     Us *= 10
     Is *= 10
     dU, dI = torch.from_numpy(Us).to(dev), torch.from_numpy(Is).to(dev)
-    q = torch.from_numpy(np.random.RandomState(5).permutation(N_USERS)[:T_q].astype(np.int32)).to(dev)
-    mrp, mcol = synth_mask(9, T_q, 27)
+    q = torch.from_numpy(np.random.RandomState(5).permutation(n_users)[:T_q].astype(np.int32)).to(dev)
+    mrp, mcol = synth_mask(9, T_q, mask_avg, n_items)
     dmrp, dmcol = torch.from_numpy(mrp).to(dev), torch.from_numpy(mcol).to(dev)
     dw, dwu = torch.from_numpy(ws_).to(dev), torch.from_numpy(wus).to(dev)
     sig_i = ops.score_gates(dI, dw)
@@ -906,15 +910,19 @@ def gowalla_scoring(cx, reps=10):
     Uq = ops.gather_rows(dU, q)
     ops.score_topk_tc(Uq, dI, sig_i, ops.score_gates(Uq, dwu), 40.0, dmrp, dmcol, TOPK, stats=stats)
     st = stats.cpu().tolist()
-    flops = 2.0 * D * T_q * N_ITEMS
+    flops = 2.0 * D * T_q * n_items
     pk = cx.peaks["bf16_tflops"]
-    return {"metric": "full_catalog_scores_per_sec", "value": T_q * N_ITEMS / t_sc, "unit": "scores/s",
-            "ms_per_eval": 1e3 * t_sc, "test_users": T_q, "items": N_ITEMS, "topk": TOPK,
+    return {"metric": "full_catalog_scores_per_sec", "value": T_q * n_items / t_sc, "unit": "scores/s",
+            "ms_per_eval": 1e3 * t_sc, "test_users": T_q, "items": n_items, "topk": TOPK,
             "rows_redone_by_exact_kernel": st[0], "candidates_per_row": st[1] / max(1, T_q - st[0]),
             "roofline": {"bound": "tensor", "achieved": flops / t_sc / 1e12, "peak": pk, "unit": "TFLOP/s",
                          "frac": flops / t_sc / 1e12 / pk, "note": "algorithmic flops 2*64*T*I, whole call"},
             "checksum": int(ids.to(torch.int64).sum().item()),
             "exact_fp32_kernel": {"ms_per_eval": 1e3 * t_ex, "checksum": int(eids.to(torch.int64).sum().item())}}
+
+
+def gowalla_scoring(cx, reps=10):
+    return shape_scoring(cx, N_USERS, N_ITEMS, N_TEST_USERS, 27, reps)
 
 
 def main():
