@@ -4,6 +4,7 @@ sampler / train threads, the same test-loss pass and early stopping, same log li
 Only `--alg_type lightgcn --loss bceboth` (with `--test rubiboth` or `--test normal`) is
 implemented."""
 import logging
+from concurrent.futures import ThreadPoolExecutor
 import os
 import random
 import sys
@@ -152,25 +153,49 @@ def main(argv=None, tune=False):
     cur_best_pre_0, stopping_step, should_stop = 0.0, 0, False
     best_epoch, ret = 0, None
     config["best_c_hr"], config["best_c_epoch"] = 0, 0
+    n_batch = data_generator.n_train // args.batch_size + 1
+    stepwise = os.environ.get("MACR_STEPWISE") == "1"
+    # Epoch path (default): the reference draws n_batch + 1 train batches per epoch (the last one is
+    # sampled by the look-ahead thread and never used, LightGCN.py:762-777) and, at logging epochs,
+    # n_batch + 1 test batches -- in that order, from streams nothing else touches.  One native call
+    # draws them all (worker thread, one epoch ahead of the device), one call trains the epoch, one
+    # call runs the loss-only pass: same triples, same steps, same loss sums as the per-step loop
+    # (MACR_STEPWISE=1 keeps that loop: one sampler thread + one train thread per step).
+    sampler_pool = None if stepwise else ThreadPoolExecutor(max_workers=1)
+
+    def sample_job(ep):
+        tr = data_generator.sample_epoch(n_batch + 1)
+        te = data_generator.sample_test_epoch(n_batch + 1) if ep % args.log_interval == 0 else None
+        return tr, te, (random.getstate(), np.random.get_state())
+
+    pending = None if stepwise else sampler_pool.submit(sample_job, 1)
+    rng_after, test_batches = None, None
     for epoch in range(1, args.epoch + 1):
         t1 = time()
         loss, mf_loss, emb_loss, reg_loss = 0.0, 0.0, 0.0, 0.0
-        n_batch = data_generator.n_train // args.batch_size + 1
-        sample_last = _Worker(data_generator.sample)
-        sample_last.start()
-        sample_last.join()
-        for _ in range(n_batch):  # sampler for step t+1 overlaps the device step t (:762-777)
-            triple = sample_last.result()
-            train_cur = _Worker(lambda tr=triple: run_on(train_fetch, tr))
-            sample_next = _Worker(data_generator.sample)
-            train_cur.start()
-            sample_next.start()
-            sample_next.join()
-            _, batch_loss, batch_mf_loss, batch_emb_loss, _ = train_cur.result()
-            sample_last = sample_next
-            loss += batch_loss / n_batch
-            mf_loss += batch_mf_loss / n_batch
-            emb_loss += batch_emb_loss / n_batch
+        if not stepwise:
+            train_batches, test_batches, rng_after = pending.result()
+            pending = sampler_pool.submit(sample_job, epoch + 1) if epoch < args.epoch else None
+            for bl in model.run_epoch(train_batches[:n_batch], args.loss, train=True):
+                loss += float(bl[0]) / n_batch
+                mf_loss += float(bl[1]) / n_batch
+                emb_loss += float(bl[2]) / n_batch
+        else:
+            sample_last = _Worker(data_generator.sample)
+            sample_last.start()
+            sample_last.join()
+            for _ in range(n_batch):  # sampler for step t+1 overlaps the device step t (:762-777)
+                triple = sample_last.result()
+                train_cur = _Worker(lambda tr=triple: run_on(train_fetch, tr))
+                sample_next = _Worker(data_generator.sample)
+                train_cur.start()
+                sample_next.start()
+                sample_next.join()
+                _, batch_loss, batch_mf_loss, batch_emb_loss, _ = train_cur.result()
+                sample_last = sample_next
+                loss += batch_loss / n_batch
+                mf_loss += batch_mf_loss / n_batch
+                emb_loss += batch_emb_loss / n_batch
         if np.isnan(loss):
             print("ERROR: loss is nan.")
             sys.exit()
@@ -183,21 +208,27 @@ def main(argv=None, tune=False):
 
         # test loss: n_batch loss-only steps on sample_test() triples (:799-819; consumes RNG)
         loss_test, mf_loss_test, emb_loss_test, reg_loss_test = 0.0, 0.0, 0.0, 0.0
-        sample_last = _Worker(data_generator.sample_test)
-        sample_last.start()
-        sample_last.join()
-        for _ in range(n_batch):
-            triple = sample_last.result()
-            train_cur = _Worker(lambda tr=triple: run_on(test_fetch, tr))
-            sample_next = _Worker(data_generator.sample_test)
-            train_cur.start()
-            sample_next.start()
-            sample_next.join()
-            bl, bm, be = train_cur.result()
-            sample_last = sample_next
-            loss_test += bl / n_batch
-            mf_loss_test += bm / n_batch
-            emb_loss_test += be / n_batch
+        if not stepwise:
+            for bl in model.run_epoch(test_batches[:n_batch], args.loss, train=False):
+                loss_test += float(bl[0]) / n_batch
+                mf_loss_test += float(bl[1]) / n_batch
+                emb_loss_test += float(bl[2]) / n_batch
+        else:
+            sample_last = _Worker(data_generator.sample_test)
+            sample_last.start()
+            sample_last.join()
+            for _ in range(n_batch):
+                triple = sample_last.result()
+                train_cur = _Worker(lambda tr=triple: run_on(test_fetch, tr))
+                sample_next = _Worker(data_generator.sample_test)
+                train_cur.start()
+                sample_next.start()
+                sample_next.join()
+                bl, bm, be = train_cur.result()
+                sample_last = sample_next
+                loss_test += bl / n_batch
+                mf_loss_test += bm / n_batch
+                emb_loss_test += be / n_batch
 
         t2 = time()
         users_to_test = list(data_generator.test_set.keys())
@@ -251,13 +282,17 @@ def main(argv=None, tune=False):
             best_epoch = epoch
         if args.save_flag == 1:
             checkpoint.save(weights_save_path + "/weights_{}-{}.npz".format(args.saveID, epoch), model,
-                            {"epoch": epoch})
+                            {"epoch": epoch}, rng_state=rng_after)
             print("save the weights in path: ", weights_save_path)
         if should_stop and args.early_stop == 1:
             if args.save_flag == 1:
                 with open(weights_save_path + "/best_epoch_{}.txt".format(args.saveID), "w") as f:
                     f.write(str(config["best_c_epoch"] if args.test != "normal" else best_epoch))
             break
+    if pending is not None:  # early stop: let the speculative draw of the next epoch finish
+        pending.result()
+    if sampler_pool is not None:
+        sampler_pool.shutdown()
     model.close()
     return {"best_epoch": best_epoch, "best_hr": cur_best_pre_0, "last": ret}
 

@@ -181,14 +181,27 @@ class Data:
         3.11; list(keys) draws the same stream."""
         from . import native_sampler as ns
 
+        self._build_test_csr()
+        u, p, n = ns.sample_lgcn(self._ns_test_pop, self.n_users, self.n_items, self._ns_test,
+                                 self._ns_test_ban, self.batch_size)
+        return u.tolist(), p.tolist(), n.tolist()
+
+    def _build_test_csr(self):
+        from . import native_sampler as ns
+
         if getattr(self, "_ns_test", None) is None:
             self._ns_test = ns.ListCSR(self.test_set, self.n_users)
             both = {u: list(set(v) | set(self.train_items.get(u, ()))) for u, v in self.test_set.items()}
             self._ns_test_ban = ns.ListCSR(both, self.n_users)
             self._ns_test_pop = np.asarray(list(self.test_set.keys()), np.int32)
-        u, p, n = ns.sample_lgcn(self._ns_test_pop, self.n_users, self.n_items, self._ns_test,
-                                 self._ns_test_ban, self.batch_size)
-        return u.tolist(), p.tolist(), n.tolist()
+
+    def sample_test_epoch(self, n_batches, out=None):
+        """`n_batches` consecutive sample_test() calls -> int32 [n_batches, 3, B]."""
+        from . import native_sampler as ns
+
+        self._build_test_csr()
+        return ns.sample_lgcn_epoch(self._ns_test_pop, self.n_users, self.n_items, self._ns_test,
+                                    self._ns_test_ban, self.batch_size, n_batches, out)
 
     def sample_test_py(self):
         B = self.batch_size

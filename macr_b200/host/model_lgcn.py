@@ -107,6 +107,24 @@ class LightGCN(_ScoringMixin):
         with torch.cuda.device(self.dev):
             return self.trainer.step_host(users, pos_items, neg_items, train=train)
 
+    _MODE_OF_LOSS = {"bceboth": ops.LGCNTrainer.RUBIBCEBOTH, "bce": ops.LGCNTrainer.NORMALBCE,
+                     "bce1": ops.LGCNTrainer.RUBIBCE}
+
+    def run_epoch(self, batches, loss="bceboth", train=True):
+        """`batches` int32 [n,3,B] on the host (e.g. `Data.sample_epoch`) -> float32 [n,4] host losses
+        {loss, mf_loss, emb_loss, L_ori}: n `sess.run` fetches of the `--loss` graph as ONE call (one
+        H2D, n step graphs, one D2H); train=False is the loss-only pass of LightGCN.py:799-819."""
+        mode = self._MODE_OF_LOSS[loss]
+        if getattr(self, "_mode", ops.LGCNTrainer.RUBIBCEBOTH) != mode:
+            self.trainer.set_mode(mode)
+            self._mode = mode
+        b = torch.as_tensor(np.ascontiguousarray(batches, dtype=np.int32))
+        if getattr(self, "_pin", None) is None or self._pin.shape != b.shape:
+            self._pin = torch.empty(b.shape, dtype=torch.int32).pin_memory()
+        self._pin.copy_(b)
+        with torch.cuda.device(self.dev):
+            return self.trainer._run_host_train(self._pin, train)
+
     def _score_tables(self):
         with torch.cuda.device(self.dev):
             ue, ie = self.trainer.embeddings()  # propagated once per parameter version

@@ -479,6 +479,15 @@ class LGCNTrainer:
                              C.c_void_p(losses_host.data_ptr())), "trainer_run_host")
         return losses_host
 
+    def _run_host_train(self, batches_host, train=True):
+        """run_host with the train / loss-only switch -> float32 [n,4] numpy losses."""
+        n, three, B = batches_host.shape
+        assert three == 3 and batches_host.dtype == torch.int32 and not batches_host.is_cuda
+        losses_host = torch.empty((n, 4), dtype=torch.float32)
+        check(self._run_host(n, B, C.c_void_p(batches_host.data_ptr()), C.c_void_p(losses_host.data_ptr()),
+                             train), "macr_lgcn_trainer_run_host")
+        return losses_host.numpy()
+
     # ---- row-partitioned mode (include/macr_b200.h: macr_lgcn_trainer_shard) ----
     def ipc_export(self):
         """IPC handles of the trainer's {E_mean, layer buffers, flags}: 3 x 64 bytes."""

@@ -239,6 +239,30 @@ def test_mf_cli_pipelined_sampler_equals_the_stepwise_loop(tmp_path, monkeypatch
     np.testing.assert_array_equal(z["py_random_key"], np.asarray(random.getstate()[1], np.uint32))
 
 
+def test_lgcn_cli_epoch_path_equals_the_stepwise_thread_loop(tmp_path, monkeypatch, capsys):
+    """The LightGCN CLI draws an epoch's n_batch + 1 train batches (and, at logging epochs, the
+    n_batch + 1 test batches) in one native call on a worker thread and runs the epoch / the
+    loss-only pass as one call each: it must print what the reference's per-step sampler-thread /
+    train-thread loop prints (LightGCN.py:762-819, MACR_STEPWISE=1) and end on the same metrics."""
+    from macr_b200.cli import lightgcn
+
+    monkeypatch.chdir(tmp_path)
+    argv = ["--data_path", GOLD + "/", "--dataset", "tiny", "--batch_size", "32", "--epoch", "4", "--log_interval", "2",
+            "--layer_size", "[64,64]", "--Ks", "[20]", "--loss", "bceboth", "--test", "normal", "--lr", "0.001",
+            "--verbose", "1", "--save_flag", "0", "--weights_path", str(tmp_path) + "/"]
+    a = lightgcn.main(argv)
+    out_a = [l for l in capsys.readouterr().out.splitlines() if "train==" in l or "test==" in l]
+    monkeypatch.setenv("MACR_STEPWISE", "1")
+    b = lightgcn.main(argv)
+    out_b = [l for l in capsys.readouterr().out.splitlines() if "train==" in l or "test==" in l]
+    monkeypatch.delenv("MACR_STEPWISE")
+    strip = lambda l: l.split("]: ", 1)[1]  # drop the wall-clock prefix
+    assert len(out_a) == 4 and [strip(l) for l in out_a] == [strip(l) for l in out_b]
+    assert a["best_hr"] == b["best_hr"] and a["best_epoch"] == b["best_epoch"]
+    for k in ("recall", "hr", "ndcg"):
+        np.testing.assert_array_equal(a["last"][k], b["last"][k])
+
+
 def test_cli_drivers_run_end_to_end(tmp_path, monkeypatch, capsys):
     from macr_b200.cli import lightgcn, train_mf
 
