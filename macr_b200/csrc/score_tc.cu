@@ -796,15 +796,18 @@ rerank_kernel(const float *__restrict__ Uq, int T, const float *__restrict__ It,
   // ---- (1) cut on the approximate scores ----
   uint32_t key[kLoad];
   int gidv[kLoad];
+  const int nload = (total + 31) >> 5;  // warp-uniform: lists are ~K * stride long, 3 of the 8 rounds
 #pragma unroll
   for (int r = 0; r < kLoad; ++r) {
-    const int e = r * 32 + lane;
     key[r] = 0u;
     gidv[r] = 0;
-    if (e < total) {
-      const uint2 cv = cand[(size_t)t * kCap + e];
-      key[r] = fkey(__uint_as_float(cv.x));
-      gidv[r] = (int)cv.y;
+    if (r < nload) {
+      const int e = r * 32 + lane;
+      if (e < total) {
+        const uint2 cv = cand[(size_t)t * kCap + e];
+        key[r] = fkey(__uint_as_float(cv.x));
+        gidv[r] = (int)cv.y;
+      }
     }
   }
   uint32_t cut = 1u;  // fewer than K candidates (fewer than K unmasked items exist): keep all
@@ -819,6 +822,7 @@ rerank_kernel(const float *__restrict__ Uq, int T, const float *__restrict__ It,
   int n_keep = 0;
 #pragma unroll
   for (int r = 0; r < kLoad; ++r) {
+    if (r >= nload) break;  // warp-uniform
     const bool keep = key[r] >= cut && key[r] != 0u;
     const unsigned bal = __ballot_sync(0xffffffffu, keep);
     const int pos = n_keep + __popc(bal & ((1u << lane) - 1u));
