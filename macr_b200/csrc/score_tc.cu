@@ -10,7 +10,7 @@
 // the pass itself (half an instruction per score).  Instead:
 //   prep         items: bf16(sig_i * I_i) and the three bf16 pieces of -c*sig_i as an augmented K
 //                step (rows padded to whole tiles with -inf there); users: bf16(U), |u|.
-//   pass MAX     over a SAMPLE of the item tiles (every `stride`-th tile, stride <= 4): per row and
+//   pass MAX     over a SAMPLE of the item tiles (every `stride`-th tile, stride <= 4 by catalogue size): per row and
 //                item chunk, 32 running maxima of the approximate score -- one per (32-column batch
 //                position, column residue mod 4) -- kept in registers, train items of the row left
 //                out.  The groups are disjoint item sets, so nothing but 128 bytes per (row, chunk)
@@ -978,7 +978,18 @@ static Plan make_plan(int T, long long n_items, int K) {
   // the maxima pass visits every stride-th tile: the threshold then sits near rank K * stride of
   // the row instead of K (that many candidates reach the re-rank's approximate cut), for 1/stride
   // of a pass; small catalogues keep enough sampled batches for tight group maxima
-  p.stride = p.n_itiles >= 32 * kMaxStride ? kMaxStride : p.n_itiles >= 64 ? 2 : 1;
+  // measured (profiles/r2s_stride.txt): 15 424 x 40 981 (161 tiles): 0.351 / 0.317 / 0.303 / 0.320 ms at stride
+  // 1 / 2 / 3 / 4 (a looser threshold makes more warps take the filter pass's append path);
+  // 262 144 x 1 M (3907 tiles): 52.2 ms at stride 2, 43.9 ms at stride 4
+  p.stride = p.n_itiles >= 256 ? kMaxStride : p.n_itiles >= 96 ? 3 : p.n_itiles >= 64 ? 2 : 1;
+  {
+    static int env_stride = -1;
+    if (env_stride < 0) {
+      const char *e = getenv("MACR_TC_STRIDE");  // developer knob
+      env_stride = e ? atoi(e) : 0;
+    }
+    if (env_stride >= 1 && env_stride <= kMaxStride) p.stride = env_stride;
+  }
   p.n_stiles = (p.n_itiles + p.stride - 1) / p.stride;
   // row blocks: group maxima + candidate lists at most ~2 GiB per block, and blocks of equal size
   // (a short trailing block would leave most SMs idle for a whole pass over the catalogue)
