@@ -60,6 +60,9 @@ shard_exchange_kernel(const float *__restrict__ U, const float *__restrict__ I, 
       float *dst = is_user ? peers.u[r] : peers.i[r];
       st_stream(reinterpret_cast<float4 *>(dst + ghost * kD) + hl, v);
     }
+    // the peer stores of this thread are performed system-wide before it retires: the flag of
+    // the barrier kernel that follows in the stream is then never seen ahead of the rows
+    __threadfence_system();
   } else {
     reinterpret_cast<float4 *>(ex + (long long)q * kD)[hl] = own ? *src : make_float4(0.f, 0.f, 0.f, 0.f);
   }
@@ -107,6 +110,7 @@ peer_push_kernel(PeerPush p) {
     for (int r = 0; r < p.world; ++r)
       if (r != p.rank) st_stream(reinterpret_cast<float4 *>(p.dst[k][r]) + off, v);
   }
+  __threadfence_system();  // see shard_exchange_kernel
 }
 
 int launch_peer_push(const PeerPush &p, cudaStream_t s) {
@@ -134,6 +138,7 @@ peer_push_batch_rows_kernel(const float *__restrict__ buf, PeerBufs peers, macr_
 #pragma unroll 1
   for (int r = 0; r < d.world; ++r)
     if (r != d.rank) st_stream(reinterpret_cast<float4 *>(peers.p[r] + off) + hl, v);
+  __threadfence_system();  // see shard_exchange_kernel
 }
 
 int launch_peer_push_batch_rows(const float *buf, const PeerBufs &peers, const macr_shard_desc &desc,

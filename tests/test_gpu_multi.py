@@ -24,6 +24,27 @@ N_USERS, N_ITEMS, B, STEPS = 2001, 4745, 512, 6
 HP = dict(lr=1e-2, alpha=1e-2, beta=1e-3, decay=1e-4, batch_size=B)
 
 
+def _spawn(fn, args, world, out_dir):
+    """mp.spawn with the workers' tracebacks kept: a failing rank writes `fail_rank<r>.txt`."""
+    try:
+        mp.spawn(_guard, args=(fn, out_dir) + args, nprocs=world, join=True)
+    except Exception as e:  # noqa: BLE001
+        logs = "".join(open(os.path.join(out_dir, f)).read() for f in sorted(os.listdir(out_dir))
+                       if f.startswith("fail_rank"))
+        raise AssertionError(f"a worker failed: {e}\n{logs}") from e
+
+
+def _guard(rank, fn, out_dir, *args):
+    import traceback
+
+    try:
+        fn(rank, *args)
+    except BaseException:
+        with open(os.path.join(out_dir, f"fail_rank{rank}.txt"), "w") as f:
+            f.write(f"--- rank {rank} ---\n" + traceback.format_exc())
+        raise
+
+
 def _n_gpus():
     return torch.cuda.device_count() if torch.cuda.is_available() else 0
 
@@ -77,7 +98,7 @@ def test_row_sharded_training_over_nccl_equals_single_gpu(tmp_path, exchange):
     from macr_b200 import ops
 
     world = min(_n_gpus(), 4)
-    mp.spawn(_train_worker, args=(world, _free_port(), str(tmp_path), exchange), nprocs=world, join=True)
+    _spawn(_train_worker, (world, _free_port(), str(tmp_path), exchange), world, str(tmp_path))
     U, I, w, wu = make_model(71, N_USERS, N_ITEMS, scale=4.0)
     tr = ops.MFTrainer(U, I, w, wu, ops.HParams.make(**HP), max_batch=B)
     want = []
@@ -149,7 +170,7 @@ def test_row_partitioned_lightgcn_equals_single_gpu(tmp_path):
     from macr_b200 import ops
 
     world = min(_n_gpus(), 4)
-    mp.spawn(_lgcn_worker, args=(world, _free_port(), str(tmp_path)), nprocs=world, join=True)
+    _spawn(_lgcn_worker, (world, _free_port(), str(tmp_path)), world, str(tmp_path))
     rowptr, col, val, U, I, w, wu, batches = _lg_inputs()
     tr = ops.LGCNTrainer(rowptr, col, val, U, I, w, wu, LG_L, ops.HParams.make(**LG_HP), max_batch=LG_B)
     db = torch.from_numpy(batches).cuda()
@@ -215,7 +236,7 @@ def test_sharded_scoring_over_nccl_equals_unsharded(tmp_path):
     from macr_b200 import ops
 
     world = min(_n_gpus(), 4)
-    mp.spawn(_score_worker, args=(world, _free_port(), str(tmp_path)), nprocs=world, join=True)
+    _spawn(_score_worker, (world, _free_port(), str(tmp_path)), world, str(tmp_path))
     U, I, w, wu, rp, col = _score_inputs()
     to = lambda a: torch.from_numpy(a).cuda()
     dU, dI = to(U), to(I)
