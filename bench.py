@@ -553,8 +553,12 @@ def sharded_scoring(cx, reps=3):
     out = {"metric": "full_catalog_scores_per_sec", "value": T * n_items / t, "unit": "scores/s",
            "ms_per_eval": 1e3 * t, "ms_local_scoring": 1e3 * t_local, "query_users": T, "items": n_items,
            "topk": TOPK, "sharding": f"items/{cx.world}", "scaling": "strong",
-           "exchange": "all-gather of the [T,K] (id, score) candidates + on-device K-way merge, inside the timed region",
-           "exchange_bytes_per_rank": T * TOPK * 8,
+           "exchange": {"p2p": "ONE kernel over NVLink peer memory: rank j merges rows [jT/N,(j+1)T/N) reading every "
+                               "shard's candidates from the peers' buffers and stores the merged rows into every rank's "
+                               "result (all-to-all + K-way merge + all-gather fused), two flag barriers; inside the timed region",
+                        "nccl": "all-to-all of row blocks + on-device K-way merge + all-gather over NCCL, inside the timed region",
+                        "none": "single shard"}[sc.exchange],
+           "exchange_kind": sc.exchange, "exchange_bytes_per_rank": T * TOPK * 8,
            "rows_redone_by_exact_kernel_rank0": st[0], "candidates_per_row_rank0": st[1] / max(1, T - st[0]),
            "roofline": {"bound": "tensor", "achieved": flops / t / 1e12, "peak": pk * cx.world,
                         "peak_kind": cx.peak_kind, "unit": "TFLOP/s", "frac": flops / t / 1e12 / (pk * cx.world),
@@ -572,6 +576,8 @@ def sharded_scoring(cx, reps=3):
                                       40.0, sub_rp, sub_col, TOPK)
         out["spot_parity_vs_exact_fp32_kernel"] = bool((ei == ids[sel.long()]).all().item()
                                                        and (es == scs[sel.long()]).all().item())
+    sc.check_peers()
+    sc.close()
     del sc, Uq
     torch.cuda.empty_cache()
     return out

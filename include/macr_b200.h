@@ -434,6 +434,17 @@ int macr_lgcn_trainer_shard(macr_lgcn_trainer *h, const macr_shard_desc *desc,
                             float *const *peer_U, float *const *peer_I, float *const *peer_Emean,
                             float *const *peer_tmp, uint64_t *const *peer_flags);
 int macr_lgcn_trainer_peer_error(macr_lgcn_trainer *h, int *err_out);
+/* Item-partitioned scoring (SURVEY.md 8e row "full-catalogue scoring"): exchange + merge of the
+ * shards' [T][K] candidate lists in ONE kernel over NVLink peer memory.  This rank merges the
+ * query rows [row0, row0 + rows): cand_*_host[r] = rank r's candidate buffers ([T][K], ids global,
+ * lists sorted and padded with -1 / -inf) as mapped in THIS process (macr_ipc_open; own buffers for
+ * r == rank), out_*_host[r] = rank r's result buffers: the merged rows are stored into all of them.
+ * Same order rule as macr_topk_merge (score desc, lower id first; shards in rank order), so the
+ * result equals the unsharded call bit for bit.  Bracket it with two macr_shard_barrier calls
+ * (candidates of every rank complete / merged rows landed everywhere). */
+int macr_topk_merge_peers(const int32_t *const *cand_ids_host, const float *const *cand_scores_host,
+                          int32_t *const *out_ids_host, float *const *out_scores_host, int world,
+                          int K, int row0, int rows, macr_stream_t stream);
 int macr_ipc_alloc(size_t bytes, void **dev_ptr, unsigned char handle_out[MACR_IPC_HANDLE_BYTES]);
 int macr_ipc_open(const unsigned char handle[MACR_IPC_HANDLE_BYTES], void **peer_ptr);
 int macr_ipc_close(void *peer_ptr);

@@ -109,6 +109,7 @@ PROTOTYPES = {
     "macr_lgcn_trainer_ipc_export": (i32, [vp, C.c_char_p]),
     "macr_lgcn_trainer_shard": (i32, [vp, C.POINTER(ShardDesc)] + [C.POINTER(vp)] * 5),
     "macr_lgcn_trainer_peer_error": (i32, [vp, C.POINTER(i32)]),
+    "macr_topk_merge_peers": (i32, [C.POINTER(vp)] * 4 + [i32, i32, i32, i32, vp]),
     "macr_ipc_alloc": (i32, [sz, C.POINTER(vp), C.c_char_p]),
     "macr_ipc_open": (i32, [C.c_char_p, C.POINTER(vp)]),
     "macr_ipc_close": (i32, [vp]),

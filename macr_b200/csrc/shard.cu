@@ -20,6 +20,7 @@
 //     runs step t (it cannot reach t+2 before this rank has passed barrier t+1).
 //   * pack (for an NCCL all-reduce by the caller): owned rows -> ex[3B][64], zeros elsewhere;
 //     after the sum macr_shard_unpack copies ex into the ghost slots.
+#include "score.cuh"
 #include "shard.cuh"
 #include "train_kernels.cuh"
 
@@ -183,6 +184,66 @@ int launch_peer_barrier_dev(const PeerFlagsDev &f, unsigned long long *epoch_ctr
   return MACR_OK;
 }
 
+// ---- item-partitioned scoring: exchange + merge of the shards' candidates in ONE kernel ----------
+// Rank j owns the query rows [row0, row0 + rows).  For each of them a warp reads the K candidates of
+// every shard straight from that shard's buffer (peer loads over NVLink, shard order = rank order,
+// the order rule of topk_merge_kernel), merges them and stores the merged row into the result
+// buffer of EVERY rank (peer stores): all-to-all, K-way merge and all-gather without a staging
+// buffer.  The caller brackets it with two flag barriers (candidates complete / results landed).
+struct MergePeers {
+  const int32_t *ids[kMaxRanks];
+  const float *sc[kMaxRanks];
+  int32_t *out_ids[kMaxRanks];
+  float *out_sc[kMaxRanks];
+  int world;
+};
+
+__global__ void __launch_bounds__(256)
+topk_merge_peers_kernel(MergePeers p, int row0, int rows, int K) {
+  const int lane = threadIdx.x & 31;
+  const int w = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (w >= rows) return;
+  const long long base = (long long)(row0 + w) * K;
+  const unsigned kmask = (K >= 32) ? 0xffffffffu : ((1u << K) - 1u);
+  float ls = -INFINITY;
+  int li = 0x7fffffff;
+  float s[kMaxRanks];
+  int id[kMaxRanks];
+#pragma unroll
+  for (int g = 0; g < kMaxRanks; ++g) {  // all peer loads in flight before the first merge step
+    s[g] = -INFINITY;
+    id[g] = -1;
+    if (g < p.world && lane < K) {
+      s[g] = p.sc[g][base + lane];
+      id[g] = p.ids[g][base + lane];
+    }
+  }
+#pragma unroll
+  for (int g = 0; g < kMaxRanks; ++g) {
+    if (g >= p.world) break;
+    for (int k = 0; k < K; ++k) {
+      const float cs = __shfl_sync(0xffffffffu, s[g], k);
+      const int cid = __shfl_sync(0xffffffffu, id[g], k);
+      if (cid < 0) break;  // lists are padded at the tail
+      const float ws = __shfl_sync(0xffffffffu, ls, K - 1);
+      const int wi = __shfl_sync(0xffffffffu, li, K - 1);
+      if (!score_better(cs, cid, ws, wi)) break;  // sorted input: the rest of this list loses too
+      score_list_insert(ls, li, cs, cid, lane, kmask, K);
+    }
+  }
+  if (lane < K) {
+    const bool empty = li == 0x7fffffff;
+    const int oi = empty ? -1 : li;
+    const float os = empty ? -INFINITY : ls;
+#pragma unroll 1
+    for (int r = 0; r < p.world; ++r) {
+      p.out_ids[r][base + lane] = oi;
+      p.out_sc[r][base + lane] = os;
+    }
+  }
+  __threadfence_system();  // see shard_exchange_kernel
+}
+
 static int check_desc(const macr_shard_desc *d, int B, const char *who) {
   MACR_CHECK_ARG(d, "%s: null descriptor", who);
   MACR_CHECK_ARG(d->world >= 1 && d->world <= kMaxRanks && d->rank >= 0 && d->rank < d->world,
@@ -300,5 +361,30 @@ extern "C" int macr_ipc_close(void *peer_ptr) {
 
 extern "C" int macr_ipc_free(void *dev_ptr) {
   if (dev_ptr) MACR_CUDA(cudaFree(dev_ptr));
+  return MACR_OK;
+}
+
+extern "C" int macr_topk_merge_peers(const int32_t *const *cand_ids_host, const float *const *cand_scores_host,
+                                     int32_t *const *out_ids_host, float *const *out_scores_host, int world,
+                                     int K, int row0, int rows, macr_stream_t stream) {
+  MACR_CHECK_ARG(cand_ids_host && cand_scores_host && out_ids_host && out_scores_host,
+                 "macr_topk_merge_peers: null pointer table");
+  MACR_CHECK_ARG(world >= 1 && world <= kMaxRanks, "macr_topk_merge_peers: world %d outside [1,%d]", world,
+                 kMaxRanks);
+  MACR_CHECK_ARG(K >= 1 && K <= 32, "macr_topk_merge_peers: K must be in [1,32] (got %d)", K);
+  MACR_CHECK_ARG(row0 >= 0 && rows >= 0, "macr_topk_merge_peers: negative row range");
+  if (rows == 0) return MACR_OK;
+  MergePeers p{};
+  p.world = world;
+  for (int r = 0; r < world; ++r) {
+    MACR_CHECK_ARG(cand_ids_host[r] && cand_scores_host[r] && out_ids_host[r] && out_scores_host[r],
+                   "macr_topk_merge_peers: null pointer (rank %d)", r);
+    p.ids[r] = cand_ids_host[r];
+    p.sc[r] = cand_scores_host[r];
+    p.out_ids[r] = out_ids_host[r];
+    p.out_sc[r] = out_scores_host[r];
+  }
+  topk_merge_peers_kernel<<<(rows + 7) / 8, 256, 0, as_stream(stream)>>>(p, row0, rows, K);
+  MACR_LAUNCH_CHECK();
   return MACR_OK;
 }

@@ -47,9 +47,17 @@ def all_gather_candidates(ids, scores, group=None):
 
 
 class ShardedScorer:
-    """Holds this rank's item shard (rows + gates) and scores query users against it."""
+    """Holds this rank's item shard (rows + gates) and scores query users against it.
 
-    def __init__(self, item_table, w, rank=None, world=None, group=None):
+    With one rank per GPU (NCCL group) the exchange of the shards' candidates is ONE kernel over
+    NVLink peer memory (`macr_topk_merge_peers`): every rank writes its `[T,K]` candidates into a
+    CUDA-IPC buffer, a flag barrier, then rank j merges the rows `[j*Tb, (j+1)*Tb)` reading all G
+    shards' lists straight from the peers' buffers and stores the merged rows into every rank's
+    result buffer, a second flag barrier -- all-to-all, K-way merge and all-gather fused, no
+    staging, no NCCL on the data path.  `exchange="nccl"` (or a failed peer mapping) keeps
+    `merge_shard_candidates` (all-to-all + merge + all-gather over NCCL; gloo in the CPU tests)."""
+
+    def __init__(self, item_table, w, rank=None, world=None, group=None, exchange="auto"):
         from .. import ops  # CUDA library: only needed on the device path
 
         self.ops, self.group = ops, group
@@ -61,13 +69,90 @@ class ShardedScorer:
         self.items = item_table[self.lo:self.hi].contiguous()
         self.sig_i = ops.score_gates(self.items, w) if self.hi > self.lo else \
             torch.zeros(0, dtype=torch.float32, device=item_table.device)
+        self._p2p = None  # (T, K) -> peer-mapped buffers
+        self._epoch = 0
+        self.exchange = "none" if self.world == 1 else "nccl"
+        self._want_p2p = (exchange in ("auto", "p2p") and self.world > 1 and self.items.is_cuda
+                          and dist.is_initialized() and dist.get_backend(group) == "nccl")
+        if exchange == "p2p" and not self._want_p2p:
+            raise ValueError("exchange='p2p' needs world > 1, CUDA and one rank per GPU (NCCL group)")
+
+    def _peer_buffers(self, T, K):
+        """[cand ids | cand scores | result ids | result scores | flags] in ONE peer-mapped allocation,
+        (re)built when the query shape changes; every rank maps every peer's copy."""
+        import ctypes as C
+
+        if self._p2p is not None and self._p2p["shape"] == (T, K):
+            return self._p2p
+        self._release_p2p()
+        ops, dev, n = self.ops, self.items.device, T * K
+        buf = ops.IpcBuffer(4 * n * 4 + 256, dev)
+        every = [None] * self.world
+        dist.all_gather_object(every, buf.handle, group=self.group)
+        tabs = [(C.c_void_p * self.world)() for _ in range(5)]
+        peers, ok = [], 1
+        try:
+            for r, h in enumerate(every):
+                base = buf.ptr if r == self.rank else ops.IpcBuffer.open_peer(h)
+                if r != self.rank:
+                    peers.append(base)
+                for k in range(5):
+                    tabs[k][r] = base + 4 * n * k
+        except ops.MacrError:
+            ok = 0
+        flag = torch.tensor([ok], dtype=torch.int32, device=dev)
+        dist.all_reduce(flag, op=dist.ReduceOp.MIN, group=self.group)
+        flat = buf.as_f32((4 * n + 64,))
+        st = {"shape": (T, K), "buf": buf, "peers": peers, "tabs": tabs, "ok": int(flag.item()) == 1,
+              "cand": (flat[:n].view(torch.int32).view(T, K), flat[n:2 * n].view(T, K)),
+              "res": (flat[2 * n:3 * n].view(torch.int32).view(T, K), flat[3 * n:4 * n].view(T, K)),
+              "err": torch.zeros(1, dtype=torch.int32, device=dev)}
+        torch.cuda.synchronize(dev)
+        dist.barrier(group=self.group)  # flags are zeroed and mapped everywhere before the first signal
+        self._p2p = st
+        self.exchange = "p2p" if st["ok"] else "nccl"
+        return st
+
+    def _release_p2p(self):
+        if self._p2p is None:
+            return
+        torch.cuda.synchronize(self.items.device)
+        if dist.is_initialized():
+            dist.barrier(group=self.group)  # no peer may still be reading / writing this rank's buffers
+        for p in self._p2p["peers"]:
+            self.ops.IpcBuffer.close_peer(p)
+        self._p2p["buf"].free()
+        self._p2p = None
+
+    def close(self):
+        self._release_p2p()
 
     def topk(self, Uq, sig_u, c, mask_rowptr, mask_col, K):
-        ids, sc = self.ops.score_topk(Uq, self.items, self.sig_i, sig_u, c, mask_rowptr, mask_col, K,
-                                      item_id_offset=self.lo)
-        if self.world == 1:
-            return ids, sc
-        return merge_shard_candidates(self.ops, ids, sc, self.world, self.group)
+        ops, T = self.ops, Uq.shape[0]
+        st = self._peer_buffers(T, K) if self._want_p2p and T > 0 else None
+        if st is None or not st["ok"]:
+            ids, sc = ops.score_topk(Uq, self.items, self.sig_i, sig_u, c, mask_rowptr, mask_col, K,
+                                     item_id_offset=self.lo)
+            if self.world == 1:
+                return ids, sc
+            return merge_shard_candidates(ops, ids, sc, self.world, self.group)
+        ops.score_topk(Uq, self.items, self.sig_i, sig_u, c, mask_rowptr, mask_col, K, item_id_offset=self.lo,
+                       out=st["cand"])
+        t = st["tabs"]
+        self._epoch += 1
+        ops.shard_barrier(t[4], self.rank, self.world, self._epoch, st["err"])  # every shard's candidates are complete
+        Tb = (T + self.world - 1) // self.world
+        row0 = min(T, self.rank * Tb)
+        ops.topk_merge_peers(t[0], t[1], t[2], t[3], self.world, K, row0, min(T, row0 + Tb) - row0)
+        self._epoch += 1
+        ops.shard_barrier(t[4], self.rank, self.world, self._epoch, st["err"])  # merged rows landed everywhere
+        return st["res"][0].clone(), st["res"][1].clone()  # the buffers are reused by the next call
+
+    def check_peers(self):
+        if self._p2p is not None:
+            e = int(self._p2p["err"].item())
+            if e:
+                raise self.ops.MacrError(f"rank {self.rank}: peer {e - 1} never reached a scoring barrier")
 
 
 def merge_shard_candidates(ops, ids, scores, world, group=None):

@@ -170,13 +170,22 @@ def gather_rows(table, ids):
 TC_MIN_ITEMS = 4096  # smaller catalogues go to the exact fp32 kernel (the tcgen05 path needs >= 2048)
 
 
-def score_topk_tc(Uq, It, sig_i, sig_u, c, mask_rowptr, mask_col, K, item_id_offset=0, stats=None):
+def _topk_out(out, T, K, dev):
+    """(ids int32 [T,K], scores f32 [T,K]): fresh tensors, or the caller's (e.g. peer-mapped) ones."""
+    if out is None:
+        return torch.empty((T, K), dtype=torch.int32, device=dev), torch.empty((T, K), dtype=torch.float32, device=dev)
+    ids, sc = out
+    if tuple(ids.shape) != (T, K) or tuple(sc.shape) != (T, K):
+        raise MacrError(f"out tensors must be [{T},{K}]")
+    return _cuda(ids, torch.int32), _cuda(sc, torch.float32)
+
+
+def score_topk_tc(Uq, It, sig_i, sig_u, c, mask_rowptr, mask_col, K, item_id_offset=0, stats=None, out=None):
     """Tensor-core (tcgen05 + TMA) score + mask + top-K; bit-identical to `score_topk_exact`.
     stats: optional int64[2] device tensor, += {rows re-done by the exact kernel, candidates}."""
     T, n_items = Uq.shape[0], It.shape[0]
     dev = Uq.device
-    ids = torch.empty((T, K), dtype=torch.int32, device=dev)
-    sc = torch.empty((T, K), dtype=torch.float32, device=dev)
+    ids, sc = _topk_out(out, T, K, dev)
     nbytes = lib().macr_score_topk_tc_workspace_bytes(T, n_items, K)
     ws = torch.empty(nbytes + 1024, dtype=torch.uint8, device=dev)
     off = (-ws.data_ptr()) % 1024
@@ -187,21 +196,20 @@ def score_topk_tc(Uq, It, sig_i, sig_u, c, mask_rowptr, mask_col, K, item_id_off
     return ids, sc
 
 
-def score_topk(Uq, It, sig_i, sig_u, c, mask_rowptr, mask_col, K, item_id_offset=0):
+def score_topk(Uq, It, sig_i, sig_u, c, mask_rowptr, mask_col, K, item_id_offset=0, out=None):
     """Fused score + mask + top-K. -> (ids [T,K] int32 global ids, scores [T,K] fp32).
     Catalogues of at least TC_MIN_ITEMS items go to the tcgen05 path, smaller ones to the exact
     fp32 kernel; both give the same bits."""
     if It.shape[0] >= TC_MIN_ITEMS and K <= 32 and Uq.shape[0] > 0:
-        return score_topk_tc(Uq, It, sig_i, sig_u, c, mask_rowptr, mask_col, K, item_id_offset)
-    return score_topk_exact(Uq, It, sig_i, sig_u, c, mask_rowptr, mask_col, K, item_id_offset)
+        return score_topk_tc(Uq, It, sig_i, sig_u, c, mask_rowptr, mask_col, K, item_id_offset, out=out)
+    return score_topk_exact(Uq, It, sig_i, sig_u, c, mask_rowptr, mask_col, K, item_id_offset, out=out)
 
 
-def score_topk_exact(Uq, It, sig_i, sig_u, c, mask_rowptr, mask_col, K, item_id_offset=0):
+def score_topk_exact(Uq, It, sig_i, sig_u, c, mask_rowptr, mask_col, K, item_id_offset=0, out=None):
     """Exact fp32 CUDA-core kernel (score.cu)."""
     T, n_items = Uq.shape[0], It.shape[0]
     dev = Uq.device
-    ids = torch.empty((T, K), dtype=torch.int32, device=dev)
-    sc = torch.empty((T, K), dtype=torch.float32, device=dev)
+    ids, sc = _topk_out(out, T, K, dev)
     nbytes = lib().macr_score_topk_workspace_bytes(T, n_items, K)
     ws = torch.empty(nbytes, dtype=torch.uint8, device=dev)
     check(lib().macr_score_topk(_f(Uq), T, _f(It), n_items, Uq.shape[1], _f(sig_i), _f(sig_u), c,
@@ -585,6 +593,12 @@ def shard_push(U_local, I_local, desc, ids3, B, parity, local3, peer_u, peer_i):
     """peer_u / peer_i: ctypes arrays (c_void_p * world) of the peers' ghost bases in this process."""
     check(lib().macr_shard_push(_f(U_local), _f(I_local), C.byref(desc), _i(ids3), B, parity, _i(local3),
                                 peer_u, peer_i, stream_ptr()), "macr_shard_push")
+
+
+def topk_merge_peers(cand_ids, cand_sc, out_ids, out_sc, world, K, row0, rows):
+    """cand_* / out_*: ctypes arrays (c_void_p * world) of every rank's buffers mapped into this process."""
+    check(lib().macr_topk_merge_peers(cand_ids, cand_sc, out_ids, out_sc, world, K, row0, rows, stream_ptr()),
+          "macr_topk_merge_peers")
 
 
 def shard_barrier(peer_flags, rank, world, epoch, err_flag):

@@ -222,8 +222,16 @@ def _score_worker(rank, world, port, out_dir):
         to = lambda a: torch.from_numpy(a).to(dev)
         dU, dI, dw, dwu, drp, dcol = to(U), to(I), to(w), to(wu), to(rp), to(col)
         su = ops.score_gates(dU, dwu)
-        for name, cls in (("items", mdist.ShardedScorer), ("users", mdist.UserShardedScorer)):
-            ids, sc = cls(dI, dw, rank=rank, world=world).topk(dU, su, 40.0, drp, dcol, K)
+        for name, make in (("items", lambda: mdist.ShardedScorer(dI, dw, rank=rank, world=world)),
+                           ("items_nccl", lambda: mdist.ShardedScorer(dI, dw, rank=rank, world=world, exchange="nccl")),
+                           ("users", lambda: mdist.UserShardedScorer(dI, dw, rank=rank, world=world))):
+            scorer = make()
+            for rep in range(3):  # the peer buffers are reused call after call
+                ids, sc = scorer.topk(dU, su, 40.0, drp, dcol, K)
+            if name == "items":
+                assert scorer.exchange == "p2p", scorer.exchange  # fused exchange + merge over peer memory
+                scorer.check_peers()
+                scorer.close()
             np.savez(os.path.join(out_dir, f"score_{name}_rank{rank}.npz"), ids=ids.cpu().numpy(),
                      sc=sc.cpu().numpy())
     finally:
@@ -242,7 +250,7 @@ def test_sharded_scoring_over_nccl_equals_unsharded(tmp_path):
     dU, dI = to(U), to(I)
     ids, sc = ops.score_topk(dU, dI, ops.score_gates(dI, to(w)), ops.score_gates(dU, to(wu)), 40.0, to(rp),
                              to(col), K)
-    for name in ("items", "users"):
+    for name in ("items", "items_nccl", "users"):
         for r in range(world):
             z = np.load(tmp_path / f"score_{name}_rank{r}.npz")
             np.testing.assert_array_equal(z["ids"], ids.cpu().numpy(), err_msg=f"{name} rank {r}")
