@@ -537,6 +537,22 @@ def sharded_scoring(cx, reps=3):
     s1.record()
     cx.barrier()
     t = cx.max_over_ranks(s0.elapsed_time(s1) * 1e-3) / reps
+    t_nccl = None
+    if cx.world > 1 and sc.exchange == "p2p":  # the same call with the NCCL exchange, for comparison
+        sc_n = ShardedScorer(sc.items, dw, rank=0, world=1)  # reuse the shard; only topk's exchange differs
+        sc_n.world, sc_n.rank, sc_n.lo, sc_n.hi, sc_n.exchange, sc_n._want_p2p = cx.world, cx.rank, sc.lo, sc.hi, "nccl", False
+        sc_n.sig_i = sc.sig_i
+        for _ in range(2):
+            sc_n.topk(Uq, su, 40.0, dmrp_l, dmcol_l, TOPK)
+        cx.barrier()
+        n0, n1 = cx.events()
+        n0.record()
+        for _ in range(reps):
+            ids_n, _ = sc_n.topk(Uq, su, 40.0, dmrp_l, dmcol_l, TOPK)
+        n1.record()
+        cx.barrier()
+        t_nccl = cx.max_over_ranks(n0.elapsed_time(n1) * 1e-3) / reps
+        assert int(ids_n.to(torch.int64).sum().item()) == int(ids.to(torch.int64).sum().item())
     # local part alone (no collective, no merge): what the shard kernel pipeline takes
     l0, l1 = cx.events()
     l0.record()
@@ -551,7 +567,8 @@ def sharded_scoring(cx, reps=3):
     flops = 2.0 * D * T * n_items  # algorithmic, not executed
     pk = cx.peaks["bf16_tflops"]
     out = {"metric": "full_catalog_scores_per_sec", "value": T * n_items / t, "unit": "scores/s",
-           "ms_per_eval": 1e3 * t, "ms_local_scoring": 1e3 * t_local, "query_users": T, "items": n_items,
+           "ms_per_eval": 1e3 * t, "ms_local_scoring": 1e3 * t_local,
+           "ms_per_eval_nccl_exchange": None if t_nccl is None else 1e3 * t_nccl, "query_users": T, "items": n_items,
            "topk": TOPK, "sharding": f"items/{cx.world}", "scaling": "strong",
            "exchange": {"p2p": "ONE kernel over NVLink peer memory: rank j merges rows [jT/N,(j+1)T/N) reading every "
                                "shard's candidates from the peers' buffers and stores the merged rows into every rank's "
