@@ -539,9 +539,7 @@ def sharded_scoring(cx, reps=3):
     t = cx.max_over_ranks(s0.elapsed_time(s1) * 1e-3) / reps
     t_nccl = None
     if cx.world > 1 and sc.exchange == "p2p":  # the same call with the NCCL exchange, for comparison
-        sc_n = ShardedScorer(sc.items, dw, rank=0, world=1)  # reuse the shard; only topk's exchange differs
-        sc_n.world, sc_n.rank, sc_n.lo, sc_n.hi, sc_n.exchange, sc_n._want_p2p = cx.world, cx.rank, sc.lo, sc.hi, "nccl", False
-        sc_n.sig_i = sc.sig_i
+        sc_n = ShardedScorer(None, None, rank=cx.rank, world=cx.world, exchange="nccl", shard_of=sc)
         for _ in range(2):
             sc_n.topk(Uq, su, 40.0, dmrp_l, dmcol_l, TOPK)
         cx.barrier()

@@ -57,18 +57,21 @@ class ShardedScorer:
     staging, no NCCL on the data path.  `exchange="nccl"` (or a failed peer mapping) keeps
     `merge_shard_candidates` (all-to-all + merge + all-gather over NCCL; gloo in the CPU tests)."""
 
-    def __init__(self, item_table, w, rank=None, world=None, group=None, exchange="auto"):
+    def __init__(self, item_table, w, rank=None, world=None, group=None, exchange="auto", shard_of=None):
         from .. import ops  # CUDA library: only needed on the device path
 
         self.ops, self.group = ops, group
         self.rank = dist.get_rank(group) if rank is None else rank
         self.world = dist.get_world_size(group) if world is None else world
-        n_items = item_table.shape[0]
-        b = item_shard_bounds(n_items, self.world)
-        self.lo, self.hi = int(b[self.rank]), int(b[self.rank + 1])
-        self.items = item_table[self.lo:self.hi].contiguous()
-        self.sig_i = ops.score_gates(self.items, w) if self.hi > self.lo else \
-            torch.zeros(0, dtype=torch.float32, device=item_table.device)
+        if shard_of is not None:  # share another scorer's shard (e.g. to time a different exchange)
+            self.lo, self.hi, self.items, self.sig_i = shard_of.lo, shard_of.hi, shard_of.items, shard_of.sig_i
+        else:
+            n_items = item_table.shape[0]
+            b = item_shard_bounds(n_items, self.world)
+            self.lo, self.hi = int(b[self.rank]), int(b[self.rank + 1])
+            self.items = item_table[self.lo:self.hi].contiguous()
+            self.sig_i = ops.score_gates(self.items, w) if self.hi > self.lo else \
+                torch.zeros(0, dtype=torch.float32, device=item_table.device)
         self._p2p = None  # (T, K) -> peer-mapped buffers
         self._epoch = 0
         self.exchange = "none" if self.world == 1 else "nccl"
@@ -294,7 +297,7 @@ class RowShardedMFTrainer:
         self.dev = self.trainer.dev
         self._local3 = torch.zeros(3 * max_batch, dtype=torch.int32, device=self.dev)
         self._ex = torch.zeros((3 * max_batch, Uloc.shape[1]), dtype=torch.float32, device=self.dev)
-        self._step, self._epoch, self._peers = 0, 0, []
+        self._step, self._peers = 0, []
         self._epoch_ids = self._epoch_losses = None
         self.exchange = "allreduce" if self.world > 1 else "none"
         if want_push:

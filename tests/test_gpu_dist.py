@@ -116,3 +116,40 @@ def test_row_partitioned_lightgcn_world1_equals_plain_trainer():
     sh.check_peers()
     sh.close()
     tr.close()
+
+
+def test_topk_merge_peers_kernel_on_one_gpu(oracle):
+    """`macr_topk_merge_peers` (the fused exchange + merge of item-sharded scoring) with three
+    "ranks" whose buffers all live on this GPU: every rank's row block, merged from all shards'
+    candidate lists and stored into every rank's result buffer, must equal the oracle's merge of
+    the [G,T,K] block -- the same kernel then runs over NVLink peer mappings (test_gpu_multi.py)."""
+    import ctypes as C
+
+    import torch
+
+    from macr_b200 import ops
+
+    G, T, K = 3, 77, 20
+    rng = np.random.RandomState(3)
+    ids = np.full((G, T, K), -1, np.int32)
+    sc = np.full((G, T, K), -np.inf, np.float32)
+    for g in range(G):
+        for t in range(T):
+            n = int(rng.randint(0, K + 1))  # short lists are padded with -1 / -inf
+            cand = rng.choice(np.arange(g * 1000, (g + 1) * 1000), size=n, replace=False)
+            s_ = np.round(rng.randn(n), 1).astype(np.float32)  # coarse scores: ties across shards
+            order = np.lexsort((cand, -s_))
+            ids[g, t, :n], sc[g, t, :n] = cand[order], s_[order]
+    want_i, want_s = oracle.topk_merge(ids.copy(), sc.copy())
+    d_ids = [torch.from_numpy(ids[g].copy()).cuda() for g in range(G)]
+    d_sc = [torch.from_numpy(sc[g].copy()).cuda() for g in range(G)]
+    o_ids = [torch.full((T, K), -7, dtype=torch.int32, device="cuda") for _ in range(G)]
+    o_sc = [torch.zeros((T, K), dtype=torch.float32, device="cuda") for _ in range(G)]
+    tab = lambda ts: (C.c_void_p * G)(*[t.data_ptr() for t in ts])
+    Tb = (T + G - 1) // G
+    for r in range(G):  # "rank" r merges its row block and stores it into every rank's result
+        row0 = min(T, r * Tb)
+        ops.topk_merge_peers(tab(d_ids), tab(d_sc), tab(o_ids), tab(o_sc), G, K, row0, min(T, row0 + Tb) - row0)
+    for r in range(G):
+        np.testing.assert_array_equal(o_ids[r].cpu().numpy(), want_i)
+        np.testing.assert_array_equal(o_sc[r].cpu().numpy(), want_s)
