@@ -362,6 +362,26 @@ int macr_sample_lgcn(uint32_t *py_state, uint32_t *np_state, const int32_t *user
                      const int32_t *ban_sorted, int B, int32_t *users, int32_t *pos,
                      int32_t *neg);
 
+/* Epoch forms: n_batches consecutive calls of the functions above in one go, out = int32
+ * [n_batches][3][B] (users, pos, neg per batch -- the layout macr_mf_trainer_run_host stages).
+ * Same streams and triples word for word (the epoch loops of macr_mf/train.py:470-499 and
+ * macr_lightgcn/LightGCN.py:765-773 call sample() once per step), but drawn speculatively in
+ * chunks so the sequential part never waits for the lists: ~4x the per-batch functions.
+ * tags: hashed (user, rejected id) pair set over rowptr / sorted (ban_rowptr / ban_sorted):
+ * uint16[8 << log2_buckets], 16-byte aligned, filled by macr_pairset_build (size it for ~2-3
+ * pairs per bucket; a full bucket only costs exact look-ups, never a wrong answer). */
+int macr_pairset_build(const int64_t *rowptr, const int32_t *ids, int n_rows, uint16_t *tags,
+                       int log2_buckets);
+int macr_sample_mf_epoch(uint32_t *py_state, const int32_t *users_pop, int n_pop, int n_users,
+                         int n_items, const int64_t *rowptr, const int32_t *order,
+                         const int32_t *sorted, const uint16_t *tags, int log2_buckets, int B,
+                         int n_batches, int32_t *out);
+int macr_sample_lgcn_epoch(uint32_t *py_state, uint32_t *np_state, const int32_t *users_pop,
+                           int n_pop, int n_users, int n_items, const int64_t *pos_rowptr,
+                           const int32_t *pos_order, const int64_t *ban_rowptr,
+                           const int32_t *ban_sorted, const uint16_t *ban_tags, int log2_buckets,
+                           int B, int n_batches, int32_t *out);
+
 /* ------------------------------------------------------------------------- *
  * Row-partitioned training over the GPUs of one box (SURVEY.md 8e rows "dense Adam
  * sweep" and "gather + grid + row grads"): every rank owns a contiguous id range

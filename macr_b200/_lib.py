@@ -98,6 +98,9 @@ PROTOTYPES = {
     "macr_foldout_metrics": (i32, [vp, i32, i32, vp, vp, vp, vp, vp]),
     "macr_sample_mf": (i32, [vp, vp, i32, i32, i32, vp, vp, vp, i32, vp, vp, vp]),
     "macr_sample_lgcn": (i32, [vp, vp, vp, i32, i32, i32, vp, vp, vp, vp, i32, vp, vp, vp]),
+    "macr_pairset_build": (i32, [vp, vp, i32, vp, i32]),
+    "macr_sample_mf_epoch": (i32, [vp, vp, i32, i32, i32, vp, vp, vp, vp, i32, i32, i32, vp]),
+    "macr_sample_lgcn_epoch": (i32, [vp, vp, vp, i32, i32, i32, vp, vp, vp, vp, vp, i32, i32, i32, vp]),
     "macr_shard_pack": (i32, [vp, vp, C.POINTER(ShardDesc), vp, i32, i32, vp, vp, vp]),
     "macr_shard_unpack": (i32, [vp, vp, C.POINTER(ShardDesc), vp, i32, i32, vp]),
     "macr_shard_push": (i32, [vp, vp, C.POINTER(ShardDesc), vp, i32, i32, vp, C.POINTER(vp),

@@ -17,6 +17,7 @@
 //                          shuffle of a pool copy; else rejection against a set of chosen indices
 //   np randint(0, n, 1)    rng = n - 1; rng == 0: no draw; else mask = 2^bits(rng) - 1 and
 //                          32-bit draws `genrand & mask` until <= rng   (masked rejection)
+#include <emmintrin.h>
 #include <math.h>
 
 #include <algorithm>
@@ -61,7 +62,8 @@ struct MT {
 inline int bit_length(uint32_t n) { return n ? 32 - __builtin_clz(n) : 0; }
 
 // random.Random._randbelow_with_getrandbits (n >= 1, n < 2^31 here)
-inline uint32_t py_randbelow(MT &g, uint32_t n) {
+template <class G>
+inline uint32_t py_randbelow(G &g, uint32_t n) {
   const int k = bit_length(n);
   uint32_t r = g.next() >> (32 - k);
   while (r >= n) r = g.next() >> (32 - k);
@@ -69,7 +71,8 @@ inline uint32_t py_randbelow(MT &g, uint32_t n) {
 }
 
 // numpy legacy RandomState.randint(0, n, size=1)[0]
-inline uint32_t np_randint(MT &g, uint32_t n) {
+template <class G>
+inline uint32_t np_randint(G &g, uint32_t n) {
   const uint32_t rng = n - 1;
   if (rng == 0) return 0;
   uint32_t mask = rng;
@@ -81,19 +84,30 @@ inline uint32_t np_randint(MT &g, uint32_t n) {
 }
 
 // random.sample(pop, k) / [random.choice(pop) for _ in range(k)] as the samplers use them
-void py_pick_users(MT &g, const int32_t *pop, int n, int B, int n_users_flag, int32_t *out) {
+struct PickScratch {
+  std::vector<int32_t> pool;
+  std::vector<uint8_t> chosen;
+};
+
+template <class G>
+void py_pick_users(G &g, const int32_t *pop, int n, int B, int n_users_flag, int32_t *out,
+                   PickScratch *scratch = nullptr) {
+  PickScratch local;
+  if (!scratch) scratch = &local;
   if (B <= n_users_flag) {  // rd.sample(pop, B)
     long long setsize = 21;
     if (B > 5) setsize += (long long)llround(pow(4.0, ceil(log((double)B * 3.0) / log(4.0))));
     if (n <= setsize) {
-      std::vector<int32_t> pool(pop, pop + n);
+      std::vector<int32_t> &pool = scratch->pool;
+      pool.assign(pop, pop + n);
       for (int i = 0; i < B; ++i) {
         const uint32_t j = py_randbelow(g, (uint32_t)(n - i));
         out[i] = pool[j];
         pool[j] = pool[n - i - 1];
       }
     } else {
-      std::vector<uint8_t> chosen((size_t)n, 0);
+      std::vector<uint8_t> &chosen = scratch->chosen;
+      chosen.assign((size_t)n, 0);
       for (int i = 0; i < B; ++i) {
         uint32_t j = py_randbelow(g, (uint32_t)n);
         while (chosen[j]) j = py_randbelow(g, (uint32_t)n);
@@ -204,5 +218,351 @@ extern "C" int macr_sample_lgcn(uint32_t *py_state /*[625]*/, uint32_t *np_state
   }
   py_state[624] = (uint32_t)gp.idx;
   np_state[624] = (uint32_t)gn.idx;
+  return MACR_OK;
+}
+
+// =============================================================================================
+// Epoch samplers.  Same streams, same triples, but the sequential part no longer waits for
+// memory: the per-batch functions above spend most of their ~50-80 ns per triple on the lists
+// (two dependent cache misses and a scan per triple) although only ~0.1-1 % of the negative
+// draws are ever rejected by them.  Here a chunk of triples is drawn SPECULATIVELY -- every
+// candidate negative assumed "not a train item" -- touching nothing but the word stream and the
+// list lengths, and issuing prefetches for the two lines it will need; a second pass over the
+// chunk then reads the positives and tests the candidates against a hashed pair set (one
+// prefetched probe) with many independent accesses in flight.  A candidate that IS in the user's
+// list invalidates what was drawn after it: the word cursor goes back to just behind that
+// draw, the rejection loop is finished the literal way, and the chunk is redrawn from the next
+// triple.  The words themselves come from block-wise (vectorisable) MT19937 generation into a
+// buffer that can be re-read from the chunk's start.
+// =============================================================================================
+namespace macr {
+namespace {
+
+inline uint32_t mt_temper(uint32_t y) {
+  y ^= (y >> 11);
+  y ^= (y << 7) & 0x9d2c5680u;
+  y ^= (y << 15) & 0xefc60000u;
+  y ^= (y >> 18);
+  return y;
+}
+
+// inverse of mt_temper: the raw state word behind an output word
+inline uint32_t mt_untemper(uint32_t y) {
+  y ^= y >> 18;
+  y ^= (y << 15) & 0xefc60000u;
+  uint32_t x = y;
+  for (int k = 0; k < 5; ++k) x = y ^ ((x << 7) & 0x9d2c5680u);
+  y = x;
+  for (int k = 0; k < 3; ++k) x = y ^ (x >> 11);
+  return x;
+}
+
+// next 624 raw words in place; three ranges so that every loop only reads words that are final
+// for it (dependence distance 227: the loops vectorise)
+void mt_next_block(uint32_t *__restrict mt) {
+  const uint32_t UPPER = 0x80000000u, LOWER = 0x7fffffffu, MATRIX_A = 0x9908b0dfu;
+  for (int kk = 0; kk < 227; ++kk) {
+    const uint32_t y = (mt[kk] & UPPER) | (mt[kk + 1] & LOWER);
+    mt[kk] = mt[kk + 397] ^ (y >> 1) ^ ((0u - (y & 1u)) & MATRIX_A);
+  }
+  for (int kk = 227; kk < 623; ++kk) {
+    const uint32_t y = (mt[kk] & UPPER) | (mt[kk + 1] & LOWER);
+    mt[kk] = mt[kk - 227] ^ (y >> 1) ^ ((0u - (y & 1u)) & MATRIX_A);
+  }
+  const uint32_t y = (mt[623] & UPPER) | (mt[0] & LOWER);
+  mt[623] = mt[396] ^ (y >> 1) ^ ((0u - (y & 1u)) & MATRIX_A);
+}
+
+// Output words of one generator, addressed by their absolute position in the stream (position 0
+// = first word of the block the caller's state sits in).  `cur` may be moved back to any
+// position not yet released.
+class WordStream {
+ public:
+  size_t cur;
+
+  explicit WordStream(uint32_t *state) : cur(state[624]), state_(state), base_(0), end_(0) {
+    memcpy(raw_, state, sizeof(raw_));
+    append_tempered();
+  }
+  inline uint32_t next() {
+    if (__builtin_expect(cur >= end_, 0)) grow();
+    return p_[cur++];
+  }
+  const uint32_t *words() const { return p_; }  // indexed by absolute position
+  size_t end() const { return end_; }
+  void ensure() { grow(); }  // make position `cur` readable
+  // positions before `mark` will not be revisited (one block of slack is kept for store_state)
+  void release_before(size_t mark) {
+    const size_t keep = (mark ? (mark - 1) / 624 : 0) * 624;
+    if (keep >= base_ + 64 * 624) {
+      w_.erase(w_.begin(), w_.begin() + (keep - base_));
+      base_ = keep;
+      p_ = w_.data() - base_;
+    }
+  }
+  // the generator state a draw-by-draw consumer would hold at `cur` (CPython / numpy regenerate
+  // lazily: after the last word of a block the position is 624, not 0 of the next block)
+  void store_state() const {
+    size_t blk = cur / 624, idx = cur % 624;
+    if (cur > 0 && idx == 0) blk -= 1, idx = 624;
+    if ((blk + 1) * 624 == end_) {
+      memcpy(state_, raw_, sizeof(raw_));
+    } else {
+      for (int k = 0; k < 624; ++k) state_[k] = mt_untemper(p_[blk * 624 + k]);
+    }
+    state_[624] = (uint32_t)idx;
+  }
+
+ private:
+  void append_tempered() {
+    const size_t n = w_.size();
+    w_.resize(n + 624);
+    uint32_t *dst = w_.data() + n;
+    for (int k = 0; k < 624; ++k) dst[k] = mt_temper(raw_[k]);
+    end_ += 624;
+    p_ = w_.data() - base_;
+  }
+  __attribute__((noinline)) void grow() {
+    while (cur >= end_) {
+      mt_next_block(raw_);
+      append_tempered();
+    }
+  }
+  uint32_t *state_;
+  uint32_t raw_[624];  // raw state of the newest generated block
+  std::vector<uint32_t> w_;
+  const uint32_t *p_;  // w_.data() - base_
+  size_t base_, end_;
+};
+
+// ---- hashed (row, id) pair set -------------------------------------------------------------
+// Buckets of eight 16-bit tags (one 16-byte load, one SSE2 compare, no probe loop); tag 0 = empty
+// slot, a bucket whose eighth slot is taken may have lost pairs and answers "maybe" to everything.
+// "Maybe" (a true member, or one query in ~10^4 by tag collision) is settled on the exact list.
+inline uint64_t pair_hash(uint32_t row, uint32_t id) {
+  return (((uint64_t)row << 32) | id) * 0x9E3779B97F4A7C15ull;
+}
+inline uint16_t pair_tag(uint64_t h) { return (uint16_t)((h >> 8) | 1u); }
+
+struct PairSet {
+  const uint16_t *tags;   // [buckets][8]
+  int shift;              // 64 - log2(buckets)
+  const int64_t *rowptr;  // exact lists behind the tags (ascending ids per row)
+  const int32_t *sorted;
+
+  inline const uint16_t *bucket_of(uint64_t h) const { return tags + ((h >> shift) << 3); }
+  inline bool maybe(uint64_t h) const {
+    const __m128i b = _mm_load_si128(reinterpret_cast<const __m128i *>(bucket_of(h)));
+    const __m128i eq = _mm_cmpeq_epi16(b, _mm_set1_epi16((short)pair_tag(h)));
+    // byte mask: tag matches anywhere, or slot 7 (bytes 14, 15) not empty
+    const int m = _mm_movemask_epi8(eq);
+    const int full = _mm_movemask_epi8(_mm_cmpeq_epi16(b, _mm_setzero_si128())) & 0xc000;
+    return (m | (full ^ 0xc000)) != 0;
+  }
+  inline bool exact(uint32_t row, int32_t id) const {
+    return in_sorted(sorted + rowptr[row], sorted + rowptr[row + 1], id);
+  }
+  inline bool contains(uint32_t row, int32_t id) const {
+    return maybe(pair_hash(row, (uint32_t)id)) && exact(row, id);
+  }
+};
+
+// Triples drawn ahead of their verification: a rejected candidate costs half a chunk of redrawn
+// triples, so the chunk shrinks with the density of the lists (pairs / (rows * ids)).
+inline int chunk_for(double pairs, double rows, double ids) {
+  const double p = pairs / (rows * ids > 0 ? rows * ids : 1);
+  int c = 256;
+  while (c > 16 && c * p > 0.25) c >>= 1;
+  return c;
+}
+
+}  // namespace
+}  // namespace macr
+
+extern "C" int macr_pairset_build(const int64_t *rowptr, const int32_t *ids, int n_rows,
+                                  uint16_t *tags, int log2_buckets) {
+  MACR_CHECK_ARG(rowptr && ids && tags, "macr_pairset_build: null pointer");
+  MACR_CHECK_ARG(n_rows >= 0 && log2_buckets >= 0 && log2_buckets <= 40, "macr_pairset_build: bad size");
+  MACR_CHECK_ARG(((uintptr_t)tags & 15) == 0, "macr_pairset_build: tags must be 16-byte aligned");
+  const uint64_t buckets = 1ull << log2_buckets;
+  memset(tags, 0, buckets * 16);
+  for (int r = 0; r < n_rows; ++r)
+    for (int64_t k = rowptr[r]; k < rowptr[r + 1]; ++k) {
+      const uint64_t h = pair_hash((uint32_t)r, (uint32_t)ids[k]);
+      uint16_t *b = tags + ((log2_buckets ? h >> (64 - log2_buckets) : 0) << 3);
+      int s = 0;
+      while (s < 7 && b[s]) ++s;
+      b[s] = pair_tag(h);  // slot 7 taken = "bucket may have lost pairs"
+    }
+  return MACR_OK;
+}
+
+namespace macr {
+namespace {
+
+// Register-resident view of a WordStream for the draw loops (the stream object itself is only
+// touched when a block runs out).
+struct Reader {
+  WordStream &g;
+  const uint32_t *p;
+  size_t cur, end;
+  explicit Reader(WordStream &s) : g(s), p(s.words()), cur(s.cur), end(s.end()) {}
+  ~Reader() { g.cur = cur; }
+  inline uint32_t next() {
+    if (__builtin_expect(cur >= end, 0)) refill();
+    return p[cur++];
+  }
+  __attribute__((noinline)) void refill() {
+    g.cur = cur;
+    g.ensure();
+    p = g.words();
+    end = g.end();
+  }
+};
+
+struct PyDraw {  // random.choice / _randbelow
+  static inline uint32_t below(Reader &r, uint32_t n) { return py_randbelow(r, n); }
+};
+struct NpDraw {  // np.random.randint(0, n, size=1)[0]
+  static inline uint32_t below(Reader &r, uint32_t n) { return np_randint(r, n); }
+};
+
+// Pass A over triples [i0, i1): positions of the positives, candidate negatives, and the
+// cursor behind every triple (relative to `cur0`).  Reads the stream, lo/len -- nothing else.
+template <class D>
+__attribute__((noinline)) void draw_chunk(WordStream &g, int i0, int i1, const int64_t *lo,
+                                          const uint32_t *len, uint32_t n_items, int64_t *pos_at,
+                                          int32_t *neg, uint32_t *cur_after, size_t cur0) {
+  Reader r(g);
+  for (int i = i0; i < i1; ++i) {
+    const uint32_t n = len[i];
+    pos_at[i] = n ? lo[i] + (int64_t)D::below(r, n) : -1;
+    neg[i] = (int32_t)D::below(r, n_items);
+    cur_after[i] = (uint32_t)(r.cur - cur0);
+  }
+}
+
+// The chunk loop shared by both samplers.  `g` is the stream the item draws come from.
+template <class D>
+void sample_items(WordStream &g, const PairSet &set, int chunk, int B, const int32_t *users,
+                  const int64_t *lo, const uint32_t *len, const int32_t *order, uint32_t n_items,
+                  int32_t *pos, int32_t *neg, int64_t *pos_at, uint32_t *cur_after) {
+  for (int c0 = 0; c0 < B; c0 += chunk) {
+    const int c1 = c0 + chunk < B ? c0 + chunk : B;
+    const size_t cur0 = g.cur;
+    int i0 = c0;  // first triple not yet final
+    while (i0 < c1) {
+      // speculative draws: every candidate assumed "not in the list"
+      draw_chunk<D>(g, i0, c1, lo, len, n_items, pos_at, neg, cur_after, cur0);
+      int hit = -1;
+      for (int i = i0; i < c1; ++i) {  // verification: independent accesses, misses overlap
+        pos[i] = pos_at[i] >= 0 ? order[pos_at[i]] : 0;
+        if (set.maybe(pair_hash((uint32_t)users[i], (uint32_t)neg[i])) && hit < 0 &&
+            set.exact((uint32_t)users[i], neg[i]))
+          hit = i;
+      }
+      if (hit < 0) break;
+      // the candidate of triple `hit` is in the list: finish its rejection loop the literal way
+      // and redraw everything after it
+      g.cur = cur0 + cur_after[hit];
+      {
+        Reader r(g);
+        for (;;) {
+          const int32_t c = (int32_t)D::below(r, n_items);
+          if (!set.contains((uint32_t)users[hit], c)) {
+            neg[hit] = c;
+            break;
+          }
+        }
+      }
+      i0 = hit + 1;
+    }
+  }
+}
+
+struct EpochScratch {
+  std::vector<int64_t> lo, pos_at;
+  std::vector<uint32_t> len, cur_after;
+  PickScratch pick;
+  explicit EpochScratch(int B) : lo((size_t)B), pos_at((size_t)B), len((size_t)B), cur_after((size_t)B) {}
+};
+
+}  // namespace
+}  // namespace macr
+
+// n_batches consecutive macr_sample_mf calls; out = int32 [n_batches][3][B] (users, pos, neg).
+extern "C" int macr_sample_mf_epoch(uint32_t *py_state, const int32_t *users_pop, int n_pop,
+                                    int n_users, int n_items, const int64_t *rowptr,
+                                    const int32_t *order, const int32_t *sorted,
+                                    const uint16_t *tags, int log2_buckets, int B, int n_batches,
+                                    int32_t *out) {
+  MACR_CHECK_ARG(py_state && users_pop && rowptr && order && sorted && tags && out,
+                 "macr_sample_mf_epoch: null pointer");
+  MACR_CHECK_ARG(n_pop > 0 && n_items > 0 && B > 0 && n_batches >= 0, "macr_sample_mf_epoch: empty population");
+  MACR_CHECK_ARG(B > n_users || B <= n_pop, "macr_sample_mf_epoch: sample larger than population");
+  MACR_CHECK_ARG(py_state[624] <= 624 && log2_buckets >= 1 && log2_buckets <= 40 && ((uintptr_t)tags & 15) == 0,
+                 "macr_sample_mf_epoch: bad state / table");
+  WordStream g(py_state);
+  const PairSet set{tags, 64 - log2_buckets, rowptr, sorted};
+  const int chunk = chunk_for((double)rowptr[n_users], n_users, n_items);
+  EpochScratch s(B);
+  for (int b = 0; b < n_batches; ++b) {
+    int32_t *users = out + (size_t)b * 3 * B, *pos = users + B, *neg = pos + B;
+    g.release_before(g.cur);
+    {
+      Reader r(g);
+      py_pick_users(r, users_pop, n_pop, B, n_users, users, &s.pick);
+    }
+    for (int i = 0; i < B; ++i) {  // independent loads: the misses overlap
+      const int64_t l = rowptr[users[i]];
+      s.lo[i] = l;
+      s.len[i] = (uint32_t)(rowptr[users[i] + 1] - l);
+    }
+    sample_items<PyDraw>(g, set, chunk, B, users, s.lo.data(), s.len.data(), order,
+                         (uint32_t)n_items, pos, neg, s.pos_at.data(), s.cur_after.data());
+  }
+  g.store_state();
+  return MACR_OK;
+}
+
+// n_batches consecutive macr_sample_lgcn calls; out = int32 [n_batches][3][B].  ban_tags: pair
+// set of (user, banned id) over ban_rowptr / ban_sorted.
+extern "C" int macr_sample_lgcn_epoch(uint32_t *py_state, uint32_t *np_state,
+                                      const int32_t *users_pop, int n_pop, int n_users,
+                                      int n_items, const int64_t *pos_rowptr,
+                                      const int32_t *pos_order, const int64_t *ban_rowptr,
+                                      const int32_t *ban_sorted, const uint16_t *ban_tags,
+                                      int log2_buckets, int B, int n_batches, int32_t *out) {
+  MACR_CHECK_ARG(py_state && np_state && users_pop && pos_rowptr && pos_order && ban_rowptr &&
+                     ban_sorted && ban_tags && out,
+                 "macr_sample_lgcn_epoch: null pointer");
+  MACR_CHECK_ARG(n_pop > 0 && n_items > 0 && B > 0 && n_batches >= 0, "macr_sample_lgcn_epoch: empty population");
+  MACR_CHECK_ARG(B > n_users || B <= n_pop, "macr_sample_lgcn_epoch: sample larger than population");
+  MACR_CHECK_ARG(py_state[624] <= 624 && np_state[624] <= 624 && log2_buckets >= 1 && log2_buckets <= 40 &&
+                     ((uintptr_t)ban_tags & 15) == 0,
+                 "macr_sample_lgcn_epoch: bad state / table");
+  WordStream gp(py_state), gn(np_state);
+  const PairSet set{ban_tags, 64 - log2_buckets, ban_rowptr, ban_sorted};
+  const int chunk = chunk_for((double)ban_rowptr[n_users], n_users, n_items);
+  EpochScratch s(B);
+  for (int b = 0; b < n_batches; ++b) {
+    int32_t *users = out + (size_t)b * 3 * B, *pos = users + B, *neg = pos + B;
+    gp.release_before(gp.cur);
+    gn.release_before(gn.cur);
+    {
+      Reader r(gp);
+      py_pick_users(r, users_pop, n_pop, B, n_users, users, &s.pick);
+    }
+    for (int i = 0; i < B; ++i) {
+      const int64_t l = pos_rowptr[users[i]];
+      s.lo[i] = l;
+      s.len[i] = (uint32_t)(pos_rowptr[users[i] + 1] - l);
+      MACR_CHECK_ARG(s.len[i] > 0, "macr_sample_lgcn_epoch: user %d has no positive item", (int)users[i]);
+    }
+    sample_items<NpDraw>(gn, set, chunk, B, users, s.lo.data(), s.len.data(), pos_order,
+                         (uint32_t)n_items, pos, neg, s.pos_at.data(), s.cur_after.data());
+  }
+  gp.store_state();
+  gn.store_state();
   return MACR_OK;
 }

@@ -36,6 +36,23 @@ class ListCSR:
                 a = np.asarray(items, np.int32)
                 self.order[lo:lo + len(a)] = a
                 self.sorted[lo:lo + len(a)] = np.sort(a)
+        self._tags = None
+
+    def pair_tags(self, log2=None):
+        """Hashed (user, id) pair set over `sorted` for the epoch samplers (built once):
+        -> (uint16 tags [buckets, 8], log2 of the bucket count), ~2 pairs per bucket unless
+        `log2` says otherwise (a crowded table costs exact look-ups, never a wrong answer)."""
+        if self._tags is None or log2 is not None:
+            n = int(self.rowptr[-1])
+            if log2 is None:
+                log2 = max(1, int(np.ceil(np.log2(max(1, n) / 2.0))))
+            raw = np.empty((8 << log2) + 8, np.uint16)
+            off = (-raw.ctypes.data % 16) // 2          # 16-byte aligned view
+            tags = raw[off:off + (8 << log2)]
+            check(lib().macr_pairset_build(_p(self.rowptr), _p(self.sorted), len(self.rowptr) - 1,
+                                           _p(tags), log2), "macr_pairset_build")
+            self._tags = (tags, log2)
+        return self._tags
 
 
 def _py_state():
@@ -80,17 +97,17 @@ def sample_mf(users_pop, n_users, n_items, csr, B):
 
 
 def sample_mf_epoch(users_pop, n_users, n_items, csr, B, n_batches, out=None):
-    """n_batches consecutive `sample()` calls in one go -> int32 [n_batches, 3, B] (the layout
-    `MFTrainer.run_host` takes); the generator state crosses the boundary once."""
+    """n_batches consecutive `sample()` calls in one native call -> int32 [n_batches, 3, B] (the
+    layout `MFTrainer.run_host` takes); speculative chunked draws (macr_sample_mf_epoch)."""
     _check_population(B, n_users, len(users_pop))
     st, meta = _py_state()
     if out is None:
         out = np.empty((n_batches, 3, B), np.int32)
-    fn = lib().macr_sample_mf
-    args = (_p(st), _p(users_pop), len(users_pop), n_users, n_items, _p(csr.rowptr), _p(csr.order),
-            _p(csr.sorted), B)
-    for k in range(n_batches):
-        check(fn(*args, _p(out[k, 0]), _p(out[k, 1]), _p(out[k, 2])), "macr_sample_mf")
+    assert out.dtype == np.int32 and out.flags.c_contiguous and out.shape == (n_batches, 3, B)
+    tags, log2 = csr.pair_tags()
+    check(lib().macr_sample_mf_epoch(_p(st), _p(users_pop), len(users_pop), n_users, n_items,
+                                     _p(csr.rowptr), _p(csr.order), _p(csr.sorted), _p(tags), log2,
+                                     B, n_batches, _p(out)), "macr_sample_mf_epoch")
     _py_restore(st, meta)
     return out
 
@@ -101,11 +118,12 @@ def sample_lgcn_epoch(users_pop, n_users, n_items, pos_csr, ban_csr, B, n_batche
     nst, nmeta = _np_state()
     if out is None:
         out = np.empty((n_batches, 3, B), np.int32)
-    fn = lib().macr_sample_lgcn
-    args = (_p(st), _p(nst), _p(users_pop), len(users_pop), n_users, n_items, _p(pos_csr.rowptr),
-            _p(pos_csr.order), _p(ban_csr.rowptr), _p(ban_csr.sorted), B)
-    for k in range(n_batches):
-        check(fn(*args, _p(out[k, 0]), _p(out[k, 1]), _p(out[k, 2])), "macr_sample_lgcn")
+    assert out.dtype == np.int32 and out.flags.c_contiguous and out.shape == (n_batches, 3, B)
+    tags, log2 = ban_csr.pair_tags()
+    check(lib().macr_sample_lgcn_epoch(_p(st), _p(nst), _p(users_pop), len(users_pop), n_users,
+                                       n_items, _p(pos_csr.rowptr), _p(pos_csr.order),
+                                       _p(ban_csr.rowptr), _p(ban_csr.sorted), _p(tags), log2, B,
+                                       n_batches, _p(out)), "macr_sample_lgcn_epoch")
     _py_restore(st, meta)
     _np_restore(nst, nmeta)
     return out

@@ -246,3 +246,82 @@ def test_sample_epoch_equals_consecutive_samples():
     random.seed(4)
     np.random.seed(4)
     np.testing.assert_array_equal(ld.sample_epoch(5), want)
+
+
+def _states():
+    return random.getstate(), np.random.get_state()
+
+
+def _same_states(a, b):
+    return a[0] == b[0] and a[1][0] == b[1][0] and np.array_equal(a[1][1], b[1][1]) and a[1][2:] == b[1][2:]
+
+
+@pytest.mark.parametrize("crowded", [False, True])
+def test_epoch_samplers_redraw_after_rejected_candidates(crowded):
+    """The epoch samplers draw chunks speculatively and go back in the word stream when a
+    candidate turns out to be a list member.  Dense lists (every second draw rejected) make that
+    the common case; triples AND generator states must still equal the per-batch samplers',
+    whatever the chunking, the position inside the 624-word block, or the crowding of the hashed
+    pair set (`crowded`: 2 buckets for ~2000 pairs -> every look-up settles on the exact list)."""
+    from macr_b200.host import native_sampler as ns
+
+    rng = np.random.RandomState(11)
+    n_users, n_items = 70, 61
+    lists = {u: rng.permutation(n_items)[:rng.randint(1, 50)].tolist() for u in range(n_users)}
+    lists[5] = []          # MF: a user without train items gets positive 0, no draw
+    both = {u: sorted(set(v) | set(rng.randint(0, n_items, 5).tolist())) for u, v in lists.items()}
+    csr, ban = ns.ListCSR(lists, n_users), ns.ListCSR(both, n_users)
+    if crowded:
+        csr.pair_tags(log2=1), ban.pair_tags(log2=1)
+    pop = np.arange(n_users, dtype=np.int32)
+    pop_l = np.array([u for u in range(n_users) if lists[u]], np.int32)
+    for B, n_b, skip in ((16, 9, 0), (64, 5, 623), (300, 3, 7), (1, 40, 0)):
+        random.seed(B)
+        np.random.seed(B)
+        for _ in range(skip):        # start somewhere inside a block / right at its end
+            random.getrandbits(32), np.random.randint(0, 1 << 30)
+        start = _states()
+        want = np.array([ns.sample_mf(pop, n_users, n_items, csr, B) for _ in range(n_b)])
+        end = _states()
+        random.setstate(start[0]), np.random.set_state(start[1])
+        got = np.concatenate([ns.sample_mf_epoch(pop, n_users, n_items, csr, B, k)
+                              for k in (n_b - 2, 0, 2)])
+        np.testing.assert_array_equal(got, want)
+        assert _same_states(_states(), end)
+        # LightGCN: two streams, numpy's masked rejection, ban list != positive list
+        random.setstate(start[0]), np.random.set_state(start[1])
+        want = np.array([ns.sample_lgcn(pop_l, n_users, n_items, csr, ban, B) for _ in range(n_b)])
+        end = _states()
+        random.setstate(start[0]), np.random.set_state(start[1])
+        got = np.concatenate([ns.sample_lgcn_epoch(pop_l, n_users, n_items, csr, ban, B, k)
+                              for k in (1, n_b - 1)])
+        np.testing.assert_array_equal(got, want)
+        assert _same_states(_states(), end)
+        for u, n in zip(got[:, 0].ravel(), got[:, 2].ravel()):
+            assert n not in both[u]
+
+
+@pytest.mark.skipif(not os.path.isdir(os.path.join(REF_DATA, "addressa")), reason="reference data not mounted")
+def test_epoch_samplers_equal_per_batch_on_addressa():
+    """Real lists (addressa, B=1024, one epoch = 111 batches): the epoch forms reproduce the
+    per-batch twins (themselves pinned to the reference's sampler by sha1) and leave both
+    generators where they do."""
+    from macr_b200.host.data_lgcn import Data as LData
+    from macr_b200.host.data_mf import Data
+
+    data = Data(_mf_args(REF_DATA + "/", "addressa", 1024))
+    n_b = data.n_train // 1024 + 1
+    random.seed(12345)
+    want = np.array([data.sample() for _ in range(n_b)], np.int32)
+    end = random.getstate()
+    random.seed(12345)
+    np.testing.assert_array_equal(data.sample_epoch(n_b), want)
+    assert random.getstate() == end
+    ld = LData(os.path.join(REF_DATA, "addressa"), 1024, types.SimpleNamespace(valid_set="test"))
+    for one, many in ((ld.sample, ld.sample_epoch), (ld.sample_test, ld.sample_test_epoch)):
+        random.seed(7), np.random.seed(7)
+        want = np.array([one() for _ in range(20)], np.int32)
+        end = _states()
+        random.seed(7), np.random.seed(7)
+        np.testing.assert_array_equal(many(20), want)
+        assert _same_states(_states(), end)
