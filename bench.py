@@ -577,8 +577,9 @@ def sharded_scoring(cx, reps=3):
            "rows_redone_by_exact_kernel_rank0": st[0], "candidates_per_row_rank0": st[1] / max(1, T - st[0]),
            "roofline": {"bound": "tensor", "achieved": flops / t / 1e12, "peak": pk * cx.world,
                         "peak_kind": cx.peak_kind, "unit": "TFLOP/s", "frac": flops / t / 1e12 / (pk * cx.world),
-                        "note": "ALGORITHMIC flops 2*64*T*I over the whole call (operand prep, threshold, "
-                                "filter, re-rank, all-gather, merge) against N x the measured bf16 peak"},
+                        "note": "ALGORITHMIC flops 2*64*T*I over the whole call (query operand prep, threshold, "
+                                "filter, re-rank, all-gather, merge; the shard's bf16 item operands are prepared once "
+                                "per scorer = per model version) against N x the measured bf16 peak"},
            "checksum": int(ids.to(torch.int64).sum().item()),
            "score_checksum": float(scs.double().sum().item())}
     if cx.world == 1:  # spot parity against the exact fp32 kernel on 256 rows
@@ -926,6 +927,10 @@ def shape_scoring(cx, n_users, n_items, T_q, mask_avg, reps=10):
         return s0.elapsed_time(s1) * 1e-3 / n, ids
 
     t_sc, ids = timed(ops.score_topk, reps)
+    # what an evaluation pays per query block: item operands prepared once per model version
+    prep = ops.TcItems(dI, sig_i, 40.0)
+    t_pr, pids = timed(lambda *a: ops.score_topk(*a, prepared=prep), reps)
+    assert torch.equal(pids, ids)
     t_ex, eids = timed(ops.score_topk_exact, 3)
     stats = torch.zeros(2, dtype=torch.int64, device=dev)
     Uq = ops.gather_rows(dU, q)
@@ -934,7 +939,8 @@ def shape_scoring(cx, n_users, n_items, T_q, mask_avg, reps=10):
     flops = 2.0 * D * T_q * n_items
     pk = cx.peaks["bf16_tflops"]
     return {"metric": "full_catalog_scores_per_sec", "value": T_q * n_items / t_sc, "unit": "scores/s",
-            "ms_per_eval": 1e3 * t_sc, "test_users": T_q, "items": n_items, "topk": TOPK,
+            "ms_per_eval": 1e3 * t_sc, "ms_per_eval_items_prepared": 1e3 * t_pr,
+            "test_users": T_q, "items": n_items, "topk": TOPK,
             "rows_redone_by_exact_kernel": st[0], "candidates_per_row": st[1] / max(1, T_q - st[0]),
             "roofline": {"bound": "tensor", "achieved": flops / t_sc / 1e12, "peak": pk, "unit": "TFLOP/s",
                          "frac": flops / t_sc / 1e12 / pk, "note": "algorithmic flops 2*64*T*I, whole call"},

@@ -308,6 +308,27 @@ int macr_score_topk_tc(const float *Uq, int T, const float *It, int64_t n_items,
                        int K, int32_t item_id_offset,
                        int32_t *out_ids, float *out_scores,
                        void *ws, size_t ws_bytes, int64_t *stats, macr_stream_t stream);
+/* The item-side operands of that path (bf16 rows scaled by sig_i, the -c*sig_i pieces, the largest
+ * item norm) depend on (It, sig_i, c) alone.  An evaluation scores many query blocks against ONE
+ * model (train.py:174-180 walks the test users in batches, batch_test.py:38-43 likewise), so the
+ * preparation can be done once per evaluation instead of once per call:
+ *   macr_score_tc_prepare_items   fills items_ws (macr_score_tc_items_bytes(n_items) bytes,
+ *                                 1024-byte aligned)
+ *   macr_score_topk_tc_prepared   macr_score_topk_tc without the item preparation; It, sig_i, c,
+ *                                 n_items must be the ones items_ws was prepared from (It and
+ *                                 sig_i are still read: the re-rank recomputes exact fp32 scores);
+ *                                 ws: macr_score_topk_tc_prepared_workspace_bytes(T, n_items, K).
+ * Same ids and scores, bit for bit, as macr_score_topk_tc. */
+size_t macr_score_tc_items_bytes(int64_t n_items);
+int macr_score_tc_prepare_items(const float *It, int64_t n_items, int d, const float *sig_i,
+                                float c, void *items_ws, size_t items_bytes, macr_stream_t stream);
+size_t macr_score_topk_tc_prepared_workspace_bytes(int T, int64_t n_items, int K);
+int macr_score_topk_tc_prepared(const float *Uq, int T, const float *It, int64_t n_items, int d,
+                                const float *sig_i, const float *sig_u, float c,
+                                const int32_t *mask_rowptr, const int32_t *mask_col,
+                                int K, int32_t item_id_offset,
+                                int32_t *out_ids, float *out_scores, const void *items_ws,
+                                void *ws, size_t ws_bytes, int64_t *stats, macr_stream_t stream);
 /* dense score matrix, the literal rubi_ratings_both fetch ([T][n_items] fp32, no mask) */
 int macr_score_matrix(const float *Uq, int T, const float *It, int64_t n_items, int d,
                       const float *sig_i, const float *sig_u, float c,

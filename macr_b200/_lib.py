@@ -92,6 +92,11 @@ PROTOTYPES = {
     "macr_score_topk_tc_workspace_bytes": (sz, [i32, i64, i32]),
     "macr_score_topk_tc": (i32, [vp, i32, vp, i64, i32, vp, vp, f32, vp, vp, i32, C.c_int32, vp, vp,
                                  vp, sz, vp, vp]),
+    "macr_score_tc_items_bytes": (sz, [i64]),
+    "macr_score_tc_prepare_items": (i32, [vp, i64, i32, vp, f32, vp, sz, vp]),
+    "macr_score_topk_tc_prepared_workspace_bytes": (sz, [i32, i64, i32]),
+    "macr_score_topk_tc_prepared": (i32, [vp, i32, vp, i64, i32, vp, vp, f32, vp, vp, i32, C.c_int32,
+                                          vp, vp, vp, vp, sz, vp, vp]),
     "macr_score_matrix": (i32, [vp, i32, vp, i64, i32, vp, vp, f32, vp, vp]),
     "macr_topk_merge": (i32, [vp, vp, i32, i32, i32, vp, vp, vp]),
     "macr_topk_rows": (i32, [vp, i32, i32, i32, vp, vp]),

@@ -946,7 +946,8 @@ struct Plan {
   int TB;        // query rows per row block
   int n_itiles, n_chunks, tiles_per_chunk;          // filter pass: the whole catalogue
   int stride, n_stiles, n_chunks_s, tiles_per_chunk_s, ld_g;  // maxima pass: the sampled tiles
-  size_t off_uhi, off_ihi, off_iaug, off_uaug, off_unorm, off_misc, off_gmax, off_thr, off_cand,
+  size_t scratch, off_items;  // bytes of per-call scratch; where macr_score_topk_tc keeps its items
+  size_t off_uhi, off_unorm, off_misc, off_gmax, off_thr, off_cand,
       off_cnt, off_fbrows, off_exact, total;
   size_t exact_bytes;
 };
@@ -970,6 +971,29 @@ static int pick_tiles_per_chunk(int utiles, int n_tiles, int nc_min, int nc_max)
     }
   }
   return (n_tiles + best - 1) / best;
+}
+
+// prepared item operands: bf16 rows scaled by sig_i, augmented rows (three bf16 pieces of
+// -c*sig_i; -inf for the padding rows), the user-side augmented tile, and the largest item norm
+struct ItemsLayout {
+  size_t off_ihi, off_iaug, off_uaug, off_norm, total;
+  long long n_pad;
+};
+static ItemsLayout items_layout(long long n_items) {
+  ItemsLayout L;
+  L.n_pad = (n_items + BN - 1) / BN * BN;  // items padded to whole tiles
+  size_t o = 0;
+  auto take = [&](size_t bytes) {
+    const size_t at = o;
+    o = align_up(o + bytes, 1024);
+    return at;
+  };
+  L.off_ihi = take((size_t)L.n_pad * kD * sizeof(oper_t));
+  L.off_iaug = take((size_t)L.n_pad * KA * sizeof(oper_t));
+  L.off_uaug = take((size_t)BM * KA * sizeof(oper_t));
+  L.off_norm = take(64);  // [0] item norm max (uint bits)
+  L.total = o;
+  return L;
 }
 
 static Plan make_plan(int T, long long n_items, int K) {
@@ -1018,12 +1042,8 @@ static Plan make_plan(int T, long long n_items, int K) {
     return at;
   };
   p.off_uhi = take((size_t)p.TB * kD * sizeof(oper_t));
-  const size_t n_pad = (size_t)p.n_itiles * BN;  // items padded to whole tiles
-  p.off_ihi = take(n_pad * kD * sizeof(oper_t));
-  p.off_iaug = take(n_pad * KA * sizeof(oper_t));
-  p.off_uaug = take((size_t)BM * KA * sizeof(oper_t));
   p.off_unorm = take((size_t)p.TB * 4);
-  p.off_misc = take(64);  // [0] item norm max (uint bits) [1] fb_count [2..3] cand_total (u64)
+  p.off_misc = take(64);  // [1] fb_count [2..3] cand_total (u64)
   p.off_gmax = take((size_t)p.TB * p.ld_g * 4);
   p.off_thr = take((size_t)p.TB * 8);
   p.off_cand = take((size_t)p.TB * kCap * 8);
@@ -1031,7 +1051,12 @@ static Plan make_plan(int T, long long n_items, int K) {
   p.off_fbrows = take((size_t)p.TB * 4);
   p.exact_bytes = score_exact_workspace_bytes(p.TB, n_items, K);
   p.off_exact = take(p.exact_bytes);
-  p.total = o + 1024;
+  // the item-side operands depend on (items, sig_i, c) alone: a caller that scores several query
+  // blocks against one model prepares them once (macr_score_tc_prepare_items) into its own
+  // buffer; macr_score_topk_tc keeps one behind its scratch
+  p.scratch = o;
+  p.off_items = o;
+  p.total = o + items_layout(n_items).total + 1024;
   return p;
 }
 
@@ -1075,38 +1100,71 @@ extern "C" size_t macr_score_topk_tc_workspace_bytes(int T, int64_t n_items, int
   return tc::make_plan(T, n_items, K).total;
 }
 
-extern "C" int macr_score_topk_tc(const float *Uq, int T, const float *It, int64_t n_items, int d,
-                                  const float *sig_i, const float *sig_u, float c,
-                                  const int32_t *mask_rowptr, const int32_t *mask_col, int K,
-                                  int32_t item_id_offset, int32_t *out_ids, float *out_scores,
-                                  void *ws, size_t ws_bytes, int64_t *stats,
-                                  macr_stream_t stream) {
+static int prepare_items(const float *It, long long n_items, const float *sig_i, float c,
+                         unsigned char *iw, cudaStream_t s) {
   using namespace tc;
-  MACR_CHECK_ARG(d == kD, "macr_score_topk_tc: d must be %d (got %d)", kD, d);
-  MACR_CHECK_ARG(K >= 1 && K <= 32, "macr_score_topk_tc: K must be in [1,32] (got %d)", K);
-  MACR_CHECK_ARG(T >= 0 && n_items >= 0, "macr_score_topk_tc: negative size");
-  if (T == 0) return MACR_OK;
-  MACR_CHECK_ARG(n_items >= 2048 && n_items < (1LL << 31) - BN,
-                 "macr_score_topk_tc: needs at least 2048 items (got %lld): use macr_score_topk",
+  const ItemsLayout L = items_layout(n_items);
+  oper_t *ihi = reinterpret_cast<oper_t *>(iw + L.off_ihi);
+  oper_t *iaug = reinterpret_cast<oper_t *>(iw + L.off_iaug);
+  oper_t *uaug = reinterpret_cast<oper_t *>(iw + L.off_uaug);
+  unsigned int *norm = reinterpret_cast<unsigned int *>(iw + L.off_norm);
+  MACR_CUDA(cudaMemsetAsync(norm, 0, 64, s));
+  split_rows_kernel<<<(unsigned)((L.n_pad * 16 + 255) / 256), 256, 0, s>>>(
+      It, n_items, L.n_pad, sig_i, c, ihi, iaug, nullptr, norm);
+  MACR_LAUNCH_CHECK();
+  fill_user_aug_kernel<<<(BM * KA + 255) / 256, 256, 0, s>>>(uaug);
+  MACR_LAUNCH_CHECK();
+  return MACR_OK;
+}
+
+static int check_tc_shape(const char *who, int d, int K, int T, int64_t n_items) {
+  using namespace tc;
+  MACR_CHECK_ARG(d == kD, "%s: d must be %d (got %d)", who, kD, d);
+  MACR_CHECK_ARG(K >= 1 && K <= 32, "%s: K must be in [1,32] (got %d)", who, K);
+  MACR_CHECK_ARG(T >= 0 && n_items >= 0, "%s: negative size", who);
+  MACR_CHECK_ARG(T == 0 || (n_items >= 2048 && n_items < (1LL << 31) - BN),
+                 "%s: needs at least 2048 items (got %lld): use macr_score_topk", who,
                  (long long)n_items);
-  MACR_CHECK_ARG(Uq && It && sig_i && sig_u && out_ids && out_scores && ws,
-                 "macr_score_topk_tc: null pointer");
-  MACR_CHECK_ARG((reinterpret_cast<uintptr_t>(ws) & 1023) == 0,
-                 "macr_score_topk_tc: workspace must be 1024-byte aligned");
-  const Plan p = make_plan(T, n_items, K);
-  if (ws_bytes < p.total)
-    return fail(MACR_ERR_WORKSPACE, "macr_score_topk_tc: workspace %zu < %zu bytes", ws_bytes,
-                p.total);
-  cudaStream_t s = as_stream(stream);
-  unsigned char *w = reinterpret_cast<unsigned char *>(ws);
+  return MACR_OK;
+}
+
+extern "C" size_t macr_score_tc_items_bytes(int64_t n_items) {
+  return n_items > 0 ? tc::items_layout(n_items).total : 1024;
+}
+
+extern "C" int macr_score_tc_prepare_items(const float *It, int64_t n_items, int d,
+                                           const float *sig_i, float c, void *items_ws,
+                                           size_t items_bytes, macr_stream_t stream) {
+  int rc = check_tc_shape("macr_score_tc_prepare_items", d, 1, 1, n_items);
+  if (rc) return rc;
+  MACR_CHECK_ARG(It && sig_i && items_ws, "macr_score_tc_prepare_items: null pointer");
+  MACR_CHECK_ARG((reinterpret_cast<uintptr_t>(items_ws) & 1023) == 0,
+                 "macr_score_tc_prepare_items: buffer must be 1024-byte aligned");
+  if (items_bytes < tc::items_layout(n_items).total)
+    return fail(MACR_ERR_WORKSPACE, "macr_score_tc_prepare_items: buffer %zu < %zu bytes",
+                items_bytes, tc::items_layout(n_items).total);
+  return prepare_items(It, n_items, sig_i, c, reinterpret_cast<unsigned char *>(items_ws),
+                       as_stream(stream));
+}
+
+// the passes, thresholds and re-rank of one call; `iw` holds the prepared item operands
+static int score_topk_tc_run(const float *Uq, int T, const float *It, int64_t n_items,
+                             const float *sig_i, const float *sig_u, float c,
+                             const int32_t *mask_rowptr, const int32_t *mask_col, int K,
+                             int32_t item_id_offset, int32_t *out_ids, float *out_scores,
+                             const unsigned char *iw, unsigned char *w, const tc::Plan &p,
+                             int64_t *stats, cudaStream_t s) {
+  using namespace tc;
+  const ItemsLayout L = items_layout(n_items);
   oper_t *uhi = reinterpret_cast<oper_t *>(w + p.off_uhi);
-  oper_t *ihi = reinterpret_cast<oper_t *>(w + p.off_ihi);
+  const oper_t *ihi = reinterpret_cast<const oper_t *>(iw + L.off_ihi);
   float *unorm = reinterpret_cast<float *>(w + p.off_unorm);
   unsigned int *misc = reinterpret_cast<unsigned int *>(w + p.off_misc);
+  const unsigned int *inorm_max = reinterpret_cast<const unsigned int *>(iw + L.off_norm);
   float *gmax = reinterpret_cast<float *>(w + p.off_gmax);
   float2 *thr = reinterpret_cast<float2 *>(w + p.off_thr);
-  oper_t *iaug = reinterpret_cast<oper_t *>(w + p.off_iaug);
-  oper_t *uaug = reinterpret_cast<oper_t *>(w + p.off_uaug);
+  const oper_t *iaug = reinterpret_cast<const oper_t *>(iw + L.off_iaug);
+  const oper_t *uaug = reinterpret_cast<const oper_t *>(iw + L.off_uaug);
   uint2 *cand = reinterpret_cast<uint2 *>(w + p.off_cand);
   int *cnt = reinterpret_cast<int *>(w + p.off_cnt);
   int32_t *fb_rows = reinterpret_cast<int32_t *>(w + p.off_fbrows);
@@ -1114,12 +1172,7 @@ extern "C" int macr_score_topk_tc(const float *Uq, int T, const float *It, int64
   unsigned long long *cand_total = reinterpret_cast<unsigned long long *>(misc + 2);
 
   MACR_CUDA(cudaMemsetAsync(misc, 0, 64, s));
-  const long long n_pad = (long long)p.n_itiles * BN;
-  split_rows_kernel<<<(unsigned)((n_pad * 16 + 255) / 256), 256, 0, s>>>(
-      It, n_items, n_pad, sig_i, c, ihi, iaug, nullptr, misc);
-  MACR_LAUNCH_CHECK();
-  fill_user_aug_kernel<<<(BM * KA + 255) / 256, 256, 0, s>>>(uaug);
-  MACR_LAUNCH_CHECK();
+  const long long n_pad = L.n_pad;
   CUtensorMap mih, mia, mua;
   int rc = make_map(&mih, ihi, n_pad, BN, kD);
   if (rc) return rc;
@@ -1159,7 +1212,7 @@ extern "C" int macr_score_topk_tc(const float *Uq, int T, const float *It, int64
     if (rc) return rc;
     MACR_CUDA(cudaMemsetAsync(cnt, 0, (size_t)nb * sizeof(int), s));
     row_threshold_kernel<<<(nb + 7) / 8, 256, 0, s>>>(gmax, nb, p.ld_g, p.ld_g, K, mrp, (int)n_items,
-                                                      unorm, misc, c, kappa_sum, thr, cnt);
+                                                      unorm, inorm_max, c, kappa_sum, thr, cnt);
     MACR_LAUNCH_CHECK();
     // ONE pass over the whole catalogue; train items are filtered inside it whenever a mask is given
     P.n_itiles = p.n_itiles;
@@ -1190,4 +1243,59 @@ extern "C" int macr_score_topk_tc(const float *Uq, int T, const float *It, int64
     }
   }
   return MACR_OK;
+}
+
+extern "C" int macr_score_topk_tc(const float *Uq, int T, const float *It, int64_t n_items, int d,
+                                  const float *sig_i, const float *sig_u, float c,
+                                  const int32_t *mask_rowptr, const int32_t *mask_col, int K,
+                                  int32_t item_id_offset, int32_t *out_ids, float *out_scores,
+                                  void *ws, size_t ws_bytes, int64_t *stats,
+                                  macr_stream_t stream) {
+  int rc = check_tc_shape("macr_score_topk_tc", d, K, T, n_items);
+  if (rc) return rc;
+  if (T == 0) return MACR_OK;
+  MACR_CHECK_ARG(Uq && It && sig_i && sig_u && out_ids && out_scores && ws,
+                 "macr_score_topk_tc: null pointer");
+  MACR_CHECK_ARG((reinterpret_cast<uintptr_t>(ws) & 1023) == 0,
+                 "macr_score_topk_tc: workspace must be 1024-byte aligned");
+  const tc::Plan p = tc::make_plan(T, n_items, K);
+  if (ws_bytes < p.total)
+    return fail(MACR_ERR_WORKSPACE, "macr_score_topk_tc: workspace %zu < %zu bytes", ws_bytes,
+                p.total);
+  unsigned char *w = reinterpret_cast<unsigned char *>(ws);
+  rc = prepare_items(It, n_items, sig_i, c, w + p.off_items, as_stream(stream));
+  if (rc) return rc;
+  return score_topk_tc_run(Uq, T, It, n_items, sig_i, sig_u, c, mask_rowptr, mask_col, K,
+                           item_id_offset, out_ids, out_scores, w + p.off_items, w, p, stats,
+                           as_stream(stream));
+}
+
+extern "C" size_t macr_score_topk_tc_prepared_workspace_bytes(int T, int64_t n_items, int K) {
+  if (T <= 0 || n_items <= 0 || K <= 0) return 1024;
+  return tc::make_plan(T, n_items, K).scratch + 1024;
+}
+
+extern "C" int macr_score_topk_tc_prepared(const float *Uq, int T, const float *It,
+                                           int64_t n_items, int d, const float *sig_i,
+                                           const float *sig_u, float c,
+                                           const int32_t *mask_rowptr, const int32_t *mask_col,
+                                           int K, int32_t item_id_offset, int32_t *out_ids,
+                                           float *out_scores, const void *items_ws, void *ws,
+                                           size_t ws_bytes, int64_t *stats, macr_stream_t stream) {
+  int rc = check_tc_shape("macr_score_topk_tc_prepared", d, K, T, n_items);
+  if (rc) return rc;
+  if (T == 0) return MACR_OK;
+  MACR_CHECK_ARG(Uq && It && sig_i && sig_u && out_ids && out_scores && ws && items_ws,
+                 "macr_score_topk_tc_prepared: null pointer");
+  MACR_CHECK_ARG((reinterpret_cast<uintptr_t>(ws) & 1023) == 0 &&
+                     (reinterpret_cast<uintptr_t>(items_ws) & 1023) == 0,
+                 "macr_score_topk_tc_prepared: buffers must be 1024-byte aligned");
+  const tc::Plan p = tc::make_plan(T, n_items, K);
+  if (ws_bytes < p.scratch)
+    return fail(MACR_ERR_WORKSPACE, "macr_score_topk_tc_prepared: workspace %zu < %zu bytes",
+                ws_bytes, p.scratch);
+  return score_topk_tc_run(Uq, T, It, n_items, sig_i, sig_u, c, mask_rowptr, mask_col, K,
+                           item_id_offset, out_ids, out_scores,
+                           reinterpret_cast<const unsigned char *>(items_ws),
+                           reinterpret_cast<unsigned char *>(ws), p, stats, as_stream(stream));
 }

@@ -1162,7 +1162,7 @@ int launch_adam_sweep2(float *var0, float *m0, float *v0, int64_t rows0, const u
 // owns dims 2l, 2l+1) are issued 4 entries at a time.  Segments longer than one unit leave
 // per-unit partials in `unit_part`; the last unit to arrive (per-segment ticket) adds them in
 // unit order, so the sum is order-deterministic.
-// Extra CTAs at the end of the grid reduce grad(w) = sum_b dsp_b*pe_b + dsn_b*ne_b and
+// Extra CTAs at the start of the grid reduce grad(w) = sum_b dsp_b*pe_b + dsn_b*ne_b and
 // grad(w_user) = sum_b dsu_b*ue_b into per-CTA partials (fixed composition, fixed order).
 // With tail.fused the last CTA of the whole grid (arrival ticket) also runs the step tail:
 // ApplyAdam on w / w_user, the loss reduction and the step-state advance.
@@ -1189,8 +1189,20 @@ __device__ void step_tail_body(float *w, float *mw, float *vw, float *wu, float 
   if (train) {
     const int k = tid & 63, which = (tid >> 6) & 1, grp = tid / (2 * kD);
     const float *src = which ? gwu_part : gw_part;
+    // partials q = grp, grp + GR, ... summed in that order; the loads go out 16 at a time (the
+    // whole step waits for this CTA: one round trip per partial was ~5 us at B = 4096)
     float a = 0.f;
-    for (int q = grp; q < n_part; q += GR) a += __ldcg(src + (long long)q * kD + k);
+    for (int q0 = grp; q0 < n_part; q0 += 16 * GR) {
+      float t[16];
+#pragma unroll
+      for (int j = 0; j < 16; ++j) {
+        const int q = q0 + j * GR;
+        t[j] = q < n_part ? __ldcg(src + (long long)q * kD + k) : 0.f;
+      }
+#pragma unroll
+      for (int j = 0; j < 16; ++j)
+        if (q0 + j * GR < n_part) a += t[j];
+    }
     shg[which * GR + grp][k] = a;
   }
   __syncthreads();
@@ -1232,8 +1244,11 @@ row_grads_kernel(const float *__restrict__ snap, const float *__restrict__ w,
   const int lane = threadIdx.x & 31, wl = threadIdx.x >> 5;
   const float *snapU = snap, *snapP = snap + (long long)B * kD, *snapN = snap + 2LL * B * kD;
 
-  if ((int)blockIdx.x >= pos_ctas) {  // ---- grad(w), grad(w_user) partials ----
-    const int cta = blockIdx.x - pos_ctas;
+  // the partial CTAs come FIRST in the grid: dispatched ahead of the row CTAs they are long done
+  // when the last row CTA retires and the step tail sums their output
+  const int w_ctas = (int)gridDim.x - pos_ctas;
+  if ((int)blockIdx.x < w_ctas) {  // ---- grad(w), grad(w_user) partials ----
+    const int cta = blockIdx.x;
     float2 aw = make_float2(0.f, 0.f), awu = make_float2(0.f, 0.f);
     const int b0 = cta * kWgradPerCta + wl * (kWgradPerCta / kRowWarps);
 #pragma unroll 4
@@ -1266,7 +1281,7 @@ row_grads_kernel(const float *__restrict__ snap, const float *__restrict__ w,
       reinterpret_cast<float2 *>(gwu_part + (long long)cta * kD)[lane] = c;
     }
   } else {
-    const int wid = blockIdx.x * kRowWarps + wl;  // one warp per sorted index: users, then items
+    const int wid = ((int)blockIdx.x - w_ctas) * kRowWarps + wl;  // one warp per sorted index: users, then items
     const bool item = wid >= B;
     const int k = item ? wid - B : wid;
     const PlanBufs &pl = item ? planI : planU;
@@ -1328,13 +1343,13 @@ row_grads_kernel(const float *__restrict__ snap, const float *__restrict__ w,
       for (int e0 = 0; e0 < cnt; e0 += 4) {
         float2 va[4], vb[4];
         float fa[4], fb[4], fs[4];
+        // partner rows first: their addresses need the plan record only, so these loads go out
+        // together with the coefficient loads above instead of behind them (a shuffle of `ca`
+        // waits for its load)
 #pragma unroll
         for (int q = 0; q < 4; ++q) {
           const int e = min(e0 + q, cnt - 1);
           const int ia = __shfl_sync(0xffffffffu, ra, e);
-          fa[q] = __shfl_sync(0xffffffffu, ca, e);
-          fb[q] = __shfl_sync(0xffffffffu, cb, e);
-          fs[q] = __shfl_sync(0xffffffffu, cs, e);
           if (item) {
             va[q] = reinterpret_cast<const float2 *>(snapU + (long long)ia * kD)[lane];
             vb[q] = make_float2(0.f, 0.f);
@@ -1342,6 +1357,13 @@ row_grads_kernel(const float *__restrict__ snap, const float *__restrict__ w,
             va[q] = reinterpret_cast<const float2 *>(snapP + (long long)ia * kD)[lane];
             vb[q] = reinterpret_cast<const float2 *>(snapN + (long long)ia * kD)[lane];
           }
+        }
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+          const int e = min(e0 + q, cnt - 1);
+          fa[q] = __shfl_sync(0xffffffffu, ca, e);
+          fb[q] = __shfl_sync(0xffffffffu, cb, e);
+          fs[q] = __shfl_sync(0xffffffffu, cs, e);
         }
 #pragma unroll
         for (int q = 0; q < 4; ++q) {

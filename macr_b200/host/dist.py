@@ -80,6 +80,15 @@ class ShardedScorer:
         if exchange == "p2p" and not self._want_p2p:
             raise ValueError("exchange='p2p' needs world > 1, CUDA and one rank per GPU (NCCL group)")
 
+    def _prepared(self, c, K):
+        """tensor-core operands of this rank's shard: items and gates are fixed for the scorer's
+        lifetime, so they are prepared once per c"""
+        if not (self.items.is_cuda and self.ops.uses_tc(self.items.shape[0], K)):
+            return None
+        if getattr(self, "_tc", None) is None or self._tc.c != float(c):
+            self._tc = self.ops.TcItems(self.items, self.sig_i, c)
+        return self._tc
+
     def _peer_buffers(self, T, K):
         """[cand ids | cand scores | result ids | result scores | flags] in ONE peer-mapped allocation,
         (re)built when the query shape changes; every rank maps every peer's copy."""
@@ -135,12 +144,12 @@ class ShardedScorer:
         st = self._peer_buffers(T, K) if self._want_p2p and T > 0 else None
         if st is None or not st["ok"]:
             ids, sc = ops.score_topk(Uq, self.items, self.sig_i, sig_u, c, mask_rowptr, mask_col, K,
-                                     item_id_offset=self.lo)
+                                     item_id_offset=self.lo, prepared=self._prepared(c, K))
             if self.world == 1:
                 return ids, sc
             return merge_shard_candidates(ops, ids, sc, self.world, self.group)
         ops.score_topk(Uq, self.items, self.sig_i, sig_u, c, mask_rowptr, mask_col, K, item_id_offset=self.lo,
-                       out=st["cand"])
+                       out=st["cand"], prepared=self._prepared(c, K))
         t = st["tabs"]
         self._epoch += 1
         ops.shard_barrier(t[4], self.rank, self.world, self._epoch, st["err"])  # every shard's candidates are complete
@@ -226,8 +235,12 @@ class UserShardedScorer:
         mrp = None
         if mask_rowptr is not None:
             mrp = mask_rowptr[lo:hi + 1].contiguous()  # absolute offsets into mask_col stay valid
+        if getattr(self, "_tc", None) is None or self._tc.c != float(c):
+            self._tc = self.ops.TcItems(self.items, self.sig_i, c) \
+                if self.items.is_cuda and self.ops.uses_tc(self.items.shape[0], K) else None
         return self.ops.score_topk(Uq[lo:hi].contiguous(), self.items, self.sig_i,
-                                   sig_u[lo:hi].contiguous(), c, mrp, mask_col, K)
+                                   sig_u[lo:hi].contiguous(), c, mrp, mask_col, K,
+                                   prepared=self._tc if hi > lo else None)
 
     def topk(self, Uq, sig_u, c, mask_rowptr, mask_col, K):
         ids, sc = self.topk_local(Uq, sig_u, c, mask_rowptr, mask_col, K)

@@ -80,10 +80,11 @@ class MFEvaluator:
         sums = {k: np.zeros(len(self.Ks)) for k in ("precision", "recall", "ndcg", "hit_ratio")}
         n_test_users, count = len(test_users), 0
         head = _HEAD_OF[_FETCH_OF[model_type]]
+        prep = {}  # item gates + tensor-core item operands: prepared by the first batch, shared by the rest
         for user_batch in _batches(test_users, self.batch_size):
             mrp, mcol = self.data.train_csr(user_batch)  # all_items - train_items, train.py:132-133
             if self.eval_mode == "fused":
-                ids, _ = model.topk(user_batch, Kmax, mrp, mcol, head=head)
+                ids, _ = model.topk(user_batch, Kmax, mrp, mcol, head=head, prep=prep)
                 ids = ids.cpu().numpy()
             else:  # literal: fetch the matrix, mask, rank on the host (heapq.nlargest order)
                 rate = sess.run(getattr(model, _FETCH_OF[model_type]),
@@ -127,12 +128,13 @@ class LGCNEvaluator:
         max_top = int(max(top_show))
         head = _HEAD_OF[_FETCH_OF[method]]
         all_result, count = [], 0
+        prep = {}  # item gates + tensor-core item operands of this evaluation
         for user_batch in _batches(users_to_test, self.batch_size):
             mrp, mcol = self.data.train_csr(user_batch) if train_set_flag == 0 else \
                 (np.zeros(len(user_batch) + 1, np.int32), np.zeros(0, np.int32))
             trp, tcol = self.data.truth_csr(user_batch)
             if self.eval_mode == "fused":
-                ids, _ = model.topk(user_batch, max_top, mrp, mcol, head=head)
+                ids, _ = model.topk(user_batch, max_top, mrp, mcol, head=head, prep=prep)
                 with torch.cuda.device(model.dev):
                     res = ops.foldout_metrics(ids, model._ids(trp), model._ids(tcol)).cpu().numpy()
             else:

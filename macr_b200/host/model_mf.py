@@ -75,19 +75,27 @@ class _ScoringMixin:
     def _ids(self, seq):
         return torch.as_tensor(np.ascontiguousarray(np.asarray(seq, dtype=np.int32))).to(self.dev)
 
+    def _head_c(self, head, c):
+        if head not in ("plain", "item", "both"):
+            raise ValueError(f"unknown score head {head!r}")
+        return 0.0 if head == "plain" else (self.rubi_c if c is None else float(c))
+
+    def _item_gate(self, Iq, w, head):
+        if head == "plain":
+            return torch.ones(Iq.shape[0], dtype=torch.float32, device=self.dev)
+        return ops.score_gates(Iq, w)
+
+    def _user_gate(self, Uq, wu, head):
+        if head != "both":
+            return torch.ones(Uq.shape[0], dtype=torch.float32, device=self.dev)
+        return ops.score_gates(Uq, wu)
+
     def _gates(self, Uq, Iq, w, wu, head, c):
         """(sig_i, sig_u, c) of a score head: "both" = rubi_ratings_both (model.py:199), "item" =
         rubi_ratings / rubi_ratings1 (model.py:141, LightGCN.py:442; x * 1.0 is exact, so the user
         gate is a vector of ones), "plain" = batch_ratings (((y - 0) * 1) * 1 == y exactly)."""
-        ones = lambda n: torch.ones(n, dtype=torch.float32, device=self.dev)
-        if head == "plain":
-            return ones(Iq.shape[0]), ones(Uq.shape[0]), 0.0
-        cc = self.rubi_c if c is None else float(c)
-        if head == "item":
-            return ops.score_gates(Iq, w), ones(Uq.shape[0]), cc
-        if head != "both":
-            raise ValueError(f"unknown score head {head!r}")
-        return ops.score_gates(Iq, w), ops.score_gates(Uq, wu), cc
+        cc = self._head_c(head, c)
+        return self._item_gate(Iq, w, head), self._user_gate(Uq, wu, head), cc
 
     def score_matrix(self, users, items=None, c=None, gated=True, head=None):
         """A score head (`head`; `gated` is the older both/plain switch) as a device tensor [B_u, n]."""
@@ -99,18 +107,31 @@ class _ScoringMixin:
             si, su, cc = self._gates(Uq, Iq, w, wu, head, c)
             return ops.score_matrix(Uq, Iq, si, su, cc)
 
-    def topk(self, users, K, mask_rowptr=None, mask_col=None, c=None, head="both"):
+    def topk(self, users, K, mask_rowptr=None, mask_col=None, c=None, head="both", prep=None):
         """Fused score + mask + top-K over the whole catalogue -> (ids [T,K], scores [T,K])
-        device tensors; masked = CSR over `users` of item ids to exclude (their train items)."""
+        device tensors; masked = CSR over `users` of item ids to exclude (their train items).
+        prep: a dict the caller keeps for as long as the parameters do not change (one evaluation:
+        train.py:174-180 / batch_test.py:38-43 walk the test users in batches against one model);
+        the item gates and the tensor-core item operands are then prepared by the first batch only."""
         Ut, It, w, wu = self._score_tables()
         with torch.cuda.device(self.dev):
             Uq = ops.gather_rows(Ut, self._ids(users))
-            si, su, cc = self._gates(Uq, It, w, wu, head, c)
             mrp = None if mask_rowptr is None else self._ids(mask_rowptr)
             mcol = None if mask_col is None else self._ids(mask_col)
             if mcol is not None and mcol.numel() == 0:
                 mcol = torch.zeros(1, dtype=torch.int32, device=self.dev)
-            return ops.score_topk(Uq, It, si, su, cc, mrp, mcol, K)
+            if prep is None:
+                si, su, cc = self._gates(Uq, It, w, wu, head, c)
+                return ops.score_topk(Uq, It, si, su, cc, mrp, mcol, K)
+            cc = self._head_c(head, c)
+            key = (head, cc, It.data_ptr())
+            if key not in prep:
+                si = self._item_gate(It, w, head)
+                items = ops.TcItems(It, si, cc) if ops.uses_tc(It.shape[0], K) else None
+                prep[key] = (It, si, items)  # `It` kept alive: the key holds its address
+            _, si, items = prep[key]
+            su = self._user_gate(Uq, wu, head)
+            return ops.score_topk(Uq, It, si, su, cc, mrp, mcol, K, prepared=items)
 
     def _is_full_range(self, items):
         n = self.n_items

@@ -180,28 +180,72 @@ def _topk_out(out, T, K, dev):
     return _cuda(ids, torch.int32), _cuda(sc, torch.float32)
 
 
-def score_topk_tc(Uq, It, sig_i, sig_u, c, mask_rowptr, mask_col, K, item_id_offset=0, stats=None, out=None):
+def _aligned_bytes(nbytes, dev):
+    """-> (owner tensor, 1024-byte aligned address) of a device scratch buffer"""
+    buf = torch.empty(nbytes + 1024, dtype=torch.uint8, device=dev)
+    return buf, buf.data_ptr() + (-buf.data_ptr()) % 1024
+
+
+class TcItems:
+    """Item-side operands of the tensor-core scoring path (bf16 rows scaled by sig_i, the
+    -c*sig_i pieces), prepared ONCE for (It, sig_i, c) and reused by every query block scored
+    against them: `score_topk(..., prepared=TcItems(It, sig_i, c))`.  The caller vouches that
+    It / sig_i do not change while the object is in use (one evaluation, one scorer)."""
+
+    def __init__(self, It, sig_i, c):
+        self.It, self.sig_i, self.c = _cuda(It, torch.float32), _cuda(sig_i, torch.float32), float(c)
+        n_items = It.shape[0]
+        self.nbytes = lib().macr_score_tc_items_bytes(n_items)
+        self._buf, self.ptr = _aligned_bytes(self.nbytes, It.device)
+        check(lib().macr_score_tc_prepare_items(_f(self.It), n_items, It.shape[1], _f(self.sig_i), self.c,
+                                                C.c_void_p(self.ptr), self.nbytes, stream_ptr()),
+              "macr_score_tc_prepare_items")
+
+    def matches(self, It, sig_i, c):
+        return It.data_ptr() == self.It.data_ptr() and It.shape == self.It.shape and \
+            sig_i.data_ptr() == self.sig_i.data_ptr() and float(c) == self.c
+
+
+def score_topk_tc(Uq, It, sig_i, sig_u, c, mask_rowptr, mask_col, K, item_id_offset=0, stats=None, out=None,
+                  prepared=None):
     """Tensor-core (tcgen05 + TMA) score + mask + top-K; bit-identical to `score_topk_exact`.
-    stats: optional int64[2] device tensor, += {rows re-done by the exact kernel, candidates}."""
+    stats: optional int64[2] device tensor, += {rows re-done by the exact kernel, candidates}.
+    prepared: a `TcItems` of the same (It, sig_i, c) -- skips the per-call item preparation."""
     T, n_items = Uq.shape[0], It.shape[0]
     dev = Uq.device
     ids, sc = _topk_out(out, T, K, dev)
+    if prepared is not None:
+        if not prepared.matches(It, sig_i, c):
+            raise MacrError("score_topk_tc: `prepared` was built from other items / gates / c")
+        nbytes = lib().macr_score_topk_tc_prepared_workspace_bytes(T, n_items, K)
+        ws, at = _aligned_bytes(nbytes, dev)
+        check(lib().macr_score_topk_tc_prepared(_f(Uq), T, _f(It), n_items, Uq.shape[1], _f(sig_i), _f(sig_u),
+                                                c, ptr(mask_rowptr), ptr(mask_col), K, item_id_offset,
+                                                ptr(ids), ptr(sc), C.c_void_p(prepared.ptr), C.c_void_p(at),
+                                                nbytes, ptr(stats), stream_ptr()),
+              "macr_score_topk_tc_prepared")
+        return ids, sc
     nbytes = lib().macr_score_topk_tc_workspace_bytes(T, n_items, K)
-    ws = torch.empty(nbytes + 1024, dtype=torch.uint8, device=dev)
-    off = (-ws.data_ptr()) % 1024
+    ws, at = _aligned_bytes(nbytes, dev)
     check(lib().macr_score_topk_tc(_f(Uq), T, _f(It), n_items, Uq.shape[1], _f(sig_i), _f(sig_u), c,
                                    ptr(mask_rowptr), ptr(mask_col), K, item_id_offset, ptr(ids),
-                                   ptr(sc), C.c_void_p(ws.data_ptr() + off), nbytes, ptr(stats),
+                                   ptr(sc), C.c_void_p(at), nbytes, ptr(stats),
                                    stream_ptr()), "macr_score_topk_tc")
     return ids, sc
 
 
-def score_topk(Uq, It, sig_i, sig_u, c, mask_rowptr, mask_col, K, item_id_offset=0, out=None):
+def uses_tc(n_items, K, T=1):
+    """does `score_topk` take the tensor-core path for this shape?"""
+    return n_items >= TC_MIN_ITEMS and K <= 32 and T > 0
+
+
+def score_topk(Uq, It, sig_i, sig_u, c, mask_rowptr, mask_col, K, item_id_offset=0, out=None, prepared=None):
     """Fused score + mask + top-K. -> (ids [T,K] int32 global ids, scores [T,K] fp32).
     Catalogues of at least TC_MIN_ITEMS items go to the tcgen05 path, smaller ones to the exact
-    fp32 kernel; both give the same bits."""
-    if It.shape[0] >= TC_MIN_ITEMS and K <= 32 and Uq.shape[0] > 0:
-        return score_topk_tc(Uq, It, sig_i, sig_u, c, mask_rowptr, mask_col, K, item_id_offset, out=out)
+    fp32 kernel; both give the same bits.  prepared: optional `TcItems` (tensor-core path only)."""
+    if uses_tc(It.shape[0], K, Uq.shape[0]):
+        return score_topk_tc(Uq, It, sig_i, sig_u, c, mask_rowptr, mask_col, K, item_id_offset, out=out,
+                             prepared=prepared)
     return score_topk_exact(Uq, It, sig_i, sig_u, c, mask_rowptr, mask_col, K, item_id_offset, out=out)
 
 

@@ -375,3 +375,40 @@ def test_epoch_path_equals_stepwise_session_loop():
         assert torch.equal(x, y)
     a.close()
     b.close()
+
+
+def test_facade_topk_with_an_evaluation_cache_equals_the_plain_call():
+    """`model.topk(..., prep=cache)` (what both evaluators pass: item gates and tensor-core item
+    operands prepared by the first user batch of an evaluation, reused by the others) returns the
+    ids and scores of the plain call bit for bit -- tensor-core catalogue (5000 items), all three
+    score heads; a parameter change between evaluations is picked up by a fresh cache."""
+    import torch
+
+    from macr_b200.host.model_mf import BPRMF
+
+    n_users, n_items, K = 300, 5000, 20
+    model = BPRMF(mf_args(), {"n_users": n_users, "n_items": n_items})
+    with torch.no_grad():
+        model.trainer.tab.U.mul_(8.0), model.trainer.tab.I.mul_(8.0)
+    model.update_c(None, 30.0)
+    rng = np.random.RandomState(2)
+    batches = [list(range(0, 130)), list(range(130, 131)), list(range(131, 300))]
+    masks = []
+    for b in batches:
+        rows = [np.sort(rng.choice(n_items, size=rng.randint(0, 40), replace=False)) for _ in b]
+        rp = np.zeros(len(b) + 1, np.int32)
+        rp[1:] = np.cumsum([len(r) for r in rows])
+        masks.append((rp, np.concatenate(rows).astype(np.int32) if rp[-1] else np.zeros(0, np.int32)))
+    for head in ("both", "item", "plain"):
+        cache = {}
+        for b, (rp, col) in zip(batches, masks):
+            want_i, want_s = model.topk(b, K, rp, col, head=head)
+            got_i, got_s = model.topk(b, K, rp, col, head=head, prep=cache)
+            assert torch.equal(got_i, want_i) and torch.equal(got_s, want_s)
+        assert len(cache) == 1
+    with torch.no_grad():
+        model.trainer.tab.I.mul_(0.5)
+    want_i, _ = model.topk(batches[0], K, *masks[0])
+    got_i, _ = model.topk(batches[0], K, *masks[0], prep={})
+    assert torch.equal(got_i, want_i)
+    model.close()

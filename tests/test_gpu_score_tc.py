@@ -174,3 +174,28 @@ def test_tc_argument_errors(T, ops):
         ops.score_topk_tc(U, I, s, s[:4], 40.0, None, None, 20)
     ids, _ = ops.score_topk(U, I, s, s[:4], 40.0, None, None, 20)  # dispatcher -> exact kernel
     assert ids.shape == (4, 20)
+
+
+def test_tc_prepared_items_give_the_same_bits(T, ops):
+    """`macr_score_tc_prepare_items` + `macr_score_topk_tc_prepared` (item operands prepared once
+    per evaluation, query blocks of different sizes scored against them) == `macr_score_topk_tc`
+    bit for bit; operands prepared from other items / another c are refused."""
+    n_items, K, c = 6000, 20, 40.0
+    U, I, w, wu = make_model(11, 700, n_items, scale=10.0)
+    mrp, mcol = lists_to_csr(make_interactions(3, 700, n_items, 25))
+    dU, dI, gsi, gsu = _gates(T, ops, U, I, w, wu)
+    prep = ops.TcItems(dI, gsi, c)
+    for lo, hi in ((0, 300), (300, 301), (301, 700)):   # three blocks, three plans
+        m = (mrp[lo:hi + 1] - mrp[lo]).astype(np.int32)
+        mc = mcol[mrp[lo]:mrp[hi]]
+        args = (dU[lo:hi].contiguous(), dI, gsi, gsu[lo:hi].contiguous(), c, dev(T, m), dev(T, mc), K)
+        want_i, want_s = ops.score_topk_tc(*args)
+        stats = T.zeros(2, dtype=T.int64, device="cuda")
+        got_i, got_s = ops.score_topk(*args, prepared=prep)
+        assert bool((got_i == want_i).all().item()) and bool((got_s == want_s).all().item())
+        got_i, got_s = ops.score_topk_tc(*args, stats=stats, prepared=prep)
+        assert bool((got_i == want_i).all().item()) and int(stats[0].item()) == 0
+    with pytest.raises(ops.MacrError):
+        ops.score_topk_tc(dU, dI, gsi, gsu, c + 1.0, None, None, K, prepared=prep)
+    with pytest.raises(ops.MacrError):
+        ops.score_topk_tc(dU, dI.clone(), gsi, gsu, c, None, None, K, prepared=prep)
