@@ -19,6 +19,15 @@ int fail(int code, const char *fmt, ...) {
   return code;
 }
 
+bool pdl_enabled() {
+  static int on = -1;
+  if (on < 0) {
+    const char *e = getenv("MACR_PDL");
+    on = (e && e[0] == '1') ? 1 : 0;
+  }
+  return on == 1;
+}
+
 int sm_count() {
   static int sms = 0;
   if (sms == 0) {

@@ -32,6 +32,31 @@ inline cudaStream_t as_stream(macr_stream_t s) { return reinterpret_cast<cudaStr
 
 int sm_count();
 
+// Programmatic dependent launch (MACR_PDL=1): a kernel launched with launch_k(..., pdl = true)
+// may become resident while its predecessor in the stream still runs; it must execute
+// pdl_wait() before it touches anything the predecessor reads or writes (the wait returns once
+// every prerequisite grid has completed and flushed).  The predecessor opens the window with
+// pdl_trigger() (all of its CTAs must have issued it or exited).  Both are no-ops otherwise.
+bool pdl_enabled();
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void pdl_trigger() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+
+template <class... KArgs, class... Args>
+inline cudaError_t launch_k(void (*kern)(KArgs...), dim3 grid, dim3 block, size_t smem,
+                            cudaStream_t s, bool pdl, Args... args) {
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = grid;
+  cfg.blockDim = block;
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = s;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = (pdl && pdl_enabled()) ? 1 : 0;
+  return cudaLaunchKernelEx(&cfg, kern, KArgs(args)...);
+}
+
 constexpr int kD = MACR_EMBED_DIM;  // embedding width every kernel is specialised for
 constexpr float kBceEps = 1e-10f;   // "+1e-10" of macr_mf/model.py:211
 

@@ -63,6 +63,7 @@ gather_dots_kernel(const float *__restrict__ Ue, const float *__restrict__ Ie,
                    int B, float *__restrict__ yp, float *__restrict__ yn, float *__restrict__ sp,
                    float *__restrict__ sn, float *__restrict__ su, float *__restrict__ regsq,
                    float *__restrict__ snap, GateOut gates) {
+  pdl_trigger();  // the grid kernel's CTAs may take their slots (they wait for this grid's results)
   const int lane = threadIdx.x & 31;
   const int b = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   if (b >= B) return;
@@ -401,6 +402,8 @@ grid_bce_kernel(const float *__restrict__ yp, const float *__restrict__ yn, int 
 
   const int tid = threadIdx.x, tx = tid & 15, ty = tid >> 4;
   const int Bpad = ws.Bpad;
+  pdl_wait();     // dots and gates of the batch (gather_dots / gate kernel) are complete
+  pdl_trigger();  // row_grads' CTAs may queue behind this grid's last wave
   if ((int)blockIdx.y >= ws.nblk_i) {  // folders ride at the end of the grid
     const int f = (blockIdx.y - ws.nblk_i) * gridDim.x + blockIdx.x;
     if (f == 0)
@@ -677,15 +680,15 @@ int launch_gates(const float *sp, const float *sn, const float *su, int B, const
 
 template <int RI, int RJ, int MINB, bool kGrad>
 static void launch_grid_t(const float *yp, const float *yn, int B, float alpha, float beta,
-                          const GridWs &ws, const GridOut &out, cudaStream_t s) {
+                          const GridWs &ws, const GridOut &out, cudaStream_t s, bool pdl) {
   // tiles, then the loss folder and (grad only) one folder CTA per row band and per column band
   const int folders = 1 + (kGrad ? ws.nblk_i + ws.nblk_j : 0);
   const int fold_rows = (folders + ws.ngrp_j - 1) / ws.ngrp_j;
   dim3 grid(ws.ngrp_j, ws.nblk_i + fold_rows);
   if (B % ws.tile_i == 0 && B % ws.tile_j == 0)
-    grid_bce_kernel<RI, RJ, MINB, false, kGrad><<<grid, 256, 0, s>>>(yp, yn, B, alpha, beta, ws, out);
+    launch_k(grid_bce_kernel<RI, RJ, MINB, false, kGrad>, grid, dim3(256), 0, s, pdl, yp, yn, B, alpha, beta, ws, out);
   else
-    grid_bce_kernel<RI, RJ, MINB, true, kGrad><<<grid, 256, 0, s>>>(yp, yn, B, alpha, beta, ws, out);
+    launch_k(grid_bce_kernel<RI, RJ, MINB, true, kGrad>, grid, dim3(256), 0, s, pdl, yp, yn, B, alpha, beta, ws, out);
 }
 
 // the partial-sum slots of `ws` (first ws.part_bytes bytes) must hold 0xff bytes before the first
@@ -694,14 +697,14 @@ static void launch_grid_t(const float *yp, const float *yn, int B, float alpha, 
 int launch_grid_bce(const float *yp, const float *yn, int B, const macr_hparams &hp,
                     const GridWs &ws, float *d_yp, float *d_yn, float *d_sp, float *d_sn,
                     float *d_su, int want_grad, const float *regsq, const StepState *st,
-                    float *losses3, cudaStream_t s) {
+                    float *losses3, cudaStream_t s, bool pdl) {
   const float alpha = hp.alpha, beta = hp.beta;
   const GridOut out{d_yp, d_yn, d_sp, d_sn, d_su, regsq, hp, st, losses3};
   const int ri = ws.tile_i / 16, rj = ws.tile_j / 16;
 #define MACR_GRID_CASE(RI_, RJ_, MINB_)                                                          \
   if (ri == RI_ && rj == RJ_) {                                                                   \
-    if (want_grad) launch_grid_t<RI_, RJ_, MINB_, true>(yp, yn, B, alpha, beta, ws, out, s);      \
-    else launch_grid_t<RI_, RJ_, MINB_, false>(yp, yn, B, alpha, beta, ws, out, s);               \
+    if (want_grad) launch_grid_t<RI_, RJ_, MINB_, true>(yp, yn, B, alpha, beta, ws, out, s, pdl); \
+    else launch_grid_t<RI_, RJ_, MINB_, false>(yp, yn, B, alpha, beta, ws, out, s, pdl);          \
   } else
   MACR_GRID_CASE(8, 8, 2)
   MACR_GRID_CASE(4, 8, 3)
@@ -1164,7 +1167,7 @@ int launch_adam_sweep2(float *var0, float *m0, float *v0, int64_t rows0, const u
 // unit order, so the sum is order-deterministic.
 // Extra CTAs at the start of the grid reduce grad(w) = sum_b dsp_b*pe_b + dsn_b*ne_b and
 // grad(w_user) = sum_b dsu_b*ue_b into per-CTA partials (fixed composition, fixed order).
-// With tail.fused the last CTA of the whole grid (arrival ticket) also runs the step tail:
+// With tail.fused one more CTA at the end of the grid waits for every warp's signal and runs the step tail:
 // ApplyAdam on w / w_user, the loss reduction and the step-state advance.
 // ---------------------------------------------------------------------------------------------
 constexpr int kRowWarps = 8;
@@ -1240,13 +1243,34 @@ row_grads_kernel(const float *__restrict__ snap, const float *__restrict__ w,
                  float *__restrict__ gwu_part, AdamTabs tabs, TailArgs tail) {
   __shared__ float2 sW[kRowWarps][32], sWU[kRowWarps][32];
   __shared__ float sTailG[2 * (kRowWarps * 32 / (2 * kD))][kD];
-  __shared__ int sLast;
   const int lane = threadIdx.x & 31, wl = threadIdx.x >> 5;
   const float *snapU = snap, *snapP = snap + (long long)B * kD, *snapN = snap + 2LL * B * kD;
+  pdl_wait();  // the grid's folders have written d_yp .. d_su (and everything before them is done)
 
-  // the partial CTAs come FIRST in the grid: dispatched ahead of the row CTAs they are long done
-  // when the last row CTA retires and the step tail sums their output
-  const int w_ctas = (int)gridDim.x - pos_ctas;
+  // grid = [partial CTAs | row CTAs | tail CTA (tail.fused)].  The partial CTAs come FIRST:
+  // dispatched ahead of the row CTAs they are long done when the last row warp retires.
+  const int w_ctas = (int)gridDim.x - pos_ctas - (tail.fused ? 1 : 0);
+  if (tail.fused && blockIdx.x == gridDim.x - 1) {
+    // ---- the step tail: the LAST CTA of the grid waits until every other warp of the kernel has
+    // signalled (all of them are resident or done by the time this CTA is dispatched), then runs
+    // ApplyAdam on w / w_user and advances the step state.  No other CTA waits for anything: a
+    // row warp signals and retires (the CTA-wide barrier + ticket round trip that used to end
+    // every CTA was the kernel's largest stall).
+    if (threadIdx.x == 0) {
+      const unsigned expected = (unsigned)w_ctas + (unsigned)pos_ctas * kRowWarps;
+      unsigned seen = 0;
+      for (long long spin = 0; spin < (1LL << 24); ++spin) {  // bounded: a lost signal must not hang the GPU
+        asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(seen) : "l"(tail.ticket) : "memory");
+        if (seen >= expected) break;
+        __nanosleep(64);
+      }
+      *tail.ticket = 0;  // re-armed for the next step
+    }
+    __syncthreads();
+    step_tail_body<kRowWarps * 32>(tail.w, tail.mw, tail.vw, tail.wu, tail.mwu, tail.vwu, gw_part,
+                                   gwu_part, w_ctas, tail.hp, tail.st, 1 | (tail.frozen << 1), sTailG);
+    return;
+  }
   if ((int)blockIdx.x < w_ctas) {  // ---- grad(w), grad(w_user) partials ----
     const int cta = blockIdx.x;
     float2 aw = make_float2(0.f, 0.f), awu = make_float2(0.f, 0.f);
@@ -1279,7 +1303,15 @@ row_grads_kernel(const float *__restrict__ snap, const float *__restrict__ w,
       }
       reinterpret_cast<float2 *>(gw_part + (long long)cta * kD)[lane] = a;
       reinterpret_cast<float2 *>(gwu_part + (long long)cta * kD)[lane] = c;
+      if (tail.fused) {
+        __syncwarp();
+        if (lane == 0) {
+          __threadfence();
+          atomicAdd(tail.ticket, 1u);
+        }
+      }
     }
+    return;
   } else {
     const int wid = ((int)blockIdx.x - w_ctas) * kRowWarps + wl;  // one warp per sorted index: users, then items
     const bool item = wid >= B;
@@ -1434,22 +1466,12 @@ row_grads_kernel(const float *__restrict__ snap, const float *__restrict__ w,
     }
   }
   if (!tail.fused) return;
-  // ---- last CTA of the grid: the step tail ----
-  __syncthreads();
-  if (threadIdx.x == 0) {
-    __threadfence();  // cumulative over the CTA's writes ordered by the barrier above
-    const bool last = atomicAdd(tail.ticket, 1u) == gridDim.x - 1;
-    if (last) {
-      __threadfence();
-      *tail.ticket = 0;  // re-armed for the next step
-    }
-    sLast = last;
+  // this warp's rows (var / m / v, bitmap bits) are written: signal the tail CTA and retire
+  __syncwarp();
+  if (lane == 0) {
+    __threadfence();
+    atomicAdd(tail.ticket, 1u);
   }
-  __syncthreads();
-  if (!sLast) return;
-  step_tail_body<kRowWarps * 32>(tail.w, tail.mw, tail.vw, tail.wu, tail.mwu, tail.vwu, gw_part,
-                                 gwu_part, gridDim.x - pos_ctas, tail.hp, tail.st,
-                                 1 | (tail.frozen << 1), sTailG);
 }
 
 int row_grads_max_parts(int B) { return (B + kWgradPerCta - 1) / kWgradPerCta; }
@@ -1459,16 +1481,16 @@ int launch_row_grads(const float *snap, const float *w, const float *wu, int B, 
                      const float *d_yn, const float *d_sp, const float *d_sn, const float *d_su,
                      float lam, PlanBufs planU, PlanBufs planI, float *gU, float *gI,
                      float *unit_part, float *gw_part, float *gwu_part, int *n_part,
-                     const AdamTabs *tabs, const TailArgs *tail, cudaStream_t s) {
+                     const AdamTabs *tabs, const TailArgs *tail, cudaStream_t s, bool pdl) {
   const int pos_ctas = (3 * B + kRowWarps - 1) / kRowWarps;
   const int w_ctas = row_grads_max_parts(B);
   AdamTabs tb{};
   if (tabs) tb = *tabs;
   TailArgs tl{};
   if (tail) tl = *tail;
-  row_grads_kernel<<<pos_ctas + w_ctas, kRowWarps * 32, 0, s>>>(
-      snap, w, wu, B, d_yp, d_yn, d_sp, d_sn, d_su, lam, planU, planI, gU, gI, unit_part, pos_ctas,
-      gw_part, gwu_part, tb, tl);
+  launch_k(row_grads_kernel, dim3(pos_ctas + w_ctas + (tl.fused ? 1 : 0)), dim3(kRowWarps * 32), 0, s, pdl,
+           snap, w, wu, B, d_yp, d_yn, d_sp, d_sn, d_su, lam, planU, planI, gU, gI, unit_part, pos_ctas,
+           gw_part, gwu_part, tb, tl);
   MACR_LAUNCH_CHECK();
   if (n_part) *n_part = w_ctas;
   return MACR_OK;

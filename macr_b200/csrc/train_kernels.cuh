@@ -67,7 +67,7 @@ int launch_gates(const float *sp, const float *sn, const float *su, int B, const
 int launch_grid_bce(const float *yp, const float *yn, int B, const macr_hparams &hp,
                     const GridWs &ws, float *d_yp, float *d_yn, float *d_sp, float *d_sn,
                     float *d_su, int want_grad, const float *regsq, const StepState *st,
-                    float *losses3, cudaStream_t s);
+                    float *losses3, cudaStream_t s, bool pdl = false);
 // `--train normalbce`: element-wise BCE on (yp, yn) instead of the B x B grid
 int launch_plain_bce(const float *yp, const float *yn, int B, const macr_hparams &hp,
                      const float *regsq, const StepState *st, float *losses_direct, float *d_yp,
@@ -106,7 +106,7 @@ int launch_row_grads(const float *snap, const float *w, const float *wu, int B, 
                      const float *d_yn, const float *d_sp, const float *d_sn, const float *d_su,
                      float lam, PlanBufs planU, PlanBufs planI, float *gU, float *gI,
                      float *unit_part, float *gw_part, float *gwu_part, int *n_part,
-                     const AdamTabs *tabs, const TailArgs *tail, cudaStream_t s);
+                     const AdamTabs *tabs, const TailArgs *tail, cudaStream_t s, bool pdl = false);
 int launch_adam_rows2(float *U, float *mU, float *vU, PlanBufs planU, const float *gU,
                       uint32_t *bmU, float *I, float *mI, float *vI, PlanBufs planI,
                       const float *gI, uint32_t *bmI, int max_rows, float lr_t,
