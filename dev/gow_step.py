@@ -4,6 +4,9 @@ import os, sys, time
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import numpy as np
 import bench
+from macr_b200 import _lib
+if os.environ.get("MACR_LIB"):
+    _lib.LIB_PATH = os.environ["MACR_LIB"]  # A/B against an older build
 cx = bench.Ctx()
 torch = cx.torch
 from macr_b200 import ops

@@ -1167,7 +1167,7 @@ int launch_adam_sweep2(float *var0, float *m0, float *v0, int64_t rows0, const u
 // unit order, so the sum is order-deterministic.
 // Extra CTAs at the start of the grid reduce grad(w) = sum_b dsp_b*pe_b + dsn_b*ne_b and
 // grad(w_user) = sum_b dsu_b*ue_b into per-CTA partials (fixed composition, fixed order).
-// With tail.fused one more CTA at the end of the grid waits for every warp's signal and runs the step tail:
+// With tail.fused the last CTA of the whole grid (arrival ticket) also runs the step tail:
 // ApplyAdam on w / w_user, the loss reduction and the step-state advance.
 // ---------------------------------------------------------------------------------------------
 constexpr int kRowWarps = 8;
@@ -1243,34 +1243,14 @@ row_grads_kernel(const float *__restrict__ snap, const float *__restrict__ w,
                  float *__restrict__ gwu_part, AdamTabs tabs, TailArgs tail) {
   __shared__ float2 sW[kRowWarps][32], sWU[kRowWarps][32];
   __shared__ float sTailG[2 * (kRowWarps * 32 / (2 * kD))][kD];
+  __shared__ int sLast;
   const int lane = threadIdx.x & 31, wl = threadIdx.x >> 5;
   const float *snapU = snap, *snapP = snap + (long long)B * kD, *snapN = snap + 2LL * B * kD;
   pdl_wait();  // the grid's folders have written d_yp .. d_su (and everything before them is done)
 
-  // grid = [partial CTAs | row CTAs | tail CTA (tail.fused)].  The partial CTAs come FIRST:
-  // dispatched ahead of the row CTAs they are long done when the last row warp retires.
-  const int w_ctas = (int)gridDim.x - pos_ctas - (tail.fused ? 1 : 0);
-  if (tail.fused && blockIdx.x == gridDim.x - 1) {
-    // ---- the step tail: the LAST CTA of the grid waits until every other warp of the kernel has
-    // signalled (all of them are resident or done by the time this CTA is dispatched), then runs
-    // ApplyAdam on w / w_user and advances the step state.  No other CTA waits for anything: a
-    // row warp signals and retires (the CTA-wide barrier + ticket round trip that used to end
-    // every CTA was the kernel's largest stall).
-    if (threadIdx.x == 0) {
-      const unsigned expected = (unsigned)w_ctas + (unsigned)pos_ctas * kRowWarps;
-      unsigned seen = 0;
-      for (long long spin = 0; spin < (1LL << 24); ++spin) {  // bounded: a lost signal must not hang the GPU
-        asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(seen) : "l"(tail.ticket) : "memory");
-        if (seen >= expected) break;
-        __nanosleep(64);
-      }
-      *tail.ticket = 0;  // re-armed for the next step
-    }
-    __syncthreads();
-    step_tail_body<kRowWarps * 32>(tail.w, tail.mw, tail.vw, tail.wu, tail.mwu, tail.vwu, gw_part,
-                                   gwu_part, w_ctas, tail.hp, tail.st, 1 | (tail.frozen << 1), sTailG);
-    return;
-  }
+  // the partial CTAs come FIRST in the grid: dispatched ahead of the row CTAs they are long done
+  // when the last row CTA retires and the step tail sums their output
+  const int w_ctas = (int)gridDim.x - pos_ctas;
   if ((int)blockIdx.x < w_ctas) {  // ---- grad(w), grad(w_user) partials ----
     const int cta = blockIdx.x;
     float2 aw = make_float2(0.f, 0.f), awu = make_float2(0.f, 0.f);
@@ -1303,15 +1283,7 @@ row_grads_kernel(const float *__restrict__ snap, const float *__restrict__ w,
       }
       reinterpret_cast<float2 *>(gw_part + (long long)cta * kD)[lane] = a;
       reinterpret_cast<float2 *>(gwu_part + (long long)cta * kD)[lane] = c;
-      if (tail.fused) {
-        __syncwarp();
-        if (lane == 0) {
-          __threadfence();
-          atomicAdd(tail.ticket, 1u);
-        }
-      }
     }
-    return;
   } else {
     const int wid = ((int)blockIdx.x - w_ctas) * kRowWarps + wl;  // one warp per sorted index: users, then items
     const bool item = wid >= B;
@@ -1466,12 +1438,22 @@ row_grads_kernel(const float *__restrict__ snap, const float *__restrict__ w,
     }
   }
   if (!tail.fused) return;
-  // this warp's rows (var / m / v, bitmap bits) are written: signal the tail CTA and retire
-  __syncwarp();
-  if (lane == 0) {
-    __threadfence();
-    atomicAdd(tail.ticket, 1u);
+  // ---- last CTA of the grid: the step tail ----
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    __threadfence();  // cumulative over the CTA's writes ordered by the barrier above
+    const bool last = atomicAdd(tail.ticket, 1u) == gridDim.x - 1;
+    if (last) {
+      __threadfence();
+      *tail.ticket = 0;  // re-armed for the next step
+    }
+    sLast = last;
   }
+  __syncthreads();
+  if (!sLast) return;
+  step_tail_body<kRowWarps * 32>(tail.w, tail.mw, tail.vw, tail.wu, tail.mwu, tail.vwu, gw_part,
+                                 gwu_part, gridDim.x - pos_ctas, tail.hp, tail.st,
+                                 1 | (tail.frozen << 1), sTailG);
 }
 
 int row_grads_max_parts(int B) { return (B + kWgradPerCta - 1) / kWgradPerCta; }
@@ -1488,7 +1470,7 @@ int launch_row_grads(const float *snap, const float *w, const float *wu, int B, 
   if (tabs) tb = *tabs;
   TailArgs tl{};
   if (tail) tl = *tail;
-  launch_k(row_grads_kernel, dim3(pos_ctas + w_ctas + (tl.fused ? 1 : 0)), dim3(kRowWarps * 32), 0, s, pdl,
+  launch_k(row_grads_kernel, dim3(pos_ctas + w_ctas), dim3(kRowWarps * 32), 0, s, pdl,
            snap, w, wu, B, d_yp, d_yn, d_sp, d_sn, d_su, lam, planU, planI, gU, gI, unit_part, pos_ctas,
            gw_part, gwu_part, tb, tl);
   MACR_LAUNCH_CHECK();
