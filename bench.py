@@ -892,7 +892,8 @@ def gowalla_cli_epoch(cx):
             "value_incl_sampler": inter / t_pipe, "unit": "interactions/s",
             "sampler_share_of_epoch": min(1.0, t_sample / t_pipe),
             "note": "epoch wall = max(sampler, train) with the sampler one epoch ahead on a worker thread; "
-                    "the sampler (single thread, sequential MT19937 stream consumed word for word) is the bound"}
+                    "the sampler (single thread: the MT19937 stream is consumed word for word, chunks of triples drawn "
+                    "speculatively and verified afterwards) is still the longer of the two"}
 
 
 def shape_scoring(cx, n_users, n_items, T_q, mask_avg, reps=10):

@@ -8,7 +8,8 @@ import ctypes as C
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libmacr_b200.so")
+# MACR_B200_LIB: developer override (A/B of two builds of the same ABI); never a fallback
+LIB_PATH = os.environ.get("MACR_B200_LIB") or os.path.join(_HERE, "libmacr_b200.so")
 _LIB = None
 
 vp = C.c_void_p
