@@ -566,3 +566,21 @@ extern "C" int macr_sample_lgcn_epoch(uint32_t *py_state, uint32_t *np_state,
   gn.store_state();
   return MACR_OK;
 }
+
+// Developer / test hook (not in the public header): the word stream alone.  Consumes `advance`
+// words from `state`, moves the cursor `back` words back (<= advance) and writes the generator
+// state of that position -- what a draw-by-draw consumer holds after advance - back words, also
+// when blocks beyond the final position were already generated (the state is then rebuilt from
+// the buffered output words).
+extern "C" int macr_sampler_stream_selftest(uint32_t *state /*[625]*/, int64_t advance, int64_t back,
+                                            uint32_t *xor_of_words) {
+  MACR_CHECK_ARG(state && state[624] <= 624 && advance >= 0 && back >= 0 && back <= advance,
+                 "macr_sampler_stream_selftest: bad arguments");
+  WordStream g(state);
+  uint32_t x = 0;
+  for (int64_t k = 0; k < advance; ++k) x ^= g.next();
+  g.cur -= (size_t)back;
+  g.store_state();
+  if (xor_of_words) *xor_of_words = x;
+  return MACR_OK;
+}

@@ -325,3 +325,37 @@ def test_epoch_samplers_equal_per_batch_on_addressa():
         random.seed(7), np.random.seed(7)
         np.testing.assert_array_equal(many(20), want)
         assert _same_states(_states(), end)
+
+
+def test_sampler_word_stream_rewind_rebuilds_the_generator_state():
+    """The epoch samplers read MT19937 output from a buffer they may re-read from an earlier
+    position.  When the final position lies in a block older than the newest generated one, the
+    state handed back to `random` is rebuilt from the buffered OUTPUT words (inverse tempering);
+    at a block boundary the position is reported lazily (index 624 of the finished block), as
+    CPython leaves it.  Checked against `random` itself, word for word."""
+    import ctypes as C
+
+    from macr_b200._lib import lib
+
+    fn = lib().macr_sampler_stream_selftest
+    fn.argtypes = [C.c_void_p, C.c_int64, C.c_int64, C.c_void_p]
+    fn.restype = C.c_int
+    for skip, advance, back in ((0, 10, 3), (5, 700, 200), (5, 1300, 1290), (100, 2000, 0), (100, 2000, 1376),
+                                (7, 617, 0), (7, 617 + 624, 624), (7, 3000, 3000 - 617), (623, 1, 0), (623, 700, 699),
+                                (0, 624 * 3, 624), (0, 0, 0)):
+        random.seed(skip * 7 + advance)
+        for _ in range(skip):
+            random.getrandbits(32)
+        version, internal, gauss = random.getstate()
+        st = np.array(internal, dtype=np.uint32)
+        x = np.zeros(1, np.uint32)
+        assert fn(C.c_void_p(st.ctypes.data), advance, back, C.c_void_p(x.ctypes.data)) == 0
+        want_x = 0
+        start = (version, internal, gauss)
+        for _ in range(advance):
+            want_x ^= random.getrandbits(32)
+        assert int(x[0]) == want_x
+        random.setstate(start)
+        for _ in range(advance - back):
+            random.getrandbits(32)
+        assert tuple(int(v) for v in st) == random.getstate()[1], (skip, advance, back)
