@@ -420,12 +420,26 @@ struct Reader {
   }
 };
 
-struct PyDraw {  // random.choice / _randbelow
+// A bounded draw as one test per stream word: value = op(word, hi32(param)), accepted when
+// value <= lo32(param); a rejected word is simply followed by the next one.
+struct PyDraw {  // random.choice / _randbelow: getrandbits(k) = word >> (32 - k), accepted below n
   static inline uint32_t below(Reader &r, uint32_t n) { return py_randbelow(r, n); }
+  static constexpr uint32_t kMinN = 1;  // every n >= 1 consumes at least one word
+  static inline uint64_t param(uint32_t n) { return ((uint64_t)(32 - bit_length(n)) << 32) | (n - 1); }
+  static inline uint32_t value(uint32_t w, uint32_t hi) { return w >> hi; }
 };
-struct NpDraw {  // np.random.randint(0, n, size=1)[0]
+struct NpDraw {  // np.random.randint(0, n, size=1)[0]: word & mask, accepted up to n - 1
   static inline uint32_t below(Reader &r, uint32_t n) { return np_randint(r, n); }
+  static constexpr uint32_t kMinN = 2;  // n == 1 returns 0 without a draw
+  static inline uint64_t param(uint32_t n) {
+    uint32_t mask = n - 1;
+    mask |= mask >> 1, mask |= mask >> 2, mask |= mask >> 4, mask |= mask >> 8, mask |= mask >> 16;
+    return ((uint64_t)mask << 32) | (n - 1);
+  }
+  static inline uint32_t value(uint32_t w, uint32_t hi) { return w & hi; }
 };
+
+constexpr int kMaxChunk = 256;
 
 // Pass A over triples [i0, i1): positions of the positives, candidate negatives, and the
 // cursor behind every triple (relative to `cur0`).  Reads the stream, lo/len -- nothing else.
@@ -442,6 +456,129 @@ __attribute__((noinline)) void draw_chunk(WordStream &g, int i0, int i1, const i
   }
 }
 
+// The same pass driven by the WORDS instead of the draws.  A rejection loop is a branch the
+// predictor cannot learn (about one miss per triple: most of the old pass).  Here every
+// iteration takes the next word -- the position advances by one, unconditionally -- tests it
+// against the parameters of the current draw (draw 2 j = positive of triple j, draw 2 j + 1 = its
+// candidate negative), stores the value into the draw's slot and moves to the next draw only if
+// the word was accepted; a rejected value is overwritten by the following word.  No data-dependent
+// branch is left; the loop-carried state is the draw index and its parameter word.
+// Needs every list of the chunk to take a draw (len >= D::kMinN), checked by the caller.
+template <class D>
+__attribute__((noinline)) void draw_chunk_words(WordStream &g, int i0, int i1, const int64_t *lo,
+                                                const uint32_t *len, uint32_t n_items,
+                                                int64_t *pos_at, int32_t *neg, uint32_t *cur_after,
+                                                size_t cur0) {
+  // parameters of draw q, packed: low half = shift count / mask, high half = largest accepted value
+  uint64_t par[2 * kMaxChunk + 4];
+  uint32_t val[2 * kMaxChunk + 1], endp[2 * kMaxChunk + 1];
+  const int nt = i1 - i0, qend = 2 * nt;
+  auto pack = [](uint64_t pp) { return (pp << 32) | (pp >> 32); };
+  const uint64_t neg_par = pack(D::param(n_items));
+  for (int j = 0; j < nt; ++j) {
+    par[2 * j] = pack(D::param(len[i0 + j]));
+    par[2 * j + 1] = neg_par;
+  }
+  for (int k = qend; k < qend + 4; ++k) par[k] = neg_par;  // read ahead, never used
+  size_t p = g.cur;
+  long q = 0;
+  // the current draw's parameters and those of the next two live in registers: on an accepted
+  // word they shift down by conditional moves and the slot two ahead is loaded -- its value is
+  // not needed before the accept after next, so no load sits in the loop-carried chain
+  uint64_t c0 = par[0], c1 = par[1], c2 = par[2];
+  while (q < qend) {
+    if (p >= g.end()) {
+      g.cur = p;
+      g.ensure();
+    }
+    const uint32_t *W = g.words();
+    const size_t pend = g.end();
+    while (q < qend && p < pend) {
+      const uint32_t v = D::value(W[p], (uint32_t)c0);
+      ++p;
+      val[q] = v;
+      endp[q] = (uint32_t)(p - cur0);
+#if defined(__x86_64__)
+      // accepted (v <= bound): c0 <- c1, c1 <- c2, ++q -- conditional moves off ONE compare (the
+      // compiler turns plain selects back into a branch, which is what this loop exists to avoid)
+      const uint64_t bound = c0 >> 32;
+      asm("cmp %[v], %[b]\n\t"
+          "cmovae %[c1], %[c0]\n\t"
+          "cmovae %[c2], %[c1]\n\t"
+          "sbb $-1, %[q]"
+          : [c0] "+r"(c0), [c1] "+r"(c1), [q] "+r"(q)
+          : [v] "r"((uint64_t)v), [b] "r"(bound), [c2] "r"(c2)
+          : "cc");
+#else
+      const uint64_t m = 0ull - (uint64_t)(v <= (uint32_t)(c0 >> 32));
+      q -= (long)m;
+      c0 = (c1 & m) | (c0 & ~m);
+      c1 = (c2 & m) | (c1 & ~m);
+#endif
+      c2 = par[q + 2];
+    }
+  }
+  g.cur = p;
+  for (int j = 0; j < nt; ++j) {
+    pos_at[i0 + j] = lo[i0 + j] + (int64_t)val[2 * j];
+    neg[i0 + j] = (int32_t)val[2 * j + 1];
+    cur_after[i0 + j] = endp[2 * j + 1];
+  }
+}
+
+// random.sample(pop, B) / [random.choice(pop) ...] driven by the words: a word is rejected when it
+// is out of range or (sample) already chosen -- both "draw again" in CPython -- so with the
+// out-of-range values marked as taken from the start, one table look-up decides, and again no
+// data-dependent branch is left.  The small-population branch of random.sample (partial shuffle
+// of a pool copy, n <= setsize) keeps the draw-by-draw code: returns false.
+bool pick_users_words(WordStream &g, const int32_t *pop, int n, int B, int n_users_flag,
+                      int32_t *out, PickScratch *scratch) {
+  const bool sample = B <= n_users_flag;
+  if (sample) {
+    long long setsize = 21;
+    if (B > 5) setsize += (long long)llround(pow(4.0, ceil(log((double)B * 3.0) / log(4.0))));
+    if (n <= setsize) return false;
+  }
+  const int k = bit_length((uint32_t)n), shift = 32 - k;
+  std::vector<uint8_t> &taken = scratch->chosen;
+  taken.assign((size_t)1 << k, 0);
+  std::fill(taken.begin() + n, taken.end(), (uint8_t)1);
+  std::vector<int32_t> &idx = scratch->pool;
+  idx.resize((size_t)B + 1);
+  uint8_t *tk = taken.data();
+  int32_t *ix = idx.data();
+  size_t p = g.cur;
+  int q = 0;
+  while (q < B) {
+    if (p >= g.end()) {
+      g.cur = p;
+      g.ensure();
+    }
+    const uint32_t *W = g.words();
+    const size_t pend = g.end();
+    if (sample) {
+      while (q < B && p < pend) {
+        const uint32_t v = W[p] >> shift;
+        ++p;
+        const uint8_t t = tk[v];
+        ix[q] = (int32_t)v;
+        tk[v] = 1;  // taken from now on (it already was if t != 0)
+        q += t == 0;
+      }
+    } else {  // with replacement: only the range test rejects
+      while (q < B && p < pend) {
+        const uint32_t v = W[p] >> shift;
+        ++p;
+        ix[q] = (int32_t)v;
+        q += v < (uint32_t)n;
+      }
+    }
+  }
+  g.cur = p;
+  for (int i = 0; i < B; ++i) out[i] = pop[ix[i]];
+  return true;
+}
+
 // The chunk loop shared by both samplers.  `g` is the stream the item draws come from.
 template <class D>
 void sample_items(WordStream &g, const PairSet &set, int chunk, int B, const int32_t *users,
@@ -453,7 +590,10 @@ void sample_items(WordStream &g, const PairSet &set, int chunk, int B, const int
     int i0 = c0;  // first triple not yet final
     while (i0 < c1) {
       // speculative draws: every candidate assumed "not in the list"
-      draw_chunk<D>(g, i0, c1, lo, len, n_items, pos_at, neg, cur_after, cur0);
+      bool all_draw = n_items >= D::kMinN && c1 - i0 <= kMaxChunk;
+      for (int i = i0; i < c1; ++i) all_draw = all_draw && len[i] >= D::kMinN;
+      if (all_draw) draw_chunk_words<D>(g, i0, c1, lo, len, n_items, pos_at, neg, cur_after, cur0);
+      else draw_chunk<D>(g, i0, c1, lo, len, n_items, pos_at, neg, cur_after, cur0);
       int hit = -1;
       for (int i = i0; i < c1; ++i) {  // verification: independent accesses, misses overlap
         pos[i] = pos_at[i] >= 0 ? order[pos_at[i]] : 0;
@@ -509,7 +649,7 @@ extern "C" int macr_sample_mf_epoch(uint32_t *py_state, const int32_t *users_pop
   for (int b = 0; b < n_batches; ++b) {
     int32_t *users = out + (size_t)b * 3 * B, *pos = users + B, *neg = pos + B;
     g.release_before(g.cur);
-    {
+    if (!pick_users_words(g, users_pop, n_pop, B, n_users, users, &s.pick)) {
       Reader r(g);
       py_pick_users(r, users_pop, n_pop, B, n_users, users, &s.pick);
     }
@@ -549,7 +689,7 @@ extern "C" int macr_sample_lgcn_epoch(uint32_t *py_state, uint32_t *np_state,
     int32_t *users = out + (size_t)b * 3 * B, *pos = users + B, *neg = pos + B;
     gp.release_before(gp.cur);
     gn.release_before(gn.cur);
-    {
+    if (!pick_users_words(gp, users_pop, n_pop, B, n_users, users, &s.pick)) {
       Reader r(gp);
       py_pick_users(r, users_pop, n_pop, B, n_users, users, &s.pick);
     }

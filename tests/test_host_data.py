@@ -359,3 +359,37 @@ def test_sampler_word_stream_rewind_rebuilds_the_generator_state():
         for _ in range(advance - back):
             random.getrandbits(32)
         assert tuple(int(v) for v in st) == random.getstate()[1], (skip, advance, back)
+
+
+def test_epoch_samplers_small_ranges_and_single_item_lists():
+    """Word-driven draw loops vs the draw-by-draw twins where a draw may consume NO word (numpy's
+    randint over one value; an MF user without train items) or a power-of-two range never rejects:
+    catalogues of 1, 2, 3, 64, 65 items, lists of one item."""
+    from macr_b200.host import native_sampler as ns
+
+    n_users = 40
+    pop = np.arange(n_users, dtype=np.int32)
+    for n_items in (1, 2, 3, 64, 65):
+        rng = np.random.RandomState(n_items)
+        pos_lists = {u: rng.randint(0, n_items, rng.randint(1, 4)).tolist() for u in range(n_users)}
+        pos_lists[3] = [0]
+        ban_lists = {u: ([] if n_items < 3 else sorted(set(rng.randint(0, n_items, 2).tolist()) - {n_items - 1}))
+                     for u in range(n_users)}
+        pos, ban = ns.ListCSR(pos_lists, n_users), ns.ListCSR(ban_lists, n_users)
+        mf_lists = dict(ban_lists)
+        mf_lists[7] = []
+        mf = ns.ListCSR(mf_lists, n_users)
+        for B in (8, 40, 100):
+            random.seed(n_items * 31 + B), np.random.seed(n_items * 31 + B)
+            start = _states()
+            want = np.array([ns.sample_lgcn(pop, n_users, n_items, pos, ban, B) for _ in range(6)])
+            end = _states()
+            random.setstate(start[0]), np.random.set_state(start[1])
+            np.testing.assert_array_equal(ns.sample_lgcn_epoch(pop, n_users, n_items, pos, ban, B, 6), want)
+            assert _same_states(_states(), end)
+            random.setstate(start[0])
+            want = np.array([ns.sample_mf(pop, n_users, n_items, mf, B) for _ in range(6)])
+            end = random.getstate()
+            random.setstate(start[0])
+            np.testing.assert_array_equal(ns.sample_mf_epoch(pop, n_users, n_items, mf, B, 6), want)
+            assert random.getstate() == end
