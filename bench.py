@@ -896,8 +896,8 @@ def gowalla_cli_epoch(cx):
             "value_incl_sampler": inter / t_pipe, "unit": "interactions/s",
             "sampler_share_of_epoch": min(1.0, t_sample / t_pipe),
             "note": "epoch wall = max(sampler, train) with the sampler one epoch ahead on a worker thread; "
-                    "the sampler (single thread: the MT19937 stream is consumed word for word, chunks of triples drawn "
-                    "speculatively and verified afterwards) is still the longer of the two"}
+                    "the sampler (the MT19937 stream is consumed word for word by one thread, chunks of triples drawn "
+                    "speculatively and verified behind it by a second one) is still the longer of the two"}
 
 
 def gowalla_lightgcn(cx):

@@ -19,8 +19,11 @@
 //                          32-bit draws `genrand & mask` until <= rng   (masked rejection)
 #include <emmintrin.h>
 #include <math.h>
+#include <stdlib.h>
 
 #include <algorithm>
+#include <atomic>
+#include <thread>
 #include <vector>
 
 #include "common.cuh"
@@ -620,6 +623,153 @@ void sample_items(WordStream &g, const PairSet &set, int chunk, int B, const int
   }
 }
 
+// ---- the verification pass on a second thread ------------------------------------------------
+// The draws are one dependent chain, but the verification (two cache misses per triple) is not
+// part of it: with sparse lists a second thread reads the positives and tests the candidates
+// BEHIND the drawing thread, which keeps drawing speculatively.  A candidate found in its list
+// is reported back; the drawing thread then returns to that triple, finishes its rejection loop
+// and redraws what it had drawn beyond it (with one rejected candidate per ~1400 triples on
+// gowalla that is a chunk or two).  Hand-over is by three atomics; the arrays of a batch are
+// written by one side and read by the other strictly in that order.
+inline void spin_wait(int &spins) {
+  if (++spins < 4096) _mm_pause();
+  else std::this_thread::yield();  // oversubscribed machine: let the other side run
+}
+
+struct Verifier {
+  // the batch in flight (written by the drawing thread before `batch` is bumped)
+  const PairSet *set = nullptr;
+  const int32_t *users = nullptr, *order = nullptr, *neg = nullptr;
+  const int64_t *pos_at = nullptr;
+  int32_t *pos = nullptr;
+  int B = 0;
+  std::atomic<int> batch{0};     // bumped when a batch's arrays are ready (drawn == 0)
+  std::atomic<int> drawn{0};     // triples of the batch drawn so far
+  std::atomic<int> hit{-1};      // first triple whose candidate IS in its list; -1: none pending
+  std::atomic<int> verified{0};  // == B once the whole batch is verified
+  std::atomic<bool> quit{false};
+  std::thread th;
+
+  ~Verifier() { stop(); }  // also on the error returns of the entry points
+  bool start() {  // false: no thread to be had -- the caller stays single-threaded
+    try {
+      th = std::thread([this] { run(); });
+    } catch (...) {
+      return false;
+    }
+    return true;
+  }
+  void stop() {
+    quit.store(true, std::memory_order_release);
+    if (th.joinable()) th.join();
+  }
+  void run() {
+    int seen = 0;
+    for (;;) {
+      int spins = 0;
+      while (batch.load(std::memory_order_acquire) == seen) {
+        if (quit.load(std::memory_order_acquire)) return;
+        spin_wait(spins);
+      }
+      seen = batch.load(std::memory_order_acquire);
+      const int n = B;
+      int v = 0;
+      spins = 0;
+      while (v < n) {
+        const int d = drawn.load(std::memory_order_acquire);
+        if (d <= v) {
+          spin_wait(spins);
+          continue;
+        }
+        spins = 0;
+        int h = -1;
+        for (int i = v; i < d; ++i) {
+          pos[i] = pos_at[i] >= 0 ? order[pos_at[i]] : 0;
+          if (set->maybe(pair_hash((uint32_t)users[i], (uint32_t)neg[i])) &&
+              set->exact((uint32_t)users[i], neg[i])) {
+            h = i;
+            break;
+          }
+        }
+        if (h < 0) {
+          v = d;
+          continue;
+        }
+        hit.store(h, std::memory_order_release);  // everything drawn after h is void
+        while (hit.load(std::memory_order_acquire) >= 0) spin_wait(spins);
+        v = h + 1;  // the drawing thread has settled triple h and reset `drawn` to h + 1
+      }
+      verified.store(n, std::memory_order_release);
+    }
+  }
+};
+
+// sample_items with the verification on `vf`'s thread
+template <class D>
+void sample_items_mt(Verifier &vf, WordStream &g, const PairSet &set, int chunk, int B,
+                     const int32_t *users, const int64_t *lo, const uint32_t *len,
+                     const int32_t *order, uint32_t n_items, int32_t *pos, int32_t *neg,
+                     int64_t *pos_at, uint32_t *cur_after) {
+  vf.set = &set, vf.users = users, vf.order = order, vf.neg = neg, vf.pos_at = pos_at, vf.pos = pos, vf.B = B;
+  vf.drawn.store(0, std::memory_order_relaxed);
+  vf.verified.store(0, std::memory_order_relaxed);
+  vf.hit.store(-1, std::memory_order_relaxed);
+  vf.batch.fetch_add(1, std::memory_order_release);
+  const size_t cur0 = g.cur;
+  // triple h's candidate is in its list: finish its rejection loop the literal way; -> next triple
+  auto settle = [&](int h) {
+    g.cur = cur0 + cur_after[h];
+    {
+      Reader r(g);
+      for (;;) {
+        const int32_t c = (int32_t)D::below(r, n_items);
+        if (!set.contains((uint32_t)users[h], c)) {
+          neg[h] = c;
+          break;
+        }
+      }
+    }
+    cur_after[h] = (uint32_t)(g.cur - cur0);
+    vf.drawn.store(h + 1, std::memory_order_release);  // before the verifier is let go
+    vf.hit.store(-1, std::memory_order_release);
+    return h + 1;
+  };
+  int i = 0;
+  for (;;) {
+    while (i < B) {
+      const int c1 = i + chunk < B ? i + chunk : B;
+      bool all_draw = n_items >= D::kMinN && c1 - i <= kMaxChunk;
+      for (int k = i; k < c1; ++k) all_draw = all_draw && len[k] >= D::kMinN;
+      if (all_draw) draw_chunk_words<D>(g, i, c1, lo, len, n_items, pos_at, neg, cur_after, cur0);
+      else draw_chunk<D>(g, i, c1, lo, len, n_items, pos_at, neg, cur_after, cur0);
+      vf.drawn.store(c1, std::memory_order_release);
+      i = c1;
+      const int h = vf.hit.load(std::memory_order_acquire);
+      if (h >= 0) i = settle(h);
+    }
+    int spins = 0;
+    for (;;) {  // everything is drawn: wait for the verifier's verdict on the rest
+      const int h = vf.hit.load(std::memory_order_acquire);
+      if (h >= 0) {
+        i = settle(h);
+        break;
+      }
+      if (vf.verified.load(std::memory_order_acquire) == B) return;
+      spin_wait(spins);
+    }
+  }
+}
+
+// 0: single thread; 1: verification on a second thread.  Sparse lists only (a rejected candidate
+// voids what was drawn behind it: with dense lists the second thread would mostly wait);
+// MACR_SAMPLER_THREADS=1 / =2 forces the choice.
+inline bool use_verifier_thread(int chunk, long long triples) {
+  const char *e = getenv("MACR_SAMPLER_THREADS");
+  if (e && e[0] == '1') return false;
+  if (e && e[0] == '2') return true;
+  return chunk >= 64 && triples >= 16384 && std::thread::hardware_concurrency() >= 2;
+}
+
 struct EpochScratch {
   std::vector<int64_t> lo, pos_at;
   std::vector<uint32_t> len, cur_after;
@@ -646,6 +796,8 @@ extern "C" int macr_sample_mf_epoch(uint32_t *py_state, const int32_t *users_pop
   const PairSet set{tags, 64 - log2_buckets, rowptr, sorted};
   const int chunk = chunk_for((double)rowptr[n_users], n_users, n_items);
   EpochScratch s(B);
+  Verifier vf;
+  const bool mt = n_batches > 0 && use_verifier_thread(chunk, (long long)B * n_batches) && vf.start();
   for (int b = 0; b < n_batches; ++b) {
     int32_t *users = out + (size_t)b * 3 * B, *pos = users + B, *neg = pos + B;
     g.release_before(g.cur);
@@ -658,9 +810,14 @@ extern "C" int macr_sample_mf_epoch(uint32_t *py_state, const int32_t *users_pop
       s.lo[i] = l;
       s.len[i] = (uint32_t)(rowptr[users[i] + 1] - l);
     }
-    sample_items<PyDraw>(g, set, chunk, B, users, s.lo.data(), s.len.data(), order,
-                         (uint32_t)n_items, pos, neg, s.pos_at.data(), s.cur_after.data());
+    if (mt)
+      sample_items_mt<PyDraw>(vf, g, set, chunk, B, users, s.lo.data(), s.len.data(), order,
+                              (uint32_t)n_items, pos, neg, s.pos_at.data(), s.cur_after.data());
+    else
+      sample_items<PyDraw>(g, set, chunk, B, users, s.lo.data(), s.len.data(), order,
+                           (uint32_t)n_items, pos, neg, s.pos_at.data(), s.cur_after.data());
   }
+  if (mt) vf.stop();
   g.store_state();
   return MACR_OK;
 }
@@ -685,6 +842,8 @@ extern "C" int macr_sample_lgcn_epoch(uint32_t *py_state, uint32_t *np_state,
   const PairSet set{ban_tags, 64 - log2_buckets, ban_rowptr, ban_sorted};
   const int chunk = chunk_for((double)ban_rowptr[n_users], n_users, n_items);
   EpochScratch s(B);
+  Verifier vf;
+  const bool mt = n_batches > 0 && use_verifier_thread(chunk, (long long)B * n_batches) && vf.start();
   for (int b = 0; b < n_batches; ++b) {
     int32_t *users = out + (size_t)b * 3 * B, *pos = users + B, *neg = pos + B;
     gp.release_before(gp.cur);
@@ -699,9 +858,14 @@ extern "C" int macr_sample_lgcn_epoch(uint32_t *py_state, uint32_t *np_state,
       s.len[i] = (uint32_t)(pos_rowptr[users[i] + 1] - l);
       MACR_CHECK_ARG(s.len[i] > 0, "macr_sample_lgcn_epoch: user %d has no positive item", (int)users[i]);
     }
-    sample_items<NpDraw>(gn, set, chunk, B, users, s.lo.data(), s.len.data(), pos_order,
-                         (uint32_t)n_items, pos, neg, s.pos_at.data(), s.cur_after.data());
+    if (mt)
+      sample_items_mt<NpDraw>(vf, gn, set, chunk, B, users, s.lo.data(), s.len.data(), pos_order,
+                              (uint32_t)n_items, pos, neg, s.pos_at.data(), s.cur_after.data());
+    else
+      sample_items<NpDraw>(gn, set, chunk, B, users, s.lo.data(), s.len.data(), pos_order,
+                           (uint32_t)n_items, pos, neg, s.pos_at.data(), s.cur_after.data());
   }
+  if (mt) vf.stop();
   gp.store_state();
   gn.store_state();
   return MACR_OK;

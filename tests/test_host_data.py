@@ -393,3 +393,35 @@ def test_epoch_samplers_small_ranges_and_single_item_lists():
             random.setstate(start[0])
             np.testing.assert_array_equal(ns.sample_mf_epoch(pop, n_users, n_items, mf, B, 6), want)
             assert random.getstate() == end
+
+
+@pytest.mark.parametrize("dense", [True, False])
+def test_epoch_sampler_verifier_thread_equals_single_thread(dense, monkeypatch):
+    """MACR_SAMPLER_THREADS=2 puts the verification pass on a second thread that runs behind the
+    speculative draws and reports rejected candidates back (the drawing thread then rewinds).  Same
+    triples and generator states as the single-threaded epoch form and as the per-batch twins --
+    with dense lists (a rewind every other triple) and sparse ones (long speculative runs)."""
+    from macr_b200.host import native_sampler as ns
+
+    rng = np.random.RandomState(5)
+    n_users, n_items = (300, 90) if dense else (1500, 30000)
+    lists = {u: rng.choice(n_items, size=rng.randint(2, 40), replace=False).tolist() for u in range(n_users)}
+    csr = ns.ListCSR(lists, n_users)
+    pop = np.arange(n_users, dtype=np.int32)
+    B, n_b = 256, 24
+    results = []
+    for mode in ("1", "2", "2"):
+        monkeypatch.setenv("MACR_SAMPLER_THREADS", mode)
+        random.seed(99), np.random.seed(99)
+        a = ns.sample_mf_epoch(pop, n_users, n_items, csr, B, n_b)
+        b = ns.sample_lgcn_epoch(pop, n_users, n_items, csr, csr, B, n_b)
+        results.append((a, b, _states()))
+    monkeypatch.delenv("MACR_SAMPLER_THREADS")
+    random.seed(99), np.random.seed(99)
+    want_a = np.array([ns.sample_mf(pop, n_users, n_items, csr, B) for _ in range(n_b)])
+    want_b = np.array([ns.sample_lgcn(pop, n_users, n_items, csr, csr, B) for _ in range(n_b)])
+    want_state = _states()
+    for a, b, st in results:
+        np.testing.assert_array_equal(a, want_a)
+        np.testing.assert_array_equal(b, want_b)
+        assert _same_states(st, want_state)
