@@ -495,8 +495,12 @@ __attribute__((noinline)) void draw_chunk_words(WordStream &g, int i0, int i1, c
       g.ensure();
     }
     const uint32_t *W = g.words();
-    const size_t pend = g.end();
-    while (q < qend && p < pend) {
+    // qend - q more draws need at least that many words and cannot accept more than they get:
+    // a pass of exactly that many words (or what the block still holds) has ONE loop condition
+    // and can never run past the last draw; ~2/3 of a pass is accepted, so passes shrink fast
+    const size_t left = g.end() - p, want = (size_t)(qend - q);
+    const size_t pstop = p + (left < want ? left : want);
+    while (p < pstop) {
       const uint32_t v = D::value(W[p], (uint32_t)c0);
       ++p;
       val[q] = v;
