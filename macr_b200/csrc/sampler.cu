@@ -226,17 +226,20 @@ extern "C" int macr_sample_lgcn(uint32_t *py_state /*[625]*/, uint32_t *np_state
 
 // =============================================================================================
 // Epoch samplers.  Same streams, same triples, but the sequential part no longer waits for
-// memory: the per-batch functions above spend most of their ~50-80 ns per triple on the lists
-// (two dependent cache misses and a scan per triple) although only ~0.1-1 % of the negative
-// draws are ever rejected by them.  Here a chunk of triples is drawn SPECULATIVELY -- every
-// candidate negative assumed "not a train item" -- touching nothing but the word stream and the
-// list lengths, and issuing prefetches for the two lines it will need; a second pass over the
-// chunk then reads the positives and tests the candidates against a hashed pair set (one
-// prefetched probe) with many independent accesses in flight.  A candidate that IS in the user's
-// list invalidates what was drawn after it: the word cursor goes back to just behind that
-// draw, the rejection loop is finished the literal way, and the chunk is redrawn from the next
-// triple.  The words themselves come from block-wise (vectorisable) MT19937 generation into a
-// buffer that can be re-read from the chunk's start.
+// memory nor for a branch predictor:
+//  * the per-batch functions above spend most of their ~50-80 ns per triple on the lists (two
+//    dependent cache misses and a scan per triple) although only ~0.1-1 % of the negative draws
+//    are ever rejected by them.  Here a chunk of triples is drawn SPECULATIVELY -- every candidate
+//    negative assumed "not a train item" -- touching nothing but the word stream and the list
+//    lengths; a verification pass then reads the positives and tests the candidates against a
+//    hashed pair set with many independent accesses in flight (on a second thread when the lists
+//    are sparse).  A candidate that IS in the user's list invalidates what was drawn after it: the
+//    word cursor goes back to just behind that draw, the rejection loop is finished the literal
+//    way, and the chunk is redrawn from the next triple;
+//  * the draws themselves are driven by the stream WORDS (draw_chunk_words, pick_users_words): one
+//    word per iteration, accepted or not, with conditional moves instead of rejection loops;
+//  * the words come from block-wise (vectorisable) MT19937 generation into a buffer that can be
+//    re-read from the chunk's start.
 // =============================================================================================
 namespace macr {
 namespace {
