@@ -60,29 +60,52 @@ def mf_metrics_from_hits(hits, n_pos, Ks, n_ranked=None):
     return out
 
 
-def _hits(topk_ids, truth_lists):
-    ids = np.asarray(topk_ids)
-    out = np.zeros(ids.shape, np.float64)
-    for t, pos in enumerate(truth_lists):
-        out[t] = np.isin(ids[t], pos)
-    return out
+def _truth_keys(truth_lists):
+    """ragged truth lists -> (lens int64 [T], flat item ids int64) for `_hits`"""
+    lens = np.fromiter((len(t) for t in truth_lists), np.int64, len(truth_lists))
+    flat = np.fromiter((i for t in truth_lists for i in t), np.int64, int(lens.sum()))
+    return lens, flat
+
+
+def _hits(topk_ids, truth_lists, keys=None):
+    """r[t, k] = 1.0 if the k-th ranked item of user t is in the user's test list (train.py:94-99,
+    `if i in user_pos_test`), for all users at once: one sorted membership test over (row, item)
+    keys instead of one `np.isin` per user (0.09 s per evaluation on addressa, 1.2 s on gowalla)."""
+    ids = np.asarray(topk_ids).astype(np.int64)
+    T = ids.shape[0]
+    lens, flat = _truth_keys(truth_lists) if keys is None else keys
+    stride = max(int(ids.max(initial=0)), int(flat.max(initial=0))) + 2  # ids of -1 (padding) hit nothing
+    rows = np.arange(T, dtype=np.int64)
+    return np.isin(rows[:, None] * stride + ids, np.repeat(rows, lens) * stride + flat).astype(np.float64)
 
 
 class MFEvaluator:
     def __init__(self, data, Ks, batch_size, eval_mode="fused"):
         self.data, self.Ks, self.batch_size, self.eval_mode = data, list(Ks), batch_size, eval_mode
+        self._per_batch = {}  # (valid_set, users of the batch) -> train CSR, truth lists as arrays
+
+    def _batch_lists(self, user_batch, valid_set):
+        """train-item mask CSR and test lists of one user batch; every evaluation of a run walks the
+        same batches (train.py:174-180), so the ragged Python lists are flattened once"""
+        key = (valid_set, tuple(user_batch))
+        got = self._per_batch.get(key)
+        if got is None:
+            truth_of = self.data.test_user_list if valid_set == "test" else self.data.valid_user_list
+            truth = [truth_of[u] for u in user_batch]
+            got = self._per_batch[key] = (self.data.train_csr(user_batch), truth, _truth_keys(truth),
+                                          np.array([len(t) for t in truth], np.float64))
+        return got
 
     def test(self, sess, model, test_users, batch_test_flag=False, model_type="o", valid_set="test"):
         if model_type not in _FETCH_OF:
             raise NotImplementedError(f"model_type {model_type!r} is outside the MACR hot path")
         Kmax = max(self.Ks)
-        truth_of = self.data.test_user_list if valid_set == "test" else self.data.valid_user_list
         sums = {k: np.zeros(len(self.Ks)) for k in ("precision", "recall", "ndcg", "hit_ratio")}
         n_test_users, count = len(test_users), 0
         head = _HEAD_OF[_FETCH_OF[model_type]]
         prep = {}  # item gates + tensor-core item operands: prepared by the first batch, shared by the rest
         for user_batch in _batches(test_users, self.batch_size):
-            mrp, mcol = self.data.train_csr(user_batch)  # all_items - train_items, train.py:132-133
+            (mrp, mcol), truth, keys, n_pos = self._batch_lists(user_batch, valid_set)  # all_items - train_items, train.py:132-133
             if self.eval_mode == "fused":
                 ids, _ = model.topk(user_batch, Kmax, mrp, mcol, head=head, prep=prep)
                 ids = ids.cpu().numpy()
@@ -90,8 +113,7 @@ class MFEvaluator:
                 rate = sess.run(getattr(model, _FETCH_OF[model_type]),
                                 {model.users: user_batch, model.pos_items: range(self.data.n_items)})
                 ids = host_topk(rate, mrp, mcol, Kmax)
-            truth = [truth_of[u] for u in user_batch]
-            part = mf_metrics_from_hits(_hits(ids, truth), [len(t) for t in truth], self.Ks,
+            part = mf_metrics_from_hits(_hits(ids, truth, keys), n_pos, self.Ks,
                                         n_ranked=(np.asarray(ids) >= 0).sum(1))
             for k in sums:
                 sums[k] += part[k]

@@ -162,3 +162,54 @@ def test_drivers_reject_modes_outside_the_hot_path():
         train_mf.main(["--dataset", "tiny", "--train", "rubi"])  # BPR two-branch variant: not implemented
     with pytest.raises(SystemExit):
         lightgcn.main(["--dataset", "tiny", "--loss", "bpr"])
+
+
+def test_mf_evaluator_walks_user_batches_like_the_reference_and_reuses_its_lists():
+    """MFEvaluator.test (train.py:162-311) with a stand-in model whose `topk` ranks a fixed score
+    matrix on the host: the batch walk, the train-item mask, the vectorised hit test and the metric
+    sums equal the oracle's restatement evaluated over all users at once -- on the first call and
+    on the second (per-batch lists cached), for the test and the valid split, padding ids included."""
+    import torch
+
+    rng = np.random.RandomState(3)
+    n_users, n_items, Ks = 75, 40, [5, 20]
+    lists = lambda lo, hi: {u: rng.choice(n_items, size=rng.randint(lo, hi), replace=False).tolist()
+                            for u in range(n_users)}
+    data = types.SimpleNamespace(n_items=n_items, train_user_list=lists(1, 30), test_user_list=lists(1, 8),
+                                 valid_user_list=lists(1, 5))
+    data.train_user_list[4] = list(range(n_items - 7))  # fewer than K unmasked items: ids padded with -1
+    calls = []
+
+    def train_csr(users):
+        calls.append(len(users))
+        rows = [np.unique(np.asarray(data.train_user_list[u], np.int32)) for u in users]
+        rp = np.zeros(len(users) + 1, np.int32)
+        rp[1:] = np.cumsum([len(r) for r in rows])
+        return rp, np.concatenate(rows).astype(np.int32)
+
+    data.train_csr = train_csr
+    rating = rng.rand(n_users, n_items).astype(np.float32)
+
+    class Model:
+        def topk(self, users, K, mrp, mcol, head="both", prep=None):
+            assert head == "both" and isinstance(prep, dict)
+            ids = evaluate.host_topk(rating[np.asarray(users)], mrp, mcol, K)
+            return torch.from_numpy(ids), None
+
+    users = list(range(n_users))
+    ev = evaluate.MFEvaluator(data, Ks, 32, "fused")
+    for valid_set, truth_of in (("test", data.test_user_list), ("valid", data.valid_user_list), ("test", data.test_user_list)):
+        got = ev.test(None, Model(), users, model_type="rubi_both", valid_set=valid_set)
+        mrp, mcol = train_csr(users)
+        ids = evaluate.host_topk(rating, mrp, mcol, max(Ks))
+        assert (ids[4] == -1).sum() == max(Ks) - 7
+        truth = [truth_of[u] for u in users]
+        want = evaluate.mf_metrics_from_hits(evaluate._hits(ids, truth), [len(t) for t in truth], Ks,
+                                             n_ranked=(ids >= 0).sum(1))
+        ref = mf_metrics.evaluate(ids, truth, Ks)
+        for k in want:
+            np.testing.assert_allclose(got[k], want[k] / n_users, rtol=1e-12, err_msg=k)
+            if k != "precision":  # the oracle's precision divides by K (no padded rows in its contract)
+                np.testing.assert_allclose(got[k], ref[k], rtol=1e-12, err_msg=k)
+    # three batches per walk, flattened once per split: train_csr ran for 2 splits x 3 batches + 3 checks
+    assert calls.count(32) == 4 and calls.count(11) == 2
