@@ -1,12 +1,9 @@
 """Quick probe: gowalla-shape MF step (ring of 3 models / back to back), no other bench blocks.
-  MACR_GRAPH_UNROLL=8 python dev/gow_step.py"""
+  MACR_GRAPH_UNROLL=8 python dev/gow_step.py      (MACR_B200_LIB=/path/to/other/libmacr_b200.so for an A/B)"""
 import os, sys, time
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import numpy as np
 import bench
-from macr_b200 import _lib
-if os.environ.get("MACR_LIB"):
-    _lib.LIB_PATH = os.environ["MACR_LIB"]  # A/B against an older build
 cx = bench.Ctx()
 torch = cx.torch
 from macr_b200 import ops
