@@ -477,7 +477,7 @@ __attribute__((noinline)) void draw_chunk_words(WordStream &g, int i0, int i1, c
                                                 size_t cur0) {
   // parameters of draw q, packed: low half = shift count / mask, high half = largest accepted value
   uint64_t par[2 * kMaxChunk + 4];
-  uint32_t val[2 * kMaxChunk + 1], endp[2 * kMaxChunk + 1];
+  uint64_t rec[2 * kMaxChunk + 1];  // per draw: value | cursor behind the word << 32 (one store per word)
   const int nt = i1 - i0, qend = 2 * nt;
   auto pack = [](uint64_t pp) { return (pp << 32) | (pp >> 32); };
   const uint64_t neg_par = pack(D::param(n_items));
@@ -506,8 +506,7 @@ __attribute__((noinline)) void draw_chunk_words(WordStream &g, int i0, int i1, c
     while (p < pstop) {
       const uint32_t v = D::value(W[p], (uint32_t)c0);
       ++p;
-      val[q] = v;
-      endp[q] = (uint32_t)(p - cur0);
+      rec[q] = (uint64_t)v | ((uint64_t)(p - cur0) << 32);
 #if defined(__x86_64__)
       // accepted (v <= bound): c0 <- c1, c1 <- c2, ++q -- conditional moves off ONE compare (the
       // compiler turns plain selects back into a branch, which is what this loop exists to avoid)
@@ -530,9 +529,9 @@ __attribute__((noinline)) void draw_chunk_words(WordStream &g, int i0, int i1, c
   }
   g.cur = p;
   for (int j = 0; j < nt; ++j) {
-    pos_at[i0 + j] = lo[i0 + j] + (int64_t)val[2 * j];
-    neg[i0 + j] = (int32_t)val[2 * j + 1];
-    cur_after[i0 + j] = endp[2 * j + 1];
+    pos_at[i0 + j] = lo[i0 + j] + (int64_t)(uint32_t)rec[2 * j];
+    neg[i0 + j] = (int32_t)(uint32_t)rec[2 * j + 1];
+    cur_after[i0 + j] = (uint32_t)(rec[2 * j + 1] >> 32);
   }
 }
 
